@@ -1,0 +1,274 @@
+// neurosis_b200 — shared device/host helpers for the sm_100a kernels.
+//
+// Everything tensor-core related here is raw PTX (tcgen05 / TMEM / TMA / mbarrier);
+// there is no CUTLASS dependency.  The bit layouts of the shared-memory matrix
+// descriptor and of the tcgen05 instruction descriptor follow the PTX ISA
+// "tcgen05 matrix descriptor" / "instruction descriptor" tables.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/nk_b200.h"
+
+namespace nk {
+
+typedef __nv_bfloat16 bf16;
+
+// ----------------------------------------------------------------------------------------------
+// error codes returned by every C-ABI entry point (0 = ok, negative = failure)
+// ----------------------------------------------------------------------------------------------
+// (NK_OK / NK_ERR_* are defined by the public header)
+
+void set_last_error(const char* fmt, ...);
+const char* last_error();
+int check_cuda(cudaError_t e, const char* what);
+
+#define NK_CUDA(call)                                      \
+    do {                                                   \
+        int _e = ::nk::check_cuda((call), #call);          \
+        if (_e) return _e;                                 \
+    } while (0)
+
+#define NK_REQUIRE(cond, code, ...)                        \
+    do {                                                   \
+        if (!(cond)) {                                     \
+            ::nk::set_last_error(__VA_ARGS__);             \
+            return (code);                                 \
+        }                                                  \
+    } while (0)
+
+int device_sm_count();
+
+#if defined(__CUDACC__)
+
+// ----------------------------------------------------------------------------------------------
+// small device utilities
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(v);
+}
+
+// device-side watchdog: a pipeline bug must not hang the GPU box.  Waits give up after
+// ~2 s of wall clock and trap (the host sees cudaErrorLaunchFailure).
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ----------------------------------------------------------------------------------------------
+// mbarrier
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+static __device__ __noinline__ void mbar_timeout_trap(uint32_t tag) {
+    printf("[nk] mbarrier wait timed out: block (%d,%d,%d) thread %d tag %u\n", blockIdx.x,
+           blockIdx.y, blockIdx.z, threadIdx.x, tag);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3ffu) == 0) {
+            if (globaltimer_ns() - t0 > 2000000000ull) mbar_timeout_trap(tag);
+        }
+    }
+}
+
+// generic-proxy writes (st.shared) -> visible to the async proxy (UMMA / TMA reads of smem)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor), tiled mode, 128B swizzle
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar, void* dst,
+                                            int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :
+        : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0),
+          "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// make an mbarrier track completion of all tcgen05.mma issued so far by this thread
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::
+                     "r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread t of the warp gets lane (quadrant base + t)
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// Shared-memory matrix descriptor for 128B-swizzled operand tiles whose rows are 128 bytes
+// (64 bf16) wide and densely packed (row r at byte r*128, tile base 1024B-aligned) — exactly
+// what a TMA box {64, rows} with CU_TENSOR_MAP_SWIZZLE_128B produces.
+//   bits [0,14)  start address >> 4          bits [16,30) leading-dim byte offset >> 4
+//   bits [32,46) stride-dim byte offset >> 4 bits [46,48) version = 1 (sm_100)
+//   bits [61,64) layout type: 2 = SWIZZLE_128B
+// K-major operand  (row = M/N index, 128B = 64 K elements):  SBO = 1024 (8-row group), LBO unused.
+// MN-major operand (row = K index,   128B = 64 M/N elements): SBO = 1024 (8 K-rows),
+//                                                             LBO = bytes between 64-wide MN atoms.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3fffu);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// tcgen05 instruction descriptor, kind::f16, A/B = bf16, D = fp32, dense, no negate.
+//   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
+//   [15] A major (0 = K, 1 = MN)  [16] B major  [17,23) N >> 3  [24,29) M >> 4
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn_major,
+                                                             int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+           (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+           (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+#endif  // __CUDACC__
+
+// ----------------------------------------------------------------------------------------------
+// host: tensor-map encoding through the driver entry point (no link-time libcuda dependency)
+// ----------------------------------------------------------------------------------------------
+// dims/strides innermost-first, strides in BYTES for dims 1..rank-1 (dim 0 is contiguous).
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box);
+
+}  // namespace nk

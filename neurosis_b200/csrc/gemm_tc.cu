@@ -1,0 +1,586 @@
+// Persistent, warp-specialised bf16 GEMM on the sm_100a tensor cores.
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1      : MMA issuer     (one lane issues tcgen05.mma, accumulators in TMEM, 2 buffers)
+//   warps 2..5  : epilogue       (tcgen05.ld -> registers -> fused epilogue -> global)
+//
+// The same kernel serves
+//   * linear layers and their gradients (K-major and MN-major operands, split-K with fp32 red),
+//   * 3x3 / 1x1 convolution forward and data-gradient as implicit GEMM: the A tile of a
+//     k-iteration is one TMA box {64 channels, bw, bh} of the NHWC activation, shifted by the
+//     filter tap; out-of-image pixels are zero-filled by the TMA unit (that is the padding),
+//   * convolution weight-gradient (reduction over pixels, both operands MN-major, tap = batch),
+//   * the batched attention GEMMs with softmax-aware epilogues.
+//
+// Replaces in the reference: nn.Linear / nn.Conv2d dispatch sites K1,K3,K4,K5 of SURVEY.md §2.2
+// (modules/diffusion/openaimodel.py:247-301, modules/attention.py:50-74,283-290,616-639).
+#include "gemm_tc.cuh"
+
+#include <algorithm>
+
+namespace nk {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int ATOM_BYTES = 64 * 64 * 2;     // one 64x64 bf16 box, 8 KB
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;
+
+enum { MODE_PLAIN = 0, MODE_CONV_FWD = 1, MODE_CONV_WGRAD = 2 };
+
+struct alignas(64) GemmDev {
+    CUtensorMap tmA;
+    CUtensorMap tmB;
+    int M, N;
+    int BN;
+    int tiles_m, tiles_n, nb2, nb1, splits;
+    int k_iters, k_iters_total;
+    int stages;
+    int a_mn, b_mn;
+    int mode;
+    int a_b2, a_b1, b_b2, b_b1;  // 0/1: does the operand carry that batch dimension
+    // conv geometry
+    int cH, cW, bw, bh, tiles_w, tiles_h, cin_blocks, ksize, pad;
+    // epilogue
+    void* C;
+    long long ldc, c_b2, c_b1;
+    int out, epi;
+    float alpha;
+    const float* bias;
+    const float* bias_img;
+    int rows_per_img;
+    const bf16* residual;
+    long long ldr;
+    const float* rowvec;
+    const bf16* aux;
+    uint32_t idesc;
+    uint32_t a_bytes, b_bytes;  // bytes landed per stage for A and B
+};
+
+struct TileCoord {
+    int mt, nt, b2, b1, split;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmDev& g, int t) {
+    TileCoord c;
+    c.mt = t % g.tiles_m;
+    t /= g.tiles_m;
+    c.nt = t % g.tiles_n;
+    t /= g.tiles_n;
+    c.b2 = t % g.nb2;
+    t /= g.nb2;
+    c.b1 = t % g.nb1;
+    c.split = t / g.nb1;
+    return c;
+}
+
+__device__ __forceinline__ int iters_of_split(const GemmDev& g, int split) {
+    int rem = g.k_iters_total - split * g.k_iters;
+    return rem < g.k_iters ? rem : g.k_iters;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmDev g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024B alignment is required by the 128B swizzle atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    const int stages = g.stages;
+    const uint32_t b_stage_bytes = static_cast<uint32_t>(g.BN) * 128u;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + static_cast<size_t>(stages) * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + static_cast<size_t>(stages) * b_stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + stages;
+    uint64_t* tmem_full = bars + 2 * stages;
+    uint64_t* tmem_empty = bars + 2 * stages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = g.tiles_m * g.tiles_n * g.nb2 * g.nb1 * g.splits;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&g.tmA);
+        tma_prefetch_desc(&g.tmB);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full[0], 1);
+        mbar_init(&tmem_full[1], 1);
+        mbar_init(&tmem_empty[0], 4);
+        mbar_init(&tmem_empty[1], 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(g, t);
+                const int n0 = tc.nt * g.BN;
+                const int m0 = tc.mt * BM;
+                const int iters = iters_of_split(g, tc.split);
+                int img = 0, th = 0, tw = 0;
+                if (g.mode == MODE_CONV_FWD) {
+                    tw = tc.mt % g.tiles_w;
+                    th = (tc.mt / g.tiles_w) % g.tiles_h;
+                    img = tc.mt / (g.tiles_w * g.tiles_h);
+                }
+                for (int it = 0; it < iters; ++it) {
+                    const int gi = tc.split * g.k_iters + it;
+                    mbar_wait(&empty_bar[stage], phase ^ 1u, 100u + stage);
+                    mbar_arrive_expect_tx(&full_bar[stage], g.a_bytes + g.b_bytes);
+                    uint8_t* sa = smem_a + static_cast<size_t>(stage) * A_STAGE_BYTES;
+                    uint8_t* sb = smem_b + static_cast<size_t>(stage) * b_stage_bytes;
+                    if (g.mode == MODE_PLAIN) {
+                        const int k0 = gi * BK;
+                        if (!g.a_mn) {
+                            tma_load_4d(&g.tmA, &full_bar[stage], sa, k0, m0, tc.b2 * g.a_b2,
+                                        tc.b1 * g.a_b1);
+                        } else {
+                            tma_load_4d(&g.tmA, &full_bar[stage], sa, m0, k0, tc.b2 * g.a_b2,
+                                        tc.b1 * g.a_b1);
+                            tma_load_4d(&g.tmA, &full_bar[stage], sa + ATOM_BYTES, m0 + 64, k0,
+                                        tc.b2 * g.a_b2, tc.b1 * g.a_b1);
+                        }
+                        if (!g.b_mn) {
+                            tma_load_4d(&g.tmB, &full_bar[stage], sb, k0, n0, tc.b2 * g.b_b2,
+                                        tc.b1 * g.b_b1);
+                        } else {
+                            for (int j = 0; j < g.BN / 64; ++j)
+                                tma_load_4d(&g.tmB, &full_bar[stage], sb + j * ATOM_BYTES,
+                                            n0 + 64 * j, k0, tc.b2 * g.b_b2, tc.b1 * g.b_b1);
+                        }
+                    } else if (g.mode == MODE_CONV_FWD) {
+                        const int tap = gi / g.cin_blocks;
+                        const int cb = gi - tap * g.cin_blocks;
+                        const int dy = tap / g.ksize - g.pad;
+                        const int dx = tap % g.ksize - g.pad;
+                        tma_load_4d(&g.tmA, &full_bar[stage], sa, cb * 64, tw * g.bw + dx,
+                                    th * g.bh + dy, img);
+                        tma_load_4d(&g.tmB, &full_bar[stage], sb, gi * BK, n0, 0, 0);
+                    } else {  // MODE_CONV_WGRAD: k-iteration = one 64-pixel tile, tap = b2
+                        const int ptw = gi % g.tiles_w;
+                        const int pth = (gi / g.tiles_w) % g.tiles_h;
+                        const int pimg = gi / (g.tiles_w * g.tiles_h);
+                        const int dy = tc.b2 / g.ksize - g.pad;
+                        const int dx = tc.b2 % g.ksize - g.pad;
+                        tma_load_4d(&g.tmA, &full_bar[stage], sa, m0, ptw * g.bw, pth * g.bh, pimg);
+                        tma_load_4d(&g.tmA, &full_bar[stage], sa + ATOM_BYTES, m0 + 64, ptw * g.bw,
+                                    pth * g.bh, pimg);
+                        for (int j = 0; j < g.BN / 64; ++j)
+                            tma_load_4d(&g.tmB, &full_bar[stage], sb + j * ATOM_BYTES, n0 + 64 * j,
+                                        ptw * g.bw + dx, pth * g.bh + dy, pimg);
+                    }
+                    if (++stage == stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            // per-k16 descriptor advance (in 16-byte units)
+            const uint32_t a_adv = g.a_mn ? (2048u >> 4) : (32u >> 4);
+            const uint32_t b_adv = g.b_mn ? (2048u >> 4) : (32u >> 4);
+            const uint32_t a_lbo = g.a_mn ? static_cast<uint32_t>(ATOM_BYTES) : 16u;
+            const uint32_t b_lbo = g.b_mn ? static_cast<uint32_t>(ATOM_BYTES) : 16u;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+                const TileCoord tc = decode_tile(g, t);
+                const int iters = iters_of_split(g, tc.split);
+                const int acc = local & 1;
+                mbar_wait(&tmem_empty[acc], ((local >> 1) & 1u) ^ 1u, 200u + acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * ACC_STRIDE);
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(&full_bar[stage], phase, 300u + stage);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem_a + static_cast<size_t>(stage) * A_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(smem_b + static_cast<size_t>(stage) * b_stage_bytes);
+                    const uint64_t a_desc = make_smem_desc(sa, a_lbo, 1024u);
+                    const uint64_t b_desc = make_smem_desc(sb, b_lbo, 1024u);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        tc_mma_ss(d_tmem, a_desc + static_cast<uint64_t>(k * a_adv),
+                                  b_desc + static_cast<uint64_t>(k * b_adv), g.idesc,
+                                  (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++stage == stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        const int r = quad * 32 + lane;
+        int local = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+            const TileCoord tc = decode_tile(g, t);
+            const int n0 = tc.nt * g.BN;
+            const int acc = local & 1;
+            // output row of this thread
+            long long row = 0;
+            bool row_ok = false;
+            int img = 0;
+            if (g.mode == MODE_CONV_FWD) {
+                const int tw = tc.mt % g.tiles_w;
+                const int th = (tc.mt / g.tiles_w) % g.tiles_h;
+                img = tc.mt / (g.tiles_w * g.tiles_h);
+                const int hh = r / g.bw;
+                const int ww = r - hh * g.bw;
+                const int h = th * g.bh + hh;
+                const int w = tw * g.bw + ww;
+                row_ok = (hh < g.bh) && (h < g.cH) && (w < g.cW);
+                row = (static_cast<long long>(img) * g.cH + h) * g.cW + w;
+            } else {
+                row = static_cast<long long>(tc.mt) * BM + r;
+                row_ok = row < g.M;
+                if (g.bias_img) img = static_cast<int>(row / g.rows_per_img);
+            }
+            const long long boff = tc.b2 * g.c_b2 + tc.b1 * g.c_b1;
+            float rv = 0.f;
+            if (g.rowvec && row_ok)
+                rv = g.rowvec[(static_cast<long long>(tc.b1) * g.nb2 + tc.b2) * g.M + row];
+
+            mbar_wait(&tmem_full[acc], (local >> 1) & 1u, 400u + acc);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                    static_cast<uint32_t>(acc * ACC_STRIDE);
+            for (int c = 0; c < g.BN / 16; ++c) {
+                uint32_t raw[16];
+                tc_ld16(taddr0 + static_cast<uint32_t>(c * 16), raw);
+                tc_wait_ld();
+                const int n = n0 + c * 16;
+                if (!row_ok || n >= g.N) continue;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+                const bool full = (n + 16 <= g.N);
+                if (g.epi == EPI_LINEAR) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] *= g.alpha;
+                    if (g.bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (full || n + j < g.N) v[j] += __ldg(g.bias + n + j);
+                    }
+                    if (g.bias_img) {
+                        const float* bi = g.bias_img + static_cast<long long>(img) * g.N + n;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (full || n + j < g.N) v[j] += __ldg(bi + j);
+                    }
+                    if (g.residual) {
+                        const bf16* rp = g.residual + boff + row * g.ldr + n;
+                        if (full && ((reinterpret_cast<uintptr_t>(rp) & 15u) == 0)) {
+                            const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
+                            const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+                            const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 f = unpack_bf16x2(w[j]);
+                                v[2 * j] += f.x;
+                                v[2 * j + 1] += f.y;
+                            }
+                        } else {
+                            for (int j = 0; j < 16 && n + j < g.N; ++j)
+                                v[j] += __bfloat162float(rp[j]);
+                        }
+                    }
+                } else if (g.epi == EPI_EXP2) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = exp2f(v[j] * g.alpha - rv);
+                } else {  // EPI_DSOFTMAX
+                    const bf16* ap = g.aux + boff + row * g.ldc + n;
+                    for (int j = 0; j < 16 && n + j < g.N; ++j)
+                        v[j] = __bfloat162float(ap[j]) * (v[j] - rv) * g.alpha;
+                }
+                // ---- store ----
+                if (g.out == OUT_BF16) {
+                    bf16* cp = reinterpret_cast<bf16*>(g.C) + boff + row * g.ldc + n;
+                    if (full && ((reinterpret_cast<uintptr_t>(cp) & 15u) == 0)) {
+                        uint4 q0, q1;
+                        q0.x = pack_bf16x2(v[0], v[1]);
+                        q0.y = pack_bf16x2(v[2], v[3]);
+                        q0.z = pack_bf16x2(v[4], v[5]);
+                        q0.w = pack_bf16x2(v[6], v[7]);
+                        q1.x = pack_bf16x2(v[8], v[9]);
+                        q1.y = pack_bf16x2(v[10], v[11]);
+                        q1.z = pack_bf16x2(v[12], v[13]);
+                        q1.w = pack_bf16x2(v[14], v[15]);
+                        reinterpret_cast<uint4*>(cp)[0] = q0;
+                        reinterpret_cast<uint4*>(cp)[1] = q1;
+                    } else {
+                        for (int j = 0; j < 16 && n + j < g.N; ++j) cp[j] = __float2bfloat16(v[j]);
+                    }
+                } else if (g.out == OUT_F32) {
+                    float* cp = reinterpret_cast<float*>(g.C) + boff + row * g.ldc + n;
+                    if (full && ((reinterpret_cast<uintptr_t>(cp) & 15u) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            reinterpret_cast<float4*>(cp)[j] =
+                                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+                        for (int j = 0; j < 16 && n + j < g.N; ++j) cp[j] = v[j];
+                    }
+                } else {  // OUT_F32_ATOMIC
+                    float* cp = reinterpret_cast<float*>(g.C) + boff + row * g.ldc + n;
+                    if (full && ((reinterpret_cast<uintptr_t>(cp) & 15u) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + 4 * j),
+                                         "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]),
+                                         "f"(v[4 * j + 3])
+                                         : "memory");
+                    } else {
+                        for (int j = 0; j < 16 && n + j < g.N; ++j) atomicAdd(cp + j, v[j]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+
+int make_operand_tmap(CUtensorMap* tm, const GemmOperand& o, int box_rows_or_bw, int box_bh) {
+    uint64_t dims[4];
+    uint64_t strides[3];
+    uint32_t box[4];
+    if (!o.conv) {
+        dims[0] = static_cast<uint64_t>(o.inner);
+        dims[1] = static_cast<uint64_t>(o.rows);
+        dims[2] = static_cast<uint64_t>(o.nb2 > 0 ? o.nb2 : 1);
+        dims[3] = static_cast<uint64_t>(o.nb1 > 0 ? o.nb1 : 1);
+        strides[0] = static_cast<uint64_t>(o.row_stride) * 2;
+        strides[1] = static_cast<uint64_t>(dims[2] > 1 ? o.b2_stride : o.row_stride * o.rows) * 2;
+        strides[2] = static_cast<uint64_t>(dims[3] > 1 ? o.b1_stride : o.row_stride * o.rows) * 2;
+        box[0] = 64;
+        box[1] = static_cast<uint32_t>(box_rows_or_bw);
+        box[2] = 1;
+        box[3] = 1;
+    } else {
+        dims[0] = static_cast<uint64_t>(o.inner);
+        dims[1] = static_cast<uint64_t>(o.W);
+        dims[2] = static_cast<uint64_t>(o.H);
+        dims[3] = static_cast<uint64_t>(o.nimg);
+        strides[0] = static_cast<uint64_t>(o.row_stride) * 2;
+        strides[1] = strides[0] * static_cast<uint64_t>(o.W);
+        strides[2] = strides[1] * static_cast<uint64_t>(o.H);
+        box[0] = 64;
+        box[1] = static_cast<uint32_t>(box_rows_or_bw);
+        box[2] = static_cast<uint32_t>(box_bh);
+        box[3] = 1;
+    }
+    return encode_tmap_bf16(tm, o.ptr, 4, dims, strides, box);
+}
+
+int pick_bn(const GemmProblem& p, long long tiles_m_batches, int nsm) {
+    if (p.force_bn > 0) return p.force_bn;
+    const int step = p.B.mn_major ? 64 : 16;
+    long long best_cost = -1;
+    int best = 256;
+    for (int bn = 256; bn >= step; bn -= step) {
+        const long long tiles = tiles_m_batches * ((p.N + bn - 1) / bn);
+        const long long waves = (tiles + nsm - 1) / nsm;
+        // cycles per k16 step: tensor pipe BN/2 vs smem feed (4 KB of A + BN*32 B of B at 128 B/clk)
+        const long long per = std::max<long long>(bn / 2, 32 + bn / 4) + 6;
+        const long long cost = waves * per;
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = bn;
+        }
+    }
+    return best;
+}
+
+}  // namespace
+
+// pixel-tile shape for a conv forward M tile (<=128 pixels) or wgrad K tile (exactly 64 pixels)
+static void pick_pixel_tile(int H, int W, int target, bool exact, int* bw_out, int* bh_out) {
+    long long best = -1;
+    int bbw = 1, bbh = target;
+    for (int bw = 1; bw <= std::min(W, target); ++bw) {
+        if (exact && (target % bw) != 0) continue;
+        int bh = target / bw;
+        if (bh > 256) continue;
+        if (bh > H) bh = exact ? bh : H;
+        const long long tiles = static_cast<long long>((W + bw - 1) / bw) * ((H + bh - 1) / bh);
+        if (best < 0 || tiles < best || (tiles == best && bw > bbw)) {
+            best = tiles;
+            bbw = bw;
+            bbh = bh;
+        }
+    }
+    *bw_out = bbw;
+    *bh_out = bbh;
+}
+
+int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
+    static int nsm = 0;
+    static bool attr_set = false;
+    if (nsm == 0) nsm = device_sm_count();
+    NK_REQUIRE(nsm > 0, NK_ERR_CUDA, "no CUDA device");
+    NK_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, NK_ERR_SHAPE, "gemm: empty problem %d %d %d", p.M, p.N, p.K);
+
+    GemmDev g;
+    memset(&g, 0, sizeof(g));
+    g.M = p.M;
+    g.N = p.N;
+    g.nb2 = p.nb2 > 0 ? p.nb2 : 1;
+    g.nb1 = p.nb1 > 0 ? p.nb1 : 1;
+    g.a_mn = p.A.mn_major;
+    g.b_mn = p.B.mn_major;
+    g.ksize = p.ksize > 0 ? p.ksize : 1;
+    g.pad = p.pad;
+    g.mode = MODE_PLAIN;
+    if (p.wgrad) {
+        g.mode = MODE_CONV_WGRAD;
+        NK_REQUIRE(p.A.conv && p.B.conv && p.A.mn_major && p.B.mn_major, NK_ERR_UNSUPPORTED,
+                   "wgrad needs MN-major image operands");
+    } else if (p.A.conv) {
+        g.mode = MODE_CONV_FWD;
+        NK_REQUIRE(!p.A.mn_major && !p.B.conv && !p.B.mn_major, NK_ERR_UNSUPPORTED,
+                   "conv forward needs K-major operands");
+        NK_REQUIRE(p.A.inner % 64 == 0, NK_ERR_SHAPE, "conv: C_in %lld not a multiple of 64", p.A.inner);
+    }
+
+    int a_box1 = BM, a_box2 = 1, b_box2 = 1;
+    if (g.mode == MODE_CONV_FWD) {
+        g.cH = p.A.H;
+        g.cW = p.A.W;
+        pick_pixel_tile(g.cH, g.cW, BM, false, &g.bw, &g.bh);
+        g.tiles_w = (g.cW + g.bw - 1) / g.bw;
+        g.tiles_h = (g.cH + g.bh - 1) / g.bh;
+        g.tiles_m = p.A.nimg * g.tiles_w * g.tiles_h;
+        g.cin_blocks = static_cast<int>(p.A.inner / 64);
+        g.k_iters_total = g.ksize * g.ksize * g.cin_blocks;
+        a_box1 = g.bw;
+        a_box2 = g.bh;
+        g.a_bytes = static_cast<uint32_t>(g.bw * g.bh * 128);
+    } else if (g.mode == MODE_CONV_WGRAD) {
+        g.cH = p.A.H;
+        g.cW = p.A.W;
+        pick_pixel_tile(g.cH, g.cW, 64, true, &g.bw, &g.bh);
+        g.tiles_w = (g.cW + g.bw - 1) / g.bw;
+        g.tiles_h = (g.cH + g.bh - 1) / g.bh;
+        g.tiles_m = (p.M + BM - 1) / BM;
+        g.k_iters_total = p.A.nimg * g.tiles_w * g.tiles_h;
+        a_box1 = g.bw;
+        a_box2 = g.bh;
+        b_box2 = g.bh;
+        g.a_bytes = 2 * ATOM_BYTES;
+        NK_REQUIRE(g.nb2 == g.ksize * g.ksize, NK_ERR_SHAPE, "wgrad: nb2 must equal taps");
+    } else {
+        g.tiles_m = (p.M + BM - 1) / BM;
+        g.k_iters_total = (p.K + BK - 1) / BK;
+        a_box1 = p.A.mn_major ? 64 : BM;
+        g.a_bytes = A_STAGE_BYTES;
+    }
+
+    const long long tiles_mb = static_cast<long long>(g.tiles_m) * g.nb2 * g.nb1;
+    g.BN = pick_bn(p, tiles_mb, nsm);
+    NK_REQUIRE(g.BN >= 16 && g.BN <= 256 && g.BN % 16 == 0, NK_ERR_SHAPE, "bad BN %d", g.BN);
+    NK_REQUIRE(!p.B.mn_major || g.BN % 64 == 0, NK_ERR_SHAPE, "MN-major B needs BN %% 64 == 0");
+    g.tiles_n = (p.N + g.BN - 1) / g.BN;
+    g.b_bytes = static_cast<uint32_t>(g.BN) * 128u;
+
+    // split-K only when accumulating atomically
+    int splits = 1;
+    if (p.out == OUT_F32_ATOMIC) {
+        const long long tiles = tiles_mb * g.tiles_n;
+        if (p.force_splits > 0)
+            splits = p.force_splits;
+        else if (tiles < nsm)
+            splits = static_cast<int>(std::min<long long>((2LL * nsm + tiles - 1) / tiles,
+                                                           std::max(1, g.k_iters_total / 8)));
+        splits = std::max(1, std::min(splits, g.k_iters_total));
+    }
+    g.k_iters = (g.k_iters_total + splits - 1) / splits;
+    g.splits = (g.k_iters_total + g.k_iters - 1) / g.k_iters;
+
+    g.a_b2 = (!p.A.conv && p.A.nb2 > 1) ? 1 : 0;
+    g.a_b1 = (!p.A.conv && p.A.nb1 > 1) ? 1 : 0;
+    g.b_b2 = (!p.B.conv && p.B.nb2 > 1) ? 1 : 0;
+    g.b_b1 = (!p.B.conv && p.B.nb1 > 1) ? 1 : 0;
+
+    int e = make_operand_tmap(&g.tmA, p.A, a_box1, a_box2);
+    if (e) return e;
+    const int b_box1 = p.B.conv ? g.bw : (p.B.mn_major ? 64 : g.BN);
+    e = make_operand_tmap(&g.tmB, p.B, b_box1, b_box2);
+    if (e) return e;
+
+    g.C = p.C;
+    g.ldc = p.ldc;
+    g.c_b2 = p.c_b2_stride;
+    g.c_b1 = p.c_b1_stride;
+    g.out = p.out;
+    g.epi = p.epi;
+    g.alpha = p.alpha;
+    g.bias = p.bias;
+    g.bias_img = p.bias_img;
+    g.rows_per_img = p.rows_per_img > 0 ? p.rows_per_img : 1;
+    g.residual = p.residual;
+    g.ldr = p.ldr;
+    g.rowvec = p.rowvec;
+    g.aux = p.aux;
+    g.idesc = make_idesc_bf16(BM, g.BN, g.a_mn, g.b_mn);
+    NK_REQUIRE(p.epi != EPI_DSOFTMAX || (p.aux && p.rowvec), NK_ERR_SHAPE, "dsoftmax needs aux+rowvec");
+    NK_REQUIRE(p.epi != EPI_EXP2 || p.rowvec, NK_ERR_SHAPE, "exp2 epilogue needs rowvec");
+
+    const int stage_bytes = A_STAGE_BYTES + g.BN * 128;
+    const int max_smem = 227 * 1024;
+    int stages = (max_smem - 1024 - 256) / stage_bytes;
+    stages = std::max(2, std::min(stages, 8));
+    g.stages = stages;
+    const int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 5) * 8;
+    if (!attr_set) {
+        NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_set = true;
+    }
+    const long long total = tiles_mb * g.tiles_n * g.splits;
+    NK_REQUIRE(total < (1LL << 31), NK_ERR_SHAPE, "too many tiles");
+    const int grid = static_cast<int>(std::min<long long>(total, nsm));
+    gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(g);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+
+}  // namespace nk

@@ -1,0 +1,58 @@
+// Internal description of one tcgen05 GEMM launch (shared by the linear, conv and attention
+// entry points).  See gemm_tc.cu for the kernel.
+#pragma once
+#include "common.cuh"
+
+namespace nk {
+
+enum GemmEpilogue : int {
+    EPI_LINEAR = 0,  // C = alpha*acc (+ bias[n]) (+ bias_img[img,n]) (+ residual[m,n])
+    EPI_EXP2 = 1,    // C = exp2(alpha*acc - rowvec[m])                 (attention probabilities)
+    EPI_DSOFTMAX = 2,  // C = aux[m,n] * (acc - rowvec[m]) * alpha       (attention dS)
+};
+
+enum GemmOut : int {
+    OUT_BF16 = 0,
+    OUT_F32 = 1,
+    OUT_F32_ATOMIC = 2,  // red.global.add.f32 into C (split-K / gradient accumulation)
+};
+
+// One operand.  Matrix form: `rows` x `inner` with `inner` contiguous, plus two batch dims.
+// Image form (conv=1): NHWC tensor (nimg, H, W, inner) with pixel stride `row_stride`.
+struct GemmOperand {
+    const bf16* ptr;
+    int mn_major;  // 0: `inner` is the reduction dim K;  1: `inner` is the M (or N) dim
+    int conv;      // 1: addressed through pixel tiles (4D coordinates c, w, h, img)
+    long long inner, rows, row_stride;      // elements
+    long long nb2, b2_stride, nb1, b1_stride;  // batch dims (matrix form)
+    int H, W, nimg;                         // image form
+};
+
+struct GemmProblem {
+    GemmOperand A, B;
+    int M, N, K;          // per batch entry
+    int nb2, nb1;         // batch extents of the launch (C is indexed by them as well)
+    // conv forward / dgrad (A.conv=1, A K-major): K = taps*Cin, k-iteration -> (tap, 64-channel block)
+    int ksize, pad;       // 3,1 or 1,0
+    // conv wgrad (A.conv = B.conv = 1, both MN-major): batch index b2 = tap, K = all pixels
+    int wgrad;
+    // output
+    void* C;
+    long long ldc, c_b2_stride, c_b1_stride;  // elements
+    int out;              // GemmOut
+    int epi;              // GemmEpilogue
+    float alpha;
+    const float* bias;        // [N] or null
+    const float* bias_img;    // [nimg, N] or null (row m belongs to image m / rows_per_img)
+    int rows_per_img;
+    const bf16* residual;     // [M, ldr] or null (batch strides = C's)
+    long long ldr;
+    const float* rowvec;      // [M] per batch entry (stride M), EPI_EXP2 / EPI_DSOFTMAX
+    const bf16* aux;          // [M, N] like C, EPI_DSOFTMAX
+    int force_bn;             // 0 = heuristic
+    int force_splits;         // 0 = heuristic (only with OUT_F32_ATOMIC)
+};
+
+int launch_gemm(const GemmProblem& p, cudaStream_t stream);
+
+}  // namespace nk
