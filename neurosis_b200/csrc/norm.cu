@@ -1,0 +1,545 @@
+// GroupNorm(+SiLU) and LayerNorm, forward and backward, for bf16 activations with fp32 statistics.
+// HBM-bound kernels: 128-bit vectorised, fully coalesced NHWC / row-major access, per-thread fp32
+// partial sums, shared-memory + warp-shuffle reductions.
+//
+// Replaces in the reference (paths under /root/reference/src/neurosis):
+//   nn.GroupNorm(32, C) + nn.SiLU  modules/diffusion/openaimodel.py:247-249,281-283,798 (eps 1e-5)
+//   nn.GroupNorm(32, C, eps=1e-6)  modules/attention.py:612 ; modules/layers.py:5-7 (+F.silu model.py:116-124)
+//   nn.LayerNorm(dim)              modules/attention.py:468-470
+#include "common.cuh"
+
+namespace nk {
+namespace {
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+// d/dv silu(v) = s + v*s*(1-s), s = sigmoid(v)
+__device__ __forceinline__ float dsilu_f(float v) {
+    const float s = 1.f / (1.f + __expf(-v));
+    return s * (1.f + v * (1.f - s));
+}
+
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]);
+    q.y = pack_bf16x2(v[2], v[3]);
+    q.z = pack_bf16x2(v[4], v[5]);
+    q.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = q;
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm forward
+// ------------------------------------------------------------------------------------------
+// stats pass: grid (chunks, nimg). Thread t owns channel octet (t % V) and walks pixels
+// (t / V) + k*ppb of its chunk.  partial[(img*chunks + chunk)*G + g] = {sum, sumsq}
+__global__ void gn_stats_kernel(const bf16* __restrict__ x, long long pix_stride, float2* __restrict__ partial,
+                                int HW, int C, int G, int V, int ppb, int pix_per_chunk) {
+    extern __shared__ float sm[];  // [2*C]
+    float* s_sum = sm;
+    float* s_sq = sm + C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int img = blockIdx.y, chunk = blockIdx.x;
+    const int v = threadIdx.x % V, pl = threadIdx.x / V;
+    if (pl < ppb) {
+        float s[8], q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+        const int p0 = chunk * pix_per_chunk;
+        const int p1 = min(HW, p0 + pix_per_chunk);
+        const bf16* base = x + (static_cast<long long>(img) * HW) * pix_stride + v * 8;
+        for (int p = p0 + pl; p < p1; p += ppb) {
+            float f[8];
+            load8(base + p * pix_stride, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s[j] += f[j];
+                q[j] += f[j] * f[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&s_sum[v * 8 + j], s[j]);
+            atomicAdd(&s_sq[v * 8 + j], q[j]);
+        }
+    }
+    __syncthreads();
+    const int cpg = C / G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            a += s_sum[c];
+            b += s_sq[c];
+        }
+        partial[(static_cast<long long>(img) * gridDim.x + chunk) * G + g] = make_float2(a, b);
+    }
+}
+
+// finalize: grid nimg, block G threads
+__global__ void gn_finalize_kernel(const float2* __restrict__ partial, float* __restrict__ mean,
+                                   float* __restrict__ rstd, int chunks, int G, float inv_count, float eps) {
+    const int img = blockIdx.x, g = threadIdx.x;
+    if (g >= G) return;
+    double a = 0.0, b = 0.0;
+    for (int c = 0; c < chunks; ++c) {
+        const float2 p = partial[(static_cast<long long>(img) * chunks + c) * G + g];
+        a += p.x;
+        b += p.y;
+    }
+    const double m = a * inv_count;
+    double var = b * inv_count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[img * G + g] = static_cast<float>(m);
+    rstd[img * G + g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, long long x_stride, bf16* __restrict__ y,
+                                long long y_stride, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, int HW, int C, int G, int V, int ppb,
+                                int pix_per_chunk, int silu) {
+    extern __shared__ float sm[];  // a[C], b[C]
+    float* s_a = sm;
+    float* s_b = sm + C;
+    const int img = blockIdx.y, chunk = blockIdx.x;
+    const int cpg = C / G;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float r = rstd[img * G + g], m = mean[img * G + g];
+        const float a = r * gamma[c];
+        s_a[c] = a;
+        s_b[c] = beta[c] - m * a;
+    }
+    __syncthreads();
+    const int v = threadIdx.x % V, pl = threadIdx.x / V;
+    if (pl >= ppb) return;
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = s_a[v * 8 + j];
+        b[j] = s_b[v * 8 + j];
+    }
+    const int p0 = chunk * pix_per_chunk;
+    const int p1 = min(HW, p0 + pix_per_chunk);
+    const bf16* xb = x + (static_cast<long long>(img) * HW) * x_stride + v * 8;
+    bf16* yb = y + (static_cast<long long>(img) * HW) * y_stride + v * 8;
+    for (int p = p0 + pl; p < p1; p += ppb) {
+        float f[8];
+        load8(xb + p * x_stride, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = fmaf(f[j], a[j], b[j]);
+            f[j] = silu ? silu_f(t) : t;
+        }
+        store8(yb + p * y_stride, f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm backward
+// ------------------------------------------------------------------------------------------
+// pass 1: per (img, chunk) per-channel sums of dyp*xhat and dyp, dyp = dy * silu'(pre)
+__global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, long long dy_stride, const bf16* __restrict__ x,
+                                    long long x_stride, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, float2* __restrict__ partial, int HW, int C,
+                                    int G, int V, int ppb, int pix_per_chunk, int silu) {
+    extern __shared__ float sm[];  // A[C], B[C]
+    float* s_A = sm;
+    float* s_B = sm + C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int img = blockIdx.y, chunk = blockIdx.x;
+    const int cpg = C / G;
+    const int v = threadIdx.x % V, pl = threadIdx.x / V;
+    if (pl < ppb) {
+        float m[8], r[8], ga[8], be[8], A[8], B[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = v * 8 + j, g = c / cpg;
+            m[j] = mean[img * G + g];
+            r[j] = rstd[img * G + g];
+            ga[j] = gamma[c];
+            be[j] = beta[c];
+            A[j] = B[j] = 0.f;
+        }
+        const int p0 = chunk * pix_per_chunk;
+        const int p1 = min(HW, p0 + pix_per_chunk);
+        const bf16* xb = x + (static_cast<long long>(img) * HW) * x_stride + v * 8;
+        const bf16* db = dy + (static_cast<long long>(img) * HW) * dy_stride + v * 8;
+        for (int p = p0 + pl; p < p1; p += ppb) {
+            float f[8], d[8];
+            load8(xb + p * x_stride, f);
+            load8(db + p * dy_stride, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (f[j] - m[j]) * r[j];
+                float dp = d[j];
+                if (silu) dp *= dsilu_f(fmaf(xh, ga[j], be[j]));
+                A[j] += dp * xh;
+                B[j] += dp;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&s_A[v * 8 + j], A[j]);
+            atomicAdd(&s_B[v * 8 + j], B[j]);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        partial[(static_cast<long long>(img) * gridDim.x + chunk) * C + c] = make_float2(s_A[c], s_B[c]);
+}
+
+// pass 2: grid nimg.  Reduces chunks; per-group s1,s2 -> coef[img][g] ; per-image channel sums -> chan[img][c]
+__global__ void gn_bwd_finalize_kernel(const float2* __restrict__ partial, const float* __restrict__ gamma,
+                                       float2* __restrict__ chan, float2* __restrict__ coef, int chunks, int C,
+                                       int G) {
+    extern __shared__ float sm[];  // A[C], B[C]
+    float* s_A = sm;
+    float* s_B = sm + C;
+    const int img = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < chunks; ++k) {
+            const float2 p = partial[(static_cast<long long>(img) * chunks + k) * C + c];
+            a += p.x;
+            b += p.y;
+        }
+        s_A[c] = a;
+        s_B[c] = b;
+        chan[static_cast<long long>(img) * C + c] = make_float2(a, b);
+    }
+    __syncthreads();
+    const int cpg = C / G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            s1 += gamma[c] * s_A[c];
+            s2 += gamma[c] * s_B[c];
+        }
+        coef[img * G + g] = make_float2(s1, s2);
+    }
+}
+
+// dgamma[c] += sum_img A ; dbeta[c] += sum_img B
+__global__ void gn_bwd_param_kernel(const float2* __restrict__ chan, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int nimg, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < nimg; ++i) {
+        const float2 p = chan[static_cast<long long>(i) * C + c];
+        a += p.x;
+        b += p.y;
+    }
+    dgamma[c] += a;
+    dbeta[c] += b;
+}
+
+// pass 3: dx = rstd * (gamma*dyp - (s2 + xhat*s1) / m)
+__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_stride, const bf16* __restrict__ x,
+                                    long long x_stride, bf16* __restrict__ dx, long long dx_stride,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float2* __restrict__ coef, int HW, int C, int G, int V, int ppb,
+                                    int pix_per_chunk, int silu, float inv_m) {
+    const int img = blockIdx.y, chunk = blockIdx.x;
+    const int cpg = C / G;
+    const int v = threadIdx.x % V, pl = threadIdx.x / V;
+    if (pl >= ppb) return;
+    float m[8], r[8], ga[8], be[8], s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = v * 8 + j, g = c / cpg;
+        m[j] = mean[img * G + g];
+        r[j] = rstd[img * G + g];
+        ga[j] = gamma[c];
+        be[j] = beta[c];
+        const float2 cf = coef[img * G + g];
+        s1[j] = cf.x * inv_m;
+        s2[j] = cf.y * inv_m;
+    }
+    const int p0 = chunk * pix_per_chunk;
+    const int p1 = min(HW, p0 + pix_per_chunk);
+    const bf16* xb = x + (static_cast<long long>(img) * HW) * x_stride + v * 8;
+    const bf16* db = dy + (static_cast<long long>(img) * HW) * dy_stride + v * 8;
+    bf16* ob = dx + (static_cast<long long>(img) * HW) * dx_stride + v * 8;
+    for (int p = p0 + pl; p < p1; p += ppb) {
+        float f[8], d[8];
+        load8(xb + p * x_stride, f);
+        load8(db + p * dy_stride, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (f[j] - m[j]) * r[j];
+            float dp = d[j];
+            if (silu) dp *= dsilu_f(fmaf(xh, ga[j], be[j]));
+            f[j] = r[j] * (ga[j] * dp - (s2[j] + xh * s1[j]));
+        }
+        store8(ob + p * dx_stride, f);
+    }
+}
+
+struct GnPlan {
+    int V, ppb, threads, chunks, pix_per_chunk;
+};
+GnPlan gn_plan(int nimg, int HW, int C) {
+    GnPlan p;
+    p.V = C / 8;
+    p.ppb = std::max(1, 256 / p.V);
+    p.threads = ((p.V * p.ppb + 31) / 32) * 32;
+    // aim for ~8 blocks per SM overall, at least ppb*4 pixels per block
+    int want = std::max(1, (148 * 8) / std::max(1, nimg));
+    int max_chunks = std::max(1, HW / (p.ppb * 4));
+    p.chunks = std::max(1, std::min(want, max_chunks));
+    p.pix_per_chunk = (HW + p.chunks - 1) / p.chunks;
+    p.chunks = (HW + p.pix_per_chunk - 1) / p.pix_per_chunk;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row cached in registers (C <= 2560)
+// ------------------------------------------------------------------------------------------
+template <int MAXV>  // max 8-element vectors per lane
+__global__ void ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* __restrict__ mean, float* __restrict__ rstd, int rows, int C, float eps) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int V = C / 8;
+    for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); row < rows;
+         row += static_cast<long long>(gridDim.x) * warps_per_block) {
+        float f[MAXV][8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + i * 32;
+            if (v < V) {
+                load8(x + row * ldx + v * 8, f[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += f[i][j];
+            }
+        }
+        s = warp_sum(s);
+        const float m = s / C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + i * 32;
+            if (v < V) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float d = f[i][j] - m;
+                    q += d * d;
+                }
+            }
+        }
+        q = warp_sum(q);
+        const float r = rsqrtf(q / C + eps);
+        if (lane == 0) {
+            mean[row] = m;
+            rstd[row] = r;
+        }
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + i * 32;
+            if (v < V) {
+                float g[8], b[8], o[8];
+                const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8);
+                const float4 g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+                g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - m) * r * g[j] + b[j];
+                store8(y + row * ldy + v * 8, o);
+            }
+        }
+    }
+}
+
+// dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)); dgamma += sum dy*xhat; dbeta += sum dy
+template <int MAXV>
+__global__ void ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ x, long long ldx,
+                              bf16* __restrict__ dx, long long lddx, const float* __restrict__ gamma,
+                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C) {
+    extern __shared__ float sm[];  // dgamma[C], dbeta[C] block accumulators
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int V = C / 8;
+    float ag[MAXV][8], ab[MAXV][8];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
+    for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); row < rows;
+         row += static_cast<long long>(gridDim.x) * warps_per_block) {
+        const float m = mean[row], r = rstd[row];
+        float xh[MAXV][8], gd[MAXV][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + i * 32;
+            if (v < V) {
+                float d[8];
+                load8(x + row * ldx + v * 8, xh[i]);
+                load8(dy + row * lddy + v * 8, d);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xh[i][j] = (xh[i][j] - m) * r;
+                    ag[i][j] += d[j] * xh[i][j];
+                    ab[i][j] += d[j];
+                    gd[i][j] = d[j] * __ldg(gamma + v * 8 + j);
+                    s1 += gd[i][j];
+                    s2 += gd[i][j] * xh[i][j];
+                }
+            }
+        }
+        s1 = warp_sum(s1) / C;
+        s2 = warp_sum(s2) / C;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + i * 32;
+            if (v < V) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = r * (gd[i][j] - s1 - xh[i][j] * s2);
+                store8(dx + row * lddx + v * 8, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < V) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                atomicAdd(&sm[v * 8 + j], ag[i][j]);
+                atomicAdd(&sm[C + v * 8 + j], ab[i][j]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(dgamma + c, sm[c]);
+        atomicAdd(dbeta + c, sm[C + c]);
+    }
+}
+
+}  // namespace
+}  // namespace nk
+
+using namespace nk;
+
+extern "C" {
+
+int64_t nk_groupnorm_workspace_bytes(int nimg, int HW, int C, int G) {
+    if (C <= 0 || C % 8 != 0 || G <= 0) return -1;
+    const GnPlan p = gn_plan(nimg, HW, C);
+    // forward: partial float2 [nimg, chunks, G];  backward: partial float2 [nimg, chunks, C] + chan [nimg, C] + coef [nimg, G]
+    const int64_t fwd = static_cast<int64_t>(nimg) * p.chunks * G * 8;
+    const int64_t bwd = static_cast<int64_t>(nimg) * p.chunks * C * 8 + static_cast<int64_t>(nimg) * C * 8 +
+                        static_cast<int64_t>(nimg) * G * 8;
+    return std::max(fwd, bwd) + 256;
+}
+
+int nk_groupnorm_fwd(const void* x, int64_t x_pix_stride, const float* gamma, const float* beta, void* y,
+                     int64_t y_pix_stride, float* mean, float* rstd, void* workspace, int64_t workspace_bytes,
+                     int nimg, int HW, int C, int G, float eps, int silu, nk_stream_t stream) {
+    NK_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 4096, NK_ERR_SHAPE, "groupnorm: C=%d G=%d", C, G);
+    NK_REQUIRE(x_pix_stride % 8 == 0 && y_pix_stride % 8 == 0, NK_ERR_SHAPE, "groupnorm: strides must be multiples of 8");
+    NK_REQUIRE(workspace_bytes >= nk_groupnorm_workspace_bytes(nimg, HW, C, G), NK_ERR_WORKSPACE, "groupnorm workspace");
+    const GnPlan p = gn_plan(nimg, HW, C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float2* partial = static_cast<float2*>(workspace);
+    gn_stats_kernel<<<dim3(p.chunks, nimg), p.threads, 2 * C * sizeof(float), st>>>(
+        static_cast<const bf16*>(x), x_pix_stride, partial, HW, C, G, p.V, p.ppb, p.pix_per_chunk);
+    gn_finalize_kernel<<<nimg, ((G + 31) / 32) * 32, 0, st>>>(partial, mean, rstd, p.chunks, G,
+                                                             1.f / (static_cast<float>(HW) * (C / G)), eps);
+    gn_apply_kernel<<<dim3(p.chunks, nimg), p.threads, 2 * C * sizeof(float), st>>>(
+        static_cast<const bf16*>(x), x_pix_stride, static_cast<bf16*>(y), y_pix_stride, gamma, beta, mean, rstd, HW,
+        C, G, p.V, p.ppb, p.pix_per_chunk, silu);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_groupnorm_bwd(const void* dy, int64_t dy_pix_stride, const void* x, int64_t x_pix_stride,
+                     const float* gamma, const float* beta, const float* mean, const float* rstd, void* dx,
+                     int64_t dx_pix_stride, float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
+                     int nimg, int HW, int C, int G, int silu, nk_stream_t stream) {
+    NK_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 4096, NK_ERR_SHAPE, "groupnorm: C=%d G=%d", C, G);
+    NK_REQUIRE(workspace_bytes >= nk_groupnorm_workspace_bytes(nimg, HW, C, G), NK_ERR_WORKSPACE, "groupnorm workspace");
+    const GnPlan p = gn_plan(nimg, HW, C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float2* partial = static_cast<float2*>(workspace);
+    float2* chan = partial + static_cast<size_t>(nimg) * p.chunks * C;
+    float2* coef = chan + static_cast<size_t>(nimg) * C;
+    gn_bwd_stats_kernel<<<dim3(p.chunks, nimg), p.threads, 2 * C * sizeof(float), st>>>(
+        static_cast<const bf16*>(dy), dy_pix_stride, static_cast<const bf16*>(x), x_pix_stride, gamma, beta, mean,
+        rstd, partial, HW, C, G, p.V, p.ppb, p.pix_per_chunk, silu);
+    gn_bwd_finalize_kernel<<<nimg, 256, 2 * C * sizeof(float), st>>>(partial, gamma, chan, coef, p.chunks, C, G);
+    if (dgamma && dbeta) gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, st>>>(chan, dgamma, dbeta, nimg, C);
+    gn_bwd_apply_kernel<<<dim3(p.chunks, nimg), p.threads, 0, st>>>(
+        static_cast<const bf16*>(dy), dy_pix_stride, static_cast<const bf16*>(x), x_pix_stride,
+        static_cast<bf16*>(dx), dx_pix_stride, gamma, beta, mean, rstd, coef, HW, C, G, p.V, p.ppb, p.pix_per_chunk,
+        silu, 1.f / (static_cast<float>(HW) * (C / G)));
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
+                     float* mean, float* rstd, int rows, int C, float eps, nk_stream_t stream) {
+    NK_REQUIRE(C % 8 == 0 && C <= 2560, NK_ERR_SHAPE, "layernorm: C=%d", C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int wpb = 8;
+    const int grid = static_cast<int>(std::min<long long>((rows + wpb - 1) / wpb, 148LL * 8));
+    const int V = C / 8;
+    if (V <= 64)
+        ln_fwd_kernel<2><<<grid, wpb * 32, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, gamma,
+                                                    beta, mean, rstd, rows, C, eps);
+    else if (V <= 160)
+        ln_fwd_kernel<5><<<grid, wpb * 32, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, gamma,
+                                                    beta, mean, rstd, rows, C, eps);
+    else
+        ln_fwd_kernel<10><<<grid, wpb * 32, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy,
+                                                     gamma, beta, mean, rstd, rows, C, eps);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
+                     const float* mean, const float* rstd, void* dx, int64_t lddx, float* dgamma, float* dbeta,
+                     int rows, int C, nk_stream_t stream) {
+    NK_REQUIRE(C % 8 == 0 && C <= 1280, NK_ERR_SHAPE, "layernorm bwd: C=%d", C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int wpb = 8;
+    const int grid = static_cast<int>(std::min<long long>((rows + wpb - 1) / wpb, 148LL * 2));
+    const int V = C / 8;
+    const size_t smem = 2 * C * sizeof(float);
+    if (V <= 64)
+        ln_bwd_kernel<2><<<grid, wpb * 32, smem, st>>>(static_cast<const bf16*>(dy), lddy, static_cast<const bf16*>(x),
+                                                       ldx, static_cast<bf16*>(dx), lddx, gamma, mean, rstd, dgamma,
+                                                       dbeta, rows, C);
+    else
+        ln_bwd_kernel<5><<<grid, wpb * 32, smem, st>>>(static_cast<const bf16*>(dy), lddy, static_cast<const bf16*>(x),
+                                                       ldx, static_cast<bf16*>(dx), lddx, gamma, mean, rstd, dgamma,
+                                                       dbeta, rows, C);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+
+}  // extern "C"
