@@ -109,6 +109,97 @@ int nk_conv2d_wgrad(const void* dy, int64_t dy_pix_stride, const void* x, int64_
                     float* dw_packed, int nimg, int H, int W, int Cin, int Cout, int ksize,
                     nk_stream_t stream);
 
+/* Fused flash-style attention forward (tcgen05/TMEM), head_dim 64, no mask/dropout.
+ * q,k,v: bf16 [B, N, H, 64] addressed by (batch_stride, row_stride, head offset h*64); they may be
+ * column slices of a wider projection output.  o: bf16 [B, Nq, H, 64]; lse: fp32 [B, H, Nq] or NULL.
+ * Replaces F.scaled_dot_product_attention / xformers memory_efficient_attention at
+ * modules/attention.py:346-352,410-412. */
+int nk_attention_fwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride, const void* k,
+                     int64_t k_row_stride, int64_t k_batch_stride, const void* v, int64_t v_row_stride,
+                     int64_t v_batch_stride, void* o, int64_t o_row_stride, int64_t o_batch_stride,
+                     float* lse, int B, int H, int Nq, int Nk, int head_dim, float scale, nk_stream_t stream);
+/* delta[b,h,q] = sum_d dO*O on [B,N,H,D] tensors (attention backward). */
+int nk_attn_delta(const void* dO, const void* O, float* delta, int B, int N, int H, int D, nk_stream_t stream);
+/* P = softmax(scale*S) row-wise (S fp32 [rows, lds], P bf16), lse optional — materialised attention path
+ * for head dims the fused kernel does not cover (SD1.5 d=40/80/160, VAE d=512: model.py:155-166). */
+int nk_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp, float* lse, int64_t rows, int N, float scale,
+                    nk_stream_t stream);
+
+/* ---- normalisation (HBM-bound) --------------------------------------------------------------- */
+/* GroupNorm (+ optional fused SiLU) on NHWC bf16; mean/rstd fp32 [nimg*G] are outputs of fwd and inputs of bwd.
+ * Replaces nn.GroupNorm(32,C)+nn.SiLU: modules/diffusion/openaimodel.py:247-249,281-283,798 (eps 1e-5);
+ * modules/attention.py:612 and modules/layers.py:5-7 (eps 1e-6). */
+int64_t nk_groupnorm_workspace_bytes(int nimg, int HW, int C, int G);
+int nk_groupnorm_fwd(const void* x, int64_t x_pix_stride, const float* gamma, const float* beta, void* y,
+                     int64_t y_pix_stride, float* mean, float* rstd, void* workspace, int64_t workspace_bytes,
+                     int nimg, int HW, int C, int G, float eps, int silu, nk_stream_t stream);
+/* dgamma/dbeta (fp32 [C]) are accumulated into (+=); pass NULL to skip. */
+int nk_groupnorm_bwd(const void* dy, int64_t dy_pix_stride, const void* x, int64_t x_pix_stride,
+                     const float* gamma, const float* beta, const float* mean, const float* rstd, void* dx,
+                     int64_t dx_pix_stride, float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
+                     int nimg, int HW, int C, int G, int silu, nk_stream_t stream);
+/* LayerNorm over the last dim of [rows, C] bf16.  Replaces nn.LayerNorm: modules/attention.py:468-470. */
+int nk_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
+                     float* mean, float* rstd, int rows, int C, float eps, nk_stream_t stream);
+/* dgamma/dbeta fp32 [C] accumulated with atomics (+=). */
+int nk_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
+                     const float* mean, const float* rstd, void* dx, int64_t lddx, float* dgamma, float* dbeta,
+                     int rows, int C, nk_stream_t stream);
+
+/* ---- elementwise / layout (HBM-bound) --------------------------------------------------------- */
+/* GEGLU: h = [value | gate] (bf16 [M, 2D]); out = value * gelu_erf(gate).  modules/attention.py:50-57 */
+int nk_geglu_fwd(const void* h, int64_t ldh, void* out, int64_t ldo, int64_t M, int D, nk_stream_t stream);
+int nk_geglu_bwd(const void* h, int64_t ldh, const void* dout, int64_t ldo, void* dh, int64_t lddh, int64_t M, int D,
+                 nk_stream_t stream);
+int nk_silu_fwd(const void* x, void* y, int64_t n, nk_stream_t stream);
+int nk_silu_bwd(const void* x, const void* dy, void* dx, int64_t n, nk_stream_t stream);
+int nk_add(const void* a, const void* b, void* y, int64_t n, nk_stream_t stream);
+int nk_cast_f32_bf16(const float* x, void* y, int64_t n, nk_stream_t stream);
+int nk_cast_bf16_f32(const void* x, float* y, int64_t n, int accumulate, nk_stream_t stream);
+/* copy C channels of every pixel between NHWC buffers with different pixel strides (skip concat / split:
+ * modules/diffusion/openaimodel.py:836) */
+int nk_copy_channels(const void* src, int64_t src_stride, void* dst, int64_t dst_stride, int64_t npix, int C,
+                     nk_stream_t stream);
+/* nearest-neighbour 2x upsampling, NHWC (modules/diffusion/openaimodel.py:140) and its adjoint */
+int nk_upsample2x_fwd(const void* x, void* y, int nimg, int H, int W, int C, nk_stream_t stream);
+int nk_upsample2x_bwd(const void* dy, void* dx, int nimg, int H, int W, int C, nk_stream_t stream);
+/* NCHW (fp32|bf16) -> NHWC bf16 with zero channel padding to Cpad and optional per-image scale; and back */
+int nk_nchw_to_nhwc(const void* src, int src_is_f32, void* dst, const float* scale, int nimg, int C, int HW, int Cpad,
+                    nk_stream_t stream);
+int nk_nhwc_to_nchw(const void* src, int64_t src_stride, void* dst, int dst_is_f32, int nimg, int C, int HW,
+                    nk_stream_t stream);
+/* explicit im2col / col2im for the stride-2 convolutions (openaimodel.py:183-190; VAE model.py:65-82 with
+ * pad (0,1,0,1) expressed as pad_t = pad_l = 0) */
+int nk_im2col(const void* x, int64_t x_stride, void* col, int nimg, int H, int W, int C, int ks, int stride, int pad_t,
+              int pad_l, int Ho, int Wo, nk_stream_t stream);
+int nk_col2im(const void* dcol, void* dx, int nimg, int H, int W, int C, int ks, int stride, int pad_t, int pad_l,
+              int Ho, int Wo, nk_stream_t stream);
+/* out[g, c] (=|+=) sum over the rows of group g of x[rows, C] (bias / timestep-embedding gradients) */
+int nk_colsum(const void* x, int64_t ldx, float* out, int groups, int rows_per_group, int C, int accumulate,
+              nk_stream_t stream);
+/* sinusoidal embedding cos|sin (modules/diffusion/util.py:152-177); t fp32 [B], out bf16 [B, dim] */
+int nk_timestep_embedding(const float* t, void* out, int B, int dim, float max_period, nk_stream_t stream);
+/* fp32 OIHW conv weight -> packed bf16 forward [CoP, taps*CiP] and data-gradient [CiP, taps*CoP] operands */
+int nk_conv_pack_weights(const float* w, void* wp_fwd, void* wp_dgrad, int Co, int Ci, int ks, int CoP, int CiP,
+                         nk_stream_t stream);
+/* packed fp32 weight gradient [Co, taps, CiP] -> OIHW fp32 (=|+=) */
+int nk_conv_unpack_wgrad(const float* dw_packed, float* dw, int Co, int Ci, int ks, int CiP, int accumulate,
+                         nk_stream_t stream);
+
+/* ---- diffusion objective (modules/diffusion/loss.py:117-155, denoiser.py:40-57) --------------- */
+int nk_noise_mix(const float* x, const float* noise, const float* sigma, float* z, int B, int64_t per_sample,
+                 int rectified_flow, nk_stream_t stream);
+/* y[b,:] = s[b] * x[b,:]  (c_in scaling of the network input, denoiser.py:49) */
+int nk_scale_per_sample(const float* x, const float* s, float* y, int B, int64_t per_sample, nk_stream_t stream);
+/* out[b,:] = a[b]*x[b,:] + c[b]*y[b,:] (y may be NULL): D = F*c_out + z_t*c_skip, denoiser.py:53 */
+int nk_lincomb_per_sample(const float* x, const float* a, const float* y, const float* c, float* out, int B,
+                          int64_t per_sample, nk_stream_t stream);
+/* loss[b] = w[b] * mean((D[b]-T[b])^2) and its gradient w.r.t. D */
+int nk_weighted_mse_fwd(const float* D, const float* T, const float* w, float* loss, int B, int64_t per_sample,
+                        nk_stream_t stream);
+int nk_weighted_mse_bwd(const float* D, const float* T, const float* w, const float* dloss, float* dD, int B,
+                        int64_t per_sample, nk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

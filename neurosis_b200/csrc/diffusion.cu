@@ -1,0 +1,126 @@
+// Noise mixing, denoiser preconditioning and the per-sample weighted MSE of the diffusion loss.
+// Tiny tensors (C*H*W = 65 536 per SDXL latent) — these kernels exist to remove a dozen
+// launch-bound ATen kernels and to emit the UNet input directly in its NHWC bf16 layout.
+//
+// Reference (under /root/reference/src/neurosis/modules/diffusion):
+//   loss.py:117-146       sigma draw, noise mix  z_t = x + sigma*n   (edm)  /  (1-sigma) x + sigma n  (rf)
+//   denoiser.py:40-57     c_in scaling of the network input, D = F*c_out + z_t*c_skip (nk_lincomb_per_sample)
+//   loss.py:153-155 + ../losses/functions.py:81-94   loss[b] = mean((D - target)^2) * w[b]  (fp32)
+#include "common.cuh"
+
+namespace nk {
+namespace {
+
+// z[b, i] = a_b * x[b, i] + sigma_b * noise[b, i];  a_b = 1 (edm) or 1 - sigma_b (rf)
+__global__ void noise_mix_kernel(const float* __restrict__ x, const float* __restrict__ noise,
+                                 const float* __restrict__ sigma, float* __restrict__ z, long long per_sample,
+                                 long long total, int rf) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float s = sigma[i / per_sample];
+        const float a = rf ? 1.f - s : 1.f;
+        z[i] = a * x[i] + s * noise[i];
+    }
+}
+
+// y[b, i] = s[b] * x[b, i]
+__global__ void scale_per_sample_kernel(const float* __restrict__ x, const float* __restrict__ s, float* __restrict__ y,
+                                        long long per_sample, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        y[i] = x[i] * s[i / per_sample];
+}
+
+// out[b, i] = a[b] * x[b, i] + c[b] * y[b, i]   (y may be null)
+__global__ void lincomb_per_sample_kernel(const float* __restrict__ x, const float* __restrict__ a,
+                                          const float* __restrict__ y, const float* __restrict__ c,
+                                          float* __restrict__ out, long long per_sample, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / per_sample;
+        float v = a[b] * x[i];
+        if (y) v += c[b] * y[i];
+        out[i] = v;
+    }
+}
+
+// loss[b] = w[b] * mean_i (D[b,i] - T[b,i])^2 ; one block per sample, fixed-order reduction
+__global__ void weighted_mse_fwd_kernel(const float* __restrict__ D, const float* __restrict__ T,
+                                        const float* __restrict__ w, float* __restrict__ loss, long long n) {
+    const int b = blockIdx.x;
+    const float* d = D + b * n;
+    const float* t = T + b * n;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float e = d[i] - t[i];
+        acc += e * e;
+    }
+    __shared__ float red[32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) loss[b] = v / static_cast<float>(n) * w[b];
+    }
+}
+// dD[b,i] = dloss[b] * w[b] * 2/n * (D - T)
+__global__ void weighted_mse_bwd_kernel(const float* __restrict__ D, const float* __restrict__ T,
+                                        const float* __restrict__ w, const float* __restrict__ dloss,
+                                        float* __restrict__ dD, long long n, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / n;
+        dD[i] = dloss[b] * w[b] * (2.f / static_cast<float>(n)) * (D[i] - T[i]);
+    }
+}
+
+inline int grid_for(long long work, int block) {
+    const long long g = (work + block - 1) / block;
+    return static_cast<int>(std::max<long long>(1, std::min<long long>(g, 148LL * 8)));
+}
+
+}  // namespace
+}  // namespace nk
+
+using namespace nk;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int nk_noise_mix(const float* x, const float* noise, const float* sigma, float* z, int B, int64_t per_sample,
+                 int rectified_flow, nk_stream_t stream) {
+    const long long total = static_cast<long long>(B) * per_sample;
+    noise_mix_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(x, noise, sigma, z, per_sample, total, rectified_flow);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_scale_per_sample(const float* x, const float* s, float* y, int B, int64_t per_sample, nk_stream_t stream) {
+    const long long total = static_cast<long long>(B) * per_sample;
+    scale_per_sample_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(x, s, y, per_sample, total);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_lincomb_per_sample(const float* x, const float* a, const float* y, const float* c, float* out, int B,
+                          int64_t per_sample, nk_stream_t stream) {
+    const long long total = static_cast<long long>(B) * per_sample;
+    lincomb_per_sample_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(x, a, y, c, out, per_sample, total);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_weighted_mse_fwd(const float* D, const float* T, const float* w, float* loss, int B, int64_t per_sample,
+                        nk_stream_t stream) {
+    weighted_mse_fwd_kernel<<<B, 1024, 0, ST(stream)>>>(D, T, w, loss, per_sample);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_weighted_mse_bwd(const float* D, const float* T, const float* w, const float* dloss, float* dD, int B,
+                        int64_t per_sample, nk_stream_t stream) {
+    const long long total = static_cast<long long>(B) * per_sample;
+    weighted_mse_bwd_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(D, T, w, dloss, dD, per_sample, total);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,605 @@
+// Bandwidth-bound helper kernels of the diffusion training step: GEGLU, SiLU, adds, layout
+// conversion, nearest upsampling, channel concat/split, im2col for the strided / thin convs,
+// column sums (bias gradients), weight packing, row softmax.  All 128-bit vectorised where the
+// layout allows; fp32 math, bf16 storage.
+//
+// Reference call sites (under /root/reference/src/neurosis):
+//   GEGLU                       modules/attention.py:50-57 (x * F.gelu(gate), exact erf GELU)
+//   nn.SiLU on embeddings       modules/diffusion/openaimodel.py:273-279,586-590
+//   F.interpolate nearest 2x    modules/diffusion/openaimodel.py:140
+//   torch.cat skip concat       modules/diffusion/openaimodel.py:836
+//   rearrange NCHW<->(HW)C      modules/attention.py:655,664
+//   timestep_embedding          modules/diffusion/util.py:152-177
+//   Downsample conv s2          modules/diffusion/openaimodel.py:183-190 ; model.py:65-82 (pad (0,1,0,1))
+#include "common.cuh"
+
+namespace nk {
+namespace {
+
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]);
+    q.y = pack_bf16x2(v[2], v[3]);
+    q.z = pack_bf16x2(v[4], v[5]);
+    q.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = q;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+    const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// ---- GEGLU ----------------------------------------------------------------------------------
+// h: [M, 2D] = (value | gate); out[m, d] = value * gelu(gate)
+__global__ void geglu_fwd_kernel(const bf16* __restrict__ h, long long ldh, bf16* __restrict__ out, long long ldo,
+                                 long long M, int D) {
+    const int V = D / 8;
+    const long long total = M * V;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long m = i / V;
+        const int v = static_cast<int>(i - m * V);
+        float a[8], g[8];
+        ld8(h + m * ldh + v * 8, a);
+        ld8(h + m * ldh + D + v * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] *= gelu_erf(g[j]);
+        st8(out + m * ldo + v * 8, a);
+    }
+}
+// dh[m, :D] = dout * gelu(gate);  dh[m, D:] = dout * value * gelu'(gate)
+__global__ void geglu_bwd_kernel(const bf16* __restrict__ h, long long ldh, const bf16* __restrict__ dout,
+                                 long long ldo, bf16* __restrict__ dh, long long lddh, long long M, int D) {
+    const int V = D / 8;
+    const long long total = M * V;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long m = i / V;
+        const int v = static_cast<int>(i - m * V);
+        float a[8], g[8], d[8], da[8], dg[8];
+        ld8(h + m * ldh + v * 8, a);
+        ld8(h + m * ldh + D + v * 8, g);
+        ld8(dout + m * ldo + v * 8, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            da[j] = d[j] * gelu_erf(g[j]);
+            dg[j] = d[j] * a[j] * dgelu_erf(g[j]);
+        }
+        st8(dh + m * lddh + v * 8, da);
+        st8(dh + m * lddh + D + v * 8, dg);
+    }
+}
+
+// ---- small elementwise ------------------------------------------------------------------------
+enum { EW_SILU = 0, EW_SILU_BWD = 1, EW_ADD = 2, EW_SCALE_ADD = 3 };
+// y = op(a, b): SILU: silu(a); SILU_BWD: b * silu'(a); ADD: a + b; SCALE_ADD: a + alpha*b
+__global__ void ew_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ y, long long n,
+                          int op, float alpha) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float x = __bfloat162float(a[i]);
+        float r;
+        if (op == EW_SILU) {
+            r = x / (1.f + __expf(-x));
+        } else if (op == EW_SILU_BWD) {
+            const float s = 1.f / (1.f + __expf(-x));
+            r = __bfloat162float(b[i]) * s * (1.f + x * (1.f - s));
+        } else if (op == EW_ADD) {
+            r = x + __bfloat162float(b[i]);
+        } else {
+            r = x + alpha * __bfloat162float(b[i]);
+        }
+        y[i] = __float2bfloat16(r);
+    }
+}
+__global__ void ew_vec_add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ y,
+                                  long long nvec) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float x[8], z[8];
+        ld8(a + i * 8, x);
+        ld8(b + i * 8, z);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += z[j];
+        st8(y + i * 8, x);
+    }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        y[i] = __float2bfloat16(x[i]);
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n, int accumulate) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float v = __bfloat162float(x[i]);
+        y[i] = accumulate ? y[i] + v : v;
+    }
+}
+
+// ---- channel-slice copy (concat / split of NHWC tensors) -------------------------------------
+__global__ void copy_channels_kernel(const bf16* __restrict__ src, long long src_stride, bf16* __restrict__ dst,
+                                     long long dst_stride, long long npix, int C) {
+    const int V = C / 8;
+    const long long total = npix * V;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long p = i / V;
+        const int v = static_cast<int>(i - p * V);
+        *reinterpret_cast<uint4*>(dst + p * dst_stride + v * 8) =
+            *reinterpret_cast<const uint4*>(src + p * src_stride + v * 8);
+    }
+}
+
+// ---- nearest 2x upsample ------------------------------------------------------------------------
+__global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int nimg, int H, int W, int C) {
+    const int V = C / 8;
+    const long long total = static_cast<long long>(nimg) * (2 * H) * (2 * W) * V;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(i % V);
+        long long p = i / V;
+        const int ow = static_cast<int>(p % (2 * W));
+        p /= (2 * W);
+        const int oh = static_cast<int>(p % (2 * H));
+        const int n = static_cast<int>(p / (2 * H));
+        const long long src = ((static_cast<long long>(n) * H + (oh >> 1)) * W + (ow >> 1)) * C + v * 8;
+        *reinterpret_cast<uint4*>(y + i * 8) = *reinterpret_cast<const uint4*>(x + src);
+    }
+}
+__global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int nimg, int H, int W, int C) {
+    const int V = C / 8;
+    const long long total = static_cast<long long>(nimg) * H * W * V;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(i % V);
+        long long p = i / V;
+        const int w = static_cast<int>(p % W);
+        p /= W;
+        const int h = static_cast<int>(p % H);
+        const int n = static_cast<int>(p / H);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                float f[8];
+                ld8(dy + ((static_cast<long long>(n) * 2 * H + 2 * h + a) * (2 * W) + 2 * w + b) * C + v * 8, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+        st8(dx + i * 8, acc);
+    }
+}
+
+// ---- layout conversion --------------------------------------------------------------------------
+// src NCHW (fp32 or bf16), dst NHWC bf16 with Cpad >= C channels (extra channels zero), value scaled
+// per image by scale[n] (nullptr = 1)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, bf16* __restrict__ dst, const float* __restrict__ scale,
+                                    int nimg, int C, int HW, int Cpad) {
+    const long long total = static_cast<long long>(nimg) * HW * Cpad;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % Cpad);
+        const long long p = i / Cpad;
+        const int hw = static_cast<int>(p % HW);
+        const int n = static_cast<int>(p / HW);
+        float v = 0.f;
+        if (c < C) {
+            v = static_cast<float>(src[(static_cast<long long>(n) * C + c) * HW + hw]);
+            if (scale) v *= scale[n];
+        }
+        dst[i] = __float2bfloat16(v);
+    }
+}
+// src NHWC bf16 (pixel stride), dst NCHW (fp32 or bf16), first C channels
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, long long src_stride, T* __restrict__ dst, int nimg,
+                                    int C, int HW) {
+    const long long total = static_cast<long long>(nimg) * C * HW;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int hw = static_cast<int>(i % HW);
+        const long long q = i / HW;
+        const int c = static_cast<int>(q % C);
+        const int n = static_cast<int>(q / C);
+        dst[i] = static_cast<T>(__bfloat162float(src[(static_cast<long long>(n) * HW + hw) * src_stride + c]));
+    }
+}
+
+// ---- im2col / col2im for strided convs ------------------------------------------------------------
+// col[(n,oh,ow), tap*C + c] = x[n, oh*stride + ky - pad_t, ow*stride + kx - pad_l, c] (0 outside)
+__global__ void im2col_kernel(const bf16* __restrict__ x, long long x_stride, bf16* __restrict__ col, int nimg, int H,
+                              int W, int C, int ks, int stride, int pad_t, int pad_l, int Ho, int Wo) {
+    const int V = C / 8;
+    const long long total = static_cast<long long>(nimg) * Ho * Wo * ks * ks * V;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(i % V);
+        long long q = i / V;
+        const int tap = static_cast<int>(q % (ks * ks));
+        q /= (ks * ks);
+        const int ow = static_cast<int>(q % Wo);
+        q /= Wo;
+        const int oh = static_cast<int>(q % Ho);
+        const int n = static_cast<int>(q / Ho);
+        const int h = oh * stride + tap / ks - pad_t;
+        const int w = ow * stride + tap % ks - pad_l;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (h >= 0 && h < H && w >= 0 && w < W)
+            val = *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(n) * H + h) * W + w) * x_stride + v * 8);
+        *reinterpret_cast<uint4*>(col + i * 8) = val;
+    }
+}
+// dx[n,h,w,c] = sum over (oh,ow,tap) that read (h,w):  gather form, no atomics
+__global__ void col2im_kernel(const bf16* __restrict__ dcol, bf16* __restrict__ dx, int nimg, int H, int W, int C,
+                              int ks, int stride, int pad_t, int pad_l, int Ho, int Wo) {
+    const int V = C / 8;
+    const long long total = static_cast<long long>(nimg) * H * W * V;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(i % V);
+        long long q = i / V;
+        const int w = static_cast<int>(q % W);
+        q /= W;
+        const int h = static_cast<int>(q % H);
+        const int n = static_cast<int>(q / H);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int ky = 0; ky < ks; ++ky) {
+            const int th = h + pad_t - ky;
+            if (th < 0 || th % stride != 0) continue;
+            const int oh = th / stride;
+            if (oh >= Ho) continue;
+            for (int kx = 0; kx < ks; ++kx) {
+                const int tw = w + pad_l - kx;
+                if (tw < 0 || tw % stride != 0) continue;
+                const int ow = tw / stride;
+                if (ow >= Wo) continue;
+                float f[8];
+                ld8(dcol + (((static_cast<long long>(n) * Ho + oh) * Wo + ow) * (ks * ks) + ky * ks + kx) * C + v * 8, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+        }
+        st8(dx + i * 8, acc);
+    }
+}
+
+// ---- column sums: out[g, c] (+)= sum_{r < rows_per_group} x[g*rows_per_group + r, c] -------------
+__global__ void colsum_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, int rows_per_group,
+                              int C, int row_chunks, int accumulate_atomic) {
+    // grid (ceil(C/64), row_chunks, groups); block (64 columns-pairs... ) 256 threads = 32 col-pairs x 8 row lanes
+    const int g = blockIdx.z;
+    const int cpair = blockIdx.x * 32 + (threadIdx.x & 31);  // handles columns 2*cpair, 2*cpair+1
+    const int rl = threadIdx.x >> 5;                         // 0..7
+    const int rows_per_chunk = (rows_per_group + row_chunks - 1) / row_chunks;
+    const int r0 = blockIdx.y * rows_per_chunk;
+    const int r1 = min(rows_per_group, r0 + rows_per_chunk);
+    float a0 = 0.f, a1 = 0.f;
+    if (2 * cpair < C) {
+        const bf16* base = x + (static_cast<long long>(g) * rows_per_group) * ldx + 2 * cpair;
+        for (int r = r0 + rl; r < r1; r += 8) {
+            const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + r * ldx));
+            a0 += f.x;
+            a1 += f.y;
+        }
+    }
+    __shared__ float s0[8][33], s1[8][33];
+    s0[rl][threadIdx.x & 31] = a0;
+    s1[rl][threadIdx.x & 31] = a1;
+    __syncthreads();
+    if (rl == 0 && 2 * cpair < C) {
+        for (int k = 1; k < 8; ++k) {
+            a0 += s0[k][threadIdx.x & 31];
+            a1 += s1[k][threadIdx.x & 31];
+        }
+        float* o = out + static_cast<long long>(g) * C + 2 * cpair;
+        if (accumulate_atomic) {
+            atomicAdd(o, a0);
+            atomicAdd(o + 1, a1);
+        } else {
+            o[0] = a0;
+            o[1] = a1;
+        }
+    }
+}
+
+// ---- sinusoidal timestep embedding: out[b, :] = cos(t*f) | sin(t*f), f_i = exp(-ln(P) i/half) -------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, bf16* __restrict__ out, int B, int dim,
+                                          float max_period) {
+    const int half = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, k = i - b * half;
+    const float freq = expf(-logf(max_period) * static_cast<float>(k) / static_cast<float>(half));
+    const float arg = t[b] * freq;
+    out[static_cast<long long>(b) * dim + k] = __float2bfloat16(cosf(arg));
+    out[static_cast<long long>(b) * dim + half + k] = __float2bfloat16(sinf(arg));
+    if ((dim & 1) && k == 0) out[static_cast<long long>(b) * dim + dim - 1] = __float2bfloat16(0.f);
+}
+
+// ---- conv weight packing ------------------------------------------------------------------------------
+// w: fp32 OIHW [Co, Ci, ks, ks].
+// fwd  : wp[co, tap*CiP + ci]            (co < CoP rows, zero padded)      tap = ky*ks + kx
+// dgrad: wd[ci, tapf*CoP + co]           (ci < CiP rows, zero padded)      tapf = (ks-1-ky)*ks + (ks-1-kx)
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, bf16* __restrict__ wp, bf16* __restrict__ wd,
+                                        int Co, int Ci, int ks, int CoP, int CiP) {
+    const int taps = ks * ks;
+    const long long total = static_cast<long long>(CoP) * taps * CiP;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % CiP);
+        long long q = i / CiP;
+        const int tap = static_cast<int>(q % taps);
+        const int co = static_cast<int>(q / taps);
+        float v = 0.f;
+        if (co < Co && ci < Ci) v = w[((static_cast<long long>(co) * Ci + ci) * taps) + tap];
+        const bf16 bv = __float2bfloat16(v);
+        if (wp) wp[i] = bv;
+        if (wd) wd[(static_cast<long long>(ci) * taps + (taps - 1 - tap)) * CoP + co] = bv;
+    }
+}
+// dw[co, ci, ky, kx] += dwp[co, tap, ci]   (dwp row stride = taps*CiP)
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int ks,
+                                         int CiP, int accumulate) {
+    const int taps = ks * ks;
+    const long long total = static_cast<long long>(Co) * Ci * taps;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int tap = static_cast<int>(i % taps);
+        long long q = i / taps;
+        const int ci = static_cast<int>(q % Ci);
+        const int co = static_cast<int>(q / Ci);
+        const float v = dwp[(static_cast<long long>(co) * taps + tap) * CiP + ci];
+        dw[i] = accumulate ? dw[i] + v : v;
+    }
+}
+
+// ---- row softmax for the materialised attention path -------------------------------------------------
+// S fp32 [rows, ld] -> P bf16 [rows, ldp] = softmax(scale * S[:, :N]) ; lse[row] = log-sum-exp (natural log)
+__global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, bf16* __restrict__ P, long long ldp,
+                                    float* __restrict__ lse, long long rows, int N, float scale) {
+    const long long row = blockIdx.x;
+    if (row >= rows) return;
+    const float* s = S + row * lds;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) mx = fmaxf(mx, s[i]);
+    __shared__ float red[32];
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+        v = warp_max(v);
+        if (threadIdx.x == 0) red[0] = v;
+    }
+    __syncthreads();
+    mx = red[0];
+    __syncthreads();
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sum += __expf((s[i] - mx) * scale);
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) red[0] = v;
+    }
+    __syncthreads();
+    sum = red[0];
+    const float inv = 1.f / sum;
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        P[row * ldp + i] = __float2bfloat16(__expf((s[i] - mx) * scale) * inv);
+    if (threadIdx.x == 0 && lse) lse[row] = mx * scale + logf(sum);
+}
+
+// delta[b, h, q] = sum_d dO[b,q,h,d] * O[b,q,h,d]     (tensors laid out [B, N, H, D])
+__global__ void attn_delta_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ O, float* __restrict__ delta,
+                                  int B, int N, int H, int D) {
+    const long long total = static_cast<long long>(B) * N * H;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x >> 3) + (threadIdx.x >> 3);  // 8 lanes per row
+    const int sub = threadIdx.x & 7;
+    float acc = 0.f;
+    if (idx < total) {
+        const bf16* a = dO + idx * D;
+        const bf16* b = O + idx * D;
+        for (int d = sub * 8; d < D; d += 64) {
+            float x[8], y[8];
+            ld8(a + d, x);
+            ld8(b + d, y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += x[j] * y[j];
+        }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (idx < total && sub == 0) {
+        const int h = static_cast<int>(idx % H);
+        const long long bn = idx / H;
+        const int q = static_cast<int>(bn % N);
+        const int b = static_cast<int>(bn / N);
+        delta[(static_cast<long long>(b) * H + h) * N + q] = acc;
+    }
+}
+
+inline int grid_for(long long work, int block) {
+    const long long g = (work + block - 1) / block;
+    return static_cast<int>(std::max<long long>(1, std::min<long long>(g, 148LL * 16)));
+}
+
+}  // namespace
+}  // namespace nk
+
+using namespace nk;
+#define ST(s) static_cast<cudaStream_t>(s)
+#define BF(p) static_cast<bf16*>(p)
+#define CBF(p) static_cast<const bf16*>(p)
+
+extern "C" {
+
+int nk_geglu_fwd(const void* h, int64_t ldh, void* out, int64_t ldo, int64_t M, int D, nk_stream_t stream) {
+    NK_REQUIRE(D % 8 == 0 && ldh % 8 == 0 && ldo % 8 == 0, NK_ERR_SHAPE, "geglu: D=%d", D);
+    geglu_fwd_kernel<<<grid_for(M * (D / 8), 256), 256, 0, ST(stream)>>>(CBF(h), ldh, BF(out), ldo, M, D);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_geglu_bwd(const void* h, int64_t ldh, const void* dout, int64_t ldo, void* dh, int64_t lddh, int64_t M, int D,
+                 nk_stream_t stream) {
+    NK_REQUIRE(D % 8 == 0 && ldh % 8 == 0 && ldo % 8 == 0 && lddh % 8 == 0, NK_ERR_SHAPE, "geglu: D=%d", D);
+    geglu_bwd_kernel<<<grid_for(M * (D / 8), 256), 256, 0, ST(stream)>>>(CBF(h), ldh, CBF(dout), ldo, BF(dh), lddh, M, D);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_silu_fwd(const void* x, void* y, int64_t n, nk_stream_t stream) {
+    ew_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(CBF(x), nullptr, BF(y), n, EW_SILU, 0.f);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_silu_bwd(const void* x, const void* dy, void* dx, int64_t n, nk_stream_t stream) {
+    ew_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(CBF(x), CBF(dy), BF(dx), n, EW_SILU_BWD, 0.f);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_add(const void* a, const void* b, void* y, int64_t n, nk_stream_t stream) {
+    if (n % 8 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
+        ew_vec_add_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>(CBF(a), CBF(b), BF(y), n / 8);
+    else
+        ew_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(CBF(a), CBF(b), BF(y), n, EW_ADD, 1.f);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_cast_f32_bf16(const float* x, void* y, int64_t n, nk_stream_t stream) {
+    cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, BF(y), n);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_cast_bf16_f32(const void* x, float* y, int64_t n, int accumulate, nk_stream_t stream) {
+    cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(CBF(x), y, n, accumulate);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_copy_channels(const void* src, int64_t src_stride, void* dst, int64_t dst_stride, int64_t npix, int C,
+                     nk_stream_t stream) {
+    NK_REQUIRE(C % 8 == 0 && src_stride % 8 == 0 && dst_stride % 8 == 0, NK_ERR_SHAPE, "copy_channels: C=%d", C);
+    copy_channels_kernel<<<grid_for(npix * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(src), src_stride, BF(dst), dst_stride, npix, C);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_upsample2x_fwd(const void* x, void* y, int nimg, int H, int W, int C, nk_stream_t stream) {
+    NK_REQUIRE(C % 8 == 0, NK_ERR_SHAPE, "upsample: C=%d", C);
+    upsample2x_fwd_kernel<<<grid_for(4LL * nimg * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(x), BF(y), nimg, H, W, C);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_upsample2x_bwd(const void* dy, void* dx, int nimg, int H, int W, int C, nk_stream_t stream) {
+    NK_REQUIRE(C % 8 == 0, NK_ERR_SHAPE, "upsample: C=%d", C);
+    upsample2x_bwd_kernel<<<grid_for(1LL * nimg * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(dy), BF(dx), nimg, H, W, C);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_nchw_to_nhwc(const void* src, int src_is_f32, void* dst, const float* scale, int nimg, int C, int HW, int Cpad,
+                    nk_stream_t stream) {
+    const long long total = 1LL * nimg * HW * Cpad;
+    if (src_is_f32)
+        nchw_to_nhwc_kernel<float><<<grid_for(total, 256), 256, 0, ST(stream)>>>(static_cast<const float*>(src), BF(dst), scale, nimg, C, HW, Cpad);
+    else
+        nchw_to_nhwc_kernel<bf16><<<grid_for(total, 256), 256, 0, ST(stream)>>>(CBF(src), BF(dst), scale, nimg, C, HW, Cpad);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_nhwc_to_nchw(const void* src, int64_t src_stride, void* dst, int dst_is_f32, int nimg, int C, int HW,
+                    nk_stream_t stream) {
+    const long long total = 1LL * nimg * HW * C;
+    if (dst_is_f32)
+        nhwc_to_nchw_kernel<float><<<grid_for(total, 256), 256, 0, ST(stream)>>>(CBF(src), src_stride, static_cast<float*>(dst), nimg, C, HW);
+    else
+        nhwc_to_nchw_kernel<bf16><<<grid_for(total, 256), 256, 0, ST(stream)>>>(CBF(src), src_stride, BF(dst), nimg, C, HW);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_im2col(const void* x, int64_t x_stride, void* col, int nimg, int H, int W, int C, int ks, int stride, int pad_t,
+              int pad_l, int Ho, int Wo, nk_stream_t stream) {
+    NK_REQUIRE(C % 8 == 0 && x_stride % 8 == 0, NK_ERR_SHAPE, "im2col: C=%d", C);
+    im2col_kernel<<<grid_for(1LL * nimg * Ho * Wo * ks * ks * (C / 8), 256), 256, 0, ST(stream)>>>(
+        CBF(x), x_stride, BF(col), nimg, H, W, C, ks, stride, pad_t, pad_l, Ho, Wo);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_col2im(const void* dcol, void* dx, int nimg, int H, int W, int C, int ks, int stride, int pad_t, int pad_l,
+              int Ho, int Wo, nk_stream_t stream) {
+    NK_REQUIRE(C % 8 == 0, NK_ERR_SHAPE, "col2im: C=%d", C);
+    col2im_kernel<<<grid_for(1LL * nimg * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(dcol), BF(dx), nimg, H, W, C, ks,
+                                                                                    stride, pad_t, pad_l, Ho, Wo);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_colsum(const void* x, int64_t ldx, float* out, int groups, int rows_per_group, int C, int accumulate,
+              nk_stream_t stream) {
+    NK_REQUIRE(C % 2 == 0 && ldx % 2 == 0, NK_ERR_SHAPE, "colsum: C=%d", C);
+    int row_chunks = 1;
+    const int col_blocks = (C / 2 + 31) / 32;
+    if (accumulate) row_chunks = std::max(1, std::min(rows_per_group / 64, (148 * 4) / std::max(1, col_blocks * groups)));
+    colsum_kernel<<<dim3(col_blocks, row_chunks, groups), 256, 0, ST(stream)>>>(CBF(x), ldx, out, rows_per_group, C,
+                                                                               row_chunks, accumulate);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_timestep_embedding(const float* t, void* out, int B, int dim, float max_period, nk_stream_t stream) {
+    const int n = B * (dim / 2);
+    timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, ST(stream)>>>(t, BF(out), B, dim, max_period);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_conv_pack_weights(const float* w, void* wp_fwd, void* wp_dgrad, int Co, int Ci, int ks, int CoP, int CiP,
+                         nk_stream_t stream) {
+    NK_REQUIRE(CoP >= Co && CiP >= Ci, NK_ERR_SHAPE, "pack: padded dims too small");
+    pack_conv_weight_kernel<<<grid_for(1LL * CoP * ks * ks * CiP, 256), 256, 0, ST(stream)>>>(w, BF(wp_fwd), BF(wp_dgrad), Co, Ci,
+                                                                                           ks, CoP, CiP);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_conv_unpack_wgrad(const float* dw_packed, float* dw, int Co, int Ci, int ks, int CiP, int accumulate,
+                         nk_stream_t stream) {
+    unpack_conv_wgrad_kernel<<<grid_for(1LL * Co * Ci * ks * ks, 256), 256, 0, ST(stream)>>>(dw_packed, dw, Co, Ci, ks, CiP,
+                                                                                          accumulate);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp, float* lse, int64_t rows, int N, float scale,
+                    nk_stream_t stream) {
+    NK_REQUIRE(rows < (1LL << 31), NK_ERR_SHAPE, "softmax rows");
+    const int threads = N >= 1024 ? 256 : 128;
+    softmax_rows_kernel<<<static_cast<unsigned>(rows), threads, 0, ST(stream)>>>(S, lds, BF(P), ldp, lse, rows, N, scale);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_attn_delta(const void* dO, const void* O, float* delta, int B, int N, int H, int D, nk_stream_t stream) {
+    NK_REQUIRE(D % 8 == 0, NK_ERR_SHAPE, "attn_delta: D=%d", D);
+    const long long rows = 1LL * B * N * H;
+    attn_delta_kernel<<<static_cast<unsigned>((rows + 31) / 32), 256, 0, ST(stream)>>>(CBF(dO), CBF(O), delta, B, N, H, D);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+
+}  // extern "C"

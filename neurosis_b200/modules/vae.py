@@ -1,0 +1,238 @@
+"""KL-f8 VAE encoder (latent encode of the training step) on the sm_100a kernels.
+
+Drop-in for /root/reference/src/neurosis/modules/diffusion/model.py: `Normalize` (layers.py:5-7),
+`ResnetBlock` (:85-134), `AttnBlock` (:144-172, the "vanilla"/xformers semantics — NOT the buggy
+`TorchSDPAttnBlock`), `Downsample` (:65-82, asymmetric (0,1,0,1) pad + 3x3 s2),
+`Encoder` (:456-606) incl. the `standalone` quant_conv, and `DiagonalGaussianRegularizer` in mode
+(sample=False) form (regularizers.py:23-41).  `AutoencoderKL.encode` mirrors
+models/autoencoder.py:469-487.  Attribute names (=> state-dict keys such as
+`down.0.block.0.norm1.weight`, `mid.attn_1.q.weight`) are unchanged.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+from .util import as_nhwc, from_nhwc
+
+
+def Normalize(in_channels: int, num_groups: int = 32) -> nn.GroupNorm:
+    return nn.GroupNorm(num_groups=num_groups, num_channels=in_channels, eps=1e-6, affine=True)
+
+
+def _gn(norm: nn.GroupNorm, x: Tensor, silu: bool) -> Tensor:
+    return ops.group_norm(x, norm.weight, norm.bias, norm.num_groups, norm.eps, silu=silu)
+
+
+def _conv1x1(conv: nn.Conv2d, x: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+    n, h, w, c = x.shape
+    r = residual.reshape(n * h * w, -1) if residual is not None else None
+    y = ops.linear(x.reshape(n * h * w, c), conv.weight.view(conv.weight.shape[0], -1), conv.bias, r)
+    return y.view(n, h, w, -1)
+
+
+class Downsample(nn.Module):
+    def __init__(self, in_channels: int, with_conv: bool):
+        super().__init__()
+        if not with_conv:
+            raise NotImplementedError("average-pool downsampling is not used by the reference configs")
+        self.with_conv = with_conv
+        self.padding = nn.ConstantPad2d((0, 1, 0, 1), 0)
+        self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return from_nhwc(ops.conv2d_stride2(as_nhwc(x), self.conv.weight, self.conv.bias, asymmetric=True))
+
+
+class ResnetBlock(nn.Module):
+    def __init__(self, *, in_channels: int, out_channels: Optional[int] = None, conv_shortcut: bool = False,
+                 dropout: float = 0.0, temb_channels: int = 512):
+        super().__init__()
+        out_channels = in_channels if out_channels is None else out_channels
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.use_conv_shortcut = conv_shortcut
+        if temb_channels > 0 or dropout > 0.0:
+            raise NotImplementedError("the VAE path uses temb_channels=0 and dropout=0")
+        self.norm1 = Normalize(in_channels)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        self.norm2 = Normalize(out_channels)
+        self.dropout = nn.Identity()
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        if in_channels != out_channels:
+            if conv_shortcut:
+                self.conv_shortcut = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
+            else:
+                self.nin_shortcut = nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=1, padding=0)
+
+    def forward(self, x: Tensor, temb: Optional[Tensor] = None) -> Tensor:
+        xn = as_nhwc(x)
+        h = ops.conv2d(_gn(self.norm1, xn, True), self.conv1.weight, self.conv1.bias)
+        h = _gn(self.norm2, h, True)
+        if self.in_channels != self.out_channels:
+            if self.use_conv_shortcut:
+                skip = ops.conv2d(xn, self.conv_shortcut.weight, self.conv_shortcut.bias)
+            else:
+                skip = _conv1x1(self.nin_shortcut, xn)
+        else:
+            skip = xn
+        return from_nhwc(ops.conv2d(h, self.conv2.weight, self.conv2.bias, None, skip))
+
+
+class AttnBlock(nn.Module):
+    """single-head attention over all pixels, head_dim = channels (512): materialised tcgen05 path."""
+
+    def __init__(self, in_channels: int):
+        super().__init__()
+        self.in_channels = in_channels
+        self.norm = Normalize(in_channels)
+        self.q = nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
+        self.k = nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
+        self.v = nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
+        self.proj_out = nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
+        self.max_images_per_call = 2  # bounds the fp32 score matrix (1 GiB per 1024^2 image)
+
+    def forward(self, x: Tensor, **kwargs) -> Tensor:
+        xn = as_nhwc(x)
+        n, h, w, c = xn.shape
+        t = _gn(self.norm, xn, False)
+        q, k, v = (_conv1x1(m, t).view(n, h * w, 1, c) for m in (self.q, self.k, self.v))
+        outs = []
+        for i in range(0, n, self.max_images_per_call):
+            j = min(n, i + self.max_images_per_call)
+            outs.append(ops.attention(q[i:j], k[i:j], v[i:j], c ** -0.5))
+        o = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        return from_nhwc(_conv1x1(self.proj_out, o.view(n, h, w, c), residual=xn))
+
+
+def make_attn(in_channels: int, attn_type: str = "vanilla") -> nn.Module:
+    if attn_type in ("vanilla", "vanilla-xformers", "torch-sdp", "b200"):
+        return AttnBlock(in_channels)
+    if attn_type == "none":
+        return nn.Identity()
+    raise NotImplementedError(f"attention type {attn_type!r} is not supported")
+
+
+class DiagonalGaussianRegularizer(nn.Module):
+    """mode (sample=False) of the diagonal Gaussian posterior = the mean half of the moments."""
+
+    def __init__(self, sample: bool = False):
+        super().__init__()
+        if sample:
+            raise NotImplementedError("sampling posterior is not used by the diffusion training step")
+        self.sample = sample
+
+    def forward(self, z: Tensor):
+        mean, _logvar = torch.chunk(z, 2, dim=1)
+        return mean, {}
+
+
+class Encoder(nn.Module):
+    def __init__(self, *, ch: int, out_ch: int, ch_mult: Sequence[int] = (1, 2, 4, 8), num_res_blocks: int,
+                 attn_resolutions: Sequence[int], dropout: float = 0.0, resamp_with_conv: bool = True,
+                 in_channels: int, resolution: int, z_channels: int, double_z: bool = True,
+                 use_linear_attn: bool = False, attn_type: str = "vanilla", embed_dim: int = 256,
+                 standalone: bool = False, **kwargs):
+        super().__init__()
+        self.ch = ch
+        self.temb_ch = 0
+        self.num_resolutions = len(ch_mult)
+        self.num_res_blocks = num_res_blocks
+        self.resolution = resolution
+        self.in_channels = in_channels
+        self.conv_in = nn.Conv2d(in_channels, ch, kernel_size=3, stride=1, padding=1)
+        curr_res = resolution
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.in_ch_mult = in_ch_mult
+        self.down = nn.ModuleList()
+        block_in = ch
+        for i_level in range(self.num_resolutions):
+            block, attn = nn.ModuleList(), nn.ModuleList()
+            block_in = ch * in_ch_mult[i_level]
+            block_out = ch * ch_mult[i_level]
+            for _ in range(num_res_blocks):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, temb_channels=0, dropout=dropout))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    attn.append(make_attn(block_in, attn_type=attn_type))
+            down = nn.Module()
+            down.block = block
+            down.attn = attn
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in, resamp_with_conv)
+                curr_res = curr_res // 2
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=0, dropout=dropout)
+        self.mid.attn_1 = make_attn(block_in, attn_type=attn_type)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=0, dropout=dropout)
+        self.norm_out = Normalize(block_in)
+        self.z_out = 2 * z_channels if double_z else z_channels
+        self.conv_out = nn.Conv2d(block_in, self.z_out, kernel_size=3, stride=1, padding=1)
+        self.regularizer = DiagonalGaussianRegularizer(sample=False)
+        self.max_batch_size = None
+        self.standalone = standalone
+        if standalone:
+            self.quant_conv = nn.Conv2d((1 + double_z) * z_channels, (1 + double_z) * embed_dim, 1)
+        else:
+            self.quant_conv = nn.Identity()
+
+    def encode(self, x: Tensor) -> Tensor:
+        """(N, 3, H, W) in [-1, 1] -> moments (N, H/8, W/8, 64-padded) NHWC bf16."""
+        h = ops.conv2d(as_nhwc(x, cpad=64), self.conv_in.weight, self.conv_in.bias)
+        h = from_nhwc(h)
+        for i_level in range(self.num_resolutions):
+            for i_block in range(self.num_res_blocks):
+                h = self.down[i_level].block[i_block](h, None)
+                if len(self.down[i_level].attn) > 0:
+                    h = self.down[i_level].attn[i_block](h)
+            if i_level != self.num_resolutions - 1:
+                h = self.down[i_level].downsample(h)
+        h = self.mid.block_1(h, None)
+        h = self.mid.attn_1(h)
+        h = self.mid.block_2(h, None)
+        hn = _gn(self.norm_out, as_nhwc(h), True)
+        return ops.conv2d(hn, self.conv_out.weight, self.conv_out.bias)  # padded to 64 channels
+
+    def _encode_quant(self, x: Tensor, quant_conv: Optional[nn.Module] = None) -> Tensor:
+        z = self.encode(x)  # (N, h, w, 64) with z_out valid channels
+        qc = quant_conv if quant_conv is not None else self.quant_conv
+        if isinstance(qc, nn.Conv2d):
+            n, h, w, cp = z.shape
+            wq = torch.zeros((qc.weight.shape[0], cp), dtype=qc.weight.dtype, device=qc.weight.device)
+            wq[:, : qc.weight.shape[1]] = qc.weight.detach().view(qc.weight.shape[0], -1)
+            y = ops.linear_fwd(z.view(n * h * w, cp), ops.cast_bf16(wq), ops.f32_param(qc.bias), out_f32=True)
+            return y.view(n, h, w, -1).permute(0, 3, 1, 2).contiguous()
+        return ops.nhwc_to_nchw(z, self.z_out, out_f32=True)
+
+    def forward(self, x: Tensor, regularize: bool = False):
+        if self.max_batch_size is None:
+            z = self._encode_quant(x)
+        else:
+            bs = self.max_batch_size
+            z = torch.cat([self._encode_quant(x[i: i + bs]) for i in range(0, x.shape[0], bs)], 0)
+        if regularize:
+            z, _ = self.regularizer(z)
+        return z
+
+
+class AutoencoderKL(nn.Module):
+    """`encode` half of the reference AutoencoderKL (models/autoencoder.py:429-504): encoder ->
+    quant_conv -> DiagonalGaussian mode.  State-dict keys: encoder.*, quant_conv.*."""
+
+    def __init__(self, embed_dim: int, ddconfig: dict, **kwargs):
+        super().__init__()
+        cfg = dict(ddconfig)
+        cfg.pop("standalone", None)
+        self.encoder = Encoder(**cfg, embed_dim=embed_dim, standalone=False)
+        z_ch = cfg["z_channels"]
+        self.quant_conv = nn.Conv2d((1 + cfg.get("double_z", True)) * z_ch, (1 + cfg.get("double_z", True)) * embed_dim, 1)
+        self.embed_dim = embed_dim
+
+    @torch.no_grad()
+    def encode(self, x: Tensor, return_reg_log: bool = False):
+        z = self.encoder._encode_quant(x, self.quant_conv)  # same arithmetic as Encoder(standalone=True)
+        z, reg_log = self.encoder.regularizer(z)
+        return (z, reg_log) if return_reg_log else z

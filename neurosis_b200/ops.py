@@ -1,0 +1,957 @@
+"""Tensor-level wrappers (and autograd Functions) over the C ABI of libnk_b200.so.
+
+PyTorch is used only for device memory, streams and the autograd graph; every computation on
+the hot path is a kernel of this repository.  All wrappers raise if the tensors are not on a
+CUDA device — there is no CPU path.
+
+Layout conventions
+  * image activations: contiguous bf16 tensors of shape (N, H, W, C)  ("NHWC")
+  * token activations: bf16 (..., C) with a contiguous last dim
+  * parameters: the fp32 nn.Parameters of the reference layout; bf16 / packed copies for the
+    kernels are cached per parameter version (`bf16_weight`, `packed_conv_weight`).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import weakref
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from ._lib import check, lib, nk_gemm_desc
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+LAUNCHES = 0  # number of kernel-launching C-ABI calls made (bench.py reports it)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _req_cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("neurosis_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+# --------------------------------------------------------------------------------------------
+# parameter copies for the kernels
+# --------------------------------------------------------------------------------------------
+_wcache: dict[int, tuple] = {}  # id(param) -> (weakref(param), cache dict)
+
+
+def _cache_for(p: Tensor) -> dict:
+    """per-parameter cache of kernel-side copies, invalidated by in-place updates (optimizer steps)."""
+    base = p._base if p._base is not None else p
+    key = id(base)
+    ent = _wcache.get(key)
+    if ent is not None and ent[0]() is base:
+        d = ent[1]
+        if d["version"] == base._version and d["ptr"] == base.data_ptr():
+            return d
+    d = {"version": base._version, "ptr": base.data_ptr()}
+    _wcache[key] = (weakref.ref(base, lambda _r, k=key: _wcache.pop(k, None)), d)
+    return d
+
+
+def cast_bf16(x: Tensor) -> Tensor:
+    """fp32 -> bf16 copy with our kernel (bf16 input is returned as is)."""
+    if x.dtype == BF16:
+        return x.contiguous()
+    _req_cuda(x)
+    x = x.contiguous().float()
+    y = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(lib.nk_cast_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "cast_f32_bf16")
+    _count()
+    return y
+
+
+def bf16_weight(p: Tensor) -> Tensor:
+    d = _cache_for(p)
+    w = d.get("bf16")
+    if w is None:
+        base = p._base if p._base is not None else p
+        w = cast_bf16(base.detach())
+        d["bf16"] = w
+    return w.view(p.shape) if w.shape != p.shape else w
+
+
+def f32_param(p: Optional[Tensor]) -> Optional[Tensor]:
+    if p is None:
+        return None
+    t = p.detach()
+    return t if t.dtype == F32 and t.is_contiguous() else t.float().contiguous()
+
+
+def _pad64(c: int) -> int:
+    return c if c >= 64 else 64
+
+
+def packed_conv_weight(p: Tensor, need_dgrad: bool = True):
+    """(wp_fwd [CoP, taps*CiP], wp_dgrad [CiP, taps*CoP]) bf16 packings of an OIHW fp32 weight."""
+    d = _cache_for(p)
+    pk = d.get("packed")
+    if pk is None:
+        co, ci, ks, _ = p.shape
+        cop, cip = _pad64(co), _pad64(ci)
+        w = f32_param(p)
+        wf = torch.empty((cop, ks * ks * cip), dtype=BF16, device=p.device)
+        wd = torch.empty((cip, ks * ks * cop), dtype=BF16, device=p.device)
+        check(lib.nk_conv_pack_weights(w.data_ptr(), wf.data_ptr(), wd.data_ptr(), co, ci, ks, cop, cip, _stream()),
+              "conv_pack_weights")
+        _count()
+        pk = (wf, wd)
+        d["packed"] = pk
+    return pk
+
+
+# --------------------------------------------------------------------------------------------
+# raw (non-autograd) kernels
+# --------------------------------------------------------------------------------------------
+def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
+               out_f32: bool = False) -> Tensor:
+    """y[M,N] = x[M,K] @ w[N,K]^T + bias + residual;  x, w, residual bf16; bias fp32."""
+    _req_cuda(x, w)
+    K = x.shape[-1]
+    N = w.shape[0]
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    y = torch.empty((M, N), dtype=F32 if out_f32 else BF16, device=x.device)
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, N)
+        if r2.stride(-1) != 1:
+            r2 = r2.contiguous()
+    check(lib.nk_linear_fwd(x2.data_ptr(), x2.stride(0), w.data_ptr(), w.stride(0), _p(bias), _p(r2),
+                            r2.stride(0) if r2 is not None else 0, y.data_ptr(), N, int(out_f32), M, N, K, _stream()),
+          "linear_fwd")
+    _count()
+    return y.view(*x.shape[:-1], N)
+
+
+def linear_dgrad(dy: Tensor, w: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+    """dx[M,K] = dy[M,N] @ w[N,K] (+ residual)."""
+    N, K = w.shape
+    d2 = dy.reshape(-1, N)
+    if d2.stride(-1) != 1:
+        d2 = d2.contiguous()
+    M = d2.shape[0]
+    dx = torch.empty((M, K), dtype=BF16, device=dy.device)
+    r2 = residual.reshape(-1, K) if residual is not None else None
+    check(lib.nk_linear_dgrad(d2.data_ptr(), d2.stride(0), w.data_ptr(), w.stride(0), _p(r2),
+                              r2.stride(0) if r2 is not None else 0, dx.data_ptr(), K, M, N, K, _stream()),
+          "linear_dgrad")
+    _count()
+    return dx.view(*dy.shape[:-1], K)
+
+
+def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """dw[N,K] fp32 = dy[M,N]^T @ x[M,K]; with `out` given the product is accumulated into it."""
+    N = dy.shape[-1]
+    K = x.shape[-1]
+    d2 = dy.reshape(-1, N)
+    x2 = x.reshape(-1, K)
+    if d2.stride(-1) != 1:
+        d2 = d2.contiguous()
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    M = d2.shape[0]
+    acc = out is not None
+    dw = out if acc else torch.empty((N, K), dtype=F32, device=dy.device)
+    check(lib.nk_linear_wgrad(d2.data_ptr(), d2.stride(0), x2.data_ptr(), x2.stride(0), dw.data_ptr(), dw.stride(0),
+                              int(acc), M, N, K, _stream()), "linear_wgrad")
+    _count()
+    return dw
+
+
+def colsum(x: Tensor, groups: int = 1) -> Tensor:
+    """fp32 [groups, C] column sums of a bf16 [groups*rows, C] matrix."""
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    rows = x2.shape[0] // groups
+    out = torch.zeros((groups, C), dtype=F32, device=x.device)
+    check(lib.nk_colsum(x2.data_ptr(), x2.stride(0), out.data_ptr(), groups, rows, C, 1, _stream()), "colsum")
+    _count()
+    return out
+
+
+def conv2d_fwd(x: Tensor, wp: Tensor, cout: int, ksize: int, bias: Optional[Tensor] = None,
+               bias_img: Optional[Tensor] = None, residual: Optional[Tensor] = None) -> Tensor:
+    """x: (N,H,W,Cin) bf16 with Cin % 64 == 0; wp packed [CoP, taps*Cin]; returns (N,H,W,CoP) with
+    the first `cout` channels written (CoP = max(cout, 64); padded channels are zero)."""
+    _req_cuda(x, wp)
+    n, h, w_, cin = x.shape
+    cop = _pad64(cout)
+    if cop != cout:
+        y = torch.zeros((n, h, w_, cop), dtype=BF16, device=x.device)
+    else:
+        y = torch.empty((n, h, w_, cop), dtype=BF16, device=x.device)
+    check(lib.nk_conv2d_fwd(x.data_ptr(), x.stride(2), wp.data_ptr(), _p(bias), _p(bias_img), _p(residual),
+                            residual.stride(2) if residual is not None else 0, y.data_ptr(), cop, n, h, w_, cin, cout,
+                            ksize, _stream()), "conv2d_fwd")
+    _count()
+    return y
+
+
+def conv2d_wgrad(dy: Tensor, x: Tensor, cout: int, ksize: int) -> Tensor:
+    """packed fp32 gradient [cout, taps, Cin_phys]."""
+    n, h, w_, cin = x.shape
+    dwp = torch.zeros((cout, ksize * ksize, cin), dtype=F32, device=x.device)
+    check(lib.nk_conv2d_wgrad(dy.data_ptr(), dy.stride(2), x.data_ptr(), x.stride(2), dwp.data_ptr(), n, h, w_, cin,
+                              cout, ksize, _stream()), "conv2d_wgrad")
+    _count()
+    return dwp
+
+
+def conv_unpack_wgrad(dwp: Tensor, co: int, ci: int, ks: int) -> Tensor:
+    cip = dwp.shape[-1] if dwp.dim() == 3 else dwp.shape[-1] // (ks * ks)
+    dw = torch.empty((co, ci, ks, ks), dtype=F32, device=dwp.device)
+    check(lib.nk_conv_unpack_wgrad(dwp.data_ptr(), dw.data_ptr(), co, ci, ks, cip, 0, _stream()), "conv_unpack_wgrad")
+    _count()
+    return dw
+
+
+def im2col(x: Tensor, ks: int, stride: int, pad_t: int, pad_l: int, ho: int, wo: int) -> Tensor:
+    n, h, w_, c = x.shape
+    col = torch.empty((n * ho * wo, ks * ks * c), dtype=BF16, device=x.device)
+    check(lib.nk_im2col(x.data_ptr(), x.stride(2), col.data_ptr(), n, h, w_, c, ks, stride, pad_t, pad_l, ho, wo,
+                        _stream()), "im2col")
+    _count()
+    return col
+
+
+def col2im(dcol: Tensor, shape, ks: int, stride: int, pad_t: int, pad_l: int, ho: int, wo: int) -> Tensor:
+    n, h, w_, c = shape
+    dx = torch.empty((n, h, w_, c), dtype=BF16, device=dcol.device)
+    check(lib.nk_col2im(dcol.data_ptr(), dx.data_ptr(), n, h, w_, c, ks, stride, pad_t, pad_l, ho, wo, _stream()),
+          "col2im")
+    _count()
+    return dx
+
+
+def groupnorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: float, silu: bool):
+    _req_cuda(x)
+    n, h, w_, c = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty((n, groups), dtype=F32, device=x.device)
+    rstd = torch.empty((n, groups), dtype=F32, device=x.device)
+    ws_bytes = lib.nk_groupnorm_workspace_bytes(n, h * w_, c, groups)
+    if ws_bytes < 0:
+        raise ValueError(f"groupnorm: unsupported channel count {c}")
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+    check(lib.nk_groupnorm_fwd(x.data_ptr(), x.stride(2), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), c,
+                               mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(), ws_bytes, n, h * w_, c, groups,
+                               float(eps), int(silu), _stream()), "groupnorm_fwd")
+    _count(3)
+    return y, mean, rstd
+
+
+def groupnorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, beta: Tensor, mean: Tensor, rstd: Tensor, groups: int,
+                  silu: bool):
+    n, h, w_, c = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.zeros((c,), dtype=F32, device=x.device)
+    dbeta = torch.zeros((c,), dtype=F32, device=x.device)
+    ws_bytes = lib.nk_groupnorm_workspace_bytes(n, h * w_, c, groups)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+    check(lib.nk_groupnorm_bwd(dy.data_ptr(), dy.stride(2), x.data_ptr(), x.stride(2), gamma.data_ptr(),
+                               beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), c, dgamma.data_ptr(),
+                               dbeta.data_ptr(), ws.data_ptr(), ws_bytes, n, h * w_, c, groups, int(silu), _stream()),
+          "groupnorm_bwd")
+    _count(4)
+    return dx, dgamma, dbeta
+
+
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float):
+    _req_cuda(x)
+    c = x.shape[-1]
+    x2 = x.reshape(-1, c)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    rows = x2.shape[0]
+    y = torch.empty((rows, c), dtype=BF16, device=x.device)
+    mean = torch.empty((rows,), dtype=F32, device=x.device)
+    rstd = torch.empty((rows,), dtype=F32, device=x.device)
+    check(lib.nk_layernorm_fwd(x2.data_ptr(), x2.stride(0), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), c,
+                               mean.data_ptr(), rstd.data_ptr(), rows, c, float(eps), _stream()), "layernorm_fwd")
+    _count()
+    return y.view(x.shape), mean, rstd
+
+
+def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor):
+    c = x.shape[-1]
+    x2 = x.reshape(-1, c)
+    d2 = dy.reshape(-1, c)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    if d2.stride(-1) != 1:
+        d2 = d2.contiguous()
+    rows = x2.shape[0]
+    dx = torch.empty((rows, c), dtype=BF16, device=x.device)
+    dgamma = torch.zeros((c,), dtype=F32, device=x.device)
+    dbeta = torch.zeros((c,), dtype=F32, device=x.device)
+    check(lib.nk_layernorm_bwd(d2.data_ptr(), d2.stride(0), x2.data_ptr(), x2.stride(0), gamma.data_ptr(),
+                               mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), c, dgamma.data_ptr(), dbeta.data_ptr(),
+                               rows, c, _stream()), "layernorm_bwd")
+    _count()
+    return dx.view(x.shape), dgamma, dbeta
+
+
+def geglu_fwd(h: Tensor) -> Tensor:
+    d2 = h.shape[-1]
+    d = d2 // 2
+    h2 = h.reshape(-1, d2)
+    out = torch.empty((h2.shape[0], d), dtype=BF16, device=h.device)
+    check(lib.nk_geglu_fwd(h2.data_ptr(), h2.stride(0), out.data_ptr(), d, h2.shape[0], d, _stream()), "geglu_fwd")
+    _count()
+    return out.view(*h.shape[:-1], d)
+
+
+def geglu_bwd(h: Tensor, dout: Tensor) -> Tensor:
+    d2 = h.shape[-1]
+    d = d2 // 2
+    h2 = h.reshape(-1, d2)
+    do2 = dout.reshape(-1, d)
+    if do2.stride(-1) != 1:
+        do2 = do2.contiguous()
+    dh = torch.empty_like(h2)
+    check(lib.nk_geglu_bwd(h2.data_ptr(), h2.stride(0), do2.data_ptr(), do2.stride(0), dh.data_ptr(), d2, h2.shape[0],
+                           d, _stream()), "geglu_bwd")
+    _count()
+    return dh.view(h.shape)
+
+
+def silu_fwd(x: Tensor) -> Tensor:
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(lib.nk_silu_fwd(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "silu_fwd")
+    _count()
+    return y
+
+
+def silu_bwd(x: Tensor, dy: Tensor) -> Tensor:
+    x = x.contiguous()
+    dy = dy.contiguous()
+    dx = torch.empty_like(x)
+    check(lib.nk_silu_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), _stream()), "silu_bwd")
+    _count()
+    return dx
+
+
+def add(a: Tensor, b: Tensor) -> Tensor:
+    a = a.contiguous()
+    b = b.contiguous()
+    y = torch.empty_like(a)
+    check(lib.nk_add(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), _stream()), "add")
+    _count()
+    return y
+
+
+def copy_channels(src: Tensor, dst: Tensor, c: int) -> None:
+    """copy the first c channels of every pixel of src (.., Cs) into dst (.., Cd) (views allowed)."""
+    npix = src.numel() // src.shape[-1] if src.is_contiguous() else math.prod(src.shape[:-1])
+    check(lib.nk_copy_channels(src.data_ptr(), src.stride(-2), dst.data_ptr(), dst.stride(-2), npix, c, _stream()),
+          "copy_channels")
+    _count()
+
+
+def cat_channels(a: Tensor, b: Tensor) -> Tensor:
+    ca, cb = a.shape[-1], b.shape[-1]
+    out = torch.empty((*a.shape[:-1], ca + cb), dtype=BF16, device=a.device)
+    copy_channels(a, out, ca)
+    copy_channels(b, out[..., ca:], cb)
+    return out
+
+
+def upsample2x_fwd(x: Tensor) -> Tensor:
+    n, h, w_, c = x.shape
+    y = torch.empty((n, 2 * h, 2 * w_, c), dtype=BF16, device=x.device)
+    check(lib.nk_upsample2x_fwd(x.data_ptr(), y.data_ptr(), n, h, w_, c, _stream()), "upsample2x_fwd")
+    _count()
+    return y
+
+
+def upsample2x_bwd(dy: Tensor) -> Tensor:
+    n, h2, w2, c = dy.shape
+    dx = torch.empty((n, h2 // 2, w2 // 2, c), dtype=BF16, device=dy.device)
+    check(lib.nk_upsample2x_bwd(dy.data_ptr(), dx.data_ptr(), n, h2 // 2, w2 // 2, c, _stream()), "upsample2x_bwd")
+    _count()
+    return dx
+
+
+def nchw_to_nhwc(x: Tensor, cpad: Optional[int] = None, scale: Optional[Tensor] = None) -> Tensor:
+    """(N,C,H,W) fp32|bf16 contiguous -> (N,H,W,Cpad) bf16, zero padded channels, optional per-image scale."""
+    _req_cuda(x)
+    if x.dtype not in (F32, BF16):
+        x = x.float()
+    x = x.contiguous()
+    n, c, h, w_ = x.shape
+    cpad = cpad or c
+    y = torch.empty((n, h, w_, cpad), dtype=BF16, device=x.device)
+    check(lib.nk_nchw_to_nhwc(x.data_ptr(), int(x.dtype == F32), y.data_ptr(), _p(scale), n, c, h * w_, cpad,
+                              _stream()), "nchw_to_nhwc")
+    _count()
+    return y
+
+
+def nhwc_to_nchw(x: Tensor, c: Optional[int] = None, out_f32: bool = True) -> Tensor:
+    n, h, w_, cp = x.shape
+    c = c or cp
+    y = torch.empty((n, c, h, w_), dtype=F32 if out_f32 else BF16, device=x.device)
+    check(lib.nk_nhwc_to_nchw(x.data_ptr(), x.stride(2), y.data_ptr(), int(out_f32), n, c, h * w_, _stream()),
+          "nhwc_to_nchw")
+    _count()
+    return y
+
+
+def timestep_embedding(t: Tensor, dim: int, max_period: float = 10000.0) -> Tensor:
+    _req_cuda(t)
+    tf = t.float().contiguous()
+    out = torch.empty((tf.shape[0], dim), dtype=BF16, device=t.device)
+    check(lib.nk_timestep_embedding(tf.data_ptr(), out.data_ptr(), tf.shape[0], dim, float(max_period), _stream()),
+          "timestep_embedding")
+    _count()
+    return out
+
+
+# ---- generic batched GEMM descriptor helpers (attention) --------------------------------------
+def _operand(o, t: Tensor, mn_major: int, rows: int, inner: int, row_stride: int, nb2: int, b2_stride: int, nb1: int,
+             b1_stride: int) -> None:
+    o.ptr = t.data_ptr()
+    o.mn_major = mn_major
+    o.conv = 0
+    o.inner = inner
+    o.rows = rows
+    o.row_stride = row_stride
+    o.nb2 = nb2
+    o.b2_stride = b2_stride
+    o.nb1 = nb1
+    o.b1_stride = b1_stride
+
+
+def _bhnd(t: Tensor):
+    """strides (batch, row, head) in elements of a (B, N, H, D) view with contiguous D."""
+    assert t.stride(3) == 1
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+def attention_fwd(q: Tensor, k: Tensor, v: Tensor, scale: float):
+    """q (B,Nq,H,D), k/v (B,Nk,H,D) bf16 views (last dim contiguous) -> o (B,Nq,H,D), lse (B,H,Nq)."""
+    _req_cuda(q, k, v)
+    B, Nq, H, D = q.shape
+    Nk = k.shape[1]
+    o = torch.empty((B, Nq, H, D), dtype=BF16, device=q.device)
+    lse = torch.empty((B, H, Nq), dtype=F32, device=q.device)
+    if D == 64 and q.stride(2) == 64 and k.stride(2) == 64 and v.stride(2) == 64:
+        check(lib.nk_attention_fwd(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
+                                   v.data_ptr(), v.stride(1), v.stride(0), o.data_ptr(), o.stride(1), o.stride(0),
+                                   lse.data_ptr(), B, H, Nq, Nk, D, float(scale), _stream()), "attention_fwd")
+        _count()
+        return o, lse
+    # materialised path: S = Q K^T (fp32) -> row softmax -> O = P V
+    S = torch.empty((B, H, Nq, Nk), dtype=F32, device=q.device)
+    d = nk_gemm_desc()
+    qb, qr, qh = _bhnd(q)
+    kb, kr, kh = _bhnd(k)
+    _operand(d.A, q, 0, Nq, D, qr, H, qh, B, qb)
+    _operand(d.B, k, 0, Nk, D, kr, H, kh, B, kb)
+    d.M, d.N, d.K, d.nb2, d.nb1, d.ksize = Nq, Nk, D, H, B, 1
+    d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = S.data_ptr(), Nk, Nq * Nk, H * Nq * Nk
+    d.out, d.epi, d.alpha = 1, 0, 1.0
+    check(lib.nk_gemm_ex(ctypes.byref(d), _stream()), "attention S gemm")
+    Nkp = (Nk + 7) // 8 * 8
+    P = torch.empty((B, H, Nq, Nkp), dtype=BF16, device=q.device) if Nkp == Nk else torch.zeros(
+        (B, H, Nq, Nkp), dtype=BF16, device=q.device)
+    check(lib.nk_softmax_rows(S.data_ptr(), Nk, P.data_ptr(), Nkp, lse.data_ptr(), B * H * Nq, Nk, float(scale),
+                              _stream()), "softmax_rows")
+    del S
+    _pv(P, v, o, Nk)
+    _count(3)
+    return o, lse
+
+
+def _pv(P: Tensor, v: Tensor, o: Tensor, Nk: int) -> None:
+    """o[b,:,h,:] = P[b,h] @ v[b,:,h,:]  (B operand = V is MN-major: head dim contiguous)."""
+    B, H, Nq, Nkp = P.shape
+    D = v.shape[-1]
+    d = nk_gemm_desc()
+    vb, vr, vh = _bhnd(v)
+    _operand(d.A, P, 0, Nq, Nk, Nkp, H, Nq * Nkp, B, H * Nq * Nkp)
+    _operand(d.B, v, 1, Nk, D, vr, H, vh, B, vb)
+    d.M, d.N, d.K, d.nb2, d.nb1, d.ksize = Nq, D, Nk, H, B, 1
+    d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = o.data_ptr(), o.stride(1), o.stride(2), o.stride(0)
+    d.out, d.epi, d.alpha = 0, 0, 1.0
+    check(lib.nk_gemm_ex(ctypes.byref(d), _stream()), "attention PV gemm")
+
+
+def attention_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, scale: float):
+    """Gradients of attention_fwd via batched tensor-core GEMMs with softmax-aware epilogues:
+       P = exp(scale*QK^T - lse); dV = P^T dO; dP = dO V^T; dS = P*(dP - delta)*scale; dQ = dS K; dK = dS^T Q."""
+    B, Nq, H, D = q.shape
+    Nk = k.shape[1]
+    dev = q.device
+    do = do.contiguous() if do.stride(3) != 1 else do
+    delta = torch.empty((B, H, Nq), dtype=F32, device=dev)
+    doc = do.contiguous()
+    check(lib.nk_attn_delta(doc.data_ptr(), o.data_ptr(), delta.data_ptr(), B, Nq, H, D, _stream()), "attn_delta")
+    Nkp = (Nk + 7) // 8 * 8
+    P = torch.zeros((B, H, Nq, Nkp), dtype=BF16, device=dev) if Nkp != Nk else torch.empty(
+        (B, H, Nq, Nkp), dtype=BF16, device=dev)
+    LOG2E = 1.4426950408889634
+    lse2 = (lse * LOG2E).contiguous()  # tiny (B,H,Nq) helper tensor
+    qb, qr, qh = _bhnd(q)
+    kb, kr, kh = _bhnd(k)
+    vb, vr, vh = _bhnd(v)
+    ob, orr, oh = _bhnd(doc)
+    st = _stream()
+    # P = exp2(scale*log2e * Q K^T - lse*log2e)
+    d = nk_gemm_desc()
+    _operand(d.A, q, 0, Nq, D, qr, H, qh, B, qb)
+    _operand(d.B, k, 0, Nk, D, kr, H, kh, B, kb)
+    d.M, d.N, d.K, d.nb2, d.nb1, d.ksize = Nq, Nk, D, H, B, 1
+    d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = P.data_ptr(), Nkp, Nq * Nkp, H * Nq * Nkp
+    d.out, d.epi, d.alpha = 0, 1, float(scale) * LOG2E
+    d.rowvec = lse2.data_ptr()
+    check(lib.nk_gemm_ex(ctypes.byref(d), st), "attention bwd P gemm")
+    # dV[b,:,h,:] = P^T dO : A = P as MN-major (M = kv), B = dO MN-major (N = d), K = Nq
+    dq = torch.empty((B, Nq, H, D), dtype=BF16, device=dev)
+    dk = torch.empty((B, Nk, H, D), dtype=BF16, device=dev)
+    dv = torch.empty((B, Nk, H, D), dtype=BF16, device=dev)
+    d = nk_gemm_desc()
+    _operand(d.A, P, 1, Nq, Nk, Nkp, H, Nq * Nkp, B, H * Nq * Nkp)
+    _operand(d.B, doc, 1, Nq, D, orr, H, oh, B, ob)
+    d.M, d.N, d.K, d.nb2, d.nb1, d.ksize = Nk, D, Nq, H, B, 1
+    d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = dv.data_ptr(), dv.stride(1), dv.stride(2), dv.stride(0)
+    d.out, d.epi, d.alpha = 0, 0, 1.0
+    check(lib.nk_gemm_ex(ctypes.byref(d), st), "attention bwd dV gemm")
+    # dS = P * (dO V^T - delta) * scale
+    dS = torch.zeros_like(P) if Nkp != Nk else torch.empty_like(P)
+    d = nk_gemm_desc()
+    _operand(d.A, doc, 0, Nq, D, orr, H, oh, B, ob)
+    _operand(d.B, v, 0, Nk, D, vr, H, vh, B, vb)
+    d.M, d.N, d.K, d.nb2, d.nb1, d.ksize = Nq, Nk, D, H, B, 1
+    d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = dS.data_ptr(), Nkp, Nq * Nkp, H * Nq * Nkp
+    d.out, d.epi, d.alpha = 0, 2, float(scale)
+    d.rowvec = delta.data_ptr()
+    d.aux = P.data_ptr()
+    check(lib.nk_gemm_ex(ctypes.byref(d), st), "attention bwd dS gemm")
+    # dQ = dS K : A = dS K-major (K = kv), B = K matrix MN-major (N = d)
+    d = nk_gemm_desc()
+    _operand(d.A, dS, 0, Nq, Nk, Nkp, H, Nq * Nkp, B, H * Nq * Nkp)
+    _operand(d.B, k, 1, Nk, D, kr, H, kh, B, kb)
+    d.M, d.N, d.K, d.nb2, d.nb1, d.ksize = Nq, D, Nk, H, B, 1
+    d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = dq.data_ptr(), dq.stride(1), dq.stride(2), dq.stride(0)
+    d.out, d.epi, d.alpha = 0, 0, 1.0
+    check(lib.nk_gemm_ex(ctypes.byref(d), st), "attention bwd dQ gemm")
+    # dK = dS^T Q : A = dS MN-major (M = kv), B = Q MN-major (N = d), K = Nq
+    d = nk_gemm_desc()
+    _operand(d.A, dS, 1, Nq, Nk, Nkp, H, Nq * Nkp, B, H * Nq * Nkp)
+    _operand(d.B, q, 1, Nq, D, qr, H, qh, B, qb)
+    d.M, d.N, d.K, d.nb2, d.nb1, d.ksize = Nk, D, Nq, H, B, 1
+    d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = dk.data_ptr(), dk.stride(1), dk.stride(2), dk.stride(0)
+    d.out, d.epi, d.alpha = 0, 0, 1.0
+    check(lib.nk_gemm_ex(ctypes.byref(d), st), "attention bwd dK gemm")
+    _count(6)
+    return dq, dk, dv
+
+
+# ---- diffusion objective ----------------------------------------------------------------------
+def noise_mix(x: Tensor, noise: Tensor, sigma: Tensor, rectified_flow: bool = False) -> Tensor:
+    _req_cuda(x, noise, sigma)
+    x = x.float().contiguous()
+    noise = noise.float().contiguous()
+    sigma = sigma.float().contiguous()
+    z = torch.empty_like(x)
+    B = x.shape[0]
+    check(lib.nk_noise_mix(x.data_ptr(), noise.data_ptr(), sigma.data_ptr(), z.data_ptr(), B, x.numel() // B,
+                           int(rectified_flow), _stream()), "noise_mix")
+    _count()
+    return z
+
+
+# --------------------------------------------------------------------------------------------
+# autograd Functions
+# --------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b (+ residual); W, b are the fp32 parameters (reference layout [out, in])."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, out_f32):
+        w = bf16_weight(weight)
+        y = linear_fwd(x, w, f32_param(bias), residual, out_f32)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        if dy.dtype != BF16:
+            dy = cast_bf16(dy)
+        dy = dy.contiguous()
+        w = bf16_weight(weight)
+        dx = linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
+        dw = linear_wgrad(dy, x) if ctx.needs_input_grad[1] else None
+        db = colsum(dy)[0] if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dres = dy.view(-1, dy.shape[-1]).view(dy.shape) if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        return dx, dw, db, dres, None
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
+           out_f32: bool = False) -> Tensor:
+    return LinearFn.apply(x, weight, bias, residual, out_f32)
+
+
+class Conv2dFn(torch.autograd.Function):
+    """stride-1 3x3 (pad 1) / 1x1 convolution on NHWC bf16 (implicit GEMM).  Input channels must be
+    physically padded to >= 64 (zero) — `cin_phys = x.shape[-1]`."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bias_img, residual):
+        co, ci, ks, _ = weight.shape
+        wf, _ = packed_conv_weight(weight)
+        y = conv2d_fwd(x, wf, co, ks, f32_param(bias), bias_img, residual)
+        ctx.save_for_backward(x, weight)
+        ctx.flags = (bias is not None, bias_img is not None, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        co, ci, ks, _ = weight.shape
+        has_bias, has_bimg, has_res = ctx.flags
+        dy = dy.contiguous()
+        _, wd = packed_conv_weight(weight)
+        dx = dw = db = dbi = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = conv2d_fwd(dy, wd, x.shape[-1], ks)
+            if dx.shape[-1] != x.shape[-1]:
+                dx = dx[..., : x.shape[-1]].contiguous()
+        if ctx.needs_input_grad[1]:
+            dwp = conv2d_wgrad(dy, x, co, ks)
+            dw = conv_unpack_wgrad(dwp, co, ci, ks)
+        if (has_bias and ctx.needs_input_grad[2]) or (has_bimg and ctx.needs_input_grad[3]):
+            n = dy.shape[0]
+            s = colsum(dy, groups=n)[:, :co]
+            if has_bimg and ctx.needs_input_grad[3]:
+                dbi = s.contiguous()
+            if has_bias and ctx.needs_input_grad[2]:
+                db = colsum(dy)[0, :co].contiguous()
+        if has_res and ctx.needs_input_grad[4]:
+            dres = dy
+        return dx, dw, db, dbi, dres
+
+
+def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, bias_img: Optional[Tensor] = None,
+           residual: Optional[Tensor] = None) -> Tensor:
+    return Conv2dFn.apply(x, weight, bias, bias_img, residual)
+
+
+class ConvStridedFn(torch.autograd.Function):
+    """3x3 stride-2 convolution (UNet Downsample pad 1; VAE Downsample pad (0,1,0,1)) = im2col + GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pad_t, pad_l, ho, wo):
+        co, ci, ks, _ = weight.shape
+        wf, _ = packed_conv_weight(weight)
+        col = im2col(x, ks, 2, pad_t, pad_l, ho, wo)
+        y = linear_fwd(col, wf[:co], f32_param(bias))
+        ctx.save_for_backward(x, weight)
+        ctx.geom = (pad_t, pad_l, ho, wo)
+        ctx.has_bias = bias is not None
+        return y.view(x.shape[0], ho, wo, co)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        co, ci, ks, _ = weight.shape
+        pad_t, pad_l, ho, wo = ctx.geom
+        dy2 = dy.contiguous().view(-1, co)
+        wf, _ = packed_conv_weight(weight)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dcol = linear_dgrad(dy2, wf[:co])
+            dx = col2im(dcol, x.shape, ks, 2, pad_t, pad_l, ho, wo)
+        if ctx.needs_input_grad[1]:
+            col = im2col(x, ks, 2, pad_t, pad_l, ho, wo)
+            dwp = linear_wgrad(dy2, col)
+            dw = conv_unpack_wgrad(dwp, co, ci, ks)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2)[0]
+        return dx, dw, db, None, None, None, None
+
+
+def conv2d_stride2(x: Tensor, weight: Tensor, bias: Optional[Tensor], asymmetric: bool = False) -> Tensor:
+    n, h, w_, c = x.shape
+    if asymmetric:  # ConstantPad2d((0,1,0,1)) + conv k3 s2 p0
+        ho, wo = (h + 1 - 3) // 2 + 1, (w_ + 1 - 3) // 2 + 1
+        return ConvStridedFn.apply(x, weight, bias, 0, 0, ho, wo)
+    ho, wo = (h + 2 - 3) // 2 + 1, (w_ + 2 - 3) // 2 + 1
+    return ConvStridedFn.apply(x, weight, bias, 1, 1, ho, wo)
+
+
+class GroupNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, silu):
+        g, b = f32_param(gamma), f32_param(beta)
+        y, mean, rstd = groupnorm_fwd(x, g, b, groups, eps, silu)
+        ctx.save_for_backward(x, g, b, mean, rstd)
+        ctx.cfg = (groups, silu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, b, mean, rstd = ctx.saved_tensors
+        groups, silu = ctx.cfg
+        dx, dg, db = groupnorm_bwd(dy.contiguous(), x, g, b, mean, rstd, groups, silu)
+        return dx, dg, db, None, None, None
+
+
+def group_norm(x: Tensor, gamma: Tensor, beta: Tensor, groups: int = 32, eps: float = 1e-5, silu: bool = False):
+    return GroupNormFn.apply(x, gamma, beta, groups, eps, silu)
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        g, b = f32_param(gamma), f32_param(beta)
+        y, mean, rstd = layernorm_fwd(x, g, b, eps)
+        ctx.save_for_backward(x, g, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, mean, rstd = ctx.saved_tensors
+        dx, dg, db = layernorm_bwd(dy, x, g, mean, rstd)
+        return dx, dg, db, None
+
+
+def layer_norm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tensor:
+    return LayerNormFn.apply(x, gamma, beta, eps)
+
+
+class GegluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h):
+        ctx.save_for_backward(h)
+        return geglu_fwd(h)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (h,) = ctx.saved_tensors
+        return geglu_bwd(h, dout)
+
+
+def geglu(h: Tensor) -> Tensor:
+    return GegluFn.apply(h)
+
+
+class SiluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return silu_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return silu_bwd(x, dy if dy.dtype == BF16 else cast_bf16(dy))
+
+
+def silu(x: Tensor) -> Tensor:
+    return SiluFn.apply(x)
+
+
+class AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return add(a, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add_bf16(a: Tensor, b: Tensor) -> Tensor:
+    return AddFn.apply(a, b)
+
+
+class AttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, scale):
+        o, lse = attention_fwd(q, k, v, scale)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.scale = scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        dq, dk, dv = attention_bwd(do, q, k, v, o, lse, ctx.scale)
+        return dq, dk, dv, None
+
+
+def attention(q: Tensor, k: Tensor, v: Tensor, scale: Optional[float] = None) -> Tensor:
+    """softmax(scale * q k^T) v for (B, N, H, D) bf16 tensors."""
+    if scale is None:
+        scale = q.shape[-1] ** -0.5
+    return AttentionFn.apply(q, k, v, float(scale))
+
+
+class CatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.ca, ctx.cb = a.shape[-1], b.shape[-1]
+        return cat_channels(a, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        ca, cb = ctx.ca, ctx.cb
+        da = torch.empty((*dy.shape[:-1], ca), dtype=BF16, device=dy.device)
+        db = torch.empty((*dy.shape[:-1], cb), dtype=BF16, device=dy.device)
+        copy_channels(dy, da, ca)
+        copy_channels(dy[..., ca:], db, cb)
+        return da, db
+
+
+def cat(a: Tensor, b: Tensor) -> Tensor:
+    return CatFn.apply(a, b)
+
+
+class Upsample2xFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return upsample2x_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return upsample2x_bwd(dy.contiguous())
+
+
+def upsample2x(x: Tensor) -> Tensor:
+    return Upsample2xFn.apply(x)
+
+
+class ToNhwcFn(torch.autograd.Function):
+    """(N,C,H,W) float -> (N,H,W,Cpad) bf16 with optional per-image scale (c_in of the denoiser)."""
+
+    @staticmethod
+    def forward(ctx, x, cpad, scale):
+        ctx.c = x.shape[1]
+        ctx.save_for_backward(scale if scale is not None else torch.empty(0, device=x.device))
+        ctx.in_dtype = x.dtype
+        return nchw_to_nhwc(x, cpad, scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (scale,) = ctx.saved_tensors
+        dx = nhwc_to_nchw(dy.contiguous(), ctx.c, out_f32=True)
+        if scale.numel():
+            dx = dx * scale.view(-1, 1, 1, 1)
+        return dx.to(ctx.in_dtype), None, None
+
+
+def to_nhwc(x: Tensor, cpad: Optional[int] = None, scale: Optional[Tensor] = None) -> Tensor:
+    return ToNhwcFn.apply(x, cpad, scale)
+
+
+def lincomb_per_sample(x: Tensor, a: Tensor, y: Optional[Tensor] = None, c: Optional[Tensor] = None) -> Tensor:
+    """out[b] = a[b]*x[b] + c[b]*y[b] on fp32 tensors (no autograd)."""
+    _req_cuda(x)
+    x = x.float().contiguous()
+    a = a.float().contiguous()
+    B = x.shape[0]
+    out = torch.empty_like(x)
+    if y is not None:
+        y = y.float().contiguous()
+        c = c.float().contiguous()
+    check(lib.nk_lincomb_per_sample(x.data_ptr(), a.data_ptr(), _p(y), _p(c), out.data_ptr(), B, x.numel() // B,
+                                    _stream()), "lincomb_per_sample")
+    _count()
+    return out
+
+
+class DenoiseCombineFn(torch.autograd.Function):
+    """D = net * c_out[b] + z * c_skip[b] on (N,C,H,W) fp32 tensors (denoiser.py:53); grad flows to net."""
+
+    @staticmethod
+    def forward(ctx, net, z, c_out, c_skip):
+        c_out = c_out.float().reshape(-1).contiguous()
+        ctx.save_for_backward(c_out)
+        return lincomb_per_sample(net, c_out, z, None if z is None else c_skip.float().reshape(-1))
+
+    @staticmethod
+    def backward(ctx, dD):
+        (c_out,) = ctx.saved_tensors
+        return lincomb_per_sample(dD, c_out), None, None, None
+
+
+def denoise_combine(net: Tensor, z: Optional[Tensor], c_out: Tensor, c_skip: Tensor) -> Tensor:
+    return DenoiseCombineFn.apply(net, z, c_out, c_skip)
+
+
+class FromNhwcFn(torch.autograd.Function):
+    """(N,H,W,Cp) bf16 -> (N,C,H,W) fp32 taking the first C channels; backward re-pads with zeros."""
+
+    @staticmethod
+    def forward(ctx, y, c):
+        ctx.cp = y.shape[-1]
+        return nhwc_to_nchw(y, c, out_f32=True)
+
+    @staticmethod
+    def backward(ctx, d):
+        return nchw_to_nhwc(d.float().contiguous(), ctx.cp), None
+
+
+def from_nhwc_f32(y: Tensor, channels: int) -> Tensor:
+    return FromNhwcFn.apply(y, channels)
+
+
+class WeightedMseFn(torch.autograd.Function):
+    """loss[b] = w[b] * mean((D[b]-T[b])^2) in fp32 (loss.py:153-155, losses/functions.py:81-94)."""
+
+    @staticmethod
+    def forward(ctx, D, T, w):
+        D = D.float().contiguous()
+        T = T.float().contiguous()
+        w = w.float().contiguous()
+        B = D.shape[0]
+        loss = torch.empty((B,), dtype=F32, device=D.device)
+        check(lib.nk_weighted_mse_fwd(D.data_ptr(), T.data_ptr(), w.data_ptr(), loss.data_ptr(), B, D.numel() // B,
+                                      _stream()), "weighted_mse_fwd")
+        _count()
+        ctx.save_for_backward(D, T, w)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        D, T, w = ctx.saved_tensors
+        B = D.shape[0]
+        dD = torch.empty_like(D)
+        dl = dloss.float().contiguous()
+        check(lib.nk_weighted_mse_bwd(D.data_ptr(), T.data_ptr(), w.data_ptr(), dl.data_ptr(), dD.data_ptr(), B,
+                                      D.numel() // B, _stream()), "weighted_mse_bwd")
+        _count()
+        return dD, None, None
+
+
+def weighted_mse(D: Tensor, T: Tensor, w: Tensor) -> Tensor:
+    return WeightedMseFn.apply(D, T, w)
