@@ -1,0 +1,268 @@
+"""Per-kernel parity on the GPU: every C-ABI op against a plain PyTorch fp32 reference of the same op
+(floating-point kernels: bf16 storage, fp32 accumulation — tolerance = relative L2 error stated per test)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from neurosis_b200 import ops
+
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+def rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ---------------------------------------------------------------- linear / GEMM
+@pytest.mark.parametrize("M,N,K", [(256, 320, 320), (300, 328, 200), (2, 1280, 320), (1024, 10240, 1280), (77 * 2, 640, 2048)])
+def test_linear_fwd_bwd(M, N, K):
+    x = rnd(M, K).to(BF).requires_grad_(True)
+    w = (rnd(N, K, seed=1) * K ** -0.5).requires_grad_(True)
+    b = rnd(N, seed=2).requires_grad_(True)
+    r = rnd(M, N, seed=3).to(BF).requires_grad_(True)
+    y = ops.linear(x, w, b, r)
+    gy = rnd(M, N, seed=4).to(BF)
+    y.backward(gy)
+    xr, wr, br, rr = (t.detach().float().requires_grad_(True) for t in (x, w.to(BF), b, r))
+    yr = F.linear(xr, wr, br) + rr
+    yr.backward(gy.float())
+    assert rel(y, yr) < 6e-3
+    assert rel(x.grad, xr.grad) < 6e-3
+    assert rel(w.grad, wr.grad) < 6e-3
+    assert rel(b.grad, br.grad) < 6e-3
+    assert rel(r.grad, rr.grad) < 1e-6
+
+
+def test_linear_out_f32():
+    x, w = rnd(64, 320).to(BF), rnd(640, 320, seed=1) * 0.05
+    y = ops.linear(x, w, None, None, True)
+    assert y.dtype == torch.float32
+    assert rel(y, x.float() @ w.to(BF).float().t()) < 1e-5
+
+
+# ---------------------------------------------------------------- convolution (implicit GEMM)
+@pytest.mark.parametrize("n,h,w,ci,co", [(2, 32, 32, 64, 128), (1, 16, 16, 320, 320), (2, 64, 64, 128, 64),
+                                         (1, 36, 28, 64, 64), (1, 8, 8, 1280, 640), (1, 128, 128, 64, 64)])
+def test_conv3x3_fwd_bwd(n, h, w, ci, co):
+    x = rnd(n, h, w, ci).to(BF).requires_grad_(True)
+    wt = (rnd(co, ci, 3, 3, seed=1) * (9 * ci) ** -0.5).requires_grad_(True)
+    b = rnd(co, seed=2).requires_grad_(True)
+    bi = rnd(n, co, seed=3).requires_grad_(True)
+    r = rnd(n, h, w, co, seed=4).to(BF).requires_grad_(True)
+    y = ops.conv2d(x, wt, b, bi, r)
+    gy = rnd(n, h, w, co, seed=5).to(BF)
+    y.backward(gy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.detach().to(BF).float().requires_grad_(True)
+    br, bir = b.detach().clone().requires_grad_(True), bi.detach().clone().requires_grad_(True)
+    rr = r.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, padding=1) + bir[:, :, None, None] + rr
+    yr.backward(gy.float().permute(0, 3, 1, 2))
+    assert rel(y.permute(0, 3, 1, 2), yr) < 6e-3
+    assert rel(x.grad.permute(0, 3, 1, 2), xr.grad) < 6e-3
+    assert rel(wt.grad, wr.grad) < 6e-3
+    assert rel(b.grad, br.grad) < 6e-3
+    assert rel(bi.grad, bir.grad) < 6e-3
+    assert rel(r.grad.permute(0, 3, 1, 2), rr.grad) < 1e-6
+
+
+def test_conv_thin_channels():
+    """stem (4 -> 64, input zero-padded to 64 channels) and head (64 -> 4, output padded to 64)."""
+    n, h, w = 2, 16, 16
+    x4 = rnd(n, 4, h, w)
+    xn = ops.to_nhwc(x4, 64)
+    assert xn.shape == (n, h, w, 64) and float(xn[..., 4:].abs().sum()) == 0.0
+    w1 = (rnd(64, 4, 3, 3, seed=1) * 0.2).requires_grad_(True)
+    y1 = ops.conv2d(xn, w1, None, None, None)
+    w2 = (rnd(4, 64, 3, 3, seed=2) * 0.05).requires_grad_(True)
+    y2 = ops.conv2d(y1, w2, None, None, None)
+    assert y2.shape == (n, h, w, 64) and float(y2[..., 4:].abs().sum()) == 0.0
+    out = ops.from_nhwc_f32(y2, 4)
+    g = rnd(n, 4, h, w, seed=3)
+    out.backward(g)
+    w1r, w2r = (t.detach().to(BF).float().requires_grad_(True) for t in (w1, w2))
+    y1r = F.conv2d(x4.to(BF).float(), w1r, padding=1)
+    outr = F.conv2d(y1r, w2r, padding=1)
+    outr.backward(g)
+    assert rel(out, outr) < 1e-2
+    assert rel(w1.grad, w1r.grad) < 1.5e-2
+    assert rel(w2.grad, w2r.grad) < 1.5e-2
+
+
+@pytest.mark.parametrize("asym", [False, True])
+def test_conv_stride2(asym):
+    n, h, w, c = 2, 32, 32, 128
+    x = rnd(n, h, w, c).to(BF).requires_grad_(True)
+    wt = (rnd(c, c, 3, 3, seed=1) * (9 * c) ** -0.5).requires_grad_(True)
+    b = rnd(c, seed=2).requires_grad_(True)
+    y = ops.conv2d_stride2(x, wt, b, asymmetric=asym)
+    gy = rnd(*y.shape, seed=3).to(BF)
+    y.backward(gy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr, br = wt.detach().to(BF).float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = F.conv2d(F.pad(xr, (0, 1, 0, 1)), wr, br, stride=2) if asym else F.conv2d(xr, wr, br, stride=2, padding=1)
+    assert yr.shape == y.permute(0, 3, 1, 2).shape
+    yr.backward(gy.float().permute(0, 3, 1, 2))
+    assert rel(y.permute(0, 3, 1, 2), yr) < 6e-3
+    assert rel(x.grad.permute(0, 3, 1, 2), xr.grad) < 8e-3
+    assert rel(wt.grad, wr.grad) < 6e-3
+    assert rel(b.grad, br.grad) < 6e-3
+
+
+# ---------------------------------------------------------------- normalisation
+@pytest.mark.parametrize("n,hw,c,silu,eps", [(2, 32, 320, True, 1e-5), (1, 16, 2560, True, 1e-5), (2, 64, 128, True, 1e-6),
+                                              (3, 24, 640, False, 1e-6), (1, 7, 960, True, 1e-5)])
+def test_groupnorm_fwd_bwd(n, hw, c, silu, eps):
+    x = (rnd(n, hw, hw, c) * 2 + 0.5).to(BF).requires_grad_(True)
+    g = (1 + 0.2 * rnd(c, seed=1)).requires_grad_(True)
+    b = (0.1 * rnd(c, seed=2)).requires_grad_(True)
+    y = ops.group_norm(x, g, b, 32, eps, silu)
+    gy = rnd(n, hw, hw, c, seed=3).to(BF)
+    y.backward(gy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    gr, br = g.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = F.group_norm(xr, 32, gr, br, eps)
+    yr = F.silu(yr) if silu else yr
+    yr.backward(gy.float().permute(0, 3, 1, 2))
+    assert rel(y.permute(0, 3, 1, 2), yr) < 5e-3
+    assert rel(x.grad.permute(0, 3, 1, 2), xr.grad) < 8e-3
+    assert rel(g.grad, gr.grad) < 5e-3
+    assert rel(b.grad, br.grad) < 5e-3
+
+
+@pytest.mark.parametrize("rows,c", [(2048, 640), (1000, 1280), (77, 320)])
+def test_layernorm_fwd_bwd(rows, c):
+    x = (rnd(rows, c) * 1.5 + 0.3).to(BF).requires_grad_(True)
+    g = (1 + 0.2 * rnd(c, seed=1)).requires_grad_(True)
+    b = (0.1 * rnd(c, seed=2)).requires_grad_(True)
+    y = ops.layer_norm(x, g, b, 1e-5)
+    gy = rnd(rows, c, seed=3).to(BF)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    gr, br = g.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (c,), gr, br, 1e-5)
+    yr.backward(gy.float())
+    assert rel(y, yr) < 5e-3
+    assert rel(x.grad, xr.grad) < 8e-3
+    assert rel(g.grad, gr.grad) < 5e-3
+    assert rel(b.grad, br.grad) < 5e-3
+
+
+# ---------------------------------------------------------------- elementwise
+def test_geglu_fwd_bwd():
+    h = rnd(512, 2 * 640).to(BF).requires_grad_(True)
+    y = ops.geglu(h)
+    gy = rnd(512, 640, seed=1).to(BF)
+    y.backward(gy)
+    hr = h.detach().float().requires_grad_(True)
+    a, gate = hr.chunk(2, dim=-1)
+    yr = a * F.gelu(gate)
+    yr.backward(gy.float())
+    assert rel(y, yr) < 4e-3 and rel(h.grad, hr.grad) < 6e-3
+
+
+def test_silu_add_cat_upsample():
+    x = rnd(4, 1280).to(BF).requires_grad_(True)
+    y = ops.silu(x)
+    y.backward(torch.ones_like(y))
+    xr = x.detach().float().requires_grad_(True)
+    F.silu(xr).sum().backward()
+    assert rel(y, F.silu(xr)) < 4e-3 and rel(x.grad, xr.grad) < 5e-3
+    a, b = rnd(2, 8, 8, 64).to(BF), rnd(2, 8, 8, 128, seed=1).to(BF)
+    assert torch.equal(ops.cat(a, b), torch.cat([a, b], -1))
+    assert torch.equal(ops.add_bf16(a, a), (a.float() * 2).to(BF))
+    u = ops.upsample2x(a)
+    assert torch.equal(u.permute(0, 3, 1, 2), F.interpolate(a.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest").to(BF))
+    ar = a.clone().requires_grad_(True)
+    ops.upsample2x(ar).backward(torch.ones_like(u))
+    assert torch.equal(ar.grad, torch.full_like(a, 4.0))
+    c2 = ops.cat(a.clone().requires_grad_(True), b.clone().requires_grad_(True))
+    assert c2.shape[-1] == 192
+
+
+def test_timestep_embedding_and_layout():
+    t = torch.tensor([0, 17, 999], device=DEV)
+    e = ops.timestep_embedding(t, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=DEV) / half)
+    args = t[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert (e.float() - ref).abs().max() < 1e-2  # bf16 storage of values in [-1,1]
+    x = rnd(2, 4, 8, 8)
+    n = ops.nchw_to_nhwc(x, 64, torch.tensor([2.0, 0.5], device=DEV))
+    assert rel(n[..., :4].permute(0, 3, 1, 2), x * torch.tensor([2.0, 0.5], device=DEV).view(2, 1, 1, 1)) < 4e-3
+    back = ops.nhwc_to_nchw(n, 4)
+    assert back.shape == (2, 4, 8, 8) and back.dtype == torch.float32
+
+
+# ---------------------------------------------------------------- attention
+def sdpa_ref(q, k, v, scale):
+    qf, kf, vf = (t.float().transpose(1, 2) for t in (q, k, v))  # (B,H,N,D)
+    w = torch.softmax(qf @ kf.transpose(-1, -2) * scale, -1)
+    return (w @ vf).transpose(1, 2)
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,D", [(2, 4, 256, 256, 64), (1, 2, 1024, 1024, 64), (2, 3, 200, 77, 64), (1, 5, 1008, 1008, 64),
+                                         (1, 1, 128, 300, 64), (2, 8, 256, 256, 40), (1, 2, 320, 77, 160), (1, 1, 512, 512, 512)])
+def test_attention_fwd_bwd(B, H, Nq, Nk, D):
+    q = rnd(B, Nq, H, D).to(BF).requires_grad_(True)
+    k = rnd(B, Nk, H, D, seed=1).to(BF).requires_grad_(True)
+    v = rnd(B, Nk, H, D, seed=2).to(BF).requires_grad_(True)
+    scale = D ** -0.5
+    o = ops.attention(q, k, v, scale)
+    go = rnd(B, Nq, H, D, seed=3).to(BF)
+    o.backward(go)
+    qr, kr, vr = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    orf = sdpa_ref(qr, kr, vr, scale)
+    orf.backward(go.float())
+    assert rel(o, orf) < 1e-2
+    assert rel(q.grad, qr.grad) < 2e-2
+    assert rel(k.grad, kr.grad) < 2e-2
+    assert rel(v.grad, vr.grad) < 2e-2
+
+
+def test_attention_strided_qkv_views():
+    """q/k/v as column slices of one fused projection output (row stride 3*H*D)."""
+    B, N, H, D = 2, 384, 5, 64
+    qkv = rnd(B, N, 3 * H * D).to(BF)
+    q, k, v = (qkv[..., i * H * D:(i + 1) * H * D].view(B, N, H, D) for i in range(3))
+    o, lse = ops.attention_fwd(q, k, v, D ** -0.5)
+    assert rel(o, sdpa_ref(q, k, v, D ** -0.5)) < 1e-2
+    qf, kf = q.float().transpose(1, 2), k.float().transpose(1, 2)
+    lse_ref = torch.logsumexp(qf @ kf.transpose(-1, -2) * D ** -0.5, -1)
+    assert (lse - lse_ref).abs().max() < 2e-2
+
+
+# ---------------------------------------------------------------- diffusion objective kernels
+def test_objective_kernels():
+    B = 3
+    x, nz = rnd(B, 4, 16, 16), rnd(B, 4, 16, 16, seed=1)
+    sig = torch.tensor([0.1, 2.0, 14.0], device=DEV)
+    z = ops.noise_mix(x, nz, sig)
+    assert torch.allclose(z, x + sig.view(B, 1, 1, 1) * nz, atol=1e-6)
+    zr = ops.noise_mix(x, nz, sig * 0.05, rectified_flow=True)
+    assert torch.allclose(zr, (1 - sig.view(B, 1, 1, 1) * 0.05) * x + sig.view(B, 1, 1, 1) * 0.05 * nz, atol=1e-6)
+    net = rnd(B, 4, 16, 16, seed=2).requires_grad_(True)
+    c_out, c_skip = -sig, torch.ones_like(sig)
+    D_ = ops.denoise_combine(net, z, c_out, c_skip)
+    w = sig ** -2.0
+    loss = ops.weighted_mse(D_, x, w)
+    loss.mean().backward()
+    netr = net.detach().clone().requires_grad_(True)
+    Dr = netr * c_out.view(B, 1, 1, 1) + z * c_skip.view(B, 1, 1, 1)
+    lr = ((Dr - x) ** 2).flatten(1).mean(1) * w
+    lr.mean().backward()
+    assert torch.allclose(loss, lr, rtol=1e-5)
+    assert rel(net.grad, netr.grad) < 1e-5
