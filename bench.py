@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one SDXL diffusion training step per "step"
+(VAE latent encode of 1024^2 images, no-grad  ->  noise/sigma preconditioning  ->  UNetModel forward
+ ->  weighted MSE  ->  backward  ->  bucketed gradient all-reduce when N > 1).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...          (N > 1: one rank per GPU, NCCL)
+
+Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM (CUDA-event timed, max over ranks);
+`e2e` = the same metric through the public API (engine.training_step) with pinned HOST batches copied in and the
+loss read back every step.  `--impl reference` times the CPU restatement of the reference path (oracle/) on the host
+cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SDXL_UNET = dict(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=[4, 2],
+                 channel_mult=[1, 2, 4], num_head_channels=64, transformer_depth=[1, 2, 10], context_dim=2048,
+                 use_linear_in_transformer=True, num_classes="sequential", adm_in_channels=2816,
+                 spatial_transformer_attn_type="b200", use_checkpoint=False)  # configs/sdxl/sdxl.example.yaml:68-84
+SDXL_VAE = dict(ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], in_channels=3,
+                resolution=256, z_channels=4, double_z=True)                    # configs/sdxl/sdxl.example.yaml:102-113
+GFLOP_UNET_STEP = 20283.7   # per image, fwd + bwd (3x fwd), SURVEY.md §8d
+GFLOP_VAE_ENC = 4879.0      # per image, 1024^2 encode
+GFLOP_STEP = GFLOP_UNET_STEP + GFLOP_VAE_ENC
+METRIC = "sdxl_unet_train_images_per_sec_1024px_bf16"
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"tflops": d.get("bf16_tflops_sustained", 1395.3), "hbm": d.get("hbm_gbs", 6454.0), "src": "measured"}
+    return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.rows: list[list[str]] = []
+        self.proc = None
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        # samples under load only (upper half), median
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle port on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(steps: int, warmup: int, latent: int = 32) -> dict:
+    """SDXL UNet (full width/depth, random weights) loss fwd+bwd + VAE encode on the CPU through the oracle at a
+    reduced resolution; converted to 1024^2 images/s by the algorithmic-FLOP ratio (stated in `sample`)."""
+    import torch
+    from oracle import objective as O
+    from oracle.unet import unet_forward, unet_param_shapes
+    from oracle.vae import vae_encode, vae_param_shapes
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(42)
+    sd = {}
+    for k, shp in unet_param_shapes(SDXL_UNET).items():
+        t = torch.randn(shp, generator=g) * (0.02 if len(shp) > 1 else 0.05)
+        if len(shp) == 1 and k.endswith(".weight"):
+            t = t + 1.0
+        sd[k] = t.requires_grad_(True)
+    vsd = {k: torch.randn(s, generator=g) * 0.02 + (1.0 if (len(s) == 1 and k.endswith("weight")) else 0.0)
+           for k, s in vae_param_shapes(SDXL_VAE, 4, True).items()}
+    table = O.ddpm_sigma_table(1000)
+    B, px = 1, latent * 8
+    img = torch.rand(B, 3, px, px, generator=g) * 2 - 1
+    cond = {"crossattn": torch.randn(B, 77, 2048, generator=g), "vector": torch.randn(B, 2816, generator=g)}
+    net = lambda x, t, c: unet_forward(sd, SDXL_UNET, x, t, c["crossattn"], c["vector"])  # noqa: E731
+    # algorithmic FLOPs of the sample: token-proportional terms scale with (latent/128)^2; attention with ^4
+    r2 = (latent / 128.0) ** 2
+    unet_lin_conv = (6761.2 - 751.6 - 32.3) * r2
+    attn = 751.6 * r2 * r2 + 32.3 * r2
+    vae = (4879.0 - 550.0) * r2 + 550.0 * r2 * r2
+    sample_gflop = 3 * (unet_lin_conv + attn) + vae
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            z = 0.13025 * vae_encode(vsd, SDXL_VAE, img)
+        sig = table[torch.randint(0, 1000, (B,), generator=g)].clamp_min(0.03)
+        loss = O.diffusion_loss(net, table, z, cond, sig, torch.randn(z.shape, generator=g))
+        loss.mean().backward()
+        for v in sd.values():
+            v.grad = None
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    gflops = sample_gflop / sec
+    return {"img_per_s": gflops / GFLOP_STEP, "sec_per_sample_step": sec, "cores": cores, "gflops": gflops,
+            "sample": (f"SDXL UNet (full 2.57B params) loss fwd+bwd + VAE encode via the CPU oracle at {px}x{px} px "
+                       f"(latent {latent}x{latent}), B=1, fp32, {cores} threads: {sample_gflop:.0f} algorithmic GFLOP in "
+                       f"{sec:.2f} s; images/s quoted at 1024x1024 by the FLOP ratio ({GFLOP_STEP:.0f} GFLOP/img)")}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_sample(max(1, args.steps), max(0, min(args.warmup, 1)))
+    line = {"impl": "reference", "metric": METRIC, "value": r["img_per_s"], "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_sample_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SDXL base UNet 1024x1024 training step (VAE encode + loss + backward)",
+                       "note": "reference's CPU path restated in oracle/ (reference is pure PyTorch; lightning-dependent glue restated)"},
+            "cpu_baseline": {"value": r["img_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port",
+                             "sample": r["sample"]},
+            "e2e": {"value": r["img_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_engine(dev, seed: int = 42):
+    import torch
+    from neurosis_b200.engine import DiffusionEngine
+    from neurosis_b200.modules import UNetModel
+    from neurosis_b200.modules.conditioner import GeneralConditioner, IdentityEncoder
+    from neurosis_b200.modules.denoiser import DiscreteDenoiser, EpsPreconditioning, EpsWeighting
+    from neurosis_b200.modules.loss import StandardDiffusionLoss
+    from neurosis_b200.modules.schedule import DiscreteSigmaGenerator, LegacyDDPMDiscretization
+    from neurosis_b200.modules.vae import Encoder
+
+    torch.manual_seed(seed)  # identical weights on every rank
+    with torch.device(dev):
+        unet = UNetModel(**SDXL_UNET)
+        enc = Encoder(**SDXL_VAE, embed_dim=4, standalone=True)
+    with torch.no_grad():  # re-draw the zero-initialised layers, otherwise most gradients are identically zero
+        for name, p in unet.named_parameters():
+            if float(p.abs().sum()) == 0.0 and p.dim() > 1:
+                p.normal_(0.0, 0.02)
+
+    class RandIdxSigma(DiscreteSigmaGenerator):
+        """harness-side draw: the reference's `t=None` randint branch (its loss passes t in [0,1) which always
+        selects sigma = 0 and yields NaN with EpsWeighting — SURVEY.md §0.7)."""
+
+        def __call__(self, n, t=None):
+            return super().__call__(n, None).clamp_min(0.03)
+
+    return DiffusionEngine(
+        unet, DiscreteDenoiser(EpsPreconditioning(), 1000, LegacyDDPMDiscretization()), enc,
+        GeneralConditioner([IdentityEncoder(input_key="crossattn_emb"), IdentityEncoder(input_key="vector_emb")]),
+        StandardDiffusionLoss(RandIdxSigma(LegacyDDPMDiscretization(), 1000), EpsWeighting()),
+        scale_factor=0.13025, vae_batch_size=None).to(dev)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("NK_BENCH_BATCH", "8")), help="images per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from neurosis_b200 import ops
+    from neurosis_b200.ddp import BucketedGradReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    B = args.batch
+    eng = build_engine(dev)
+    params = [p for p in eng.model.parameters() if p.requires_grad]
+    reducer = BucketedGradReducer(params, bucket_mb=256.0)
+
+    g = torch.Generator().manual_seed(42 + rank)  # per-rank data
+    host = {"image": (torch.rand(B, 3, 1024, 1024, generator=g) * 2 - 1).pin_memory(),
+            "crossattn_emb": torch.randn(B, 77, 2048, generator=g).pin_memory(),
+            "vector_emb": torch.randn(B, 2816, generator=g).pin_memory()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def step(batch: dict, read_loss: bool) -> float:
+        reducer.zero_grad()
+        loss = eng.training_step(dict(batch))
+        loss.backward()
+        reducer.finish()
+        return loss.item() if read_loss else 0.0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k: int, fn) -> float:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(W):
+        step(resident, False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ops.LAUNCHES
+    ms_dev = timed(args.steps, lambda: step(resident, False))
+    launches = ops.LAUNCHES - l0
+    ms_e2e = timed(args.steps, lambda: step({k: v.to(dev, non_blocking=True) for k, v in host.items()}, True))
+    clocks = sampler.stop() if sampler else None
+
+    # per-kernel roofline of the dominant kernel (gemm_tc_kernel): CUDA events around every launch of one extra step
+    pk = peaks()
+    roof = None
+    if not args.no_profile:
+        ops.PROFILE_GEMM = []
+        step(resident, False)
+        torch.cuda.synchronize()
+        recs, ops.PROFILE_GEMM = ops.PROFILE_GEMM, None
+        t_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+        fl = sum(f for _, _, f in recs)
+        ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+        roof = {"kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "bound": "tensor", "achieved": ach,
+                "peak": pk["tflops"], "peak_source": pk["src"] + " sustained bf16", "unit": "TFLOP/s",
+                "frac": ach / pk["tflops"], "traffic": None, "launches": len(recs),
+                "share_of_step": t_ms / (ms_dev / args.steps) if ms_dev > 0 else None,
+                "alg_tflop_per_step": fl / 1e12}
+
+    if rank == 0:
+        ips = world * B * args.steps / (ms_dev * 1e-3)
+        ips_e2e = world * B * args.steps / (ms_e2e * 1e-3)
+        line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "SDXL base UNet (configs/sdxl) 1024x1024 training step: VAE encode + diffusion loss + backward"
+                                       + (" + bucketed NCCL gradient all-reduce" if world > 1 else ""),
+                           "batch_per_gpu": B, "global_batch": B * world, "latent": "128x128x4",
+                           "parallelism": f"dp{world}", "l2": "working set (5 GB bf16 weights + activations) >> 126 MB L2",
+                           "step_tflop_algorithmic": GFLOP_STEP * B / 1e3,
+                           "mfu_vs_peak": ips / world * GFLOP_STEP * 1e9 / (pk["tflops"] * 1e12)},
+                "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof}
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_sample(1, 1)
+            line["cpu_baseline"] = {"value": r["img_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

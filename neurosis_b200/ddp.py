@@ -1,0 +1,124 @@
+"""Data-parallel gradient reduction for the training step: bucketed all-reduce overlapped with backward.
+
+The reference never calls a collective itself — Lightning's `strategy: auto` wraps the module in torch DDP
+(25 MiB buckets, fp32 grads).  Here the reducer is explicit and sized for NVLink 5 / NVSwitch:
+
+  * parameters are grouped, in reverse registration order (the order backward produces gradients), into buckets of
+    `bucket_mb` (default 256 MiB — NVSwitch saturates only on large messages, link count is not the limit);
+  * every parameter's `.grad` is a VIEW into its bucket's flat fp32 buffer, so no pack/unpack kernels exist;
+  * `register_post_accumulate_grad_hook` counts ready gradients; when a bucket is complete its all-reduce is
+    enqueued on a side stream (after an event on the compute stream) and runs while backward continues;
+  * `finish()` makes the compute stream wait for the outstanding reductions.
+
+Works with NCCL (CUDA tensors, op AVG) and with gloo (CPU tensors, SUM then scale) — the latter is what the
+world_size-2 CPU tests exercise.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+class BucketedGradReducer:
+    def __init__(self, params: Iterable[nn.Parameter], bucket_mb: float = 256.0,
+                 process_group: Optional[dist.ProcessGroup] = None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.buckets: list[dict] = []
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        cur: list[nn.Parameter] = []
+        n = 0
+        for p in reversed(self.params):
+            if cur and n + p.numel() > cap:
+                self._make_bucket(cur)
+                cur, n = [], 0
+            cur.append(p)
+            n += p.numel()
+        if cur:
+            self._make_bucket(cur)
+        self._index = {}
+        for bi, b in enumerate(self.buckets):
+            for p in b["params"]:
+                self._index[p] = bi
+        self.enabled = True
+        self._works: list = []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        dev = self.params[0].device
+        self._cuda = dev.type == "cuda"
+        self._stream = torch.cuda.Stream(device=dev) if self._cuda else None
+
+    def _make_bucket(self, ps: list) -> None:
+        total = sum(p.numel() for p in ps)
+        flat = torch.zeros(total, dtype=torch.float32, device=ps[0].device)
+        off = 0
+        for p in ps:
+            p.grad = flat[off: off + p.numel()].view_as(p)
+            off += p.numel()
+        self.buckets.append({"params": ps, "flat": flat, "pending": len(ps)})
+
+    # -- per step ---------------------------------------------------------------------------------
+    def zero_grad(self) -> None:
+        for b in self.buckets:
+            b["flat"].zero_()
+            b["pending"] = len(b["params"])
+            for p, view in zip(b["params"], self._views(b)):
+                if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                    p.grad = view
+
+    def _views(self, b: dict):
+        off = 0
+        for p in b["params"]:
+            yield b["flat"][off: off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def _on_grad(self, p: nn.Parameter) -> None:
+        if not self.enabled or self.world == 1:
+            return
+        b = self.buckets[self._index[p]]
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            self._launch(b)
+
+    def _launch(self, b: dict) -> None:
+        flat = b["flat"]
+        if self._cuda:
+            ev = torch.cuda.current_stream().record_event()
+            with torch.cuda.stream(self._stream):
+                self._stream.wait_event(ev)
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._works.append((w, flat))
+
+    def finish(self) -> None:
+        """call after backward: every bucket has been reduced when this returns (stream-ordered on CUDA)."""
+        if self.world == 1:
+            return
+        for b in self.buckets:  # parameters that received no gradient this step still take part
+            if b["pending"] > 0:
+                self._launch(b)
+                b["pending"] = 0
+        if self._cuda:
+            torch.cuda.current_stream().wait_stream(self._stream)
+        else:
+            for w, flat in self._works:
+                w.wait()
+                flat.div_(self.world)
+            self._works.clear()
+
+    def no_sync(self):
+        """context manager: accumulate locally, skip the reduction (gradient accumulation micro-steps)."""
+        reducer = self
+
+        class _Ctx:
+            def __enter__(self):
+                reducer.enabled = False
+
+            def __exit__(self, *a):
+                reducer.enabled = True
+
+        return _Ctx()

@@ -26,6 +26,19 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 LAUNCHES = 0  # number of kernel-launching C-ABI calls made (bench.py reports it)
+PROFILE_GEMM = None  # bench.py sets this to a list: (start_event, end_event, algorithmic_flops) per tensor-core launch
+
+
+def _tc(rc_fn, what: str, flops: float, *args) -> None:
+    """call a tensor-core GEMM entry point; optionally bracket it with CUDA events for the roofline report."""
+    if PROFILE_GEMM is None:
+        check(rc_fn(*args), what)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(rc_fn(*args), what)
+    e1.record()
+    PROFILE_GEMM.append((e0, e1, flops))
 
 
 def _stream() -> int:
@@ -137,9 +150,8 @@ def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, residual: Op
         r2 = residual.reshape(-1, N)
         if r2.stride(-1) != 1:
             r2 = r2.contiguous()
-    check(lib.nk_linear_fwd(x2.data_ptr(), x2.stride(0), w.data_ptr(), w.stride(0), _p(bias), _p(r2),
-                            r2.stride(0) if r2 is not None else 0, y.data_ptr(), N, int(out_f32), M, N, K, _stream()),
-          "linear_fwd")
+    _tc(lib.nk_linear_fwd, "linear_fwd", 2.0 * M * N * K, x2.data_ptr(), x2.stride(0), w.data_ptr(), w.stride(0),
+        _p(bias), _p(r2), r2.stride(0) if r2 is not None else 0, y.data_ptr(), N, int(out_f32), M, N, K, _stream())
     _count()
     return y.view(*x.shape[:-1], N)
 
@@ -153,9 +165,8 @@ def linear_dgrad(dy: Tensor, w: Tensor, residual: Optional[Tensor] = None) -> Te
     M = d2.shape[0]
     dx = torch.empty((M, K), dtype=BF16, device=dy.device)
     r2 = residual.reshape(-1, K) if residual is not None else None
-    check(lib.nk_linear_dgrad(d2.data_ptr(), d2.stride(0), w.data_ptr(), w.stride(0), _p(r2),
-                              r2.stride(0) if r2 is not None else 0, dx.data_ptr(), K, M, N, K, _stream()),
-          "linear_dgrad")
+    _tc(lib.nk_linear_dgrad, "linear_dgrad", 2.0 * M * N * K, d2.data_ptr(), d2.stride(0), w.data_ptr(), w.stride(0),
+        _p(r2), r2.stride(0) if r2 is not None else 0, dx.data_ptr(), K, M, N, K, _stream())
     _count()
     return dx.view(*dy.shape[:-1], K)
 
@@ -173,8 +184,8 @@ def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     M = d2.shape[0]
     acc = out is not None
     dw = out if acc else torch.empty((N, K), dtype=F32, device=dy.device)
-    check(lib.nk_linear_wgrad(d2.data_ptr(), d2.stride(0), x2.data_ptr(), x2.stride(0), dw.data_ptr(), dw.stride(0),
-                              int(acc), M, N, K, _stream()), "linear_wgrad")
+    _tc(lib.nk_linear_wgrad, "linear_wgrad", 2.0 * M * N * K, d2.data_ptr(), d2.stride(0), x2.data_ptr(), x2.stride(0),
+        dw.data_ptr(), dw.stride(0), int(acc), M, N, K, _stream())
     _count()
     return dw
 
@@ -203,9 +214,9 @@ def conv2d_fwd(x: Tensor, wp: Tensor, cout: int, ksize: int, bias: Optional[Tens
         y = torch.zeros((n, h, w_, cop), dtype=BF16, device=x.device)
     else:
         y = torch.empty((n, h, w_, cop), dtype=BF16, device=x.device)
-    check(lib.nk_conv2d_fwd(x.data_ptr(), x.stride(2), wp.data_ptr(), _p(bias), _p(bias_img), _p(residual),
-                            residual.stride(2) if residual is not None else 0, y.data_ptr(), cop, n, h, w_, cin, cout,
-                            ksize, _stream()), "conv2d_fwd")
+    _tc(lib.nk_conv2d_fwd, "conv2d_fwd", 2.0 * n * h * w_ * cout * ksize * ksize * cin, x.data_ptr(), x.stride(2),
+        wp.data_ptr(), _p(bias), _p(bias_img), _p(residual), residual.stride(2) if residual is not None else 0,
+        y.data_ptr(), cop, n, h, w_, cin, cout, ksize, _stream())
     _count()
     return y
 
@@ -214,8 +225,8 @@ def conv2d_wgrad(dy: Tensor, x: Tensor, cout: int, ksize: int) -> Tensor:
     """packed fp32 gradient [cout, taps, Cin_phys]."""
     n, h, w_, cin = x.shape
     dwp = torch.zeros((cout, ksize * ksize, cin), dtype=F32, device=x.device)
-    check(lib.nk_conv2d_wgrad(dy.data_ptr(), dy.stride(2), x.data_ptr(), x.stride(2), dwp.data_ptr(), n, h, w_, cin,
-                              cout, ksize, _stream()), "conv2d_wgrad")
+    _tc(lib.nk_conv2d_wgrad, "conv2d_wgrad", 2.0 * n * h * w_ * cout * ksize * ksize * cin, dy.data_ptr(), dy.stride(2),
+        x.data_ptr(), x.stride(2), dwp.data_ptr(), n, h, w_, cin, cout, ksize, _stream())
     _count()
     return dwp
 
@@ -475,7 +486,7 @@ def attention_fwd(q: Tensor, k: Tensor, v: Tensor, scale: float):
     d.M, d.N, d.K, d.nb2, d.nb1, d.ksize = Nq, Nk, D, H, B, 1
     d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = S.data_ptr(), Nk, Nq * Nk, H * Nq * Nk
     d.out, d.epi, d.alpha = 1, 0, 1.0
-    check(lib.nk_gemm_ex(ctypes.byref(d), _stream()), "attention S gemm")
+    _tc(lib.nk_gemm_ex, "attention S gemm", 2.0 * d.M * d.N * d.K * d.nb1 * d.nb2, ctypes.byref(d), _stream())
     Nkp = (Nk + 7) // 8 * 8
     P = torch.empty((B, H, Nq, Nkp), dtype=BF16, device=q.device) if Nkp == Nk else torch.zeros(
         (B, H, Nq, Nkp), dtype=BF16, device=q.device)
@@ -498,7 +509,7 @@ def _pv(P: Tensor, v: Tensor, o: Tensor, Nk: int) -> None:
     d.M, d.N, d.K, d.nb2, d.nb1, d.ksize = Nq, D, Nk, H, B, 1
     d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = o.data_ptr(), o.stride(1), o.stride(2), o.stride(0)
     d.out, d.epi, d.alpha = 0, 0, 1.0
-    check(lib.nk_gemm_ex(ctypes.byref(d), _stream()), "attention PV gemm")
+    _tc(lib.nk_gemm_ex, "attention PV gemm", 2.0 * d.M * d.N * d.K * d.nb1 * d.nb2, ctypes.byref(d), _stream())
 
 
 def attention_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, scale: float):
@@ -529,7 +540,7 @@ def attention_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: T
     d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = P.data_ptr(), Nkp, Nq * Nkp, H * Nq * Nkp
     d.out, d.epi, d.alpha = 0, 1, float(scale) * LOG2E
     d.rowvec = lse2.data_ptr()
-    check(lib.nk_gemm_ex(ctypes.byref(d), st), "attention bwd P gemm")
+    _tc(lib.nk_gemm_ex, "attention bwd P gemm", 2.0 * d.M * d.N * d.K * d.nb1 * d.nb2, ctypes.byref(d), st)
     # dV[b,:,h,:] = P^T dO : A = P as MN-major (M = kv), B = dO MN-major (N = d), K = Nq
     dq = torch.empty((B, Nq, H, D), dtype=BF16, device=dev)
     dk = torch.empty((B, Nk, H, D), dtype=BF16, device=dev)
@@ -540,7 +551,7 @@ def attention_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: T
     d.M, d.N, d.K, d.nb2, d.nb1, d.ksize = Nk, D, Nq, H, B, 1
     d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = dv.data_ptr(), dv.stride(1), dv.stride(2), dv.stride(0)
     d.out, d.epi, d.alpha = 0, 0, 1.0
-    check(lib.nk_gemm_ex(ctypes.byref(d), st), "attention bwd dV gemm")
+    _tc(lib.nk_gemm_ex, "attention bwd dV gemm", 2.0 * d.M * d.N * d.K * d.nb1 * d.nb2, ctypes.byref(d), st)
     # dS = P * (dO V^T - delta) * scale
     dS = torch.zeros_like(P) if Nkp != Nk else torch.empty_like(P)
     d = nk_gemm_desc()
@@ -551,7 +562,7 @@ def attention_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: T
     d.out, d.epi, d.alpha = 0, 2, float(scale)
     d.rowvec = delta.data_ptr()
     d.aux = P.data_ptr()
-    check(lib.nk_gemm_ex(ctypes.byref(d), st), "attention bwd dS gemm")
+    _tc(lib.nk_gemm_ex, "attention bwd dS gemm", 2.0 * d.M * d.N * d.K * d.nb1 * d.nb2, ctypes.byref(d), st)
     # dQ = dS K : A = dS K-major (K = kv), B = K matrix MN-major (N = d)
     d = nk_gemm_desc()
     _operand(d.A, dS, 0, Nq, Nk, Nkp, H, Nq * Nkp, B, H * Nq * Nkp)
@@ -559,7 +570,7 @@ def attention_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: T
     d.M, d.N, d.K, d.nb2, d.nb1, d.ksize = Nq, D, Nk, H, B, 1
     d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = dq.data_ptr(), dq.stride(1), dq.stride(2), dq.stride(0)
     d.out, d.epi, d.alpha = 0, 0, 1.0
-    check(lib.nk_gemm_ex(ctypes.byref(d), st), "attention bwd dQ gemm")
+    _tc(lib.nk_gemm_ex, "attention bwd dQ gemm", 2.0 * d.M * d.N * d.K * d.nb1 * d.nb2, ctypes.byref(d), st)
     # dK = dS^T Q : A = dS MN-major (M = kv), B = Q MN-major (N = d), K = Nq
     d = nk_gemm_desc()
     _operand(d.A, dS, 1, Nq, Nk, Nkp, H, Nq * Nkp, B, H * Nq * Nkp)
@@ -567,7 +578,7 @@ def attention_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: T
     d.M, d.N, d.K, d.nb2, d.nb1, d.ksize = Nk, D, Nq, H, B, 1
     d.C, d.ldc, d.c_b2_stride, d.c_b1_stride = dk.data_ptr(), dk.stride(1), dk.stride(2), dk.stride(0)
     d.out, d.epi, d.alpha = 0, 0, 1.0
-    check(lib.nk_gemm_ex(ctypes.byref(d), st), "attention bwd dK gemm")
+    _tc(lib.nk_gemm_ex, "attention bwd dK gemm", 2.0 * d.M * d.N * d.K * d.nb1 * d.nb2, ctypes.byref(d), st)
     _count(6)
     return dq, dk, dv
 
