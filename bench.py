@@ -193,6 +193,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--breakdown", default="", help="write a per-call-site breakdown of tensor-core time to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -267,8 +268,21 @@ def main() -> None:
         step(resident, False)
         torch.cuda.synchronize()
         recs, ops.PROFILE_GEMM = ops.PROFILE_GEMM, None
-        t_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
-        fl = sum(f for _, _, f in recs)
+        t_ms = sum(r[0].elapsed_time(r[1]) for r in recs)
+        fl = sum(r[2] for r in recs)
+        if args.breakdown and rank == 0:
+            agg = {}
+            for e0, e1, f, what, dims in recs:
+                key = (what, dims[-6:] if what.startswith("conv") else dims[-3:]) if "gemm" not in what else (what, ())
+                a = agg.setdefault(key, [0.0, 0.0, 0])
+                a[0] += e0.elapsed_time(e1)
+                a[1] += f
+                a[2] += 1
+            rows = sorted(agg.items(), key=lambda kv: -kv[1][0])
+            with open(args.breakdown, "w") as fh:
+                fh.write(f"total gemm ms {t_ms:.2f}  step ms {ms_dev / args.steps:.2f}\n")
+                for (what, dims), (ms, f, n) in rows[:80]:
+                    fh.write(f"{ms:9.3f} ms  {n:5d}x  {f / ms / 1e9 if ms > 0 else 0:8.1f} TFLOP/s  {what} {dims}\n")
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
         roof = {"kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "bound": "tensor", "achieved": ach,
                 "peak": pk["tflops"], "peak_source": pk["src"] + " sustained bf16", "unit": "TFLOP/s",

@@ -38,7 +38,7 @@ def _tc(rc_fn, what: str, flops: float, *args) -> None:
     e0.record()
     check(rc_fn(*args), what)
     e1.record()
-    PROFILE_GEMM.append((e0, e1, flops))
+    PROFILE_GEMM.append((e0, e1, flops, what, tuple(a for a in args if isinstance(a, int) and 0 < a < (1 << 24))))
 
 
 def _stream() -> int:
