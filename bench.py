@@ -213,7 +213,7 @@ def main() -> None:
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    W = max(3, args.warmup)
+    W = max(int(os.environ.get("NK_BENCH_MIN_WARMUP", "3")), args.warmup)  # >= 3 unless overridden for profiler runs
     B = args.batch
     eng = build_engine(dev)
     params = [p for p in eng.model.parameters() if p.requires_grad]

@@ -73,6 +73,7 @@ typedef struct nk_gemm_desc {
     const float* rowvec;
     const void* aux; /* bf16 */
     int32_t force_bn, force_splits;
+    int32_t force_cta_group, _reserved; /* 0 = heuristic, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2) */
 } nk_gemm_desc;
 
 int nk_gemm_ex(const nk_gemm_desc* d, nk_stream_t stream);

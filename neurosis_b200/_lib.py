@@ -66,6 +66,8 @@ class nk_gemm_desc(ctypes.Structure):
         ("aux", ctypes.c_void_p),
         ("force_bn", ctypes.c_int32),
         ("force_splits", ctypes.c_int32),
+        ("force_cta_group", ctypes.c_int32),
+        ("_reserved", ctypes.c_int32),
     ]
 
 

@@ -94,6 +94,7 @@ int nk_gemm_ex(const nk_gemm_desc* d, nk_stream_t stream) {
     p.aux = static_cast<const bf16*>(d->aux);
     p.force_bn = d->force_bn;
     p.force_splits = d->force_splits;
+    p.force_cta_group = d->force_cta_group;
     return launch_gemm(p, static_cast<cudaStream_t>(stream));
 }
 

@@ -17,6 +17,7 @@
 #include "gemm_tc.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace nk {
 
@@ -37,7 +38,8 @@ struct alignas(64) GemmDev {
     CUtensorMap tmB;
     int M, N;
     int BN;
-    int tiles_m, tiles_n, nb2, nb1, splits;
+    int tiles_m, tiles_n, nb2, nb1, splits;  // tiles_m counts (CG*128)-row tiles
+    int tiles_m128;                          // 128-row tiles actually present (validity of a CTA's half)
     int k_iters, k_iters_total;
     int stages;
     int a_mn, b_mn;
@@ -83,13 +85,18 @@ __device__ __forceinline__ int iters_of_split(const GemmDev& g, int split) {
     return rem < g.k_iters ? rem : g.k_iters;
 }
 
+template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmDev g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024B alignment is required by the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
     const int stages = g.stages;
-    const uint32_t b_stage_bytes = static_cast<uint32_t>(g.BN) * 128u;
+    const int BNc = g.BN / CG;  // rows of the B tile held by this CTA
+    const uint32_t b_stage_bytes = static_cast<uint32_t>(BNc) * 128u;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int num_groups = gridDim.x / CG;
+    const int group = blockIdx.x / CG;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + static_cast<size_t>(stages) * A_STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + static_cast<size_t>(stages) * b_stage_bytes);
@@ -112,16 +119,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         }
         mbar_init(&tmem_full[0], 1);
         mbar_init(&tmem_full[1], 1);
-        mbar_init(&tmem_empty[0], 4);
-        mbar_init(&tmem_empty[1], 4);
+        mbar_init(&tmem_empty[0], 4 * CG);
+        mbar_init(&tmem_empty[1], 4 * CG);
         fence_barrier_init();
     }
+    if (CG == 2) cluster_sync_all();  // barrier inits visible to the peer CTA before anything is signalled
     if (warp == 1) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
+        if (CG == 2) {
+            tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+            tmem_relinquish_2cta();
+        } else {
+            tmem_alloc(tmem_slot, TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -130,40 +143,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            auto tma_load = [](const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+                if (CG == 2) tma_load_4d_2cta(tm, bar, dst, c0, c1, c2, c3);
+                else tma_load_4d(tm, bar, dst, c0, c1, c2, c3);
+            };
+            for (int t = group; t < total_tiles; t += num_groups) {
                 const TileCoord tc = decode_tile(g, t);
-                const int n0 = tc.nt * g.BN;
-                const int m0 = tc.mt * BM;
+                const int n0 = tc.nt * g.BN + static_cast<int>(rank) * BNc;  // this CTA's slice of the B tile
+                const int mt = tc.mt * CG + static_cast<int>(rank);          // this CTA's 128-row tile
+                const int m0 = mt * BM;
                 const int iters = iters_of_split(g, tc.split);
                 int img = 0, th = 0, tw = 0;
                 if (g.mode == MODE_CONV_FWD) {
-                    tw = tc.mt % g.tiles_w;
-                    th = (tc.mt / g.tiles_w) % g.tiles_h;
-                    img = tc.mt / (g.tiles_w * g.tiles_h);
+                    tw = mt % g.tiles_w;
+                    th = (mt / g.tiles_w) % g.tiles_h;
+                    img = mt / (g.tiles_w * g.tiles_h);  // may be >= nimg for the odd last tile: TMA zero-fills
                 }
                 for (int it = 0; it < iters; ++it) {
                     const int gi = tc.split * g.k_iters + it;
                     mbar_wait(&empty_bar[stage], phase ^ 1u, 100u + stage);
-                    mbar_arrive_expect_tx(&full_bar[stage], g.a_bytes + g.b_bytes);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * (g.a_bytes + g.b_bytes));
                     uint8_t* sa = smem_a + static_cast<size_t>(stage) * A_STAGE_BYTES;
                     uint8_t* sb = smem_b + static_cast<size_t>(stage) * b_stage_bytes;
                     if (g.mode == MODE_PLAIN) {
                         const int k0 = gi * BK;
                         if (!g.a_mn) {
-                            tma_load_4d(&g.tmA, &full_bar[stage], sa, k0, m0, tc.b2 * g.a_b2,
+                            tma_load(&g.tmA, &full_bar[stage], sa, k0, m0, tc.b2 * g.a_b2,
                                         tc.b1 * g.a_b1);
                         } else {
-                            tma_load_4d(&g.tmA, &full_bar[stage], sa, m0, k0, tc.b2 * g.a_b2,
+                            tma_load(&g.tmA, &full_bar[stage], sa, m0, k0, tc.b2 * g.a_b2,
                                         tc.b1 * g.a_b1);
-                            tma_load_4d(&g.tmA, &full_bar[stage], sa + ATOM_BYTES, m0 + 64, k0,
+                            tma_load(&g.tmA, &full_bar[stage], sa + ATOM_BYTES, m0 + 64, k0,
                                         tc.b2 * g.a_b2, tc.b1 * g.a_b1);
                         }
                         if (!g.b_mn) {
-                            tma_load_4d(&g.tmB, &full_bar[stage], sb, k0, n0, tc.b2 * g.b_b2,
+                            tma_load(&g.tmB, &full_bar[stage], sb, k0, n0, tc.b2 * g.b_b2,
                                         tc.b1 * g.b_b1);
                         } else {
-                            for (int j = 0; j < g.BN / 64; ++j)
-                                tma_load_4d(&g.tmB, &full_bar[stage], sb + j * ATOM_BYTES,
+                            for (int j = 0; j < BNc / 64; ++j)
+                                tma_load(&g.tmB, &full_bar[stage], sb + j * ATOM_BYTES,
                                             n0 + 64 * j, k0, tc.b2 * g.b_b2, tc.b1 * g.b_b1);
                         }
                     } else if (g.mode == MODE_CONV_FWD) {
@@ -171,20 +189,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         const int cb = gi - tap * g.cin_blocks;
                         const int dy = tap / g.ksize - g.pad;
                         const int dx = tap % g.ksize - g.pad;
-                        tma_load_4d(&g.tmA, &full_bar[stage], sa, cb * 64, tw * g.bw + dx,
+                        tma_load(&g.tmA, &full_bar[stage], sa, cb * 64, tw * g.bw + dx,
                                     th * g.bh + dy, img);
-                        tma_load_4d(&g.tmB, &full_bar[stage], sb, gi * BK, n0, 0, 0);
+                        tma_load(&g.tmB, &full_bar[stage], sb, gi * BK, n0, 0, 0);
                     } else {  // MODE_CONV_WGRAD: k-iteration = one 64-pixel tile, tap = b2
                         const int ptw = gi % g.tiles_w;
                         const int pth = (gi / g.tiles_w) % g.tiles_h;
                         const int pimg = gi / (g.tiles_w * g.tiles_h);
                         const int dy = tc.b2 / g.ksize - g.pad;
                         const int dx = tc.b2 % g.ksize - g.pad;
-                        tma_load_4d(&g.tmA, &full_bar[stage], sa, m0, ptw * g.bw, pth * g.bh, pimg);
-                        tma_load_4d(&g.tmA, &full_bar[stage], sa + ATOM_BYTES, m0 + 64, ptw * g.bw,
+                        tma_load(&g.tmA, &full_bar[stage], sa, m0, ptw * g.bw, pth * g.bh, pimg);
+                        tma_load(&g.tmA, &full_bar[stage], sa + ATOM_BYTES, m0 + 64, ptw * g.bw,
                                     pth * g.bh, pimg);
-                        for (int j = 0; j < g.BN / 64; ++j)
-                            tma_load_4d(&g.tmB, &full_bar[stage], sb + j * ATOM_BYTES, n0 + 64 * j,
+                        for (int j = 0; j < BNc / 64; ++j)
+                            tma_load(&g.tmB, &full_bar[stage], sb + j * ATOM_BYTES, n0 + 64 * j,
                                         ptw * g.bw + dx, pth * g.bh + dy, pimg);
                     }
                     if (++stage == stages) {
@@ -195,8 +213,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (leader CTA of the pair only) =====================
+        if (lane == 0 && rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
@@ -205,7 +223,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             const uint32_t b_adv = g.b_mn ? (2048u >> 4) : (32u >> 4);
             const uint32_t a_lbo = g.a_mn ? static_cast<uint32_t>(ATOM_BYTES) : 16u;
             const uint32_t b_lbo = g.b_mn ? static_cast<uint32_t>(ATOM_BYTES) : 16u;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+            for (int t = group; t < total_tiles; t += num_groups, ++local) {
                 const TileCoord tc = decode_tile(g, t);
                 const int iters = iters_of_split(g, tc.split);
                 const int acc = local & 1;
@@ -221,17 +239,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     const uint64_t b_desc = make_smem_desc(sb, b_lbo, 1024u);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        tc_mma_ss(d_tmem, a_desc + static_cast<uint64_t>(k * a_adv),
-                                  b_desc + static_cast<uint64_t>(k * b_adv), g.idesc,
-                                  (it > 0 || k > 0) ? 1u : 0u);
+                        if (CG == 2)
+                            tc_mma_ss_2cta(d_tmem, a_desc + static_cast<uint64_t>(k * a_adv),
+                                           b_desc + static_cast<uint64_t>(k * b_adv), g.idesc,
+                                           (it > 0 || k > 0) ? 1u : 0u);
+                        else
+                            tc_mma_ss(d_tmem, a_desc + static_cast<uint64_t>(k * a_adv),
+                                      b_desc + static_cast<uint64_t>(k * b_adv), g.idesc,
+                                      (it > 0 || k > 0) ? 1u : 0u);
                     }
-                    tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (CG == 2) tc_commit_2cta(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
                     if (++stage == stages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+                if (CG == 2) tc_commit_2cta(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
             }
         }
     } else {
@@ -239,26 +262,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
         const int r = quad * 32 + lane;
         int local = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+        for (int t = group; t < total_tiles; t += num_groups, ++local) {
             const TileCoord tc = decode_tile(g, t);
             const int n0 = tc.nt * g.BN;
+            const int mt = tc.mt * CG + static_cast<int>(rank);
             const int acc = local & 1;
             // output row of this thread
             long long row = 0;
             bool row_ok = false;
             int img = 0;
             if (g.mode == MODE_CONV_FWD) {
-                const int tw = tc.mt % g.tiles_w;
-                const int th = (tc.mt / g.tiles_w) % g.tiles_h;
-                img = tc.mt / (g.tiles_w * g.tiles_h);
+                const int tw = mt % g.tiles_w;
+                const int th = (mt / g.tiles_w) % g.tiles_h;
+                img = mt / (g.tiles_w * g.tiles_h);
                 const int hh = r / g.bw;
                 const int ww = r - hh * g.bw;
                 const int h = th * g.bh + hh;
                 const int w = tw * g.bw + ww;
-                row_ok = (hh < g.bh) && (h < g.cH) && (w < g.cW);
+                row_ok = (mt < g.tiles_m128) && (hh < g.bh) && (h < g.cH) && (w < g.cW);
                 row = (static_cast<long long>(img) * g.cH + h) * g.cW + w;
             } else {
-                row = static_cast<long long>(tc.mt) * BM + r;
+                row = static_cast<long long>(mt) * BM + r;
                 row_ok = row < g.M;
                 if (g.bias_img) img = static_cast<int>(row / g.rows_per_img);
             }
@@ -364,15 +388,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_remote(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+            }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (CG == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -412,16 +438,17 @@ int make_operand_tmap(CUtensorMap* tm, const GemmOperand& o, int box_rows_or_bw,
     return encode_tmap_bf16(tm, o.ptr, 4, dims, strides, box);
 }
 
-int pick_bn(const GemmProblem& p, long long tiles_m_batches, int nsm) {
+// tile width (and CTA-group size) minimising waves x per-k16 cost.  `groups` = CTA groups that run concurrently.
+int pick_bn(const GemmProblem& p, long long tiles_m_batches, int groups, int cg) {
     if (p.force_bn > 0) return p.force_bn;
-    const int step = p.B.mn_major ? 64 : 16;
+    const int step = p.B.mn_major ? 64 * cg : 16 * cg;
     long long best_cost = -1;
     int best = 256;
     for (int bn = 256; bn >= step; bn -= step) {
         const long long tiles = tiles_m_batches * ((p.N + bn - 1) / bn);
-        const long long waves = (tiles + nsm - 1) / nsm;
-        // cycles per k16 step: tensor pipe BN/2 vs smem feed (4 KB of A + BN*32 B of B at 128 B/clk)
-        const long long per = std::max<long long>(bn / 2, 32 + bn / 4) + 6;
+        const long long waves = (tiles + groups - 1) / groups;
+        // cycles per k16 step and CTA: tensor pipe BN/2 vs smem feed (4 KB of A + (BN/cg)*32 B of B at 128 B/clk)
+        const long long per = std::max<long long>(bn / 2, 32 + bn / (4 * cg)) + 6;
         const long long cost = waves * per;
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
@@ -489,7 +516,7 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
         pick_pixel_tile(g.cH, g.cW, BM, false, &g.bw, &g.bh);
         g.tiles_w = (g.cW + g.bw - 1) / g.bw;
         g.tiles_h = (g.cH + g.bh - 1) / g.bh;
-        g.tiles_m = p.A.nimg * g.tiles_w * g.tiles_h;
+        g.tiles_m128 = p.A.nimg * g.tiles_w * g.tiles_h;
         g.cin_blocks = static_cast<int>(p.A.inner / 64);
         g.k_iters_total = g.ksize * g.ksize * g.cin_blocks;
         a_box1 = g.bw;
@@ -501,7 +528,7 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
         pick_pixel_tile(g.cH, g.cW, 64, true, &g.bw, &g.bh);
         g.tiles_w = (g.cW + g.bw - 1) / g.bw;
         g.tiles_h = (g.cH + g.bh - 1) / g.bh;
-        g.tiles_m = (p.M + BM - 1) / BM;
+        g.tiles_m128 = (p.M + BM - 1) / BM;
         g.k_iters_total = p.A.nimg * g.tiles_w * g.tiles_h;
         a_box1 = g.bw;
         a_box2 = g.bh;
@@ -509,27 +536,43 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
         g.a_bytes = 2 * ATOM_BYTES;
         NK_REQUIRE(g.nb2 == g.ksize * g.ksize, NK_ERR_SHAPE, "wgrad: nb2 must equal taps");
     } else {
-        g.tiles_m = (p.M + BM - 1) / BM;
+        g.tiles_m128 = (p.M + BM - 1) / BM;
         g.k_iters_total = (p.K + BK - 1) / BK;
         a_box1 = p.A.mn_major ? 64 : BM;
         g.a_bytes = A_STAGE_BYTES;
     }
 
+    // CTA-group size: pairs (cta_group::2, 256-row tiles, B tile split across the pair) whenever the problem has
+    // at least two 128-row tiles and a wide enough N; single CTAs otherwise.
+    static int env_cg = -1;
+    if (env_cg < 0) {
+        const char* e_ = getenv("NK_GEMM_CTA_GROUP");  // debugging / A-B switch: 1 or 2
+        env_cg = e_ ? atoi(e_) : 0;
+    }
+    int cg = 2;
+    if (p.force_cta_group == 1 || p.force_cta_group == 2) cg = p.force_cta_group;
+    else if (env_cg == 1) cg = 1;
+    else if (g.tiles_m128 < 2 || p.N < 32 || (p.B.mn_major && p.N < 128)) cg = 1;
+    if (p.force_bn > 0 && (p.force_bn % (p.B.mn_major ? 64 * cg : 16 * cg)) != 0) cg = 1;
+    g.tiles_m = (g.tiles_m128 + cg - 1) / cg;
+
     const long long tiles_mb = static_cast<long long>(g.tiles_m) * g.nb2 * g.nb1;
-    g.BN = pick_bn(p, tiles_mb, nsm);
-    NK_REQUIRE(g.BN >= 16 && g.BN <= 256 && g.BN % 16 == 0, NK_ERR_SHAPE, "bad BN %d", g.BN);
-    NK_REQUIRE(!p.B.mn_major || g.BN % 64 == 0, NK_ERR_SHAPE, "MN-major B needs BN %% 64 == 0");
+    g.BN = pick_bn(p, tiles_mb, nsm / cg, cg);
+    NK_REQUIRE(g.BN >= 16 * cg && g.BN <= 256 && g.BN % (16 * cg) == 0, NK_ERR_SHAPE, "bad BN %d (cta group %d)", g.BN, cg);
+    NK_REQUIRE(!p.B.mn_major || g.BN % (64 * cg) == 0, NK_ERR_SHAPE, "MN-major B needs BN %% %d == 0", 64 * cg);
     g.tiles_n = (p.N + g.BN - 1) / g.BN;
-    g.b_bytes = static_cast<uint32_t>(g.BN) * 128u;
+    const int bnc = g.BN / cg;
+    g.b_bytes = static_cast<uint32_t>(bnc) * 128u;
 
     // split-K only when accumulating atomically
     int splits = 1;
     if (p.out == OUT_F32_ATOMIC) {
         const long long tiles = tiles_mb * g.tiles_n;
+        const int groups = nsm / cg;
         if (p.force_splits > 0)
             splits = p.force_splits;
-        else if (tiles < nsm)
-            splits = static_cast<int>(std::min<long long>((2LL * nsm + tiles - 1) / tiles,
+        else if (tiles < groups)
+            splits = static_cast<int>(std::min<long long>((2LL * groups + tiles - 1) / tiles,
                                                            std::max(1, g.k_iters_total / 8)));
         splits = std::max(1, std::min(splits, g.k_iters_total));
     }
@@ -543,7 +586,7 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
 
     int e = make_operand_tmap(&g.tmA, p.A, a_box1, a_box2);
     if (e) return e;
-    const int b_box1 = p.B.conv ? g.bw : (p.B.mn_major ? 64 : g.BN);
+    const int b_box1 = p.B.conv ? g.bw : (p.B.mn_major ? 64 : bnc);
     e = make_operand_tmap(&g.tmB, p.B, b_box1, b_box2);
     if (e) return e;
 
@@ -561,24 +604,43 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     g.ldr = p.ldr;
     g.rowvec = p.rowvec;
     g.aux = p.aux;
-    g.idesc = make_idesc_bf16(BM, g.BN, g.a_mn, g.b_mn);
+    g.idesc = make_idesc_bf16(BM * cg, g.BN, g.a_mn, g.b_mn);
     NK_REQUIRE(p.epi != EPI_DSOFTMAX || (p.aux && p.rowvec), NK_ERR_SHAPE, "dsoftmax needs aux+rowvec");
     NK_REQUIRE(p.epi != EPI_EXP2 || p.rowvec, NK_ERR_SHAPE, "exp2 epilogue needs rowvec");
 
-    const int stage_bytes = A_STAGE_BYTES + g.BN * 128;
+    const int stage_bytes = A_STAGE_BYTES + bnc * 128;
     const int max_smem = 227 * 1024;
     int stages = (max_smem - 1024 - 256) / stage_bytes;
     stages = std::max(2, std::min(stages, 8));
     g.stages = stages;
     const int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 5) * 8;
     if (!attr_set) {
-        NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set = true;
     }
     const long long total = tiles_mb * g.tiles_n * g.splits;
     NK_REQUIRE(total < (1LL << 31), NK_ERR_SHAPE, "too many tiles");
-    const int grid = static_cast<int>(std::min<long long>(total, nsm));
-    gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(g);
+    if (cg == 1) {
+        const int grid = static_cast<int>(std::min<long long>(total, nsm));
+        gemm_tc_kernel<1><<<grid, NUM_THREADS, smem_bytes, stream>>>(g);
+    } else {
+        const int grid = 2 * static_cast<int>(std::min<long long>(total, nsm / 2));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        NK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, g));
+    }
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }

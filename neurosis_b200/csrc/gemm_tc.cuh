@@ -51,6 +51,7 @@ struct GemmProblem {
     const bf16* aux;          // [M, N] like C, EPI_DSOFTMAX
     int force_bn;             // 0 = heuristic
     int force_splits;         // 0 = heuristic (only with OUT_F32_ATOMIC)
+    int force_cta_group;      // 0 = heuristic, 1 = single CTA tiles, 2 = CTA pairs (cta_group::2)
 };
 
 int launch_gemm(const GemmProblem& p, cudaStream_t stream);

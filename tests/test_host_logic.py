@@ -25,7 +25,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(_lib.lib, name), name
     assert _lib.lib.nk_version() >= 100
-    assert ctypes.sizeof(_lib.nk_gemm_desc) == 312  # matches sizeof(nk_gemm_desc) in the header
+    assert ctypes.sizeof(_lib.nk_gemm_desc) == 320  # matches sizeof(nk_gemm_desc) in the header
 
 
 def test_cabi_rejects_bad_arguments_without_gpu():
