@@ -2,7 +2,7 @@
 //
 //   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
 //   warp 1      : MMA issuer     (one lane issues tcgen05.mma, accumulators in TMEM, 2 buffers)
-//   warps 2..5  : epilogue       (tcgen05.ld -> registers -> fused epilogue -> global)
+//   warps 2..9  : epilogue       (tcgen05.ld -> registers -> fused epilogue -> global), 2 warps per TMEM quadrant
 //
 // The same kernel serves
 //   * linear layers and their gradients (K-major and MN-major operands, split-K with fp32 red),
@@ -27,7 +27,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int ATOM_BYTES = 64 * 64 * 2;     // one 64x64 bf16 box, 8 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
 
@@ -85,6 +85,24 @@ __device__ __forceinline__ int iters_of_split(const GemmDev& g, int split) {
     return rem < g.k_iters ? rem : g.k_iters;
 }
 
+// v[0..15] += p[0..15] (fp32 vector, same address for every lane of the warp -> broadcast loads)
+__device__ __forceinline__ void add_vec16(float (&v)[16], const float* p, bool full, int remaining) {
+    if (full && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(p) + j);
+            v[4 * j] += f.x;
+            v[4 * j + 1] += f.y;
+            v[4 * j + 2] += f.z;
+            v[4 * j + 3] += f.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < remaining) v[j] += __ldg(p + j);
+    }
+}
+
 template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmDev g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -119,8 +137,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         }
         mbar_init(&tmem_full[0], 1);
         mbar_init(&tmem_full[1], 1);
-        mbar_init(&tmem_empty[0], 4 * CG);
-        mbar_init(&tmem_empty[1], 4 * CG);
+        mbar_init(&tmem_empty[0], 8 * CG);
+        mbar_init(&tmem_empty[1], 8 * CG);
         fence_barrier_init();
     }
     if (CG == 2) cluster_sync_all();  // barrier inits visible to the peer CTA before anything is signalled
@@ -258,9 +276,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        // ===================== epilogue (warps 2..9) =====================
+        // Two warps per TMEM lane quadrant, each owning half of the tile's 16-column chunks.  TMEM reads and the
+        // side input (residual / aux) of chunk c+1 are issued before chunk c is processed, so their latency overlaps.
+        const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;   // which half of the column chunks
         const int r = quad * 32 + lane;
+        const int nch = g.BN / 16;
+        const int c_begin = half ? (nch + 1) / 2 : 0;
+        const int c_end = half ? nch : (nch + 1) / 2;
         int local = 0;
         for (int t = group; t < total_tiles; t += num_groups, ++local) {
             const TileCoord tc = decode_tile(g, t);
@@ -290,59 +314,71 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             float rv = 0.f;
             if (g.rowvec && row_ok)
                 rv = g.rowvec[(static_cast<long long>(tc.b1) * g.nb2 + tc.b2) * g.M + row];
+            // side input row pointer: residual (EPI_LINEAR) or aux (EPI_DSOFTMAX)
+            const bf16* side_row = nullptr;
+            if (row_ok) {
+                if (g.epi == EPI_LINEAR && g.residual) side_row = g.residual + boff + row * g.ldr;
+                else if (g.epi == EPI_DSOFTMAX) side_row = g.aux + boff + row * g.ldc;
+            }
+            const float* bias_img_row = g.bias_img ? g.bias_img + static_cast<long long>(img) * g.N : nullptr;
 
             mbar_wait(&tmem_full[acc], (local >> 1) & 1u, 400u + acc);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                     static_cast<uint32_t>(acc * ACC_STRIDE);
-            for (int c = 0; c < g.BN / 16; ++c) {
-                uint32_t raw[16];
-                tc_ld16(taddr0 + static_cast<uint32_t>(c * 16), raw);
-                tc_wait_ld();
+
+            auto side_vec_ok = [&](int c) -> bool {
                 const int n = n0 + c * 16;
-                if (!row_ok || n >= g.N) continue;
+                return side_row != nullptr && (n + 16 <= g.N) &&
+                       ((reinterpret_cast<uintptr_t>(side_row + n) & 15u) == 0);
+            };
+            auto issue = [&](int c, uint32_t (&raw)[16], uint4& sa, uint4& sb) {
+                tc_ld16(taddr0 + static_cast<uint32_t>(c * 16), raw);
+                if (side_vec_ok(c)) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(side_row + n0 + c * 16);
+                    sa = __ldg(sp);
+                    sb = __ldg(sp + 1);
+                }
+            };
+            auto process = [&](int c, const uint32_t (&raw)[16], const uint4& sa, const uint4& sb) {
+                const int n = n0 + c * 16;
+                if (!row_ok || n >= g.N) return;
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
                 const bool full = (n + 16 <= g.N);
+                // side values (fp32) when present
+                float sv[16];
+                const bool has_side = side_row != nullptr;
+                if (has_side) {
+                    if (side_vec_ok(c)) {
+                        const uint32_t w[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 f = unpack_bf16x2(w[j]);
+                            sv[2 * j] = f.x;
+                            sv[2 * j + 1] = f.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) sv[j] = (n + j < g.N) ? __bfloat162float(side_row[n + j]) : 0.f;
+                    }
+                }
                 if (g.epi == EPI_LINEAR) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] *= g.alpha;
-                    if (g.bias) {
+                    if (g.bias) add_vec16(v, g.bias + n, full, g.N - n);
+                    if (bias_img_row) add_vec16(v, bias_img_row + n, full, g.N - n);
+                    if (has_side) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (full || n + j < g.N) v[j] += __ldg(g.bias + n + j);
-                    }
-                    if (g.bias_img) {
-                        const float* bi = g.bias_img + static_cast<long long>(img) * g.N + n;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (full || n + j < g.N) v[j] += __ldg(bi + j);
-                    }
-                    if (g.residual) {
-                        const bf16* rp = g.residual + boff + row * g.ldr + n;
-                        if (full && ((reinterpret_cast<uintptr_t>(rp) & 15u) == 0)) {
-                            const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
-                            const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-                            const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float2 f = unpack_bf16x2(w[j]);
-                                v[2 * j] += f.x;
-                                v[2 * j + 1] += f.y;
-                            }
-                        } else {
-                            for (int j = 0; j < 16 && n + j < g.N; ++j)
-                                v[j] += __bfloat162float(rp[j]);
-                        }
+                        for (int j = 0; j < 16; ++j) v[j] += sv[j];
                     }
                 } else if (g.epi == EPI_EXP2) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = exp2f(v[j] * g.alpha - rv);
                 } else {  // EPI_DSOFTMAX
-                    const bf16* ap = g.aux + boff + row * g.ldc + n;
-                    for (int j = 0; j < 16 && n + j < g.N; ++j)
-                        v[j] = __bfloat162float(ap[j]) * (v[j] - rv) * g.alpha;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = sv[j] * (v[j] - rv) * g.alpha;
                 }
                 // ---- store ----
                 if (g.out == OUT_BF16) {
@@ -360,7 +396,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         reinterpret_cast<uint4*>(cp)[0] = q0;
                         reinterpret_cast<uint4*>(cp)[1] = q1;
                     } else {
-                        for (int j = 0; j < 16 && n + j < g.N; ++j) cp[j] = __float2bfloat16(v[j]);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n + j < g.N) cp[j] = __float2bfloat16(v[j]);
                     }
                 } else if (g.out == OUT_F32) {
                     float* cp = reinterpret_cast<float*>(g.C) + boff + row * g.ldc + n;
@@ -370,7 +408,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                             reinterpret_cast<float4*>(cp)[j] =
                                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     } else {
-                        for (int j = 0; j < 16 && n + j < g.N; ++j) cp[j] = v[j];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n + j < g.N) cp[j] = v[j];
                     }
                 } else {  // OUT_F32_ATOMIC
                     float* cp = reinterpret_cast<float*>(g.C) + boff + row * g.ldc + n;
@@ -378,11 +418,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + 4 * j),
-                                         "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]),
-                                         "f"(v[4 * j + 3])
+                                         "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
                                          : "memory");
                     } else {
-                        for (int j = 0; j < 16 && n + j < g.N; ++j) atomicAdd(cp + j, v[j]);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n + j < g.N) atomicAdd(cp + j, v[j]);
+                    }
+                }
+            };
+            if (c_begin < c_end) {
+                uint32_t r0[16], r1[16];
+                uint4 s0a = make_uint4(0, 0, 0, 0), s0b = s0a, s1a = s0a, s1b = s0a;
+                issue(c_begin, r0, s0a, s0b);
+                for (int c = c_begin; c < c_end; c += 2) {
+                    tc_wait_ld16(r0);
+                    if (c + 1 < c_end) issue(c + 1, r1, s1a, s1b);
+                    process(c, r0, s0a, s0b);
+                    if (c + 1 < c_end) {
+                        tc_wait_ld16(r1);
+                        if (c + 2 < c_end) issue(c + 2, r0, s0a, s0b);
+                        process(c + 1, r1, s1a, s1b);
                     }
                 }
             }
