@@ -119,6 +119,14 @@ int nk_attention_fwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
                      int64_t k_row_stride, int64_t k_batch_stride, const void* v, int64_t v_row_stride,
                      int64_t v_batch_stride, void* o, int64_t o_row_stride, int64_t o_batch_stride,
                      float* lse, int B, int H, int Nq, int Nk, int head_dim, float scale, nk_stream_t stream);
+/* Fused attention backward (head_dim 64): dq_acc fp32 [B,Nq,H,64] must be zero-initialised (K/V tiles accumulate
+ * into it with red.global.add); dk, dv bf16 [B,Nk,H,64] contiguous; lse from nk_attention_fwd, delta from
+ * nk_attn_delta.  Autograd of the attention call sites modules/attention.py:346-352,410-412. */
+int nk_attention_bwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride, const void* k, int64_t k_row_stride,
+                     int64_t k_batch_stride, const void* v, int64_t v_row_stride, int64_t v_batch_stride,
+                     const void* dO, int64_t do_row_stride, int64_t do_batch_stride, const float* lse,
+                     const float* delta, float* dq_acc, void* dk, void* dv, int B, int H, int Nq, int Nk, int head_dim,
+                     float scale, nk_stream_t stream);
 /* delta[b,h,q] = sum_d dO*O on [B,N,H,D] tensors (attention backward). */
 int nk_attn_delta(const void* dO, const void* O, float* delta, int B, int N, int H, int D, nk_stream_t stream);
 /* P = softmax(scale*S) row-wise (S fp32 [rows, lds], P bf16), lse optional — materialised attention path

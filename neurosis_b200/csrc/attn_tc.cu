@@ -276,6 +276,286 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     }
 }
 
+
+// =================================================================================================
+// Fused attention backward (head_dim 64).  One CTA owns one 128-row K/V tile of one (batch, head) and
+// loops over the 128-row Q tiles:
+//     S  = Q_i K^T            dP = dO_i V^T                      (TMEM, 128x128 each)
+//     P  = exp2(scale*log2e*S - lse*log2e)                        (softmax warps, bf16 -> smem)
+//     dS = P * (dP - delta) * scale                               (softmax warps, bf16 -> smem)
+//     dV += P^T dO_i          dK += dS^T Q_i                      (TMEM accumulators over the Q loop)
+//     dQ_i = dS K             -> red.global.add.f32 into dQ_acc   (other K/V tiles add to the same rows)
+// P and dS are stored once in the 128B-swizzled [q][kv] layout and consumed both as K-major (dQ) and as
+// MN-major (dV, dK) UMMA operands; dO, Q and K are likewise consumed in both majors without transposes.
+// =================================================================================================
+struct alignas(64) AttnBwdDev {
+    CUtensorMap tmQ, tmK, tmV, tmdO;
+    const float* lse;    // [B, H, Nq]
+    const float* delta;  // [B, H, Nq]
+    float* dQ;           // fp32 accumulator [B, Nq, H, 64] (zero-initialised by the caller)
+    bf16* dK;
+    bf16* dV;            // [B, Nk, H, 64]
+    long long dq_row_stride, dq_batch_stride, dkv_row_stride, dkv_batch_stride;
+    int Nq, Nk, H, B;
+    float scale, scale_log2;
+};
+
+constexpr int BW_K = 0;
+constexpr int BW_V = BW_K + TILE_BYTES;
+constexpr int BW_Q = BW_V + TILE_BYTES;        // 2 stages
+constexpr int BW_DO = BW_Q + 2 * TILE_BYTES;   // 2 stages
+constexpr int BW_P = BW_DO + 2 * TILE_BYTES;   // 128x128 bf16 = 2 tiles
+constexpr int BW_DS = BW_P + 2 * TILE_BYTES;
+constexpr int BW_BAR = BW_DS + 2 * TILE_BYTES;
+constexpr int BW_SMEM = BW_BAR + 256 + 1024;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdDev g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BW_BAR);
+    uint64_t* kv_full = bars;            // 1
+    uint64_t* qdo_full = bars + 1;       // 2
+    uint64_t* qdo_empty = bars + 3;      // 2
+    uint64_t* s_full = bars + 5;
+    uint64_t* dp_full = bars + 6;
+    uint64_t* p_ready = bars + 7;        // 128 arrivals
+    uint64_t* ds_ready = bars + 8;       // 128 arrivals
+    uint64_t* dq_full = bars + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int kv0 = blockIdx.x * BKV;
+    const int h = blockIdx.y;
+    const int b = blockIdx.z;
+    const int Tq = (g.Nq + BQ - 1) / BQ;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&g.tmQ);
+        tma_prefetch_desc(&g.tmK);
+        tma_prefetch_desc(&g.tmV);
+        tma_prefetch_desc(&g.tmdO);
+        mbar_init(kv_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&qdo_full[s], 1);
+            mbar_init(&qdo_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(dp_full, 1);
+        mbar_init(p_ready, 128);
+        mbar_init(ds_ready, 128);
+        mbar_init(dq_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
+            tma_load_4d(&g.tmK, kv_full, smem + BW_K, 0, h, kv0, b);
+            tma_load_4d(&g.tmV, kv_full, smem + BW_V, 0, h, kv0, b);
+            for (int i = 0; i < Tq; ++i) {
+                const int st = i & 1;
+                mbar_wait(&qdo_empty[st], (((i >> 1) & 1) ^ 1) & 1u, 40u + st);
+                mbar_arrive_expect_tx(&qdo_full[st], 2 * TILE_BYTES);
+                tma_load_4d(&g.tmQ, &qdo_full[st], smem + BW_Q + st * TILE_BYTES, 0, h, i * BQ, b);
+                tma_load_4d(&g.tmdO, &qdo_full[st], smem + BW_DO + st * TILE_BYTES, 0, h, i * BQ, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);  // S, dP: both operands K-major
+            const uint32_t idesc_mm = make_idesc_bf16(128, HD, 1, 1);   // dV, dK: both operands MN-major
+            const uint32_t idesc_km = make_idesc_bf16(128, HD, 0, 1);   // dQ: dS K-major, K MN-major
+            const uint32_t k_addr = smem_u32(smem + BW_K), v_addr = smem_u32(smem + BW_V);
+            const uint32_t p_addr = smem_u32(smem + BW_P), ds_addr = smem_u32(smem + BW_DS);
+            mbar_wait(kv_full, 0, 50);
+            for (int i = 0; i < Tq; ++i) {
+                const int st = i & 1;
+                const uint32_t par = static_cast<uint32_t>(i & 1);
+                const uint32_t q_addr = smem_u32(smem + BW_Q + st * TILE_BYTES);
+                const uint32_t do_addr = smem_u32(smem + BW_DO + st * TILE_BYTES);
+                mbar_wait(&qdo_full[st], (i >> 1) & 1u, 51u);
+                tc_fence_after();
+                // S = Q K^T ; dP = dO V^T   (K = d = 64: 4 k-steps of 32 bytes)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc_mma_ss(tmem_base + TM_S, make_smem_desc(q_addr + k * 32, 16u, 1024u),
+                              make_smem_desc(k_addr + k * 32, 16u, 1024u), idesc_kk, k > 0 ? 1u : 0u);
+                tc_commit(s_full);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc_mma_ss(tmem_base + TM_DP, make_smem_desc(do_addr + k * 32, 16u, 1024u),
+                              make_smem_desc(v_addr + k * 32, 16u, 1024u), idesc_kk, k > 0 ? 1u : 0u);
+                tc_commit(dp_full);
+                // dV += P^T dO   (M = kv, N = d, K = q = 128: 8 k-steps of 16 q-rows = 2048 bytes)
+                mbar_wait(p_ready, par, 52u);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    tc_mma_ss(tmem_base + TM_DV, make_smem_desc(p_addr + k * 2048, 16384u, 1024u),
+                              make_smem_desc(do_addr + k * 2048, 8192u, 1024u), idesc_mm, (i > 0 || k > 0) ? 1u : 0u);
+                // dK += dS^T Q ;  dQ_i = dS K
+                mbar_wait(ds_ready, par, 53u);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    tc_mma_ss(tmem_base + TM_DK, make_smem_desc(ds_addr + k * 2048, 16384u, 1024u),
+                              make_smem_desc(q_addr + k * 2048, 8192u, 1024u), idesc_mm, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    tc_mma_ss(tmem_base + TM_DQ,
+                              make_smem_desc(ds_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16u, 1024u),
+                              make_smem_desc(k_addr + k * 2048, 8192u, 1024u), idesc_km, k > 0 ? 1u : 0u);
+                tc_commit(dq_full);
+                tc_commit(&qdo_empty[st]);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+        const int kv_valid = g.Nk - kv0;  // columns >= kv_valid are padding
+        uint8_t* pbuf = smem + BW_P;
+        uint8_t* dsbuf = smem + BW_DS;
+        for (int i = 0; i < Tq; ++i) {
+            const uint32_t par = static_cast<uint32_t>(i & 1);
+            const int q = i * BQ + r;
+            const bool valid = q < g.Nq;
+            const long long sidx = (static_cast<long long>(b) * g.H + h) * g.Nq + q;
+            const float lse2 = valid ? g.lse[sidx] * 1.4426950408889634f : 0.f;
+            const float dlt = valid ? g.delta[sidx] : 0.f;
+            // ---- P ----
+            mbar_wait(s_full, par, 60u);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t raw[32];
+                tc_ld32(lane_addr + TM_S + static_cast<uint32_t>(c * 32), raw);
+                tc_wait_ld();
+                float p[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float e = exp2f(__uint_as_float(raw[k]) * g.scale_log2 - lse2);
+                    p[k] = (valid && (c * 32 + k < kv_valid)) ? e : 0.f;
+                }
+                uint8_t* rowp = pbuf + (c >> 1) * TILE_BYTES + r * 128;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    uint4 w;
+                    w.x = pack_bf16x2(p[8 * qq + 0], p[8 * qq + 1]);
+                    w.y = pack_bf16x2(p[8 * qq + 2], p[8 * qq + 3]);
+                    w.z = pack_bf16x2(p[8 * qq + 4], p[8 * qq + 5]);
+                    w.w = pack_bf16x2(p[8 * qq + 6], p[8 * qq + 7]);
+                    const int chunk = ((c & 1) * 4 + qq) ^ (r & 7);
+                    *reinterpret_cast<uint4*>(rowp + chunk * 16) = w;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_ready);
+            // ---- dS = P * (dP - delta) * scale ----
+            mbar_wait(dp_full, par, 61u);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t raw[32], rdp[32];
+                tc_ld32(lane_addr + TM_S + static_cast<uint32_t>(c * 32), raw);
+                tc_ld32(lane_addr + TM_DP + static_cast<uint32_t>(c * 32), rdp);
+                tc_wait_ld();
+                float d[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float e = exp2f(__uint_as_float(raw[k]) * g.scale_log2 - lse2);
+                    const float ds = e * (__uint_as_float(rdp[k]) - dlt) * g.scale;
+                    d[k] = (valid && (c * 32 + k < kv_valid)) ? ds : 0.f;
+                }
+                uint8_t* rowp = dsbuf + (c >> 1) * TILE_BYTES + r * 128;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    uint4 w;
+                    w.x = pack_bf16x2(d[8 * qq + 0], d[8 * qq + 1]);
+                    w.y = pack_bf16x2(d[8 * qq + 2], d[8 * qq + 3]);
+                    w.z = pack_bf16x2(d[8 * qq + 4], d[8 * qq + 5]);
+                    w.w = pack_bf16x2(d[8 * qq + 6], d[8 * qq + 7]);
+                    const int chunk = ((c & 1) * 4 + qq) ^ (r & 7);
+                    *reinterpret_cast<uint4*>(rowp + chunk * 16) = w;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(ds_ready);
+            // ---- dQ_i partial -> global fp32 accumulator ----
+            mbar_wait(dq_full, par, 62u);
+            tc_fence_after();
+            float* dqp = g.dQ + static_cast<long long>(b) * g.dq_batch_stride + static_cast<long long>(q) * g.dq_row_stride +
+                         static_cast<long long>(h) * HD;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t raw[32];
+                tc_ld32(lane_addr + TM_DQ + static_cast<uint32_t>(c * 32), raw);
+                tc_wait_ld();
+                if (valid) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqp + c * 32 + 4 * k),
+                                     "f"(__uint_as_float(raw[4 * k])), "f"(__uint_as_float(raw[4 * k + 1])),
+                                     "f"(__uint_as_float(raw[4 * k + 2])), "f"(__uint_as_float(raw[4 * k + 3]))
+                                     : "memory");
+                }
+            }
+            tc_fence_before();
+        }
+        // ---- dV, dK of this K/V tile (all MMAs retired: dq_full of the last tile covers them) ----
+        const int kvrow = kv0 + r;
+        if (Tq == 0) {
+            // nothing accumulated
+        }
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            float o[HD];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t raw[32];
+                tc_ld32(lane_addr + (which ? TM_DK : TM_DV) + static_cast<uint32_t>(c * 32), raw);
+                tc_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) o[c * 32 + k] = __uint_as_float(raw[k]);
+            }
+            if (kvrow < g.Nk) {
+                bf16* op = (which ? g.dK : g.dV) + static_cast<long long>(b) * g.dkv_batch_stride +
+                           static_cast<long long>(kvrow) * g.dkv_row_stride + static_cast<long long>(h) * HD;
+#pragma unroll
+                for (int c = 0; c < HD / 8; ++c) {
+                    uint4 w;
+                    w.x = pack_bf16x2(o[8 * c + 0], o[8 * c + 1]);
+                    w.y = pack_bf16x2(o[8 * c + 2], o[8 * c + 3]);
+                    w.z = pack_bf16x2(o[8 * c + 4], o[8 * c + 5]);
+                    w.w = pack_bf16x2(o[8 * c + 6], o[8 * c + 7]);
+                    reinterpret_cast<uint4*>(op)[c] = w;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 int make_qkv_tmap(CUtensorMap* tm, const void* p, int N, int H, int B, long long row_stride, long long head_stride,
                   long long batch_stride) {
     const uint64_t dims[4] = {static_cast<uint64_t>(HD), static_cast<uint64_t>(H), static_cast<uint64_t>(N),
@@ -327,6 +607,52 @@ int nk_attention_fwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
     }
     dim3 grid((Nq + BQ - 1) / BQ, H, B);
     attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(g);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+
+
+// Gradients of nk_attention_fwd.  dq_acc: fp32 [B, Nq, H, 64] ZERO-INITIALISED accumulator (contiguous);
+// dk, dv: bf16 [B, Nk, H, 64] (contiguous).  lse from the forward, delta[b,h,q] = sum_d dO*O (nk_attn_delta).
+int nk_attention_bwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride, const void* k, int64_t k_row_stride,
+                     int64_t k_batch_stride, const void* v, int64_t v_row_stride, int64_t v_batch_stride,
+                     const void* dO, int64_t do_row_stride, int64_t do_batch_stride, const float* lse,
+                     const float* delta, float* dq_acc, void* dk, void* dv, int B, int H, int Nq, int Nk, int head_dim,
+                     float scale, nk_stream_t stream) {
+    NK_REQUIRE(head_dim == HD, NK_ERR_UNSUPPORTED, "fused attention backward supports head_dim 64 (got %d)", head_dim);
+    NK_REQUIRE(B > 0 && H > 0 && Nq > 0 && Nk > 0, NK_ERR_SHAPE, "attention bwd: empty problem");
+    AttnBwdDev g;
+    memset(&g, 0, sizeof(g));
+    int e = make_qkv_tmap(&g.tmQ, q, Nq, H, B, q_row_stride, HD, q_batch_stride);
+    if (e) return e;
+    e = make_qkv_tmap(&g.tmK, k, Nk, H, B, k_row_stride, HD, k_batch_stride);
+    if (e) return e;
+    e = make_qkv_tmap(&g.tmV, v, Nk, H, B, v_row_stride, HD, v_batch_stride);
+    if (e) return e;
+    e = make_qkv_tmap(&g.tmdO, dO, Nq, H, B, do_row_stride, HD, do_batch_stride);
+    if (e) return e;
+    g.lse = lse;
+    g.delta = delta;
+    g.dQ = dq_acc;
+    g.dK = static_cast<bf16*>(dk);
+    g.dV = static_cast<bf16*>(dv);
+    g.dq_row_stride = static_cast<long long>(H) * HD;
+    g.dq_batch_stride = static_cast<long long>(Nq) * H * HD;
+    g.dkv_row_stride = static_cast<long long>(H) * HD;
+    g.dkv_batch_stride = static_cast<long long>(Nk) * H * HD;
+    g.Nq = Nq;
+    g.Nk = Nk;
+    g.H = H;
+    g.B = B;
+    g.scale = scale;
+    g.scale_log2 = scale * 1.4426950408889634f;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
+        attr_set = true;
+    }
+    dim3 grid((Nk + BKV - 1) / BKV, H, B);
+    attn_bwd_kernel<<<grid, ATT_THREADS, BW_SMEM, static_cast<cudaStream_t>(stream)>>>(g);
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }

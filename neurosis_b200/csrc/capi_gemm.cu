@@ -148,6 +148,16 @@ int nk_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, fl
     p.ldc = lddw;
     p.out = accumulate ? OUT_F32_ATOMIC : OUT_F32;
     p.epi = EPI_LINEAR;
+    if (!accumulate) {
+        // few output tiles but a long reduction (e.g. 640x640 weights, 32k tokens): zero the output and split K
+        // across CTAs with fp32 red.global.add instead of leaving most SMs idle
+        const long long tiles = static_cast<long long>((N + 255) / 256) * ((K + 255) / 256);
+        if (tiles * 2 <= nk::device_sm_count() / 2 && M >= 2048) {
+            NK_CUDA(cudaMemset2DAsync(dw, static_cast<size_t>(lddw) * 4, 0, static_cast<size_t>(K) * 4, N,
+                                      static_cast<cudaStream_t>(stream)));
+            p.out = OUT_F32_ATOMIC;
+        }
+    }
     return launch_gemm(p, static_cast<cudaStream_t>(stream));
 }
 

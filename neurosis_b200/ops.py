@@ -26,6 +26,7 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 LAUNCHES = 0  # number of kernel-launching C-ABI calls made (bench.py reports it)
+FORCE_MATERIALIZED_ATTN_BWD = False  # tests: exercise the batched-GEMM attention backward for head_dim 64 too
 PROFILE_GEMM = None  # bench.py sets this to a list: (start_event, end_event, algorithmic_flops) per tensor-core launch
 
 
@@ -522,6 +523,17 @@ def attention_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: T
     delta = torch.empty((B, H, Nq), dtype=F32, device=dev)
     doc = do.contiguous()
     check(lib.nk_attn_delta(doc.data_ptr(), o.data_ptr(), delta.data_ptr(), B, Nq, H, D, _stream()), "attn_delta")
+    if D == 64 and q.stride(2) == 64 and k.stride(2) == 64 and v.stride(2) == 64 and not FORCE_MATERIALIZED_ATTN_BWD:
+        # fused flash-style backward: one kernel, nothing of size Nq x Nk touches HBM
+        dq_acc = torch.zeros((B, Nq, H, D), dtype=F32, device=dev)
+        dk = torch.empty((B, Nk, H, D), dtype=BF16, device=dev)
+        dv = torch.empty((B, Nk, H, D), dtype=BF16, device=dev)
+        check(lib.nk_attention_bwd(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
+                                   v.data_ptr(), v.stride(1), v.stride(0), doc.data_ptr(), doc.stride(1), doc.stride(0),
+                                   lse.data_ptr(), delta.data_ptr(), dq_acc.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                   B, H, Nq, Nk, D, float(scale), _stream()), "attention_bwd")
+        _count(2)
+        return cast_bf16(dq_acc), dk, dv
     Nkp = (Nk + 7) // 8 * 8
     P = torch.zeros((B, H, Nq, Nkp), dtype=BF16, device=dev) if Nkp != Nk else torch.empty(
         (B, H, Nq, Nkp), dtype=BF16, device=dev)

@@ -233,6 +233,21 @@ def test_attention_fwd_bwd(B, H, Nq, Nk, D):
     assert rel(v.grad, vr.grad) < 2e-2
 
 
+def test_attention_bwd_materialized_path_d64():
+    """the batched-GEMM backward (used for head dims != 64) must agree with the fused kernel's reference too."""
+    B, H, N, D = 1, 3, 384, 64
+    q, k, v = (rnd(B, N, H, D, seed=s_).to(BF).requires_grad_(True) for s_ in (0, 1, 2))
+    go = rnd(B, N, H, D, seed=3).to(BF)
+    ops.FORCE_MATERIALIZED_ATTN_BWD = True
+    try:
+        ops.attention(q, k, v).backward(go)
+    finally:
+        ops.FORCE_MATERIALIZED_ATTN_BWD = False
+    qr, kr, vr = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    sdpa_ref(qr, kr, vr, D ** -0.5).backward(go.float())
+    assert rel(q.grad, qr.grad) < 2e-2 and rel(k.grad, kr.grad) < 2e-2 and rel(v.grad, vr.grad) < 2e-2
+
+
 def test_attention_strided_qkv_views():
     """q/k/v as column slices of one fused projection output (row stride 3*H*D)."""
     B, N, H, D = 2, 384, 5, 64
