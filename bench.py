@@ -268,6 +268,24 @@ def main() -> None:
         step(resident, False)
         torch.cuda.synchronize()
         recs, ops.PROFILE_GEMM = ops.PROFILE_GEMM, None
+        if args.breakdown and rank == 0:  # second pass: every C-ABI entry point
+            ops.PROFILE_KERNELS = []
+            e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_a.record()
+            step(resident, False)
+            e_b.record()
+            torch.cuda.synchronize()
+            krecs, ops.PROFILE_KERNELS = ops.PROFILE_KERNELS, None
+            kagg = {}
+            for name, a, b in krecs:
+                v = kagg.setdefault(name, [0.0, 0])
+                v[0] += a.elapsed_time(b)
+                v[1] += 1
+            with open(args.breakdown + ".entrypoints", "w") as fh:
+                tot = sum(v[0] for v in kagg.values())
+                fh.write(f"profiled step {e_a.elapsed_time(e_b):.2f} ms ; sum over C-ABI calls {tot:.2f} ms ; calls {len(krecs)}\n")
+                for name, (ms, n) in sorted(kagg.items(), key=lambda kv: -kv[1][0]):
+                    fh.write(f"{ms:9.3f} ms {100 * ms / tot:5.1f}%  {n:5d}x  {name}\n")
         t_ms = sum(r[0].elapsed_time(r[1]) for r in recs)
         fl = sum(r[2] for r in recs)
         if args.breakdown and rank == 0:

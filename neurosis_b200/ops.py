@@ -20,7 +20,8 @@ from typing import Optional
 import torch
 from torch import Tensor
 
-from ._lib import check, lib, nk_gemm_desc
+from ._lib import check, nk_gemm_desc
+from ._lib import lib as _real_lib
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -28,6 +29,36 @@ F32 = torch.float32
 LAUNCHES = 0  # number of kernel-launching C-ABI calls made (bench.py reports it)
 FORCE_MATERIALIZED_ATTN_BWD = False  # tests: exercise the batched-GEMM attention backward for head_dim 64 too
 PROFILE_GEMM = None  # bench.py sets this to a list: (start_event, end_event, algorithmic_flops) per tensor-core launch
+
+
+PROFILE_KERNELS = None  # bench.py --breakdown: list of (entry point, start_event, end_event) for every C-ABI call
+
+
+class _LibProxy:
+    """forwards to the ctypes library; when PROFILE_KERNELS is a list every call is bracketed by CUDA events."""
+
+    def __init__(self, real):
+        self._real = real
+
+    def __getattr__(self, name):
+        fn = getattr(self._real, name)
+
+        def call(*args):
+            prof = PROFILE_KERNELS
+            if prof is None:
+                return fn(*args)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            prof.append((name, e0, e1))
+            return rc
+
+        self.__dict__[name] = call
+        return call
+
+
+lib = _LibProxy(_real_lib)
 
 
 def _tc(rc_fn, what: str, flops: float, *args) -> None:
