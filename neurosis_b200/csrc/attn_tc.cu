@@ -42,6 +42,63 @@ constexpr int SM_P = SM_V + KV_STAGES * TILE_BYTES;
 constexpr int SM_BAR = SM_P + 4 * TILE_BYTES;
 constexpr int ATT_SMEM = SM_BAR + 256 + 1024;
 
+// ---- softmax building blocks shared by the forward kernel: one thread = one query row, S row lives in TMEM ----
+template <bool MASK>
+__device__ __forceinline__ float tile_rowmax(uint32_t s_addr, int kv_valid) {
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; c += 2) {
+        uint32_t ra[32], rb[32];
+        tc_ld32(s_addr + static_cast<uint32_t>(c * 32), ra);
+        tc_ld32(s_addr + static_cast<uint32_t>((c + 1) * 32), rb);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float a = __uint_as_float(ra[i]), b = __uint_as_float(rb[i]);
+            if (MASK) {
+                a = (c * 32 + i < kv_valid) ? a : -INFINITY;
+                b = ((c + 1) * 32 + i < kv_valid) ? b : -INFINITY;
+            }
+            m0 = fmaxf(m0, a);
+            m1 = fmaxf(m1, b);
+        }
+    }
+    return fmaxf(m0, m1);
+}
+
+// p = exp2(s*scale_log2 - mb) -> bf16, written to the 128B-swizzled [row][kv] tile pair at pbuf; returns the row sum
+template <bool MASK>
+__device__ __forceinline__ float tile_probs(uint32_t s_addr, int kv_valid, float scale_log2, float mb, uint8_t* pbuf,
+                                            int r) {
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tc_ld32(s_addr + static_cast<uint32_t>(c * 32), raw);
+        tc_wait_ld();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float v = exp2f(fmaf(__uint_as_float(raw[i]), scale_log2, -mb));
+            if (MASK) v = (c * 32 + i < kv_valid) ? v : 0.f;
+            p[i] = v;
+            if (i & 1) l1 += v; else l0 += v;
+        }
+        uint8_t* rowp = pbuf + (c >> 1) * TILE_BYTES + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 w;
+            w.x = pack_bf16x2(p[8 * q + 0], p[8 * q + 1]);
+            w.y = pack_bf16x2(p[8 * q + 2], p[8 * q + 3]);
+            w.z = pack_bf16x2(p[8 * q + 4], p[8 * q + 5]);
+            w.w = pack_bf16x2(p[8 * q + 6], p[8 * q + 7]);
+            const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+            *reinterpret_cast<uint4*>(rowp + chunk * 16) = w;
+        }
+    }
+    return l0 + l1;
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnDev g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -171,50 +228,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
             tc_fence_after();
             const uint32_t s_addr = lane_addr + TM_S + static_cast<uint32_t>((j & 1) * 128);
             const int kv_valid = g.Nk - j * BKV;  // columns >= kv_valid are padding
-            // pass 1: row max
-            float m_tile = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t raw[32];
-                tc_ld32(s_addr + static_cast<uint32_t>(c * 32), raw);
-                tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float v = (c * 32 + i < kv_valid) ? __uint_as_float(raw[i]) : -INFINITY;
-                    m_tile = fmaxf(m_tile, v);
-                }
-            }
+            // pass 1: row max ; pass 2: probabilities -> smem (bf16, swizzled) + row sum.  Only the last K/V tile
+            // can be partial, so the masked variant is taken at most once per row.
+            const bool tail = kv_valid < BKV;
+            const float m_tile = tail ? tile_rowmax<true>(s_addr, kv_valid) : tile_rowmax<false>(s_addr, kv_valid);
             const float m_new = fmaxf(m_run, m_tile);
             const float alpha = exp2f((m_run - m_new) * g.scale_log2);  // 0 on the first tile
             const float mb = m_new * g.scale_log2;
-            // pass 2: probabilities -> smem (bf16, swizzled), row sum
-            float l_tile = 0.f;
             uint8_t* pbuf = smem + SM_P + (j & 1) * 2 * TILE_BYTES;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t raw[32];
-                tc_ld32(s_addr + static_cast<uint32_t>(c * 32), raw);
-                tc_wait_ld();
-                float p[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float v = exp2f(__uint_as_float(raw[i]) * g.scale_log2 - mb);
-                    p[i] = (c * 32 + i < kv_valid) ? v : 0.f;
-                    l_tile += p[i];
-                }
-                // columns c*32 .. c*32+31 -> K-block (c>>1), 16B chunks ((c&1)*4 .. +3)
-                uint8_t* rowp = pbuf + (c >> 1) * TILE_BYTES + r * 128;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 w;
-                    w.x = pack_bf16x2(p[8 * q + 0], p[8 * q + 1]);
-                    w.y = pack_bf16x2(p[8 * q + 2], p[8 * q + 3]);
-                    w.z = pack_bf16x2(p[8 * q + 4], p[8 * q + 5]);
-                    w.w = pack_bf16x2(p[8 * q + 6], p[8 * q + 7]);
-                    const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
-                    *reinterpret_cast<uint4*>(rowp + chunk * 16) = w;
-                }
-            }
+            const float l_tile = tail ? tile_probs<true>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r)
+                                      : tile_probs<false>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[j & 1]);

@@ -61,6 +61,7 @@ struct alignas(64) GemmDev {
     const bf16* aux;
     uint32_t idesc;
     uint32_t a_bytes, b_bytes;  // bytes landed per stage for A and B
+    long long* dbg;             // optional per-CTA cycle counters (NK_GEMM_DEBUG_TIMING), 8 per CTA
 };
 
 struct TileCoord {
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            long long dbg_acc0 = 0;
             auto tma_load = [](const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
                 if (CG == 2) tma_load_4d_2cta(tm, bar, dst, c0, c1, c2, c3);
                 else tma_load_4d(tm, bar, dst, c0, c1, c2, c3);
@@ -179,7 +181,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 }
                 for (int it = 0; it < iters; ++it) {
                     const int gi = tc.split * g.k_iters + it;
+                    const long long tw0 = g.dbg ? clock64() : 0;
                     mbar_wait(&empty_bar[stage], phase ^ 1u, 100u + stage);
+                    if (g.dbg) dbg_acc0 += clock64() - tw0;
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * (g.a_bytes + g.b_bytes));
                     uint8_t* sa = smem_a + static_cast<size_t>(stage) * A_STAGE_BYTES;
                     uint8_t* sb = smem_b + static_cast<size_t>(stage) * b_stage_bytes;
@@ -229,6 +233,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     }
                 }
             }
+            if (g.dbg) g.dbg[blockIdx.x * 8 + 0] = dbg_acc0;
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA of the pair only) =====================
@@ -236,25 +241,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
+            long long dbg_full = 0, dbg_tempty = 0;
+            const long long dbg_t0 = g.dbg ? clock64() : 0;
             // per-k16 descriptor advance (in 16-byte units)
             const uint32_t a_adv = g.a_mn ? (2048u >> 4) : (32u >> 4);
             const uint32_t b_adv = g.b_mn ? (2048u >> 4) : (32u >> 4);
             const uint32_t a_lbo = g.a_mn ? static_cast<uint32_t>(ATOM_BYTES) : 16u;
             const uint32_t b_lbo = g.b_mn ? static_cast<uint32_t>(ATOM_BYTES) : 16u;
+            const uint64_t a_desc0 = make_smem_desc(smem_u32(smem_a), a_lbo, 1024u);
+            const uint64_t b_desc0 = make_smem_desc(smem_u32(smem_b), b_lbo, 1024u);
             for (int t = group; t < total_tiles; t += num_groups, ++local) {
                 const TileCoord tc = decode_tile(g, t);
                 const int iters = iters_of_split(g, tc.split);
                 const int acc = local & 1;
+                long long tw = g.dbg ? clock64() : 0;
                 mbar_wait(&tmem_empty[acc], ((local >> 1) & 1u) ^ 1u, 200u + acc);
+                if (g.dbg) dbg_tempty += clock64() - tw;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * ACC_STRIDE);
                 for (int it = 0; it < iters; ++it) {
+                    tw = g.dbg ? clock64() : 0;
                     mbar_wait(&full_bar[stage], phase, 300u + stage);
+                    if (g.dbg) dbg_full += clock64() - tw;
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem_a + static_cast<size_t>(stage) * A_STAGE_BYTES);
-                    const uint32_t sb = smem_u32(smem_b + static_cast<size_t>(stage) * b_stage_bytes);
-                    const uint64_t a_desc = make_smem_desc(sa, a_lbo, 1024u);
-                    const uint64_t b_desc = make_smem_desc(sb, b_lbo, 1024u);
+                    const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * A_STAGE_BYTES) >> 4);
+                    const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * b_stage_bytes) >> 4);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         if (CG == 2)
@@ -274,6 +285,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 }
                 if (CG == 2) tc_commit_2cta(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
             }
+            if (g.dbg) {
+                g.dbg[blockIdx.x * 8 + 1] = dbg_full;
+                g.dbg[blockIdx.x * 8 + 2] = dbg_tempty;
+                g.dbg[blockIdx.x * 8 + 3] = clock64() - dbg_t0;
+                g.dbg[blockIdx.x * 8 + 6] = local;
+            }
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
@@ -286,6 +303,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int c_begin = half ? (nch + 1) / 2 : 0;
         const int c_end = half ? nch : (nch + 1) / 2;
         int local = 0;
+        long long dbg_wait = 0, dbg_proc = 0;
         for (int t = group; t < total_tiles; t += num_groups, ++local) {
             const TileCoord tc = decode_tile(g, t);
             const int n0 = tc.nt * g.BN;
@@ -322,24 +340,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
             const float* bias_img_row = g.bias_img ? g.bias_img + static_cast<long long>(img) * g.N : nullptr;
 
-            mbar_wait(&tmem_full[acc], (local >> 1) & 1u, 400u + acc);
-            tc_fence_after();
-            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                    static_cast<uint32_t>(acc * ACC_STRIDE);
-
             auto side_vec_ok = [&](int c) -> bool {
                 const int n = n0 + c * 16;
                 return side_row != nullptr && (n + 16 <= g.N) &&
                        ((reinterpret_cast<uintptr_t>(side_row + n) & 15u) == 0);
             };
-            auto issue = [&](int c, uint32_t (&raw)[16], uint4& sa, uint4& sb) {
-                tc_ld16(taddr0 + static_cast<uint32_t>(c * 16), raw);
-                if (side_vec_ok(c)) {
+            auto load_side = [&](int c, uint4& sa, uint4& sb) {
+                if (c < c_end && side_vec_ok(c)) {
                     const uint4* sp = reinterpret_cast<const uint4*>(side_row + n0 + c * 16);
                     sa = __ldg(sp);
                     sb = __ldg(sp + 1);
                 }
             };
+            // side inputs of the first four chunks are requested BEFORE waiting for the accumulator, the rest as
+            // ring slots free up: their L2/HBM latency is off the critical path of the tile
+            uint4 sd[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sd[i][0] = make_uint4(0, 0, 0, 0);
+                sd[i][1] = make_uint4(0, 0, 0, 0);
+                load_side(c_begin + i, sd[i][0], sd[i][1]);
+            }
+
+            const long long te0 = g.dbg ? clock64() : 0;
+            mbar_wait(&tmem_full[acc], (local >> 1) & 1u, 400u + acc);
+            const long long te1 = g.dbg ? clock64() : 0;
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                    static_cast<uint32_t>(acc * ACC_STRIDE);
             auto process = [&](int c, const uint32_t (&raw)[16], const uint4& sa, const uint4& sb) {
                 const int n = n0 + c * 16;
                 if (!row_ok || n >= g.N) return;
@@ -428,17 +456,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 }
             };
             if (c_begin < c_end) {
-                uint32_t r0[16], r1[16];
-                uint4 s0a = make_uint4(0, 0, 0, 0), s0b = s0a, s1a = s0a, s1b = s0a;
-                issue(c_begin, r0, s0a, s0b);
-                for (int c = c_begin; c < c_end; c += 2) {
-                    tc_wait_ld16(r0);
-                    if (c + 1 < c_end) issue(c + 1, r1, s1a, s1b);
-                    process(c, r0, s0a, s0b);
-                    if (c + 1 < c_end) {
-                        tc_wait_ld16(r1);
-                        if (c + 2 < c_end) issue(c + 2, r0, s0a, s0b);
-                        process(c + 1, r1, s1a, s1b);
+                uint32_t rw[2][16];
+                tc_ld16(taddr0 + static_cast<uint32_t>(c_begin * 16), rw[0]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {  // at most 8 chunks per warp (BN <= 256)
+                    const int c = c_begin + i;
+                    if (c < c_end) {
+                        tc_wait_ld16(rw[i & 1]);
+                        if (c + 1 < c_end) tc_ld16(taddr0 + static_cast<uint32_t>((c + 1) * 16), rw[(i + 1) & 1]);
+                        process(c, rw[i & 1], sd[i & 3][0], sd[i & 3][1]);
+                        load_side(c + 4, sd[i & 3][0], sd[i & 3][1]);
                     }
                 }
             }
@@ -447,6 +474,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             if (lane == 0) {
                 if (CG == 2) mbar_arrive_remote(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
             }
+            if (g.dbg) {
+                dbg_wait += te1 - te0;
+                dbg_proc += clock64() - te1;
+            }
+        }
+        if (g.dbg && warp == 2 && lane == 0) {
+            g.dbg[blockIdx.x * 8 + 4] = dbg_wait;
+            g.dbg[blockIdx.x * 8 + 5] = dbg_proc;
         }
     }
 
@@ -600,6 +635,12 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
 
     // CTA-group size: pairs (cta_group::2, 256-row tiles, B tile split across the pair) whenever the problem has
     // at least two 128-row tiles and a wide enough N; single CTAs otherwise.
+    static long long* dbg_buf = nullptr;
+    static int dbg_on = -1;
+    if (dbg_on < 0) {
+        dbg_on = getenv("NK_GEMM_DEBUG_TIMING") ? 1 : 0;
+        if (dbg_on) NK_CUDA(cudaMalloc(&dbg_buf, 8 * 1024 * sizeof(long long)));
+    }
     static int env_cg = -1;
     if (env_cg < 0) {
         const char* e_ = getenv("NK_GEMM_CTA_GROUP");  // debugging / A-B switch: 1 or 2
@@ -620,16 +661,26 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     const int bnc = g.BN / cg;
     g.b_bytes = static_cast<uint32_t>(bnc) * 128u;
 
-    // split-K only when accumulating atomically
+    // split-K only when accumulating atomically: pick the split count that minimises
+    // waves x (k-iterations per split + fixed per-tile cost), i.e. fills the last wave
     int splits = 1;
     if (p.out == OUT_F32_ATOMIC) {
         const long long tiles = tiles_mb * g.tiles_n;
         const int groups = nsm / cg;
-        if (p.force_splits > 0)
+        if (p.force_splits > 0) {
             splits = p.force_splits;
-        else if (tiles < groups)
-            splits = static_cast<int>(std::min<long long>((2LL * groups + tiles - 1) / tiles,
-                                                           std::max(1, g.k_iters_total / 8)));
+        } else {
+            const int max_s = std::max(1, std::min(64, g.k_iters_total / 4));
+            long long best = -1;
+            for (int sp = 1; sp <= max_s; ++sp) {
+                const long long waves = (tiles * sp + groups - 1) / groups;
+                const long long cost = waves * ((g.k_iters_total + sp - 1) / sp + 10);
+                if (best < 0 || cost < best) {
+                    best = cost;
+                    splits = sp;
+                }
+            }
+        }
         splits = std::max(1, std::min(splits, g.k_iters_total));
     }
     g.k_iters = (g.k_iters_total + splits - 1) / splits;
@@ -677,6 +728,8 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     }
     const long long total = tiles_mb * g.tiles_n * g.splits;
     NK_REQUIRE(total < (1LL << 31), NK_ERR_SHAPE, "too many tiles");
+    g.dbg = dbg_buf;
+    if (dbg_buf) NK_CUDA(cudaMemsetAsync(dbg_buf, 0, 8 * 1024 * sizeof(long long), stream));
     if (cg == 1) {
         const int grid = static_cast<int>(std::min<long long>(total, nsm));
         gemm_tc_kernel<1><<<grid, NUM_THREADS, smem_bytes, stream>>>(g);
@@ -698,6 +751,24 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
         NK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, g));
     }
     NK_CUDA(cudaGetLastError());
+    if (dbg_buf) {  // debugging aid: per-role cycle accounting of the launch that just ran
+        NK_CUDA(cudaStreamSynchronize(stream));
+        static long long host[8 * 1024];
+        NK_CUDA(cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost));
+        const int nb = cg == 1 ? static_cast<int>(std::min<long long>(total, nsm)) : 2 * static_cast<int>(std::min<long long>(total, nsm / 2));
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int nlead = 0;
+        for (int b = 0; b < nb && b < 1024; b += cg) {
+            for (int i = 0; i < 8; ++i) a[i] += static_cast<double>(host[b * 8 + i]);
+            ++nlead;
+        }
+        for (int i = 0; i < 8; ++i) a[i] /= std::max(1, nlead);
+        fprintf(stderr,
+                "[nk gemm dbg] M=%d N=%d k_iters=%d BN=%d cg=%d stages=%d tiles=%lld splits=%d | per leader CTA: tiles %.1f  "
+                "mma loop %.0f clk (wait full %.0f, wait tmem_empty %.0f)  producer wait empty %.0f  "
+                "epilogue wait full %.0f proc %.0f\n",
+                p.M, p.N, g.k_iters, g.BN, cg, g.stages, total, g.splits, a[6], a[3], a[1], a[2], a[0], a[4], a[5]);
+    }
     return NK_OK;
 }
 
