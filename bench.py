@@ -218,6 +218,7 @@ def main() -> None:
     eng = build_engine(dev)
     params = [p for p in eng.model.parameters() if p.requires_grad]
     reducer = BucketedGradReducer(params, bucket_mb=256.0)
+    reducer.attach_as_grad_sink()  # wgrad kernels accumulate straight into the gradient buckets
 
     g = torch.Generator().manual_seed(42 + rank)  # per-rank data
     host = {"image": (torch.rand(B, 3, 1024, 1024, generator=g) * 2 - 1).pin_memory(),

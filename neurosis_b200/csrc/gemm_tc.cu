@@ -340,34 +340,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
             const float* bias_img_row = g.bias_img ? g.bias_img + static_cast<long long>(img) * g.N : nullptr;
 
-            auto side_vec_ok = [&](int c) -> bool {
-                const int n = n0 + c * 16;
-                return side_row != nullptr && (n + 16 <= g.N) &&
-                       ((reinterpret_cast<uintptr_t>(side_row + n) & 15u) == 0);
-            };
-            auto load_side = [&](int c, uint4& sa, uint4& sb) {
-                if (c < c_end && side_vec_ok(c)) {
-                    const uint4* sp = reinterpret_cast<const uint4*>(side_row + n0 + c * 16);
-                    sa = __ldg(sp);
-                    sb = __ldg(sp + 1);
-                }
-            };
-            // side inputs of the first four chunks are requested BEFORE waiting for the accumulator, the rest as
-            // ring slots free up: their L2/HBM latency is off the critical path of the tile
-            uint4 sd[4][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                sd[i][0] = make_uint4(0, 0, 0, 0);
-                sd[i][1] = make_uint4(0, 0, 0, 0);
-                load_side(c_begin + i, sd[i][0], sd[i][1]);
-            }
-
             const long long te0 = g.dbg ? clock64() : 0;
             mbar_wait(&tmem_full[acc], (local >> 1) & 1u, 400u + acc);
             const long long te1 = g.dbg ? clock64() : 0;
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                     static_cast<uint32_t>(acc * ACC_STRIDE);
+
+            auto side_vec_ok = [&](int c) -> bool {
+                const int n = n0 + c * 16;
+                return side_row != nullptr && (n + 16 <= g.N) &&
+                       ((reinterpret_cast<uintptr_t>(side_row + n) & 15u) == 0);
+            };
+            auto issue = [&](int c, uint32_t (&raw)[16], uint4& sa, uint4& sb) {
+                tc_ld16(taddr0 + static_cast<uint32_t>(c * 16), raw);
+                if (side_vec_ok(c)) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(side_row + n0 + c * 16);
+                    sa = __ldg(sp);
+                    sb = __ldg(sp + 1);
+                }
+            };
             auto process = [&](int c, const uint32_t (&raw)[16], const uint4& sa, const uint4& sb) {
                 const int n = n0 + c * 16;
                 if (!row_ok || n >= g.N) return;
@@ -456,16 +448,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 }
             };
             if (c_begin < c_end) {
-                uint32_t rw[2][16];
-                tc_ld16(taddr0 + static_cast<uint32_t>(c_begin * 16), rw[0]);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {  // at most 8 chunks per warp (BN <= 256)
-                    const int c = c_begin + i;
-                    if (c < c_end) {
-                        tc_wait_ld16(rw[i & 1]);
-                        if (c + 1 < c_end) tc_ld16(taddr0 + static_cast<uint32_t>((c + 1) * 16), rw[(i + 1) & 1]);
-                        process(c, rw[i & 1], sd[i & 3][0], sd[i & 3][1]);
-                        load_side(c + 4, sd[i & 3][0], sd[i & 3][1]);
+                uint32_t r0[16], r1[16];
+                uint4 s0a = make_uint4(0, 0, 0, 0), s0b = s0a, s1a = s0a, s1b = s0a;
+                issue(c_begin, r0, s0a, s0b);
+                for (int c = c_begin; c < c_end; c += 2) {
+                    tc_wait_ld16(r0);
+                    if (c + 1 < c_end) issue(c + 1, r1, s1a, s1b);
+                    process(c, r0, s0a, s0b);
+                    if (c + 1 < c_end) {
+                        tc_wait_ld16(r1);
+                        if (c + 2 < c_end) issue(c + 2, r0, s0a, s0b);
+                        process(c + 1, r1, s1a, s1b);
                     }
                 }
             }
@@ -538,8 +531,11 @@ int pick_bn(const GemmProblem& p, long long tiles_m_batches, int groups, int cg)
     for (int bn = 256; bn >= step; bn -= step) {
         const long long tiles = tiles_m_batches * ((p.N + bn - 1) / bn);
         const long long waves = (tiles + groups - 1) / groups;
-        // cycles per k16 step and CTA: tensor pipe BN/2 vs smem feed (4 KB of A + (BN/cg)*32 B of B at 128 B/clk)
-        const long long per = std::max<long long>(bn / 2, 32 + bn / (4 * cg)) + 6;
+        // cycles per k16 step: BN/2 on the tensor pipe, but never below ~128: measured on B200 (in-kernel cycle
+        // accounting, profiles/r01_gemm_debug_timing.txt) every UMMA with a 128-row A slab per SM costs >= ~130 clk
+        // whatever N is (the A operand is re-read from smem per instruction), so narrow tiles only pay off when they
+        // remove whole waves
+        const long long per = std::max<long long>(bn / 2, 128) + 8;
         const long long cost = waves * per;
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;

@@ -75,6 +75,25 @@ class BucketedGradReducer:
             yield b["flat"][off: off + p.numel()].view_as(p)
             off += p.numel()
 
+    # -- gradient sink protocol used by neurosis_b200.ops (weight gradients are written straight into the buckets) --
+    def buffer_for(self, p: nn.Parameter):
+        if p not in self._index:
+            return None
+        g = p.grad
+        return g if (g is not None and g.dtype == torch.float32) else None
+
+    def mark_ready(self, p: nn.Parameter) -> None:
+        self._on_grad(p)
+
+    def attach_as_grad_sink(self) -> None:
+        from . import ops
+        ops.GRAD_SINK = self
+
+    def detach_grad_sink(self) -> None:
+        from . import ops
+        if ops.GRAD_SINK is self:
+            ops.GRAD_SINK = None
+
     def _on_grad(self, p: nn.Parameter) -> None:
         if not self.enabled or self.world == 1:
             return

@@ -61,6 +61,21 @@ class _LibProxy:
 lib = _LibProxy(_real_lib)
 
 
+GRAD_SINK = None  # set by neurosis_b200.ddp.BucketedGradReducer: weight gradients are written straight into its buckets
+
+
+def _grad_sink(weight: Tensor):
+    """(fp32 buffer shaped like `weight`, base parameter) if a reducer owns this parameter's gradient storage."""
+    sink = GRAD_SINK
+    if sink is None:
+        return None, None
+    base = weight._base if weight._base is not None else weight
+    buf = sink.buffer_for(base)
+    if buf is None:
+        return None, None
+    return buf.view(weight.shape), base
+
+
 def _tc(rc_fn, what: str, flops: float, *args) -> None:
     """call a tensor-core GEMM entry point; optionally bracket it with CUDA events for the roofline report."""
     if PROFILE_GEMM is None:
@@ -263,10 +278,12 @@ def conv2d_wgrad(dy: Tensor, x: Tensor, cout: int, ksize: int) -> Tensor:
     return dwp
 
 
-def conv_unpack_wgrad(dwp: Tensor, co: int, ci: int, ks: int) -> Tensor:
+def conv_unpack_wgrad(dwp: Tensor, co: int, ci: int, ks: int, out: Optional[Tensor] = None) -> Tensor:
+    """packed [co, taps, cip] fp32 -> OIHW fp32; with `out` given the values are ADDED into it."""
     cip = dwp.shape[-1] if dwp.dim() == 3 else dwp.shape[-1] // (ks * ks)
-    dw = torch.empty((co, ci, ks, ks), dtype=F32, device=dwp.device)
-    check(lib.nk_conv_unpack_wgrad(dwp.data_ptr(), dw.data_ptr(), co, ci, ks, cip, 0, _stream()), "conv_unpack_wgrad")
+    dw = out if out is not None else torch.empty((co, ci, ks, ks), dtype=F32, device=dwp.device)
+    check(lib.nk_conv_unpack_wgrad(dwp.data_ptr(), dw.data_ptr(), co, ci, ks, cip, int(out is not None), _stream()),
+          "conv_unpack_wgrad")
     _count()
     return dw
 
@@ -663,7 +680,14 @@ class LinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         w = bf16_weight(weight)
         dx = linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
-        dw = linear_wgrad(dy, x) if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            buf, base = _grad_sink(weight)
+            if buf is not None:  # accumulate straight into the (zeroed) gradient bucket, no autograd "+=" pass
+                linear_wgrad(dy, x, out=buf)
+                GRAD_SINK.mark_ready(base)
+            else:
+                dw = linear_wgrad(dy, x)
         db = colsum(dy)[0] if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         dres = dy.view(-1, dy.shape[-1]).view(dy.shape) if (ctx.has_res and ctx.needs_input_grad[3]) else None
         return dx, dw, db, dres, None
@@ -701,7 +725,12 @@ class Conv2dFn(torch.autograd.Function):
                 dx = dx[..., : x.shape[-1]].contiguous()
         if ctx.needs_input_grad[1]:
             dwp = conv2d_wgrad(dy, x, co, ks)
-            dw = conv_unpack_wgrad(dwp, co, ci, ks)
+            buf, base = _grad_sink(weight)
+            if buf is not None:
+                conv_unpack_wgrad(dwp, co, ci, ks, out=buf)
+                GRAD_SINK.mark_ready(base)
+            else:
+                dw = conv_unpack_wgrad(dwp, co, ci, ks)
         if (has_bias and ctx.needs_input_grad[2]) or (has_bimg and ctx.needs_input_grad[3]):
             n = dy.shape[0]
             s = colsum(dy, groups=n)[:, :co]
@@ -747,7 +776,12 @@ class ConvStridedFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             col = im2col(x, ks, 2, pad_t, pad_l, ho, wo)
             dwp = linear_wgrad(dy2, col)
-            dw = conv_unpack_wgrad(dwp, co, ci, ks)
+            buf, base = _grad_sink(weight)
+            if buf is not None:
+                conv_unpack_wgrad(dwp, co, ci, ks, out=buf)
+                GRAD_SINK.mark_ready(base)
+            else:
+                dw = conv_unpack_wgrad(dwp, co, ci, ks)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2)[0]
         return dx, dw, db, None, None, None, None

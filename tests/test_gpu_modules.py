@@ -150,3 +150,28 @@ def test_engine_training_step_end_to_end():
     grads = [p.grad for p in unet.parameters()]
     assert all(g is not None and torch.isfinite(g).all() for g in grads)
     assert all(p.grad is None for p in enc.parameters())
+
+
+def test_grad_sink_matches_autograd_accumulation():
+    """weight gradients written straight into the reducer's buckets == gradients accumulated by autograd."""
+    from neurosis_b200.ddp import BucketedGradReducer
+    cfg = TINY_SD15
+    x = synth_tensor("sd15.x", (2, 4, 16, 16)).to(DEV)
+    ctx = synth_tensor("sd15.ctx", (2, 77, cfg["context_dim"])).to(DEV)
+    ts = torch.tensor([17, 803], device=DEV)
+    gout = synth_tensor("sd15.gout", (2, 4, 16, 16), scale=0.1).to(DEV)
+    m1 = build_unet(cfg)
+    (m1(x, ts, ctx) * gout).sum().backward()
+    m2 = build_unet(cfg)
+    red = BucketedGradReducer(m2.parameters(), bucket_mb=8.0)
+    red.attach_as_grad_sink()
+    try:
+        for _ in range(2):  # second pass checks zero_grad + re-accumulation into the same buckets
+            red.zero_grad()
+            (m2(x, ts, ctx) * gout).sum().backward()
+            red.finish()
+    finally:
+        red.detach_grad_sink()
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert p2.grad.data_ptr() == next(v for q, v in zip(red.buckets[red._index[p2]]["params"], red._views(red.buckets[red._index[p2]])) if q is p2).data_ptr()
+        assert rel(p2.grad, p1.grad) < 2e-3, n1
