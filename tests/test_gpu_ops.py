@@ -45,6 +45,16 @@ def test_linear_fwd_bwd(M, N, K):
     assert rel(r.grad, rr.grad) < 1e-6
 
 
+def test_linear_wgrad_into_grad_sink_is_exact():
+    """accumulating dW into a pre-zeroed bucket (fp32 red.global.add) equals the stored result up to fp32 reordering."""
+    x, dy = rnd(4096, 640).to(BF), rnd(4096, 320, seed=1).to(BF)
+    ref = ops.linear_wgrad(dy, x)
+    buf = torch.zeros_like(ref)
+    ops.linear_wgrad(dy, x, out=buf)
+    ops.linear_wgrad(dy, x, out=buf)
+    assert rel(buf, 2 * ref) < 1e-5
+
+
 def test_linear_out_f32():
     x, w = rnd(64, 320).to(BF), rnd(640, 320, seed=1) * 0.05
     y = ops.linear(x, w, None, None, True)
