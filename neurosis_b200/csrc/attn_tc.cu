@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     uint64_t* p_ready = bars + 7;        // 128 arrivals
     uint64_t* ds_ready = bars + 8;       // 128 arrivals
     uint64_t* dq_full = bars + 9;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* dv_done = bars + 10;       // commit after the dV MMAs: P smem may be rewritten
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
         mbar_init(p_ready, 128);
         mbar_init(ds_ready, 128);
         mbar_init(dq_full, 1);
+        mbar_init(dv_done, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -401,25 +403,32 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
             const uint32_t idesc_km = make_idesc_bf16(128, HD, 0, 1);   // dQ: dS K-major, K MN-major
             const uint32_t k_addr = smem_u32(smem + BW_K), v_addr = smem_u32(smem + BW_V);
             const uint32_t p_addr = smem_u32(smem + BW_P), ds_addr = smem_u32(smem + BW_DS);
+            // S_i / dP_i of the NEXT tile are issued right after ds_ready(i) so they execute behind dK_i / dQ_i and the
+            // softmax warps never wait for the tensor pipe in steady state.
+            auto issue_s_dp = [&](int i) {
+                const int st = i & 1;
+                const uint32_t q_addr = smem_u32(smem + BW_Q + st * TILE_BYTES);
+                const uint32_t do_addr = smem_u32(smem + BW_DO + st * TILE_BYTES);
+                mbar_wait(&qdo_full[st], (i >> 1) & 1u, 51u);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // S = Q K^T   (K = d = 64: 4 k-steps of 32 bytes)
+                    tc_mma_ss(tmem_base + TM_S, make_smem_desc(q_addr + k * 32, 16u, 1024u),
+                              make_smem_desc(k_addr + k * 32, 16u, 1024u), idesc_kk, k > 0 ? 1u : 0u);
+                tc_commit(s_full);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // dP = dO V^T
+                    tc_mma_ss(tmem_base + TM_DP, make_smem_desc(do_addr + k * 32, 16u, 1024u),
+                              make_smem_desc(v_addr + k * 32, 16u, 1024u), idesc_kk, k > 0 ? 1u : 0u);
+                tc_commit(dp_full);
+            };
             mbar_wait(kv_full, 0, 50);
+            issue_s_dp(0);
             for (int i = 0; i < Tq; ++i) {
                 const int st = i & 1;
                 const uint32_t par = static_cast<uint32_t>(i & 1);
                 const uint32_t q_addr = smem_u32(smem + BW_Q + st * TILE_BYTES);
                 const uint32_t do_addr = smem_u32(smem + BW_DO + st * TILE_BYTES);
-                mbar_wait(&qdo_full[st], (i >> 1) & 1u, 51u);
-                tc_fence_after();
-                // S = Q K^T ; dP = dO V^T   (K = d = 64: 4 k-steps of 32 bytes)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    tc_mma_ss(tmem_base + TM_S, make_smem_desc(q_addr + k * 32, 16u, 1024u),
-                              make_smem_desc(k_addr + k * 32, 16u, 1024u), idesc_kk, k > 0 ? 1u : 0u);
-                tc_commit(s_full);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    tc_mma_ss(tmem_base + TM_DP, make_smem_desc(do_addr + k * 32, 16u, 1024u),
-                              make_smem_desc(v_addr + k * 32, 16u, 1024u), idesc_kk, k > 0 ? 1u : 0u);
-                tc_commit(dp_full);
                 // dV += P^T dO   (M = kv, N = d, K = q = 128: 8 k-steps of 16 q-rows = 2048 bytes)
                 mbar_wait(p_ready, par, 52u);
                 tc_fence_after();
@@ -427,6 +436,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
                 for (int k = 0; k < 8; ++k)
                     tc_mma_ss(tmem_base + TM_DV, make_smem_desc(p_addr + k * 2048, 16384u, 1024u),
                               make_smem_desc(do_addr + k * 2048, 8192u, 1024u), idesc_mm, (i > 0 || k > 0) ? 1u : 0u);
+                tc_commit(dv_done);
                 // dK += dS^T Q ;  dQ_i = dS K
                 mbar_wait(ds_ready, par, 53u);
                 tc_fence_after();
@@ -441,6 +451,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
                               make_smem_desc(k_addr + k * 2048, 8192u, 1024u), idesc_km, k > 0 ? 1u : 0u);
                 tc_commit(dq_full);
                 tc_commit(&qdo_empty[st]);
+                if (i + 1 < Tq) issue_s_dp(i + 1);  // S/dP TMEM are free: the softmax warps passed ds_ready(i)
             }
         }
     } else {
@@ -450,6 +461,30 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
         const int kv_valid = g.Nk - kv0;  // columns >= kv_valid are padding
         uint8_t* pbuf = smem + BW_P;
         uint8_t* dsbuf = smem + BW_DS;
+        const bool kv_full_tile = kv_valid >= BKV;
+        // dQ partial of tile `it` -> global fp32 accumulator (other K/V tiles add to the same rows)
+        auto flush_dq = [&](int it) {
+            mbar_wait(dq_full, static_cast<uint32_t>(it & 1), 62u);
+            tc_fence_after();
+            const int q = it * BQ + r;
+            float* dqp = g.dQ + static_cast<long long>(b) * g.dq_batch_stride + static_cast<long long>(q) * g.dq_row_stride +
+                         static_cast<long long>(h) * HD;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t raw[32];
+                tc_ld32(lane_addr + TM_DQ + static_cast<uint32_t>(c * 32), raw);
+                tc_wait_ld();
+                if (q < g.Nq) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqp + c * 32 + 4 * k),
+                                     "f"(__uint_as_float(raw[4 * k])), "f"(__uint_as_float(raw[4 * k + 1])),
+                                     "f"(__uint_as_float(raw[4 * k + 2])), "f"(__uint_as_float(raw[4 * k + 3]))
+                                     : "memory");
+                }
+            }
+            tc_fence_before();
+        };
         for (int i = 0; i < Tq; ++i) {
             const uint32_t par = static_cast<uint32_t>(i & 1);
             const int q = i * BQ + r;
@@ -457,9 +492,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
             const long long sidx = (static_cast<long long>(b) * g.H + h) * g.Nq + q;
             const float lse2 = valid ? g.lse[sidx] * 1.4426950408889634f : 0.f;
             const float dlt = valid ? g.delta[sidx] : 0.f;
-            // ---- P ----
+            const bool nomask = kv_full_tile && ((i + 1) * BQ <= g.Nq);  // warp-uniform: whole tile in range
+            // ---- P = exp2(scale*log2e*S - lse*log2e) ----
             mbar_wait(s_full, par, 60u);
             tc_fence_after();
+            if (i > 0) mbar_wait(dv_done, static_cast<uint32_t>((i - 1) & 1), 63u);  // dV_{i-1} no longer reads P
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t raw[32];
@@ -468,8 +505,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
                 float p[32];
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
-                    const float e = exp2f(__uint_as_float(raw[k]) * g.scale_log2 - lse2);
-                    p[k] = (valid && (c * 32 + k < kv_valid)) ? e : 0.f;
+                    const float e = exp2f(fmaf(__uint_as_float(raw[k]), g.scale_log2, -lse2));
+                    p[k] = (nomask || (valid && (c * 32 + k < kv_valid))) ? e : 0.f;
                 }
                 uint8_t* rowp = pbuf + (c >> 1) * TILE_BYTES + r * 128;
 #pragma unroll
@@ -486,58 +523,44 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(p_ready);
-            // ---- dS = P * (dP - delta) * scale ----
+            // ---- dQ of the previous tile (its MMAs ran behind our P pass); also frees the dS smem tile ----
+            if (i > 0) flush_dq(i - 1);
+            // ---- dS = P * (dP - delta) * scale ; P (bf16) is read back from this thread's own smem row ----
             mbar_wait(dp_full, par, 61u);
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                uint32_t raw[32], rdp[32];
-                tc_ld32(lane_addr + TM_S + static_cast<uint32_t>(c * 32), raw);
+                uint32_t rdp[32];
                 tc_ld32(lane_addr + TM_DP + static_cast<uint32_t>(c * 32), rdp);
-                tc_wait_ld();
-                float d[32];
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float e = exp2f(__uint_as_float(raw[k]) * g.scale_log2 - lse2);
-                    const float ds = e * (__uint_as_float(rdp[k]) - dlt) * g.scale;
-                    d[k] = (valid && (c * 32 + k < kv_valid)) ? ds : 0.f;
-                }
+                const uint8_t* prow = pbuf + (c >> 1) * TILE_BYTES + r * 128;
                 uint8_t* rowp = dsbuf + (c >> 1) * TILE_BYTES + r * 128;
+                uint4 pw[4];
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
-                    uint4 w;
-                    w.x = pack_bf16x2(d[8 * qq + 0], d[8 * qq + 1]);
-                    w.y = pack_bf16x2(d[8 * qq + 2], d[8 * qq + 3]);
-                    w.z = pack_bf16x2(d[8 * qq + 4], d[8 * qq + 5]);
-                    w.w = pack_bf16x2(d[8 * qq + 6], d[8 * qq + 7]);
                     const int chunk = ((c & 1) * 4 + qq) ^ (r & 7);
-                    *reinterpret_cast<uint4*>(rowp + chunk * 16) = w;
+                    pw[qq] = *reinterpret_cast<const uint4*>(prow + chunk * 16);
+                }
+                tc_wait_ld();
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const uint32_t pin[4] = {pw[qq].x, pw[qq].y, pw[qq].z, pw[qq].w};
+                    uint32_t dout[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 pf = unpack_bf16x2(pin[e]);
+                        const float d0 = pf.x * (__uint_as_float(rdp[8 * qq + 2 * e]) - dlt) * g.scale;
+                        const float d1 = pf.y * (__uint_as_float(rdp[8 * qq + 2 * e + 1]) - dlt) * g.scale;
+                        dout[e] = pack_bf16x2(d0, d1);  // P is already 0 on masked rows / columns
+                    }
+                    const int chunk = ((c & 1) * 4 + qq) ^ (r & 7);
+                    *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(dout[0], dout[1], dout[2], dout[3]);
                 }
             }
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(ds_ready);
-            // ---- dQ_i partial -> global fp32 accumulator ----
-            mbar_wait(dq_full, par, 62u);
-            tc_fence_after();
-            float* dqp = g.dQ + static_cast<long long>(b) * g.dq_batch_stride + static_cast<long long>(q) * g.dq_row_stride +
-                         static_cast<long long>(h) * HD;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t raw[32];
-                tc_ld32(lane_addr + TM_DQ + static_cast<uint32_t>(c * 32), raw);
-                tc_wait_ld();
-                if (valid) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqp + c * 32 + 4 * k),
-                                     "f"(__uint_as_float(raw[4 * k])), "f"(__uint_as_float(raw[4 * k + 1])),
-                                     "f"(__uint_as_float(raw[4 * k + 2])), "f"(__uint_as_float(raw[4 * k + 3]))
-                                     : "memory");
-                }
-            }
-            tc_fence_before();
         }
+        flush_dq(Tq - 1);
         // ---- dV, dK of this K/V tile (all MMAs retired: dq_full of the last tile covers them) ----
         const int kvrow = kv0 + r;
         if (Tq == 0) {
