@@ -531,11 +531,11 @@ int pick_bn(const GemmProblem& p, long long tiles_m_batches, int groups, int cg)
     for (int bn = 256; bn >= step; bn -= step) {
         const long long tiles = tiles_m_batches * ((p.N + bn - 1) / bn);
         const long long waves = (tiles + groups - 1) / groups;
-        // cycles per k16 step: BN/2 on the tensor pipe, but never below ~128: measured on B200 (in-kernel cycle
-        // accounting, profiles/r01_gemm_debug_timing.txt) every UMMA with a 128-row A slab per SM costs >= ~130 clk
-        // whatever N is (the A operand is re-read from smem per instruction), so narrow tiles only pay off when they
-        // remove whole waves
-        const long long per = std::max<long long>(bn / 2, 128) + 8;
+        // cycles per k16 step: BN/2 on the tensor pipe, or the L2->smem operand feed: per k-iteration every SM pulls a
+        // 16 KB A slab plus BN/cg rows of B, and ~32 KB per 512 clk is what the fabric sustains when all SMs stream
+        // (measured: profiles/r01_gemm_debug_timing.txt, tools/ktest mainloop_* cases), so narrow tiles are fed
+        // no faster than wide ones do math and only pay off when they remove whole waves
+        const long long per = std::max<long long>(bn / 2, 64 + bn / (2 * cg)) + 8;
         const long long cost = waves * per;
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;

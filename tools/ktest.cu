@@ -160,11 +160,11 @@ static int report(const char* name, const Cmp& c, size_t n, int cols, double ms,
 }
 
 template <typename F>
-static double time_ms(F&& f, int iters = 5) {
+static double time_ms(F&& f, int iters = 10) {
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a));
     CK(cudaEventCreate(&b));
-    f();
+    for (int i = 0; i < 3; ++i) f();
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(a));
     for (int i = 0; i < iters; ++i) f();
@@ -364,6 +364,9 @@ static Case cases[] = {
     {"lin_m2", []() { return test_linear("lin_m2 2x1280x320 (embed MLP)", 2, 1280, 320, true, false, true); }},
     {"lin_big", []() { return test_linear("lin_big 8192x1280x1280", 8192, 1280, 1280, true, true, false); }},
     {"lin_ff", []() { return test_linear("lin_ff 8192x10240x1280", 8192, 10240, 1280, true, false, false); }},
+    {"mainloop_n256", []() { return test_linear("mainloop_n256 18944x256x16384 (1 tile/pair, pure k-loop)", 18944, 256, 16384, false, false, false); }},
+    {"mainloop_n128", []() { return test_linear("mainloop_n128 18944x128x16384 (1 tile/pair, pure k-loop)", 18944, 128, 16384, false, false, false); }},
+    {"mainloop_n64", []() { return test_linear("mainloop_n64 18944x64x16384 (1 tile/pair, pure k-loop)", 18944, 64, 16384, false, false, false); }},
     {"dgrad_small", []() { return test_dgrad("dgrad_small 128x64x128", 128, 64, 128); }},
     {"dgrad_ragged", []() { return test_dgrad("dgrad_ragged 300x200x320", 300, 200, 320); }},
     {"dgrad_big", []() { return test_dgrad("dgrad_big 8192x1280x1280", 8192, 1280, 1280); }},
