@@ -23,6 +23,7 @@ constexpr int HD = 64;
 constexpr int KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 constexpr int ATT_THREADS = 192;
+constexpr int ATT_BWD_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps (2 per TMEM lane quadrant)
 
 struct alignas(64) AttnDev {
     CUtensorMap tmQ, tmK, tmV;
@@ -332,7 +333,7 @@ constexpr int BW_DS = BW_P + 2 * TILE_BYTES;
 constexpr int BW_BAR = BW_DS + 2 * TILE_BYTES;
 constexpr int BW_SMEM = BW_BAR + 256 + 1024;
 
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdDev g) {
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdDev g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
@@ -342,8 +343,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     uint64_t* qdo_empty = bars + 3;      // 2
     uint64_t* s_full = bars + 5;
     uint64_t* dp_full = bars + 6;
-    uint64_t* p_ready = bars + 7;        // 128 arrivals
-    uint64_t* ds_ready = bars + 8;       // 128 arrivals
+    uint64_t* p_ready = bars + 7;        // 256 arrivals
+    uint64_t* ds_ready = bars + 8;       // 256 arrivals
     uint64_t* dq_full = bars + 9;
     uint64_t* dv_done = bars + 10;       // commit after the dV MMAs: P smem may be rewritten
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
@@ -367,8 +368,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
         }
         mbar_init(s_full, 1);
         mbar_init(dp_full, 1);
-        mbar_init(p_ready, 128);
-        mbar_init(ds_ready, 128);
+        mbar_init(p_ready, 256);
+        mbar_init(ds_ready, 256);
         mbar_init(dq_full, 1);
         mbar_init(dv_done, 1);
         fence_barrier_init();
@@ -455,60 +456,69 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
             }
         }
     } else {
+        // ===================== softmax warps: 2 per TMEM lane quadrant, each owning 64 of the 128 kv columns =====
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;  // kv columns [64*half, 64*half + 64) == 128B-swizzled smem tile `half`
         const int r = quad * 32 + lane;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
         const int kv_valid = g.Nk - kv0;  // columns >= kv_valid are padding
-        uint8_t* pbuf = smem + BW_P;
-        uint8_t* dsbuf = smem + BW_DS;
+        const uint32_t p_row = smem_u32(smem + BW_P) + static_cast<uint32_t>(half * TILE_BYTES + r * 128);
+        const uint32_t ds_row = smem_u32(smem + BW_DS) + static_cast<uint32_t>(half * TILE_BYTES + r * 128);
         const bool kv_full_tile = kv_valid >= BKV;
-        // dQ partial of tile `it` -> global fp32 accumulator (other K/V tiles add to the same rows)
+        const int col0 = half * 64;
+        // dQ partial of tile `it` (this warp: 32 of the 64 columns) -> global fp32 accumulator
         auto flush_dq = [&](int it) {
             mbar_wait(dq_full, static_cast<uint32_t>(it & 1), 62u);
             tc_fence_after();
             const int q = it * BQ + r;
             float* dqp = g.dQ + static_cast<long long>(b) * g.dq_batch_stride + static_cast<long long>(q) * g.dq_row_stride +
-                         static_cast<long long>(h) * HD;
+                         static_cast<long long>(h) * HD + half * 32;
+            uint32_t raw[32];
+            tc_ld32(lane_addr + TM_DQ + static_cast<uint32_t>(half * 32), raw);
+            tc_wait_ld();
+            if (q < g.Nq) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t raw[32];
-                tc_ld32(lane_addr + TM_DQ + static_cast<uint32_t>(c * 32), raw);
-                tc_wait_ld();
-                if (q < g.Nq) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqp + c * 32 + 4 * k),
-                                     "f"(__uint_as_float(raw[4 * k])), "f"(__uint_as_float(raw[4 * k + 1])),
-                                     "f"(__uint_as_float(raw[4 * k + 2])), "f"(__uint_as_float(raw[4 * k + 3]))
-                                     : "memory");
-                }
+                for (int k = 0; k < 8; ++k)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqp + 4 * k),
+                                 "f"(__uint_as_float(raw[4 * k])), "f"(__uint_as_float(raw[4 * k + 1])),
+                                 "f"(__uint_as_float(raw[4 * k + 2])), "f"(__uint_as_float(raw[4 * k + 3]))
+                                 : "memory");
             }
             tc_fence_before();
         };
+        const long long sbase = (static_cast<long long>(b) * g.H + h) * g.Nq;
+        float lse_next = (r < g.Nq) ? g.lse[sbase + r] : 0.f;
+        float dlt_next = (r < g.Nq) ? g.delta[sbase + r] : 0.f;
         for (int i = 0; i < Tq; ++i) {
             const uint32_t par = static_cast<uint32_t>(i & 1);
             const int q = i * BQ + r;
             const bool valid = q < g.Nq;
-            const long long sidx = (static_cast<long long>(b) * g.H + h) * g.Nq + q;
-            const float lse2 = valid ? g.lse[sidx] * 1.4426950408889634f : 0.f;
-            const float dlt = valid ? g.delta[sidx] : 0.f;
+            const float lse2 = lse_next * 1.4426950408889634f;
+            const float dlt = dlt_next;
+            {  // prefetch the next tile's row statistics: their L2 latency hides behind this tile
+                const int qn = q + BQ;
+                const bool vn = (i + 1 < Tq) && (qn < g.Nq);
+                lse_next = vn ? g.lse[sbase + qn] : 0.f;
+                dlt_next = vn ? g.delta[sbase + qn] : 0.f;
+            }
             const bool nomask = kv_full_tile && ((i + 1) * BQ <= g.Nq);  // warp-uniform: whole tile in range
             // ---- P = exp2(scale*log2e*S - lse*log2e) ----
             mbar_wait(s_full, par, 60u);
             tc_fence_after();
+            uint32_t ra[32], rb[32];
+            tc_ld32(lane_addr + TM_S + static_cast<uint32_t>(col0), ra);
+            tc_ld32(lane_addr + TM_S + static_cast<uint32_t>(col0 + 32), rb);
             if (i > 0) mbar_wait(dv_done, static_cast<uint32_t>((i - 1) & 1), 63u);  // dV_{i-1} no longer reads P
+            tc_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t raw[32];
-                tc_ld32(lane_addr + TM_S + static_cast<uint32_t>(c * 32), raw);
-                tc_wait_ld();
+            for (int cc = 0; cc < 2; ++cc) {
                 float p[32];
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
-                    const float e = exp2f(fmaf(__uint_as_float(raw[k]), g.scale_log2, -lse2));
-                    p[k] = (nomask || (valid && (c * 32 + k < kv_valid))) ? e : 0.f;
+                    const float sraw = __uint_as_float(cc ? rb[k] : ra[k]);
+                    const float e = exp2f(fmaf(sraw, g.scale_log2, -lse2));
+                    p[k] = (nomask || (valid && (col0 + cc * 32 + k < kv_valid))) ? e : 0.f;
                 }
-                uint8_t* rowp = pbuf + (c >> 1) * TILE_BYTES + r * 128;
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
                     uint4 w;
@@ -516,8 +526,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
                     w.y = pack_bf16x2(p[8 * qq + 2], p[8 * qq + 3]);
                     w.z = pack_bf16x2(p[8 * qq + 4], p[8 * qq + 5]);
                     w.w = pack_bf16x2(p[8 * qq + 6], p[8 * qq + 7]);
-                    const int chunk = ((c & 1) * 4 + qq) ^ (r & 7);
-                    *reinterpret_cast<uint4*>(rowp + chunk * 16) = w;
+                    st_shared_v4(p_row + static_cast<uint32_t>(((cc * 4 + qq) ^ (r & 7)) * 16), w);
                 }
             }
             fence_proxy_async_smem();
@@ -528,65 +537,48 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
             // ---- dS = P * (dP - delta) * scale ; P (bf16) is read back from this thread's own smem row ----
             mbar_wait(dp_full, par, 61u);
             tc_fence_after();
+            tc_ld32(lane_addr + TM_DP + static_cast<uint32_t>(col0), ra);
+            tc_ld32(lane_addr + TM_DP + static_cast<uint32_t>(col0 + 32), rb);
+            uint4 pw[8];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t rdp[32];
-                tc_ld32(lane_addr + TM_DP + static_cast<uint32_t>(c * 32), rdp);
-                const uint8_t* prow = pbuf + (c >> 1) * TILE_BYTES + r * 128;
-                uint8_t* rowp = dsbuf + (c >> 1) * TILE_BYTES + r * 128;
-                uint4 pw[4];
+            for (int j = 0; j < 8; ++j) pw[j] = ld_shared_v4(p_row + static_cast<uint32_t>((j ^ (r & 7)) * 16));
+            tc_wait_ld();
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const int chunk = ((c & 1) * 4 + qq) ^ (r & 7);
-                    pw[qq] = *reinterpret_cast<const uint4*>(prow + chunk * 16);
+            for (int j = 0; j < 8; ++j) {  // 16-byte chunk j = columns 8j .. 8j+7 of this warp's 64
+                const uint32_t pin[4] = {pw[j].x, pw[j].y, pw[j].z, pw[j].w};
+                uint32_t dout[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = 8 * j + 2 * e;  // 0..63
+                    const float dp0 = __uint_as_float(col < 32 ? ra[col & 31] : rb[col & 31]);
+                    const float dp1 = __uint_as_float(col + 1 < 32 ? ra[(col + 1) & 31] : rb[(col + 1) & 31]);
+                    const float2 pf = unpack_bf16x2(pin[e]);
+                    dout[e] = pack_bf16x2(pf.x * (dp0 - dlt) * g.scale, pf.y * (dp1 - dlt) * g.scale);  // P is 0 where masked
                 }
-                tc_wait_ld();
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const uint32_t pin[4] = {pw[qq].x, pw[qq].y, pw[qq].z, pw[qq].w};
-                    uint32_t dout[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 pf = unpack_bf16x2(pin[e]);
-                        const float d0 = pf.x * (__uint_as_float(rdp[8 * qq + 2 * e]) - dlt) * g.scale;
-                        const float d1 = pf.y * (__uint_as_float(rdp[8 * qq + 2 * e + 1]) - dlt) * g.scale;
-                        dout[e] = pack_bf16x2(d0, d1);  // P is already 0 on masked rows / columns
-                    }
-                    const int chunk = ((c & 1) * 4 + qq) ^ (r & 7);
-                    *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(dout[0], dout[1], dout[2], dout[3]);
-                }
+                st_shared_v4(ds_row + static_cast<uint32_t>((j ^ (r & 7)) * 16), make_uint4(dout[0], dout[1], dout[2], dout[3]));
             }
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(ds_ready);
         }
         flush_dq(Tq - 1);
-        // ---- dV, dK of this K/V tile (all MMAs retired: dq_full of the last tile covers them) ----
+        // ---- dV, dK of this K/V tile (all MMAs retired: dq_full of the last tile covers them); 32 columns per warp ----
         const int kvrow = kv0 + r;
-        if (Tq == 0) {
-            // nothing accumulated
-        }
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
-            float o[HD];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t raw[32];
-                tc_ld32(lane_addr + (which ? TM_DK : TM_DV) + static_cast<uint32_t>(c * 32), raw);
-                tc_wait_ld();
-#pragma unroll
-                for (int k = 0; k < 32; ++k) o[c * 32 + k] = __uint_as_float(raw[k]);
-            }
+            uint32_t raw[32];
+            tc_ld32(lane_addr + (which ? TM_DK : TM_DV) + static_cast<uint32_t>(half * 32), raw);
+            tc_wait_ld();
             if (kvrow < g.Nk) {
                 bf16* op = (which ? g.dK : g.dV) + static_cast<long long>(b) * g.dkv_batch_stride +
-                           static_cast<long long>(kvrow) * g.dkv_row_stride + static_cast<long long>(h) * HD;
+                           static_cast<long long>(kvrow) * g.dkv_row_stride + static_cast<long long>(h) * HD + half * 32;
 #pragma unroll
-                for (int c = 0; c < HD / 8; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     uint4 w;
-                    w.x = pack_bf16x2(o[8 * c + 0], o[8 * c + 1]);
-                    w.y = pack_bf16x2(o[8 * c + 2], o[8 * c + 3]);
-                    w.z = pack_bf16x2(o[8 * c + 4], o[8 * c + 5]);
-                    w.w = pack_bf16x2(o[8 * c + 6], o[8 * c + 7]);
+                    w.x = pack_bf16x2(__uint_as_float(raw[8 * c + 0]), __uint_as_float(raw[8 * c + 1]));
+                    w.y = pack_bf16x2(__uint_as_float(raw[8 * c + 2]), __uint_as_float(raw[8 * c + 3]));
+                    w.z = pack_bf16x2(__uint_as_float(raw[8 * c + 4]), __uint_as_float(raw[8 * c + 5]));
+                    w.w = pack_bf16x2(__uint_as_float(raw[8 * c + 6]), __uint_as_float(raw[8 * c + 7]));
                     reinterpret_cast<uint4*>(op)[c] = w;
                 }
             }
@@ -698,7 +690,7 @@ int nk_attention_bwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
         attr_set = true;
     }
     dim3 grid((Nk + BKV - 1) / BKV, H, B);
-    attn_bwd_kernel<<<grid, ATT_THREADS, BW_SMEM, static_cast<cudaStream_t>(stream)>>>(g);
+    attn_bwd_kernel<<<grid, ATT_BWD_THREADS, BW_SMEM, static_cast<cudaStream_t>(stream)>>>(g);
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }
