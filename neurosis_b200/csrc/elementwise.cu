@@ -284,42 +284,52 @@ __global__ void col2im_kernel(const bf16* __restrict__ dcol, bf16* __restrict__ 
     }
 }
 
-// ---- column sums: out[g, c] (+)= sum_{r < rows_per_group} x[g*rows_per_group + r, c] -------------
+// ---- column sums: out[g, c] += sum_{r < rows_per_group} x[g*rows_per_group + r, c] ----------------------
+// block = 32 column octets (256 columns, 16-byte loads) x 8 row lanes; 4 rows in flight per thread; partial sums are
+// combined in shared memory and added to `out` with one atomic per column and block (out must be initialised).
 __global__ void colsum_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, int rows_per_group,
-                              int C, int row_chunks, int accumulate_atomic) {
-    // grid (ceil(C/64), row_chunks, groups); block (64 columns-pairs... ) 256 threads = 32 col-pairs x 8 row lanes
+                              int C, int row_chunks) {
     const int g = blockIdx.z;
-    const int cpair = blockIdx.x * 32 + (threadIdx.x & 31);  // handles columns 2*cpair, 2*cpair+1
-    const int rl = threadIdx.x >> 5;                         // 0..7
+    const int cv = blockIdx.x * 32 + (threadIdx.x & 31);  // column octet: columns 8*cv .. 8*cv+7
+    const int rl = threadIdx.x >> 5;                      // 0..7
     const int rows_per_chunk = (rows_per_group + row_chunks - 1) / row_chunks;
     const int r0 = blockIdx.y * rows_per_chunk;
     const int r1 = min(rows_per_group, r0 + rows_per_chunk);
-    float a0 = 0.f, a1 = 0.f;
-    if (2 * cpair < C) {
-        const bf16* base = x + (static_cast<long long>(g) * rows_per_group) * ldx + 2 * cpair;
-        for (int r = r0 + rl; r < r1; r += 8) {
-            const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + r * ldx));
-            a0 += f.x;
-            a1 += f.y;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const bool col_ok = 8 * cv < C;
+    if (col_ok) {
+        const bf16* base = x + (static_cast<long long>(g) * rows_per_group) * ldx + 8 * cv;
+        int r = r0 + rl;
+        for (; r + 24 < r1; r += 32) {  // 4 independent 16-byte loads in flight
+            float f0[8], f1[8], f2[8], f3[8];
+            ld8(base + static_cast<long long>(r) * ldx, f0);
+            ld8(base + static_cast<long long>(r + 8) * ldx, f1);
+            ld8(base + static_cast<long long>(r + 16) * ldx, f2);
+            ld8(base + static_cast<long long>(r + 24) * ldx, f3);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+        }
+        for (; r < r1; r += 8) {
+            float f0[8];
+            ld8(base + static_cast<long long>(r) * ldx, f0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f0[j];
         }
     }
-    __shared__ float s0[8][33], s1[8][33];
-    s0[rl][threadIdx.x & 31] = a0;
-    s1[rl][threadIdx.x & 31] = a1;
+    __shared__ float sm[8][32][9];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[rl][threadIdx.x & 31][j] = acc[j];
     __syncthreads();
-    if (rl == 0 && 2 * cpair < C) {
-        for (int k = 1; k < 8; ++k) {
-            a0 += s0[k][threadIdx.x & 31];
-            a1 += s1[k][threadIdx.x & 31];
-        }
-        float* o = out + static_cast<long long>(g) * C + 2 * cpair;
-        if (accumulate_atomic) {
-            atomicAdd(o, a0);
-            atomicAdd(o + 1, a1);
-        } else {
-            o[0] = a0;
-            o[1] = a1;
-        }
+    // 256 threads <-> 256 columns of this block
+    const int c_local = threadIdx.x;  // 0..255
+    const int c = blockIdx.x * 256 + c_local;
+    if (c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][c_local >> 3][c_local & 7];
+        atomicAdd(out + static_cast<long long>(g) * C + c, t);
     }
 }
 
@@ -376,37 +386,77 @@ __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, float* _
 
 // ---- row softmax for the materialised attention path -------------------------------------------------
 // S fp32 [rows, ld] -> P bf16 [rows, ldp] = softmax(scale * S[:, :N]) ; lse[row] = log-sum-exp (natural log)
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* red) {
+    v = is_max ? warp_max(v) : warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : (is_max ? -INFINITY : 0.f);
+        t = is_max ? warp_max(t) : warp_sum(t);
+        if (threadIdx.x == 0) red[32] = t;
+    }
+    __syncthreads();
+    const float out = red[32];
+    __syncthreads();
+    return out;
+}
+
+// one block per row; the row (<= 256 threads x VPT float4) is read from global ONCE and kept in registers
+template <int VPT>
+__global__ void softmax_rows_reg_kernel(const float* __restrict__ S, long long lds, bf16* __restrict__ P, long long ldp,
+                                        float* __restrict__ lse, int N, float scale) {
+    __shared__ float red[33];
+    const long long row = blockIdx.x;
+    const float4* s4 = reinterpret_cast<const float4*>(S + row * lds);
+    const int n4 = N >> 2;
+    float4 v[VPT];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int idx = threadIdx.x + i * blockDim.x;
+        if (idx < n4) {
+            v[i] = __ldg(s4 + idx);
+            mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+        }
+    }
+    mx = block_reduce(mx, true, red);
+    const float sl2 = scale * 1.4426950408889634f;
+    const float mb = mx * sl2;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int idx = threadIdx.x + i * blockDim.x;
+        if (idx < n4) {
+            v[i].x = exp2f(fmaf(v[i].x, sl2, -mb));
+            v[i].y = exp2f(fmaf(v[i].y, sl2, -mb));
+            v[i].z = exp2f(fmaf(v[i].z, sl2, -mb));
+            v[i].w = exp2f(fmaf(v[i].w, sl2, -mb));
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    sum = block_reduce(sum, false, red);
+    const float inv = 1.f / sum;
+    uint2* p2 = reinterpret_cast<uint2*>(P + row * ldp);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int idx = threadIdx.x + i * blockDim.x;
+        if (idx < n4) p2[idx] = make_uint2(pack_bf16x2(v[i].x * inv, v[i].y * inv), pack_bf16x2(v[i].z * inv, v[i].w * inv));
+    }
+    if (threadIdx.x == 0 && lse) lse[row] = mx * scale + logf(sum);
+}
+
 __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, bf16* __restrict__ P, long long ldp,
                                     float* __restrict__ lse, long long rows, int N, float scale) {
+    __shared__ float red[33];
     const long long row = blockIdx.x;
     if (row >= rows) return;
     const float* s = S + row * lds;
     float mx = -INFINITY;
     for (int i = threadIdx.x; i < N; i += blockDim.x) mx = fmaxf(mx, s[i]);
-    __shared__ float red[32];
-    mx = warp_max(mx);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
-        v = warp_max(v);
-        if (threadIdx.x == 0) red[0] = v;
-    }
-    __syncthreads();
-    mx = red[0];
-    __syncthreads();
+    mx = block_reduce(mx, true, red);
     float sum = 0.f;
     for (int i = threadIdx.x; i < N; i += blockDim.x) sum += __expf((s[i] - mx) * scale);
-    sum = warp_sum(sum);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-        v = warp_sum(v);
-        if (threadIdx.x == 0) red[0] = v;
-    }
-    __syncthreads();
-    sum = red[0];
+    sum = block_reduce(sum, false, red);
     const float inv = 1.f / sum;
     for (int i = threadIdx.x; i < N; i += blockDim.x)
         P[row * ldp + i] = __float2bfloat16(__expf((s[i] - mx) * scale) * inv);
@@ -556,12 +606,15 @@ int nk_col2im(const void* dcol, void* dx, int nimg, int H, int W, int C, int ks,
 }
 int nk_colsum(const void* x, int64_t ldx, float* out, int groups, int rows_per_group, int C, int accumulate,
               nk_stream_t stream) {
-    NK_REQUIRE(C % 2 == 0 && ldx % 2 == 0, NK_ERR_SHAPE, "colsum: C=%d", C);
-    int row_chunks = 1;
-    const int col_blocks = (C / 2 + 31) / 32;
-    if (accumulate) row_chunks = std::max(1, std::min(rows_per_group / 64, (148 * 4) / std::max(1, col_blocks * groups)));
+    NK_REQUIRE(C % 8 == 0 && ldx % 8 == 0, NK_ERR_SHAPE, "colsum: C=%d ldx=%lld must be multiples of 8", C,
+               static_cast<long long>(ldx));
+    if (!accumulate)
+        NK_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(groups) * C * sizeof(float), ST(stream)));
+    const int col_blocks = (C + 255) / 256;
+    // enough blocks to fill the machine, at least 64 rows each
+    int row_chunks = std::max(1, std::min(rows_per_group / 64, (148 * 8) / std::max(1, col_blocks * groups)));
     colsum_kernel<<<dim3(col_blocks, row_chunks, groups), 256, 0, ST(stream)>>>(CBF(x), ldx, out, rows_per_group, C,
-                                                                               row_chunks, accumulate);
+                                                                               row_chunks);
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }
@@ -589,8 +642,15 @@ int nk_conv_unpack_wgrad(const float* dw_packed, float* dw, int Co, int Ci, int 
 int nk_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp, float* lse, int64_t rows, int N, float scale,
                     nk_stream_t stream) {
     NK_REQUIRE(rows < (1LL << 31), NK_ERR_SHAPE, "softmax rows");
-    const int threads = N >= 1024 ? 256 : 128;
-    softmax_rows_kernel<<<static_cast<unsigned>(rows), threads, 0, ST(stream)>>>(S, lds, BF(P), ldp, lse, rows, N, scale);
+    const bool vec_ok = (N % 4 == 0) && (lds % 4 == 0) && (ldp % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(S) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(P) & 7u) == 0);
+    const unsigned grid = static_cast<unsigned>(rows);
+    if (vec_ok && N <= 256 * 4 * 4)
+        softmax_rows_reg_kernel<4><<<grid, 256, 0, ST(stream)>>>(S, lds, BF(P), ldp, lse, N, scale);
+    else if (vec_ok && N <= 256 * 4 * 16)
+        softmax_rows_reg_kernel<16><<<grid, 256, 0, ST(stream)>>>(S, lds, BF(P), ldp, lse, N, scale);
+    else
+        softmax_rows_kernel<<<grid, N >= 1024 ? 256 : 128, 0, ST(stream)>>>(S, lds, BF(P), ldp, lse, rows, N, scale);
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }

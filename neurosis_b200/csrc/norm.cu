@@ -370,42 +370,58 @@ __global__ void ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, bf16* _
 }
 
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)); dgamma += sum dy*xhat; dbeta += sum dy
+// One warp per row.  x and dy stay packed (bf16) in registers; the per-column parameter gradients are accumulated
+// with conflict-free shared-memory atomics (layout [j][v]: consecutive lanes -> consecutive banks) instead of
+// per-thread register accumulators, which keeps the kernel at ~80 registers so enough rows are in flight to
+// cover HBM latency.
 template <int MAXV>
-__global__ void ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ x, long long ldx,
-                              bf16* __restrict__ dx, long long lddx, const float* __restrict__ gamma,
-                              const float* __restrict__ mean, const float* __restrict__ rstd,
-                              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C) {
-    extern __shared__ float sm[];  // dgamma[C], dbeta[C] block accumulators
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ x,
+                                                     long long ldx, bf16* __restrict__ dx, long long lddx,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, int rows, int C) {
+    extern __shared__ float sm[];  // dgamma[8][V], dbeta[8][V]
+    const int V = C / 8;
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
     __syncthreads();
+    float* s_dg = sm;
+    float* s_db = sm + C;
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int V = C / 8;
-    float ag[MAXV][8], ab[MAXV][8];
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
     for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); row < rows;
          row += static_cast<long long>(gridDim.x) * warps_per_block) {
+        uint4 px[MAXV], pd[MAXV];
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + i * 32;
+            if (v < V) {
+                px[i] = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + v * 8));
+                pd[i] = __ldg(reinterpret_cast<const uint4*>(dy + row * lddy + v * 8));
+            }
+        }
         const float m = mean[row], r = rstd[row];
-        float xh[MAXV][8], gd[MAXV][8];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             const int v = lane + i * 32;
             if (v < V) {
-                float d[8];
-                load8(x + row * ldx + v * 8, xh[i]);
-                load8(dy + row * lddy + v * 8, d);
+                const uint32_t wx[4] = {px[i].x, px[i].y, px[i].z, px[i].w};
+                const uint32_t wd[4] = {pd[i].x, pd[i].y, pd[i].z, pd[i].w};
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    xh[i][j] = (xh[i][j] - m) * r;
-                    ag[i][j] += d[j] * xh[i][j];
-                    ab[i][j] += d[j];
-                    gd[i][j] = d[j] * __ldg(gamma + v * 8 + j);
-                    s1 += gd[i][j];
-                    s2 += gd[i][j] * xh[i][j];
+                for (int e = 0; e < 4; ++e) {
+                    const float2 fx = unpack_bf16x2(wx[e]);
+                    const float2 fd = unpack_bf16x2(wd[e]);
+                    const float xh0 = (fx.x - m) * r, xh1 = (fx.y - m) * r;
+                    const float gd0 = fd.x * g[2 * e], gd1 = fd.y * g[2 * e + 1];
+                    s1 += gd0 + gd1;
+                    s2 += gd0 * xh0 + gd1 * xh1;
+                    atomicAdd(&s_dg[(2 * e) * V + v], fd.x * xh0);
+                    atomicAdd(&s_dg[(2 * e + 1) * V + v], fd.y * xh1);
+                    atomicAdd(&s_db[(2 * e) * V + v], fd.x);
+                    atomicAdd(&s_db[(2 * e + 1) * V + v], fd.y);
                 }
             }
         }
@@ -415,28 +431,28 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const
         for (int i = 0; i < MAXV; ++i) {
             const int v = lane + i * 32;
             if (v < V) {
-                float o[8];
+                const uint32_t wx[4] = {px[i].x, px[i].y, px[i].z, px[i].w};
+                const uint32_t wd[4] = {pd[i].x, pd[i].y, pd[i].z, pd[i].w};
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                uint32_t o[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = r * (gd[i][j] - s1 - xh[i][j] * s2);
-                store8(dx + row * lddx + v * 8, o);
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        const int v = lane + i * 32;
-        if (v < V) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                atomicAdd(&sm[v * 8 + j], ag[i][j]);
-                atomicAdd(&sm[C + v * 8 + j], ab[i][j]);
+                for (int e = 0; e < 4; ++e) {
+                    const float2 fx = unpack_bf16x2(wx[e]);
+                    const float2 fd = unpack_bf16x2(wd[e]);
+                    const float xh0 = (fx.x - m) * r, xh1 = (fx.y - m) * r;
+                    o[e] = pack_bf16x2(r * (fd.x * g[2 * e] - s1 - xh0 * s2), r * (fd.y * g[2 * e + 1] - s1 - xh1 * s2));
+                }
+                *reinterpret_cast<uint4*>(dx + row * lddx + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
             }
         }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        atomicAdd(dgamma + c, sm[c]);
-        atomicAdd(dbeta + c, sm[C + c]);
+        const int v = c >> 3, j = c & 7;
+        atomicAdd(dgamma + c, s_dg[j * V + v]);
+        atomicAdd(dbeta + c, s_db[j * V + v]);
     }
 }
 
@@ -527,7 +543,7 @@ int nk_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, c
     NK_REQUIRE(C % 8 == 0 && C <= 1280, NK_ERR_SHAPE, "layernorm bwd: C=%d", C);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int wpb = 8;
-    const int grid = static_cast<int>(std::min<long long>((rows + wpb - 1) / wpb, 148LL * 2));
+    const int grid = static_cast<int>(std::min<long long>((rows + wpb - 1) / wpb, 148LL * 4));
     const int V = C / 8;
     const size_t smem = 2 * C * sizeof(float);
     if (V <= 64)

@@ -244,8 +244,8 @@ def colsum(x: Tensor, groups: int = 1) -> Tensor:
     if x2.stride(-1) != 1:
         x2 = x2.contiguous()
     rows = x2.shape[0] // groups
-    out = torch.zeros((groups, C), dtype=F32, device=x.device)
-    check(lib.nk_colsum(x2.data_ptr(), x2.stride(0), out.data_ptr(), groups, rows, C, 1, _stream()), "colsum")
+    out = torch.empty((groups, C), dtype=F32, device=x.device)
+    check(lib.nk_colsum(x2.data_ptr(), x2.stride(0), out.data_ptr(), groups, rows, C, 0, _stream()), "colsum")
     _count()
     return out
 
@@ -732,11 +732,12 @@ class Conv2dFn(torch.autograd.Function):
             else:
                 dw = conv_unpack_wgrad(dwp, co, ci, ks)
         if (has_bias and ctx.needs_input_grad[2]) or (has_bimg and ctx.needs_input_grad[3]):
-            n = dy.shape[0]
-            s = colsum(dy, groups=n)[:, :co]
             if has_bimg and ctx.needs_input_grad[3]:
+                s = colsum(dy, groups=dy.shape[0])[:, :co]  # per-image sums (timestep-embedding gradient)
                 dbi = s.contiguous()
-            if has_bias and ctx.needs_input_grad[2]:
+                if has_bias and ctx.needs_input_grad[2]:
+                    db = s.sum(0)  # O(batch x C) glue
+            elif has_bias and ctx.needs_input_grad[2]:
                 db = colsum(dy)[0, :co].contiguous()
         if has_res and ctx.needs_input_grad[4]:
             dres = dy
