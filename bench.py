@@ -194,6 +194,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--breakdown", default="", help="write a per-call-site breakdown of tensor-core time to this file")
+    ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -309,6 +310,13 @@ def main() -> None:
                 "share_of_step": t_ms / (ms_dev / args.steps) if ms_dev > 0 else None,
                 "alg_tflop_per_step": fl / 1e12}
 
+    if args.torch_profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            step(resident, False)
+            torch.cuda.synchronize()
+        with open(args.torch_profile, "w") as fh:
+            fh.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
     if rank == 0:
         ips = world * B * args.steps / (ms_dev * 1e-3)
         ips_e2e = world * B * args.steps / (ms_e2e * 1e-3)

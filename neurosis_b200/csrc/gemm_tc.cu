@@ -536,7 +536,8 @@ int pick_bn(const GemmProblem& p, long long tiles_m_batches, int groups, int cg)
         // (measured: profiles/r01_gemm_debug_timing.txt, tools/ktest mainloop_* cases), so narrow tiles are fed
         // no faster than wide ones do math and only pay off when they remove whole waves
         const long long per = std::max<long long>(bn / 2, 64 + bn / (2 * cg)) + 8;
-        const long long cost = waves * per;
+        // with split-K (atomic accumulation) the K range is spread over idle CTAs, so total work counts, not waves
+        const long long cost = (p.out == OUT_F32_ATOMIC) ? (tiles * per * 16) / groups : waves * per * 16;
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             best = bn;
