@@ -60,7 +60,7 @@ typedef struct nk_gemm_desc {
     int32_t M, N, K;
     int32_t nb2, nb1;
     int32_t ksize, pad; /* conv forward/dgrad: A.conv = 1 */
-    int32_t wgrad;      /* conv weight gradient: A.conv = B.conv = 1, b2 = filter tap */
+    int32_t wgrad;      /* conv weight gradient: A.conv = B.conv = 1, N = taps*Cin (column = tap*Cin + ci) */
     void* C;
     int64_t ldc, c_b2_stride, c_b1_stride;
     int32_t out, epi;

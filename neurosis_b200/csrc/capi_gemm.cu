@@ -196,15 +196,13 @@ int nk_conv2d_wgrad(const void* dy, int64_t dy_pix_stride, const void* x, int64_
     p.A = image(dy, 1, nimg, H, W, Cout, dy_pix_stride);
     p.B = image(x, 1, nimg, H, W, Cin, x_pix_stride);
     p.M = Cout;
-    p.N = Cin;
+    p.N = taps * Cin;  // column index = tap*Cin + ci: the packed gradient is one [Cout, taps*Cin] matrix
     p.K = nimg * H * W;
-    p.nb2 = taps;
     p.ksize = ksize;
     p.pad = ksize / 2;
     p.wgrad = 1;
     p.C = dw_packed;
     p.ldc = static_cast<long long>(taps) * Cin;
-    p.c_b2_stride = Cin;  // tap selects a column block of the packed gradient
     p.out = OUT_F32_ATOMIC;
     p.epi = EPI_LINEAR;
     return launch_gemm(p, static_cast<cudaStream_t>(stream));

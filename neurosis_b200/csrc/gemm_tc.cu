@@ -9,7 +9,7 @@
 //   * 3x3 / 1x1 convolution forward and data-gradient as implicit GEMM: the A tile of a
 //     k-iteration is one TMA box {64 channels, bw, bh} of the NHWC activation, shifted by the
 //     filter tap; out-of-image pixels are zero-filled by the TMA unit (that is the padding),
-//   * convolution weight-gradient (reduction over pixels, both operands MN-major, tap = batch),
+//   * convolution weight-gradient (reduction over pixels, both operands MN-major, taps folded into N),
 //   * the batched attention GEMMs with softmax-aware epilogues.
 //
 // Replaces in the reference: nn.Linear / nn.Conv2d dispatch sites K1,K3,K4,K5 of SURVEY.md §2.2
@@ -214,18 +214,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         tma_load(&g.tmA, &full_bar[stage], sa, cb * 64, tw * g.bw + dx,
                                     th * g.bh + dy, img);
                         tma_load(&g.tmB, &full_bar[stage], sb, gi * BK, n0, 0, 0);
-                    } else {  // MODE_CONV_WGRAD: k-iteration = one 64-pixel tile, tap = b2
+                    } else {  // MODE_CONV_WGRAD: k-iteration = one 64-pixel tile; N index = tap*Cin + ci
                         const int ptw = gi % g.tiles_w;
                         const int pth = (gi / g.tiles_w) % g.tiles_h;
                         const int pimg = gi / (g.tiles_w * g.tiles_h);
-                        const int dy = tc.b2 / g.ksize - g.pad;
-                        const int dx = tc.b2 % g.ksize - g.pad;
                         tma_load(&g.tmA, &full_bar[stage], sa, m0, ptw * g.bw, pth * g.bh, pimg);
                         tma_load(&g.tmA, &full_bar[stage], sa + ATOM_BYTES, m0 + 64, ptw * g.bw,
                                     pth * g.bh, pimg);
-                        for (int j = 0; j < BNc / 64; ++j)
-                            tma_load(&g.tmB, &full_bar[stage], sb + j * ATOM_BYTES, n0 + 64 * j,
+                        // every 64-channel atom of the B tile carries its own filter tap (its own pixel shift), so a
+                        // 256-wide N tile may straddle taps; atoms past N are fetched out of range (zero-filled)
+                        for (int j = 0; j < BNc / 64; ++j) {
+                            const int atom = (n0 >> 6) + j;
+                            const int tap = atom / g.cin_blocks;
+                            const int c0 = (atom - tap * g.cin_blocks) << 6;
+                            const bool in_range = tap < g.ksize * g.ksize;
+                            const int dy = tap / g.ksize - g.pad;
+                            const int dx = tap % g.ksize - g.pad;
+                            tma_load(&g.tmB, &full_bar[stage], sb + j * ATOM_BYTES, in_range ? c0 : (g.cin_blocks << 6),
                                         ptw * g.bw + dx, pth * g.bh + dy, pimg);
+                        }
                     }
                     if (++stage == stages) {
                         stage = 0;
@@ -622,7 +629,9 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
         a_box2 = g.bh;
         b_box2 = g.bh;
         g.a_bytes = 2 * ATOM_BYTES;
-        NK_REQUIRE(g.nb2 == g.ksize * g.ksize, NK_ERR_SHAPE, "wgrad: nb2 must equal taps");
+        g.cin_blocks = static_cast<int>(p.B.inner / 64);
+        NK_REQUIRE(p.B.inner % 64 == 0, NK_ERR_SHAPE, "wgrad: C_in %lld not a multiple of 64", p.B.inner);
+        NK_REQUIRE(p.N == g.ksize * g.ksize * static_cast<int>(p.B.inner), NK_ERR_SHAPE, "wgrad: N must be taps*C_in");
     } else {
         g.tiles_m128 = (p.M + BM - 1) / BM;
         g.k_iters_total = (p.K + BK - 1) / BK;

@@ -34,7 +34,7 @@ struct GemmProblem {
     int nb2, nb1;         // batch extents of the launch (C is indexed by them as well)
     // conv forward / dgrad (A.conv=1, A K-major): K = taps*Cin, k-iteration -> (tap, 64-channel block)
     int ksize, pad;       // 3,1 or 1,0
-    // conv wgrad (A.conv = B.conv = 1, both MN-major): batch index b2 = tap, K = all pixels
+    // conv wgrad (A.conv = B.conv = 1, both MN-major): N = taps*Cin (every 64-channel atom has its own tap shift), K = all pixels
     int wgrad;
     // output
     void* C;
