@@ -617,6 +617,7 @@ int nk_attention_fwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
                      int64_t k_batch_stride, const void* v, int64_t v_row_stride, int64_t v_batch_stride, void* o,
                      int64_t o_row_stride, int64_t o_batch_stride, float* lse, int B, int H, int Nq, int Nk,
                      int head_dim, float scale, nk_stream_t stream) {
+    ::nk::enter(stream);
     NK_REQUIRE(head_dim == HD, NK_ERR_UNSUPPORTED, "fused attention supports head_dim 64 (got %d)", head_dim);
     NK_REQUIRE(B > 0 && H > 0 && Nq > 0 && Nk > 0, NK_ERR_SHAPE, "attention: empty problem");
     NK_REQUIRE(o_row_stride % 8 == 0 && o_batch_stride % 8 == 0, NK_ERR_SHAPE, "attention: output strides");
@@ -657,6 +658,7 @@ int nk_attention_bwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
                      const void* dO, int64_t do_row_stride, int64_t do_batch_stride, const float* lse,
                      const float* delta, float* dq_acc, void* dk, void* dv, int B, int H, int Nq, int Nk, int head_dim,
                      float scale, nk_stream_t stream) {
+    ::nk::enter(stream);
     NK_REQUIRE(head_dim == HD, NK_ERR_UNSUPPORTED, "fused attention backward supports head_dim 64 (got %d)", head_dim);
     NK_REQUIRE(B > 0 && H > 0 && Nq > 0 && Nk > 0, NK_ERR_SHAPE, "attention bwd: empty problem");
     AttnBwdDev g;

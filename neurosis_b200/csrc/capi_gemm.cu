@@ -95,7 +95,7 @@ int nk_gemm_ex(const nk_gemm_desc* d, nk_stream_t stream) {
     p.force_bn = d->force_bn;
     p.force_splits = d->force_splits;
     p.force_cta_group = d->force_cta_group;
-    return launch_gemm(p, static_cast<cudaStream_t>(stream));
+    return launch_gemm(p, ::nk::enter(stream));
 }
 
 int nk_linear_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
@@ -114,7 +114,7 @@ int nk_linear_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const 
     p.bias = bias;
     p.residual = static_cast<const bf16*>(residual);
     p.ldr = ldr;
-    return launch_gemm(p, static_cast<cudaStream_t>(stream));
+    return launch_gemm(p, ::nk::enter(stream));
 }
 
 int nk_linear_dgrad(const void* dy, int64_t lddy, const void* w, int64_t ldw, const void* residual,
@@ -132,7 +132,7 @@ int nk_linear_dgrad(const void* dy, int64_t lddy, const void* w, int64_t ldw, co
     p.epi = EPI_LINEAR;
     p.residual = static_cast<const bf16*>(residual);
     p.ldr = ldr;
-    return launch_gemm(p, static_cast<cudaStream_t>(stream));
+    return launch_gemm(p, ::nk::enter(stream));
 }
 
 int nk_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw,
@@ -154,11 +154,11 @@ int nk_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, fl
         const long long tiles = static_cast<long long>((N + 255) / 256) * ((K + 255) / 256);
         if (tiles * 2 <= nk::device_sm_count() / 2 && M >= 2048) {
             NK_CUDA(cudaMemset2DAsync(dw, static_cast<size_t>(lddw) * 4, 0, static_cast<size_t>(K) * 4, N,
-                                      static_cast<cudaStream_t>(stream)));
+                                      ::nk::enter(stream)));
             p.out = OUT_F32_ATOMIC;
         }
     }
-    return launch_gemm(p, static_cast<cudaStream_t>(stream));
+    return launch_gemm(p, ::nk::enter(stream));
 }
 
 int nk_conv2d_fwd(const void* x, int64_t x_pix_stride, const void* wp, const float* bias,
@@ -184,7 +184,7 @@ int nk_conv2d_fwd(const void* x, int64_t x_pix_stride, const void* wp, const flo
     p.rows_per_img = H * W;
     p.residual = static_cast<const bf16*>(residual);
     p.ldr = r_pix_stride;
-    return launch_gemm(p, static_cast<cudaStream_t>(stream));
+    return launch_gemm(p, ::nk::enter(stream));
 }
 
 int nk_conv2d_wgrad(const void* dy, int64_t dy_pix_stride, const void* x, int64_t x_pix_stride,
@@ -205,7 +205,7 @@ int nk_conv2d_wgrad(const void* dy, int64_t dy_pix_stride, const void* x, int64_
     p.ldc = static_cast<long long>(taps) * Cin;
     p.out = OUT_F32_ATOMIC;
     p.epi = EPI_LINEAR;
-    return launch_gemm(p, static_cast<cudaStream_t>(stream));
+    return launch_gemm(p, ::nk::enter(stream));
 }
 
 }  // extern "C"

@@ -32,6 +32,48 @@ int device_sm_count() {
     return n;
 }
 
+// ---- driver context of the calling thread -----------------------------------------------------------------------
+// Entry points may be called from threads that never touched CUDA (PyTorch's autograd worker threads): the driver
+// then has no current context and raw driver calls (TMA descriptor encoding) fail with CUDA_ERROR_INVALID_CONTEXT,
+// while runtime calls would silently bind device 0.  Every entry point therefore adopts the context the caller's
+// stream belongs to.
+typedef CUresult (*PFN_ctxGetCurrent)(CUcontext*);
+typedef CUresult (*PFN_ctxSetCurrent)(CUcontext);
+typedef CUresult (*PFN_streamGetCtx)(CUstream, CUcontext*);
+
+static void* driver_fn(const char* name) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    return p;
+}
+
+cudaStream_t enter(void* stream) {
+    static PFN_ctxGetCurrent get_cur = reinterpret_cast<PFN_ctxGetCurrent>(driver_fn("cuCtxGetCurrent"));
+    static PFN_ctxSetCurrent set_cur = reinterpret_cast<PFN_ctxSetCurrent>(driver_fn("cuCtxSetCurrent"));
+    static PFN_streamGetCtx stream_ctx = reinterpret_cast<PFN_streamGetCtx>(driver_fn("cuStreamGetCtx"));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static CUcontext process_ctx = nullptr;  // one process per GPU: the first context seen is the process's context
+    if (get_cur && set_cur) {
+        CUcontext cur = nullptr;
+        if (get_cur(&cur) == CUDA_SUCCESS) {
+            if (cur != nullptr) {
+                if (process_ctx == nullptr) process_ctx = cur;
+            } else {
+                CUcontext want = nullptr;
+                if (st != nullptr && stream_ctx && stream_ctx(reinterpret_cast<CUstream>(st), &want) == CUDA_SUCCESS && want)
+                    set_cur(want);
+                else if (process_ctx != nullptr)
+                    set_cur(process_ctx);  // legacy default stream: fall back to the context used so far
+                else
+                    cudaFree(nullptr);  // nothing known yet: bind the runtime's current device
+            }
+        }
+    }
+    return st;
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (fn) return fn;

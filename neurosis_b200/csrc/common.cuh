@@ -43,6 +43,8 @@ int check_cuda(cudaError_t e, const char* what);
     } while (0)
 
 int device_sm_count();
+// adopt the CUDA context of the caller's stream on this thread (see common.cu) and return the stream
+cudaStream_t enter(void* stream);
 
 #if defined(__CUDACC__)
 

@@ -85,7 +85,7 @@ inline int grid_for(long long work, int block) {
 }  // namespace nk
 
 using namespace nk;
-#define ST(s) static_cast<cudaStream_t>(s)
+#define ST(s) ::nk::enter(s)
 
 extern "C" {
 

@@ -502,7 +502,7 @@ inline int grid_for(long long work, int block) {
 }  // namespace nk
 
 using namespace nk;
-#define ST(s) static_cast<cudaStream_t>(s)
+#define ST(s) ::nk::enter(s)
 #define BF(p) static_cast<bf16*>(p)
 #define CBF(p) static_cast<const bf16*>(p)
 

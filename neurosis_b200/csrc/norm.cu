@@ -480,7 +480,7 @@ int nk_groupnorm_fwd(const void* x, int64_t x_pix_stride, const float* gamma, co
     NK_REQUIRE(x_pix_stride % 8 == 0 && y_pix_stride % 8 == 0, NK_ERR_SHAPE, "groupnorm: strides must be multiples of 8");
     NK_REQUIRE(workspace_bytes >= nk_groupnorm_workspace_bytes(nimg, HW, C, G), NK_ERR_WORKSPACE, "groupnorm workspace");
     const GnPlan p = gn_plan(nimg, HW, C);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = ::nk::enter(stream);
     float2* partial = static_cast<float2*>(workspace);
     gn_stats_kernel<<<dim3(p.chunks, nimg), p.threads, 2 * C * sizeof(float), st>>>(
         static_cast<const bf16*>(x), x_pix_stride, partial, HW, C, G, p.V, p.ppb, p.pix_per_chunk);
@@ -500,7 +500,7 @@ int nk_groupnorm_bwd(const void* dy, int64_t dy_pix_stride, const void* x, int64
     NK_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 4096, NK_ERR_SHAPE, "groupnorm: C=%d G=%d", C, G);
     NK_REQUIRE(workspace_bytes >= nk_groupnorm_workspace_bytes(nimg, HW, C, G), NK_ERR_WORKSPACE, "groupnorm workspace");
     const GnPlan p = gn_plan(nimg, HW, C);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = ::nk::enter(stream);
     float2* partial = static_cast<float2*>(workspace);
     float2* chan = partial + static_cast<size_t>(nimg) * p.chunks * C;
     float2* coef = chan + static_cast<size_t>(nimg) * C;
@@ -520,7 +520,7 @@ int nk_groupnorm_bwd(const void* dy, int64_t dy_pix_stride, const void* x, int64
 int nk_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
                      float* mean, float* rstd, int rows, int C, float eps, nk_stream_t stream) {
     NK_REQUIRE(C % 8 == 0 && C <= 2560, NK_ERR_SHAPE, "layernorm: C=%d", C);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = ::nk::enter(stream);
     const int wpb = 8;
     const int grid = static_cast<int>(std::min<long long>((rows + wpb - 1) / wpb, 148LL * 8));
     const int V = C / 8;
@@ -541,7 +541,7 @@ int nk_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, c
                      const float* mean, const float* rstd, void* dx, int64_t lddx, float* dgamma, float* dbeta,
                      int rows, int C, nk_stream_t stream) {
     NK_REQUIRE(C % 8 == 0 && C <= 1280, NK_ERR_SHAPE, "layernorm bwd: C=%d", C);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = ::nk::enter(stream);
     const int wpb = 8;
     const int grid = static_cast<int>(std::min<long long>((rows + wpb - 1) / wpb, 148LL * 4));
     const int V = C / 8;
