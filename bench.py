@@ -193,6 +193,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--breakdown", default="", help="write a per-call-site breakdown of tensor-core time to this file")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
     args = ap.parse_args()
@@ -228,12 +229,25 @@ def main() -> None:
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
-    def step(batch: dict, read_loss: bool) -> float:
+    def eager_step(batch: dict, read_loss: bool) -> float:
+        ops.invalidate_weight_cache()  # a real loop updates the fp32 weights every step: re-derive the bf16 copies
         reducer.zero_grad()
         loss = eng.training_step(dict(batch))
         loss.backward()
         reducer.finish()
         return loss.item() if read_loss else 0.0
+
+    step = eager_step
+    graphed = None
+    if not args.no_graph:
+        from neurosis_b200.graph import GraphedTrainStep
+        graphed = GraphedTrainStep(eng, reducer, resident["image"], resident["crossattn_emb"], resident["vector_emb"])
+
+        def step(batch: dict, read_loss: bool) -> float:  # noqa: F811  (replays the captured step)
+            same = batch is resident
+            loss = graphed.step(None if same else batch["image"], None if same else batch["crossattn_emb"],
+                                None if same else batch["vector_emb"])
+            return loss.item() if read_loss else 0.0
 
     def barrier():
         if world > 1:
@@ -254,12 +268,15 @@ def main() -> None:
         return float(ms.item())
 
     for _ in range(W):
-        step(resident, False)
+        step(resident, False)  # (graph capture already ran its own eager warm-up steps)
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ops.LAUNCHES
     ms_dev = timed(args.steps, lambda: step(resident, False))
-    launches = ops.LAUNCHES - l0
-    ms_e2e = timed(args.steps, lambda: step({k: v.to(dev, non_blocking=True) for k, v in host.items()}, True))
+    launches = ops.LAUNCHES - l0 if graphed is None else graphed.launches_per_replay * args.steps
+    if graphed is not None:
+        ms_e2e = timed(args.steps, lambda: step(host, True))  # pinned host -> static device buffers -> replay -> loss
+    else:
+        ms_e2e = timed(args.steps, lambda: step({k: v.to(dev, non_blocking=True) for k, v in host.items()}, True))
     clocks = sampler.stop() if sampler else None
 
     # per-kernel roofline of the dominant kernel (gemm_tc_kernel): CUDA events around every launch of one extra step
@@ -267,14 +284,14 @@ def main() -> None:
     roof = None
     if not args.no_profile:
         ops.PROFILE_GEMM = []
-        step(resident, False)
+        eager_step(resident, False)
         torch.cuda.synchronize()
         recs, ops.PROFILE_GEMM = ops.PROFILE_GEMM, None
         if args.breakdown and rank == 0:  # second pass: every C-ABI entry point
             ops.PROFILE_KERNELS = []
             e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e_a.record()
-            step(resident, False)
+            eager_step(resident, False)
             e_b.record()
             torch.cuda.synchronize()
             krecs, ops.PROFILE_KERNELS = ops.PROFILE_KERNELS, None
@@ -313,7 +330,7 @@ def main() -> None:
     if args.torch_profile and rank == 0:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-            step(resident, False)
+            eager_step(resident, False)
             torch.cuda.synchronize()
         with open(args.torch_profile, "w") as fh:
             fh.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
@@ -325,7 +342,7 @@ def main() -> None:
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "SDXL base UNet (configs/sdxl) 1024x1024 training step: VAE encode + diffusion loss + backward"
                                        + (" + bucketed NCCL gradient all-reduce" if world > 1 else ""),
-                           "batch_per_gpu": B, "global_batch": B * world, "latent": "128x128x4",
+                           "batch_per_gpu": B, "global_batch": B * world, "cuda_graph": graphed is not None, "latent": "128x128x4",
                            "parallelism": f"dp{world}", "l2": "working set (5 GB bf16 weights + activations) >> 126 MB L2",
                            "step_tflop_algorithmic": GFLOP_STEP * B / 1e3,
                            "mfu_vs_peak": ips / world * GFLOP_STEP * 1e9 / (pk["tflops"] * 1e12)},

@@ -1,0 +1,83 @@
+"""CUDA-graph capture of the whole training step (VAE encode -> loss -> backward -> gradient all-reduce).
+
+The step launches ~4 000 kernels of this library plus the autograd engine's own bookkeeping; issued eagerly that is
+~0.3 s of Python/ctypes work per step, comparable to the GPU time.  Shapes are static in training (aspect buckets give
+a handful of shapes — one graph per bucket), so the step is captured once and replayed: the host only refreshes the
+static input buffers (images, conditioning, the per-sample sigma draw and loss weights) and launches one graph.
+
+Host-side semantics stay those of `DiffusionEngine.training_step` (reference models/diffusion.py:205-233): sigma draw
+on the CPU generator (`StandardDiffusionLoss.draw_sigmas`), loss hooks as per-sample weights, `loss.mean()`.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+from .ddp import BucketedGradReducer
+from .engine import DiffusionEngine
+
+
+class GraphedTrainStep:
+    def __init__(self, engine: DiffusionEngine, reducer: BucketedGradReducer, image: Tensor, crossattn: Tensor,
+                 vector: Optional[Tensor], warmup: int = 3):
+        self.engine, self.reducer = engine, reducer
+        dev = image.device
+        self.image = image.clone()
+        self.crossattn = crossattn.clone()
+        self.vector = vector.clone() if vector is not None else None
+        n = image.shape[0]
+        self.sigmas = torch.ones(n, dtype=torch.float32, device=dev)
+        self.weights = torch.ones(n, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.per_sample = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._refresh_sigmas()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._core()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        ops.invalidate_weight_cache()  # capture the fp32 -> bf16 / packed weight refresh: replayed every step
+        l0 = ops.LAUNCHES
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._core()
+        self.launches_per_replay = ops.LAUNCHES - l0
+
+    def _core(self) -> None:
+        eng = self.engine
+        self.reducer.zero_grad()
+        z = eng.encode_first_stage(self.image) if eng.first_stage_model is not None else self.image
+        cond = {"crossattn": self.crossattn}
+        if self.vector is not None:
+            cond["vector"] = self.vector
+        loss = eng.loss_fn._forward(eng.model, eng.denoiser, cond, z, {}, sigmas=self.sigmas)
+        total = (loss * self.weights).mean()
+        total.backward()
+        self.reducer.finish()
+        self.per_sample.copy_(loss.detach())
+        self.loss.copy_(total.detach())
+
+    def _refresh_sigmas(self) -> None:
+        s = self.engine.loss_fn.draw_sigmas(self.sigmas.shape[0]).float()
+        self.sigmas.copy_(s)  # a few bytes, stream-ordered before the replay
+
+    def step(self, image: Optional[Tensor] = None, crossattn: Optional[Tensor] = None, vector: Optional[Tensor] = None,
+             weights: Optional[Tensor] = None) -> Tensor:
+        """copy the new batch into the static buffers (host or device tensors), draw sigmas, replay.  Returns the
+        device scalar loss (read it with .item() when needed)."""
+        if image is not None:
+            self.image.copy_(image, non_blocking=True)
+        if crossattn is not None:
+            self.crossattn.copy_(crossattn, non_blocking=True)
+        if vector is not None and self.vector is not None:
+            self.vector.copy_(vector, non_blocking=True)
+        if weights is not None:
+            self.weights.copy_(weights, non_blocking=True)
+        self._refresh_sigmas()
+        self.graph.replay()
+        return self.loss

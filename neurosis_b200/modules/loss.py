@@ -74,14 +74,22 @@ class StandardDiffusionLoss(DiffusionLoss):
             raise ValueError(f"Unknown objective type: '{objective_type}'")
         self.input_keys = set(input_keys if isinstance(input_keys, list) else [input_keys])
 
+    def draw_sigmas(self, n: int) -> Tensor:
+        """host-side sigma draw exactly as `_forward` does it (CPU generator, float64 t)."""
+        return self.sigma_generator(n, torch.rand((n,), dtype=torch.float64))
+
     def _forward(self, network, denoiser, cond, inputs, batch, return_dict=False, *,
-                 t: Optional[Tensor] = None, noise: Optional[Tensor] = None):
-        """`t` / `noise` overrides exist for parity tests (the reference draws both internally)."""
+                 t: Optional[Tensor] = None, noise: Optional[Tensor] = None, sigmas: Optional[Tensor] = None):
+        """`t` / `noise` overrides exist for parity tests (the reference draws both internally); `sigmas` (a device
+        tensor filled from `draw_sigmas`) lets the whole step be captured in a CUDA graph without a host copy."""
         extra = {k: batch[k] for k in batch if k in self.input_keys}
         n = inputs.shape[0]
-        if t is None:
-            t = torch.rand((n,), dtype=torch.float64)
-        sigmas = self.sigma_generator(n, t).to(inputs)
+        if sigmas is None:
+            if t is None:
+                t = torch.rand((n,), dtype=torch.float64)
+            sigmas = self.sigma_generator(n, t).to(inputs)
+        else:
+            sigmas = sigmas.to(inputs)
         if noise is None:
             noise = torch.randn_like(inputs)
         noise = self.apply_noise_offset(noise, inputs)

@@ -127,6 +127,13 @@ def _cache_for(p: Tensor) -> dict:
     return d
 
 
+def invalidate_weight_cache() -> None:
+    """drop every cached bf16 / packed weight copy (they are re-derived by kernels on next use).  A training loop
+    whose optimizer updates the fp32 parameters in place gets this for free through the version check; callers
+    that capture CUDA graphs call it before capture so the casts are part of the graph and replayed every step."""
+    _wcache.clear()
+
+
 def cast_bf16(x: Tensor) -> Tensor:
     """fp32 -> bf16 copy with our kernel (bf16 input is returned as is)."""
     if x.dtype == BF16:
