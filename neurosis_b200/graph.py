@@ -41,6 +41,7 @@ class GraphedTrainStep:
                 self._core()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()  # the eager warm-up's activations must not stay cached next to the graph's pool
         ops.invalidate_weight_cache()  # capture the fp32 -> bf16 / packed weight refresh: replayed every step
         l0 = ops.LAUNCHES
         self.graph = torch.cuda.CUDAGraph()

