@@ -5,9 +5,10 @@
 // One CTA handles 128 query rows of one (batch, head):
 //   warp 0     TMA producer: Q tile once, then a ring of (K_j, V_j) 128-row tiles
 //   warp 1     MMA issuer:   S_j = Q K_j^T (TMEM, double buffered)   and   O_j = P_j V_j (TMEM, x2)
-//   warps 2-5  softmax:      one thread per query row; reads S_j from TMEM, online max/sum,
-//                            writes P_j (bf16, 128B-swizzled K-major) to smem for the PV MMA,
-//                            accumulates O in registers from the per-tile partial products.
+//   warps 2-9  softmax:      two threads per query row (64 kv columns / 32 output columns each); read S_j from
+//                            TMEM, online max/sum (row max exchanged through smem + a 64-thread named barrier),
+//                            write P_j (bf16, 128B-swizzled K-major) to smem for the PV MMA, accumulate O in
+//                            registers from the per-tile partial products.
 // S_{j+1} is issued before P_j V_j so the tensor pipe works while the softmax warps run.
 //
 // Replaces F.scaled_dot_product_attention / xformers.memory_efficient_attention at
@@ -22,7 +23,7 @@ constexpr int BKV = 128;
 constexpr int HD = 64;
 constexpr int KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;      // TMA warp, MMA warp, 8 softmax warps (2 per TMEM lane quadrant)
 constexpr int ATT_BWD_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps (2 per TMEM lane quadrant)
 
 struct alignas(64) AttnDev {
@@ -40,65 +41,9 @@ constexpr int SM_Q = 0;
 constexpr int SM_K = SM_Q + TILE_BYTES;
 constexpr int SM_V = SM_K + KV_STAGES * TILE_BYTES;
 constexpr int SM_P = SM_V + KV_STAGES * TILE_BYTES;
-constexpr int SM_BAR = SM_P + 4 * TILE_BYTES;
+constexpr int SM_XCHG = SM_P + 4 * TILE_BYTES;        // row max / sum exchange: 3 x 2 x 128 floats
+constexpr int SM_BAR = SM_XCHG + 3 * 2 * 128 * 4;
 constexpr int ATT_SMEM = SM_BAR + 256 + 1024;
-
-// ---- softmax building blocks shared by the forward kernel: one thread = one query row, S row lives in TMEM ----
-template <bool MASK>
-__device__ __forceinline__ float tile_rowmax(uint32_t s_addr, int kv_valid) {
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < 4; c += 2) {
-        uint32_t ra[32], rb[32];
-        tc_ld32(s_addr + static_cast<uint32_t>(c * 32), ra);
-        tc_ld32(s_addr + static_cast<uint32_t>((c + 1) * 32), rb);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            float a = __uint_as_float(ra[i]), b = __uint_as_float(rb[i]);
-            if (MASK) {
-                a = (c * 32 + i < kv_valid) ? a : -INFINITY;
-                b = ((c + 1) * 32 + i < kv_valid) ? b : -INFINITY;
-            }
-            m0 = fmaxf(m0, a);
-            m1 = fmaxf(m1, b);
-        }
-    }
-    return fmaxf(m0, m1);
-}
-
-// p = exp2(s*scale_log2 - mb) -> bf16, written to the 128B-swizzled [row][kv] tile pair at pbuf; returns the row sum
-template <bool MASK>
-__device__ __forceinline__ float tile_probs(uint32_t s_addr, int kv_valid, float scale_log2, float mb, uint8_t* pbuf,
-                                            int r) {
-    float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tc_ld32(s_addr + static_cast<uint32_t>(c * 32), raw);
-        tc_wait_ld();
-        float p[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            float v = exp2f(fmaf(__uint_as_float(raw[i]), scale_log2, -mb));
-            if (MASK) v = (c * 32 + i < kv_valid) ? v : 0.f;
-            p[i] = v;
-            if (i & 1) l1 += v; else l0 += v;
-        }
-        uint8_t* rowp = pbuf + (c >> 1) * TILE_BYTES + r * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint4 w;
-            w.x = pack_bf16x2(p[8 * q + 0], p[8 * q + 1]);
-            w.y = pack_bf16x2(p[8 * q + 2], p[8 * q + 3]);
-            w.z = pack_bf16x2(p[8 * q + 4], p[8 * q + 5]);
-            w.w = pack_bf16x2(p[8 * q + 6], p[8 * q + 7]);
-            const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
-            *reinterpret_cast<uint4*>(rowp + chunk * 16) = w;
-        }
-    }
-    return l0 + l1;
-}
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnDev g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -109,7 +54,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     uint64_t* kv_full = bars + 1;            // KV_STAGES
     uint64_t* kv_empty = bars + 1 + KV_STAGES;
     uint64_t* s_full = bars + 1 + 2 * KV_STAGES;  // 2
-    uint64_t* p_full = s_full + 2;                // 2 (128 arrivals)
+    uint64_t* p_full = s_full + 2;                // 2 (256 arrivals)
     uint64_t* o_full = p_full + 2;                // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
@@ -131,7 +76,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 128);
+            mbar_init(&p_full[i], 256);
             mbar_init(&o_full[i], 1);
         }
         fence_barrier_init();
@@ -215,71 +160,108 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
             }
         }
     } else {
-        // ===================== softmax / output warps =====================
+        // ===================== softmax / output warps: 2 per TMEM lane quadrant =====================
+        // Warp pair (quad, half=0/1) shares 32 query rows: each thread owns 64 of the 128 kv columns of its row (= one
+        // 64-kv swizzled P tile) and 32 of the 64 output columns.  The two partial row maxima are exchanged through
+        // shared memory with a 64-thread named barrier per tile; partial row sums are only combined at the end.
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int r = quad * 32 + lane;  // query row within the tile == TMEM lane
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-        float o[HD];
+        float* xchg = reinterpret_cast<float*>(smem + SM_XCHG);  // [2 (tile parity)][2 (half)][128 rows]
+        const int col0 = half * 64;
+        float o[32];
 #pragma unroll
-        for (int i = 0; i < HD; ++i) o[i] = 0.f;
-        float m_run = -INFINITY;  // running max of raw scores
-        float l_run = 0.f;
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+        float m_run = -INFINITY;  // running max of raw scores (identical in both threads of a row)
+        float l_run = 0.f;        // partial row sum over this thread's columns
         for (int j = 0; j < T; ++j) {
             mbar_wait(&s_full[j & 1], (j >> 1) & 1u, 30u);
             tc_fence_after();
-            const uint32_t s_addr = lane_addr + TM_S + static_cast<uint32_t>((j & 1) * 128);
-            const int kv_valid = g.Nk - j * BKV;  // columns >= kv_valid are padding
-            // pass 1: row max ; pass 2: probabilities -> smem (bf16, swizzled) + row sum.  Only the last K/V tile
-            // can be partial, so the masked variant is taken at most once per row.
-            const bool tail = kv_valid < BKV;
-            const float m_tile = tail ? tile_rowmax<true>(s_addr, kv_valid) : tile_rowmax<false>(s_addr, kv_valid);
+            const uint32_t s_addr = lane_addr + TM_S + static_cast<uint32_t>((j & 1) * 128 + col0);
+            const int kv_valid = g.Nk - j * BKV - col0;  // this thread's columns >= kv_valid are padding
+            const bool tail = kv_valid < 64;
+            uint32_t ra[32], rb[32];
+            tc_ld32(s_addr, ra);
+            tc_ld32(s_addr + 32u, rb);
+            tc_wait_ld();
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float a = __uint_as_float(ra[i]), c2 = __uint_as_float(rb[i]);
+                if (tail) {
+                    a = (i < kv_valid) ? a : -INFINITY;
+                    c2 = (32 + i < kv_valid) ? c2 : -INFINITY;
+                }
+                m0 = fmaxf(m0, a);
+                m1 = fmaxf(m1, c2);
+            }
+            const float m_loc = fmaxf(m0, m1);
+            xchg[((j & 1) * 2 + half) * 128 + r] = m_loc;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");  // the two warps of this quadrant
+            const float m_tile = fmaxf(m_loc, xchg[((j & 1) * 2 + (half ^ 1)) * 128 + r]);
             const float m_new = fmaxf(m_run, m_tile);
             const float alpha = exp2f((m_run - m_new) * g.scale_log2);  // 0 on the first tile
             const float mb = m_new * g.scale_log2;
-            uint8_t* pbuf = smem + SM_P + (j & 1) * 2 * TILE_BYTES;
-            const float l_tile = tail ? tile_probs<true>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r)
-                                      : tile_probs<false>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r);
+            const uint32_t p_row = smem_u32(smem + SM_P + (j & 1) * 2 * TILE_BYTES + half * TILE_BYTES + r * 128);
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                float p[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float v = exp2f(fmaf(__uint_as_float(cc ? rb[i] : ra[i]), g.scale_log2, -mb));
+                    if (tail) v = (cc * 32 + i < kv_valid) ? v : 0.f;
+                    p[i] = v;
+                    if (i & 1) l1 += v; else l0 += v;
+                }
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    uint4 w;
+                    w.x = pack_bf16x2(p[8 * qq + 0], p[8 * qq + 1]);
+                    w.y = pack_bf16x2(p[8 * qq + 2], p[8 * qq + 3]);
+                    w.z = pack_bf16x2(p[8 * qq + 4], p[8 * qq + 5]);
+                    w.w = pack_bf16x2(p[8 * qq + 6], p[8 * qq + 7]);
+                    st_shared_v4(p_row + static_cast<uint32_t>(((cc * 4 + qq) ^ (r & 7)) * 16), w);
+                }
+            }
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[j & 1]);
-            // fold in the previous tile's partial product, then rescale to the new max
+            // fold in the previous tile's partial product (this warp's 32 output columns), then rescale
             if (j > 0) {
                 mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1u, 31u);
                 tc_fence_after();
-                const uint32_t o_addr = lane_addr + TM_O + static_cast<uint32_t>(((j - 1) & 1) * 64);
+                uint32_t raw[32];
+                tc_ld32(lane_addr + TM_O + static_cast<uint32_t>(((j - 1) & 1) * 64 + half * 32), raw);
+                tc_wait_ld();
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t raw[32];
-                    tc_ld32(o_addr + static_cast<uint32_t>(c * 32), raw);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + __uint_as_float(raw[i])) * alpha;
-                }
+                for (int i = 0; i < 32; ++i) o[i] = (o[i] + __uint_as_float(raw[i])) * alpha;
             }
-            l_run = l_run * alpha + l_tile;
+            l_run = l_run * alpha + (l0 + l1);
             m_run = m_new;
         }
         // last partial product
         mbar_wait(&o_full[(T - 1) & 1], ((T - 1) >> 1) & 1u, 32u);
         tc_fence_after();
         {
-            const uint32_t o_addr = lane_addr + TM_O + static_cast<uint32_t>(((T - 1) & 1) * 64);
+            uint32_t raw[32];
+            tc_ld32(lane_addr + TM_O + static_cast<uint32_t>(((T - 1) & 1) * 64 + half * 32), raw);
+            tc_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t raw[32];
-                tc_ld32(o_addr + static_cast<uint32_t>(c * 32), raw);
-                tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(raw[i]);
-            }
+            for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(raw[i]);
         }
+        // combine the two partial row sums
+        xchg[(2 * 2 + half) * 128 + r] = l_run;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        const float l_tot = l_run + xchg[(2 * 2 + (half ^ 1)) * 128 + r];
         const int q = q0 + r;
         if (q < g.Nq) {
-            const float inv = 1.f / l_run;
+            const float inv = 1.f / l_tot;
             bf16* op = g.O + static_cast<long long>(b) * g.o_batch_stride + static_cast<long long>(q) * g.o_row_stride +
-                       static_cast<long long>(h) * HD;
+                       static_cast<long long>(h) * HD + half * 32;
 #pragma unroll
-            for (int c = 0; c < HD / 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
                 uint4 w;
                 w.x = pack_bf16x2(o[8 * c + 0] * inv, o[8 * c + 1] * inv);
                 w.y = pack_bf16x2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
@@ -287,7 +269,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
                 w.w = pack_bf16x2(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
                 reinterpret_cast<uint4*>(op)[c] = w;
             }
-            if (g.lse) g.lse[(static_cast<long long>(b) * g.H + h) * g.Nq + q] = m_run * g.scale + logf(l_run);
+            if (g.lse && half == 0) g.lse[(static_cast<long long>(b) * g.H + h) * g.Nq + q] = m_run * g.scale + logf(l_tot);
         }
         tc_fence_before();
     }
