@@ -367,7 +367,20 @@ def main() -> None:
                                     "sample": r["sample"]}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down order matters: a captured graph holds NCCL kernels, and destroying the communicator while the
+        # graph is alive blocks forever (observed: the JSON line printed, then the ranks hung in
+        # destroy_process_group).  Drop the graph first, and leave through os._exit so no NCCL finaliser can stall
+        # the launcher after the result is out.
+        del step
+        graphed = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

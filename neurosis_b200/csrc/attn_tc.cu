@@ -5,15 +5,16 @@
 // One CTA handles 128 query rows of one (batch, head):
 //   warp 0     TMA producer: Q tile once, then a ring of (K_j, V_j) 128-row tiles
 //   warp 1     MMA issuer:   S_j = Q K_j^T (TMEM, double buffered)   and   O_j = P_j V_j (TMEM, x2)
-//   warps 2-9  softmax:      two threads per query row (64 kv columns / 32 output columns each); read S_j from
-//                            TMEM, online max/sum (row max exchanged through smem + a 64-thread named barrier),
-//                            write P_j (bf16, 128B-swizzled K-major) to smem for the PV MMA, accumulate O in
-//                            registers from the per-tile partial products.
+//   warps 2-5  softmax:      one thread per query row; reads S_j from TMEM, online max/sum,
+//                            writes P_j (bf16, 128B-swizzled K-major) to smem for the PV MMA,
+//                            accumulates O in registers from the per-tile partial products.
 // S_{j+1} is issued before P_j V_j so the tensor pipe works while the softmax warps run.
 //
 // Replaces F.scaled_dot_product_attention / xformers.memory_efficient_attention at
 // /root/reference/src/neurosis/modules/attention.py:346-352,410-412 (self and cross attention).
 #include "common.cuh"
+
+#include <cstdlib>
 
 namespace nk {
 namespace {
@@ -21,9 +22,9 @@ namespace {
 constexpr int BQ = 128;
 constexpr int BKV = 128;
 constexpr int HD = 64;
-constexpr int KV_STAGES = 3;
+constexpr int KV_STAGES = 2;
 constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
-constexpr int ATT_THREADS = 320;      // TMA warp, MMA warp, 8 softmax warps (2 per TMEM lane quadrant)
+constexpr int ATT_THREADS = 192;
 constexpr int ATT_BWD_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps (2 per TMEM lane quadrant)
 
 struct alignas(64) AttnDev {
@@ -36,27 +37,98 @@ struct alignas(64) AttnDev {
     float scale;
 };
 
-// smem layout (after 1024B alignment): Q | K[3] | V[3] | P[2][2] | barriers
+// smem layout (after 1024B alignment): Q | K[2] | V[2] | P[2 atoms] | barriers  (= 113 KB: two CTAs per SM, whose
+// serial S -> softmax -> PV chains interleave on the tensor and MUFU pipes)
 constexpr int SM_Q = 0;
 constexpr int SM_K = SM_Q + TILE_BYTES;
 constexpr int SM_V = SM_K + KV_STAGES * TILE_BYTES;
 constexpr int SM_P = SM_V + KV_STAGES * TILE_BYTES;
-constexpr int SM_XCHG = SM_P + 4 * TILE_BYTES;        // row max / sum exchange: 3 x 2 x 128 floats
-constexpr int SM_BAR = SM_XCHG + 3 * 2 * 128 * 4;
-constexpr int ATT_SMEM = SM_BAR + 256 + 1024;
+constexpr int SM_BAR = SM_P + 2 * TILE_BYTES;
+// two CTAs per SM need 2 * (ATT_SMEM + 1 KB reserved) <= 228 KB, which leaves 896 bytes of alignment slack; the
+// dynamic window starts 1024-aligned in practice (no static smem) and the kernel traps if it ever does not fit
+constexpr int ATT_SMEM = 115712;
+static_assert(SM_BAR + 128 <= ATT_SMEM, "attention forward smem budget");
+constexpr int ATT_TMEM_COLS = 256;  // S at 0..127, O partial at 128..191
 
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnDev g) {
+// ---- softmax building blocks shared by the forward kernel: one thread = one query row, S row lives in TMEM ----
+template <bool MASK>
+__device__ __forceinline__ float tile_rowmax(uint32_t s_addr, int kv_valid) {
+    float m0 = -INFINITY, m1 = -INFINITY;
+    uint32_t ra[16], rb[16];
+    tc_ld16(s_addr, ra);
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+        tc_wait_ld16(ra);
+        tc_ld16(s_addr + static_cast<uint32_t>((c + 1) * 16), rb);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float a = __uint_as_float(ra[i]);
+            if (MASK) a = (c * 16 + i < kv_valid) ? a : -INFINITY;
+            if (i & 1) m1 = fmaxf(m1, a); else m0 = fmaxf(m0, a);
+        }
+        tc_wait_ld16(rb);
+        if (c + 2 < 8) tc_ld16(s_addr + static_cast<uint32_t>((c + 2) * 16), ra);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float a = __uint_as_float(rb[i]);
+            if (MASK) a = ((c + 1) * 16 + i < kv_valid) ? a : -INFINITY;
+            if (i & 1) m1 = fmaxf(m1, a); else m0 = fmaxf(m0, a);
+        }
+    }
+    return fmaxf(m0, m1);
+}
+
+// p = exp2(s*scale_log2 - mb) -> bf16, written to the 128B-swizzled [row][kv] tile pair at pbuf; returns the row sum
+template <bool MASK>
+__device__ __forceinline__ float tile_probs(uint32_t s_addr, int kv_valid, float scale_log2, float mb, uint8_t* pbuf,
+                                            int r) {
+    float l0 = 0.f, l1 = 0.f;
+    auto emit = [&](int c, const uint32_t (&raw)[16]) {  // c = 16-column chunk 0..7
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            float v0 = exp2f(fmaf(__uint_as_float(raw[i]), scale_log2, -mb));
+            float v1 = exp2f(fmaf(__uint_as_float(raw[i + 1]), scale_log2, -mb));
+            if (MASK) {
+                v0 = (c * 16 + i < kv_valid) ? v0 : 0.f;
+                v1 = (c * 16 + i + 1 < kv_valid) ? v1 : 0.f;
+            }
+            l0 += v0;
+            l1 += v1;
+            w[i >> 1] = pack_bf16x2(v0, v1);
+        }
+        uint8_t* rowp = pbuf + (c >> 2) * TILE_BYTES + r * 128;
+        const int ch = (c & 3) * 2;
+        *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (r & 7)) * 16)) = make_uint4(w[4], w[5], w[6], w[7]);
+    };
+    uint32_t ra[16], rb[16];
+    tc_ld16(s_addr, ra);
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+        tc_wait_ld16(ra);
+        tc_ld16(s_addr + static_cast<uint32_t>((c + 1) * 16), rb);
+        emit(c, ra);
+        tc_wait_ld16(rb);
+        if (c + 2 < 8) tc_ld16(s_addr + static_cast<uint32_t>((c + 2) * 16), ra);
+        emit(c + 1, rb);
+    }
+    return l0 + l1;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnDev g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
+    if (static_cast<int>(smem - smem_raw) + SM_BAR + 128 > ATT_SMEM) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
     uint64_t* q_full = bars;                 // 1
     uint64_t* kv_full = bars + 1;            // KV_STAGES
     uint64_t* kv_empty = bars + 1 + KV_STAGES;
-    uint64_t* s_full = bars + 1 + 2 * KV_STAGES;  // 2
-    uint64_t* p_full = s_full + 2;                // 2 (256 arrivals)
-    uint64_t* o_full = p_full + 2;                // 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+    uint64_t* s_full = bars + 1 + 2 * KV_STAGES;  // S_j complete in TMEM
+    uint64_t* p_full = s_full + 1;                // P_j in smem and S_j consumed (128 arrivals)
+    uint64_t* o_full = p_full + 1;                // P_j V_j complete in TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -74,22 +146,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 256);
-            mbar_init(&o_full[i], 1);
-        }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 128);
+        mbar_init(o_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, ATT_TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t TM_S = 0, TM_O = 256;  // S buffers at cols 0,128 ; O partial buffers at 256,320
+    const uint32_t TM_S = 0, TM_O = 128;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -113,34 +183,35 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
             const uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);  // S: both K-major
             const uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);   // O: P K-major, V MN-major
             const uint64_t q_desc = make_smem_desc(smem_u32(smem + SM_Q), 16u, 1024u);
-            auto issue_s = [&](int j, int stage) {
+            auto issue_s = [&](int stage) {
                 const uint64_t k_desc = make_smem_desc(smem_u32(smem + SM_K + stage * TILE_BYTES), 16u, 1024u);
-                const uint32_t d = tmem_base + TM_S + static_cast<uint32_t>((j & 1) * 128);
+                const uint32_t d = tmem_base + TM_S;
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k)
                     tc_mma_ss(d, q_desc + static_cast<uint64_t>(k * 2), k_desc + static_cast<uint64_t>(k * 2), idesc_s,
                               k > 0 ? 1u : 0u);
-                tc_commit(&s_full[j & 1]);
+                tc_commit(s_full);
             };
             mbar_wait(q_full, 0, 20);
             int stage = 0, nstage = 0;
             uint32_t nphase = 0;
             mbar_wait(&kv_full[0], 0, 21);
             tc_fence_after();
-            issue_s(0, 0);
+            issue_s(0);
             nstage = 1 % KV_STAGES;
             nphase = (KV_STAGES == 1) ? 1u : 0u;
             for (int j = 0; j < T; ++j) {
+                // P_j written and S_j fully read by the softmax warps (they also folded O_{j-1} before writing P_j)
+                mbar_wait(p_full, j & 1u, 23u);
+                tc_fence_after();
                 if (j + 1 < T) {
                     mbar_wait(&kv_full[nstage], nphase, 22u);
                     tc_fence_after();
-                    issue_s(j + 1, nstage);
+                    issue_s(nstage);
                 }
-                mbar_wait(&p_full[j & 1], (j >> 1) & 1u, 23u);
-                tc_fence_after();
                 {
-                    const uint32_t d = tmem_base + TM_O + static_cast<uint32_t>((j & 1) * 64);
-                    const uint32_t pbase = smem_u32(smem + SM_P + (j & 1) * 2 * TILE_BYTES);
+                    const uint32_t d = tmem_base + TM_O;
+                    const uint32_t pbase = smem_u32(smem + SM_P);
                     const uint32_t vbase = smem_u32(smem + SM_V + stage * TILE_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < BKV / 16; ++kk) {
@@ -149,7 +220,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
                         const uint64_t v_desc = make_smem_desc(vbase + static_cast<uint32_t>(kk * 2048), 8192u, 1024u);
                         tc_mma_ss(d, p_desc, v_desc, idesc_o, kk > 0 ? 1u : 0u);
                     }
-                    tc_commit(&o_full[j & 1]);
+                    tc_commit(o_full);
                     tc_commit(&kv_empty[stage]);
                 }
                 stage = nstage;
@@ -160,108 +231,72 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
             }
         }
     } else {
-        // ===================== softmax / output warps: 2 per TMEM lane quadrant =====================
-        // Warp pair (quad, half=0/1) shares 32 query rows: each thread owns 64 of the 128 kv columns of its row (= one
-        // 64-kv swizzled P tile) and 32 of the 64 output columns.  The two partial row maxima are exchanged through
-        // shared memory with a 64-thread named barrier per tile; partial row sums are only combined at the end.
+        // ===================== softmax / output warps =====================
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
         const int r = quad * 32 + lane;  // query row within the tile == TMEM lane
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-        float* xchg = reinterpret_cast<float*>(smem + SM_XCHG);  // [2 (tile parity)][2 (half)][128 rows]
-        const int col0 = half * 64;
-        float o[32];
+        float o[HD];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0.f;
-        float m_run = -INFINITY;  // running max of raw scores (identical in both threads of a row)
-        float l_run = 0.f;        // partial row sum over this thread's columns
+        for (int i = 0; i < HD; ++i) o[i] = 0.f;
+        float m_run = -INFINITY;  // running max of raw scores
+        float l_run = 0.f;
         for (int j = 0; j < T; ++j) {
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1u, 30u);
+            mbar_wait(s_full, j & 1u, 30u);
             tc_fence_after();
-            const uint32_t s_addr = lane_addr + TM_S + static_cast<uint32_t>((j & 1) * 128 + col0);
-            const int kv_valid = g.Nk - j * BKV - col0;  // this thread's columns >= kv_valid are padding
-            const bool tail = kv_valid < 64;
-            uint32_t ra[32], rb[32];
-            tc_ld32(s_addr, ra);
-            tc_ld32(s_addr + 32u, rb);
-            tc_wait_ld();
-            float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float a = __uint_as_float(ra[i]), c2 = __uint_as_float(rb[i]);
-                if (tail) {
-                    a = (i < kv_valid) ? a : -INFINITY;
-                    c2 = (32 + i < kv_valid) ? c2 : -INFINITY;
-                }
-                m0 = fmaxf(m0, a);
-                m1 = fmaxf(m1, c2);
-            }
-            const float m_loc = fmaxf(m0, m1);
-            xchg[((j & 1) * 2 + half) * 128 + r] = m_loc;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");  // the two warps of this quadrant
-            const float m_tile = fmaxf(m_loc, xchg[((j & 1) * 2 + (half ^ 1)) * 128 + r]);
+            const uint32_t s_addr = lane_addr + TM_S;
+            const int kv_valid = g.Nk - j * BKV;  // columns >= kv_valid are padding
+            // pass 1: row max ; pass 2: probabilities -> smem (bf16, swizzled) + row sum.  Only the last K/V tile
+            // can be partial, so the masked variant is taken at most once per row.
+            const bool tail = kv_valid < BKV;
+            const float m_tile = tail ? tile_rowmax<true>(s_addr, kv_valid) : tile_rowmax<false>(s_addr, kv_valid);
             const float m_new = fmaxf(m_run, m_tile);
             const float alpha = exp2f((m_run - m_new) * g.scale_log2);  // 0 on the first tile
             const float mb = m_new * g.scale_log2;
-            const uint32_t p_row = smem_u32(smem + SM_P + (j & 1) * 2 * TILE_BYTES + half * TILE_BYTES + r * 128);
-            float l0 = 0.f, l1 = 0.f;
+            // fold in the previous tile's partial product and rescale to the new max; its completion also means the
+            // tensor pipe is done reading the P buffer, which is rewritten next
+            if (j > 0) {
+                mbar_wait(o_full, (j - 1) & 1u, 31u);
+                tc_fence_after();
+                const uint32_t o_addr = lane_addr + TM_O;
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                float p[32];
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t raw[32];
+                    tc_ld32(o_addr + static_cast<uint32_t>(c * 32), raw);
+                    tc_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float v = exp2f(fmaf(__uint_as_float(cc ? rb[i] : ra[i]), g.scale_log2, -mb));
-                    if (tail) v = (cc * 32 + i < kv_valid) ? v : 0.f;
-                    p[i] = v;
-                    if (i & 1) l1 += v; else l0 += v;
-                }
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    uint4 w;
-                    w.x = pack_bf16x2(p[8 * qq + 0], p[8 * qq + 1]);
-                    w.y = pack_bf16x2(p[8 * qq + 2], p[8 * qq + 3]);
-                    w.z = pack_bf16x2(p[8 * qq + 4], p[8 * qq + 5]);
-                    w.w = pack_bf16x2(p[8 * qq + 6], p[8 * qq + 7]);
-                    st_shared_v4(p_row + static_cast<uint32_t>(((cc * 4 + qq) ^ (r & 7)) * 16), w);
+                    for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + __uint_as_float(raw[i])) * alpha;
                 }
             }
+            uint8_t* pbuf = smem + SM_P;
+            const float l_tile = tail ? tile_probs<true>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r)
+                                      : tile_probs<false>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r);
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(&p_full[j & 1]);
-            // fold in the previous tile's partial product (this warp's 32 output columns), then rescale
-            if (j > 0) {
-                mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1u, 31u);
-                tc_fence_after();
-                uint32_t raw[32];
-                tc_ld32(lane_addr + TM_O + static_cast<uint32_t>(((j - 1) & 1) * 64 + half * 32), raw);
-                tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = (o[i] + __uint_as_float(raw[i])) * alpha;
-            }
-            l_run = l_run * alpha + (l0 + l1);
+            mbar_arrive(p_full);
+            l_run = l_run * alpha + l_tile;
             m_run = m_new;
         }
         // last partial product
-        mbar_wait(&o_full[(T - 1) & 1], ((T - 1) >> 1) & 1u, 32u);
+        mbar_wait(o_full, (T - 1) & 1u, 32u);
         tc_fence_after();
         {
-            uint32_t raw[32];
-            tc_ld32(lane_addr + TM_O + static_cast<uint32_t>(((T - 1) & 1) * 64 + half * 32), raw);
-            tc_wait_ld();
+            const uint32_t o_addr = lane_addr + TM_O;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(raw[i]);
+            for (int c = 0; c < 2; ++c) {
+                uint32_t raw[32];
+                tc_ld32(o_addr + static_cast<uint32_t>(c * 32), raw);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(raw[i]);
+            }
         }
-        // combine the two partial row sums
-        xchg[(2 * 2 + half) * 128 + r] = l_run;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-        const float l_tot = l_run + xchg[(2 * 2 + (half ^ 1)) * 128 + r];
         const int q = q0 + r;
         if (q < g.Nq) {
-            const float inv = 1.f / l_tot;
+            const float inv = 1.f / l_run;
             bf16* op = g.O + static_cast<long long>(b) * g.o_batch_stride + static_cast<long long>(q) * g.o_row_stride +
-                       static_cast<long long>(h) * HD + half * 32;
+                       static_cast<long long>(h) * HD;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < HD / 8; ++c) {
                 uint4 w;
                 w.x = pack_bf16x2(o[8 * c + 0] * inv, o[8 * c + 1] * inv);
                 w.y = pack_bf16x2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
@@ -269,7 +304,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
                 w.w = pack_bf16x2(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
                 reinterpret_cast<uint4*>(op)[c] = w;
             }
-            if (g.lse && half == 0) g.lse[(static_cast<long long>(b) * g.H + h) * g.Nq + q] = m_run * g.scale + logf(l_tot);
+            if (g.lse) g.lse[(static_cast<long long>(b) * g.H + h) * g.Nq + q] = m_run * g.scale + logf(l_run);
         }
         tc_fence_before();
     }
@@ -278,7 +313,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, ATT_TMEM_COLS);
     }
 }
 
@@ -296,6 +331,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
 // =================================================================================================
 struct alignas(64) AttnBwdDev {
     CUtensorMap tmQ, tmK, tmV, tmdO;
+    CUtensorMap tmdQ;    // fp32 [B, Nq, H, 64] accumulator, box {32 cols, 1, 128 rows, 1}: target of the TMA reduce-add
     const float* lse;    // [B, H, Nq]
     const float* delta;  // [B, H, Nq]
     float* dQ;           // fp32 accumulator [B, Nq, H, 64] (zero-initialised by the caller)
@@ -304,6 +340,7 @@ struct alignas(64) AttnBwdDev {
     long long dq_row_stride, dq_batch_stride, dkv_row_stride, dkv_batch_stride;
     int Nq, Nk, H, B;
     float scale, scale_log2;
+    int dbg;  // NK_ATTN_DBG A/B switch: 4 = per-thread red.global for dQ instead of the staged TMA reduce-add
 };
 
 constexpr int BW_K = 0;
@@ -312,7 +349,8 @@ constexpr int BW_Q = BW_V + TILE_BYTES;        // 2 stages
 constexpr int BW_DO = BW_Q + 2 * TILE_BYTES;   // 2 stages
 constexpr int BW_P = BW_DO + 2 * TILE_BYTES;   // 128x128 bf16 = 2 tiles
 constexpr int BW_DS = BW_P + 2 * TILE_BYTES;
-constexpr int BW_BAR = BW_DS + 2 * TILE_BYTES;
+constexpr int BW_DQ = BW_DS + 2 * TILE_BYTES;  // fp32 dQ staging: 2 x (128 rows x 32 cols), 128B-swizzled like the rest
+constexpr int BW_BAR = BW_DQ + 2 * TILE_BYTES;
 constexpr int BW_SMEM = BW_BAR + 256 + 1024;
 
 __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdDev g) {
@@ -343,6 +381,7 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __gr
         tma_prefetch_desc(&g.tmK);
         tma_prefetch_desc(&g.tmV);
         tma_prefetch_desc(&g.tmdO);
+        tma_prefetch_desc(&g.tmdQ);
         mbar_init(kv_full, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&qdo_full[s], 1);
@@ -386,8 +425,6 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __gr
             const uint32_t idesc_km = make_idesc_bf16(128, HD, 0, 1);   // dQ: dS K-major, K MN-major
             const uint32_t k_addr = smem_u32(smem + BW_K), v_addr = smem_u32(smem + BW_V);
             const uint32_t p_addr = smem_u32(smem + BW_P), ds_addr = smem_u32(smem + BW_DS);
-            // S_i / dP_i of the NEXT tile are issued right after ds_ready(i) so they execute behind dK_i / dQ_i and the
-            // softmax warps never wait for the tensor pipe in steady state.
             auto issue_s_dp = [&](int i) {
                 const int st = i & 1;
                 const uint32_t q_addr = smem_u32(smem + BW_Q + st * TILE_BYTES);
@@ -423,6 +460,9 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __gr
                 // dK += dS^T Q ;  dQ_i = dS K
                 mbar_wait(ds_ready, par, 53u);
                 tc_fence_after();
+                // S/dP of the next tile go ahead of dK/dQ (their TMEM is free: the softmax warps passed ds_ready(i)), so
+                // the softmax warps find S_{i+1} ready when they come back from the dQ flush
+                if (i + 1 < Tq) issue_s_dp(i + 1);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     tc_mma_ss(tmem_base + TM_DK, make_smem_desc(ds_addr + k * 2048, 16384u, 1024u),
@@ -434,7 +474,6 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __gr
                               make_smem_desc(k_addr + k * 2048, 8192u, 1024u), idesc_km, k > 0 ? 1u : 0u);
                 tc_commit(dq_full);
                 tc_commit(&qdo_empty[st]);
-                if (i + 1 < Tq) issue_s_dp(i + 1);  // S/dP TMEM are free: the softmax warps passed ds_ready(i)
             }
         }
     } else {
@@ -449,24 +488,45 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __gr
         const bool kv_full_tile = kv_valid >= BKV;
         const int col0 = half * 64;
         // dQ partial of tile `it` (this warp: 32 of the 64 columns) -> global fp32 accumulator
+        // The 128x64 fp32 partial is staged in smem (one 128x32 swizzled tile per column half) and added to global
+        // memory by ONE TMA reduce per half: per-thread red.global (32 scattered half-sectors per warp instruction)
+        // cost a quarter of the kernel.  Rows past Nq are clipped by the TMA unit.
+        const uint32_t dq_row = smem_u32(smem + BW_DQ) + static_cast<uint32_t>(half * TILE_BYTES + r * 128);
+        const bool dq_issuer = (warp == 2 && lane == 0);
         auto flush_dq = [&](int it) {
             mbar_wait(dq_full, static_cast<uint32_t>(it & 1), 62u);
             tc_fence_after();
-            const int q = it * BQ + r;
-            float* dqp = g.dQ + static_cast<long long>(b) * g.dq_batch_stride + static_cast<long long>(q) * g.dq_row_stride +
-                         static_cast<long long>(h) * HD + half * 32;
             uint32_t raw[32];
             tc_ld32(lane_addr + TM_DQ + static_cast<uint32_t>(half * 32), raw);
             tc_wait_ld();
-            if (q < g.Nq) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqp + 4 * k),
-                                 "f"(__uint_as_float(raw[4 * k])), "f"(__uint_as_float(raw[4 * k + 1])),
-                                 "f"(__uint_as_float(raw[4 * k + 2])), "f"(__uint_as_float(raw[4 * k + 3]))
-                                 : "memory");
-            }
             tc_fence_before();
+            if (g.dbg & 4) {
+                const int q = it * BQ + r;
+                float* dqp = g.dQ + static_cast<long long>(b) * g.dq_batch_stride +
+                             static_cast<long long>(q) * g.dq_row_stride + static_cast<long long>(h) * HD + half * 32;
+                if (q < g.Nq) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqp + 4 * k),
+                                     "f"(__uint_as_float(raw[4 * k])), "f"(__uint_as_float(raw[4 * k + 1])),
+                                     "f"(__uint_as_float(raw[4 * k + 2])), "f"(__uint_as_float(raw[4 * k + 3]))
+                                     : "memory");
+                }
+                return;
+            }
+            if (dq_issuer) tma_wait_group_read<0>();  // the previous tile's reduce has finished reading the staging tile
+            named_bar_sync(1, 256);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                st_shared_v4(dq_row + static_cast<uint32_t>((k ^ (r & 7)) * 16),
+                             make_uint4(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2], raw[4 * k + 3]));
+            fence_proxy_async_smem();
+            named_bar_sync(1, 256);
+            if (dq_issuer) {
+                tma_reduce_add_4d(&g.tmdQ, smem + BW_DQ, 0, h, it * BQ, b);
+                tma_reduce_add_4d(&g.tmdQ, smem + BW_DQ + TILE_BYTES, 32, h, it * BQ, b);
+                tma_commit_group();
+            }
         };
         const long long sbase = (static_cast<long long>(b) * g.H + h) * g.Nq;
         float lse_next = (r < g.Nq) ? g.lse[sbase + r] : 0.f;
@@ -544,6 +604,7 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __gr
             mbar_arrive(ds_ready);
         }
         flush_dq(Tq - 1);
+        if (dq_issuer) tma_wait_group<0>();  // smem must outlive the last reduce
         // ---- dV, dK of this K/V tile (all MMAs retired: dq_full of the last tile covers them); 32 columns per warp ----
         const int kvrow = kv0 + r;
 #pragma unroll
@@ -653,6 +714,15 @@ int nk_attention_bwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
     if (e) return e;
     e = make_qkv_tmap(&g.tmdO, dO, Nq, H, B, do_row_stride, HD, do_batch_stride);
     if (e) return e;
+    {
+        const uint64_t dims[4] = {static_cast<uint64_t>(HD), static_cast<uint64_t>(H), static_cast<uint64_t>(Nq),
+                                  static_cast<uint64_t>(B)};
+        const uint64_t strides[3] = {static_cast<uint64_t>(HD) * 4, static_cast<uint64_t>(H) * HD * 4,
+                                     static_cast<uint64_t>(Nq) * H * HD * 4};
+        const uint32_t box[4] = {32, 1, 128, 1};
+        e = encode_tmap(&g.tmdQ, dq_acc, 4, dims, strides, box, 1);
+        if (e) return e;
+    }
     g.lse = lse;
     g.delta = delta;
     g.dQ = dq_acc;
@@ -668,6 +738,12 @@ int nk_attention_bwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
     g.B = B;
     g.scale = scale;
     g.scale_log2 = scale * 1.4426950408889634f;
+    static int dbg = -1;
+    if (dbg < 0) {
+        const char* e_ = getenv("NK_ATTN_DBG");
+        dbg = e_ ? atoi(e_) : 0;
+    }
+    g.dbg = dbg;
     static bool attr_set = false;
     if (!attr_set) {
         NK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));

@@ -90,6 +90,11 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box) {
+    return encode_tmap(out, base, rank, dims, strides_bytes, box, 0);
+}
+
+int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, int is_f32) {
     PFN_cuTensorMapEncodeTiled_v12000 fn = get_encode_fn();
     if (!fn) return NK_ERR_CUDA;
     NK_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, NK_ERR_SHAPE,
@@ -110,7 +115,8 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                    static_cast<unsigned long long>(dims[i]), box[i]);
     }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+    CUresult r = fn(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                    static_cast<cuuint32_t>(rank),
                     const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -174,6 +174,29 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar
         : "memory");
 }
 
+// smem tile -> global with an element-wise add done by the TMA unit / L2 (bulk async-group completion)
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2,
+                                                  int c3) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        :
+        : "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N bulk groups of this thread have finished READING their smem source
+template <int N>
+__device__ __forceinline__ void tma_wait_group_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_wait_group() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------------
@@ -353,6 +376,9 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a
 // host: tensor-map encoding through the driver entry point (no link-time libcuda dependency)
 // ----------------------------------------------------------------------------------------------
 // dims/strides innermost-first, strides in BYTES for dims 1..rank-1 (dim 0 is contiguous).
+// same, element type bf16 (is_f32 = 0) or fp32 (is_f32 = 1); 128B swizzle, so box[0] * element size must be 128 bytes
+int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, int is_f32);
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box);
 
