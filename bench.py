@@ -196,6 +196,9 @@ def main() -> None:
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--breakdown", default="", help="write a per-call-site breakdown of tensor-core time to this file")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
+    ap.add_argument("--ncu-sample", type=int, default=0,
+                    help="run under `ncu --profile-from-start off`: after the warm-up, ONE eager step with every N-th "
+                         "tensor-core launch inside a profiler range, then exit (feeds roofline.traffic)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -230,7 +233,7 @@ def main() -> None:
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
     def eager_step(batch: dict, read_loss: bool) -> float:
-        ops.invalidate_weight_cache()  # a real loop updates the fp32 weights every step: re-derive the bf16 copies
+        ops.refresh_weight_copies(force=True)  # a real loop updates the fp32 weights every step: re-derive the bf16 copies
         reducer.zero_grad()
         loss = eng.training_step(dict(batch))
         loss.backward()
@@ -241,6 +244,15 @@ def main() -> None:
     for _ in range(2):
         eager_step(resident, False)
     torch.cuda.synchronize()
+    if args.ncu_sample > 0:
+        ops.NCU_SAMPLE = args.ncu_sample
+        eager_step(resident, False)
+        torch.cuda.synchronize()
+        ops.NCU_SAMPLE = 0
+        out = Path(os.environ.get("NK_NCU_SHAPES", "gpurun_out/gemm_traffic_shapes.json"))
+        out.parent.mkdir(parents=True, exist_ok=True)
+        out.write_text(json.dumps({"batch_per_gpu": B, "every": args.ncu_sample, "launches": ops.NCU_SAMPLE_LOG}))
+        return
     # per-kernel roofline of the dominant kernel (gemm_tc_kernel): CUDA events around every launch of one extra step
     pk = peaks()
     prof_raw = None
@@ -341,9 +353,15 @@ def main() -> None:
     if prof_raw is not None:
         t_ms, fl, nrec = prof_raw
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+        traffic, traffic_src = None, None
+        tfiles = sorted((ROOT / "profiles").glob("*gemm_traffic*.json"))
+        if tfiles:  # committed summary of the ncu DRAM-byte sample of this kernel (tools/ncu_gemm_traffic.py)
+            td = json.loads(tfiles[-1].read_text())
+            traffic, traffic_src = td.get("dram_bytes_per_launch"), f"profiles/{tfiles[-1].name}: {td.get('source')}"
         roof = {"kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "bound": "tensor", "achieved": ach,
                 "peak": pk["tflops"], "peak_source": pk["src"] + " sustained bf16", "unit": "TFLOP/s",
-                "frac": ach / pk["tflops"], "traffic": None, "launches": nrec,
+                "frac": ach / pk["tflops"], "traffic": traffic, "traffic_unit": "bytes/launch (DRAM read+write, ncu)",
+                "traffic_source": traffic_src, "launches": nrec,
                 "share_of_step": t_ms / (ms_dev / args.steps) if ms_dev > 0 else None,
                 "alg_tflop_per_step": fl / 1e12,
                 "how": "CUDA events around every gemm_tc launch of one eagerly issued step (same kernels as the graph)"}

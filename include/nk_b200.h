@@ -164,6 +164,10 @@ int nk_silu_fwd(const void* x, void* y, int64_t n, nk_stream_t stream);
 int nk_silu_bwd(const void* x, const void* dy, void* dx, int64_t n, nk_stream_t stream);
 int nk_add(const void* a, const void* b, void* y, int64_t n, nk_stream_t stream);
 int nk_cast_f32_bf16(const float* x, void* y, int64_t n, nk_stream_t stream);
+/* the per-step fp32 -> bf16 refresh of every matmul weight in ONE launch (the reference gets the same effect from
+ * torch.autocast's per-call weight casts, models/diffusion.py:232 / trainer precision "bf16-mixed").  spans_dev: device
+ * array of n_spans records {const float* src; bf16* dst; int64 n} (24 bytes each); one thread block per span. */
+int nk_cast_f32_bf16_multi(const void* spans_dev, int n_spans, nk_stream_t stream);
 int nk_cast_bf16_f32(const void* x, float* y, int64_t n, int accumulate, nk_stream_t stream);
 /* copy C channels of every pixel between NHWC buffers with different pixel strides (skip concat / split:
  * modules/diffusion/openaimodel.py:836) */

@@ -240,6 +240,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
         for (int i = 0; i < HD; ++i) o[i] = 0.f;
         float m_run = -INFINITY;  // running max of raw scores
         float l_run = 0.f;
+        // o / l_run lag one tile behind: at tile j they are expressed relative to max m_{j-2}; folding in tile j-1's
+        // partial product (computed relative to m_{j-1}) is then ONE fma per element with alpha_{j-1} = 2^(m_{j-2}-m_{j-1})
+        float alpha_prev = 0.f, l_prev = 0.f;
         for (int j = 0; j < T; ++j) {
             mbar_wait(s_full, j & 1u, 30u);
             tc_fence_after();
@@ -252,8 +255,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
             const float m_new = fmaxf(m_run, m_tile);
             const float alpha = exp2f((m_run - m_new) * g.scale_log2);  // 0 on the first tile
             const float mb = m_new * g.scale_log2;
-            // fold in the previous tile's partial product and rescale to the new max; its completion also means the
-            // tensor pipe is done reading the P buffer, which is rewritten next
+            // fold in the previous tile's partial product; its completion also means the tensor pipe is done reading
+            // the P buffer, which is rewritten next
             if (j > 0) {
                 mbar_wait(o_full, (j - 1) & 1u, 31u);
                 tc_fence_after();
@@ -264,16 +267,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                     tc_ld32(o_addr + static_cast<uint32_t>(c * 32), raw);
                     tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + __uint_as_float(raw[i])) * alpha;
+                    for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(raw[i]));
                 }
+                l_run = fmaf(l_run, alpha_prev, l_prev);
             }
             uint8_t* pbuf = smem + SM_P;
-            const float l_tile = tail ? tile_probs<true>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r)
-                                      : tile_probs<false>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r);
+            l_prev = tail ? tile_probs<true>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r)
+                          : tile_probs<false>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(p_full);
-            l_run = l_run * alpha + l_tile;
+            alpha_prev = alpha;
             m_run = m_new;
         }
         // last partial product
@@ -287,8 +291,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                 tc_ld32(o_addr + static_cast<uint32_t>(c * 32), raw);
                 tc_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(raw[i]);
+                for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(raw[i]));
             }
+            l_run = fmaf(l_run, alpha_prev, l_prev);
         }
         const int q = q0 + r;
         if (q < g.Nq) {
@@ -536,7 +541,7 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __gr
             const int q = i * BQ + r;
             const bool valid = q < g.Nq;
             const float lse2 = lse_next * 1.4426950408889634f;
-            const float dlt = dlt_next;
+            const float dlt_s = dlt_next * g.scale;  // dS = P * (dP - delta) * scale = P * fma(dP, scale, -delta*scale)
             {  // prefetch the next tile's row statistics: their L2 latency hides behind this tile
                 const int qn = q + BQ;
                 const bool vn = (i + 1 < Tq) && (qn < g.Nq);
@@ -552,15 +557,7 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __gr
             tc_ld32(lane_addr + TM_S + static_cast<uint32_t>(col0 + 32), rb);
             if (i > 0) mbar_wait(dv_done, static_cast<uint32_t>((i - 1) & 1), 63u);  // dV_{i-1} no longer reads P
             tc_wait_ld();
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                float p[32];
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float sraw = __uint_as_float(cc ? rb[k] : ra[k]);
-                    const float e = exp2f(fmaf(sraw, g.scale_log2, -lse2));
-                    p[k] = (nomask || (valid && (col0 + cc * 32 + k < kv_valid))) ? e : 0.f;
-                }
+            auto emit_p = [&](int cc, const float (&p)[32]) {
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
                     uint4 w;
@@ -569,6 +566,27 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __gr
                     w.z = pack_bf16x2(p[8 * qq + 4], p[8 * qq + 5]);
                     w.w = pack_bf16x2(p[8 * qq + 6], p[8 * qq + 7]);
                     st_shared_v4(p_row + static_cast<uint32_t>(((cc * 4 + qq) ^ (r & 7)) * 16), w);
+                }
+            };
+            if (nomask) {  // warp-uniform: no per-element predicate in the common case
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    float p[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        p[k] = exp2f(fmaf(__uint_as_float(cc ? rb[k] : ra[k]), g.scale_log2, -lse2));
+                    emit_p(cc, p);
+                }
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    float p[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        const float e = exp2f(fmaf(__uint_as_float(cc ? rb[k] : ra[k]), g.scale_log2, -lse2));
+                        p[k] = (valid && (col0 + cc * 32 + k < kv_valid)) ? e : 0.f;
+                    }
+                    emit_p(cc, p);
                 }
             }
             fence_proxy_async_smem();
@@ -595,7 +613,7 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __gr
                     const float dp0 = __uint_as_float(col < 32 ? ra[col & 31] : rb[col & 31]);
                     const float dp1 = __uint_as_float(col + 1 < 32 ? ra[(col + 1) & 31] : rb[(col + 1) & 31]);
                     const float2 pf = unpack_bf16x2(pin[e]);
-                    dout[e] = pack_bf16x2(pf.x * (dp0 - dlt) * g.scale, pf.y * (dp1 - dlt) * g.scale);  // P is 0 where masked
+                    dout[e] = pack_bf16x2(pf.x * fmaf(dp0, g.scale, -dlt_s), pf.y * fmaf(dp1, g.scale, -dlt_s));  // P is 0 where masked
                 }
                 st_shared_v4(ds_row + static_cast<uint32_t>((j ^ (r & 7)) * 16), make_uint4(dout[0], dout[1], dout[2], dout[3]));
             }

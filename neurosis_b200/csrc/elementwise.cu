@@ -118,10 +118,37 @@ __global__ void ew_vec_add_kernel(const bf16* __restrict__ a, const bf16* __rest
     }
 }
 
+// 8 elements per thread (two 16-byte loads, one 16-byte store) when both pointers are 16-byte aligned
+__device__ __forceinline__ void cast8(const float* __restrict__ x, bf16* __restrict__ y) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 1);
+    uint4 q;
+    q.x = pack_bf16x2(a.x, a.y);
+    q.y = pack_bf16x2(a.z, a.w);
+    q.z = pack_bf16x2(b.x, b.y);
+    q.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(y) = q;
+}
+__device__ __forceinline__ void cast_span(const float* __restrict__ x, bf16* __restrict__ y, long long n, long long tid,
+                                          long long nthreads) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
+    const long long n8 = vec ? (n >> 3) : 0;
+    for (long long i = tid; i < n8; i += nthreads) cast8(x + 8 * i, y + 8 * i);
+    for (long long i = 8 * n8 + tid; i < n; i += nthreads) y[i] = __float2bfloat16(x[i]);
+}
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-        y[i] = __float2bfloat16(x[i]);
+    cast_span(x, y, n, blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x,
+              static_cast<long long>(gridDim.x) * blockDim.x);
+}
+// many tensors, one launch: block b converts spans[b] = {src, dst, n} (the host cuts every tensor into spans)
+struct CastSpan {
+    const float* src;
+    bf16* dst;
+    long long n;
+};
+__global__ void cast_f32_bf16_multi_kernel(const CastSpan* __restrict__ spans) {
+    const CastSpan sp = spans[blockIdx.x];
+    cast_span(sp.src, sp.dst, sp.n, threadIdx.x, blockDim.x);
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n, int accumulate) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -540,7 +567,15 @@ int nk_add(const void* a, const void* b, void* y, int64_t n, nk_stream_t stream)
     return NK_OK;
 }
 int nk_cast_f32_bf16(const float* x, void* y, int64_t n, nk_stream_t stream) {
-    cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, BF(y), n);
+    cast_f32_bf16_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, ST(stream)>>>(x, BF(y), n);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_cast_f32_bf16_multi(const void* spans_dev, int n_spans, nk_stream_t stream) {
+    NK_REQUIRE(n_spans >= 0 && (reinterpret_cast<uintptr_t>(spans_dev) & 7u) == 0, NK_ERR_SHAPE, "cast_multi: span table");
+    cudaStream_t st = ST(stream);
+    if (n_spans == 0) return NK_OK;
+    cast_f32_bf16_multi_kernel<<<n_spans, 256, 0, st>>>(static_cast<const CastSpan*>(spans_dev));
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }

@@ -85,17 +85,24 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long pix_stride
     }
 }
 
-// finalize: grid nimg, block G threads
+// finalize: grid nimg, block 8*G threads: 8 chunk lanes per group, combined with shuffles
 __global__ void gn_finalize_kernel(const float2* __restrict__ partial, float* __restrict__ mean,
                                    float* __restrict__ rstd, int chunks, int G, float inv_count, float eps) {
-    const int img = blockIdx.x, g = threadIdx.x;
-    if (g >= G) return;
+    const int img = blockIdx.x, g = threadIdx.x >> 3, ln = threadIdx.x & 7;
     double a = 0.0, b = 0.0;
-    for (int c = 0; c < chunks; ++c) {
-        const float2 p = partial[(static_cast<long long>(img) * chunks + c) * G + g];
-        a += p.x;
-        b += p.y;
+    if (g < G) {
+        for (int c = ln; c < chunks; c += 8) {
+            const float2 p = partial[(static_cast<long long>(img) * chunks + c) * G + g];
+            a += p.x;
+            b += p.y;
+        }
     }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (g >= G || ln != 0) return;
     const double m = a * inv_count;
     double var = b * inv_count - m * m;
     if (var < 0.0) var = 0.0;
@@ -201,32 +208,46 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ dy, long long dy_st
         partial[(static_cast<long long>(img) * gridDim.x + chunk) * C + c] = make_float2(s_A[c], s_B[c]);
 }
 
-// pass 2: grid nimg.  Reduces chunks; per-group s1,s2 -> coef[img][g] ; per-image channel sums -> chan[img][c]
-__global__ void gn_bwd_finalize_kernel(const float2* __restrict__ partial, const float* __restrict__ gamma,
-                                       float2* __restrict__ chan, float2* __restrict__ coef, int chunks, int C,
-                                       int G) {
-    extern __shared__ float sm[];  // A[C], B[C]
-    float* s_A = sm;
-    float* s_B = sm + C;
-    const int img = blockIdx.x;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a = 0.f, b = 0.f;
-        for (int k = 0; k < chunks; ++k) {
-            const float2 p = partial[(static_cast<long long>(img) * chunks + k) * C + c];
+// pass 2: grid (G, nimg), 256 threads = (channel of the group) x (chunk lane).  Reduces the chunk partials of one
+// group of one image: per-channel sums -> chan[img][c], per-group s1,s2 -> coef[img][g]
+__global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float2* __restrict__ partial,
+                                                              const float* __restrict__ gamma,
+                                                              float2* __restrict__ chan, float2* __restrict__ coef,
+                                                              int chunks, int C, int G) {
+    __shared__ float s_A[256], s_B[256];
+    const int g = blockIdx.x, img = blockIdx.y;
+    const int cpg = C / G;       // <= 256
+    const int L = 256 / cpg;     // chunk lanes
+    const int cl = threadIdx.x % cpg, ln = threadIdx.x / cpg;
+    float a = 0.f, b = 0.f;
+    if (ln < L) {
+        const float2* base = partial + static_cast<long long>(img) * chunks * C + g * cpg + cl;
+        for (int k = ln; k < chunks; k += L) {
+            const float2 p = base[static_cast<long long>(k) * C];
             a += p.x;
             b += p.y;
         }
-        s_A[c] = a;
-        s_B[c] = b;
+    }
+    s_A[threadIdx.x] = a;
+    s_B[threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x < cpg) {
+        for (int l = 1; l < L; ++l) {
+            a += s_A[l * cpg + threadIdx.x];
+            b += s_B[l * cpg + threadIdx.x];
+        }
+        const int c = g * cpg + threadIdx.x;
         chan[static_cast<long long>(img) * C + c] = make_float2(a, b);
+        const float ga = gamma[c];
+        s_A[threadIdx.x] = ga * a;
+        s_B[threadIdx.x] = ga * b;
     }
     __syncthreads();
-    const int cpg = C / G;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    if (threadIdx.x == 0) {
         float s1 = 0.f, s2 = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-            s1 += gamma[c] * s_A[c];
-            s2 += gamma[c] * s_B[c];
+        for (int c = 0; c < cpg; ++c) {
+            s1 += s_A[c];
+            s2 += s_B[c];
         }
         coef[img * G + g] = make_float2(s1, s2);
     }
@@ -369,23 +390,18 @@ __global__ void ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, bf16* _
     }
 }
 
-// dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)); dgamma += sum dy*xhat; dbeta += sum dy
-// One warp per row.  x and dy stay packed (bf16) in registers; the per-column parameter gradients are accumulated
-// with conflict-free shared-memory atomics (layout [j][v]: consecutive lanes -> consecutive banks) instead of
-// per-thread register accumulators, which keeps the kernel at ~80 registers so enough rows are in flight to
-// cover HBM latency.
+// LayerNorm backward, two streaming kernels (both HBM-bound, no cross-thread accumulators in the hot loop):
+//   ln_bwd_dx_kernel     one warp per row:  dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))
+//   ln_bwd_param_kernel  thread = 8 columns x a row lane, walks a row chunk:  dgamma += sum dy*xhat ; dbeta += sum dy
+// The second pass re-reads x and dy (mostly from L2: the first pass just streamed them), which costs less than any
+// scheme that carries 2*C accumulators per warp through the dx loop (registers: occupancy; shared atomics: CAS loops).
 template <int MAXV>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ x,
-                                                     long long ldx, bf16* __restrict__ dx, long long lddx,
-                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                     const float* __restrict__ rstd, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, int rows, int C) {
-    extern __shared__ float sm[];  // dgamma[8][V], dbeta[8][V]
+__global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const bf16* __restrict__ dy, long long lddy,
+                                                        const bf16* __restrict__ x, long long ldx, bf16* __restrict__ dx,
+                                                        long long lddx, const float* __restrict__ gamma,
+                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                        int rows, int C) {
     const int V = C / 8;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
-    float* s_dg = sm;
-    float* s_db = sm + C;
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); row < rows;
@@ -399,7 +415,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
                 pd[i] = __ldg(reinterpret_cast<const uint4*>(dy + row * lddy + v * 8));
             }
         }
-        const float m = mean[row], r = rstd[row];
+        const float m = __ldg(mean + row), r = __ldg(rstd + row);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
@@ -414,14 +430,9 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
                 for (int e = 0; e < 4; ++e) {
                     const float2 fx = unpack_bf16x2(wx[e]);
                     const float2 fd = unpack_bf16x2(wd[e]);
-                    const float xh0 = (fx.x - m) * r, xh1 = (fx.y - m) * r;
                     const float gd0 = fd.x * g[2 * e], gd1 = fd.y * g[2 * e + 1];
                     s1 += gd0 + gd1;
-                    s2 += gd0 * xh0 + gd1 * xh1;
-                    atomicAdd(&s_dg[(2 * e) * V + v], fd.x * xh0);
-                    atomicAdd(&s_dg[(2 * e + 1) * V + v], fd.y * xh1);
-                    atomicAdd(&s_db[(2 * e) * V + v], fd.x);
-                    atomicAdd(&s_db[(2 * e + 1) * V + v], fd.y);
+                    s2 = fmaf(gd0, (fx.x - m) * r, fmaf(gd1, (fx.y - m) * r, s2));
                 }
             }
         }
@@ -448,11 +459,73 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
             }
         }
     }
+}
+
+// block = 32 column octets (256 columns) x 8 row lanes; grid (column blocks, row chunks); 2 rows in flight per thread
+__global__ void __launch_bounds__(256) ln_bwd_param_kernel(const bf16* __restrict__ dy, long long lddy,
+                                                           const bf16* __restrict__ x, long long ldx,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
+                                                           int C, int row_chunks) {
+    const int cv = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rl = threadIdx.x >> 5;
+    const int rows_per_chunk = (rows + row_chunks - 1) / row_chunks;
+    const int r0 = blockIdx.y * rows_per_chunk;
+    const int r1 = min(rows, r0 + rows_per_chunk);
+    float ag[8], ab[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[j] = ab[j] = 0.f;
+    if (8 * cv < C) {
+        const bf16* xb = x + 8 * cv;
+        const bf16* db = dy + 8 * cv;
+        auto acc_row = [&](const uint4& qx, const uint4& qd, float m, float r) {
+            const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w};
+            const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 fx = unpack_bf16x2(wx[e]);
+                const float2 fd = unpack_bf16x2(wd[e]);
+                ag[2 * e] = fmaf(fd.x, (fx.x - m) * r, ag[2 * e]);
+                ag[2 * e + 1] = fmaf(fd.y, (fx.y - m) * r, ag[2 * e + 1]);
+                ab[2 * e] += fd.x;
+                ab[2 * e + 1] += fd.y;
+            }
+        };
+        int row = r0 + rl;
+        for (; row + 8 < r1; row += 16) {
+            const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(row) * ldx));
+            const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(db + static_cast<long long>(row) * lddy));
+            const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(row + 8) * ldx));
+            const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(db + static_cast<long long>(row + 8) * lddy));
+            const float m0 = __ldg(mean + row), q0 = __ldg(rstd + row);
+            const float m1 = __ldg(mean + row + 8), q1 = __ldg(rstd + row + 8);
+            acc_row(x0, d0, m0, q0);
+            acc_row(x1, d1, m1, q1);
+        }
+        for (; row < r1; row += 8) {
+            const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(row) * ldx));
+            const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(db + static_cast<long long>(row) * lddy));
+            acc_row(x0, d0, __ldg(mean + row), __ldg(rstd + row));
+        }
+    }
+    __shared__ float sg[8][32][9], sb[8][32][9];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sg[rl][threadIdx.x & 31][j] = ag[j];
+        sb[rl][threadIdx.x & 31][j] = ab[j];
+    }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int v = c >> 3, j = c & 7;
-        atomicAdd(dgamma + c, s_dg[j * V + v]);
-        atomicAdd(dbeta + c, s_db[j * V + v]);
+    const int c_local = threadIdx.x;
+    const int c = blockIdx.x * 256 + c_local;
+    if (c < C) {
+        float tg = 0.f, tb = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            tg += sg[k][c_local >> 3][c_local & 7];
+            tb += sb[k][c_local >> 3][c_local & 7];
+        }
+        atomicAdd(dgamma + c, tg);
+        atomicAdd(dbeta + c, tb);
     }
 }
 
@@ -484,7 +557,7 @@ int nk_groupnorm_fwd(const void* x, int64_t x_pix_stride, const float* gamma, co
     float2* partial = static_cast<float2*>(workspace);
     gn_stats_kernel<<<dim3(p.chunks, nimg), p.threads, 2 * C * sizeof(float), st>>>(
         static_cast<const bf16*>(x), x_pix_stride, partial, HW, C, G, p.V, p.ppb, p.pix_per_chunk);
-    gn_finalize_kernel<<<nimg, ((G + 31) / 32) * 32, 0, st>>>(partial, mean, rstd, p.chunks, G,
+    gn_finalize_kernel<<<nimg, ((8 * G + 31) / 32) * 32, 0, st>>>(partial, mean, rstd, p.chunks, G,
                                                              1.f / (static_cast<float>(HW) * (C / G)), eps);
     gn_apply_kernel<<<dim3(p.chunks, nimg), p.threads, 2 * C * sizeof(float), st>>>(
         static_cast<const bf16*>(x), x_pix_stride, static_cast<bf16*>(y), y_pix_stride, gamma, beta, mean, rstd, HW,
@@ -497,7 +570,7 @@ int nk_groupnorm_bwd(const void* dy, int64_t dy_pix_stride, const void* x, int64
                      const float* gamma, const float* beta, const float* mean, const float* rstd, void* dx,
                      int64_t dx_pix_stride, float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
                      int nimg, int HW, int C, int G, int silu, nk_stream_t stream) {
-    NK_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 4096, NK_ERR_SHAPE, "groupnorm: C=%d G=%d", C, G);
+    NK_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 4096 && C / G <= 256, NK_ERR_SHAPE, "groupnorm: C=%d G=%d", C, G);
     NK_REQUIRE(workspace_bytes >= nk_groupnorm_workspace_bytes(nimg, HW, C, G), NK_ERR_WORKSPACE, "groupnorm workspace");
     const GnPlan p = gn_plan(nimg, HW, C);
     cudaStream_t st = ::nk::enter(stream);
@@ -507,7 +580,7 @@ int nk_groupnorm_bwd(const void* dy, int64_t dy_pix_stride, const void* x, int64
     gn_bwd_stats_kernel<<<dim3(p.chunks, nimg), p.threads, 2 * C * sizeof(float), st>>>(
         static_cast<const bf16*>(dy), dy_pix_stride, static_cast<const bf16*>(x), x_pix_stride, gamma, beta, mean,
         rstd, partial, HW, C, G, p.V, p.ppb, p.pix_per_chunk, silu);
-    gn_bwd_finalize_kernel<<<nimg, 256, 2 * C * sizeof(float), st>>>(partial, gamma, chan, coef, p.chunks, C, G);
+    gn_bwd_finalize_kernel<<<dim3(G, nimg), 256, 0, st>>>(partial, gamma, chan, coef, p.chunks, C, G);
     if (dgamma && dbeta) gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, st>>>(chan, dgamma, dbeta, nimg, C);
     gn_bwd_apply_kernel<<<dim3(p.chunks, nimg), p.threads, 0, st>>>(
         static_cast<const bf16*>(dy), dy_pix_stride, static_cast<const bf16*>(x), x_pix_stride,
@@ -540,20 +613,28 @@ int nk_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float
 int nk_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
                      const float* mean, const float* rstd, void* dx, int64_t lddx, float* dgamma, float* dbeta,
                      int rows, int C, nk_stream_t stream) {
-    NK_REQUIRE(C % 8 == 0 && C <= 1280, NK_ERR_SHAPE, "layernorm bwd: C=%d", C);
+    NK_REQUIRE(C % 8 == 0 && C <= 2048, NK_ERR_SHAPE, "layernorm bwd: C=%d", C);
     cudaStream_t st = ::nk::enter(stream);
     const int wpb = 8;
-    const int grid = static_cast<int>(std::min<long long>((rows + wpb - 1) / wpb, 148LL * 4));
+    const int grid = static_cast<int>(std::min<long long>((rows + wpb - 1) / wpb, 148LL * 8));
     const int V = C / 8;
-    const size_t smem = 2 * C * sizeof(float);
+    const bf16* dyp = static_cast<const bf16*>(dy);
+    const bf16* xp = static_cast<const bf16*>(x);
     if (V <= 64)
-        ln_bwd_kernel<2><<<grid, wpb * 32, smem, st>>>(static_cast<const bf16*>(dy), lddy, static_cast<const bf16*>(x),
-                                                       ldx, static_cast<bf16*>(dx), lddx, gamma, mean, rstd, dgamma,
-                                                       dbeta, rows, C);
+        ln_bwd_dx_kernel<2><<<grid, wpb * 32, 0, st>>>(dyp, lddy, xp, ldx, static_cast<bf16*>(dx), lddx, gamma, mean,
+                                                       rstd, rows, C);
+    else if (V <= 160)
+        ln_bwd_dx_kernel<5><<<grid, wpb * 32, 0, st>>>(dyp, lddy, xp, ldx, static_cast<bf16*>(dx), lddx, gamma, mean,
+                                                       rstd, rows, C);
     else
-        ln_bwd_kernel<5><<<grid, wpb * 32, smem, st>>>(static_cast<const bf16*>(dy), lddy, static_cast<const bf16*>(x),
-                                                       ldx, static_cast<bf16*>(dx), lddx, gamma, mean, rstd, dgamma,
-                                                       dbeta, rows, C);
+        ln_bwd_dx_kernel<8><<<grid, wpb * 32, 0, st>>>(dyp, lddy, xp, ldx, static_cast<bf16*>(dx), lddx, gamma, mean,
+                                                       rstd, rows, C);
+    if (dgamma && dbeta) {
+        const int col_blocks = (C + 255) / 256;
+        const int row_chunks = std::max(1, std::min(rows / 64, (148 * 6) / col_blocks));
+        ln_bwd_param_kernel<<<dim3(col_blocks, row_chunks), 256, 0, st>>>(dyp, lddy, xp, ldx, mean, rstd, dgamma, dbeta,
+                                                                          rows, C, row_chunks);
+    }
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }

@@ -42,7 +42,9 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         torch.cuda.empty_cache()  # the eager warm-up's activations must not stay cached next to the graph's pool
-        ops.invalidate_weight_cache()  # capture the fp32 -> bf16 / packed weight refresh: replayed every step
+        # the fp32 -> bf16 / packed weight refresh is the first thing `_core` does, so it is captured and replayed every
+        # step; run it once here so its span table is built outside the capture
+        ops.refresh_weight_copies(force=True)
         l0 = ops.LAUNCHES
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
@@ -51,6 +53,7 @@ class GraphedTrainStep:
 
     def _core(self) -> None:
         eng = self.engine
+        ops.refresh_weight_copies(force=True)  # the optimizer changed the fp32 weights since the last step
         self.reducer.zero_grad()
         z = eng.encode_first_stage(self.image) if eng.first_stage_model is not None else self.image
         cond = {"crossattn": self.crossattn}

@@ -76,8 +76,36 @@ def _grad_sink(weight: Tensor):
     return buf.view(weight.shape), base
 
 
+def _grad_sink_pair(a: Optional[Tensor], b: Optional[Tensor]):
+    """sinks of two parameters at once (norm scale + shift): ((buf_a, buf_b), (base_a, base_b)) or (None, None)."""
+    if a is None or b is None:
+        return None, None
+    ba, pa = _grad_sink(a)
+    bb, pb = _grad_sink(b)
+    if ba is None or bb is None:
+        return None, None
+    return (ba, bb), (pa, pb)
+
+
+NCU_SAMPLE = 0          # > 0: every NCU_SAMPLE-th tensor-core launch runs inside a cudaProfilerStart/Stop range
+NCU_SAMPLE_LOG: list = []  # (what, small integer arguments) of the sampled launches, in launch order
+_ncu_seen = 0
+
+
 def _tc(rc_fn, what: str, flops: float, *args) -> None:
-    """call a tensor-core GEMM entry point; optionally bracket it with CUDA events for the roofline report."""
+    """call a tensor-core GEMM entry point; optionally bracket it with CUDA events for the roofline report, or (for
+    `ncu --profile-from-start off`) put a strided sample of the launches inside profiler ranges."""
+    global _ncu_seen
+    if NCU_SAMPLE > 0:
+        _ncu_seen += 1
+        if _ncu_seen % NCU_SAMPLE == 0:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            check(rc_fn(*args), what)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            NCU_SAMPLE_LOG.append((what, flops, [a for a in args if isinstance(a, int) and 0 < a < (1 << 24)]))
+            return
     if PROFILE_GEMM is None:
         check(rc_fn(*args), what)
         return
@@ -132,6 +160,59 @@ def invalidate_weight_cache() -> None:
     whose optimizer updates the fp32 parameters in place gets this for free through the version check; callers
     that capture CUDA graphs call it before capture so the casts are part of the graph and replayed every step."""
     _wcache.clear()
+    _mirror.clear()
+
+
+class _WeightMirror:
+    """Persistent bf16 copies of every parameter that `bf16_weight` has served, refreshed by ONE kernel
+    (nk_cast_f32_bf16_multi) instead of one cast launch per parameter: ~750 linear weights per SDXL step."""
+    SPAN = 1 << 18  # elements per thread block
+
+    def __init__(self):
+        self.clear()
+
+    def clear(self) -> None:
+        self.params: dict[int, tuple] = {}  # id(base) -> (weakref(base), bf16 copy)
+        self.table = None
+        self.table_key = None
+
+    def register(self, base: Tensor, copy: Tensor) -> None:
+        self.params[id(base)] = (weakref.ref(base), copy)
+        self.table = None
+
+    def refresh(self) -> int:
+        """re-derive every registered copy from the current fp32 values; returns the number of parameters."""
+        live = [(r(), c) for r, c in self.params.values() if r() is not None]
+        if not live:
+            return 0
+        key = tuple((b.data_ptr(), c.data_ptr(), b.numel()) for b, c in live)
+        if self.table is None or self.table_key != key:
+            rows = []
+            for src, dst, n in key:
+                for off in range(0, n, self.SPAN):
+                    rows.append((src + 4 * off, dst + 2 * off, min(self.SPAN, n - off)))
+            self.table = torch.tensor(rows, dtype=torch.int64).to(live[0][0].device)
+            self.table_key = key
+        check(lib.nk_cast_f32_bf16_multi(self.table.data_ptr(), self.table.shape[0], _stream()), "cast_f32_bf16_multi")
+        _count()
+        for b, c in live:
+            d = _cache_for(b)  # a fresh dict when the parameter changed since the last copy
+            d["bf16"] = c
+        return len(live)
+
+
+_mirror = _WeightMirror()
+
+
+def refresh_weight_copies(force: bool = False) -> None:
+    """Start-of-step hook of a training loop: re-derive the kernels' bf16 weight copies after the optimizer updated
+    the fp32 parameters.  Linear weights go through one multi-tensor launch; packed convolution weights are re-packed
+    lazily by their first use.  `force` treats every parameter as changed (benchmarks without an optimizer)."""
+    if force:
+        for ent in list(_wcache.values()):
+            ent[1].pop("packed", None)
+            ent[1].pop("bf16", None)
+    _mirror.refresh()
 
 
 def cast_bf16(x: Tensor) -> Tensor:
@@ -153,6 +234,8 @@ def bf16_weight(p: Tensor) -> Tensor:
         base = p._base if p._base is not None else p
         w = cast_bf16(base.detach())
         d["bf16"] = w
+        if base.dtype == F32 and base.is_contiguous():
+            _mirror.register(base, w)
     return w.view(p.shape) if w.shape != p.shape else w
 
 
@@ -244,15 +327,17 @@ def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     return dw
 
 
-def colsum(x: Tensor, groups: int = 1) -> Tensor:
-    """fp32 [groups, C] column sums of a bf16 [groups*rows, C] matrix."""
+def colsum(x: Tensor, groups: int = 1, out: Optional[Tensor] = None) -> Tensor:
+    """fp32 [groups, C] column sums of a bf16 [groups*rows, C] matrix; with `out` given the sums are added to it."""
     C = x.shape[-1]
     x2 = x.reshape(-1, C)
     if x2.stride(-1) != 1:
         x2 = x2.contiguous()
     rows = x2.shape[0] // groups
-    out = torch.empty((groups, C), dtype=F32, device=x.device)
-    check(lib.nk_colsum(x2.data_ptr(), x2.stride(0), out.data_ptr(), groups, rows, C, 0, _stream()), "colsum")
+    acc = out is not None
+    if not acc:
+        out = torch.empty((groups, C), dtype=F32, device=x.device)
+    check(lib.nk_colsum(x2.data_ptr(), x2.stride(0), out.data_ptr(), groups, rows, C, int(acc), _stream()), "colsum")
     _count()
     return out
 
@@ -331,11 +416,15 @@ def groupnorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: floa
 
 
 def groupnorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, beta: Tensor, mean: Tensor, rstd: Tensor, groups: int,
-                  silu: bool):
+                  silu: bool, out: Optional[tuple] = None):
+    """`out` = (dgamma, dbeta) fp32 buffers the parameter gradients are ADDED to (gradient buckets)."""
     n, h, w_, c = x.shape
     dx = torch.empty_like(x)
-    dgamma = torch.zeros((c,), dtype=F32, device=x.device)
-    dbeta = torch.zeros((c,), dtype=F32, device=x.device)
+    if out is not None:
+        dgamma, dbeta = out
+    else:
+        dgamma = torch.zeros((c,), dtype=F32, device=x.device)
+        dbeta = torch.zeros((c,), dtype=F32, device=x.device)
     ws_bytes = lib.nk_groupnorm_workspace_bytes(n, h * w_, c, groups)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
     check(lib.nk_groupnorm_bwd(dy.data_ptr(), dy.stride(2), x.data_ptr(), x.stride(2), gamma.data_ptr(),
@@ -362,7 +451,8 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float):
     return y.view(x.shape), mean, rstd
 
 
-def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor):
+def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, out: Optional[tuple] = None):
+    """`out` = (dgamma, dbeta) fp32 buffers the parameter gradients are ADDED to (gradient buckets)."""
     c = x.shape[-1]
     x2 = x.reshape(-1, c)
     d2 = dy.reshape(-1, c)
@@ -372,12 +462,15 @@ def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tens
         d2 = d2.contiguous()
     rows = x2.shape[0]
     dx = torch.empty((rows, c), dtype=BF16, device=x.device)
-    dgamma = torch.zeros((c,), dtype=F32, device=x.device)
-    dbeta = torch.zeros((c,), dtype=F32, device=x.device)
+    if out is not None:
+        dgamma, dbeta = out
+    else:
+        dgamma = torch.zeros((c,), dtype=F32, device=x.device)
+        dbeta = torch.zeros((c,), dtype=F32, device=x.device)
     check(lib.nk_layernorm_bwd(d2.data_ptr(), d2.stride(0), x2.data_ptr(), x2.stride(0), gamma.data_ptr(),
                                mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), c, dgamma.data_ptr(), dbeta.data_ptr(),
                                rows, c, _stream()), "layernorm_bwd")
-    _count()
+    _count(2)
     return dx.view(x.shape), dgamma, dbeta
 
 
@@ -676,6 +769,7 @@ class LinearFn(torch.autograd.Function):
         y = linear_fwd(x, w, f32_param(bias), residual, out_f32)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        ctx.bias = bias
         ctx.has_res = residual is not None
         return y
 
@@ -695,7 +789,14 @@ class LinearFn(torch.autograd.Function):
                 GRAD_SINK.mark_ready(base)
             else:
                 dw = linear_wgrad(dy, x)
-        db = colsum(dy)[0] if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            buf, base = _grad_sink(ctx.bias)
+            if buf is not None:
+                colsum(dy, out=buf.view(1, -1))
+                GRAD_SINK.mark_ready(base)
+            else:
+                db = colsum(dy)[0]
         dres = dy.view(-1, dy.shape[-1]).view(dy.shape) if (ctx.has_res and ctx.needs_input_grad[3]) else None
         return dx, dw, db, dres, None
 
@@ -811,13 +912,19 @@ class GroupNormFn(torch.autograd.Function):
         y, mean, rstd = groupnorm_fwd(x, g, b, groups, eps, silu)
         ctx.save_for_backward(x, g, b, mean, rstd)
         ctx.cfg = (groups, silu)
+        ctx.params = (gamma, beta)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, g, b, mean, rstd = ctx.saved_tensors
         groups, silu = ctx.cfg
-        dx, dg, db = groupnorm_bwd(dy.contiguous(), x, g, b, mean, rstd, groups, silu)
+        bufs, bases = _grad_sink_pair(*ctx.params) if (ctx.needs_input_grad[1] and ctx.needs_input_grad[2]) else (None, None)
+        dx, dg, db = groupnorm_bwd(dy.contiguous(), x, g, b, mean, rstd, groups, silu, out=bufs)
+        if bufs is not None:
+            GRAD_SINK.mark_ready(bases[0])
+            GRAD_SINK.mark_ready(bases[1])
+            dg = db = None
         return dx, dg, db, None, None, None
 
 
@@ -831,12 +938,18 @@ class LayerNormFn(torch.autograd.Function):
         g, b = f32_param(gamma), f32_param(beta)
         y, mean, rstd = layernorm_fwd(x, g, b, eps)
         ctx.save_for_backward(x, g, mean, rstd)
+        ctx.params = (gamma, beta)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, g, mean, rstd = ctx.saved_tensors
-        dx, dg, db = layernorm_bwd(dy, x, g, mean, rstd)
+        bufs, bases = _grad_sink_pair(*ctx.params) if (ctx.needs_input_grad[1] and ctx.needs_input_grad[2]) else (None, None)
+        dx, dg, db = layernorm_bwd(dy, x, g, mean, rstd, out=bufs)
+        if bufs is not None:
+            GRAD_SINK.mark_ready(bases[0])
+            GRAD_SINK.mark_ready(bases[1])
+            dg = db = None
         return dx, dg, db, None
 
 

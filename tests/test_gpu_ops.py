@@ -152,7 +152,7 @@ def test_groupnorm_fwd_bwd(n, hw, c, silu, eps):
     assert rel(b.grad, br.grad) < 5e-3
 
 
-@pytest.mark.parametrize("rows,c", [(2048, 640), (1000, 1280), (77, 320)])
+@pytest.mark.parametrize("rows,c", [(2048, 640), (1000, 1280), (77, 320), (4099, 1280), (3, 2048)])
 def test_layernorm_fwd_bwd(rows, c):
     x = (rnd(rows, c) * 1.5 + 0.3).to(BF).requires_grad_(True)
     g = (1 + 0.2 * rnd(c, seed=1)).requires_grad_(True)
@@ -168,6 +168,46 @@ def test_layernorm_fwd_bwd(rows, c):
     assert rel(x.grad, xr.grad) < 8e-3
     assert rel(g.grad, gr.grad) < 5e-3
     assert rel(b.grad, br.grad) < 5e-3
+
+
+def test_norm_and_bias_gradients_into_grad_sink():
+    """dgamma / dbeta / bias gradients accumulated straight into pre-zeroed bucket views equal the returned ones."""
+    rows, c = 1500, 640
+    x, dy = (rnd(rows, c) * 1.3).to(BF), rnd(rows, c, seed=1).to(BF)
+    g = 1 + 0.2 * rnd(c, seed=2)
+    _, mean, rstd = ops.layernorm_fwd(x, g, torch.zeros_like(g), 1e-5)
+    dx0, dg0, db0 = ops.layernorm_bwd(dy, x, g, mean, rstd)
+    bg, bb = torch.zeros_like(dg0), torch.zeros_like(db0)
+    dx1, _, _ = ops.layernorm_bwd(dy, x, g, mean, rstd, out=(bg, bb))
+    assert torch.equal(dx0, dx1)
+    assert rel(bg, dg0) < 1e-5 and rel(bb, db0) < 1e-5
+    s0 = ops.colsum(dy)
+    s1 = torch.ones_like(s0)
+    ops.colsum(dy, out=s1)
+    assert rel(s1 - 1, s0) < 1e-5
+
+
+def test_refresh_weight_copies_tracks_parameter_updates():
+    """one multi-tensor launch re-derives every bf16 weight copy: after an in-place update, and under `force`."""
+    ops.invalidate_weight_cache()
+    ws = [torch.nn.Parameter(rnd(n, k, seed=i) * 0.1) for i, (n, k) in enumerate([(320, 640), (7, 13), (1280, 1280), (513, 1025)])]
+    for w in ws:
+        assert torch.equal(ops.bf16_weight(w), w.detach().to(BF))
+    with torch.no_grad():
+        for w in ws:
+            w.add_(0.25)  # bumps the version counter, like an optimizer step
+    l0 = ops.LAUNCHES
+    ops.refresh_weight_copies()
+    assert ops.LAUNCHES - l0 == 1
+    for w in ws:
+        assert torch.equal(ops.bf16_weight(w), w.detach().to(BF))
+    assert ops.LAUNCHES - l0 == 1  # served from the refreshed copies, no per-parameter cast
+    for w in ws:
+        w.data.mul_(2.0)  # no version bump: only `force` can see it
+    ops.refresh_weight_copies(force=True)
+    for w in ws:
+        assert torch.equal(ops.bf16_weight(w), w.detach().to(BF))
+    ops.invalidate_weight_cache()
 
 
 # ---------------------------------------------------------------- elementwise
