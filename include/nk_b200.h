@@ -104,15 +104,26 @@ int nk_conv2d_fwd(const void* x, int64_t x_pix_stride, const void* wp, const flo
                   const float* bias_img, const void* residual, int64_t r_pix_stride, void* y,
                   int64_t y_pix_stride, int nimg, int H, int W, int Cin, int Cout, int ksize,
                   nk_stream_t stream);
+/* 3x3 stride-2 convolution forward as implicit GEMM: output pixel (h, w) reads input (2h + ky - pad_t, 2w + kx - pad_l),
+ * out-of-image taps are zero (TMA boxes traversed with element stride 2, zero-filled outside the tensor).  pad 1/1 =
+ * openaimodel.Downsample (modules/diffusion/openaimodel.py:146-189); pad 0/0 with Ho = (H + 1 - 3) / 2 + 1 =
+ * model.Downsample's ConstantPad2d((0,1,0,1)) + conv k3 s2 p0 (modules/diffusion/model.py:65-82).  wp as for
+ * nk_conv2d_fwd; Cin is the physical (64-padded) channel count of x. */
+int nk_conv2d_stride2_fwd(const void* x, int64_t x_pix_stride, const void* wp, const float* bias, void* y,
+                          int64_t y_pix_stride, int nimg, int H, int W, int Cin, int Cout, int ksize, int pad_t,
+                          int pad_l, int Ho, int Wo, nk_stream_t stream);
 /* dw_packed[Cout, taps, Cin] (fp32) += sum_pixels dy[p,co] * x[p+tap,ci]   (always accumulates;
  * zero the buffer first).  Autograd of nn.Conv2d w.r.t. its weight. */
 int nk_conv2d_wgrad(const void* dy, int64_t dy_pix_stride, const void* x, int64_t x_pix_stride,
                     float* dw_packed, int nimg, int H, int W, int Cin, int Cout, int ksize,
                     nk_stream_t stream);
 
-/* Fused flash-style attention forward (tcgen05/TMEM), head_dim 64, no mask/dropout.
- * q,k,v: bf16 [B, N, H, 64] addressed by (batch_stride, row_stride, head offset h*64); they may be
- * column slices of a wider projection output.  o: bf16 [B, Nq, H, 64]; lse: fp32 [B, H, Nq] or NULL.
+/* Fused flash-style attention forward (tcgen05/TMEM), no mask/dropout, head_dim D = 64 or a multiple of 64 up to 512.
+ * q,k,v: bf16 [B, N, H, D] addressed by (batch_stride, row_stride, head offset h*D); they may be
+ * column slices of a wider projection output.  o: bf16 [B, Nq, H, D]; lse: fp32 [B, H, Nq] or NULL.
+ * D = 64: one CTA per 128 query rows and head, two CTAs per SM.  D > 64 (the single 512-wide head of the VAE
+ * mid-block attention, AttnBlock / MemoryEfficientAttnBlock, modules/diffusion/model.py:144-236):
+ * scores are accumulated in TMEM over the 64-wide chunks of D and each CTA produces one 64-wide chunk of o.
  * Replaces F.scaled_dot_product_attention / xformers memory_efficient_attention at
  * modules/attention.py:346-352,410-412. */
 int nk_attention_fwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride, const void* k,

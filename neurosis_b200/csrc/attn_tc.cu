@@ -324,6 +324,227 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
 
 
 // =================================================================================================
+// Wide-head forward (head_dim = 64 * NC, NC <= 8; the VAE mid-block attention is one head of 512).
+// S = Q K^T is accumulated in TMEM over the NC 64-wide chunks of the head dimension; the CTA owns ONE 64-wide chunk
+// of V / O (blockIdx.y = head * NC + v-chunk), so the online-softmax state is the same 64 registers per row as in
+// the head_dim-64 kernel.  The NC CTAs of a head recompute the same S: redundant tensor work (idle otherwise) instead
+// of the [Nq, Nk] fp32 score matrix in HBM that the materialised path needs.
+//   smem: Q resident (NC x 16 KB) | K chunk ring (2 x 16 KB) | V ring (2 x 16 KB) | P (32 KB)      (224 KB at NC = 8)
+//   TMEM: S double-buffered (2 x 128 columns) | O partial (64 columns)
+// =================================================================================================
+struct alignas(64) AttnWideDev {
+    CUtensorMap tmQ, tmK, tmV;  // dims {64, H*NC, N, B}: "chunk-heads"
+    bf16* O;
+    float* lse;
+    long long o_row_stride, o_batch_stride;
+    int Nq, Nk, H, B, NC;
+    float scale_log2, scale;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_wide_kernel(const __grid_constant__ AttnWideDev g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    const int NC = g.NC;
+    uint8_t* sm_q = smem;
+    uint8_t* sm_k = sm_q + NC * TILE_BYTES;
+    uint8_t* sm_v = sm_k + 2 * TILE_BYTES;
+    uint8_t* sm_p = sm_v + 2 * TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_p + 2 * TILE_BYTES);
+    uint64_t* q_full = bars;        // 1
+    uint64_t* k_full = bars + 1;    // 2
+    uint64_t* k_empty = bars + 3;   // 2
+    uint64_t* v_full = bars + 5;    // 2
+    uint64_t* v_empty = bars + 7;   // 2
+    uint64_t* s_full = bars + 9;    // 2
+    uint64_t* p_full = bars + 11;   // 1 (128 arrivals)
+    uint64_t* o_full = bars + 12;   // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BQ;
+    const int h = blockIdx.y / NC;
+    const int vc = blockIdx.y - h * NC;  // the V / O chunk of this CTA
+    const int b = blockIdx.z;
+    const int T = (g.Nk + BKV - 1) / BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&g.tmQ);
+        tma_prefetch_desc(&g.tmK);
+        tma_prefetch_desc(&g.tmV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
+            mbar_init(&s_full[s], 1);
+        }
+        mbar_init(p_full, 128);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t TM_S = 0, TM_O = 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, static_cast<uint32_t>(NC) * TILE_BYTES);
+            for (int c = 0; c < NC; ++c) tma_load_4d(&g.tmQ, q_full, sm_q + c * TILE_BYTES, 0, h * NC + c, q0, b);
+            int ks = 0;
+            uint32_t kph = 0;
+            for (int j = 0; j < T; ++j) {
+                for (int c = 0; c < NC; ++c) {
+                    mbar_wait(&k_empty[ks], kph ^ 1u, 10u + ks);
+                    mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
+                    tma_load_4d(&g.tmK, &k_full[ks], sm_k + ks * TILE_BYTES, 0, h * NC + c, j * BKV, b);
+                    if (++ks == 2) {
+                        ks = 0;
+                        kph ^= 1u;
+                    }
+                }
+                const int vs = j & 1;
+                mbar_wait(&v_empty[vs], ((j >> 1) & 1u) ^ 1u, 12u + vs);
+                mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
+                tma_load_4d(&g.tmV, &v_full[vs], sm_v + vs * TILE_BYTES, 0, h * NC + vc, j * BKV, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
+            const uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);
+            int ks = 0;
+            uint32_t kph = 0;
+            auto issue_s = [&](int j) {
+                const uint32_t d = tmem_base + TM_S + static_cast<uint32_t>((j & 1) * 128);
+                for (int c = 0; c < NC; ++c) {
+                    mbar_wait(&k_full[ks], kph, 22u);
+                    tc_fence_after();
+                    const uint64_t q_desc = make_smem_desc(smem_u32(sm_q + c * TILE_BYTES), 16u, 1024u);
+                    const uint64_t k_desc = make_smem_desc(smem_u32(sm_k + ks * TILE_BYTES), 16u, 1024u);
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k)
+                        tc_mma_ss(d, q_desc + static_cast<uint64_t>(k * 2), k_desc + static_cast<uint64_t>(k * 2), idesc_s,
+                                  (c > 0 || k > 0) ? 1u : 0u);
+                    tc_commit(&k_empty[ks]);
+                    if (++ks == 2) {
+                        ks = 0;
+                        kph ^= 1u;
+                    }
+                }
+                tc_commit(&s_full[j & 1]);
+            };
+            mbar_wait(q_full, 0, 20);
+            tc_fence_after();
+            issue_s(0);
+            for (int j = 0; j < T; ++j) {
+                // S_{j+1} goes to the other TMEM buffer (its last reader, the softmax of tile j-1, finished before
+                // p_full(j-1), which this warp has already waited for) and overlaps the softmax of tile j
+                if (j + 1 < T) issue_s(j + 1);
+                mbar_wait(p_full, j & 1u, 23u);
+                const int vs = j & 1;
+                mbar_wait(&v_full[vs], (j >> 1) & 1u, 24u);
+                tc_fence_after();
+                const uint32_t d = tmem_base + TM_O;
+                const uint32_t pbase = smem_u32(sm_p);
+                const uint32_t vbase = smem_u32(sm_v + vs * TILE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < BKV / 16; ++kk) {
+                    const uint64_t p_desc =
+                        make_smem_desc(pbase + static_cast<uint32_t>((kk >> 2) * TILE_BYTES + (kk & 3) * 32), 16u, 1024u);
+                    const uint64_t v_desc = make_smem_desc(vbase + static_cast<uint32_t>(kk * 2048), 8192u, 1024u);
+                    tc_mma_ss(d, p_desc, v_desc, idesc_o, kk > 0 ? 1u : 0u);
+                }
+                tc_commit(o_full);
+                tc_commit(&v_empty[vs]);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+        float o[HD];
+#pragma unroll
+        for (int i = 0; i < HD; ++i) o[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f, l_prev = 0.f;
+        for (int j = 0; j < T; ++j) {
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1u, 30u);
+            tc_fence_after();
+            const uint32_t s_addr = lane_addr + TM_S + static_cast<uint32_t>((j & 1) * 128);
+            const int kv_valid = g.Nk - j * BKV;
+            const bool tail = kv_valid < BKV;
+            const float m_tile = tail ? tile_rowmax<true>(s_addr, kv_valid) : tile_rowmax<false>(s_addr, kv_valid);
+            const float m_new = fmaxf(m_run, m_tile);
+            const float alpha = exp2f((m_run - m_new) * g.scale_log2);
+            const float mb = m_new * g.scale_log2;
+            if (j > 0) {  // also: P_{j-1} V_{j-1} is done reading the single P buffer
+                mbar_wait(o_full, (j - 1) & 1u, 31u);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t raw[32];
+                    tc_ld32(lane_addr + TM_O + static_cast<uint32_t>(c * 32), raw);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(raw[i]));
+                }
+                l_run = fmaf(l_run, alpha_prev, l_prev);
+            }
+            l_prev = tail ? tile_probs<true>(s_addr, kv_valid, g.scale_log2, mb, sm_p, r)
+                          : tile_probs<false>(s_addr, kv_valid, g.scale_log2, mb, sm_p, r);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_full);
+            alpha_prev = alpha;
+            m_run = m_new;
+        }
+        mbar_wait(o_full, (T - 1) & 1u, 32u);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t raw[32];
+            tc_ld32(lane_addr + TM_O + static_cast<uint32_t>(c * 32), raw);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(raw[i]));
+        }
+        l_run = fmaf(l_run, alpha_prev, l_prev);
+        const int q = q0 + r;
+        if (q < g.Nq) {
+            const float inv = 1.f / l_run;
+            bf16* op = g.O + static_cast<long long>(b) * g.o_batch_stride + static_cast<long long>(q) * g.o_row_stride +
+                       static_cast<long long>(h * NC + vc) * HD;
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) {
+                uint4 w;
+                w.x = pack_bf16x2(o[8 * c + 0] * inv, o[8 * c + 1] * inv);
+                w.y = pack_bf16x2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+                w.z = pack_bf16x2(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+                w.w = pack_bf16x2(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+                reinterpret_cast<uint4*>(op)[c] = w;
+            }
+            if (g.lse && vc == 0) g.lse[(static_cast<long long>(b) * g.H + h) * g.Nq + q] = m_run * g.scale + logf(l_run);
+        }
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// =================================================================================================
 // Fused attention backward (head_dim 64).  One CTA owns one 128-row K/V tile of one (batch, head) and
 // loops over the 128-row Q tiles:
 //     S  = Q_i K^T            dP = dO_i V^T                      (TMEM, 128x128 each)
@@ -681,9 +902,43 @@ int nk_attention_fwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
                      int64_t o_row_stride, int64_t o_batch_stride, float* lse, int B, int H, int Nq, int Nk,
                      int head_dim, float scale, nk_stream_t stream) {
     ::nk::enter(stream);
-    NK_REQUIRE(head_dim == HD, NK_ERR_UNSUPPORTED, "fused attention supports head_dim 64 (got %d)", head_dim);
+    NK_REQUIRE(head_dim % HD == 0 && head_dim >= HD && head_dim <= 8 * HD, NK_ERR_UNSUPPORTED,
+               "fused attention supports head_dim 64..512 in steps of 64 (got %d)", head_dim);
     NK_REQUIRE(B > 0 && H > 0 && Nq > 0 && Nk > 0, NK_ERR_SHAPE, "attention: empty problem");
     NK_REQUIRE(o_row_stride % 8 == 0 && o_batch_stride % 8 == 0, NK_ERR_SHAPE, "attention: output strides");
+    if (head_dim > HD) {  // wide heads: heads must be packed (head stride = head_dim) so that 64-wide chunks tile them
+        const int NC = head_dim / HD;
+        AttnWideDev w;
+        memset(&w, 0, sizeof(w));
+        int e = make_qkv_tmap(&w.tmQ, q, Nq, H * NC, B, q_row_stride, HD, q_batch_stride);
+        if (e) return e;
+        e = make_qkv_tmap(&w.tmK, k, Nk, H * NC, B, k_row_stride, HD, k_batch_stride);
+        if (e) return e;
+        e = make_qkv_tmap(&w.tmV, v, Nk, H * NC, B, v_row_stride, HD, v_batch_stride);
+        if (e) return e;
+        w.O = static_cast<bf16*>(o);
+        w.lse = lse;
+        w.o_row_stride = o_row_stride;
+        w.o_batch_stride = o_batch_stride;
+        w.Nq = Nq;
+        w.Nk = Nk;
+        w.H = H;
+        w.B = B;
+        w.NC = NC;
+        w.scale = scale;
+        w.scale_log2 = scale * 1.4426950408889634f;
+        const int smem = (NC + 6) * TILE_BYTES + 256 + 1024;
+        static bool wide_attr_set = false;
+        if (!wide_attr_set) {
+            NK_CUDA(cudaFuncSetAttribute(attn_fwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (8 + 6) * TILE_BYTES + 256 + 1024));
+            wide_attr_set = true;
+        }
+        dim3 grid((Nq + BQ - 1) / BQ, H * NC, B);
+        attn_fwd_wide_kernel<<<grid, ATT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(w);
+        NK_CUDA(cudaGetLastError());
+        return NK_OK;
+    }
     AttnDev g;
     memset(&g, 0, sizeof(g));
     int e = make_qkv_tmap(&g.tmQ, q, Nq, H, B, q_row_stride, HD, q_batch_stride);

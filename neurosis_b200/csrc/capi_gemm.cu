@@ -187,6 +187,34 @@ int nk_conv2d_fwd(const void* x, int64_t x_pix_stride, const void* wp, const flo
     return launch_gemm(p, ::nk::enter(stream));
 }
 
+int nk_conv2d_stride2_fwd(const void* x, int64_t x_pix_stride, const void* wp, const float* bias, void* y,
+                          int64_t y_pix_stride, int nimg, int H, int W, int Cin, int Cout, int ksize, int pad_t,
+                          int pad_l, int Ho, int Wo, nk_stream_t stream) {
+    NK_REQUIRE(ksize == 3, NK_ERR_UNSUPPORTED, "strided conv ksize %d", ksize);
+    NK_REQUIRE(Ho > 0 && Wo > 0 && 2 * (Ho - 1) - pad_t < H && 2 * (Wo - 1) - pad_l < W, NK_ERR_SHAPE,
+               "strided conv: output %dx%d does not fit input %dx%d", Ho, Wo, H, W);
+    GemmProblem p = blank_problem();
+    const int taps = ksize * ksize;
+    p.A = image(x, 0, nimg, H, W, Cin, x_pix_stride);
+    p.B = matrix(wp, 0, Cout, static_cast<long long>(taps) * Cin, static_cast<long long>(taps) * Cin);
+    p.M = nimg * Ho * Wo;
+    p.N = Cout;
+    p.K = taps * Cin;
+    p.ksize = ksize;
+    p.conv_stride = 2;
+    p.pad_t = pad_t;
+    p.pad_l = pad_l;
+    p.out_H = Ho;
+    p.out_W = Wo;
+    p.C = y;
+    p.ldc = y_pix_stride;
+    p.out = OUT_BF16;
+    p.epi = EPI_LINEAR;
+    p.bias = bias;
+    p.rows_per_img = Ho * Wo;
+    return launch_gemm(p, ::nk::enter(stream));
+}
+
 int nk_conv2d_wgrad(const void* dy, int64_t dy_pix_stride, const void* x, int64_t x_pix_stride,
                     float* dw_packed, int nimg, int H, int W, int Cin, int Cout, int ksize,
                     nk_stream_t stream) {

@@ -90,11 +90,11 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box) {
-    return encode_tmap(out, base, rank, dims, strides_bytes, box, 0);
+    return encode_tmap(out, base, rank, dims, strides_bytes, box, 0, nullptr);
 }
 
 int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                const uint32_t* box, int is_f32) {
+                const uint32_t* box, int is_f32, const uint32_t* elem_strides) {
     PFN_cuTensorMapEncodeTiled_v12000 fn = get_encode_fn();
     if (!fn) return NK_ERR_CUDA;
     NK_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, NK_ERR_SHAPE,
@@ -110,6 +110,7 @@ int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* di
     for (int i = 0; i < rank; ++i) {
         gdim[i] = dims[i];
         bdim[i] = box[i];
+        if (elem_strides) estr[i] = elem_strides[i];
         NK_REQUIRE(dims[i] >= 1 && box[i] >= 1 && box[i] <= 256, NK_ERR_SHAPE,
                    "tensor map: dim[%d]=%llu box=%u out of range", i,
                    static_cast<unsigned long long>(dims[i]), box[i]);

@@ -377,8 +377,10 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a
 // ----------------------------------------------------------------------------------------------
 // dims/strides innermost-first, strides in BYTES for dims 1..rank-1 (dim 0 is contiguous).
 // same, element type bf16 (is_f32 = 0) or fp32 (is_f32 = 1); 128B swizzle, so box[0] * element size must be 128 bytes
+// elem_strides (optional): traversal step per dimension; the box then spans box[i] tensor elements and lands
+// ceil(box[i] / elem_strides[i]) of them in shared memory (strided convolution windows)
 int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                const uint32_t* box, int is_f32);
+                const uint32_t* box, int is_f32, const uint32_t* elem_strides = nullptr);
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box);
 

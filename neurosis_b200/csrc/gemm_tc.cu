@@ -46,7 +46,8 @@ struct alignas(64) GemmDev {
     int mode;
     int a_b2, a_b1, b_b2, b_b1;  // 0/1: does the operand carry that batch dimension
     // conv geometry
-    int cH, cW, bw, bh, tiles_w, tiles_h, cin_blocks, ksize, pad;
+    int cH, cW, bw, bh, tiles_w, tiles_h, cin_blocks, ksize, pad;  // cH, cW: OUTPUT image (= input unless strided)
+    int cstride, pad_t, pad_l;                                     // conv forward: input pixel = cstride*out + tap - pad
     // epilogue
     void* C;
     long long ldc, c_b2, c_b1;
@@ -209,10 +210,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     } else if (g.mode == MODE_CONV_FWD) {
                         const int tap = gi / g.cin_blocks;
                         const int cb = gi - tap * g.cin_blocks;
-                        const int dy = tap / g.ksize - g.pad;
-                        const int dx = tap % g.ksize - g.pad;
-                        tma_load(&g.tmA, &full_bar[stage], sa, cb * 64, tw * g.bw + dx,
-                                    th * g.bh + dy, img);
+                        const int dy = tap / g.ksize - g.pad_t;
+                        const int dx = tap % g.ksize - g.pad_l;
+                        tma_load(&g.tmA, &full_bar[stage], sa, cb * 64, g.cstride * (tw * g.bw) + dx,
+                                    g.cstride * (th * g.bh) + dy, img);
                         tma_load(&g.tmB, &full_bar[stage], sb, gi * BK, n0, 0, 0);
                     } else {  // MODE_CONV_WGRAD: k-iteration = one 64-pixel tile; N index = tap*Cin + ci
                         const int ptw = gi % g.tiles_w;
@@ -497,10 +498,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 // host side
 // ----------------------------------------------------------------------------------------------
 
-int make_operand_tmap(CUtensorMap* tm, const GemmOperand& o, int box_rows_or_bw, int box_bh) {
+int make_operand_tmap(CUtensorMap* tm, const GemmOperand& o, int box_rows_or_bw, int box_bh, int pix_stride = 1) {
     uint64_t dims[4];
     uint64_t strides[3];
     uint32_t box[4];
+    uint32_t estr[4] = {1, 1, 1, 1};
     if (!o.conv) {
         dims[0] = static_cast<uint64_t>(o.inner);
         dims[1] = static_cast<uint64_t>(o.rows);
@@ -525,8 +527,21 @@ int make_operand_tmap(CUtensorMap* tm, const GemmOperand& o, int box_rows_or_bw,
         box[1] = static_cast<uint32_t>(box_rows_or_bw);
         box[2] = static_cast<uint32_t>(box_bh);
         box[3] = 1;
+        if (pix_stride > 1) {
+            // a box that lands bw x bh pixels taken every `pix_stride`-th pixel spans bw*stride x bh*stride tensor elements
+            static int span = -1;
+            if (span < 0) {
+                const char* e_ = getenv("NK_TMA_STRIDE_BOX");  // "count": box dims count landed elements (A/B switch)
+                span = (e_ && e_[0] == 'c') ? 0 : 1;
+            }
+            estr[1] = estr[2] = static_cast<uint32_t>(pix_stride);
+            if (span) {
+                box[1] *= static_cast<uint32_t>(pix_stride);
+                box[2] *= static_cast<uint32_t>(pix_stride);
+            }
+        }
     }
-    return encode_tmap_bf16(tm, o.ptr, 4, dims, strides, box);
+    return encode_tmap(tm, o.ptr, 4, dims, strides, box, 0, estr);
 }
 
 // tile width (and CTA-group size) minimising waves x per-k16 cost.  `groups` = CTA groups that run concurrently.
@@ -605,9 +620,13 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     }
 
     int a_box1 = BM, a_box2 = 1, b_box2 = 1;
+    g.cstride = p.conv_stride > 1 ? p.conv_stride : 1;
+    g.pad_t = g.cstride > 1 ? p.pad_t : p.pad;
+    g.pad_l = g.cstride > 1 ? p.pad_l : p.pad;
     if (g.mode == MODE_CONV_FWD) {
-        g.cH = p.A.H;
-        g.cW = p.A.W;
+        g.cH = g.cstride > 1 ? p.out_H : p.A.H;
+        g.cW = g.cstride > 1 ? p.out_W : p.A.W;
+        NK_REQUIRE(g.cH > 0 && g.cW > 0, NK_ERR_SHAPE, "conv: empty output image");
         pick_pixel_tile(g.cH, g.cW, BM, false, &g.bw, &g.bh);
         g.tiles_w = (g.cW + g.bw - 1) / g.bw;
         g.tiles_h = (g.cH + g.bh - 1) / g.bh;
@@ -697,7 +716,7 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     g.b_b2 = (!p.B.conv && p.B.nb2 > 1) ? 1 : 0;
     g.b_b1 = (!p.B.conv && p.B.nb1 > 1) ? 1 : 0;
 
-    int e = make_operand_tmap(&g.tmA, p.A, a_box1, a_box2);
+    int e = make_operand_tmap(&g.tmA, p.A, a_box1, a_box2, g.mode == MODE_CONV_FWD ? g.cstride : 1);
     if (e) return e;
     const int b_box1 = p.B.conv ? g.bw : (p.B.mn_major ? 64 : bnc);
     e = make_operand_tmap(&g.tmB, p.B, b_box1, b_box2);

@@ -34,6 +34,9 @@ struct GemmProblem {
     int nb2, nb1;         // batch extents of the launch (C is indexed by them as well)
     // conv forward / dgrad (A.conv=1, A K-major): K = taps*Cin, k-iteration -> (tap, 64-channel block)
     int ksize, pad;       // 3,1 or 1,0
+    // strided conv forward (conv_stride = 2): output pixel (h, w) reads input (2h + ky - pad_t, 2w + kx - pad_l); the
+    // A tiles are TMA boxes traversed with element stride 2.  0 / 1 = ordinary stride-1 convolution (pad both sides).
+    int conv_stride, pad_t, pad_l, out_H, out_W;
     // conv wgrad (A.conv = B.conv = 1, both MN-major): N = taps*Cin (every 64-channel atom has its own tap shift), K = all pixels
     int wgrad;
     // output

@@ -360,6 +360,19 @@ def conv2d_fwd(x: Tensor, wp: Tensor, cout: int, ksize: int, bias: Optional[Tens
     return y
 
 
+def conv2d_stride2_fwd(x: Tensor, wp: Tensor, cout: int, ksize: int, bias: Optional[Tensor], pad_t: int, pad_l: int,
+                       ho: int, wo: int) -> Tensor:
+    """3x3 stride-2 convolution of NHWC bf16 x (physical channels % 64 == 0) with packed weights -> (n, ho, wo, cout)."""
+    _req_cuda(x, wp)
+    n, h, w_, cin = x.shape
+    y = torch.empty((n, ho, wo, cout), dtype=BF16, device=x.device)
+    _tc(lib.nk_conv2d_stride2_fwd, "conv2d_s2_fwd", 2.0 * n * ho * wo * cout * ksize * ksize * cin, x.data_ptr(),
+        x.stride(2), wp.data_ptr(), _p(bias), y.data_ptr(), cout, n, h, w_, cin, cout, ksize, pad_t, pad_l, ho, wo,
+        _stream())
+    _count()
+    return y
+
+
 def conv2d_wgrad(dy: Tensor, x: Tensor, cout: int, ksize: int) -> Tensor:
     """packed fp32 gradient [cout, taps, Cin_phys]."""
     n, h, w_, cin = x.shape
@@ -619,7 +632,8 @@ def attention_fwd(q: Tensor, k: Tensor, v: Tensor, scale: float):
     Nk = k.shape[1]
     o = torch.empty((B, Nq, H, D), dtype=BF16, device=q.device)
     lse = torch.empty((B, H, Nq), dtype=F32, device=q.device)
-    if D == 64 and q.stride(2) == 64 and k.stride(2) == 64 and v.stride(2) == 64:
+    packed = all(t.stride(3) == 1 and (H == 1 or t.stride(2) == D) for t in (q, k, v))
+    if D % 64 == 0 and D <= 512 and packed:  # flash kernel: D = 64, or wide heads in 64-column chunks (VAE: 1 x 512)
         check(lib.nk_attention_fwd(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
                                    v.data_ptr(), v.stride(1), v.stride(0), o.data_ptr(), o.stride(1), o.stride(0),
                                    lse.data_ptr(), B, H, Nq, Nk, D, float(scale), _stream()), "attention_fwd")
@@ -864,8 +878,12 @@ class ConvStridedFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, pad_t, pad_l, ho, wo):
         co, ci, ks, _ = weight.shape
         wf, _ = packed_conv_weight(weight)
-        col = im2col(x, ks, 2, pad_t, pad_l, ho, wo)
-        y = linear_fwd(col, wf[:co], f32_param(bias))
+        if ks == 3 and x.shape[-1] % 64 == 0 and wf.shape[1] == ks * ks * x.shape[-1]:
+            # implicit GEMM: the TMA unit walks the input with element stride 2, nothing is materialised
+            y = conv2d_stride2_fwd(x, wf, co, ks, f32_param(bias), pad_t, pad_l, ho, wo)
+        else:
+            col = im2col(x, ks, 2, pad_t, pad_l, ho, wo)
+            y = linear_fwd(col, wf[:co], f32_param(bias))
         ctx.save_for_backward(x, weight)
         ctx.geom = (pad_t, pad_l, ho, wo)
         ctx.has_bias = bias is not None

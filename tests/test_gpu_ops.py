@@ -265,7 +265,8 @@ def sdpa_ref(q, k, v, scale):
 
 
 @pytest.mark.parametrize("B,H,Nq,Nk,D", [(2, 4, 256, 256, 64), (1, 2, 1024, 1024, 64), (2, 3, 200, 77, 64), (1, 5, 1008, 1008, 64),
-                                         (1, 1, 128, 300, 64), (2, 8, 256, 256, 40), (1, 2, 320, 77, 160), (1, 1, 512, 512, 512)])
+                                         (1, 1, 128, 300, 64), (2, 8, 256, 256, 40), (1, 2, 320, 77, 160), (1, 1, 512, 512, 512),
+                                         (2, 2, 300, 200, 128), (1, 3, 256, 256, 192), (1, 1, 1024, 1000, 512)])
 def test_attention_fwd_bwd(B, H, Nq, Nk, D):
     q = rnd(B, Nq, H, D).to(BF).requires_grad_(True)
     k = rnd(B, Nk, H, D, seed=1).to(BF).requires_grad_(True)

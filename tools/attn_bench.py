@@ -10,6 +10,20 @@ from neurosis_b200 import ops  # noqa: E402
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 dev = "cuda"
+# the VAE mid-block attention (one 512-wide head, forward only: the encoder runs without gradients)
+qv, kv, vv = (torch.randn(8, 4096, 1, 512, device=dev).bfloat16() for _ in range(3))
+ops.attention_fwd(qv, kv, vv, 512 ** -0.5)
+torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+ev[0].record()
+for _ in range(iters):
+    ops.attention_fwd(qv, kv, vv, 512 ** -0.5)
+ev[1].record()
+torch.cuda.synchronize()
+tv = ev[0].elapsed_time(ev[1]) / iters
+print(f"vae 4096 d512    fwd {tv:7.3f} ms {4.0 * 8 * 4096 * 4096 * 512 / tv / 1e9:7.1f} TFLOP/s (useful flops)")
+del qv, kv, vv
+
 for name, B, H, Nq, Nk in (("self 1024", 8, 20, 1024, 1024), ("self 4096", 8, 10, 4096, 4096),
                            ("cross 1024x77", 8, 20, 1024, 77), ("cross 4096x77", 8, 10, 4096, 77)):
     q = torch.randn(B, Nq, H, 64, device=dev).bfloat16()
