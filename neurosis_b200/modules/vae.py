@@ -82,8 +82,8 @@ class ResnetBlock(nn.Module):
 
 
 class AttnBlock(nn.Module):
-    """single-head attention over all pixels, head_dim = channels (512): the wide-head fused tcgen05 kernel in the
-    forward; gradients (VAE training, outside the hot path) go through the materialised batched-GEMM backward."""
+    """single-head attention over all pixels, head_dim = channels (512): materialised tcgen05 path (score GEMM ->
+    row softmax -> PV GEMM), a few images per call to bound the fp32 score matrix."""
 
     def __init__(self, in_channels: int):
         super().__init__()
@@ -93,7 +93,7 @@ class AttnBlock(nn.Module):
         self.k = nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
         self.v = nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
         self.proj_out = nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
-        self.max_images_per_call = 2  # backward only: bounds the materialised score matrix (1 GiB per 1024^2 image)
+        self.max_images_per_call = 2  # bounds the fp32 score matrix (1 GiB per 1024^2 image)
 
     def forward(self, x: Tensor, **kwargs) -> Tensor:
         xn = as_nhwc(x)
@@ -101,8 +101,7 @@ class AttnBlock(nn.Module):
         t = _gn(self.norm, xn, False)
         q, k, v = (_conv1x1(m, t).view(n, h * w, 1, c) for m in (self.q, self.k, self.v))
         outs = []
-        fused_fwd_only = c % 64 == 0 and c <= 512 and not (torch.is_grad_enabled() and t.requires_grad)
-        step = n if fused_fwd_only else self.max_images_per_call
+        step = n if c in ops.FLASH_HEAD_DIMS else self.max_images_per_call
         for i in range(0, n, step):
             j = min(n, i + step)
             outs.append(ops.attention(q[i:j], k[i:j], v[i:j], c ** -0.5))

@@ -284,6 +284,23 @@ def test_attention_fwd_bwd(B, H, Nq, Nk, D):
     assert rel(v.grad, vr.grad) < 2e-2
 
 
+@pytest.mark.parametrize("B,H,Nq,Nk,D", [(1, 1, 512, 512, 512), (1, 3, 256, 200, 192), (1, 1, 1024, 1000, 512), (2, 1, 130, 130, 256)])
+def test_attention_fwd_wide_heads_fused(B, H, Nq, Nk, D):
+    """the fused forward for head dims up to 512 (scores accumulated over 64-column chunks), which the default
+    dispatch only uses for D = 128"""
+    q, k, v = (rnd(B, n, H, D, seed=i).to(BF) for i, n in enumerate((Nq, Nk, Nk)))
+    old = ops.FLASH_HEAD_DIMS
+    ops.FLASH_HEAD_DIMS = (64, 128, 192, 256, 512)
+    try:
+        o, lse = ops.attention_fwd(q, k, v, D ** -0.5)
+    finally:
+        ops.FLASH_HEAD_DIMS = old
+    ref = sdpa_ref(q, k, v, D ** -0.5)
+    assert rel(o, ref) < 1e-2
+    s_ref = torch.logsumexp(torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * D ** -0.5, -1)
+    assert (lse - s_ref).abs().max() < 2e-2
+
+
 def test_attention_bwd_materialized_path_d64():
     """the batched-GEMM backward (used for head dims != 64) must agree with the fused kernel's reference too."""
     B, H, N, D = 1, 3, 384, 64
