@@ -91,6 +91,8 @@ class BucketedGradReducer:
 
     def detach_grad_sink(self) -> None:
         from . import ops
+        if self._cuda:
+            ops.join_side_streams()
         if ops.GRAD_SINK is self:
             ops.GRAD_SINK = None
 
@@ -115,6 +117,9 @@ class BucketedGradReducer:
 
     def finish(self) -> None:
         """call after backward: every bucket has been reduced when this returns (stream-ordered on CUDA)."""
+        if self._cuda:
+            from . import ops
+            ops.join_side_streams()  # weight gradients computed on the side stream (marks their parameters ready)
         if self.world == 1:
             return
         for b in self.buckets:  # parameters that received no gradient this step still take part

@@ -12,6 +12,7 @@ Layout conventions
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 import math
 import weakref
@@ -88,6 +89,59 @@ def _grad_sink_pair(a: Optional[Tensor], b: Optional[Tensor]):
 
 
 FLASH_HEAD_DIMS = (64, 128)  # head dims routed to the fused attention forward (tests widen this to exercise 64..512)
+# ---- weight gradients on a side stream ---------------------------------------------------------------------------
+# dW (and the conv weight-gradient chain) of a layer depends only on tensors that exist when its backward starts and
+# nothing downstream in the backward pass reads it, so it runs on a second stream next to the data-gradient chain.
+# The persistent GEMM kernels leave part of the SMs idle in their last wave; CTAs of the other stream's kernel take
+# those SMs, and memory-bound kernels of the main chain overlap tensor-bound weight-gradient GEMMs.
+# Only used when the gradient goes to a sink (ddp.BucketedGradReducer): autograd never sees the tensor, and the
+# parameter is reported ready (mark_ready -> bucket all-reduce) only after the main stream has joined the side work.
+WGRAD_OVERLAP = True
+_side_streams: dict = {}
+_inflight: collections.deque = collections.deque()  # (event on the side stream, tensors kept alive, sink base params)
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=device)
+    return st
+
+
+def _retire_one(main) -> None:
+    ev, _keep, bases = _inflight.popleft()
+    main.wait_event(ev)  # from here on the main stream may reuse the kept tensors' memory
+    sink = GRAD_SINK
+    if sink is not None:
+        for b in bases:
+            sink.mark_ready(b)
+
+
+def _fork_wgrad(fn, keep: tuple, bases: tuple) -> None:
+    """run `fn` (kernel launches writing into gradient sinks) on the side stream, ordered after everything queued on
+    the current stream so far.  `keep` holds the input tensors until the main stream has waited for the side work
+    (the caching allocator must not hand their memory to a later main-stream kernel before that)."""
+    main = torch.cuda.current_stream()
+    side = _side_stream(main.device)
+    side.wait_event(main.record_event())
+    with torch.cuda.stream(side):
+        fn()
+        ev = side.record_event()
+    _inflight.append((ev, keep, bases))
+    while len(_inflight) > 2:  # at most two weight-gradient jobs trail the main stream
+        _retire_one(main)
+
+
+def join_side_streams() -> None:
+    """main stream waits for all outstanding side-stream weight gradients (end of backward / before all-reduce)."""
+    if not _inflight:
+        return
+    main = torch.cuda.current_stream()
+    while _inflight:
+        _retire_one(main)
+
+
 NCU_SAMPLE = 0          # > 0: every NCU_SAMPLE-th tensor-core launch runs inside a cudaProfilerStart/Stop range
 NCU_SAMPLE_LOG: list = []  # (what, small integer arguments) of the sampled launches, in launch order
 _ncu_seen = 0
@@ -803,8 +857,11 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             buf, base = _grad_sink(weight)
             if buf is not None:  # accumulate straight into the (zeroed) gradient bucket, no autograd "+=" pass
-                linear_wgrad(dy, x, out=buf)
-                GRAD_SINK.mark_ready(base)
+                if WGRAD_OVERLAP:
+                    _fork_wgrad(lambda: linear_wgrad(dy, x, out=buf), (dy, x), (base,))
+                else:
+                    linear_wgrad(dy, x, out=buf)
+                    GRAD_SINK.mark_ready(base)
             else:
                 dw = linear_wgrad(dy, x)
         db = None
@@ -850,13 +907,16 @@ class Conv2dFn(torch.autograd.Function):
             if dx.shape[-1] != x.shape[-1]:
                 dx = dx[..., : x.shape[-1]].contiguous()
         if ctx.needs_input_grad[1]:
-            dwp = conv2d_wgrad(dy, x, co, ks)
             buf, base = _grad_sink(weight)
-            if buf is not None:
-                conv_unpack_wgrad(dwp, co, ci, ks, out=buf)
-                GRAD_SINK.mark_ready(base)
+            if buf is not None and WGRAD_OVERLAP:
+                _fork_wgrad(lambda: conv_unpack_wgrad(conv2d_wgrad(dy, x, co, ks), co, ci, ks, out=buf), (dy, x), (base,))
             else:
-                dw = conv_unpack_wgrad(dwp, co, ci, ks)
+                dwp = conv2d_wgrad(dy, x, co, ks)
+                if buf is not None:
+                    conv_unpack_wgrad(dwp, co, ci, ks, out=buf)
+                    GRAD_SINK.mark_ready(base)
+                else:
+                    dw = conv_unpack_wgrad(dwp, co, ci, ks)
         if (has_bias and ctx.needs_input_grad[2]) or (has_bimg and ctx.needs_input_grad[3]):
             if has_bimg and ctx.needs_input_grad[3]:
                 s = colsum(dy, groups=dy.shape[0])[:, :co]  # per-image sums (timestep-embedding gradient)
@@ -905,14 +965,18 @@ class ConvStridedFn(torch.autograd.Function):
             dcol = linear_dgrad(dy2, wf[:co])
             dx = col2im(dcol, x.shape, ks, 2, pad_t, pad_l, ho, wo)
         if ctx.needs_input_grad[1]:
-            col = im2col(x, ks, 2, pad_t, pad_l, ho, wo)
-            dwp = linear_wgrad(dy2, col)
             buf, base = _grad_sink(weight)
-            if buf is not None:
-                conv_unpack_wgrad(dwp, co, ci, ks, out=buf)
-                GRAD_SINK.mark_ready(base)
+            if buf is not None and WGRAD_OVERLAP:
+                _fork_wgrad(lambda: conv_unpack_wgrad(linear_wgrad(dy2, im2col(x, ks, 2, pad_t, pad_l, ho, wo)), co, ci,
+                                                      ks, out=buf), (dy2, x), (base,))
             else:
-                dw = conv_unpack_wgrad(dwp, co, ci, ks)
+                col = im2col(x, ks, 2, pad_t, pad_l, ho, wo)
+                dwp = linear_wgrad(dy2, col)
+                if buf is not None:
+                    conv_unpack_wgrad(dwp, co, ci, ks, out=buf)
+                    GRAD_SINK.mark_ready(base)
+                else:
+                    dw = conv_unpack_wgrad(dwp, co, ci, ks)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2)[0]
         return dx, dw, db, None, None, None, None

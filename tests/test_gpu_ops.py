@@ -111,9 +111,10 @@ def test_conv_thin_channels():
     assert rel(w2.grad, w2r.grad) < 1.5e-2
 
 
-@pytest.mark.parametrize("asym", [False, True])
-def test_conv_stride2(asym):
-    n, h, w, c = 2, 32, 32, 128
+@pytest.mark.parametrize("n,h,w,c,asym", [(2, 32, 32, 128, False), (2, 32, 32, 128, True), (1, 50, 38, 64, True),
+                                          (3, 17, 23, 192, False)])
+def test_conv_stride2(n, h, w, c, asym):
+    """forward = implicit GEMM over TMA boxes walked with element stride 2 (odd sizes: ragged last tiles + padding)"""
     x = rnd(n, h, w, c).to(BF).requires_grad_(True)
     wt = (rnd(c, c, 3, 3, seed=1) * (9 * c) ** -0.5).requires_grad_(True)
     b = rnd(c, seed=2).requires_grad_(True)
