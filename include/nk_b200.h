@@ -131,13 +131,16 @@ int nk_attention_fwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
                      int64_t v_batch_stride, void* o, int64_t o_row_stride, int64_t o_batch_stride,
                      float* lse, int B, int H, int Nq, int Nk, int head_dim, float scale, nk_stream_t stream);
 /* Fused attention backward (head_dim 64): dq_acc fp32 [B,Nq,H,64] must be zero-initialised (K/V tiles accumulate
- * into it with red.global.add); dk, dv bf16 [B,Nk,H,64] contiguous; lse from nk_attention_fwd, delta from
- * nk_attn_delta.  Autograd of the attention call sites modules/attention.py:346-352,410-412. */
+ * into it with TMA reduce-adds); dk, dv bf16 [B,Nk,H,64] with element strides dkv_row_stride / dkv_batch_stride
+ * (0 = contiguous; non-zero lets them be column slices of one fused q|k|v gradient buffer); lse from
+ * nk_attention_fwd, delta from nk_attn_delta.  Autograd of the attention call sites
+ * modules/attention.py:346-352,410-412. */
 int nk_attention_bwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride, const void* k, int64_t k_row_stride,
                      int64_t k_batch_stride, const void* v, int64_t v_row_stride, int64_t v_batch_stride,
                      const void* dO, int64_t do_row_stride, int64_t do_batch_stride, const float* lse,
-                     const float* delta, float* dq_acc, void* dk, void* dv, int B, int H, int Nq, int Nk, int head_dim,
-                     float scale, nk_stream_t stream);
+                     const float* delta, float* dq_acc, void* dk, void* dv, int64_t dkv_row_stride,
+                     int64_t dkv_batch_stride, int B, int H, int Nq, int Nk, int head_dim, float scale,
+                     nk_stream_t stream);
 /* delta[b,h,q] = sum_d dO*O on [B,N,H,D] tensors (attention backward). */
 int nk_attn_delta(const void* dO, const void* O, float* delta, int B, int N, int H, int D, nk_stream_t stream);
 /* P = softmax(scale*S) row-wise (S fp32 [rows, lds], P bf16), lse optional — materialised attention path
@@ -180,6 +183,10 @@ int nk_cast_f32_bf16(const float* x, void* y, int64_t n, nk_stream_t stream);
  * array of n_spans records {const float* src; bf16* dst; int64 n} (24 bytes each); one thread block per span. */
 int nk_cast_f32_bf16_multi(const void* spans_dev, int n_spans, nk_stream_t stream);
 int nk_cast_bf16_f32(const void* x, float* y, int64_t n, int accumulate, nk_stream_t stream);
+/* row-strided fp32 -> bf16: y[r, 0:cols] = x[r, 0:cols] with leading dimensions ldx / ldy (elements; cols, ldx, ldy
+ * multiples of 8): the fp32 dQ accumulator of the attention backward into its slice of a fused q|k|v gradient. */
+int nk_cast_f32_bf16_rows(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int cols,
+                          nk_stream_t stream);
 /* copy C channels of every pixel between NHWC buffers with different pixel strides (skip concat / split:
  * modules/diffusion/openaimodel.py:836) */
 int nk_copy_channels(const void* src, int64_t src_stride, void* dst, int64_t dst_stride, int64_t npix, int C,

@@ -970,12 +970,14 @@ int nk_attention_fwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
 
 
 // Gradients of nk_attention_fwd.  dq_acc: fp32 [B, Nq, H, 64] ZERO-INITIALISED accumulator (contiguous);
-// dk, dv: bf16 [B, Nk, H, 64] (contiguous).  lse from the forward, delta[b,h,q] = sum_d dO*O (nk_attn_delta).
+// dk, dv: bf16 [B, Nk, H, 64] with row / batch strides dkv_*_stride (0 = contiguous), e.g. column slices of one
+// fused [B, Nk, 3*H*64] gradient buffer.  lse from the forward, delta[b,h,q] = sum_d dO*O (nk_attn_delta).
 int nk_attention_bwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride, const void* k, int64_t k_row_stride,
                      int64_t k_batch_stride, const void* v, int64_t v_row_stride, int64_t v_batch_stride,
                      const void* dO, int64_t do_row_stride, int64_t do_batch_stride, const float* lse,
-                     const float* delta, float* dq_acc, void* dk, void* dv, int B, int H, int Nq, int Nk, int head_dim,
-                     float scale, nk_stream_t stream) {
+                     const float* delta, float* dq_acc, void* dk, void* dv, int64_t dkv_row_stride,
+                     int64_t dkv_batch_stride, int B, int H, int Nq, int Nk, int head_dim, float scale,
+                     nk_stream_t stream) {
     ::nk::enter(stream);
     NK_REQUIRE(head_dim == HD, NK_ERR_UNSUPPORTED, "fused attention backward supports head_dim 64 (got %d)", head_dim);
     NK_REQUIRE(B > 0 && H > 0 && Nq > 0 && Nk > 0, NK_ERR_SHAPE, "attention bwd: empty problem");
@@ -1005,8 +1007,11 @@ int nk_attention_bwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
     g.dV = static_cast<bf16*>(dv);
     g.dq_row_stride = static_cast<long long>(H) * HD;
     g.dq_batch_stride = static_cast<long long>(Nq) * H * HD;
-    g.dkv_row_stride = static_cast<long long>(H) * HD;
-    g.dkv_batch_stride = static_cast<long long>(Nk) * H * HD;
+    g.dkv_row_stride = dkv_row_stride > 0 ? dkv_row_stride : static_cast<long long>(H) * HD;
+    g.dkv_batch_stride = dkv_batch_stride > 0 ? dkv_batch_stride : static_cast<long long>(Nk) * H * HD;
+    NK_REQUIRE(g.dkv_row_stride % 8 == 0 && g.dkv_batch_stride % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(dk) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dv) & 15u) == 0,
+               NK_ERR_SHAPE, "attention bwd: dk/dv must be 16-byte aligned with strides that are multiples of 8");
     g.Nq = Nq;
     g.Nk = Nk;
     g.H = H;

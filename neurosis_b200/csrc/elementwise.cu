@@ -140,6 +140,16 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restri
     cast_span(x, y, n, blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x,
               static_cast<long long>(gridDim.x) * blockDim.x);
 }
+__global__ void cast_f32_bf16_rows_kernel(const float* __restrict__ x, long long ldx, bf16* __restrict__ y,
+                                          long long ldy, long long rows, int V) {
+    const long long total = rows * V;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / V;
+        const int v = static_cast<int>(i - r * V);
+        cast8(x + r * ldx + 8 * v, y + r * ldy + 8 * v);
+    }
+}
 // many tensors, one launch: block b converts spans[b] = {src, dst, n} (the host cuts every tensor into spans)
 struct CastSpan {
     const float* src;
@@ -568,6 +578,17 @@ int nk_add(const void* a, const void* b, void* y, int64_t n, nk_stream_t stream)
 }
 int nk_cast_f32_bf16(const float* x, void* y, int64_t n, nk_stream_t stream) {
     cast_f32_bf16_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, ST(stream)>>>(x, BF(y), n);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_cast_f32_bf16_rows(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int cols,
+                          nk_stream_t stream) {
+    NK_REQUIRE(cols % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
+                   (reinterpret_cast<uintptr_t>(y) & 15u) == 0,
+               NK_ERR_SHAPE, "cast rows: cols/ld must be multiples of 8 and pointers 16-byte aligned");
+    cudaStream_t st = ST(stream);
+    if (rows <= 0 || cols <= 0) return NK_OK;
+    cast_f32_bf16_rows_kernel<<<grid_for(rows * (cols / 8), 256), 256, 0, st>>>(x, ldx, BF(y), ldy, rows, cols / 8);
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }

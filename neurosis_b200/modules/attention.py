@@ -17,6 +17,8 @@ nn.Parameters exactly as in the reference so its checkpoints load unchanged.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Any, Optional
 
 import torch
@@ -80,6 +82,8 @@ class CrossAttention(nn.Module):
         self.to_k = nn.Linear(context_dim, inner_dim, bias=False)
         self.to_v = nn.Linear(context_dim, inner_dim, bias=False)
         self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Identity())
+        # self-attention with head_dim 64: one stacked q|k|v GEMM per direction (NK_NO_FUSED_QKV=1: A/B switch)
+        self.fuse_qkv = not os.environ.get("NK_NO_FUSED_QKV")
 
     def forward(self, x: Tensor, context: Optional[Tensor] = None, mask: Optional[Tensor] = None,
                 additional_tokens: Optional[Tensor] = None, n_times_crossframe_attn_in_self: int = 0,
@@ -87,13 +91,18 @@ class CrossAttention(nn.Module):
         if mask is not None or additional_tokens is not None or n_times_crossframe_attn_in_self:
             raise NotImplementedError("mask / additional_tokens / cross-frame attention are not supported")
         b, n, _ = x.shape
-        context = x if context is None else ops.cast_bf16(context) if context.dtype != torch.bfloat16 else context
         h, d = self.heads, self.dim_head
+        out = self.to_out[0]
+        if (context is None and d == 64 and self.fuse_qkv and x.dtype == torch.bfloat16
+                and self.to_k.weight.shape == self.to_q.weight.shape):
+            # self-attention: q, k, v are one GEMM (forward, data gradient and weight gradient alike)
+            o = ops.self_attention_qkv(x, self.to_q.weight, self.to_k.weight, self.to_v.weight, h, self.scale)
+            return ops.linear(o, out.weight, out.bias, residual)
+        context = x if context is None else ops.cast_bf16(context) if context.dtype != torch.bfloat16 else context
         q = ops.linear(x, self.to_q.weight).view(b, n, h, d)
         k = ops.linear(context, self.to_k.weight).view(b, context.shape[1], h, d)
         v = ops.linear(context, self.to_v.weight).view(b, context.shape[1], h, d)
         o = ops.attention(q, k, v, self.scale).view(b, n, h * d)
-        out = self.to_out[0]
         return ops.linear(o, out.weight, out.bias, residual)
 
 

@@ -216,6 +216,7 @@ def invalidate_weight_cache() -> None:
     that capture CUDA graphs call it before capture so the casts are part of the graph and replayed every step."""
     _wcache.clear()
     _mirror.clear()
+    _wgroups.clear()
 
 
 class _WeightMirror:
@@ -292,6 +293,35 @@ def bf16_weight(p: Tensor) -> Tensor:
         if base.dtype == F32 and base.is_contiguous():
             _mirror.register(base, w)
     return w.view(p.shape) if w.shape != p.shape else w
+
+
+_wgroups: dict = {}  # tuple(id(base)) -> (weakrefs, stacked bf16 buffer, per-parameter views)
+
+
+def bf16_weight_group(ps: tuple) -> Tensor:
+    """bf16 copies of several [N_i, K] weights stacked in ONE [sum N_i, K] buffer (fused projections: q|k|v).  Every
+    parameter's slice is an ordinary cached copy (refreshed by `refresh_weight_copies`), so the stack stays valid."""
+    bases = tuple(p._base if p._base is not None else p for p in ps)
+    key = tuple(id(b) for b in bases)
+    ent = _wgroups.get(key)
+    if ent is None or any(r() is not b for r, b in zip(ent[0], bases)):
+        k = bases[0].shape[1]
+        assert all(b.dim() == 2 and b.shape[1] == k and b.dtype == F32 and b.is_contiguous() for b in bases)
+        buf = torch.empty((sum(b.shape[0] for b in bases), k), dtype=BF16, device=bases[0].device)
+        views, r0 = [], 0
+        for b in bases:
+            views.append(buf[r0: r0 + b.shape[0]])
+            r0 += b.shape[0]
+        ent = (tuple(weakref.ref(b) for b in bases), buf, views)
+        _wgroups[key] = ent
+    for b, view in zip(bases, ent[2]):
+        d = _cache_for(b)
+        if d.get("bf16") is not view:  # stale (parameter changed) or cached elsewhere: cast into the stacked slice
+            check(lib.nk_cast_f32_bf16(b.detach().data_ptr(), view.data_ptr(), b.numel(), _stream()), "cast_f32_bf16")
+            _count()
+            d["bf16"] = view
+            _mirror.register(b, view)
+    return ent[1]
 
 
 def f32_param(p: Optional[Tensor]) -> Optional[Tensor]:
@@ -733,9 +763,13 @@ def _pv(P: Tensor, v: Tensor, o: Tensor, Nk: int) -> None:
     _tc(lib.nk_gemm_ex, "attention PV gemm", 2.0 * d.M * d.N * d.K * d.nb1 * d.nb2, ctypes.byref(d), _stream())
 
 
-def attention_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, scale: float):
-    """Gradients of attention_fwd via batched tensor-core GEMMs with softmax-aware epilogues:
-       P = exp(scale*QK^T - lse); dV = P^T dO; dP = dO V^T; dS = P*(dP - delta)*scale; dQ = dS K; dK = dS^T Q."""
+def attention_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, scale: float,
+                  out: Optional[tuple] = None):
+    """Gradients of attention_fwd.  head_dim 64: the fused flash-style kernel; other head dims: batched tensor-core
+       GEMMs with softmax-aware epilogues:
+       P = exp(scale*QK^T - lse); dV = P^T dO; dP = dO V^T; dS = P*(dP - delta)*scale; dQ = dS K; dK = dS^T Q.
+       `out` = (dq, dk, dv) bf16 destination views (fused path only): (B,N,H,64) views with contiguous heads that
+       share one row/batch stride, e.g. the three column blocks of a fused [B, N, 3*H*64] gradient."""
     B, Nq, H, D = q.shape
     Nk = k.shape[1]
     dev = q.device
@@ -746,14 +780,26 @@ def attention_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: T
     if D == 64 and q.stride(2) == 64 and k.stride(2) == 64 and v.stride(2) == 64 and not FORCE_MATERIALIZED_ATTN_BWD:
         # fused flash-style backward: one kernel, nothing of size Nq x Nk touches HBM
         dq_acc = torch.zeros((B, Nq, H, D), dtype=F32, device=dev)
-        dk = torch.empty((B, Nk, H, D), dtype=BF16, device=dev)
-        dv = torch.empty((B, Nk, H, D), dtype=BF16, device=dev)
+        if out is not None:
+            dq, dk, dv = out
+            assert dk.stride() == dv.stride() and dk.stride(2) == D and dq.stride(2) == D
+        else:
+            dq = None
+            dk = torch.empty((B, Nk, H, D), dtype=BF16, device=dev)
+            dv = torch.empty((B, Nk, H, D), dtype=BF16, device=dev)
         check(lib.nk_attention_bwd(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
                                    v.data_ptr(), v.stride(1), v.stride(0), doc.data_ptr(), doc.stride(1), doc.stride(0),
                                    lse.data_ptr(), delta.data_ptr(), dq_acc.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                                   B, H, Nq, Nk, D, float(scale), _stream()), "attention_bwd")
+                                   dk.stride(1), dk.stride(0), B, H, Nq, Nk, D, float(scale), _stream()),
+              "attention_bwd")
         _count(2)
-        return cast_bf16(dq_acc), dk, dv
+        if dq is None:
+            return cast_bf16(dq_acc), dk, dv
+        assert dq.stride(0) == Nq * dq.stride(1)  # rows of all batches are equally spaced: one strided cast
+        check(lib.nk_cast_f32_bf16_rows(dq_acc.data_ptr(), H * D, dq.data_ptr(), dq.stride(1), B * Nq, H * D,
+                                        _stream()), "cast_f32_bf16_rows")
+        _count()
+        return dq, dk, dv
     Nkp = (Nk + 7) // 8 * 8
     P = torch.zeros((B, H, Nq, Nkp), dtype=BF16, device=dev) if Nkp != Nk else torch.empty(
         (B, H, Nq, Nkp), dtype=BF16, device=dev)
@@ -1102,6 +1148,77 @@ class AttentionFn(torch.autograd.Function):
         q, k, v, o, lse = ctx.saved_tensors
         dq, dk, dv = attention_bwd(do, q, k, v, o, lse, ctx.scale)
         return dq, dk, dv, None
+
+
+class SelfAttentionQKVFn(torch.autograd.Function):
+    """o = attention(x Wq^T, x Wk^T, x Wv^T) with the three projections as ONE GEMM (N = 3*inner) in each direction:
+    forward x[M,C] @ [Wv;Wk;Wq]^T, data gradient d[v|k|q][M,3*inner] @ [Wv;Wk;Wq] (which also sums the three
+    contributions to dx), weight gradient d[v|k|q]^T @ x.  The attention kernels read q/k/v and write dq/dk/dv as
+    column slices of the fused buffers.  Stack order v,k,q = the order of the parameters' gradient storage in
+    ddp.BucketedGradReducer (reverse registration), so the fused weight gradient lands in the buckets with one GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, wq, wk, wv, heads, scale):
+        B, N, C = x.shape
+        inner = wq.shape[0]
+        D = inner // heads
+        wf = bf16_weight_group((wv, wk, wq))
+        vkq = linear_fwd(x, wf).view(B, N, 3, heads, D)
+        v, k, q = vkq[:, :, 0], vkq[:, :, 1], vkq[:, :, 2]
+        o, lse = attention_fwd(q, k, v, scale)
+        ctx.save_for_backward(x, vkq, o, lse, wq, wk, wv)
+        ctx.scale = scale
+        return o.view(B, N, inner)
+
+    @staticmethod
+    def backward(ctx, do):
+        x, vkq, o, lse, wq, wk, wv = ctx.saved_tensors
+        B, N, _, H, D = vkq.shape
+        inner = H * D
+        v, k, q = vkq[:, :, 0], vkq[:, :, 1], vkq[:, :, 2]
+        if do.dtype != BF16:
+            do = cast_bf16(do)
+        dvkq = torch.empty_like(vkq)
+        outs = (dvkq[:, :, 2], dvkq[:, :, 1], dvkq[:, :, 0])
+        res = attention_bwd(do.reshape(B, N, H, D), q, k, v, o, lse, ctx.scale, out=outs)
+        for r_, o_ in zip(res, outs):  # the materialised fallback returns fresh tensors
+            if r_.data_ptr() != o_.data_ptr():
+                o_.copy_(r_)
+        d2 = dvkq.view(B * N, 3 * inner)
+        wf = bf16_weight_group((wv, wk, wq))
+        dx = linear_dgrad(d2, wf).view(x.shape) if ctx.needs_input_grad[0] else None
+        grads = [None, None, None]  # for wq, wk, wv
+        need = ctx.needs_input_grad[1:4]
+        sinks = [_grad_sink(w) for w in (wv, wk, wq)]
+        x2 = x.reshape(B * N, -1)
+        stacked = all(need) and all(b is not None for b, _ in sinks) and all(
+            sinks[i][0].data_ptr() + sinks[i][0].numel() * 4 == sinks[i + 1][0].data_ptr() for i in range(2))
+        if stacked:  # [dWv; dWk; dWq] is one contiguous [3*inner, C] block of a gradient bucket
+            bases = tuple(b for _, b in sinks)
+            buf = torch.as_strided(sinks[0][0], (3 * inner, x2.shape[1]), (x2.shape[1], 1))
+            if WGRAD_OVERLAP:
+                _fork_wgrad(lambda: linear_wgrad(d2, x2, out=buf), (d2, x2), bases)
+            else:
+                linear_wgrad(d2, x2, out=buf)
+                for b in bases:
+                    GRAD_SINK.mark_ready(b)
+        else:
+            for slot, (w, col) in enumerate(((wq, 2), (wk, 1), (wv, 0))):
+                if not need[slot]:
+                    continue
+                dy = d2[:, col * inner: (col + 1) * inner]
+                buf, base = _grad_sink(w)
+                if buf is not None:
+                    linear_wgrad(dy, x2, out=buf)
+                    GRAD_SINK.mark_ready(base)
+                else:
+                    grads[slot] = linear_wgrad(dy, x2)
+        return dx, grads[0], grads[1], grads[2], None, None
+
+
+def self_attention_qkv(x: Tensor, wq: Tensor, wk: Tensor, wv: Tensor, heads: int, scale: float) -> Tensor:
+    """fused q/k/v projection + attention for self-attention with head_dim 64; returns (B, N, heads*64)."""
+    return SelfAttentionQKVFn.apply(x, wq, wk, wv, heads, float(scale))
 
 
 def attention(q: Tensor, k: Tensor, v: Tensor, scale: Optional[float] = None) -> Tensor:

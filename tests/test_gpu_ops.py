@@ -302,6 +302,39 @@ def test_attention_fwd_wide_heads_fused(B, H, Nq, Nk, D):
     assert (lse - s_ref).abs().max() < 2e-2
 
 
+@pytest.mark.parametrize("use_sink", [False, True])
+def test_fused_qkv_self_attention_matches_separate_projections(use_sink):
+    """one stacked q|k|v GEMM per direction == three projections + attention (outputs, dx and the three dW)."""
+    from neurosis_b200.ddp import BucketedGradReducer
+    B, N, C, H = 2, 200, 320, 5
+    x = rnd(B, N, C).to(BF).requires_grad_(True)
+    ws = [torch.nn.Parameter(rnd(H * 64, C, seed=10 + i) * C ** -0.5) for i in range(3)]
+    go = rnd(B, N, H * 64, seed=4).to(BF)
+    q, k, v = (ops.linear(x, w).view(B, N, H, 64) for w in ws)
+    o_ref = ops.attention(q, k, v, 0.125).reshape(B, N, H * 64)
+    o_ref.backward(go)
+    ref = [x.grad.clone()] + [w.grad.clone() for w in ws]
+    x.grad = None
+    for w in ws:
+        w.grad = None
+    red = BucketedGradReducer(ws, bucket_mb=64.0) if use_sink else None
+    if red is not None:
+        red.attach_as_grad_sink()
+        red.zero_grad()
+    try:
+        o = ops.self_attention_qkv(x, ws[0], ws[1], ws[2], H, 0.125)
+        o.backward(go)
+        if red is not None:
+            red.finish()
+    finally:
+        if red is not None:
+            red.detach_grad_sink()
+    assert rel(o, o_ref) < 2e-3
+    assert rel(x.grad, ref[0]) < 1e-2  # dx: one fp32 accumulation over 3*inner instead of three bf16-rounded partial sums
+    for w, r in zip(ws, ref[1:]):
+        assert rel(w.grad, r) < 2e-3
+
+
 def test_attention_bwd_materialized_path_d64():
     """the batched-GEMM backward (used for head dims != 64) must agree with the fused kernel's reference too."""
     B, H, N, D = 1, 3, 384, 64
