@@ -199,6 +199,9 @@ int nk_nchw_to_nhwc(const void* src, int src_is_f32, void* dst, const float* sca
                     nk_stream_t stream);
 int nk_nhwc_to_nchw(const void* src, int64_t src_stride, void* dst, int dst_is_f32, int nimg, int C, int HW,
                     nk_stream_t stream);
+/* 3x3 (pad 1) patches of a thin NCHW fp32 image (C = 1, 3 or 4): col[p, tap*C + c] bf16 [nimg*H*W, 64], 9*C used, rest 0.
+ * Feeds the first VAE convolution Encoder.conv_in (3 -> 128, modules/diffusion/model.py:515-517) as a K = 64 GEMM. */
+int nk_image_patches3x3(const float* x, void* col, int nimg, int C, int H, int W, nk_stream_t stream);
 /* explicit im2col / col2im for the stride-2 convolutions (openaimodel.py:183-190; VAE model.py:65-82 with
  * pad (0,1,0,1) expressed as pad_t = pad_l = 0) */
 int nk_im2col(const void* x, int64_t x_stride, void* col, int nimg, int H, int W, int C, int ks, int stride, int pad_t,

@@ -168,6 +168,44 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restri
     }
 }
 
+// ---- 3x3 patches of a thin NCHW fp32 image (the RGB input of the VAE encoder) ------------------------------------
+// col[p, tap*C + c] = x[n, c, y+ky-1, x+kx-1] (zero outside the image), k = 9*C <= 64 values per pixel, zero-padded to
+// 64: the first convolution (3 -> 128 channels) then is ONE 64-deep GEMM k-iteration per tile instead of nine taps
+// over an input padded to 64 channels.  One thread per pixel: loads are coalesced along x for each (c, tap), the
+// thread writes its pixel's full 128-byte row.
+template <int C>
+__global__ void image_patches3x3_kernel(const float* __restrict__ x, bf16* __restrict__ col, int nimg, int H, int W) {
+    const long long total = static_cast<long long>(nimg) * H * W;
+    for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
+         p += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int xw = static_cast<int>(p % W);
+        const int yh = static_cast<int>((p / W) % H);
+        const long long n = p / (static_cast<long long>(W) * H);
+        const float* img = x + n * C * H * W;
+        float v[64];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) v[k] = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+            const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (in) v[tap * C + c] = __ldg(img + (static_cast<long long>(c) * H + yy) * W + xx);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(col + p * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint4 q;
+            q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            dst[j] = q;
+        }
+    }
+}
+
 // ---- channel-slice copy (concat / split of NHWC tensors) -------------------------------------
 __global__ void copy_channels_kernel(const bf16* __restrict__ src, long long src_stride, bf16* __restrict__ dst,
                                      long long dst_stride, long long npix, int C) {
@@ -602,6 +640,17 @@ int nk_cast_f32_bf16_multi(const void* spans_dev, int n_spans, nk_stream_t strea
 }
 int nk_cast_bf16_f32(const void* x, float* y, int64_t n, int accumulate, nk_stream_t stream) {
     cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(CBF(x), y, n, accumulate);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_image_patches3x3(const float* x, void* col, int nimg, int C, int H, int W, nk_stream_t stream) {
+    NK_REQUIRE((C == 1 || C == 3 || C == 4) && nimg > 0 && H > 0 && W > 0, NK_ERR_SHAPE,
+               "image_patches3x3: C=%d (1, 3 or 4)", C);
+    cudaStream_t st = ST(stream);
+    const int grid = grid_for(1LL * nimg * H * W, 128);
+    if (C == 3) image_patches3x3_kernel<3><<<grid, 128, 0, st>>>(x, BF(col), nimg, H, W);
+    else if (C == 4) image_patches3x3_kernel<4><<<grid, 128, 0, st>>>(x, BF(col), nimg, H, W);
+    else image_patches3x3_kernel<1><<<grid, 128, 0, st>>>(x, BF(col), nimg, H, W);
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }

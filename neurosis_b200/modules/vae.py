@@ -183,7 +183,13 @@ class Encoder(nn.Module):
 
     def encode(self, x: Tensor) -> Tensor:
         """(N, 3, H, W) in [-1, 1] -> moments (N, H/8, W/8, 64-padded) NHWC bf16."""
-        h = ops.conv2d(as_nhwc(x, cpad=64), self.conv_in.weight, self.conv_in.bias)
+        w_in = self.conv_in.weight
+        if (x.dim() == 4 and x.shape[1] in (1, 3, 4) and x.dtype == torch.float32 and w_in.shape[0] >= 64
+                and not (torch.is_grad_enabled() and (w_in.requires_grad or x.requires_grad))):
+            # encode path of the training step (no gradients): RGB patches -> one K = 64 GEMM
+            h = ops.conv3x3_thin_input_fwd(x, w_in, self.conv_in.bias)
+        else:
+            h = ops.conv2d(as_nhwc(x, cpad=64), w_in, self.conv_in.bias)
         h = from_nhwc(h)
         for i_level in range(self.num_resolutions):
             for i_block in range(self.num_res_blocks):

@@ -268,6 +268,7 @@ def refresh_weight_copies(force: bool = False) -> None:
         for ent in list(_wcache.values()):
             ent[1].pop("packed", None)
             ent[1].pop("bf16", None)
+            ent[1].pop("patch3x3", None)
     _mirror.refresh()
 
 
@@ -443,6 +444,25 @@ def conv2d_fwd(x: Tensor, wp: Tensor, cout: int, ksize: int, bias: Optional[Tens
         y.data_ptr(), cop, n, h, w_, cin, cout, ksize, _stream())
     _count()
     return y
+
+
+def conv3x3_thin_input_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """First convolution of the VAE encoder (RGB -> 128 channels, 3x3 pad 1), forward only: x (N,C,H,W) fp32 with
+    C in {1,3,4}; the 9*C patch values of every pixel become one 64-deep GEMM row.  Returns (N,H,W,Cout) bf16."""
+    _req_cuda(x)
+    n, c, h, w_ = x.shape
+    co = weight.shape[0]
+    x = x.float().contiguous()
+    col = torch.empty((n * h * w_, 64), dtype=BF16, device=x.device)
+    check(lib.nk_image_patches3x3(x.data_ptr(), col.data_ptr(), n, c, h, w_, _stream()), "image_patches3x3")
+    _count()
+    d = _cache_for(weight)
+    wp = d.get("patch3x3")
+    if wp is None:  # [Cout, 64] bf16, column = tap*C + c (tiny: host-side torch glue, cached per parameter version)
+        w2 = weight.detach().float().permute(0, 2, 3, 1).reshape(co, 9 * c)
+        wp = torch.nn.functional.pad(w2, (0, 64 - 9 * c)).to(BF16).contiguous()
+        d["patch3x3"] = wp
+    return linear_fwd(col, wp, f32_param(bias)).view(n, h, w_, co)
 
 
 def conv2d_stride2_fwd(x: Tensor, wp: Tensor, cout: int, ksize: int, bias: Optional[Tensor], pad_t: int, pad_l: int,

@@ -111,6 +111,18 @@ def test_conv_thin_channels():
     assert rel(w2.grad, w2r.grad) < 1.5e-2
 
 
+@pytest.mark.parametrize("n,c,h,w,co", [(2, 3, 40, 56, 128), (1, 4, 17, 9, 64), (1, 1, 8, 8, 96)])
+def test_conv3x3_thin_input_patches(n, c, h, w, co):
+    """first VAE convolution as RGB patches x [Cout, 64] GEMM (forward only) vs F.conv2d"""
+    x = rnd(n, c, h, w)
+    wt = rnd(co, c, 3, 3, seed=1) * (9 * c) ** -0.5
+    b = rnd(co, seed=2)
+    y = ops.conv3x3_thin_input_fwd(x, wt, b)
+    yr = F.conv2d(x.to(BF).float(), wt.to(BF).float(), b, padding=1)
+    assert y.shape == (n, h, w, co)
+    assert rel(y.permute(0, 3, 1, 2), yr) < 6e-3
+
+
 @pytest.mark.parametrize("n,h,w,c,asym", [(2, 32, 32, 128, False), (2, 32, 32, 128, True), (1, 50, 38, 64, True),
                                           (3, 17, 23, 192, False)])
 def test_conv_stride2(n, h, w, c, asym):
