@@ -22,6 +22,37 @@ TINY_VAE = dict(ch=64, out_ch=3, ch_mult=[1, 2], num_res_blocks=1, attn_resoluti
                 z_channels=4, double_z=True)
 
 
+# full-size UNets of the reference's example YAMLs (configs/sdxl/sdxl.example.yaml:68-84, configs/sd15/sd15.example.yml:68-81)
+FULL_SDXL = dict(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=[4, 2],
+                 channel_mult=[1, 2, 4], num_head_channels=64, transformer_depth=[1, 2, 10], context_dim=2048,
+                 use_linear_in_transformer=True, num_classes="sequential", adm_in_channels=2816,
+                 spatial_transformer_attn_type="torch-sdp", use_checkpoint=False)
+FULL_SD15 = dict(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=[4, 2, 1],
+                 channel_mult=[1, 2, 4, 4], num_heads=8, transformer_depth=1, context_dim=768,
+                 use_linear_in_transformer=False, spatial_transformer_attn_type="torch-sdp", use_checkpoint=False)
+
+
+def fast_state_dict(shapes: dict, seed: int = 0) -> dict:
+    """same distributions as oracle.weights.synth_state_dict, drawn with torch's generator (seconds instead of minutes for
+    the 2.57 B-parameter SDXL UNet); only for tests where both sides load the SAME dict (no golden involved)."""
+    import torch
+    g = torch.Generator().manual_seed(1234 + seed)
+    sd = {}
+    for name in sorted(shapes):
+        shape = tuple(shapes[name])
+        n = torch.randn(shape, generator=g)
+        if name.endswith(".bias"):
+            sd[name] = n * 0.05
+        elif len(shape) == 1:
+            sd[name] = 1.0 + n * 0.1
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            sd[name] = n * fan_in ** -0.5
+    return sd
+
+
 def have_reference() -> bool:
     return REFERENCE_SRC.exists()
 
