@@ -140,8 +140,11 @@ def run_reference(args) -> None:
     line = {"impl": "reference", "metric": METRIC, "value": r["img_per_s"], "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_sample_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SDXL base UNet 1024x1024 training step (VAE encode + loss + backward)",
-                       "note": "reference's CPU path restated in oracle/ (reference is pure PyTorch; lightning-dependent glue restated)"},
+            "config": {"workload": "SDXL base UNet (configs/sdxl) 1024x1024 training step: VAE encode + diffusion loss + backward",
+                       "batch_per_gpu": args.batch, "global_batch": args.batch, "latent": "128x128x4", "parallelism": "dp1",
+                       "note": "the reference's own CPU implementation of the path (pure PyTorch fp32) restated in "
+                               "oracle/ and timed on the host cores; each step is a bounded sample (256x256 px, "
+                               "batch 1) scaled to 1024x1024 images/s by the algorithmic FLOP ratio"},
             "cpu_baseline": {"value": r["img_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port",
                              "sample": r["sample"]},
             "e2e": {"value": r["img_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -196,6 +199,9 @@ def main() -> None:
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--breakdown", default="", help="write a per-call-site breakdown of tensor-core time to this file")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="run under `ncu --profile-from-start off`: after the warm-up, ONE eager step inside a "
+                         "profiler range, then exit (the per-launch list committed under profiles/)")
     ap.add_argument("--ncu-sample", type=int, default=0,
                     help="run under `ncu --profile-from-start off`: after the warm-up, ONE eager step with every N-th "
                          "tensor-core launch inside a profiler range, then exit (feeds roofline.traffic)")
@@ -244,6 +250,13 @@ def main() -> None:
     for _ in range(2):
         eager_step(resident, False)
     torch.cuda.synchronize()
+    if args.ncu_step:  # under `ncu --profile-from-start off`: exactly one eager step inside the profiler range
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        eager_step(resident, False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     if args.ncu_sample > 0:
         ops.NCU_SAMPLE = args.ncu_sample
         eager_step(resident, False)
