@@ -528,17 +528,12 @@ int make_operand_tmap(CUtensorMap* tm, const GemmOperand& o, int box_rows_or_bw,
         box[2] = static_cast<uint32_t>(box_bh);
         box[3] = 1;
         if (pix_stride > 1) {
-            // a box that lands bw x bh pixels taken every `pix_stride`-th pixel spans bw*stride x bh*stride tensor elements
-            static int span = -1;
-            if (span < 0) {
-                const char* e_ = getenv("NK_TMA_STRIDE_BOX");  // "count": box dims count landed elements (A/B switch)
-                span = (e_ && e_[0] == 'c') ? 0 : 1;
-            }
+            // a box that lands bw x bh pixels taken every `pix_stride`-th pixel spans bw*stride x bh*stride tensor
+            // elements: cuTensorMapEncodeTiled counts boxDim in traversed elements (verified on B200: the other reading
+            // hangs on expect_tx)
             estr[1] = estr[2] = static_cast<uint32_t>(pix_stride);
-            if (span) {
-                box[1] *= static_cast<uint32_t>(pix_stride);
-                box[2] *= static_cast<uint32_t>(pix_stride);
-            }
+            box[1] *= static_cast<uint32_t>(pix_stride);
+            box[2] *= static_cast<uint32_t>(pix_stride);
         }
     }
     return encode_tmap(tm, o.ptr, 4, dims, strides, box, 0, estr);
