@@ -160,7 +160,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The whole warp walks the k-loop; lane 0 waits for the ring slot and posts the expected byte count, then
+        // lane l issues the l-th TMA load of the k-iteration (up to 6: MN-major operands are loaded per 64-wide atom),
+        // so the issue latency of several cp.async.bulk.tensor instructions is not serialised on one thread.
+        {
             int stage = 0;
             uint32_t phase = 0;
             long long dbg_acc0 = 0;
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 if (CG == 2) tma_load_4d_2cta(tm, bar, dst, c0, c1, c2, c3);
                 else tma_load_4d(tm, bar, dst, c0, c1, c2, c3);
             };
+            const int nb_atoms = BNc / 64;  // MN-major / wgrad B tiles: 64-wide atoms per CTA
             for (int t = group; t < total_tiles; t += num_groups) {
                 const TileCoord tc = decode_tile(g, t);
                 const int n0 = tc.nt * g.BN + static_cast<int>(rank) * BNc;  // this CTA's slice of the B tile
@@ -175,64 +179,88 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 const int m0 = mt * BM;
                 const int iters = iters_of_split(g, tc.split);
                 int img = 0, th = 0, tw = 0;
+                // Every integer division in this k-loop is ~40 clk of latency that delays all operand traffic of the CTA
+                // (the conv weight gradient spent 1 500 clk per k-iteration here, 3x the tensor time).  Everything that
+                // depends only on the tile is computed once; the k-dependent indices (filter tap / channel block, or the
+                // pixel tile) advance incrementally.
+                int cb = 0, dy = 0, dx = 0;      // conv forward: k-iteration -> (tap = (dy, dx), 64-channel block)
+                int ptw = 0, pth = 0, pimg = 0;  // conv wgrad:   k-iteration -> 64-pixel tile
+                int my_c0 = 0, my_dx = 0, my_dy = 0;  // conv wgrad: channel block and tap shift of THIS lane's B atom
+                const int gi0 = tc.split * g.k_iters;
                 if (g.mode == MODE_CONV_FWD) {
                     tw = mt % g.tiles_w;
                     th = (mt / g.tiles_w) % g.tiles_h;
                     img = mt / (g.tiles_w * g.tiles_h);  // may be >= nimg for the odd last tile: TMA zero-fills
+                    const int tap = gi0 / g.cin_blocks;
+                    cb = gi0 - tap * g.cin_blocks;
+                    dy = tap / g.ksize;
+                    dx = tap - dy * g.ksize;
+                } else if (g.mode == MODE_CONV_WGRAD) {
+                    ptw = gi0 % g.tiles_w;
+                    pth = (gi0 / g.tiles_w) % g.tiles_h;
+                    pimg = gi0 / (g.tiles_w * g.tiles_h);
+                    // every 64-channel atom of the B tile carries its own filter tap (its own pixel shift), so a
+                    // 256-wide N tile may straddle taps; atoms past N are fetched out of range (zero-filled)
+                    const int atom = (n0 >> 6) + max(lane - 2, 0);
+                    const int t_ = atom / g.cin_blocks;
+                    const bool in_range = t_ < g.ksize * g.ksize;
+                    my_c0 = in_range ? ((atom - t_ * g.cin_blocks) << 6) : (g.cin_blocks << 6);
+                    my_dy = t_ / g.ksize - g.pad;
+                    my_dx = t_ % g.ksize - g.pad;
                 }
+                const int x0 = g.cstride * (tw * g.bw) - g.pad_l, y0 = g.cstride * (th * g.bh) - g.pad_t;
                 for (int it = 0; it < iters; ++it) {
-                    const int gi = tc.split * g.k_iters + it;
-                    const long long tw0 = g.dbg ? clock64() : 0;
-                    mbar_wait(&empty_bar[stage], phase ^ 1u, 100u + stage);
-                    if (g.dbg) dbg_acc0 += clock64() - tw0;
-                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * (g.a_bytes + g.b_bytes));
+                    const int gi = gi0 + it;
+                    if (lane == 0) {
+                        const long long tw0 = g.dbg ? clock64() : 0;
+                        mbar_wait(&empty_bar[stage], phase ^ 1u, 100u + stage);
+                        if (g.dbg) dbg_acc0 += clock64() - tw0;
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * (g.a_bytes + g.b_bytes));
+                    }
+                    __syncwarp();
                     uint8_t* sa = smem_a + static_cast<size_t>(stage) * A_STAGE_BYTES;
                     uint8_t* sb = smem_b + static_cast<size_t>(stage) * b_stage_bytes;
                     if (g.mode == MODE_PLAIN) {
                         const int k0 = gi * BK;
-                        if (!g.a_mn) {
-                            tma_load(&g.tmA, &full_bar[stage], sa, k0, m0, tc.b2 * g.a_b2,
-                                        tc.b1 * g.a_b1);
-                        } else {
-                            tma_load(&g.tmA, &full_bar[stage], sa, m0, k0, tc.b2 * g.a_b2,
-                                        tc.b1 * g.a_b1);
-                            tma_load(&g.tmA, &full_bar[stage], sa + ATOM_BYTES, m0 + 64, k0,
-                                        tc.b2 * g.a_b2, tc.b1 * g.a_b1);
-                        }
-                        if (!g.b_mn) {
-                            tma_load(&g.tmB, &full_bar[stage], sb, k0, n0, tc.b2 * g.b_b2,
-                                        tc.b1 * g.b_b1);
-                        } else {
-                            for (int j = 0; j < BNc / 64; ++j)
-                                tma_load(&g.tmB, &full_bar[stage], sb + j * ATOM_BYTES,
-                                            n0 + 64 * j, k0, tc.b2 * g.b_b2, tc.b1 * g.b_b1);
+                        const int na = g.a_mn ? 2 : 1;
+                        const int nb = g.b_mn ? nb_atoms : 1;
+                        if (lane < na) {
+                            if (!g.a_mn)
+                                tma_load(&g.tmA, &full_bar[stage], sa, k0, m0, tc.b2 * g.a_b2, tc.b1 * g.a_b1);
+                            else
+                                tma_load(&g.tmA, &full_bar[stage], sa + lane * ATOM_BYTES, m0 + 64 * lane, k0,
+                                         tc.b2 * g.a_b2, tc.b1 * g.a_b1);
+                        } else if (lane < na + nb) {
+                            const int j = lane - na;
+                            if (!g.b_mn)
+                                tma_load(&g.tmB, &full_bar[stage], sb, k0, n0, tc.b2 * g.b_b2, tc.b1 * g.b_b1);
+                            else
+                                tma_load(&g.tmB, &full_bar[stage], sb + j * ATOM_BYTES, n0 + 64 * j, k0, tc.b2 * g.b_b2,
+                                         tc.b1 * g.b_b1);
                         }
                     } else if (g.mode == MODE_CONV_FWD) {
-                        const int tap = gi / g.cin_blocks;
-                        const int cb = gi - tap * g.cin_blocks;
-                        const int dy = tap / g.ksize - g.pad_t;
-                        const int dx = tap % g.ksize - g.pad_l;
-                        tma_load(&g.tmA, &full_bar[stage], sa, cb * 64, g.cstride * (tw * g.bw) + dx,
-                                    g.cstride * (th * g.bh) + dy, img);
-                        tma_load(&g.tmB, &full_bar[stage], sb, gi * BK, n0, 0, 0);
+                        if (lane == 0) tma_load(&g.tmA, &full_bar[stage], sa, cb * 64, x0 + dx, y0 + dy, img);
+                        else if (lane == 1) tma_load(&g.tmB, &full_bar[stage], sb, gi * BK, n0, 0, 0);
+                        if (++cb == g.cin_blocks) {  // next filter tap
+                            cb = 0;
+                            if (++dx == g.ksize) {
+                                dx = 0;
+                                ++dy;
+                            }
+                        }
                     } else {  // MODE_CONV_WGRAD: k-iteration = one 64-pixel tile; N index = tap*Cin + ci
-                        const int ptw = gi % g.tiles_w;
-                        const int pth = (gi / g.tiles_w) % g.tiles_h;
-                        const int pimg = gi / (g.tiles_w * g.tiles_h);
-                        tma_load(&g.tmA, &full_bar[stage], sa, m0, ptw * g.bw, pth * g.bh, pimg);
-                        tma_load(&g.tmA, &full_bar[stage], sa + ATOM_BYTES, m0 + 64, ptw * g.bw,
-                                    pth * g.bh, pimg);
-                        // every 64-channel atom of the B tile carries its own filter tap (its own pixel shift), so a
-                        // 256-wide N tile may straddle taps; atoms past N are fetched out of range (zero-filled)
-                        for (int j = 0; j < BNc / 64; ++j) {
-                            const int atom = (n0 >> 6) + j;
-                            const int tap = atom / g.cin_blocks;
-                            const int c0 = (atom - tap * g.cin_blocks) << 6;
-                            const bool in_range = tap < g.ksize * g.ksize;
-                            const int dy = tap / g.ksize - g.pad;
-                            const int dx = tap % g.ksize - g.pad;
-                            tma_load(&g.tmB, &full_bar[stage], sb + j * ATOM_BYTES, in_range ? c0 : (g.cin_blocks << 6),
-                                        ptw * g.bw + dx, pth * g.bh + dy, pimg);
+                        const int px = ptw * g.bw, py = pth * g.bh;
+                        if (lane < 2)
+                            tma_load(&g.tmA, &full_bar[stage], sa + lane * ATOM_BYTES, m0 + 64 * lane, px, py, pimg);
+                        else if (lane < 2 + nb_atoms)
+                            tma_load(&g.tmB, &full_bar[stage], sb + (lane - 2) * ATOM_BYTES, my_c0, px + my_dx, py + my_dy,
+                                     pimg);
+                        if (++ptw == g.tiles_w) {  // next pixel tile
+                            ptw = 0;
+                            if (++pth == g.tiles_h) {
+                                pth = 0;
+                                ++pimg;
+                            }
                         }
                     }
                     if (++stage == stages) {
@@ -241,7 +269,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     }
                 }
             }
-            if (g.dbg) g.dbg[blockIdx.x * 8 + 0] = dbg_acc0;
+            if (g.dbg && lane == 0) g.dbg[blockIdx.x * 8 + 0] = dbg_acc0;
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA of the pair only) =====================
@@ -542,6 +570,12 @@ int make_operand_tmap(CUtensorMap* tm, const GemmOperand& o, int box_rows_or_bw,
 // tile width (and CTA-group size) minimising waves x per-k16 cost.  `groups` = CTA groups that run concurrently.
 int pick_bn(const GemmProblem& p, long long tiles_m_batches, int groups, int cg) {
     if (p.force_bn > 0) return p.force_bn;
+    static int env_bn = -1;
+    if (env_bn < 0) {
+        const char* e_ = getenv("NK_GEMM_FORCE_BN");  // experiment switch
+        env_bn = e_ ? atoi(e_) : 0;
+    }
+    if (env_bn > 0) return env_bn;
     const int step = p.B.mn_major ? 64 * cg : 16 * cg;
     long long best_cost = -1;
     int best = 256;
@@ -687,8 +721,13 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     if (p.out == OUT_F32_ATOMIC) {
         const long long tiles = tiles_mb * g.tiles_n;
         const int groups = nsm / cg;
-        if (p.force_splits > 0) {
-            splits = p.force_splits;
+        static int env_splits = -1;
+        if (env_splits < 0) {
+            const char* e_ = getenv("NK_GEMM_FORCE_SPLITS");  // experiment switch
+            env_splits = e_ ? atoi(e_) : 0;
+        }
+        if (p.force_splits > 0 || env_splits > 0) {
+            splits = p.force_splits > 0 ? p.force_splits : env_splits;
         } else {
             const int max_s = std::max(1, std::min(64, g.k_iters_total / 4));
             long long best = -1;

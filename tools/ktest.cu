@@ -382,10 +382,14 @@ static Case cases[] = {
     {"conv_cout4", []() { return test_conv("conv_cout4 1x32x32 320->4 k3", 1, 32, 32, 320, 4, 3, true); }},
     {"conv_big", []() { return test_conv("conv_big 4x64x64 640->640 k3", 4, 64, 64, 640, 640, 3, true); }},
     {"conv_sdxl128", []() { return test_conv("conv_sdxl128 2x128x128 320->320 k3", 2, 128, 128, 320, 320, 3, true); }},
+    {"conv_vae1024", []() { return test_conv("conv_vae1024 1x1024x1024 128->128 k3", 1, 1024, 1024, 128, 128, 3, true); }},
     {"cwgrad_small", []() { return test_conv_wgrad("cwgrad_small 1x16x16 64->64 k3", 1, 16, 16, 64, 64, 3); }},
     {"cwgrad_mid", []() { return test_conv_wgrad("cwgrad_mid 2x32x32 128->192 k3", 2, 32, 32, 128, 192, 3); }},
     {"cwgrad_bucket", []() { return test_conv_wgrad("cwgrad_bucket 1x36x28 64->64 k3", 1, 36, 28, 64, 64, 3); }},
     {"cwgrad_w128", []() { return test_conv_wgrad("cwgrad_w128 1x16x128 64->128 k3", 1, 16, 128, 64, 128, 3); }},
+    {"cwgrad_sdxl128", []() { return test_conv_wgrad("cwgrad_sdxl128 4x128x128 320->320 k3", 4, 128, 128, 320, 320, 3); }},
+    {"cwgrad_sdxl128b16", []() { return test_conv_wgrad("cwgrad_sdxl128b16 16x128x128 320->320 k3", 16, 128, 128, 320, 320, 3); }},
+    {"cwgrad_sdxl32", []() { return test_conv_wgrad("cwgrad_sdxl32 8x32x32 1280->1280 k3", 8, 32, 32, 1280, 1280, 3); }},
     {"bqk_d64", []() { return test_batched_qk("bqk_d64 B2 H3 256x200 d64", 2, 3, 256, 200, 64); }},
     {"bqk_d40", []() { return test_batched_qk("bqk_d40 B1 H8 128x77 d40", 1, 8, 128, 77, 40); }},
 };
