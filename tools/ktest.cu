@@ -65,8 +65,8 @@ __global__ void ref_gemm(const bf16* A, long long sam, long long sak, long long 
 // y[n,h,w,co] = sum x[n,h+dy,w+dx,ci] * wp[co, tap*Cin+ci]
 __global__ void ref_conv(const bf16* x, const bf16* wp, float* y, int nimg, int H, int W, int Cin,
                          int Cout, int ks) {
-    int co = blockIdx.x * blockDim.x + threadIdx.x;
-    long long pix = blockIdx.y;
+    int co = blockIdx.y * blockDim.x + threadIdx.x;
+    long long pix = blockIdx.x;  // grid.x: up to 2^31-1 pixels
     if (co >= Cout) return;
     int w = pix % W;
     int h = (pix / W) % H;
@@ -274,7 +274,8 @@ static int test_conv(const char* name, int nimg, int H, int W, int Cin, int Cout
     fillb(r, npix * Cout, 11);
     fillf(b, Cout, 12);
     fillf(bi, (size_t)nimg * Cout, 13);
-    ref_conv<<<dim3((Cout + 127) / 128, (unsigned)npix), 128>>>(x, wp, ref, nimg, H, W, Cin, Cout, ks);
+    ref_conv<<<dim3((unsigned)npix, (Cout + 127) / 128), 128>>>(x, wp, ref, nimg, H, W, Cin, Cout, ks);
+    CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     double ms = time_ms([&]() {
         must(nk_conv2d_fwd(x, Cin, wp, extras ? b : nullptr, extras ? bi : nullptr, extras ? r : nullptr, Cout, y,
@@ -363,6 +364,9 @@ static Case cases[] = {
     {"lin_tiny_n", []() { return test_linear("lin_tiny_n 512x4x320", 512, 4, 320, true, false, false); }},
     {"lin_m2", []() { return test_linear("lin_m2 2x1280x320 (embed MLP)", 2, 1280, 320, true, false, true); }},
     {"lin_big", []() { return test_linear("lin_big 8192x1280x1280", 8192, 1280, 1280, true, true, false); }},
+    {"lin_640", []() { return test_linear("lin_640 49152x640x640", 49152, 640, 640, true, true, false); }},
+    {"lin_big16", []() { return test_linear("lin_big16 16384x1280x1280", 16384, 1280, 1280, true, true, false); }},
+    {"lin_320", []() { return test_linear("lin_320 49152x320x1280", 49152, 320, 1280, true, false, false); }},
     {"lin_ff", []() { return test_linear("lin_ff 8192x10240x1280", 8192, 10240, 1280, true, false, false); }},
     {"mainloop_n256", []() { return test_linear("mainloop_n256 18944x256x16384 (1 tile/pair, pure k-loop)", 18944, 256, 16384, false, false, false); }},
     {"mainloop_n128", []() { return test_linear("mainloop_n128 18944x128x16384 (1 tile/pair, pure k-loop)", 18944, 128, 16384, false, false, false); }},
