@@ -443,6 +443,45 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, bf16* __res
         if (wd) wd[(static_cast<long long>(ci) * taps + (taps - 1 - tap)) * CoP + co] = bv;
     }
 }
+// Same packing, tiled through shared memory so that all three global streams are coalesced: a block owns 32 output
+// x 32 input channels, reads their (32 x 32*taps) fp32 block as contiguous row segments, and writes 64-byte bf16 row
+// segments of both packings (the scalar kernel above reads with a stride of `taps` floats and scatters 2-byte stores
+// for the transposed packing).  Requires Co, Ci, CoP, CiP multiples of 32.
+__global__ void __launch_bounds__(256) pack_conv_weight_tiled_kernel(const float* __restrict__ w, bf16* __restrict__ wp,
+                                                                     bf16* __restrict__ wd, int Co, int Ci, int taps,
+                                                                     int CoP, int CiP) {
+    extern __shared__ bf16 tile[];  // [32 co][32*taps + 2]  (ci-major within a row: index ci*taps + tap)
+    const int ld = 32 * taps + 2;
+    const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+    const int row_len = 32 * taps;  // floats per co row of this block, contiguous in w
+    for (int idx = threadIdx.x; idx < 32 * row_len; idx += blockDim.x) {
+        const int r = idx / row_len, c = idx - r * row_len;
+        const int co = co0 + r;
+        const int ci = ci0 + c / taps;
+        float v = 0.f;
+        if (co < Co && ci < Ci) v = w[(static_cast<long long>(co) * Ci + ci0) * taps + c];
+        tile[r * ld + c] = __float2bfloat16(v);
+    }
+    __syncthreads();
+    // forward packing: wp[co, tap*CiP + ci]  -> for each (co, tap): 32 consecutive ci
+    if (wp) {
+        for (int idx = threadIdx.x; idx < 32 * taps * 32; idx += blockDim.x) {
+            const int ci = idx & 31;
+            const int t = (idx >> 5) % taps;
+            const int r = idx / (32 * taps);
+            wp[(static_cast<long long>(co0 + r) * taps + t) * CiP + ci0 + ci] = tile[r * ld + ci * taps + t];
+        }
+    }
+    // data-gradient packing: wd[ci, tapf*CoP + co], tapf = taps-1-tap -> for each (ci, tap): 32 consecutive co
+    if (wd) {
+        for (int idx = threadIdx.x; idx < 32 * taps * 32; idx += blockDim.x) {
+            const int r = idx & 31;  // co within the block (fastest: contiguous in wd)
+            const int t = (idx >> 5) % taps;
+            const int ci = idx / (32 * taps);
+            wd[(static_cast<long long>(ci0 + ci) * taps + (taps - 1 - t)) * CoP + co0 + r] = tile[r * ld + ci * taps + t];
+        }
+    }
+}
 // dw[co, ci, ky, kx] += dwp[co, tap, ci]   (dwp row stride = taps*CiP)
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int ks,
                                          int CiP, int accumulate) {
@@ -732,8 +771,16 @@ int nk_timestep_embedding(const float* t, void* out, int B, int dim, float max_p
 int nk_conv_pack_weights(const float* w, void* wp_fwd, void* wp_dgrad, int Co, int Ci, int ks, int CoP, int CiP,
                          nk_stream_t stream) {
     NK_REQUIRE(CoP >= Co && CiP >= Ci, NK_ERR_SHAPE, "pack: padded dims too small");
-    pack_conv_weight_kernel<<<grid_for(1LL * CoP * ks * ks * CiP, 256), 256, 0, ST(stream)>>>(w, BF(wp_fwd), BF(wp_dgrad), Co, Ci,
-                                                                                           ks, CoP, CiP);
+    cudaStream_t st = ST(stream);
+    const int taps = ks * ks;
+    if (Co % 32 == 0 && Ci % 32 == 0 && CoP == Co && CiP == Ci && taps <= 9) {
+        const size_t smem = static_cast<size_t>(32) * (32 * taps + 2) * sizeof(bf16);
+        pack_conv_weight_tiled_kernel<<<dim3(Ci / 32, Co / 32), 256, smem, st>>>(w, BF(wp_fwd), BF(wp_dgrad), Co, Ci, taps,
+                                                                                CoP, CiP);
+    } else {
+        pack_conv_weight_kernel<<<grid_for(1LL * CoP * ks * ks * CiP, 256), 256, 0, st>>>(w, BF(wp_fwd), BF(wp_dgrad), Co,
+                                                                                         Ci, ks, CoP, CiP);
+    }
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }
