@@ -165,9 +165,11 @@ int nk_groupnorm_bwd(const void* dy, int64_t dy_pix_stride, const void* x, int64
 int nk_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
                      float* mean, float* rstd, int rows, int C, float eps, nk_stream_t stream);
 /* dgamma/dbeta fp32 [C] accumulated with atomics (+=). */
+/* dres (nullable, bf16 [rows, lddres]): gradient that reaches x through the residual branch around the norm
+ * (x -> LN -> f(.) + x, modules/attention.py:497-511); it is added into dx, so autograd needs no separate add. */
 int nk_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
-                     const float* mean, const float* rstd, void* dx, int64_t lddx, float* dgamma, float* dbeta,
-                     int rows, int C, nk_stream_t stream);
+                     const float* mean, const float* rstd, const void* dres, int64_t lddres, void* dx, int64_t lddx,
+                     float* dgamma, float* dbeta, int rows, int C, nk_stream_t stream);
 
 /* ---- elementwise / layout (HBM-bound) --------------------------------------------------------- */
 /* GEGLU: h = [value | gate] (bf16 [M, 2D]); out = value * gelu_erf(gate).  modules/attention.py:50-57 */

@@ -400,7 +400,8 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const bf16* __restrict__
                                                         const bf16* __restrict__ x, long long ldx, bf16* __restrict__ dx,
                                                         long long lddx, const float* __restrict__ gamma,
                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                        int rows, int C) {
+                                                        const bf16* __restrict__ dres, long long lddres, int rows,
+                                                        int C) {
     const int V = C / 8;
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -454,6 +455,16 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const bf16* __restrict__
                     const float2 fd = unpack_bf16x2(wd[e]);
                     const float xh0 = (fx.x - m) * r, xh1 = (fx.y - m) * r;
                     o[e] = pack_bf16x2(r * (fd.x * g[2 * e] - s1 - xh0 * s2), r * (fd.y * g[2 * e + 1] - s1 - xh1 * s2));
+                }
+                if (dres) {  // gradient arriving through the residual branch that bypasses this norm: dx += dres
+                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(dres + row * lddres + v * 8));
+                    const uint32_t wr[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 a = unpack_bf16x2(o[e]);
+                        const float2 b2 = unpack_bf16x2(wr[e]);
+                        o[e] = pack_bf16x2(a.x + b2.x, a.y + b2.y);
+                    }
                 }
                 *reinterpret_cast<uint4*>(dx + row * lddx + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
             }
@@ -611,8 +622,8 @@ int nk_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float
 }
 
 int nk_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
-                     const float* mean, const float* rstd, void* dx, int64_t lddx, float* dgamma, float* dbeta,
-                     int rows, int C, nk_stream_t stream) {
+                     const float* mean, const float* rstd, const void* dres, int64_t lddres, void* dx, int64_t lddx,
+                     float* dgamma, float* dbeta, int rows, int C, nk_stream_t stream) {
     NK_REQUIRE(C % 8 == 0 && C <= 2048, NK_ERR_SHAPE, "layernorm bwd: C=%d", C);
     cudaStream_t st = ::nk::enter(stream);
     const int wpb = 8;
@@ -620,15 +631,18 @@ int nk_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, c
     const int V = C / 8;
     const bf16* dyp = static_cast<const bf16*>(dy);
     const bf16* xp = static_cast<const bf16*>(x);
+    const bf16* rp = static_cast<const bf16*>(dres);
+    NK_REQUIRE(!dres || (lddres % 8 == 0 && (reinterpret_cast<uintptr_t>(dres) & 15u) == 0), NK_ERR_SHAPE,
+               "layernorm bwd: dres alignment");
     if (V <= 64)
         ln_bwd_dx_kernel<2><<<grid, wpb * 32, 0, st>>>(dyp, lddy, xp, ldx, static_cast<bf16*>(dx), lddx, gamma, mean,
-                                                       rstd, rows, C);
+                                                       rstd, rp, lddres, rows, C);
     else if (V <= 160)
         ln_bwd_dx_kernel<5><<<grid, wpb * 32, 0, st>>>(dyp, lddy, xp, ldx, static_cast<bf16*>(dx), lddx, gamma, mean,
-                                                       rstd, rows, C);
+                                                       rstd, rp, lddres, rows, C);
     else
         ln_bwd_dx_kernel<8><<<grid, wpb * 32, 0, st>>>(dyp, lddy, xp, ldx, static_cast<bf16*>(dx), lddx, gamma, mean,
-                                                       rstd, rows, C);
+                                                       rstd, rp, lddres, rows, C);
     if (dgamma && dbeta) {
         const int col_blocks = (C + 255) / 256;
         const int row_chunks = std::max(1, std::min(rows / 64, (148 * 6) / col_blocks));

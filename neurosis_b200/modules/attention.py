@@ -146,13 +146,21 @@ class BasicTransformerBlock(nn.Module):
     def _ln(self, norm: nn.LayerNorm, x: Tensor) -> Tensor:
         return ops.layer_norm(x, norm.weight, norm.bias, norm.eps)
 
+    def _ln_res(self, norm: nn.LayerNorm, x: Tensor):
+        return ops.layer_norm_residual(x, norm.weight, norm.bias, norm.eps)
+
     def _forward(self, x: Tensor, context: Optional[Tensor] = None, additional_tokens: Optional[Tensor] = None,
                  n_times_crossframe_attn_in_self: int = 0) -> Tensor:
         if additional_tokens is not None or n_times_crossframe_attn_in_self:
             raise NotImplementedError("additional_tokens / cross-frame attention are not supported")
-        x = self.attn1(self._ln(self.norm1, x), context=context if self.disable_self_attn else None, residual=x)
-        x = self.attn2(self._ln(self.norm2, x), context=context, residual=x)
-        x = self.ff(self._ln(self.norm3, x), residual=x)
+        # x -> x + f(LN(x)), three times; `_ln_res` hands x back so that the gradient of the residual use is folded into
+        # the LayerNorm-backward kernel instead of a separate autograd add
+        x, h = self._ln_res(self.norm1, x)
+        x = self.attn1(h, context=context if self.disable_self_attn else None, residual=x)
+        x, h = self._ln_res(self.norm2, x)
+        x = self.attn2(h, context=context, residual=x)
+        x, h = self._ln_res(self.norm3, x)
+        x = self.ff(h, residual=x)
         return x
 
 

@@ -569,8 +569,10 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float):
     return y.view(x.shape), mean, rstd
 
 
-def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, out: Optional[tuple] = None):
-    """`out` = (dgamma, dbeta) fp32 buffers the parameter gradients are ADDED to (gradient buckets)."""
+def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, out: Optional[tuple] = None,
+                  dres: Optional[Tensor] = None):
+    """`out` = (dgamma, dbeta) fp32 buffers the parameter gradients are ADDED to (gradient buckets); `dres` (bf16, shape
+    of x) is a gradient that bypasses the norm through a residual connection and is added into dx."""
     c = x.shape[-1]
     x2 = x.reshape(-1, c)
     d2 = dy.reshape(-1, c)
@@ -585,9 +587,17 @@ def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tens
     else:
         dgamma = torch.zeros((c,), dtype=F32, device=x.device)
         dbeta = torch.zeros((c,), dtype=F32, device=x.device)
+    r2 = None
+    if dres is not None:
+        r2 = dres.reshape(-1, c)
+        if r2.dtype != BF16:
+            r2 = cast_bf16(r2)
+        if r2.stride(-1) != 1:
+            r2 = r2.contiguous()
     check(lib.nk_layernorm_bwd(d2.data_ptr(), d2.stride(0), x2.data_ptr(), x2.stride(0), gamma.data_ptr(),
-                               mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), c, dgamma.data_ptr(), dbeta.data_ptr(),
-                               rows, c, _stream()), "layernorm_bwd")
+                               mean.data_ptr(), rstd.data_ptr(), _p(r2), r2.stride(0) if r2 is not None else 0,
+                               dx.data_ptr(), c, dgamma.data_ptr(), dbeta.data_ptr(), rows, c, _stream()),
+          "layernorm_bwd")
     _count(2)
     return dx.view(x.shape), dgamma, dbeta
 
@@ -1107,6 +1117,38 @@ class LayerNormFn(torch.autograd.Function):
 
 def layer_norm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tensor:
     return LayerNormFn.apply(x, gamma, beta, eps)
+
+
+class LayerNormResidualFn(torch.autograd.Function):
+    """(x, LN(x)) for the pre-norm residual pattern  x -> x + f(LN(x)):  the first output is x itself and carries the
+    residual branch.  Backward receives the gradients of BOTH uses of x at once and adds the residual one inside the
+    LayerNorm-backward kernel, so the autograd engine never launches a separate gradient add for the fork."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        g, b = f32_param(gamma), f32_param(beta)
+        y, mean, rstd = layernorm_fwd(x, g, b, eps)
+        ctx.save_for_backward(x, g, mean, rstd)
+        ctx.params = (gamma, beta)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, dres, dy):
+        x, g, mean, rstd = ctx.saved_tensors
+        if dy is None:  # LN branch unused: only the residual gradient flows
+            return dres, None, None, None
+        bufs, bases = _grad_sink_pair(*ctx.params) if (ctx.needs_input_grad[1] and ctx.needs_input_grad[2]) else (None, None)
+        dx, dg, db = layernorm_bwd(dy, x, g, mean, rstd, out=bufs, dres=dres)
+        if bufs is not None:
+            GRAD_SINK.mark_ready(bases[0])
+            GRAD_SINK.mark_ready(bases[1])
+            dg = db = None
+        return dx, dg, db, None
+
+
+def layer_norm_residual(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5):
+    """returns (x, LN(x)); use the returned x for the residual add that follows (see LayerNormResidualFn)."""
+    return LayerNormResidualFn.apply(x, gamma, beta, eps)
 
 
 class GegluFn(torch.autograd.Function):

@@ -183,6 +183,27 @@ def test_layernorm_fwd_bwd(rows, c):
     assert rel(b.grad, br.grad) < 5e-3
 
 
+def test_layernorm_residual_fork_gradient_is_fused():
+    """x -> x + W LN(x): the (x, LN(x)) function folds the residual-branch gradient into the LN-backward kernel."""
+    rows, c = 777, 640
+    x = (rnd(rows, c) * 1.2).to(BF).requires_grad_(True)
+    g = (1 + 0.2 * rnd(c, seed=1)).requires_grad_(True)
+    b = (0.1 * rnd(c, seed=2)).requires_grad_(True)
+    w = (rnd(c, c, seed=3) * c ** -0.5).requires_grad_(True)
+    gy = rnd(rows, c, seed=4).to(BF)
+    xr_, h = ops.layer_norm_residual(x, g, b, 1e-5)
+    y = ops.linear(h, w, None, xr_)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    gr, br = g.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    wr = w.detach().to(BF).float().requires_grad_(True)
+    yr = xr + F.linear(F.layer_norm(xr, (c,), gr, br, 1e-5), wr)
+    yr.backward(gy.float())
+    assert rel(y, yr) < 6e-3
+    assert rel(x.grad, xr.grad) < 8e-3
+    assert rel(g.grad, gr.grad) < 6e-3 and rel(b.grad, br.grad) < 6e-3 and rel(w.grad, wr.grad) < 6e-3
+
+
 def test_norm_and_bias_gradients_into_grad_sink():
     """dgamma / dbeta / bias gradients accumulated straight into pre-zeroed bucket views equal the returned ones."""
     rows, c = 1500, 640
