@@ -31,7 +31,10 @@ constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
 
-enum { MODE_PLAIN = 0, MODE_CONV_FWD = 1, MODE_CONV_WGRAD = 2 };
+// MODE_CONV_FWD_T: convolution with <= 128 output channels computed transposed (D = W x pixels^T): the 128 output
+// channels are the UMMA M dimension and 256 PIXELS the N dimension, because a UMMA costs the same ~150 clk for N = 128
+// and N = 256 (measured), so pixel-major tiles with N = Cout = 128 run the tensor pipe at half rate.
+enum { MODE_PLAIN = 0, MODE_CONV_FWD = 1, MODE_CONV_WGRAD = 2, MODE_CONV_FWD_T = 3 };
 
 struct alignas(64) GemmDev {
     CUtensorMap tmA;
@@ -105,7 +108,9 @@ __device__ __forceinline__ void add_vec16(float (&v)[16], const float* p, bool f
     }
 }
 
-template <int CG>
+// TRANSPOSED = true is the MODE_CONV_FWD_T instance (its epilogue lives in a separate instantiation so that its register
+// pressure cannot spill into the main kernel)
+template <int CG, bool TRANSPOSED = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmDev g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024B alignment is required by the 128B swizzle atoms
@@ -187,10 +192,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 int ptw = 0, pth = 0, pimg = 0;  // conv wgrad:   k-iteration -> 64-pixel tile
                 int my_c0 = 0, my_dx = 0, my_dy = 0;  // conv wgrad: channel block and tap shift of THIS lane's B atom
                 const int gi0 = tc.split * g.k_iters;
-                if (g.mode == MODE_CONV_FWD) {
-                    tw = mt % g.tiles_w;
-                    th = (mt / g.tiles_w) % g.tiles_h;
-                    img = mt / (g.tiles_w * g.tiles_h);  // may be >= nimg for the odd last tile: TMA zero-fills
+                if (g.mode == MODE_CONV_FWD || g.mode == MODE_CONV_FWD_T) {
+                    const int ptile = (g.mode == MODE_CONV_FWD_T) ? tc.nt : mt;  // pixel tile of this CTA
+                    tw = ptile % g.tiles_w;
+                    th = (ptile / g.tiles_w) % g.tiles_h;
+                    img = ptile / (g.tiles_w * g.tiles_h);  // may be >= nimg for the odd last tile: TMA zero-fills
                     const int tap = gi0 / g.cin_blocks;
                     cb = gi0 - tap * g.cin_blocks;
                     dy = tap / g.ksize;
@@ -238,9 +244,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                                 tma_load(&g.tmB, &full_bar[stage], sb + j * ATOM_BYTES, n0 + 64 * j, k0, tc.b2 * g.b_b2,
                                          tc.b1 * g.b_b1);
                         }
-                    } else if (g.mode == MODE_CONV_FWD) {
-                        if (lane == 0) tma_load(&g.tmA, &full_bar[stage], sa, cb * 64, x0 + dx, y0 + dy, img);
-                        else if (lane == 1) tma_load(&g.tmB, &full_bar[stage], sb, gi * BK, n0, 0, 0);
+                    } else if (g.mode == MODE_CONV_FWD || g.mode == MODE_CONV_FWD_T) {
+                        if (g.mode == MODE_CONV_FWD) {
+                            if (lane == 0) tma_load(&g.tmA, &full_bar[stage], sa, cb * 64, x0 + dx, y0 + dy, img);
+                            else if (lane == 1) tma_load(&g.tmB, &full_bar[stage], sb, gi * BK, n0, 0, 0);
+                        } else {  // transposed: A = packed weights [Cout, taps*Cin], B = 256-pixel box
+                            if (lane == 0) tma_load(&g.tmA, &full_bar[stage], sa, gi * BK, m0, 0, 0);
+                            else if (lane == 1) tma_load(&g.tmB, &full_bar[stage], sb, cb * 64, x0 + dx, y0 + dy, img);
+                        }
                         if (++cb == g.cin_blocks) {  // next filter tap
                             cb = 0;
                             if (++dx == g.ksize) {
@@ -483,7 +494,104 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     }
                 }
             };
-            if (c_begin < c_end) {
+            if constexpr (TRANSPOSED) {
+                // D[co (TMEM lane), pixel (column)]: thread = one output channel, chunk = 16 consecutive pixels of the
+                // tile.  For every pixel the 32 lanes of a warp write 32 consecutive channels (64 contiguous bytes).
+                const int pt = tc.nt;
+                const int ttw = pt % g.tiles_w, tth = (pt / g.tiles_w) % g.tiles_h, timg = pt / (g.tiles_w * g.tiles_h);
+                const int co = tc.mt * BM + r;
+                const bool co_ok = co < g.N;
+                float bco = 0.f;
+                if (co_ok && g.bias) bco += g.bias[co];
+                if (co_ok && g.bias_img) bco += g.bias_img[static_cast<long long>(timg) * g.N + co];
+                const int npx = g.bw * g.bh;
+                bf16* cbase = reinterpret_cast<bf16*>(g.C) + co;
+                const int co_c = co_ok ? co : 0;  // clamped: loads below are unconditional (their results are masked)
+                const unsigned short* rbase_c =
+                    g.residual ? reinterpret_cast<const unsigned short*>(g.residual) + co_c : nullptr;
+                // Two chunks in flight: the TMEM load and the 16 independent 2-byte residual loads of chunk c+1 are issued
+                // before chunk c is converted and stored.  (A load under a per-element branch is waited for at the branch
+                // join — 440 clk per pixel, 56 k clk per tile in the first version — so loads are unconditional on
+                // clamped addresses and masked afterwards.)
+                struct ChunkT {
+                    long long base;   // pixel index (image-global) of the chunk's first column, clamped into the tensor
+                    int nv;           // 16: all columns valid and consecutive in one image row (fast path); else -1
+                    int off[16];      // slow path: per-column pixel offsets inside the image (clamped)
+                    uint32_t okmask;  // slow path: validity of each column
+                };
+                const long long img_base = static_cast<long long>(timg) * g.cH * g.cW;
+                const bool row_chunks = (g.bw & 15) == 0;  // a 16-pixel chunk never straddles two image rows
+                auto issue_t = [&](int c, uint32_t (&raw)[16], unsigned short (&rs)[16], ChunkT& ck) {
+                    tc_ld16(taddr0 + static_cast<uint32_t>(c * 16), raw);
+                    const int p0 = c * 16;
+                    const int hh0 = p0 / g.bw, ww0 = p0 - hh0 * g.bw;
+                    const int h0 = tth * g.bh + hh0, w0 = ttw * g.bw + ww0;
+                    if (row_chunks && co_ok && hh0 < g.bh && h0 < g.cH && w0 + 16 <= g.cW) {
+                        ck.nv = 16;
+                        ck.base = img_base + static_cast<long long>(h0) * g.cW + w0;
+                        if (rbase_c) {
+                            const unsigned short* rp = rbase_c + ck.base * g.ldr;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) rs[j] = __ldg(rp + j * g.ldr);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) rs[j] = 0;
+                        }
+                        return;
+                    }
+                    ck.nv = -1;
+                    int hh = hh0, ww = ww0;
+                    ck.okmask = 0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int h = tth * g.bh + hh, w = ttw * g.bw + ww;
+                        const bool ok = co_ok && (p0 + j < npx) && (h < g.cH) && (w < g.cW);
+                        ck.okmask |= ok ? (1u << j) : 0u;
+                        ck.off[j] = min(h, g.cH - 1) * g.cW + min(w, g.cW - 1);
+                        if (++ww == g.bw) {
+                            ww = 0;
+                            ++hh;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        rs[j] = rbase_c ? __ldg(rbase_c + (img_base + ck.off[j]) * g.ldr) : static_cast<unsigned short>(0);
+                };
+                auto process_t = [&](const uint32_t (&raw)[16], const unsigned short (&rs)[16], const ChunkT& ck) {
+                    if (ck.nv == 16) {
+                        bf16* cp = cbase + ck.base * g.ldc;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float rj = __uint_as_float(static_cast<uint32_t>(rs[j]) << 16);  // bf16 -> fp32
+                            cp[j * g.ldc] = __float2bfloat16(fmaf(__uint_as_float(raw[j]), g.alpha, bco + rj));
+                        }
+                        return;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float rj = __uint_as_float(static_cast<uint32_t>(rs[j]) << 16);
+                        if ((ck.okmask >> j) & 1u)
+                            cbase[(img_base + ck.off[j]) * g.ldc] =
+                                __float2bfloat16(fmaf(__uint_as_float(raw[j]), g.alpha, bco + rj));
+                    }
+                };
+                if (c_begin < c_end) {
+                    uint32_t ra[16], rb[16];
+                    unsigned short sa_[16], sb_[16];
+                    ChunkT ca, cb_;
+                    issue_t(c_begin, ra, sa_, ca);
+                    for (int c = c_begin; c < c_end; c += 2) {
+                        tc_wait_ld16(ra);
+                        if (c + 1 < c_end) issue_t(c + 1, rb, sb_, cb_);
+                        process_t(ra, sa_, ca);
+                        if (c + 1 < c_end) {
+                            tc_wait_ld16(rb);
+                            if (c + 2 < c_end) issue_t(c + 2, ra, sa_, ca);
+                            process_t(rb, sb_, cb_);
+                        }
+                    }
+                }
+            } else if (c_begin < c_end) {
                 uint32_t r0[16], r1[16];
                 uint4 s0a = make_uint4(0, 0, 0, 0), s0b = s0a, s1a = s0a, s1b = s0a;
                 issue(c_begin, r0, s0a, s0b);
@@ -619,6 +727,29 @@ static void pick_pixel_tile(int H, int W, int target, bool exact, int* bw_out, i
     *bh_out = bbh;
 }
 
+// debugging aid (NK_GEMM_DEBUG_TIMING): per-role cycle accounting of the launch that just ran
+static int debug_report(const GemmProblem& p, const GemmDev& g, int cg, long long total, int nsm, long long* dbg_buf,
+                        cudaStream_t stream) {
+    NK_CUDA(cudaStreamSynchronize(stream));
+    static long long host[8 * 1024];
+    NK_CUDA(cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost));
+    const int nb = cg == 1 ? static_cast<int>(std::min<long long>(total, nsm))
+                           : 2 * static_cast<int>(std::min<long long>(total, nsm / 2));
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int nlead = 0;
+    for (int b = 0; b < nb && b < 1024; b += cg) {
+        for (int i = 0; i < 8; ++i) a[i] += static_cast<double>(host[b * 8 + i]);
+        ++nlead;
+    }
+    for (int i = 0; i < 8; ++i) a[i] /= std::max(1, nlead);
+    fprintf(stderr,
+            "[nk gemm dbg] mode=%d M=%d N=%d k_iters=%d BN=%d cg=%d stages=%d tiles=%lld splits=%d | per leader CTA: tiles %.1f  "
+            "mma loop %.0f clk (wait full %.0f, wait tmem_empty %.0f)  producer wait empty %.0f  "
+            "epilogue wait full %.0f proc %.0f\n",
+            g.mode, p.M, p.N, g.k_iters, g.BN, cg, g.stages, total, g.splits, a[6], a[3], a[1], a[2], a[0], a[4], a[5]);
+    return NK_OK;
+}
+
 int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     static int nsm = 0;
     static bool attr_set = false;
@@ -648,6 +779,10 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
         NK_REQUIRE(p.A.inner % 64 == 0, NK_ERR_SHAPE, "conv: C_in %lld not a multiple of 64", p.A.inner);
     }
 
+    static int env_no_swap = -1;
+    if (env_no_swap < 0) env_no_swap = getenv("NK_NO_CONV_SWAP") ? 1 : 0;  // A/B switch
+    const bool swap_ab = g.mode == MODE_CONV_FWD && p.N > 64 && p.N <= 128 && p.conv_stride <= 1 && p.out == OUT_BF16 &&
+                         p.epi == EPI_LINEAR && !env_no_swap && p.force_bn == 0 && p.force_cta_group == 0;
     int a_box1 = BM, a_box2 = 1, b_box2 = 1;
     g.cstride = p.conv_stride > 1 ? p.conv_stride : 1;
     g.pad_t = g.cstride > 1 ? p.pad_t : p.pad;
@@ -694,6 +829,57 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     if (dbg_on < 0) {
         dbg_on = getenv("NK_GEMM_DEBUG_TIMING") ? 1 : 0;
         if (dbg_on) NK_CUDA(cudaMalloc(&dbg_buf, 8 * 1024 * sizeof(long long)));
+    }
+    if (swap_ab) {
+        // ---- transposed convolution forward: M = Cout (<= 128), N = 256 pixels, single CTAs ----
+        g.mode = MODE_CONV_FWD_T;
+        pick_pixel_tile(g.cH, g.cW, 256, false, &g.bw, &g.bh);
+        g.tiles_w = (g.cW + g.bw - 1) / g.bw;
+        g.tiles_h = (g.cH + g.bh - 1) / g.bh;
+        g.tiles_m128 = 1;
+        g.tiles_m = 1;
+        g.BN = 256;
+        g.tiles_n = p.A.nimg * g.tiles_w * g.tiles_h;
+        g.a_bytes = A_STAGE_BYTES;
+        g.b_bytes = static_cast<uint32_t>(g.bw * g.bh * 128);
+        g.k_iters = g.k_iters_total;
+        g.splits = 1;
+        int e2 = make_operand_tmap(&g.tmA, p.B, BM, 1);  // packed weights [Cout, taps*Cin]: box {64 k, 128 rows}
+        if (e2) return e2;
+        e2 = make_operand_tmap(&g.tmB, p.A, g.bw, g.bh, 1);  // NHWC image: box {64 ch, bw, bh}
+        if (e2) return e2;
+        g.C = p.C;
+        g.ldc = p.ldc;
+        g.out = p.out;
+        g.epi = p.epi;
+        g.alpha = p.alpha;
+        g.bias = p.bias;
+        g.bias_img = p.bias_img;
+        g.rows_per_img = p.A.nimg;  // transposed mode: number of images (tiles past the last image load nothing)
+        g.residual = p.residual;
+        g.ldr = p.ldr;
+        g.idesc = make_idesc_bf16(BM, 256, 0, 0);
+        const int stage_bytes_t = A_STAGE_BYTES + 256 * 128;
+        const int max_smem_t = 227 * 1024;
+        g.stages = std::max(2, std::min((max_smem_t - 1024 - 256) / stage_bytes_t, 8));
+        const int smem_t = g.stages * stage_bytes_t + 1024 + (2 * g.stages + 5) * 8;
+        if (!attr_set) {
+            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_t));
+            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_t));
+            attr_set = true;
+        }
+        static bool attr_t_set = false;
+        if (!attr_t_set) {
+            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_t));
+            attr_t_set = true;
+        }
+        g.dbg = dbg_buf;
+        if (dbg_buf) NK_CUDA(cudaMemsetAsync(dbg_buf, 0, 8 * 1024 * sizeof(long long), stream));
+        const int grid_t = static_cast<int>(std::min<long long>(g.tiles_n, nsm));
+        gemm_tc_kernel<1, true><<<grid_t, NUM_THREADS, smem_t, stream>>>(g);
+        NK_CUDA(cudaGetLastError());
+        if (dbg_buf) return debug_report(p, g, 1, g.tiles_n, nsm, dbg_buf, stream);
+        return NK_OK;
     }
     static int env_cg = -1;
     if (env_cg < 0) {
@@ -810,24 +996,7 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
         NK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, g));
     }
     NK_CUDA(cudaGetLastError());
-    if (dbg_buf) {  // debugging aid: per-role cycle accounting of the launch that just ran
-        NK_CUDA(cudaStreamSynchronize(stream));
-        static long long host[8 * 1024];
-        NK_CUDA(cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost));
-        const int nb = cg == 1 ? static_cast<int>(std::min<long long>(total, nsm)) : 2 * static_cast<int>(std::min<long long>(total, nsm / 2));
-        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        int nlead = 0;
-        for (int b = 0; b < nb && b < 1024; b += cg) {
-            for (int i = 0; i < 8; ++i) a[i] += static_cast<double>(host[b * 8 + i]);
-            ++nlead;
-        }
-        for (int i = 0; i < 8; ++i) a[i] /= std::max(1, nlead);
-        fprintf(stderr,
-                "[nk gemm dbg] M=%d N=%d k_iters=%d BN=%d cg=%d stages=%d tiles=%lld splits=%d | per leader CTA: tiles %.1f  "
-                "mma loop %.0f clk (wait full %.0f, wait tmem_empty %.0f)  producer wait empty %.0f  "
-                "epilogue wait full %.0f proc %.0f\n",
-                p.M, p.N, g.k_iters, g.BN, cg, g.stages, total, g.splits, a[6], a[3], a[1], a[2], a[0], a[4], a[5]);
-    }
+    if (dbg_buf) return debug_report(p, g, cg, total, nsm, dbg_buf, stream);
     return NK_OK;
 }
 

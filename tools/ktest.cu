@@ -386,6 +386,8 @@ static Case cases[] = {
     {"conv_cout4", []() { return test_conv("conv_cout4 1x32x32 320->4 k3", 1, 32, 32, 320, 4, 3, true); }},
     {"conv_big", []() { return test_conv("conv_big 4x64x64 640->640 k3", 4, 64, 64, 640, 640, 3, true); }},
     {"conv_sdxl128", []() { return test_conv("conv_sdxl128 2x128x128 320->320 k3", 2, 128, 128, 320, 320, 3, true); }},
+    {"conv_t_ragged", []() { return test_conv("conv_t_ragged 2x36x28 64->128 k3 +bias+img+res (transposed path)", 2, 36, 28, 64, 128, 3, true); }},
+    {"conv_t_1x1", []() { return test_conv("conv_t_1x1 3x20x50 128->96 k1 (transposed path)", 3, 20, 50, 128, 96, 1, true); }},
     {"conv_vae1024", []() { return test_conv("conv_vae1024 1x1024x1024 128->128 k3", 1, 1024, 1024, 128, 128, 3, true); }},
     {"cwgrad_small", []() { return test_conv_wgrad("cwgrad_small 1x16x16 64->64 k3", 1, 16, 16, 64, 64, 3); }},
     {"cwgrad_mid", []() { return test_conv_wgrad("cwgrad_mid 2x32x32 128->192 k3", 2, 32, 32, 128, 192, 3); }},
