@@ -236,6 +236,16 @@ int nk_weighted_mse_fwd(const float* D, const float* T, const float* w, float* l
 int nk_weighted_mse_bwd(const float* D, const float* T, const float* w, const float* dloss, float* dD, int B,
                         int64_t per_sample, nk_stream_t stream);
 
+/* ---- VAE posterior (section 8(f) row 1: VAE training step) ------------------------------------
+ * DiagonalGaussianDistribution (modules/distributions.py:29-51) as used by DiagonalGaussianRegularizer
+ * (modules/regularizers.py:31-41): moments (B, 2C, H, W) fp32 NCHW, half = C*H*W.  logvar clamped to [-30, 20];
+ * z = mean + exp(logvar/2) * eps (eps NULL: mode); kl[b] = 0.5 * sum(mean^2 + var - 1 - logvar) (kl may be NULL). */
+int nk_diag_gaussian_fwd(const float* moments, const float* eps, float* z, float* kl, int B, int64_t half,
+                         nk_stream_t stream);
+/* gradient w.r.t. the moments from dz (B, C, H, W; may be NULL) and dkl (B; may be NULL) */
+int nk_diag_gaussian_bwd(const float* moments, const float* eps, const float* dz, const float* dkl, float* dmoments,
+                         int B, int64_t half, nk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

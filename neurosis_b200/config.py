@@ -20,7 +20,10 @@ REDIRECT = {
     "neurosis.modules.diffusion.UNetModel": f"{_M}.openaimodel.UNetModel",
     "neurosis.modules.diffusion.openaimodel.UNetModel": f"{_M}.openaimodel.UNetModel",
     "neurosis.modules.diffusion.model.Encoder": f"{_M}.vae.Encoder",
+    "neurosis.modules.diffusion.model.Decoder": f"{_M}.vae.Decoder",
     "neurosis.models.autoencoder.AutoencoderKL": f"{_M}.vae.AutoencoderKL",
+    "neurosis.models.autoencoder.AutoencodingEngineLegacy": f"{_M}.vae.AutoencoderKL",
+    "neurosis.modules.regularizers.DiagonalGaussianRegularizer": f"{_M}.vae.DiagonalGaussianRegularizer",
     "neurosis.modules.diffusion.wrappers.OpenAIWrapper": f"{_M}.loss.OpenAIWrapper",
     "neurosis.modules.diffusion.hooks.LossHook": f"{_M}.loss.LossHook",
     "neurosis.dataset.processing.TagFrequencyHook": f"{_M}.loss.TagFrequencyHook",

@@ -76,6 +76,56 @@ __global__ void weighted_mse_bwd_kernel(const float* __restrict__ D, const float
     }
 }
 
+// ---- diagonal Gaussian posterior of the VAE (modules/distributions.py:29-51, regularizers.py:31-41) ----------------
+// moments[b] = (mean | logvar) halves of 2*C channels, each `half` = C*H*W contiguous floats (NCHW).  logvar is clamped
+// to [-30, 20]; z = mean + exp(0.5 logvar) * eps (eps == nullptr: mode, z = mean); kl[b] = 0.5 * sum(mean^2 + var - 1
+// - logvar).  One block per sample, fixed-order reduction.
+__global__ void diag_gaussian_fwd_kernel(const float* __restrict__ moments, const float* __restrict__ eps,
+                                         float* __restrict__ z, float* __restrict__ kl, long long half) {
+    const int b = blockIdx.x;
+    const float* mean = moments + 2 * half * b;
+    const float* logvar = mean + half;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < half; i += blockDim.x) {
+        const float m = mean[i];
+        const float lv = fminf(fmaxf(logvar[i], -30.f), 20.f);
+        const float sd = expf(0.5f * lv);
+        z[half * b + i] = eps ? m + sd * eps[half * b + i] : m;
+        acc += m * m + expf(lv) - 1.f - lv;
+    }
+    __shared__ float red[32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0 && kl) kl[b] = 0.5f * v;
+    }
+}
+// d moments from dz (may be null) and dkl[b] (may be null): dmean = dz + dkl*mean;
+// dlogvar = [clamp inactive] * (dz * eps * 0.5 * sd + dkl * 0.5 * (var - 1))
+__global__ void diag_gaussian_bwd_kernel(const float* __restrict__ moments, const float* __restrict__ eps,
+                                         const float* __restrict__ dz, const float* __restrict__ dkl,
+                                         float* __restrict__ dmoments, long long half, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / half, j = i - b * half;
+        const float m = moments[2 * half * b + j];
+        const float lvr = moments[2 * half * b + half + j];
+        const float lv = fminf(fmaxf(lvr, -30.f), 20.f);
+        const float g = dz ? dz[i] : 0.f;
+        const float gk = dkl ? dkl[b] : 0.f;
+        float dlv = 0.f;
+        if (lvr >= -30.f && lvr <= 20.f) {
+            if (eps) dlv += g * eps[i] * 0.5f * expf(0.5f * lv);
+            dlv += gk * 0.5f * (expf(lv) - 1.f);
+        }
+        dmoments[2 * half * b + j] = g + gk * m;
+        dmoments[2 * half * b + half + j] = dlv;
+    }
+}
+
 inline int grid_for(long long work, int block) {
     const long long g = (work + block - 1) / block;
     return static_cast<int>(std::max<long long>(1, std::min<long long>(g, 148LL * 8)));
@@ -119,6 +169,22 @@ int nk_weighted_mse_bwd(const float* D, const float* T, const float* w, const fl
                         int64_t per_sample, nk_stream_t stream) {
     const long long total = static_cast<long long>(B) * per_sample;
     weighted_mse_bwd_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(D, T, w, dloss, dD, per_sample, total);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_diag_gaussian_fwd(const float* moments, const float* eps, float* z, float* kl, int B, int64_t half,
+                         nk_stream_t stream) {
+    NK_REQUIRE(B > 0 && half > 0, NK_ERR_SHAPE, "diag_gaussian_fwd: B=%d", B);
+    diag_gaussian_fwd_kernel<<<B, 1024, 0, ST(stream)>>>(moments, eps, z, kl, half);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_diag_gaussian_bwd(const float* moments, const float* eps, const float* dz, const float* dkl, float* dmoments,
+                         int B, int64_t half, nk_stream_t stream) {
+    NK_REQUIRE(B > 0 && half > 0, NK_ERR_SHAPE, "diag_gaussian_bwd: B=%d", B);
+    const long long total = static_cast<long long>(B) * half;
+    diag_gaussian_bwd_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(moments, eps, dz, dkl, dmoments, half, total);
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }

@@ -1429,3 +1429,125 @@ class WeightedMseFn(torch.autograd.Function):
 
 def weighted_mse(D: Tensor, T: Tensor, w: Tensor) -> Tensor:
     return WeightedMseFn.apply(D, T, w)
+
+
+# --------------------------------------------------------------------------------------------
+# VAE training step: posterior, thin 1x1 convolutions, trainable RGB stem
+# --------------------------------------------------------------------------------------------
+class DiagGaussianFn(torch.autograd.Function):
+    """(z, kl[B]) of the diagonal Gaussian posterior (reference modules/distributions.py:29-51): moments (B,2C,H,W) fp32
+    NCHW; eps (B,C,H,W) fp32 standard normal draws, or None for the mode."""
+
+    @staticmethod
+    def forward(ctx, moments, eps):
+        _req_cuda(moments, eps)
+        moments = moments.float().contiguous()
+        B, C2 = moments.shape[0], moments.shape[1]
+        half = moments.numel() // B // 2
+        z = torch.empty((B, C2 // 2, *moments.shape[2:]), dtype=F32, device=moments.device)
+        kl = torch.empty((B,), dtype=F32, device=moments.device)
+        eps = eps.float().contiguous() if eps is not None else None
+        check(lib.nk_diag_gaussian_fwd(moments.data_ptr(), _p(eps), z.data_ptr(), kl.data_ptr(), B, half, _stream()),
+              "diag_gaussian_fwd")
+        _count()
+        ctx.save_for_backward(moments, eps if eps is not None else torch.empty(0, device=moments.device))
+        return z, kl
+
+    @staticmethod
+    def backward(ctx, dz, dkl):
+        moments, eps = ctx.saved_tensors
+        eps = eps if eps.numel() else None
+        B = moments.shape[0]
+        dz = dz.float().contiguous() if dz is not None else None
+        dkl = dkl.float().contiguous() if dkl is not None else None
+        dm = torch.empty_like(moments)
+        check(lib.nk_diag_gaussian_bwd(moments.data_ptr(), _p(eps), _p(dz), _p(dkl), dm.data_ptr(), B,
+                                       moments.numel() // B // 2, _stream()), "diag_gaussian_bwd")
+        _count()
+        return dm, None
+
+
+def diag_gaussian(moments: Tensor, eps: Optional[Tensor] = None):
+    return DiagGaussianFn.apply(moments, eps)
+
+
+class ThinConv1x1Fn(torch.autograd.Function):
+    """1x1 convolution between thin channel counts (quant_conv 8 -> 8, post_quant_conv 4 -> 4; reference
+    models/autoencoder.py:452-453) on NHWC bf16 tensors whose channels are physically zero-padded to 64: one
+    [pixels, 64] x [64, 64] GEMM with the weight zero-padded (a 64 x 64 host-side pad of a <= 8 x 8 matrix)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        co, ci = weight.shape[0], weight.shape[1]
+        cp = x.shape[-1]
+        assert cp >= ci and cp % 64 == 0 and co <= 64
+        wq = torch.zeros((64, cp), dtype=F32, device=weight.device)
+        wq[:co, :ci] = weight.detach().reshape(co, ci)
+        wq = cast_bf16(wq)
+        bq = None
+        if bias is not None:
+            bq = torch.zeros((64,), dtype=F32, device=weight.device)
+            bq[:co] = bias.detach()
+        y = linear_fwd(x.reshape(-1, cp), wq, bq)
+        ctx.save_for_backward(x, wq)
+        ctx.dims = (co, ci, bias is not None)
+        ctx.wshape = weight.shape
+        return y.view(*x.shape[:-1], 64)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wq = ctx.saved_tensors
+        co, ci, has_bias = ctx.dims
+        cp = x.shape[-1]
+        dy2 = dy.contiguous().view(-1, 64)
+        dx = linear_dgrad(dy2, wq).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = linear_wgrad(dy2, x.reshape(-1, cp))[:co, :ci].reshape(ctx.wshape).contiguous()
+        if has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2)[0, :co].contiguous()
+        return dx, dw, db
+
+
+def conv1x1_thin(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    return ThinConv1x1Fn.apply(x, weight, bias)
+
+
+class Conv3x3ThinInputFn(torch.autograd.Function):
+    """Trainable form of `conv3x3_thin_input_fwd` (Encoder.conv_in, RGB -> 128): the weight gradient is the
+    [Cout, 64] x [pixels, 64] GEMM over the re-generated patch matrix; the image itself takes no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return conv3x3_thin_input_fwd(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        n, c, h, w_ = x.shape
+        co = weight.shape[0]
+        dy2 = dy.contiguous().view(-1, co)
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            xf = x.float().contiguous()
+            col = torch.empty((n * h * w_, 64), dtype=BF16, device=x.device)
+            check(lib.nk_image_patches3x3(xf.data_ptr(), col.data_ptr(), n, c, h, w_, _stream()), "image_patches3x3")
+            _count()
+            dwp = linear_wgrad(dy2, col)  # [co, 64], column = tap*C + c
+            dw = dwp[:, : 9 * c].reshape(co, 3, 3, c).permute(0, 3, 1, 2).contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2)[0].contiguous()
+        return None, dw, db
+
+
+def conv3x3_thin_input(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    return Conv3x3ThinInputFn.apply(x, weight, bias)
+
+
+def mse_loss(pred: Tensor, target: Tensor) -> Tensor:
+    """F.mse_loss(pred, target) (mean over all elements) on fp32 tensors of equal per-sample size, through the
+    per-sample reduction kernel of the diffusion loss."""
+    ones = torch.ones((pred.shape[0],), dtype=F32, device=pred.device)
+    return weighted_mse(pred, target, ones).mean()

@@ -1,0 +1,157 @@
+"""GPU parity of the SURVEY.md §8(f) "next" rows (through the C ABI): VAE decoder + VAE training step, fused optimizer
+step, device-side conditioner vector path, EMA.  Oracle = CPU fp32 restatements under oracle/, pinned by golden
+vectors generated from the reference itself (tests/golden/make_golden_next.py).
+
+Tolerances as in test_gpu_modules.py: bf16 storage with fp32 accumulation against an fp32 oracle -> relative L2
+<= 3e-2 for network outputs, median per-parameter gradient error <= 4e-2; fp32 elementwise kernels <= 1e-5."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import ROOT, TINY_VAE
+from oracle.vae import vae_decode, vae_decoder_param_shapes, vae_param_shapes, vae_train_loss
+from oracle.weights import synth_state_dict, synth_tensor
+
+pytestmark = pytest.mark.gpu
+G = np.load(str(ROOT / "tests/golden/reference_golden_next.npz"))
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+def rel(a, b) -> float:
+    a = torch.as_tensor(a).detach().float().cpu()
+    b = torch.as_tensor(b).detach().float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ---------------------------------------------------------------- row 1: VAE decoder / training step
+def test_diag_gaussian_fwd_bwd():
+    from neurosis_b200 import ops
+    m = rnd(3, 8, 12, 10)
+    m[0, 4:, :2] = 25.0   # clamp at 20
+    m[1, 4:, :2] = -40.0  # clamp at -30
+    m.requires_grad_(True)
+    eps = rnd(3, 4, 12, 10, seed=1)
+    z, kl = ops.diag_gaussian(m, eps)
+    gz, gk = rnd(3, 4, 12, 10, seed=2), rnd(3, seed=3)
+    (z * gz).sum().add((kl * gk).sum()).backward()
+    mr = m.detach().clone().requires_grad_(True)
+    mean, logvar = torch.chunk(mr, 2, dim=1)
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    zr = mean + torch.exp(0.5 * logvar) * eps
+    klr = 0.5 * torch.sum(mean ** 2 + torch.exp(logvar) - 1.0 - logvar, dim=[1, 2, 3])
+    ((zr * gz).sum() + (klr * gk).sum()).backward()
+    assert rel(z, zr) < 1e-5 and rel(kl, klr) < 1e-5
+    assert rel(m.grad, mr.grad) < 1e-5
+    zm, _ = ops.diag_gaussian(m.detach(), None)
+    assert torch.equal(zm, m.detach()[:, :4])
+
+
+def test_conv1x1_thin_fwd_bwd():
+    from neurosis_b200 import ops
+    n, h, w, ci, co = 2, 16, 12, 8, 8
+    x = rnd(n, ci, h, w)
+    wt = rnd(co, ci, 1, 1, seed=1, scale=0.3).requires_grad_(True)
+    b = rnd(co, seed=2).requires_grad_(True)
+    xn = ops.to_nhwc(x, 64)
+    y = ops.from_nhwc_f32(ops.conv1x1_thin(xn, wt, b), co)
+    g = rnd(n, co, h, w, seed=3)
+    y.backward(g)
+    wr, br = wt.detach().to(BF).float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = F.conv2d(x.to(BF).float(), wr, br)
+    yr.backward(g)
+    assert rel(y, yr) < 6e-3
+    assert rel(wt.grad, wr.grad) < 1e-2 and rel(b.grad, br.grad) < 1e-2
+
+
+def test_conv3x3_thin_input_weight_gradient():
+    from neurosis_b200 import ops
+    n, c, h, w, co = 2, 3, 24, 20, 64
+    x = rnd(n, c, h, w)
+    wt = rnd(co, c, 3, 3, seed=1, scale=(9 * c) ** -0.5).requires_grad_(True)
+    b = rnd(co, seed=2).requires_grad_(True)
+    y = ops.conv3x3_thin_input(x, wt, b)
+    g = rnd(n, h, w, co, seed=3).to(BF)
+    y.backward(g)
+    wr, br = wt.detach().to(BF).float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = F.conv2d(x.to(BF).float(), wr, br, padding=1)
+    yr.backward(g.float().permute(0, 3, 1, 2))
+    assert rel(y.permute(0, 3, 1, 2), yr) < 6e-3
+    assert rel(wt.grad, wr.grad) < 1e-2 and rel(b.grad, br.grad) < 1e-2
+
+
+def _grad_errs(module, ref_sd):
+    return {n: rel(p.grad, ref_sd[n].grad) for n, p in module.named_parameters()}
+
+
+def test_vae_decoder_vs_golden_and_oracle():
+    from neurosis_b200.modules.vae import Decoder
+    shapes = vae_decoder_param_shapes(TINY_VAE, embed_dim=4, standalone=True)
+    dec = Decoder(**TINY_VAE, embed_dim=4, standalone=True)
+    dec.load_state_dict(synth_state_dict(shapes, seed=5))
+    dec = dec.to(DEV)
+    z = synth_tensor("vaedec.z", (2, 4, 16, 16))
+    xr = dec(z.to(DEV))
+    assert xr.shape == (2, 3, 32, 32) and xr.dtype == torch.float32
+    assert rel(xr, G["vaedec.out"]) < 3e-2, "vs the reference's own Decoder"
+    g = synth_tensor("vaedec.g", (2, 3, 32, 32), scale=0.1)
+    (xr * g.to(DEV)).sum().backward()
+    sd = {k: v.requires_grad_(True) for k, v in synth_state_dict(shapes, seed=5).items()}
+    xo = vae_decode(sd, TINY_VAE, z)
+    (xo * g).sum().backward()
+    errs = _grad_errs(dec, sd)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    assert len(errs) == len(shapes)
+    assert np.median(list(errs.values())) < 4e-2, worst
+    assert worst[0][1] < 1.5e-1, worst
+    l2 = np.array([float(dict(dec.named_parameters())[n].grad.norm()) for n in sorted(shapes)])
+    assert np.allclose(l2, G["vaedec.grad_l2"], rtol=6e-2, atol=1e-5), "gradient norms vs the reference's"
+
+
+def test_vae_training_step_vs_golden_and_oracle():
+    """AutoencoderKL.training_step (encoder -> quant_conv -> sampled posterior -> post_quant_conv -> decoder -> L2)
+    with the posterior noise pinned: loss within 1e-2 of the reference's fp32 value, gradients of BOTH networks."""
+    from neurosis_b200.modules.vae import AutoencoderKL, DiagonalGaussianRegularizer
+    eshapes = vae_param_shapes(TINY_VAE, embed_dim=4, standalone=True)
+    dshapes = vae_decoder_param_shapes(TINY_VAE, embed_dim=4, standalone=True)
+    esd, dsd = synth_state_dict(eshapes, seed=2), synth_state_dict(dshapes, seed=5)
+    ae = AutoencoderKL(4, TINY_VAE, regularizer=DiagonalGaussianRegularizer(sample=True))
+    full = {}
+    for k, v in esd.items():
+        full[k if k.startswith("quant_conv.") else "encoder." + k] = v
+    for k, v in dsd.items():
+        full[k if k.startswith("post_quant_conv.") else "decoder." + k] = v
+    ae.load_state_dict(full)
+    ae = ae.to(DEV)
+    img = synth_tensor("vae.img", (2, 3, 32, 32), uniform=True)
+    eps = synth_tensor("vaetrain.eps", (2, 4, 16, 16))
+    loss = ae.training_step({"image": img.to(DEV), "posterior_eps": eps.to(DEV)})
+    assert loss.ndim == 0
+    np.testing.assert_allclose(float(loss), G["vaetrain.loss"], rtol=1e-2)
+    np.testing.assert_allclose(float(ae.last_log["kl_loss"]), G["vaetrain.kl_loss"], rtol=1e-2)
+    loss.backward()
+    ro = {k: v.requires_grad_(True) for k, v in esd.items()}
+    rd = {k: v.requires_grad_(True) for k, v in dsd.items()}
+    lo, *_ = vae_train_loss(ro, rd, TINY_VAE, img, eps)
+    lo.backward()
+    ref = {}
+    for k, v in ro.items():
+        ref[k if k.startswith("quant_conv.") else "encoder." + k] = v
+    for k, v in rd.items():
+        ref[k if k.startswith("post_quant_conv.") else "decoder." + k] = v
+    errs = _grad_errs(ae, ref)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    assert len(errs) == len(eshapes) + len(dshapes)
+    assert np.median(list(errs.values())) < 4e-2, worst
+    assert worst[0][1] < 2e-1, worst
+    # without sampling noise supplied the step draws its own and still trains
+    ae.zero_grad()
+    l2 = ae.training_step({"image": img.to(DEV)})
+    l2.backward()
+    assert torch.isfinite(l2) and all(torch.isfinite(p.grad).all() for p in ae.parameters())
