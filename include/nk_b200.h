@@ -246,6 +246,28 @@ int nk_diag_gaussian_fwd(const float* moments, const float* eps, float* z, float
 int nk_diag_gaussian_bwd(const float* moments, const float* eps, const float* dz, const float* dkl, float* dmoments,
                          int B, int64_t half, nk_stream_t stream);
 
+/* ---- optimizer side --------------------------------------
+ * One Adafactor step (reference optimizers/adafactor.py:166-246) over ALL parameters in five stream-ordered launches.
+ * tensors_dev: device array of n_tensors records (88 bytes each, 8-byte aligned):
+ *   { float* p; const float* g; float* vr; float* vc; float* exp_avg; bf16* mirror; float* scratch; int64 n;
+ *     int32 kind, Bt, R, C, group, owner; }
+ *   kind 0: 1-D parameter, vr = full second moment [n];  kind 1: Bt matrices of R x C <= 64 elements (conv kernels),
+ *   vr [Bt*R], vc [Bt*C];  kind 2: one large R x C matrix, vr [R], vc [C], scratch [R + C] floats (zero on entry, left
+ *   zero);  n = elements of the whole parameter; owner = index of the parameter's first record (a [Bt, R, C]
+ *   parameter with large R*C is Bt kind-2 records sharing their owner's sums);  exp_avg (first moment) and mirror (bf16 copy of p, refreshed in the same pass) may be NULL.
+ * blk_start_dev: int32 [n_tensors] first thread block of every tensor (kind 0: ceil(n/4096) blocks, kind 1:
+ *   ceil(Bt/1024), kind 2: ceil(R/64)*ceil(C/128)); n_blocks = their total.
+ * hyper_dev: float [groups][8] = {beta2t, rel_step, eps1, eps2, clip_threshold, weight_decay, beta1, scale_parameter}
+ *   written by the host before every step (beta2t = 1 - step^decay_rate, rel_step = min(1e-6*step | 1e-2, step^-1/2)
+ *   or the external lr).  scal_dev: float [n_tensors][4] workspace.  rms_out: float [n_tensors] = RMS(p) before the
+ *   update (state["RMS"] of the reference), may be NULL. */
+int nk_adafactor_step(const void* tensors_dev, const int32_t* blk_start_dev, int n_tensors, int n_blocks,
+                      const float* hyper_dev, float* scal_dev, float* rms_out, nk_stream_t stream);
+/* EMA shadow update of LitEma.forward (modules/ema.py:40-59): shadow -= (1 - decay) * (shadow - p) for every span
+ * {float* shadow; const float* p; int64 n} (24 bytes) of the device table, one thread block per span; the factor is
+ * read from device memory so a captured graph can be replayed with a changing decay. */
+int nk_ema_update_multi(const void* spans_dev, int n_spans, const float* one_minus_decay_dev, nk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -272,6 +272,30 @@ def refresh_weight_copies(force: bool = False) -> None:
     _mirror.refresh()
 
 
+def registered_mirror(p: Tensor) -> Optional[Tensor]:
+    """the persistent bf16 copy of a parameter that `bf16_weight` serves to the GEMMs, if one exists (the fused
+    optimizer step rewrites it in its apply pass instead of leaving it to the per-step refresh)."""
+    base = p._base if p._base is not None else p
+    ent = _mirror.params.get(id(base))
+    if ent is None or ent[0]() is not base:
+        return None
+    c = ent[1]
+    return c if c.is_contiguous() and c.numel() == base.numel() else None
+
+
+def parameters_updated_in_place(items) -> None:
+    """`items` = [(parameter, mirror_is_fresh)]: a kernel of this library wrote the fp32 values through raw pointers.
+    Bumps the autograd version counters (the per-parameter caches of packed / bf16 copies key on them) and, where the
+    same kernel also rewrote the bf16 mirror, re-attaches that copy to the new version so it is not cast again."""
+    for p, fresh in items:
+        base = p._base if p._base is not None else p
+        torch.autograd.graph.increment_version(base)
+        if fresh:
+            ent = _mirror.params.get(id(base))
+            if ent is not None and ent[0]() is base:
+                _cache_for(base)["bf16"] = ent[1]
+
+
 def cast_bf16(x: Tensor) -> Tensor:
     """fp32 -> bf16 copy with our kernel (bf16 input is returned as is)."""
     if x.dtype == BF16:

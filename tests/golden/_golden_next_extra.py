@@ -1,0 +1,54 @@
+# Rows 2-4 of make_golden_next.py (executed by it with `out`, `np`, `torch`, `synth_tensor` in scope).
+from neurosis.modules.ema import LitEma
+from neurosis.modules.encoders.metadata import ConcatTimestepEmbedderND
+from neurosis.optimizers import Adafactor
+
+# ---- row 2: Adafactor, three steps over parameters of every layout class -------------------------------------
+OPT_SHAPES = {"lin": (96, 200), "lin_ragged": (130, 70), "conv3": (24, 16, 3, 3), "conv1": (8, 12, 1, 1),
+              "bias": (300,), "stack": (2, 70, 40)}
+OPT_CASES = {
+    "yaml": dict(scale_parameter=True, relative_step=True, warmup_init=True),   # configs/sdxl/sdxl.example.yaml:160-164
+    "ext": dict(lr=1e-3, scale_parameter=False, relative_step=False, warmup_init=False, beta1=0.9, weight_decay=0.01,
+                clip_threshold=0.5),
+}
+for case, kw in OPT_CASES.items():
+    params = {k: torch.nn.Parameter(synth_tensor(f"opt.p.{k}", s, scale=0.05)) for k, s in OPT_SHAPES.items()}
+    opt = Adafactor(list(params.values()), **kw)
+    for step in range(3):
+        for k, p in params.items():
+            p.grad = synth_tensor(f"opt.g.{k}.{step}", tuple(p.shape), scale=0.02 * (step + 1))
+        opt.step()
+    for k, p in params.items():
+        out[f"opt.{case}.{k}.p"] = p.detach().numpy().copy()
+        st = opt.state[p]
+        out[f"opt.{case}.{k}.rms"] = np.array(float(st["RMS"]))
+        for sk in ("exp_avg_sq_row", "exp_avg_sq_col", "exp_avg_sq", "exp_avg"):
+            if sk in st:
+                out[f"opt.{case}.{k}.{sk}"] = st[sk].numpy().copy()
+
+# ---- row 4: LitEma, 12 updates (crosses the (1+n)/(10+n) warm-up) ------------------------------------------------
+class _M(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(40, 30)
+        self.b = torch.nn.Conv2d(8, 8, 3)
+
+m = _M()
+with torch.no_grad():
+    for n_, p in m.named_parameters():
+        p.copy_(synth_tensor(f"ema.p.{n_}", tuple(p.shape)))
+ema = LitEma(m, decay=0.9999)
+for it in range(12):
+    with torch.no_grad():
+        for n_, p in m.named_parameters():
+            p.add_(synth_tensor(f"ema.d.{n_}.{it}", tuple(p.shape), scale=0.1))
+    ema(m)
+for n_, _ in m.named_parameters():
+    out[f"ema.{n_}"] = dict(ema.named_buffers())[n_.replace(".", "_")].numpy().copy()
+out["ema.num_updates"] = np.array(int(ema.num_updates))
+
+# ---- row 3: ConcatTimestepEmbedderND (SDXL size / crop conditioning) ---------------------------------------------
+emb = ConcatTimestepEmbedderND(256)
+sizes = torch.tensor([[1024.0, 1024.0], [1152.0, 896.0], [832.0, 1216.0], [0.0, 64.0]])
+out["cond.sizes"] = sizes.numpy()
+out["cond.fourier"] = emb(sizes).numpy()

@@ -155,3 +155,135 @@ def test_vae_training_step_vs_golden_and_oracle():
     l2 = ae.training_step({"image": img.to(DEV)})
     l2.backward()
     assert torch.isfinite(l2) and all(torch.isfinite(p.grad).all() for p in ae.parameters())
+
+
+# ---------------------------------------------------------------- row 2: fused Adafactor step
+def _opt_params(case_kw):
+    from test_oracle_golden_next import OPT_SHAPES
+    return {k: torch.nn.Parameter(synth_tensor(f"opt.p.{k}", s, scale=0.05).to(DEV)) for k, s in OPT_SHAPES.items()}
+
+
+@pytest.mark.parametrize("case", ["yaml", "ext"])
+def test_adafactor_step_vs_reference_golden(case):
+    """three steps of the multi-tensor Adafactor over parameters of every layout class (large matrix, ragged matrix,
+    3x3 / 1x1 conv kernels, bias, stacked matrices) against the reference optimizer's parameters, moments and RMS."""
+    from neurosis_b200.optim import Adafactor
+    from test_oracle_golden_next import OPT_CASES, OPT_SHAPES, check_optimizer_state
+    kw = OPT_CASES[case]
+    params = _opt_params(kw)
+    p0 = {k: p.detach().cpu().numpy().copy() for k, p in params.items()}
+    opt = Adafactor(list(params.values()), **kw)
+    for step in range(3):
+        for k, p in params.items():
+            p.grad = synth_tensor(f"opt.g.{k}.{step}", OPT_SHAPES[k], scale=0.02 * (step + 1)).to(DEV)
+        v0 = {k: p._version for k, p in params.items()}
+        opt.step()
+        assert all(p._version > v0[k] for k, p in params.items()), "version counters must move (weight caches key on them)"
+    torch.cuda.synchronize()
+    for k, p in params.items():
+        st = {sk: (v.detach().cpu().numpy() if torch.is_tensor(v) else v) for sk, v in opt.state[p].items()}
+        check_optimizer_state(case, k, p.detach().cpu().numpy(), st, p0[k])
+        assert opt.state[p]["step"] == 3
+
+
+def test_adafactor_refreshes_bf16_mirrors_and_packed_weights():
+    """the apply pass rewrites the bf16 copies the GEMMs consume; packed conv weights are re-derived on next use."""
+    from neurosis_b200 import ops
+    from neurosis_b200.optim import Adafactor
+    w = torch.nn.Parameter(rnd(128, 64, seed=1, scale=0.1))
+    cw = torch.nn.Parameter(rnd(64, 64, 3, 3, seed=2, scale=0.05))
+    x = rnd(32, 64, seed=3).to(BF)
+    xi = rnd(1, 8, 8, 64, seed=4).to(BF)
+    ops.linear(x, w)          # registers the bf16 mirror of w
+    ops.conv2d(xi, cw)        # caches the packed copies of cw
+    mirror = ops.registered_mirror(w)
+    assert mirror is not None
+    opt = Adafactor([w, cw], lr=1e-2, relative_step=False, scale_parameter=False)
+    w.grad, cw.grad = rnd(128, 64, seed=5), rnd(64, 64, 3, 3, seed=6)
+    opt.step()
+    torch.cuda.synchronize()
+    assert torch.equal(mirror, w.detach().to(BF)), "mirror rewritten by the apply pass"
+    assert ops.bf16_weight(w).data_ptr() == mirror.data_ptr(), "no second cast"
+    y = ops.linear(x, w)
+    assert rel(y, x.float() @ w.detach().to(BF).float().t()) < 1e-2
+    yc = ops.conv2d(xi, cw)
+    ref = F.conv2d(xi.float().permute(0, 3, 1, 2), cw.detach().to(BF).float(), padding=1)
+    assert rel(yc.permute(0, 3, 1, 2), ref) < 1e-2, "packed conv weights follow the updated parameter"
+
+
+def test_adafactor_scheduler_reports_lr():
+    from neurosis_b200.optim import Adafactor, AdafactorScheduler
+    p = torch.nn.Parameter(rnd(70, 90, scale=0.05))
+    opt = Adafactor([p], scale_parameter=True, relative_step=True, warmup_init=True)
+    sched = AdafactorScheduler(opt, initial_lr=4e-7)
+    assert sched.get_lr() == [4e-7]
+    p.grad = rnd(70, 90, seed=1, scale=0.01)
+    opt.step()
+    rms = float(p.detach().norm() / p.numel() ** 0.5)
+    lr = sched.get_lr()[0]
+    assert abs(lr - max(1e-3, rms) * 1e-6) < 1e-9 * 0.05 + 1e-12
+
+
+# ---------------------------------------------------------------- row 4: EMA
+def test_lit_ema_vs_reference_golden():
+    from neurosis_b200.optim import LitEma
+    from test_oracle_golden_next import EMA_SHAPES
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Linear(40, 30)
+            self.b = torch.nn.Conv2d(8, 8, 3)
+
+    m = M().to(DEV)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            p.copy_(synth_tensor(f"ema.p.{n}", tuple(p.shape)))
+    ema = LitEma(m, decay=0.9999).to(DEV)
+    for it in range(12):
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                p.add_(synth_tensor(f"ema.d.{n}.{it}", tuple(p.shape), scale=0.1).to(DEV))
+        ema(m)
+    sh = dict(ema.named_buffers())
+    for n in EMA_SHAPES:
+        np.testing.assert_allclose(sh[n.replace(".", "_")].cpu().numpy(), G[f"ema.{n}"], rtol=1e-6, atol=1e-7)
+    assert int(ema.num_updates) == int(G["ema.num_updates"])
+    # store / copy_to / restore round trip
+    before = [p.detach().clone() for p in m.parameters()]
+    ema.store(m.parameters())
+    ema.copy_to(m)
+    assert torch.equal(m.a.weight.detach(), sh["a_weight"])
+    ema.restore(m.parameters())
+    assert all(torch.equal(a, b.detach()) for a, b in zip(before, m.parameters()))
+
+
+# ---------------------------------------------------------------- row 3: conditioner vector path
+def test_conditioner_vector_path_on_device():
+    from neurosis_b200.modules.conditioner import ConcatTimestepEmbedderND, GeneralConditioner, IdentityEncoder
+    emb = ConcatTimestepEmbedderND(256, input_key="original_size_as_tuple")
+    sizes = torch.from_numpy(G["cond.sizes"])
+    f = emb(sizes.to(DEV))
+    assert f.shape == (4, 512) and f.is_cuda
+    # bf16 output; arguments up to 1216 rad through the fast sin/cos path: absolute error budget 1e-2
+    assert (f.float().cpu() - torch.from_numpy(G["cond.fourier"])).abs().max() < 1e-2
+    cond = GeneralConditioner([IdentityEncoder(input_key="ctx"), IdentityEncoder(input_key="pooled"),
+                               ConcatTimestepEmbedderND(256, input_key="original_size_as_tuple"),
+                               ConcatTimestepEmbedderND(256, input_key="crop_coords_top_left", ucg_rate=0.5),
+                               ConcatTimestepEmbedderND(256, input_key="target_size_as_tuple")])
+    B = 4
+    batch = {"image": torch.zeros(B, 3, 8, 8, device=DEV), "ctx": rnd(B, 77, 64), "pooled": rnd(B, 1280, seed=1),
+             "original_size_as_tuple": [(1024, 1024), (1152, 896), (832, 1216), (1024, 1024)],   # loader lists
+             "crop_coords_top_left": [(0, 0), (16, 0), (0, 32), (8, 8)],
+             "target_size_as_tuple": sizes.to(DEV)}
+    out = cond(batch)
+    assert out["crossattn"].shape == (B, 77, 64) and out["vector"].shape == (B, 1280 + 3 * 512)
+    assert torch.equal(out["vector"][:, :1280], batch["pooled"])
+    ref_o = emb(torch.tensor(batch["original_size_as_tuple"], dtype=torch.float32))
+    assert (out["vector"][:, 1280:1792].cpu() - ref_o).abs().max() < 1e-2
+    crop = out["vector"][:, 1792:2304]
+    rows_zero = (crop.abs().sum(1) == 0)
+    ref_c = emb(torch.tensor(batch["crop_coords_top_left"], dtype=torch.float32))
+    assert all(bool(z) or float((c.cpu() - r).abs().max()) < 1e-2 for z, c, r in zip(rows_zero, crop, ref_c))
+    z = cond(batch, force_zero_embeddings=["pooled"])
+    assert float(z["vector"][:, :1280].abs().sum()) == 0.0

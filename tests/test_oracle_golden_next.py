@@ -44,3 +44,57 @@ def test_vae_training_step():
                                atol=1e-7)
     np.testing.assert_allclose(esd["conv_in.weight"].grad.numpy(), G["vaetrain.grad.conv_in.weight"], rtol=1e-3,
                                atol=1e-7)
+
+
+# ---------------------------------------------------------------- rows 2 and 4: Adafactor, EMA
+OPT_SHAPES = {"lin": (96, 200), "lin_ragged": (130, 70), "conv3": (24, 16, 3, 3), "conv1": (8, 12, 1, 1),
+              "bias": (300,), "stack": (2, 70, 40)}
+OPT_CASES = {
+    "yaml": dict(scale_parameter=True, relative_step=True, warmup_init=True),
+    "ext": dict(lr=1e-3, scale_parameter=False, relative_step=False, warmup_init=False, beta1=0.9, weight_decay=0.01,
+                clip_threshold=0.5),
+}
+
+
+def check_optimizer_state(case, name, p, st, p0):
+    """shared by the CPU (oracle) and GPU (kernel) tests: parameter, moments and RMS against the reference's."""
+    g = G[f"opt.{case}.{name}.p"]
+    p = np.asarray(p, dtype=np.float32)
+    # the relative-step case moves parameters by ~3e-7 in total: compare the values to 2 ulp (1.5e-8 at |p| ~ 0.2) and
+    # the movement itself
+    np.testing.assert_allclose(p, g, rtol=0, atol=3e-8 if case == "yaml" else 2e-7)
+    d, dg = p - p0, g - p0
+    assert np.linalg.norm(d - dg) <= (0.05 if case == "yaml" else 2e-4) * np.linalg.norm(dg), (case, name)
+    for sk in ("exp_avg_sq_row", "exp_avg_sq_col", "exp_avg_sq", "exp_avg"):
+        key = f"opt.{case}.{name}.{sk}"
+        if key in G.files:
+            np.testing.assert_allclose(np.asarray(st[sk], dtype=np.float32), G[key], rtol=2e-5, atol=1e-12, err_msg=key)
+    np.testing.assert_allclose(float(st["RMS"]), G[f"opt.{case}.{name}.rms"], rtol=1e-5)
+
+
+def test_adafactor_oracle_vs_reference():
+    from oracle.optim import adafactor_init_state, adafactor_step
+    for case, kw in OPT_CASES.items():
+        for name, shape in OPT_SHAPES.items():
+            p = synth_tensor(f"opt.p.{name}", shape, scale=0.05)
+            p0 = p.numpy().copy()
+            st = adafactor_init_state(p, kw.get("beta1"))
+            for step in range(3):
+                adafactor_step(p, synth_tensor(f"opt.g.{name}.{step}", shape, scale=0.02 * (step + 1)), st, **kw)
+            check_optimizer_state(case, name, p.numpy(), {k: (v.numpy() if torch.is_tensor(v) else v)
+                                                          for k, v in st.items()}, p0)
+
+
+EMA_SHAPES = {"a.weight": (30, 40), "a.bias": (30,), "b.weight": (8, 8, 3, 3), "b.bias": (8,)}
+
+
+def test_ema_oracle_vs_reference():
+    from oracle.optim import ema_decay, ema_update
+    for name, shape in EMA_SHAPES.items():
+        p = synth_tensor(f"ema.p.{name}", shape)
+        shadow = p.clone()
+        for it in range(12):
+            p = p + synth_tensor(f"ema.d.{name}.{it}", shape, scale=0.1)
+            ema_update(shadow, p, ema_decay(0.9999, it + 1))
+        np.testing.assert_allclose(shadow.numpy(), G[f"ema.{name}"], rtol=1e-6, atol=1e-7)
+    assert int(G["ema.num_updates"]) == 12
