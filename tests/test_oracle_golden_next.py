@@ -68,7 +68,9 @@ def check_optimizer_state(case, name, p, st, p0):
     for sk in ("exp_avg_sq_row", "exp_avg_sq_col", "exp_avg_sq", "exp_avg"):
         key = f"opt.{case}.{name}.{sk}"
         if key in G.files:
-            np.testing.assert_allclose(np.asarray(st[sk], dtype=np.float32), G[key], rtol=2e-5, atol=1e-12, err_msg=key)
+            # first moments mix terms of opposite sign: tolerance relative to the tensor's scale, not per element
+            np.testing.assert_allclose(np.asarray(st[sk], dtype=np.float32), G[key], rtol=2e-5,
+                                       atol=2e-6 * float(np.abs(G[key]).max()), err_msg=key)
     np.testing.assert_allclose(float(st["RMS"]), G[f"opt.{case}.{name}.rms"], rtol=1e-5)
 
 
