@@ -33,6 +33,12 @@ REDIRECT = {
     "neurosis.modules.encoders.IdentityEncoder": f"{_M}.conditioner.IdentityEncoder",
     "neurosis.modules.encoders.metadata.ConcatTimestepEmbedderND": f"{_M}.conditioner.ConcatTimestepEmbedderND",
     "neurosis.models.diffusion.DiffusionEngine": "neurosis_b200.engine.DiffusionEngine",
+    # optimizer side: configs/sdxl/sdxl.example.yaml:158-169
+    "neurosis.optimizers.Adafactor": "neurosis_b200.optim.Adafactor",
+    "neurosis.optimizers.AdafactorScheduler": "neurosis_b200.optim.AdafactorScheduler",
+    "neurosis.optimizers.adafactor.Adafactor": "neurosis_b200.optim.Adafactor",
+    "neurosis.optimizers.adafactor.AdafactorScheduler": "neurosis_b200.optim.AdafactorScheduler",
+    "neurosis.modules.ema.LitEma": "neurosis_b200.optim.LitEma",
     # renamed in the reference tree but still present in its example YAMLs
     "neurosis.modules.diffusion.sigma_sampling.DiscreteSampling": f"{_M}.schedule.DiscreteSigmaGenerator",
     "neurosis.modules.diffusion.sigma_sampling.EDMSampling": f"{_M}.schedule.EDMSigmaGenerator",

@@ -20,7 +20,8 @@ class DiffusionEngine(nn.Module):
     def __init__(self, model: nn.Module, denoiser: Denoiser, first_stage_model: Optional[nn.Module],
                  conditioner: nn.Module, loss_fn: DiffusionLoss, scale_factor: float = 1.0,
                  input_key: str = "image", vae_batch_size: Optional[int] = None,
-                 forward_hooks: Sequence[LossHook] = (), **kwargs):
+                 forward_hooks: Sequence[LossHook] = (), use_ema: bool = False, ema_decay_rate: float = 0.9999,
+                 ckpt_path: Optional[str] = None, **kwargs):
         super().__init__()
         self.model = model if isinstance(model, OpenAIWrapper) else OpenAIWrapper(model)
         self.denoiser = denoiser
@@ -35,6 +36,26 @@ class DiffusionEngine(nn.Module):
         self.vae_batch_size = vae_batch_size
         self.forward_hooks = list(forward_hooks)
         self.global_step = 0
+        # EMA of the UNet wrapper (reference models/diffusion.py:92-98) on the multi-tensor kernel; the shadow buffers
+        # appear under `model_ema.*` in the state dict as in the reference
+        self.use_ema = use_ema
+        if use_ema:
+            from .optim import LitEma
+            self.model_ema = LitEma(self.model, decay=ema_decay_rate)
+        else:
+            self.model_ema = None
+        if ckpt_path is not None:
+            self.init_from_ckpt(ckpt_path)
+
+    def init_from_ckpt(self, path) -> None:
+        """reference models/diffusion.py:127-144 (strict=False, relocated VAE keys tolerated)."""
+        from .checkpoint import init_from_ckpt
+        self.last_ckpt_report = init_from_ckpt(self, path)
+
+    def on_train_batch_end(self, *args, **kwargs) -> None:
+        """EMA update after the optimizer step (reference models/diffusion.py:242-244)."""
+        if self.use_ema:
+            self.model_ema(self.model)
 
     def get_input(self, batch: dict) -> Tensor:
         return batch[self.input_key]

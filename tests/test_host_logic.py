@@ -131,3 +131,45 @@ def test_tag_frequency_hook():
     assert "TagFrequencyHook/scale_mean" in d
     out2, _ = hook(None, {"caption": ["common", ""]}, loss, {})   # count 4 > 3 -> 0.8 -> 1 - 0.1
     assert torch.allclose(out2, torch.tensor([0.9, 1.0]))
+
+
+def test_adafactor_layout_plan():
+    """host side of the fused optimizer: the (kind, offset, Bt, R, C) records and block counts per parameter shape."""
+    from neurosis_b200 import optim as O
+    assert O.factor_dims((320, 4, 3, 3)) == (1280, 3, 3)          # reference factors over the LAST TWO dims
+    assert O.plan_tensor((1280, 1280)) == [(O.KIND_MAT, 0, 1, 1280, 1280)]
+    assert O.plan_tensor((320, 4, 3, 3)) == [(O.KIND_SMALL, 0, 1280, 3, 3)]
+    assert O.plan_tensor((640, 320, 1, 1)) == [(O.KIND_SMALL, 0, 640 * 320, 1, 1)]
+    assert O.plan_tensor((320,)) == [(O.KIND_VEC, 0, 1, 1, 320)]
+    assert O.plan_tensor((2, 70, 40)) == [(O.KIND_MAT, 0, 1, 70, 40), (O.KIND_MAT, 2800, 1, 70, 40)]
+    assert O.blocks_for(O.KIND_MAT, 0, 1, 130, 70) == 3 and O.blocks_for(O.KIND_VEC, 4097, 1, 1, 4097) == 2
+    assert O.blocks_for(O.KIND_SMALL, 0, 1025, 3, 3) == 2
+    # every parameter of the full SDXL UNet is covered by one of the three layouts
+    sdxl = dict(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=[4, 2],
+                channel_mult=[1, 2, 4], num_head_channels=64, transformer_depth=[1, 2, 10], context_dim=2048,
+                use_linear_in_transformer=True, num_classes="sequential", adm_in_channels=2816)
+    kinds = {}
+    for name, shape in unet_param_shapes(sdxl).items():
+        recs = O.plan_tensor(shape)
+        assert len(recs) == 1, name
+        kinds[recs[0][0]] = kinds.get(recs[0][0], 0) + 1
+    assert sum(kinds.values()) == 1680 and set(kinds) == {O.KIND_VEC, O.KIND_SMALL, O.KIND_MAT}
+    with pytest.raises(ValueError):
+        O.Adafactor([torch.nn.Parameter(torch.zeros(2))], lr=1e-3, relative_step=True)
+    with pytest.raises(NotImplementedError):
+        O.Adafactor([torch.nn.Parameter(torch.zeros(2))], lr=1e-3, relative_step=False, scale_parameter=True)
+    opt = O.Adafactor([torch.nn.Parameter(torch.zeros(2))])
+    with pytest.raises(RuntimeError):  # CPU tensors: there is no fallback
+        opt.param_groups[0]["params"][0].grad = torch.zeros(2)
+        opt.step()
+
+
+def test_optimizer_class_paths_redirect():
+    from neurosis_b200 import config, optim
+    assert config.resolve("neurosis.optimizers.Adafactor") is optim.Adafactor
+    assert config.resolve("neurosis.optimizers.AdafactorScheduler") is optim.AdafactorScheduler
+    assert config.resolve("neurosis.modules.diffusion.model.Decoder").__name__ == "Decoder"
+    cfg = config.load_yaml(str(ROOT / "tests" / "golden" / "sdxl_optimizer_node.yaml"))
+    p = torch.nn.Parameter(torch.zeros(4, 4))
+    opt = config.instantiate(cfg["optimizer"], params=[p])
+    assert isinstance(opt, optim.Adafactor) and opt.defaults["warmup_init"] and opt.defaults["relative_step"]
