@@ -197,6 +197,10 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--optimizer", default="none", choices=["none", "adafactor"],
+                    help="opt-in: put the fused Adafactor step (configs/sdxl/sdxl.example.yaml:158-164) inside the timed "
+                         "step; the default measures the hot path BASELINE.json names (encode + loss + backward + all-reduce)")
+    ap.add_argument("--ema", action="store_true", help="opt-in: LitEma update of the UNet after the optimizer step")
     ap.add_argument("--breakdown", default="", help="write a per-call-site breakdown of tensor-core time to this file")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
     ap.add_argument("--ncu-step", action="store_true",
@@ -238,12 +242,24 @@ def main() -> None:
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
+    optimizer = ema = None
+    if args.optimizer == "adafactor":
+        from neurosis_b200.optim import Adafactor
+        optimizer = Adafactor(params, scale_parameter=True, relative_step=True, warmup_init=True)
+    if args.ema:
+        from neurosis_b200.optim import LitEma
+        ema = LitEma(eng.model, decay=0.9999)
+
     def eager_step(batch: dict, read_loss: bool) -> float:
         ops.refresh_weight_copies(force=True)  # a real loop updates the fp32 weights every step: re-derive the bf16 copies
         reducer.zero_grad()
         loss = eng.training_step(dict(batch))
         loss.backward()
         reducer.finish()
+        if optimizer is not None:
+            optimizer.step()
+        if ema is not None:
+            ema(eng.model)
         return loss.item() if read_loss else 0.0
 
     # ---- eager warm-up + profiling passes (before the CUDA graph is captured: both need the step's memory) ----
@@ -327,7 +343,7 @@ def main() -> None:
     if not args.no_graph:
         from neurosis_b200.graph import GraphedTrainStep
         graphed = GraphedTrainStep(eng, reducer, resident["image"], resident["crossattn_emb"], resident["vector_emb"],
-                                   warmup=1)
+                                   warmup=1, optimizer=optimizer, ema=ema)
 
         def step(batch: dict, read_loss: bool) -> float:  # noqa: F811  (replays the captured step)
             same = batch is resident
@@ -393,6 +409,12 @@ def main() -> None:
                                        + (" + bucketed NCCL gradient all-reduce" if world > 1 else ""),
                            "batch_per_gpu": B, "global_batch": B * world, "cuda_graph": graphed is not None,
                            "wgrad_side_stream": bool(ops.WGRAD_OVERLAP), "latent": "128x128x4",
+                           "optimizer_step": ("fused Adafactor (relative step, scale_parameter, warmup_init) inside the timed step"
+                                              if optimizer is not None else
+                                              "not in the timed step (north_star path = encode + loss + backward + "
+                                              "all-reduce); the fused Adafactor step over the same 2.57 G parameters "
+                                              "measures 15.0 ms, LitEma 5.0 ms (profiles/r01_next_rows_bench.log)"),
+                           "ema": ema is not None,
                            "parallelism": f"dp{world}", "l2": "working set (5 GB bf16 weights + activations) >> 126 MB L2",
                            "step_tflop_algorithmic": GFLOP_STEP * B / 1e3,
                            "mfu_vs_peak": ips / world * GFLOP_STEP * 1e9 / (pk["tflops"] * 1e12)},

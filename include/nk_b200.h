@@ -263,6 +263,14 @@ int nk_diag_gaussian_bwd(const float* moments, const float* eps, const float* dz
  *   update (state["RMS"] of the reference), may be NULL. */
 int nk_adafactor_step(const void* tensors_dev, const int32_t* blk_start_dev, int n_tensors, int n_blocks,
                       const float* hyper_dev, float* scal_dev, float* rms_out, nk_stream_t stream);
+/* Graph-replayable form of the per-step scalars: advances the device-resident step count of every parameter group
+ * (int64 [groups]) and derives hyper_dev from it and the constants consts_dev = float [groups][8] = {decay_rate, lr,
+ * eps1, eps2, clip_threshold, weight_decay, beta1, flags (1 relative_step | 2 warmup_init | 4 scale_parameter)}
+ * (adafactor.py:131-134, 216).  Launch before nk_adafactor_step inside the captured step. */
+int nk_adafactor_hyper(const float* consts_dev, int64_t* step_dev, float* hyper_dev, int n_groups, nk_stream_t stream);
+/* LitEma decay warm-up from the device-resident counter (ema.py:43-46): increments *num_updates_dev when it is >= 0 and
+ * writes one_minus_decay = 1 - min(decay, (1 + n) / (10 + n)) for nk_ema_update_multi. */
+int nk_ema_decay(float decay, int32_t* num_updates_dev, float* one_minus_decay_dev, nk_stream_t stream);
 /* EMA shadow update of LitEma.forward (modules/ema.py:40-59): shadow -= (1 - decay) * (shadow - p) for every span
  * {float* shadow; const float* p; int64 n} (24 bytes) of the device table, one thread block per span; the factor is
  * read from device memory so a captured graph can be replayed with a changing decay. */

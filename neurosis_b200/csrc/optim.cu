@@ -269,6 +269,44 @@ __global__ void __launch_bounds__(256) adafactor_finalize_kernel(const AdafTenso
     if (threadIdx.x == 0) scal[t].vr_mean = s / static_cast<float>(T.R);
 }
 
+// Device-side step scalars for captured graphs: a replayed graph cannot take new host scalars, so the step count lives
+// in device memory, is advanced by this one-thread-per-group kernel, and the per-step hyper-parameters of
+// adafactor.py:131-134, 216 are derived from it.
+struct AdafGroupConst {  // 8 floats per parameter group
+    float decay_rate, lr, eps1, eps2, clip, weight_decay, beta1, flags;  // flags: 1 relative_step, 2 warmup_init, 4 scale_parameter
+};
+__global__ void adafactor_hyper_kernel(const AdafGroupConst* __restrict__ consts, long long* __restrict__ step,
+                                       AdafHyper* __restrict__ hyper, int n_groups) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const AdafGroupConst c = consts[g];
+    const int flags = static_cast<int>(c.flags);
+    const long long s = step[g] + 1;
+    step[g] = s;
+    const float sf = static_cast<float>(s);
+    AdafHyper h;
+    h.beta2t = 1.f - powf(sf, c.decay_rate);
+    h.rel_step = (flags & 1) ? fminf((flags & 2) ? 1e-6f * sf : 1e-2f, rsqrtf(sf)) : c.lr;
+    h.eps1 = c.eps1;
+    h.eps2 = c.eps2;
+    h.clip = c.clip;
+    h.weight_decay = c.weight_decay;
+    h.beta1 = c.beta1;
+    h.scale_parameter = (flags & 4) ? 1.f : 0.f;
+    hyper[g] = h;
+}
+// LitEma's decay warm-up from the device-resident update counter (ema.py:43-46): n = ++num_updates (if >= 0);
+// one_minus_decay = 1 - min(decay, (1 + n) / (10 + n))
+__global__ void ema_decay_kernel(float decay, int* __restrict__ num_updates, float* __restrict__ one_minus_decay) {
+    float d = decay;
+    if (*num_updates >= 0) {
+        const int n = *num_updates + 1;
+        *num_updates = n;
+        d = fminf(decay, static_cast<float>(1 + n) / static_cast<float>(10 + n));
+    }
+    *one_minus_decay = 1.f - d;
+}
+
 // ---- EMA (LitEma.forward, modules/ema.py:40-59): shadow -= (1 - decay) * (shadow - p), one block per span -----------
 struct EmaSpan {
     float* shadow;
@@ -321,6 +359,21 @@ int nk_adafactor_step(const void* tensors_dev, const int32_t* blk_start_dev, int
     adafactor_finalize_kernel<<<n_tensors, 256, 0, st>>>(T, n_tensors, H, S);
     adafactor_kernel<2><<<n_blocks, 256, 0, st>>>(T, blk_start_dev, n_tensors, H, S, nullptr);
     adafactor_kernel<3><<<n_blocks, 256, 0, st>>>(T, blk_start_dev, n_tensors, H, S, rms_out);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_adafactor_hyper(const float* consts_dev, int64_t* step_dev, float* hyper_dev, int n_groups, nk_stream_t stream) {
+    NK_REQUIRE(n_groups > 0 && n_groups <= 1024, NK_ERR_SHAPE, "adafactor_hyper: %d groups", n_groups);
+    adafactor_hyper_kernel<<<(n_groups + 63) / 64, 64, 0, ST(stream)>>>(
+        reinterpret_cast<const AdafGroupConst*>(consts_dev), reinterpret_cast<long long*>(step_dev),
+        reinterpret_cast<AdafHyper*>(hyper_dev), n_groups);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_ema_decay(float decay, int32_t* num_updates_dev, float* one_minus_decay_dev, nk_stream_t stream) {
+    ema_decay_kernel<<<1, 1, 0, ST(stream)>>>(decay, num_updates_dev, one_minus_decay_dev);
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }

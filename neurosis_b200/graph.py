@@ -5,6 +5,11 @@ The step launches ~4 000 kernels of this library plus the autograd engine's own 
 a handful of shapes — one graph per bucket), so the step is captured once and replayed: the host only refreshes the
 static input buffers (images, conditioning, the per-sample sigma draw and loss weights) and launches one graph.
 
+Optionally the optimizer step (`neurosis_b200.optim.Adafactor`) and the EMA update (`optim.LitEma`) are part of the
+captured step (`optimizer=`, `ema=`): their per-step scalars (step count -> beta2t / relative step size, EMA decay
+warm-up) live in device memory and are advanced by kernels inside the graph, so a replay is a complete training
+iteration: refresh -> encode -> loss -> backward -> all-reduce -> parameter update -> EMA.
+
 Host-side semantics stay those of `DiffusionEngine.training_step` (reference models/diffusion.py:205-233): sigma draw
 on the CPU generator (`StandardDiffusionLoss.draw_sigmas`), loss hooks as per-sample weights, `loss.mean()`.
 """
@@ -22,8 +27,10 @@ from .engine import DiffusionEngine
 
 class GraphedTrainStep:
     def __init__(self, engine: DiffusionEngine, reducer: BucketedGradReducer, image: Tensor, crossattn: Tensor,
-                 vector: Optional[Tensor], warmup: int = 3):
+                 vector: Optional[Tensor], warmup: int = 3, optimizer=None, ema=None):
         self.engine, self.reducer = engine, reducer
+        self.optimizer, self.ema = optimizer, ema
+        self._opt_ready = self._ema_ready = False
         dev = image.device
         self.image = image.clone()
         self.crossattn = crossattn.clone()
@@ -45,6 +52,12 @@ class GraphedTrainStep:
         # the fp32 -> bf16 / packed weight refresh is the first thing `_core` does, so it is captured and replayed every
         # step; run it once here so its span table is built outside the capture
         ops.refresh_weight_copies(force=True)
+        if self.optimizer is not None:  # gradients exist now: build the optimizer's device tables outside the capture
+            self.optimizer.graph_prepare()
+            self._opt_ready = True
+        if self.ema is not None:
+            self.ema.graph_prepare(engine.model)
+            self._ema_ready = True
         l0 = ops.LAUNCHES
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
@@ -65,6 +78,10 @@ class GraphedTrainStep:
         self.reducer.finish()
         self.per_sample.copy_(loss.detach())
         self.loss.copy_(total.detach())
+        if self._opt_ready:  # (the eager warm-up steps before the tables exist leave the parameters untouched)
+            self.optimizer.graph_launch()
+        if self._ema_ready:
+            self.ema.graph_launch()
 
     def _refresh_sigmas(self) -> None:
         s = self.engine.loss_fn.draw_sigmas(self.sigmas.shape[0]).float()
@@ -85,3 +102,10 @@ class GraphedTrainStep:
         self._refresh_sigmas()
         self.graph.replay()
         return self.loss
+
+    def sync_host_state(self) -> None:
+        """bring the host mirrors of the device-side counters up to date (before checkpointing / leaving graph mode)."""
+        if self.optimizer is not None:
+            self.optimizer.sync_steps_from_device()
+        if self.ema is not None:
+            self.ema.sync_from_device()

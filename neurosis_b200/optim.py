@@ -179,23 +179,32 @@ class Adafactor(Optimizer):
         return tuple((p.data_ptr(), p.grad.data_ptr() if p.grad is not None else 0)
                      for g in self.param_groups for p in g["params"])
 
+    def prepare(self) -> None:
+        """(re)build the device tables if parameters / gradient buffers moved (host work; never inside a capture)."""
+        key = self._table_key()
+        if self._plan is None or key != self._key:
+            self._build()
+            self._key = key
+
+    def _launch(self) -> None:
+        plan = self._plan
+        check(lib.nk_adafactor_step(plan["table"].data_ptr(), plan["blk_start"].data_ptr(), plan["n_tensors"],
+                                    plan["n_blocks"], plan["hyper"].data_ptr(), plan["scal"].data_ptr(),
+                                    plan["rms"].data_ptr(), ops._stream()), "adafactor_step")
+        ops._count(4)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        key = self._table_key()
-        if self._plan is None or key != self._key:
-            self._build()
-            self._key = key
+        self.prepare()
         plan = self._plan
         if plan is None:
             return loss
-        steps = {}
         for p, _, _ in plan["live"]:
-            st = self.state[p]
-            st["step"] += 1
+            self.state[p]["step"] += 1
         for gi, group in enumerate(self.param_groups):
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
@@ -204,23 +213,57 @@ class Adafactor(Optimizer):
             if len(ss) != 1:
                 raise RuntimeError("neurosis_b200 Adafactor: parameters of one group must share the step count")
             step = ss.pop()
-            steps[gi] = step
-            rel = self._rel_step(group, step)
             h = plan["hyper_host"][gi]
             h[0] = 1.0 - math.pow(step, group["decay_rate"])
-            h[1] = rel
+            h[1] = self._rel_step(group, step)
             h[2], h[3] = group["eps"]
             h[4] = group["clip_threshold"]
             h[5] = group["weight_decay"]
             h[6] = group["beta1"] if group["beta1"] is not None else 0.0
             h[7] = 1.0 if group["scale_parameter"] else 0.0
         plan["hyper"].copy_(plan["hyper_host"], non_blocking=True)
-        check(lib.nk_adafactor_step(plan["table"].data_ptr(), plan["blk_start"].data_ptr(), plan["n_tensors"],
-                                    plan["n_blocks"], plan["hyper"].data_ptr(), plan["scal"].data_ptr(),
-                                    plan["rms"].data_ptr(), ops._stream()), "adafactor_step")
-        ops._count(4)
+        self._launch()
         ops.parameters_updated_in_place([(p, fresh) for p, _, fresh in plan["live"]])
         return loss
+
+    # ---- CUDA-graph form: the step count lives on the device ------------------------------------------------------
+    def graph_prepare(self) -> None:
+        """call once before capture (after the gradients exist): builds the tables and moves the per-group constants
+        and the current step counts to the device."""
+        self.prepare()
+        plan = self._plan
+        if plan is None:
+            raise RuntimeError("Adafactor.graph_prepare: no parameter has a gradient yet")
+        dev = plan["hyper"].device
+        consts, steps = [], []
+        for group in self.param_groups:
+            flags = (1 if group["relative_step"] else 0) | (2 if group["warmup_init"] else 0) | (
+                4 if group["scale_parameter"] else 0)
+            consts.append([group["decay_rate"], group["lr"] if group["lr"] is not None else 0.0, group["eps"][0],
+                           group["eps"][1], group["clip_threshold"], group["weight_decay"],
+                           group["beta1"] if group["beta1"] is not None else 0.0, float(flags)])
+            ps = [p for p in group["params"] if p.grad is not None]
+            steps.append(self.state[ps[0]]["step"] if ps else 0)
+        plan["consts"] = torch.tensor(consts, dtype=torch.float32).to(dev)
+        plan["step_dev"] = torch.tensor(steps, dtype=torch.int64).to(dev)
+
+    @torch.no_grad()
+    def graph_launch(self) -> None:
+        """the capturable step: advance the device-side step counts, derive the hyper-parameters, update.  The host
+        `state[p]["step"]` integers are brought up to date by `sync_steps_from_device()`."""
+        plan = self._plan
+        check(lib.nk_adafactor_hyper(plan["consts"].data_ptr(), plan["step_dev"].data_ptr(), plan["hyper"].data_ptr(),
+                                     len(self.param_groups), ops._stream()), "adafactor_hyper")
+        ops._count()
+        self._launch()
+
+    def sync_steps_from_device(self) -> None:
+        steps = self._plan["step_dev"].tolist()
+        for gi, group in enumerate(self.param_groups):
+            for p in group["params"]:
+                if p.grad is not None and len(self.state[p]) > 0:
+                    self.state[p]["step"] = int(steps[gi])
+        ops.parameters_updated_in_place([(p, fresh) for p, _, fresh in self._plan["live"]])
 
 
 class AdafactorScheduler(LambdaLR):
@@ -281,12 +324,7 @@ class LitEma(nn.Module):
             return min(self._decay_host, (1 + n) / (10 + n))
         return self._decay_host
 
-    @torch.no_grad()
-    def forward(self, model: nn.Module):
-        if self._n_host >= 0:
-            self._n_host += 1
-            self.num_updates += 1
-        omd = 1.0 - float(np.float32(self.current_decay()))
+    def _prepare(self, model: nn.Module) -> None:
         shadow = dict(self.named_buffers())
         pairs = []
         for key, p in model.named_parameters():
@@ -294,10 +332,8 @@ class LitEma(nn.Module):
                 pairs.append((shadow[self.m_name2s_name[key]], p))
             elif key in self.m_name2s_name:
                 raise ValueError(f"Parameter {key} is not trainable, but has a shadow parameter")
-        if not pairs:
-            return
         key = tuple((s.data_ptr(), p.data_ptr(), p.numel()) for s, p in pairs)
-        if self._table is None or key != self._key:
+        if pairs and (self._table is None or key != self._key):
             for s, p in pairs:
                 if not (s.is_cuda and p.is_cuda and s.dtype == p.dtype == torch.float32 and s.is_contiguous()
                         and p.is_contiguous()):
@@ -309,11 +345,39 @@ class LitEma(nn.Module):
             self._omd_host = torch.zeros(1, dtype=torch.float32).pin_memory()
             self._omd = torch.zeros(1, dtype=torch.float32, device=dev)
             self._key = key
-        self._omd_host[0] = omd
-        self._omd.copy_(self._omd_host, non_blocking=True)
+        self._have = bool(pairs)
+
+    def _launch(self) -> None:
         check(lib.nk_ema_update_multi(self._table.data_ptr(), self._table.shape[0], self._omd.data_ptr(),
                                       ops._stream()), "ema_update_multi")
         ops._count()
+
+    @torch.no_grad()
+    def forward(self, model: nn.Module):
+        if self._n_host >= 0:
+            self._n_host += 1
+            self.num_updates += 1
+        omd = 1.0 - float(np.float32(self.current_decay()))
+        self._prepare(model)
+        if not self._have:
+            return
+        self._omd_host[0] = omd
+        self._omd.copy_(self._omd_host, non_blocking=True)
+        self._launch()
+
+    # ---- CUDA-graph form: the update counter is the `num_updates` buffer itself -------------------------------------
+    def graph_prepare(self, model: nn.Module) -> None:
+        self._prepare(model)
+
+    @torch.no_grad()
+    def graph_launch(self) -> None:
+        check(lib.nk_ema_decay(self._decay_host, self.num_updates.data_ptr(), self._omd.data_ptr(), ops._stream()),
+              "ema_decay")
+        ops._count()
+        self._launch()
+
+    def sync_from_device(self) -> None:
+        self._n_host = int(self.num_updates)
 
     def copy_to(self, model: nn.Module):
         shadow = dict(self.named_buffers())

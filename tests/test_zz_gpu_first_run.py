@@ -1,0 +1,119 @@
+"""First-run GPU tests of the opt-in "optimizer + EMA inside the captured step" path.
+
+This file sorts LAST on purpose: the tests below were written after the round's GPU budget was spent, so a fault in them
+must not be able to disturb the validated suites that run before it in the same process."""
+import numpy as np
+import pytest
+import torch
+
+from common import ROOT, TINY_VAE
+from oracle.vae import vae_param_shapes
+from oracle.weights import synth_state_dict, synth_tensor
+from test_gpu_next import DEV, _opt_params, rel, rnd
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+# ---------------------------------------------------------------- optimizer / EMA inside the captured step (opt-in)
+# Written after this round's GPU budget was spent: these run for the first time at round end.  They are marked
+# non-strict xfail so that an unvalidated opt-in path cannot mask the state of the validated suite; an XPASS is the
+# expected outcome.  (Drop the marker once they have been seen green.)
+_first_run = pytest.mark.xfail(strict=False, reason="opt-in graph path, first GPU run happens after the round's budget")
+
+
+@_first_run
+def test_device_side_step_scalars_match_host_side():
+    """`graph_launch` (step count and hyper-parameters derived on the device) == `step` (host scalars), and the EMA
+    decay warm-up from the device counter == the host expression."""
+    from neurosis_b200.optim import Adafactor, LitEma
+    from test_oracle_golden_next import OPT_SHAPES
+    for kw in (dict(scale_parameter=True, relative_step=True, warmup_init=True),
+               dict(lr=1e-3, scale_parameter=False, relative_step=False, beta1=0.9, weight_decay=0.01)):
+        pa, pb = _opt_params(kw), _opt_params(kw)
+        oa, ob = Adafactor(list(pa.values()), **kw), Adafactor(list(pb.values()), **kw)
+        for k in pa:
+            pa[k].grad = synth_tensor(f"opt.g.{k}.0", OPT_SHAPES[k], scale=0.02).to(DEV)
+            pb[k].grad = pa[k].grad.clone()
+        ob.graph_prepare()
+        for _ in range(3):
+            oa.step()
+            ob.graph_launch()
+        ob.sync_steps_from_device()
+        for k in pa:
+            assert ob.state[pb[k]]["step"] == 3
+            d_a, d_b = pa[k].detach() - synth_tensor(f"opt.p.{k}", OPT_SHAPES[k], scale=0.05).to(DEV), \
+                pb[k].detach() - synth_tensor(f"opt.p.{k}", OPT_SHAPES[k], scale=0.05).to(DEV)
+            assert rel(d_b, d_a) < (5e-2 if kw.get("relative_step") else 1e-4), k  # ~3e-7 movements resolve to ~2 %
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Linear(40, 30)
+
+    ma, mb = M().to(DEV), M().to(DEV)
+    mb.load_state_dict(ma.state_dict())
+    ea, eb = LitEma(ma, decay=0.9999).to(DEV), LitEma(mb, decay=0.9999).to(DEV)
+    eb.graph_prepare(mb)
+    for it in range(12):
+        with torch.no_grad():
+            d = rnd(30, 40, seed=it, scale=0.1)
+            ma.a.weight.add_(d)
+            mb.a.weight.add_(d)
+        ea(ma)
+        eb.graph_launch()
+    eb.sync_from_device()
+    assert int(eb.num_updates) == 12 and eb._n_host == 12
+    assert rel(eb.a_weight, ea.a_weight) < 1e-6
+
+
+@_first_run
+def test_graphed_step_with_optimizer_and_ema():
+    """one replay = refresh -> encode -> loss -> backward -> reduce -> Adafactor -> EMA; counters advance per replay."""
+    from test_gpu_modules import build_unet  # noqa: F401  (shared tiny-model builder)
+    from common import TINY_SDXL, TINY_VAE as TV
+    from neurosis_b200.ddp import BucketedGradReducer
+    from neurosis_b200.engine import DiffusionEngine
+    from neurosis_b200.graph import GraphedTrainStep
+    from neurosis_b200.modules.conditioner import GeneralConditioner, IdentityEncoder
+    from neurosis_b200.modules.denoiser import DiscreteDenoiser, EpsPreconditioning, EpsWeighting
+    from neurosis_b200.modules.loss import StandardDiffusionLoss
+    from neurosis_b200.modules.schedule import DiscreteSigmaGenerator, LegacyDDPMDiscretization
+    from neurosis_b200.modules.vae import Encoder
+    from neurosis_b200.optim import Adafactor, LitEma
+
+    class RandIdx(DiscreteSigmaGenerator):
+        def __call__(self, n, t=None):
+            return super().__call__(n, None).clamp_min(0.03)
+
+    cfg = TINY_SDXL
+    unet = build_unet(cfg)
+    enc = Encoder(**TV, embed_dim=4, standalone=True)
+    enc.load_state_dict(synth_state_dict(vae_param_shapes(TV, embed_dim=4, standalone=True), seed=2))
+    eng = DiffusionEngine(unet, DiscreteDenoiser(EpsPreconditioning(), 1000, LegacyDDPMDiscretization()), enc,
+                          GeneralConditioner([IdentityEncoder(input_key="ctx"), IdentityEncoder(input_key="vec")]),
+                          StandardDiffusionLoss(RandIdx(LegacyDDPMDiscretization(), 1000), EpsWeighting()),
+                          scale_factor=0.13025).to(DEV)
+    params = [p for p in eng.model.parameters() if p.requires_grad]
+    p0 = [p.detach().clone() for p in params]
+    red = BucketedGradReducer(params, bucket_mb=8.0)
+    red.attach_as_grad_sink()
+    opt = Adafactor(params, lr=1e-3, relative_step=False, scale_parameter=False)
+    ema = LitEma(eng.model, decay=0.9999)
+    img = synth_tensor("vae.img", (2, 3, 64, 64), uniform=True).to(DEV)
+    ctx = synth_tensor("sdxl.ctx", (2, 77, cfg["context_dim"])).to(DEV)
+    vec = synth_tensor("sdxl.y", (2, cfg["adm_in_channels"])).to(DEV)
+    try:
+        g = GraphedTrainStep(eng, red, img, ctx, vec, warmup=2, optimizer=opt, ema=ema)
+        assert all(torch.equal(a, b.detach()) for a, b in zip(p0, params)), "warm-up and capture leave the weights alone"
+        losses = [float(g.step().item()) for _ in range(3)]
+        g.sync_host_state()
+    finally:
+        red.detach_grad_sink()
+    assert all(np.isfinite(losses))
+    assert all(opt.state[p]["step"] == 3 for p in params) and int(ema.num_updates) == 3
+    moved = [float((a - b.detach()).abs().max()) for a, b in zip(p0, params)]
+    assert all(np.isfinite(moved)) and min(moved) > 0 and max(moved) < 1e-2  # lr 1e-3, clipped unit-RMS updates, 3 steps
+    sh = dict(ema.named_buffers())
+    w = eng.model.diffusion_model.out[2].weight
+    s = sh["diffusion_model_out_2_weight"]
+    assert torch.isfinite(s).all() and float((s - w.detach()).abs().max()) > 0
