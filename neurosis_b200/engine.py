@@ -21,7 +21,7 @@ class DiffusionEngine(nn.Module):
                  conditioner: nn.Module, loss_fn: DiffusionLoss, scale_factor: float = 1.0,
                  input_key: str = "image", vae_batch_size: Optional[int] = None,
                  forward_hooks: Sequence[LossHook] = (), use_ema: bool = False, ema_decay_rate: float = 0.9999,
-                 ckpt_path: Optional[str] = None, **kwargs):
+                 ckpt_path: Optional[str] = None, optimizer=None, scheduler=None, **kwargs):
         super().__init__()
         self.model = model if isinstance(model, OpenAIWrapper) else OpenAIWrapper(model)
         self.denoiser = denoiser
@@ -36,6 +36,7 @@ class DiffusionEngine(nn.Module):
         self.vae_batch_size = vae_batch_size
         self.forward_hooks = list(forward_hooks)
         self.global_step = 0
+        self.optimizer, self.scheduler = optimizer, scheduler  # callables: params -> optimizer, optimizer -> scheduler
         # EMA of the UNet wrapper (reference models/diffusion.py:92-98) on the multi-tensor kernel; the shadow buffers
         # appear under `model_ema.*` in the state dict as in the reference
         self.use_ema = use_ema
@@ -51,6 +52,31 @@ class DiffusionEngine(nn.Module):
         """reference models/diffusion.py:127-144 (strict=False, relocated VAE keys tolerated)."""
         from .checkpoint import init_from_ckpt
         self.last_ckpt_report = init_from_ckpt(self, path)
+
+    def configure_optimizers(self):
+        """parameter groups of the reference (models/diffusion.py:261-296): one "UNet" group plus one per trainable
+        embedder, each with its optional `initial_lr` (`base_lr` attribute).  `self.optimizer` / `self.scheduler` are
+        the callables the YAML's `optimizer:` / `scheduler:` nodes produce (default: the fused Adafactor with the
+        example configs' arguments)."""
+        groups = []
+        unet = {"name": "UNet", "params": list(self.model.parameters())}
+        if getattr(self.model, "base_lr", None) is not None:
+            unet["initial_lr"] = self.model.base_lr
+        groups.append(unet)
+        for emb in getattr(self.conditioner, "embedders", []):
+            if getattr(emb, "is_trainable", False):
+                g = {"name": getattr(emb, "name", emb.__class__.__name__), "params": list(emb.parameters())}
+                if getattr(emb, "base_lr", None) is not None:
+                    g["initial_lr"] = emb.base_lr
+                groups.append(g)
+        if self.optimizer is not None:
+            opt = self.optimizer(groups)
+        else:
+            from .optim import Adafactor
+            opt = Adafactor(groups, scale_parameter=True, relative_step=True, warmup_init=True)
+        if self.scheduler is not None:
+            return {"optimizer": opt, "lr_scheduler": {"scheduler": self.scheduler(opt), "interval": "step"}}
+        return opt
 
     def on_train_batch_end(self, *args, **kwargs) -> None:
         """EMA update after the optimizer step (reference models/diffusion.py:242-244)."""

@@ -106,3 +106,24 @@ def test_key_rewrites_equal_the_reference_converters():
                           "model.diffusion_model.out.2.weight": torch.zeros(1),
                           "first_stage_model.encoder.conv_in.weight": torch.zeros(1)}}
     assert list(ldm_sd15_to_neurosis(ldm)) == list(_extract(conv / "sd15-ldm2neurosis.py", "rename_keys")(ldm))
+
+
+def test_configure_optimizers_param_groups():
+    """reference models/diffusion.py:261-296: a "UNet" group, one group per trainable embedder, optional initial_lr."""
+    from neurosis_b200.modules.vae import Encoder
+    from neurosis_b200.optim import Adafactor, AdafactorScheduler
+    eng = _engine(Encoder(**TINY_VAE, embed_dim=4, standalone=True))
+    opt = eng.configure_optimizers()
+    assert isinstance(opt, Adafactor) and [g["name"] for g in opt.param_groups] == ["UNet"]
+    assert len(opt.param_groups[0]["params"]) == len(unet_param_shapes(TINY_SDXL))
+
+    class Emb(torch.nn.Linear):
+        is_trainable, base_lr, input_key, ucg_rate = True, 1e-6, "x", 0.0
+
+    eng.conditioner.embedders.append(Emb(4, 4))
+    eng.model.base_lr = 2e-6
+    eng.scheduler = lambda o: AdafactorScheduler(o, initial_lr=4e-7)
+    out = eng.configure_optimizers()
+    groups = out["optimizer"].param_groups
+    assert [g["name"] for g in groups] == ["UNet", "Emb"] and out["lr_scheduler"]["interval"] == "step"
+    assert isinstance(out["lr_scheduler"]["scheduler"], AdafactorScheduler)
