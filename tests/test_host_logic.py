@@ -173,3 +173,31 @@ def test_optimizer_class_paths_redirect():
     p = torch.nn.Parameter(torch.zeros(4, 4))
     opt = config.instantiate(cfg["optimizer"], params=[p])
     assert isinstance(opt, optim.Adafactor) and opt.defaults["warmup_init"] and opt.defaults["relative_step"]
+
+
+def test_synthetic_aspect_bucket_batches():
+    """§8(d) config 4 inputs: single-bucket batches, Zipf captions, size/crop tuples; deterministic per rank."""
+    from neurosis_b200.modules.conditioner import ConcatTimestepEmbedderND, GeneralConditioner, IdentityEncoder
+    from neurosis_b200.modules.loss import TagFreqScale, TagFrequencyHook
+    from neurosis_b200.synthetic import SDXL_BUCKETS, AspectBucketBatches
+    a, b = AspectBucketBatches(4, rank=0, images=False), AspectBucketBatches(4, rank=0, images=False)
+    x, y = a(), b()
+    assert x["bucket"] == y["bucket"] and x["caption"] == y["caption"]
+    assert torch.equal(x["crossattn_emb"], y["crossattn_emb"])
+    assert AspectBucketBatches(4, rank=1, images=False)()["caption"] != x["caption"]
+    assert all(8 <= len(c.split(" ")) <= 40 for c in x["caption"])
+    seen = {a()["bucket"] for _ in range(40)}
+    assert seen == {0, 1, 2}
+    full = AspectBucketBatches(2, images=True)(bucket=0)
+    w, h = SDXL_BUCKETS[0]
+    assert full["image"].shape == (2, 3, h, w) and float(full["image"].abs().max()) <= 1.0
+    # the batch feeds the conditioner (vector = pooled | 3 x Fourier(256) x 2 = 2816) and the tag-frequency hook
+    cond = GeneralConditioner([IdentityEncoder(input_key="crossattn_emb"), IdentityEncoder(input_key="pooled_emb"),
+                               ConcatTimestepEmbedderND(256, input_key="original_size_as_tuple"),
+                               ConcatTimestepEmbedderND(256, input_key="crop_coords_top_left"),
+                               ConcatTimestepEmbedderND(256, input_key="target_size_as_tuple")])
+    c = cond(full)
+    assert c["vector"].shape == (2, 2816) and c["crossattn"].shape == (2, 77, 2048)
+    hook = TagFrequencyHook(alpha=0.2, beta=0.99, freq_scale=TagFreqScale([[-1, 1.1], [2, 1.0], [10, 0.9]]))
+    wts = [hook.sample_weights(a()["caption"]) for _ in range(20)][-1]
+    assert len(wts) == 4 and all(0.9 < v < 1.1 for v in wts)
