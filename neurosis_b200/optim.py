@@ -252,6 +252,8 @@ class Adafactor(Optimizer):
         """the capturable step: advance the device-side step counts, derive the hyper-parameters, update.  The host
         `state[p]["step"]` integers are brought up to date by `sync_steps_from_device()`."""
         plan = self._plan
+        if plan is None or "consts" not in plan:
+            raise RuntimeError("Adafactor.graph_launch: call graph_prepare() first")
         check(lib.nk_adafactor_hyper(plan["consts"].data_ptr(), plan["step_dev"].data_ptr(), plan["hyper"].data_ptr(),
                                      len(self.param_groups), ops._stream()), "adafactor_hyper")
         ops._count()
@@ -367,10 +369,21 @@ class LitEma(nn.Module):
 
     # ---- CUDA-graph form: the update counter is the `num_updates` buffer itself -------------------------------------
     def graph_prepare(self, model: nn.Module) -> None:
+        """call once before capture.  The update counter and decay are created as CPU buffers (as in the reference,
+        ema.py:20-21) and normally follow the owning module's `.to(device)`; the captured decay kernel dereferences
+        `num_updates`, so it must live on the parameters' device."""
         self._prepare(model)
+        if not self._have:
+            raise RuntimeError("LitEma.graph_prepare: the model has no trainable parameters")
+        dev = self._omd.device
+        if self.num_updates.device != dev:
+            self.num_updates = self.num_updates.to(dev)
+            self.decay = self.decay.to(dev)
 
     @torch.no_grad()
     def graph_launch(self) -> None:
+        if not (self.num_updates.is_cuda and self.num_updates.dtype == torch.int32):
+            raise RuntimeError("LitEma.graph_launch: call graph_prepare(model) first (num_updates must be a CUDA int32 buffer)")
         check(lib.nk_ema_decay(self._decay_host, self.num_updates.data_ptr(), self._omd.data_ptr(), ops._stream()),
               "ema_decay")
         ops._count()

@@ -1,7 +1,12 @@
 """First-run GPU tests of the opt-in "optimizer + EMA inside the captured step" path.
 
 This file sorts LAST on purpose: the tests below were written after the round's GPU budget was spent, so a fault in them
-must not be able to disturb the validated suites that run before it in the same process."""
+must not be able to disturb the validated suites that run before it in the same process.
+
+Status after the last GPU call of round 1 (profiles/r01_pytest_gpu_first_run.log): the device-side step-scalar test
+passed; the graphed step hit an illegal address because `LitEma`'s `num_updates` buffer was still on the CPU when the
+captured decay kernel dereferenced it (the test built the EMA without `.to(device)`).  `LitEma.graph_prepare` now
+moves the counter to the parameters' device; that fix has not run on a GPU yet, hence the markers stay."""
 import numpy as np
 import pytest
 import torch
