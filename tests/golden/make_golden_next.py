@@ -73,11 +73,12 @@ out["vaetrain.dec_grad_l2"] = np.array([dec.get_parameter(n).grad.norm().item() 
 out["vaetrain.grad.quant_conv.weight"] = enc.get_parameter("quant_conv.weight").grad.numpy()
 out["vaetrain.grad.conv_in.weight"] = enc.get_parameter("conv_in.weight").grad.numpy()
 
-extra = HERE / "_golden_next_extra.py"
-if extra.exists():  # rows 2-4 (kept in a separate file so each row's generator can be read on its own)
-    exec(compile(extra.read_text(), str(extra), "exec"), {"out": out, "HERE": HERE, "np": np, "torch": torch,
-                                                           "synth_tensor": synth_tensor,
-                                                           "synth_state_dict": synth_state_dict})
+for extra in (HERE / "_golden_next_extra.py",      # rows 2-4
+              HERE / "_golden_next_families.py"):  # all shipped schedule / preconditioning / weighting variants
+    if extra.exists():  # (separate files so each generator can be read on its own)
+        exec(compile(extra.read_text(), str(extra), "exec"), {"out": out, "HERE": HERE, "np": np, "torch": torch,
+                                                               "synth_tensor": synth_tensor,
+                                                               "synth_state_dict": synth_state_dict})
 
 np.savez_compressed(HERE / "reference_golden_next.npz", **out)
 print("wrote", HERE / "reference_golden_next.npz", {k: v.shape for k, v in out.items()})

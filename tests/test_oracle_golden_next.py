@@ -100,3 +100,48 @@ def test_ema_oracle_vs_reference():
             ema_update(shadow, p, ema_decay(0.9999, it + 1))
         np.testing.assert_allclose(shadow.numpy(), G[f"ema.{name}"], rtol=1e-6, atol=1e-7)
     assert int(G["ema.num_updates"]) == 12
+
+
+# ---------------------------------------------------------------- §8(a) rows 6-8: every shipped variant, bit-exact
+def _family_cases():
+    return [k for k in G.files if k.startswith("fam.") and k not in ("fam.sigma", "fam.sigma01", "fam.t", "fam.errors")]
+
+
+def test_schedule_and_denoiser_families_bit_exact_vs_reference():
+    """every Discretization / SigmaGenerator / DenoiserPreconditioning / DenoiserWeighting class the reference ships,
+    with default constructor arguments, on fixed inputs: the drop-in classes return the SAME BITS (they use the
+    reference's torch op / dtype sequence), for n = 1000 and 40 steps, flipped and not, t given and drawn."""
+    from neurosis_b200.modules import denoiser as D
+    from neurosis_b200.modules import schedule as S
+    sig, sig01, t = (torch.from_numpy(G[k]) for k in ("fam.sigma", "fam.sigma01", "fam.t"))
+    cases = _family_cases()
+    assert len(cases) == 72
+    seen = set()
+    for key in cases:
+        _, kind, name, *rest = key.split(".")
+        seen.add((kind, name))
+        if kind == "disc":
+            val = getattr(S, name)()(int(rest[0]), flip=bool(int(rest[1])))
+        elif kind == "precond":
+            val = getattr(D, name)()(sig01 if "RectifiedFlow" in name else sig)[int(rest[0])]
+        elif kind == "weight":
+            obj = D.MinSNRGammaModifier(D.EpsWeighting()) if name == "MinSNRGammaModifier" else getattr(D, name)()
+            val = obj(sig01 if "RectifiedFlow" in name else sig)
+        else:
+            gen = (S.DiscreteSigmaGenerator(S.LegacyDDPMDiscretization(), 1000) if name == "DiscreteSigmaGenerator"
+                   else getattr(S, name)())
+            if rest[0] == "t":
+                val = gen(16, t.clone())
+            else:
+                torch.manual_seed(7)
+                val = gen(16, None)
+        got = torch.as_tensor(val).detach().double().numpy()
+        assert got.shape == G[key].shape and np.array_equal(got, G[key]), key
+    assert len({n for k, n in seen if k == "disc"}) == 7 and len({n for k, n in seen if k == "gen"}) == 6
+    assert len({n for k, n in seen if k == "precond"}) == 6 and len({n for k, n in seen if k == "weight"}) == 6
+    # the only reference failure on these inputs: LegacyDDPMDiscretization(n < 1000) raises (negative numpy stride);
+    # the drop-in returns the table instead (DESIGN.md §3)
+    assert sorted(G["fam.errors"]) == ["fam.disc.LegacyDDPMDiscretization.40.0=ValueError",
+                                       "fam.disc.LegacyDDPMDiscretization.40.1=ValueError"]
+    from neurosis_b200.modules.schedule import LegacyDDPMDiscretization
+    assert LegacyDDPMDiscretization()(40).shape == (41,)
