@@ -115,7 +115,7 @@ def test_schedule_and_denoiser_families_bit_exact_vs_reference():
     from neurosis_b200.modules import schedule as S
     sig, sig01, t = (torch.from_numpy(G[k]) for k in ("fam.sigma", "fam.sigma01", "fam.t"))
     cases = _family_cases()
-    assert len(cases) == 72
+    assert len(cases) == 68  # 26 tables + 24 preconditioning terms + 6 weightings + 12 generator draws
     seen = set()
     for key in cases:
         _, kind, name, *rest = key.split(".")
