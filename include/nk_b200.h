@@ -235,6 +235,12 @@ int nk_weighted_mse_fwd(const float* D, const float* T, const float* w, float* l
                         nk_stream_t stream);
 int nk_weighted_mse_bwd(const float* D, const float* T, const float* w, const float* dloss, float* dD, int B,
                         int64_t per_sample, nk_stream_t stream);
+/* the L1 form (BatchL1Loss, modules/losses/functions.py:65-78; StandardDiffusionLoss loss_type "l1"):
+ * loss[b] = w[b] * mean(|D[b]-T[b]|), gradient w[b]/n * sign(D - T) */
+int nk_weighted_l1_fwd(const float* D, const float* T, const float* w, float* loss, int B, int64_t per_sample,
+                       nk_stream_t stream);
+int nk_weighted_l1_bwd(const float* D, const float* T, const float* w, const float* dloss, float* dD, int B,
+                       int64_t per_sample, nk_stream_t stream);
 
 /* ---- VAE posterior (section 8(f) row 1: VAE training step) ------------------------------------
  * DiagonalGaussianDistribution (modules/distributions.py:29-51) as used by DiagonalGaussianRegularizer

@@ -76,6 +76,37 @@ __global__ void weighted_mse_bwd_kernel(const float* __restrict__ D, const float
     }
 }
 
+// L1 form (BatchL1Loss, losses/functions.py:65-78; StandardDiffusionLoss loss_type "l1"): loss[b] = w[b] * mean_i |D - T|
+__global__ void weighted_l1_fwd_kernel(const float* __restrict__ D, const float* __restrict__ T,
+                                       const float* __restrict__ w, float* __restrict__ loss, long long n) {
+    const int b = blockIdx.x;
+    const float* d = D + b * n;
+    const float* t = T + b * n;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += fabsf(d[i] - t[i]);
+    __shared__ float red[32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) loss[b] = v / static_cast<float>(n) * w[b];
+    }
+}
+// dD[b,i] = dloss[b] * w[b] / n * sign(D - T)   (sign(0) = 0, as torch's l1_loss backward)
+__global__ void weighted_l1_bwd_kernel(const float* __restrict__ D, const float* __restrict__ T,
+                                       const float* __restrict__ w, const float* __restrict__ dloss,
+                                       float* __restrict__ dD, long long n, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / n;
+        const float e = D[i] - T[i];
+        const float sg = e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f);
+        dD[i] = dloss[b] * w[b] * (1.f / static_cast<float>(n)) * sg;
+    }
+}
+
 // ---- diagonal Gaussian posterior of the VAE (modules/distributions.py:29-51, regularizers.py:31-41) ----------------
 // moments[b] = (mean | logvar) halves of 2*C channels, each `half` = C*H*W contiguous floats (NCHW).  logvar is clamped
 // to [-30, 20]; z = mean + exp(0.5 logvar) * eps (eps == nullptr: mode, z = mean); kl[b] = 0.5 * sum(mean^2 + var - 1
@@ -173,6 +204,19 @@ int nk_weighted_mse_bwd(const float* D, const float* T, const float* w, const fl
     return NK_OK;
 }
 
+int nk_weighted_l1_fwd(const float* D, const float* T, const float* w, float* loss, int B, int64_t per_sample,
+                       nk_stream_t stream) {
+    weighted_l1_fwd_kernel<<<B, 1024, 0, ST(stream)>>>(D, T, w, loss, per_sample);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
+int nk_weighted_l1_bwd(const float* D, const float* T, const float* w, const float* dloss, float* dD, int B,
+                       int64_t per_sample, nk_stream_t stream) {
+    const long long total = static_cast<long long>(B) * per_sample;
+    weighted_l1_bwd_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(D, T, w, dloss, dD, per_sample, total);
+    NK_CUDA(cudaGetLastError());
+    return NK_OK;
+}
 int nk_diag_gaussian_fwd(const float* moments, const float* eps, float* z, float* kl, int B, int64_t half,
                          nk_stream_t stream) {
     NK_REQUIRE(B > 0 && half > 0, NK_ERR_SHAPE, "diag_gaussian_fwd: B=%d", B);

@@ -67,7 +67,7 @@ class StandardDiffusionLoss(DiffusionLoss):
         if kind in ("l2", "mse"):
             self.loss_type = "l2"
         elif kind == "l1":
-            raise NotImplementedError("L1 diffusion loss has no sm_100a kernel yet (reference configs use l2)")
+            self.loss_type = "l1"
         else:
             raise ValueError(f"Unknown loss type: '{loss_type}'")
         if self.objective_type not in ("edm", "rf"):
@@ -107,6 +107,8 @@ class StandardDiffusionLoss(DiffusionLoss):
         return loss
 
     def get_loss(self, outputs: Tensor, target: Tensor, weight: Tensor) -> Tensor:
+        if self.loss_type == "l1":
+            return ops.weighted_l1(outputs, target, weight)
         return ops.weighted_mse(outputs, target, weight)
 
 

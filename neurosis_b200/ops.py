@@ -1455,6 +1455,38 @@ def weighted_mse(D: Tensor, T: Tensor, w: Tensor) -> Tensor:
     return WeightedMseFn.apply(D, T, w)
 
 
+class WeightedL1Fn(torch.autograd.Function):
+    """loss[b] = w[b] * mean(|D[b]-T[b]|) in fp32 (loss.py:153-155 with loss_type "l1", losses/functions.py:65-78)."""
+
+    @staticmethod
+    def forward(ctx, D, T, w):
+        D = D.float().contiguous()
+        T = T.float().contiguous()
+        w = w.float().contiguous()
+        B = D.shape[0]
+        loss = torch.empty((B,), dtype=F32, device=D.device)
+        check(lib.nk_weighted_l1_fwd(D.data_ptr(), T.data_ptr(), w.data_ptr(), loss.data_ptr(), B, D.numel() // B,
+                                     _stream()), "weighted_l1_fwd")
+        _count()
+        ctx.save_for_backward(D, T, w)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        D, T, w = ctx.saved_tensors
+        B = D.shape[0]
+        dD = torch.empty_like(D)
+        dl = dloss.float().contiguous()
+        check(lib.nk_weighted_l1_bwd(D.data_ptr(), T.data_ptr(), w.data_ptr(), dl.data_ptr(), dD.data_ptr(), B,
+                                     D.numel() // B, _stream()), "weighted_l1_bwd")
+        _count()
+        return dD, None, None
+
+
+def weighted_l1(D: Tensor, T: Tensor, w: Tensor) -> Tensor:
+    return WeightedL1Fn.apply(D, T, w)
+
+
 # --------------------------------------------------------------------------------------------
 # VAE training step (SURVEY.md §8(f) row 1): posterior, thin 1x1 convolutions, trainable RGB stem
 # --------------------------------------------------------------------------------------------

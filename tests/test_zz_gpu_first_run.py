@@ -122,3 +122,21 @@ def test_graphed_step_with_optimizer_and_ema():
     w = eng.model.diffusion_model.out[2].weight
     s = sh["diffusion_model_out_2_weight"]
     assert torch.isfinite(s).all() and float((s - w.detach()).abs().max()) > 0
+
+
+@_first_run
+def test_weighted_l1_loss_fwd_bwd():
+    """StandardDiffusionLoss(loss_type="l1") arithmetic: loss[b] = w[b] * mean|D - T| (BatchL1Loss) and its gradient."""
+    from neurosis_b200 import ops
+    D = rnd(3, 4, 16, 16).requires_grad_(True)
+    T = rnd(3, 4, 16, 16, seed=1)
+    with torch.no_grad():
+        D[0, 0, 0, :4] = T[0, 0, 0, :4]  # exact ties: sign(0) = 0 on both sides
+    w = rnd(3, seed=2).abs() + 0.1
+    loss = ops.weighted_l1(D, T, w)
+    g = rnd(3, seed=3)
+    loss.backward(g)
+    Dr = D.detach().clone().requires_grad_(True)
+    lr_ = (Dr - T).abs().flatten(1).mean(1) * w
+    lr_.backward(g)
+    assert rel(loss, lr_) < 1e-5 and rel(D.grad, Dr.grad) < 1e-6
