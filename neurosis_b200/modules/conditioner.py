@@ -23,13 +23,24 @@ KEY2CATDIM = {"vector": 1, "crossattn": 2, "concat": 1}
 
 
 class AbstractEmbModel(nn.Module):
-    def __init__(self, input_key: Optional[str] = None, input_keys: Optional[Sequence[str]] = None,
-                 is_trainable: bool = False, ucg_rate: float = 0.0, **kwargs):
+    """embedder base of the reference (encoders/embedding.py:17-56): same constructor arguments in the same order
+    (`name`, `input_key`, `ucg_rate`, `is_trainable`, `base_lr`); `input_keys` (multi-input embedders) is accepted as a
+    keyword.  `base_lr` feeds `DiffusionEngine.configure_optimizers` (per-group `initial_lr`)."""
+
+    def __init__(self, name: Optional[str] = None, input_key: Optional[str] = None, ucg_rate: Optional[float] = 0.0,
+                 is_trainable: Optional[bool] = None, base_lr: Optional[float] = None,
+                 input_keys: Optional[Sequence[str]] = None, **kwargs):
         super().__init__()
+        self.name = name or str(self.__class__.__name__)
         self.input_key = input_key
         self.input_keys = list(input_keys) if input_keys is not None else None
-        self.is_trainable = is_trainable
+        self.is_trainable = is_trainable or False
         self.ucg_rate = ucg_rate
+        self.base_lr = base_lr
+
+    def freeze(self) -> None:
+        self.eval()
+        self.requires_grad_(False)
 
 
 class IdentityEncoder(AbstractEmbModel):

@@ -140,8 +140,8 @@ class DiagonalGaussianRegularizer(nn.Module):
     sum(kl) / B.  Sampling draws eps with torch.randn on the moments' device (the reference draws on the CPU and
     copies, distributions.py:39-41 — a different RNG stream, same distribution); `eps` can be passed for parity."""
 
-    def __init__(self, sample: bool = False):
-        super().__init__()
+    def __init__(self, sample: bool = True):  # the reference's default (regularizers.py:24); the engine's latent
+        super().__init__()                     # encode constructs it with sample=False (autoencoder.py:443)
         self.sample = sample
 
     def get_trainable_parameters(self):

@@ -4,7 +4,7 @@ from pathlib import Path
 import pytest
 import yaml
 
-from common import have_reference
+from common import have_reference, import_reference
 from neurosis_b200 import config
 
 FRAGMENT = """
@@ -60,3 +60,55 @@ def test_reference_yaml_unet_denoiser_loss_nodes_resolve(path):
     assert den.sigmas.shape == (1001,)
     loss = config.instantiate(cfg["loss_fn"])
     assert loss.loss_type == "l2"
+
+
+@pytest.mark.skipif(not have_reference(), reason="needs /root/reference (authoring container)")
+def test_constructor_and_forward_signatures_match_the_reference():
+    """argument names, order and defaults of every mirrored class (`__init__` and `forward`) equal the reference's, so a
+    YAML `init_args` block or a positional call written for the reference binds the same way.  Allowed differences:
+    enum defaults given as their string values, `temb=None` default of the VAE ResnetBlock."""
+    import importlib
+    import inspect
+    import_reference()
+    pairs = [
+        ("neurosis.modules.diffusion.openaimodel", "neurosis_b200.modules.openaimodel",
+         ["UNetModel", "ResBlock", "Upsample", "Downsample", "Timestep", "TimestepEmbedSequential"]),
+        ("neurosis.modules.attention", "neurosis_b200.modules.attention",
+         ["SpatialTransformer", "BasicTransformerBlock", "CrossAttention", "MemoryEfficientCrossAttention",
+          "TorchSDPCrossAttention", "FeedForward", "GEGLU"]),
+        ("neurosis.modules.diffusion.model", "neurosis_b200.modules.vae",
+         ["Encoder", "Decoder", "ResnetBlock", "AttnBlock", "Upsample", "Downsample"]),
+        ("neurosis.modules.diffusion.denoiser", "neurosis_b200.modules.denoiser", ["Denoiser", "DiscreteDenoiser"]),
+        ("neurosis.modules.diffusion.loss", "neurosis_b200.modules.loss", ["StandardDiffusionLoss", "DiffusionLoss"]),
+        ("neurosis.modules.regularizers", "neurosis_b200.modules.vae", ["DiagonalGaussianRegularizer"]),
+        ("neurosis.optimizers.adafactor", "neurosis_b200.optim", ["Adafactor", "AdafactorScheduler"]),
+        ("neurosis.modules.ema", "neurosis_b200.optim", ["LitEma"]),
+        ("neurosis.modules.encoders.embedding", "neurosis_b200.modules.conditioner",
+         ["GeneralConditioner", "AbstractEmbModel"]),
+        ("neurosis.modules.encoders.metadata", "neurosis_b200.modules.conditioner", ["ConcatTimestepEmbedderND"]),
+    ]
+    allowed = {("ResnetBlock", "forward", "temb"), ("StandardDiffusionLoss", "__init__", "loss_type"),
+               ("StandardDiffusionLoss", "__init__", "objective_type")}
+    problems = []
+    for rmod, mmod, names in pairs:
+        R, M = importlib.import_module(rmod), importlib.import_module(mmod)
+        for n in names:
+            for meth in ("__init__", "forward"):
+                if not hasattr(getattr(R, n), meth):
+                    continue
+                rs = inspect.signature(getattr(getattr(R, n), meth)).parameters
+                ms = inspect.signature(getattr(getattr(M, n), meth)).parameters
+                named = lambda ps: [(k, v.default) for k, v in ps.items()  # noqa: E731
+                                    if v.kind not in (v.VAR_POSITIONAL, v.VAR_KEYWORD)]
+                mine = dict(named(ms))
+                var_kw = any(v.kind == v.VAR_KEYWORD for v in ms.values())
+                for k, d in named(rs):
+                    if k not in mine:
+                        if not var_kw:
+                            problems.append((n, meth, k, "missing"))
+                    elif repr(mine[k]) != repr(d) and (n, meth, k) not in allowed:
+                        problems.append((n, meth, k, f"default {mine[k]!r} != {d!r}"))
+                shared = [k for k, _ in named(rs) if k in mine]
+                if shared != [k for k in mine if k in dict(named(rs))]:
+                    problems.append((n, meth, "order"))
+    assert not problems, problems
