@@ -201,3 +201,25 @@ def test_synthetic_aspect_bucket_batches():
     hook = TagFrequencyHook(alpha=0.2, beta=0.99, freq_scale=TagFreqScale([[-1, 1.1], [2, 1.0], [10, 0.9]]))
     wts = [hook.sample_weights(a()["caption"]) for _ in range(20)][-1]
     assert len(wts) == 4 and all(0.9 < v < 1.1 for v in wts)
+
+
+def test_vae_decoder_and_autoencoder_state_dict_keys():
+    """Decoder / AutoencoderKL parameter names and shapes = the reference's (oracle shape tables are asserted equal to
+    the reference classes' state dicts by tests/golden/make_golden_next.py); SDXL VAE: 108 + 140 tensors."""
+    from neurosis_b200.modules.vae import AutoencoderKL, Decoder
+    from oracle.vae import vae_decoder_param_shapes
+    dec = Decoder(**TINY_VAE, embed_dim=4, standalone=True)
+    shapes = vae_decoder_param_shapes(TINY_VAE, embed_dim=4, standalone=True)
+    sd = dec.state_dict()
+    assert set(sd) == set(shapes) and all(tuple(sd[k].shape) == tuple(shapes[k]) for k in sd)
+    sdxl_vae = dict(ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], in_channels=3,
+                    resolution=256, z_channels=4, double_z=True)
+    assert len(vae_param_shapes(sdxl_vae, 4, True)) == 108 and len(vae_decoder_param_shapes(sdxl_vae, 4, True)) == 140
+    ae = AutoencoderKL(4, TINY_VAE)
+    keys = set(ae.state_dict())
+    enc_keys = {("quant_conv." + k[len("quant_conv."):]) if k.startswith("quant_conv.") else "encoder." + k
+                for k in vae_param_shapes(TINY_VAE, 4, True)}
+    dec_keys = {("post_quant_conv." + k[len("post_quant_conv."):]) if k.startswith("post_quant_conv.") else "decoder." + k
+                for k in shapes}
+    assert keys == enc_keys | dec_keys
+    assert ae.regularization.sample is False and ae.get_last_layer() is ae.decoder.conv_out.weight
