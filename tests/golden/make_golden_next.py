@@ -74,7 +74,8 @@ out["vaetrain.grad.quant_conv.weight"] = enc.get_parameter("quant_conv.weight").
 out["vaetrain.grad.conv_in.weight"] = enc.get_parameter("conv_in.weight").grad.numpy()
 
 for extra in (HERE / "_golden_next_extra.py",      # rows 2-4
-              HERE / "_golden_next_families.py"):  # all shipped schedule / preconditioning / weighting variants
+              HERE / "_golden_next_families.py",   # all shipped schedule / preconditioning / weighting variants
+              HERE / "_golden_next_fullsize.py"):  # full-size SD1.5 / SDXL UNets through the reference
     if extra.exists():  # (separate files so each generator can be read on its own)
         exec(compile(extra.read_text(), str(extra), "exec"), {"out": out, "HERE": HERE, "np": np, "torch": torch,
                                                                "synth_tensor": synth_tensor,

@@ -145,3 +145,40 @@ def test_schedule_and_denoiser_families_bit_exact_vs_reference():
                                        "fam.disc.LegacyDDPMDiscretization.40.1=ValueError"]
     from neurosis_b200.modules.schedule import LegacyDDPMDiscretization
     assert LegacyDDPMDiscretization()(40).shape == (41,)
+
+
+# ---------------------------------------------------------------- the oracle at full size
+def _full_size_oracle_vs_reference(tag, cfg):
+    from common import fast_state_dict
+    from oracle.unet import unet_forward, unet_param_shapes
+    shapes = unet_param_shapes(cfg)
+    sd = {k: v.requires_grad_(True) for k, v in fast_state_dict(shapes, seed=3).items()}
+    x = synth_tensor(f"full.{tag}.x", (1, 4, 32, 32))
+    ctx = synth_tensor(f"full.{tag}.ctx", (1, 77, cfg["context_dim"]))
+    y = synth_tensor(f"full.{tag}.y", (1, cfg["adm_in_channels"])) if cfg.get("num_classes") else None
+    o = unet_forward(sd, cfg, x, torch.tensor([481]), ctx, y)
+    np.testing.assert_allclose(o.detach().numpy(), G[f"full.{tag}.out"], rtol=2e-4, atol=2e-4)
+    (o * synth_tensor(f"full.{tag}.g", (1, 4, 32, 32), scale=0.1)).sum().backward()
+    names = sorted(shapes)
+    l2 = np.array([sd[n].grad.norm().item() for n in names])
+    np.testing.assert_allclose(l2, G[f"full.{tag}.grad_l2"], rtol=1e-3, atol=1e-6)
+    return len(names)
+
+
+def test_oracle_full_size_sd15_vs_reference():
+    """the oracle restatement against the reference's own UNetModel at the FULL SD1.5 configuration (859.5 M
+    parameters, 686 tensors): output and every parameter's gradient norm."""
+    from common import FULL_SD15
+    assert _full_size_oracle_vs_reference("sd15", FULL_SD15) == 686
+
+
+def test_oracle_full_size_sdxl_vs_reference():
+    """same at the FULL SDXL configuration (2 567.5 M parameters, 1 680 tensors, transformer depth 10): this is the
+    oracle the GPU full-size test (tests/test_gpu_modules.py::test_full_size_unet_vs_oracle) compares against.
+    Needs ~25 GB of host memory for the fp32 weights and their gradients."""
+    import psutil
+    import pytest
+    if psutil.virtual_memory().available < 40e9:
+        pytest.skip("needs 40 GB of free host memory")
+    from common import FULL_SDXL
+    assert _full_size_oracle_vs_reference("sdxl", FULL_SDXL) == 1680
