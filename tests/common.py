@@ -32,6 +32,11 @@ FULL_SD15 = dict(in_channels=4, model_channels=320, out_channels=4, num_res_bloc
                  use_linear_in_transformer=False, spatial_transformer_attn_type="torch-sdp", use_checkpoint=False)
 
 
+# the KL-f8 VAE of configs/sdxl/sdxl.example.yaml:102-113
+FULL_VAE = dict(ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], in_channels=3,
+                resolution=256, z_channels=4, double_z=True)
+
+
 def fast_state_dict(shapes: dict, seed: int = 0) -> dict:
     """same distributions as oracle.weights.synth_state_dict, drawn with torch's generator (seconds instead of minutes for
     the 2.57 B-parameter SDXL UNet); only for tests where both sides load the SAME dict (no golden involved)."""

@@ -29,3 +29,31 @@ for tag, cfg in (("sd15", FULL_SD15), ("sdxl", FULL_SDXL)):
     print("full-size", tag, len(names), "tensors, out norm", float(o.norm()))
     del ref, o
     gc.collect()
+
+# ---- the full SDXL KL-f8 VAE (configs/sdxl/sdxl.example.yaml:102-113: ch 128, mult [1,2,4,4], 2 res blocks) ------
+from common import FULL_VAE
+from neurosis.modules.diffusion.model import Decoder as _RefDec
+from neurosis.modules.diffusion.model import Encoder as _RefEnc
+
+from oracle.vae import vae_decoder_param_shapes as _dshapes
+from oracle.vae import vae_param_shapes as _eshapes
+
+_es, _ds = _eshapes(FULL_VAE, 4, True), _dshapes(FULL_VAE, 4, True)
+_enc = _RefEnc(**FULL_VAE, embed_dim=4, standalone=True, attn_type="vanilla")
+_dec = _RefDec(**FULL_VAE, embed_dim=4, standalone=True, attn_type="vanilla")
+_enc.load_state_dict(fast_state_dict(_es, seed=11))
+_dec.load_state_dict(fast_state_dict(_ds, seed=12))
+img = synth_tensor("fullvae.img", (1, 3, 64, 64), uniform=True)
+eps = synth_tensor("fullvae.eps", (1, 4, 8, 8))
+m = _enc(img)  # moments (1, 8, 8, 8)
+mean, logvar = torch.chunk(m, 2, dim=1)
+z = mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * eps
+xrec = _dec(z)
+loss = torch.nn.functional.mse_loss(xrec, img)
+loss.backward()
+out["fullvae.moments"] = m.detach().numpy()
+out["fullvae.xrec"] = xrec.detach().numpy()
+out["fullvae.loss"] = np.array(loss.item())
+out["fullvae.enc_grad_l2"] = np.array([_enc.get_parameter(n).grad.norm().item() for n in sorted(_es)], dtype=np.float64)
+out["fullvae.dec_grad_l2"] = np.array([_dec.get_parameter(n).grad.norm().item() for n in sorted(_ds)], dtype=np.float64)
+print("full-size VAE", len(_es), "+", len(_ds), "tensors, loss", loss.item())

@@ -182,3 +182,25 @@ def test_oracle_full_size_sdxl_vs_reference():
         pytest.skip("needs 40 GB of free host memory")
     from common import FULL_SDXL
     assert _full_size_oracle_vs_reference("sdxl", FULL_SDXL) == 1680
+
+
+def test_oracle_full_size_vae_vs_reference():
+    """oracle encoder + sampled posterior + decoder + L2 at the full SDXL KL-f8 configuration (ch 128, mult [1,2,4,4];
+    108 + 140 tensors) against the reference's Encoder / Decoder: moments, reconstruction, loss, gradient norms."""
+    from common import FULL_VAE, fast_state_dict
+    from oracle.vae import vae_moments
+    es, ds = vae_param_shapes(FULL_VAE, 4, True), vae_decoder_param_shapes(FULL_VAE, 4, True)
+    esd = {k: v.requires_grad_(True) for k, v in fast_state_dict(es, seed=11).items()}
+    dsd = {k: v.requires_grad_(True) for k, v in fast_state_dict(ds, seed=12).items()}
+    img = synth_tensor("fullvae.img", (1, 3, 64, 64), uniform=True)
+    eps = synth_tensor("fullvae.eps", (1, 4, 8, 8))
+    with torch.no_grad():
+        np.testing.assert_allclose(vae_moments(esd, FULL_VAE, img).numpy(), G["fullvae.moments"], rtol=1e-4, atol=2e-5)
+    loss, _, xrec, _ = vae_train_loss(esd, dsd, FULL_VAE, img, eps)
+    np.testing.assert_allclose(xrec.detach().numpy(), G["fullvae.xrec"], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(loss.item(), G["fullvae.loss"], rtol=1e-5)
+    loss.backward()
+    np.testing.assert_allclose(np.array([esd[n].grad.norm().item() for n in sorted(es)]), G["fullvae.enc_grad_l2"],
+                               rtol=1e-3, atol=1e-9)
+    np.testing.assert_allclose(np.array([dsd[n].grad.norm().item() for n in sorted(ds)]), G["fullvae.dec_grad_l2"],
+                               rtol=1e-3, atol=1e-9)

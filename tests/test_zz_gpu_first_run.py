@@ -140,3 +140,39 @@ def test_weighted_l1_loss_fwd_bwd():
     lr_ = (Dr - T).abs().flatten(1).mean(1) * w
     lr_.backward(g)
     assert rel(loss, lr_) < 1e-5 and rel(D.grad, Dr.grad) < 1e-6
+
+
+@_first_run
+def test_full_size_vae_training_step_vs_reference_golden():
+    """AutoencoderKL at the FULL SDXL KL-f8 configuration (108 + 140 tensors; 512-channel mid attention, d = 512) on a
+    64x64 image: moments, reconstruction and loss against the reference's Encoder / Decoder (goldens), gradient norms
+    of both networks."""
+    from common import FULL_VAE, fast_state_dict
+    from oracle.vae import vae_decoder_param_shapes
+    from neurosis_b200.modules.vae import AutoencoderKL, DiagonalGaussianRegularizer
+    G = np.load(str(ROOT / "tests/golden/reference_golden_next.npz"))
+    es, ds = vae_param_shapes(FULL_VAE, 4, True), vae_decoder_param_shapes(FULL_VAE, 4, True)
+    full = {}
+    for k, v in fast_state_dict(es, seed=11).items():
+        full[k if k.startswith("quant_conv.") else "encoder." + k] = v
+    for k, v in fast_state_dict(ds, seed=12).items():
+        full[k if k.startswith("post_quant_conv.") else "decoder." + k] = v
+    ae = AutoencoderKL(4, FULL_VAE, regularizer=DiagonalGaussianRegularizer(sample=True))
+    ae.load_state_dict(full)
+    ae = ae.to(DEV)
+    img = synth_tensor("fullvae.img", (1, 3, 64, 64), uniform=True).to(DEV)
+    eps = synth_tensor("fullvae.eps", (1, 4, 8, 8)).to(DEV)
+    with torch.no_grad():
+        m = ae.encoder.moments(img, ae.quant_conv)
+    assert rel(m, G["fullvae.moments"]) < 3e-2
+    loss = ae.training_step({"image": img, "posterior_eps": eps})
+    np.testing.assert_allclose(float(loss.detach()), G["fullvae.loss"], rtol=1e-2)
+    loss.backward()
+    named = dict(ae.named_parameters())
+    enc_l2 = np.array([float(named[k if k.startswith("quant_conv.") else "encoder." + k].grad.norm()) for k in sorted(es)])
+    dec_l2 = np.array([float(named[k if k.startswith("post_quant_conv.") else "decoder." + k].grad.norm())
+                       for k in sorted(ds)])
+    keep_e = np.array([not k.endswith(".k.bias") for k in sorted(es)])  # mathematically zero gradient
+    keep_d = np.array([not k.endswith(".k.bias") for k in sorted(ds)])
+    assert np.allclose(enc_l2[keep_e], G["fullvae.enc_grad_l2"][keep_e], rtol=8e-2, atol=1e-7)
+    assert np.allclose(dec_l2[keep_d], G["fullvae.dec_grad_l2"][keep_d], rtol=8e-2, atol=1e-7)
