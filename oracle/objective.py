@@ -65,3 +65,21 @@ def diffusion_loss(network: Callable, table: Tensor, x: Tensor, cond: dict, sigm
     w = sigmas ** -2.0
     per = ((D.float() - x.float()) ** 2).flatten(1).mean(1)
     return per * w.float()
+
+
+def rf_comfy_loss(network: Callable, x: Tensor, cond: dict, sigmas: Tensor, noise: Tensor) -> Tensor:
+    """rectified-flow objective (loss.py:130-139) with a continuous `Denoiser` (denoiser.py:28-57, output mode "F"),
+    RectifiedFlowComfyPreconditioning (denoiser_preconditioning.py:93-105: c_in = (s^2 + (1-s)^2)^-1/2, c_noise = 1000 s)
+    and RectifiedFlowComfyWeighting (denoiser_weighting.py:58-75, float64): loss[b] = mean((F - noise)^2) * w(s)."""
+    sigmas = sigmas.to(x)
+    sb = sigmas[(...,) + (None,) * (x.ndim - 1)]
+    z = (1.0 - sb) * x + sb * noise
+    c_in = (sb ** 2.0 + (1.0 - sb) ** 2.0) ** -0.5
+    c_noise = (1000.0 * sb).reshape(sigmas.shape)
+    F_out = network(z * c_in.to(z.dtype), c_noise, cond)
+    t = sigmas.to(torch.float64)
+    half_pi = torch.acos(torch.zeros(1, dtype=torch.float64))[0]
+    w = (1 / (1 - t) ** 2) * ((1 / (1.0 * (4.0 * half_pi) ** 0.5)) * (1 / (t * (1.0 - t)))
+                              * torch.exp(-0.5 * (torch.log(t / (1 - t)) - 0.0) ** 2 / 1.0 ** 2))
+    per = ((F_out.float() - noise.float()) ** 2).flatten(1).mean(1)
+    return per * w.float()

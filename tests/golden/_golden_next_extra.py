@@ -52,3 +52,46 @@ emb = ConcatTimestepEmbedderND(256)
 sizes = torch.tensor([[1024.0, 1024.0], [1152.0, 896.0], [832.0, 1216.0], [0.0, 64.0]])
 out["cond.sizes"] = sizes.numpy()
 out["cond.fourier"] = emb(sizes).numpy()
+
+# ---- §8(a) rows 4-6 with the rectified-flow objective (loss.py:130-139: z_t = (1-s) x + s n, target = noise, "F" output)
+from neurosis.modules.diffusion import OpenAIWrapper, StandardDiffusionLoss, UNetModel
+from neurosis.modules.diffusion.denoiser import Denoiser as _Denoiser
+from neurosis.modules.diffusion.denoiser_preconditioning import RectifiedFlowComfyPreconditioning
+from neurosis.modules.diffusion.denoiser_weighting import RectifiedFlowComfyWeighting
+
+from common import TINY_SDXL
+from oracle.unet import unet_param_shapes as _ushapes
+
+_cfg = TINY_SDXL
+_sd = synth_state_dict(_ushapes(_cfg), seed=1)
+_ref = UNetModel(**_cfg)
+_ref.load_state_dict(_sd)
+_sig = torch.tensor([0.3, 0.8])
+
+
+class _Fixed:
+    def __call__(self, n, t=None):
+        return _sig
+
+
+class _Cond(torch.nn.Module):
+    def forward(self, batch):
+        return {"crossattn": batch["ctx"], "vector": batch["vec"]}
+
+
+_lat, _noise = synth_tensor("step.latent", (2, 4, 16, 16)), synth_tensor("step.noise", (2, 4, 16, 16))
+_loss_fn = StandardDiffusionLoss(sigma_generator=_Fixed(), loss_weighting=RectifiedFlowComfyWeighting(),
+                                 objective_type="rf")
+_orig_rl = torch.randn_like
+torch.randn_like = lambda t_, **kw: _noise.to(t_)
+try:
+    _loss = _loss_fn(OpenAIWrapper(_ref), _Denoiser(RectifiedFlowComfyPreconditioning()), _Cond(), _lat,
+                     {"ctx": synth_tensor("sdxl.ctx", (2, 77, _cfg["context_dim"])),
+                      "vec": synth_tensor("sdxl.y", (2, _cfg["adm_in_channels"]))})
+finally:
+    torch.randn_like = _orig_rl
+_loss.mean().backward()
+out["rf.sigmas"] = _sig.numpy()
+out["rf.loss"] = _loss.detach().double().numpy()
+out["rf.grad.out.2.weight"] = _ref.get_parameter("out.2.weight").grad.numpy()
+out["rf.grad_l2"] = np.array([_ref.get_parameter(n).grad.norm().item() for n in sorted(_sd)], dtype=np.float64)

@@ -204,3 +204,23 @@ def test_oracle_full_size_vae_vs_reference():
                                rtol=1e-3, atol=1e-9)
     np.testing.assert_allclose(np.array([dsd[n].grad.norm().item() for n in sorted(ds)]), G["fullvae.dec_grad_l2"],
                                rtol=1e-3, atol=1e-9)
+
+
+def test_rectified_flow_objective_oracle_vs_reference():
+    """StandardDiffusionLoss(objective_type="rf") through a continuous Denoiser with the Comfy preconditioning /
+    weighting: per-sample loss and every gradient norm of the miniature SDXL UNet against the reference."""
+    from common import TINY_SDXL
+    from oracle import objective as O
+    from oracle.unet import unet_forward, unet_param_shapes
+    cfg = TINY_SDXL
+    sd = {k: v.requires_grad_(True) for k, v in synth_state_dict(unet_param_shapes(cfg), seed=1).items()}
+    lat, noise = synth_tensor("step.latent", (2, 4, 16, 16)), synth_tensor("step.noise", (2, 4, 16, 16))
+    cond = {"crossattn": synth_tensor("sdxl.ctx", (2, 77, cfg["context_dim"])),
+            "vector": synth_tensor("sdxl.y", (2, cfg["adm_in_channels"]))}
+    net = lambda x, t, c: unet_forward(sd, cfg, x, t, c["crossattn"], c["vector"])  # noqa: E731
+    loss = O.rf_comfy_loss(net, lat, cond, torch.from_numpy(G["rf.sigmas"]), noise)
+    np.testing.assert_allclose(loss.detach().numpy(), G["rf.loss"], rtol=1e-4)
+    loss.mean().backward()
+    np.testing.assert_allclose(sd["out.2.weight"].grad.numpy(), G["rf.grad.out.2.weight"], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(np.array([sd[n].grad.norm().item() for n in sorted(sd)]), G["rf.grad_l2"], rtol=5e-4,
+                               atol=1e-7)

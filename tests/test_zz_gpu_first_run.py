@@ -176,3 +176,36 @@ def test_full_size_vae_training_step_vs_reference_golden():
     keep_d = np.array([not k.endswith(".k.bias") for k in sorted(ds)])
     assert np.allclose(enc_l2[keep_e], G["fullvae.enc_grad_l2"][keep_e], rtol=8e-2, atol=1e-7)
     assert np.allclose(dec_l2[keep_d], G["fullvae.dec_grad_l2"][keep_d], rtol=8e-2, atol=1e-7)
+
+
+@_first_run
+def test_rectified_flow_objective_vs_reference_golden():
+    """StandardDiffusionLoss(objective_type="rf") + continuous Denoiser(RectifiedFlowComfyPreconditioning) +
+    RectifiedFlowComfyWeighting on the CUDA modules: bf16 step loss within 1e-2 of the reference's fp32 value, gradient
+    norms of every parameter (non-integer timesteps 300.0 / 800.0 through the sinusoidal-embedding kernel)."""
+    from common import TINY_SDXL
+    from test_gpu_modules import build_unet
+    from neurosis_b200.modules.denoiser import Denoiser, RectifiedFlowComfyPreconditioning, RectifiedFlowComfyWeighting
+    from neurosis_b200.modules.loss import OpenAIWrapper, StandardDiffusionLoss
+    G = np.load(str(ROOT / "tests/golden/reference_golden_next.npz"))
+    cfg = TINY_SDXL
+    m = build_unet(cfg)
+    sig = torch.from_numpy(G["rf.sigmas"])
+
+    class Fixed:
+        def __call__(self, n, t=None):
+            return sig
+
+    loss_fn = StandardDiffusionLoss(sigma_generator=Fixed(), loss_weighting=RectifiedFlowComfyWeighting(),
+                                    objective_type="rf")
+    lat = synth_tensor("step.latent", (2, 4, 16, 16)).to(DEV)
+    noise = synth_tensor("step.noise", (2, 4, 16, 16)).to(DEV)
+    cond = {"crossattn": synth_tensor("sdxl.ctx", (2, 77, cfg["context_dim"])).to(DEV),
+            "vector": synth_tensor("sdxl.y", (2, cfg["adm_in_channels"])).to(DEV)}
+    loss = loss_fn._forward(OpenAIWrapper(m), Denoiser(RectifiedFlowComfyPreconditioning()), cond, lat, {}, noise=noise)
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), G["rf.loss"], rtol=1e-2)
+    loss.mean().backward()
+    assert rel(m.out[2].weight.grad, G["rf.grad.out.2.weight"]) < 3e-2
+    names = sorted(n for n, _ in m.named_parameters())
+    l2 = np.array([float(dict(m.named_parameters())[n].grad.norm()) for n in names])
+    assert np.allclose(l2, G["rf.grad_l2"], rtol=6e-2, atol=1e-5)
