@@ -95,3 +95,14 @@ out["rf.sigmas"] = _sig.numpy()
 out["rf.loss"] = _loss.detach().double().numpy()
 out["rf.grad.out.2.weight"] = _ref.get_parameter("out.2.weight").grad.numpy()
 out["rf.grad_l2"] = np.array([_ref.get_parameter(n).grad.norm().item() for n in sorted(_sd)], dtype=np.float64)
+
+# ---- aspect-bucket (non-square) latents through the reference UNet: pins the oracle on the shapes the GPU test
+# tests/test_gpu_modules.py::test_unet_aspect_bucket_shapes_vs_oracle uses -----------------------------------------
+for _h, _w in ((24, 16), (12, 20)):
+    _ref.zero_grad()
+    _o = _ref(synth_tensor("bucket.x", (2, 4, _h, _w)), torch.tensor([3, 977]),
+              synth_tensor("bucket.ctx", (2, 77, _cfg["context_dim"])), synth_tensor("bucket.y", (2, _cfg["adm_in_channels"])))
+    (_o * synth_tensor("bucket.gout", (2, 4, _h, _w), scale=0.1)).sum().backward()
+    out[f"bucket.{_h}x{_w}.out"] = _o.detach().numpy()
+    out[f"bucket.{_h}x{_w}.grad_l2"] = np.array([_ref.get_parameter(n).grad.norm().item() for n in sorted(_sd)],
+                                                 dtype=np.float64)

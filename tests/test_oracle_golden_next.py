@@ -224,3 +224,19 @@ def test_rectified_flow_objective_oracle_vs_reference():
     np.testing.assert_allclose(sd["out.2.weight"].grad.numpy(), G["rf.grad.out.2.weight"], rtol=1e-3, atol=1e-5)
     np.testing.assert_allclose(np.array([sd[n].grad.norm().item() for n in sorted(sd)]), G["rf.grad_l2"], rtol=5e-4,
                                atol=1e-7)
+
+
+def test_oracle_aspect_bucket_shapes_vs_reference():
+    """non-square latents (aspect buckets): the oracle against the reference UNet on the shapes of the GPU bucket test."""
+    from common import TINY_SDXL
+    from oracle.unet import unet_forward, unet_param_shapes
+    cfg = TINY_SDXL
+    for h, w in ((24, 16), (12, 20)):
+        sd = {k: v.requires_grad_(True) for k, v in synth_state_dict(unet_param_shapes(cfg), seed=1).items()}
+        o = unet_forward(sd, cfg, synth_tensor("bucket.x", (2, 4, h, w)), torch.tensor([3, 977]),
+                         synth_tensor("bucket.ctx", (2, 77, cfg["context_dim"])),
+                         synth_tensor("bucket.y", (2, cfg["adm_in_channels"])))
+        np.testing.assert_allclose(o.detach().numpy(), G[f"bucket.{h}x{w}.out"], rtol=1e-4, atol=2e-5)
+        (o * synth_tensor("bucket.gout", (2, 4, h, w), scale=0.1)).sum().backward()
+        np.testing.assert_allclose(np.array([sd[n].grad.norm().item() for n in sorted(sd)]),
+                                   G[f"bucket.{h}x{w}.grad_l2"], rtol=2e-4, atol=1e-6)
