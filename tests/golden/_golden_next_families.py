@@ -56,3 +56,16 @@ for name, cls in _classes(_S, _S.SigmaGenerator):
         FAM_ERRORS[f"fam.gen.{name}"] = type(e).__name__
 out["fam.errors"] = np.array(sorted(f"{k}={v}" for k, v in FAM_ERRORS.items()))
 print("family goldens:", sum(1 for k in out if k.startswith("fam.")), "arrays; reference errors:", FAM_ERRORS)
+
+# ---- DiscreteDenoiser option combinations (denoiser.py:60-97): quantised sigma and the c_noise the UNet receives ----
+from neurosis.modules.diffusion.denoiser import DiscreteDenoiser as _DD
+
+for _q in (True, False):
+    for _flip in (False, True):
+        for _pname in ("EpsPreconditioning", "VPreconditioning"):
+            _den = _DD(getattr(_P, _pname)(), 1000, _D.LegacyDDPMDiscretization(), quantize_c_noise=_q, flip=_flip)
+            _den.sigmas, _den.log_sigmas = _den.sigmas.detach(), _den.log_sigmas.detach()
+            _s = _den.possibly_quantize_sigma(sig)
+            _cn = _den.possibly_quantize_c_noise(_den.preconditioning(_s)[3])
+            out[f"fam.dd.{_pname}.{int(_q)}.{int(_flip)}.sigma"] = _s.double().numpy()
+            out[f"fam.dd.{_pname}.{int(_q)}.{int(_flip)}.c_noise"] = _cn.double().numpy()

@@ -104,7 +104,27 @@ def test_ema_oracle_vs_reference():
 
 # ---------------------------------------------------------------- §8(a) rows 6-8: every shipped variant, bit-exact
 def _family_cases():
-    return [k for k in G.files if k.startswith("fam.") and k not in ("fam.sigma", "fam.sigma01", "fam.t", "fam.errors")]
+    return [k for k in G.files if k.startswith("fam.") and not k.startswith("fam.dd.")
+            and k not in ("fam.sigma", "fam.sigma01", "fam.t", "fam.errors")]
+
+
+def test_discrete_denoiser_option_combinations_bit_exact():
+    """DiscreteDenoiser with quantize_c_noise on/off, flip on/off, Eps / V preconditioning (denoiser.py:60-97): the
+    quantised sigma and the c_noise handed to the UNet (an int64 table index, or the continuous value) are bit-exact."""
+    from neurosis_b200.modules import denoiser as D
+    from neurosis_b200.modules.schedule import LegacyDDPMDiscretization
+    sig = torch.from_numpy(G["fam.sigma"])
+    keys = [k for k in G.files if k.startswith("fam.dd.") and k.endswith(".sigma")]
+    assert len(keys) == 8
+    for key in keys:
+        _, _, pname, q, flip, _ = key.split(".")
+        den = D.DiscreteDenoiser(getattr(D, pname)(), 1000, LegacyDDPMDiscretization(), quantize_c_noise=bool(int(q)),
+                                 flip=bool(int(flip)))
+        s = den.possibly_quantize_sigma(sig)
+        cn = den.possibly_quantize_c_noise(den.preconditioning(s)[3])
+        assert np.array_equal(s.double().numpy(), G[key]), key
+        assert np.array_equal(cn.double().numpy(), G[key[: -len("sigma")] + "c_noise"]), key
+        assert cn.dtype == (torch.int64 if int(q) else torch.float32)
 
 
 def test_schedule_and_denoiser_families_bit_exact_vs_reference():
