@@ -106,3 +106,23 @@ for _h, _w in ((24, 16), (12, 20)):
     out[f"bucket.{_h}x{_w}.out"] = _o.detach().numpy()
     out[f"bucket.{_h}x{_w}.grad_l2"] = np.array([_ref.get_parameter(n).grad.norm().item() for n in sorted(_sd)],
                                                  dtype=np.float64)
+
+# ---- row 3: GeneralConditioner assembly with per-sample UCG masks (embedding.py:90-149), fixed torch seed ---------
+from neurosis.modules.encoders.embedding import GeneralConditioner as _GC
+from neurosis.modules.encoders.misc import IdentityEncoder as _IdE
+
+_gc = _GC([_IdE(input_key="ctx"), _IdE(input_key="pooled", ucg_rate=0.3),
+           ConcatTimestepEmbedderND(256, input_key="original_size_as_tuple"),
+           ConcatTimestepEmbedderND(256, input_key="crop_coords_top_left", ucg_rate=0.5),
+           ConcatTimestepEmbedderND(256, input_key="target_size_as_tuple")])
+_gb = {"image": torch.zeros(6, 3, 8, 8), "ctx": synth_tensor("gc.ctx", (6, 77, 32)),
+       "pooled": synth_tensor("gc.pooled", (6, 48)),
+       "original_size_as_tuple": [(1024, 1024), (1152, 896), (832, 1216), (1024, 1024), (640, 1536), (512, 512)],
+       "crop_coords_top_left": [(0, 0), (16, 0), (0, 32), (8, 8), (0, 0), (64, 64)],
+       "target_size_as_tuple": [(1024, 1024), (896, 1152), (1216, 832), (1024, 1024), (1536, 640), (512, 512)]}
+torch.manual_seed(1234)
+_go = _gc(_gb)
+out["gc.vector"], out["gc.crossattn"] = _go["vector"].numpy(), _go["crossattn"].numpy()
+torch.manual_seed(1234)
+_go = _gc(_gb, force_zero_embeddings=["pooled", "target_size_as_tuple"])
+out["gc.vector_force_zero"] = _go["vector"].numpy()

@@ -260,3 +260,28 @@ def test_oracle_aspect_bucket_shapes_vs_reference():
         (o * synth_tensor("bucket.gout", (2, 4, h, w), scale=0.1)).sum().backward()
         np.testing.assert_allclose(np.array([sd[n].grad.norm().item() for n in sorted(sd)]),
                                    G[f"bucket.{h}x{w}.grad_l2"], rtol=2e-4, atol=1e-6)
+
+
+def test_general_conditioner_assembly_and_ucg_masks_vs_reference():
+    """GeneralConditioner (embedding.py:90-149) on a loader-style batch (per-sample size / crop tuples): concat order,
+    Fourier features, per-sample UCG dropout masks (same torch RNG consumption under a fixed seed) and
+    force_zero_embeddings — the drop-in's host path returns the reference's bits."""
+    from neurosis_b200.modules.conditioner import ConcatTimestepEmbedderND, GeneralConditioner, IdentityEncoder
+    gc = GeneralConditioner([IdentityEncoder(input_key="ctx"), IdentityEncoder(input_key="pooled", ucg_rate=0.3),
+                             ConcatTimestepEmbedderND(256, input_key="original_size_as_tuple"),
+                             ConcatTimestepEmbedderND(256, input_key="crop_coords_top_left", ucg_rate=0.5),
+                             ConcatTimestepEmbedderND(256, input_key="target_size_as_tuple")])
+    batch = {"image": torch.zeros(6, 3, 8, 8), "ctx": synth_tensor("gc.ctx", (6, 77, 32)),
+             "pooled": synth_tensor("gc.pooled", (6, 48)),
+             "original_size_as_tuple": [(1024, 1024), (1152, 896), (832, 1216), (1024, 1024), (640, 1536), (512, 512)],
+             "crop_coords_top_left": [(0, 0), (16, 0), (0, 32), (8, 8), (0, 0), (64, 64)],
+             "target_size_as_tuple": [(1024, 1024), (896, 1152), (1216, 832), (1024, 1024), (1536, 640), (512, 512)]}
+    torch.manual_seed(1234)
+    out = gc(batch)
+    assert np.array_equal(out["crossattn"].numpy(), G["gc.crossattn"])
+    assert out["vector"].shape == G["gc.vector"].shape == (6, 48 + 3 * 512)
+    assert np.array_equal(out["vector"].numpy(), G["gc.vector"])
+    assert 0 < int((G["gc.vector"][:, :48] == 0).all(1).sum()) + int((G["gc.vector"][:, 560:1072] == 0).all(1).sum())
+    torch.manual_seed(1234)
+    z = gc(batch, force_zero_embeddings=["pooled", "target_size_as_tuple"])
+    assert np.array_equal(z["vector"].numpy(), G["gc.vector_force_zero"])
