@@ -16,7 +16,7 @@ from oracle.vae import vae_param_shapes
 from oracle.weights import synth_state_dict, synth_tensor
 from test_gpu_next import DEV, _opt_params, rel, rnd
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
 
 
 # ---------------------------------------------------------------- optimizer / EMA inside the captured step (opt-in)
@@ -26,8 +26,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 _first_run = pytest.mark.xfail(strict=False, reason="opt-in graph path, first GPU run happens after the round's budget")
 
 
-@_first_run
-def test_device_side_step_scalars_match_host_side():
+def test_device_side_step_scalars_match_host_side():  # seen green on a B200 (profiles/r01_pytest_gpu_first_run.log)
     """`graph_launch` (step count and hyper-parameters derived on the device) == `step` (host scalars), and the EMA
     decay warm-up from the device counter == the host expression."""
     from neurosis_b200.optim import Adafactor, LitEma
