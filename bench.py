@@ -201,6 +201,9 @@ def main() -> None:
                     help="opt-in: put the fused Adafactor step (configs/sdxl/sdxl.example.yaml:158-164) inside the timed "
                          "step; the default measures the hot path BASELINE.json names (encode + loss + backward + all-reduce)")
     ap.add_argument("--ema", action="store_true", help="opt-in: LitEma update of the UNet after the optimizer step")
+    ap.add_argument("--shard-optimizer", action="store_true",
+                    help="opt-in (with --optimizer, N > 1): gradients are reduced to a per-bucket owner rank, the owner "
+                         "updates its parameters, updated parameters are broadcast (ddp.ShardedOptimizerReducer)")
     ap.add_argument("--breakdown", default="", help="write a per-call-site breakdown of tensor-core time to this file")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
     ap.add_argument("--ncu-step", action="store_true",
@@ -232,7 +235,11 @@ def main() -> None:
     B = args.batch
     eng = build_engine(dev)
     params = [p for p in eng.model.parameters() if p.requires_grad]
-    reducer = BucketedGradReducer(params, bucket_mb=256.0)
+    if args.shard_optimizer and args.optimizer != "none":
+        from neurosis_b200.ddp import ShardedOptimizerReducer
+        reducer = ShardedOptimizerReducer(params, bucket_mb=256.0)
+    else:
+        reducer = BucketedGradReducer(params, bucket_mb=256.0)
     reducer.attach_as_grad_sink()  # wgrad kernels accumulate straight into the gradient buckets
 
     g = torch.Generator().manual_seed(42 + rank)  # per-rank data
@@ -245,7 +252,8 @@ def main() -> None:
     optimizer = ema = None
     if args.optimizer == "adafactor":
         from neurosis_b200.optim import Adafactor
-        optimizer = Adafactor(params, scale_parameter=True, relative_step=True, warmup_init=True)
+        opt_params = reducer.owned_params() if hasattr(reducer, "owned_params") else params
+        optimizer = Adafactor(opt_params, scale_parameter=True, relative_step=True, warmup_init=True)
     if args.ema:
         from neurosis_b200.optim import LitEma
         ema = LitEma(eng.model, decay=0.9999)
@@ -258,6 +266,8 @@ def main() -> None:
         reducer.finish()
         if optimizer is not None:
             optimizer.step()
+            if hasattr(reducer, "broadcast_params"):
+                reducer.broadcast_params()
         if ema is not None:
             ema(eng.model)
         return loss.item() if read_loss else 0.0
@@ -414,7 +424,7 @@ def main() -> None:
                                               "not in the timed step (north_star path = encode + loss + backward + "
                                               "all-reduce); the fused Adafactor step over the same 2.57 G parameters "
                                               "measures 15.0 ms, LitEma 5.0 ms (profiles/r01_next_rows_bench.log)"),
-                           "ema": ema is not None,
+                           "ema": ema is not None, "optimizer_sharded": hasattr(reducer, "owned_params"),
                            "parallelism": f"dp{world}", "l2": "working set (5 GB bf16 weights + activations) >> 126 MB L2",
                            "step_tflop_algorithmic": GFLOP_STEP * B / 1e3,
                            "mfu_vs_peak": ips / world * GFLOP_STEP * 1e9 / (pk["tflops"] * 1e12)},

@@ -146,3 +146,82 @@ class BucketedGradReducer:
                 reducer.enabled = True
 
         return _Ctx()
+
+
+class ShardedOptimizerReducer(BucketedGradReducer):
+    """Optimizer-state sharding over the data-parallel ranks (ZeRO-1 style) on top of the bucketed reducer — the
+    multi-GPU form of SURVEY.md §8(f) row 2 ("optimizer step fused with the all-reduce epilogue").
+
+    An all-reduce is a reduce-scatter followed by an all-gather; here the optimizer step sits between the two halves:
+
+      * every bucket has an OWNER rank (round-robin); its gradients are reduced (averaged) TO the owner only —
+        `reduce` instead of `all_reduce`, launched per completed bucket on the side stream during backward as before;
+      * parameters live in per-bucket flat fp32 buffers (each `nn.Parameter` is re-homed as a view; names, shapes and
+        state dicts are unchanged), and each rank builds its optimizer over `owned_params()` only: optimizer compute
+        and optimizer state (Adafactor moments, Adam m/v, EMA shadows) shrink by the world size;
+      * after `optimizer.step()` the owner broadcasts the updated flat parameter buffer (`broadcast_params()`).
+
+    Bytes on the wire equal the all-reduce's (reduce + broadcast of every bucket); over NVSwitch every GPU has full
+    bandwidth to every peer, so the round-robin owners' transfers proceed concurrently.  Adafactor's factored
+    statistics need whole tensors, which is why ownership is per bucket of whole parameters and not per element range.
+    Works with NCCL (CUDA) and gloo (CPU; the world_size-2 test)."""
+
+    def __init__(self, params: Iterable[nn.Parameter], bucket_mb: float = 256.0,
+                 process_group: Optional[dist.ProcessGroup] = None):
+        super().__init__(params, bucket_mb, process_group)
+        self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        for bi, b in enumerate(self.buckets):
+            b["owner"] = bi % self.world
+            pflat = torch.empty_like(b["flat"])
+            off = 0
+            with torch.no_grad():
+                for p in b["params"]:
+                    n = p.numel()
+                    pflat[off: off + n].copy_(p.detach().reshape(-1))
+                    p.data = pflat[off: off + n].view_as(p)  # same Parameter object, storage re-homed
+                    off += n
+            b["pflat"] = pflat
+        self._bworks: list = []
+
+    def owned_params(self) -> list:
+        """parameters whose gradients are reduced to this rank: build the optimizer (and EMA) over these."""
+        return [p for b in self.buckets if b["owner"] == self.rank for p in b["params"]]
+
+    def _launch(self, b: dict) -> None:
+        flat, owner = b["flat"], b["owner"]
+        dst = dist.get_global_rank(self.group, owner) if self.group is not None else owner
+        if self._cuda:
+            ev = torch.cuda.current_stream().record_event()
+            with torch.cuda.stream(self._stream):
+                self._stream.wait_event(ev)
+                dist.reduce(flat, dst=dst, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            w = dist.reduce(flat, dst=dst, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._works.append((w, flat))
+
+    def broadcast_params(self) -> None:
+        """after the owners' optimizer steps: every rank receives every bucket's updated parameters.  CUDA: enqueued on
+        the side stream behind the optimizer kernels, the compute stream waits for all of them."""
+        if self.world == 1:
+            return
+        changed = []
+        if self._cuda:
+            ev = torch.cuda.current_stream().record_event()
+            with torch.cuda.stream(self._stream):
+                self._stream.wait_event(ev)
+                for b in self.buckets:
+                    src = dist.get_global_rank(self.group, b["owner"]) if self.group is not None else b["owner"]
+                    dist.broadcast(b["pflat"], src=src, group=self.group)
+            torch.cuda.current_stream().wait_stream(self._stream)
+            for b in self.buckets:
+                if b["owner"] != self.rank:
+                    changed.extend((p, False) for p in b["params"])
+            from . import ops
+            ops.parameters_updated_in_place(changed)  # raw writes into parameter storage: bump the version counters
+        else:
+            works = []
+            for b in self.buckets:
+                src = dist.get_global_rank(self.group, b["owner"]) if self.group is not None else b["owner"]
+                works.append(dist.broadcast(b["pflat"], src=src, group=self.group, async_op=True))
+            for w in works:
+                w.wait()

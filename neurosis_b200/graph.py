@@ -80,6 +80,8 @@ class GraphedTrainStep:
         self.loss.copy_(total.detach())
         if self._opt_ready:  # (the eager warm-up steps before the tables exist leave the parameters untouched)
             self.optimizer.graph_launch()
+            if hasattr(self.reducer, "broadcast_params"):  # ShardedOptimizerReducer: owners publish their updates
+                self.reducer.broadcast_params()
         if self._ema_ready:
             self.ema.graph_launch()
 

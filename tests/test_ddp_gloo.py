@@ -68,3 +68,66 @@ def test_reducer_matches_single_process():
     (sum(m(data[i:i + 2]).pow(2).mean() for i in (0, 2, 4, 6)) / 2).backward()  # two micro-steps per rank, averaged over ranks
     for got, p in zip(g2, m.parameters()):
         assert torch.allclose(torch.from_numpy(got), p.grad, rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# optimizer-state sharding (ZeRO-1 style): reduce to the bucket owner -> owner's optimizer step -> broadcast
+# ---------------------------------------------------------------------------------------------------------------
+def _sharded_worker(rank: int, world: int, port: int, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from neurosis_b200.ddp import ShardedOptimizerReducer
+    m = _model()
+    names = [n for n, _ in m.named_parameters()]
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    red = ShardedOptimizerReducer(m.parameters(), bucket_mb=0.004)
+    assert len(red.buckets) >= 3
+    assert all(torch.equal(before[n], p.detach()) for n, p in m.named_parameters()), "re-homing keeps the values"
+    assert [n for n, _ in m.named_parameters()] == names and set(m.state_dict()) == set(before)
+    owned = red.owned_params()
+    assert 0 < len(owned) < len(names), "each rank owns a strict subset"
+    opt = torch.optim.Adam(owned, lr=1e-2)  # optimizer state only for the owned parameters
+    torch.manual_seed(123)
+    data = torch.randn(3, 8, 16)
+    for step in range(3):
+        red.zero_grad()
+        m(data[step, rank * 4:(rank + 1) * 4]).pow(2).mean().backward()
+        red.finish()
+        opt.step()
+        red.broadcast_params()
+    n_state = sum(len(opt.state[p]) > 0 for p in owned)
+    q.put((rank, {n: p.detach().numpy().copy() for n, p in m.named_parameters()}, len(owned), n_state))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_optimizer_matches_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict()
+    owned_total = 0
+    for _ in range(2):
+        rank, params, n_owned, n_state = q.get(timeout=120)
+        got[rank] = params
+        owned_total += n_owned
+        assert n_state == n_owned
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m = _model()
+    assert owned_total == len(list(m.parameters())), "every parameter has exactly one owner"
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+    torch.manual_seed(123)
+    data = torch.randn(3, 8, 16)
+    for step in range(3):
+        opt.zero_grad()
+        m(data[step]).pow(2).mean().backward()  # mean over the concatenated batch == mean of the two rank means
+        opt.step()
+    for n, p in m.named_parameters():
+        for rank in (0, 1):
+            assert torch.allclose(torch.from_numpy(got[rank][n]), p.detach(), rtol=1e-5, atol=1e-6), (rank, n)
