@@ -88,6 +88,18 @@ class Adafactor(Optimizer):
         self._plan = None
         self._key = None
 
+    def load_state_dict(self, state_dict) -> None:
+        """resume: the loaded moment tensors are new objects, so the device table (which holds raw pointers to the
+        state) is rebuilt on the next step."""
+        super().load_state_dict(state_dict)
+        self._plan = None
+        self._key = None
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """zero IN PLACE by default (torch's default drops the tensors): stable gradient storage keeps the device
+        table valid from step to step — with `BucketedGradReducer` the gradients are views of its buckets anyway."""
+        super().zero_grad(set_to_none=set_to_none)
+
     # ---- reference helpers (host scalars) ------------------------------------------------------
     @staticmethod
     def _rel_step(group: dict, step: int) -> float:
