@@ -126,3 +126,33 @@ out["gc.vector"], out["gc.crossattn"] = _go["vector"].numpy(), _go["crossattn"].
 torch.manual_seed(1234)
 _go = _gc(_gb, force_zero_embeddings=["pooled", "target_size_as_tuple"])
 out["gc.vector_force_zero"] = _go["vector"].numpy()
+
+# ---- StandardDiffusionLoss(loss_type="l1") (loss.py:89-93, losses/functions.py:65-78), edm objective, Eps weighting ----
+from neurosis.modules.diffusion import DiscreteDenoiser as _DDen
+from neurosis.modules.diffusion import EpsPreconditioning as _EpsP
+from neurosis.modules.diffusion import EpsWeighting as _EpsW
+from neurosis.modules.diffusion import LegacyDDPMDiscretization as _LD
+
+_den = _DDen(_EpsP(), 1000, _LD())
+_den.sigmas, _den.log_sigmas = _den.sigmas.detach(), _den.log_sigmas.detach()
+_sig1 = _den.sigmas[torch.tensor([800, 300])].clone()  # descending table: [800] small sigma, [300] large
+
+
+class _Fixed1:
+    def __call__(self, n, t=None):
+        return _sig1
+
+
+_ref.zero_grad()
+_l1 = StandardDiffusionLoss(sigma_generator=_Fixed1(), loss_weighting=_EpsW(), loss_type="l1")
+torch.randn_like = lambda t_, **kw: _noise.to(t_)
+try:
+    _loss1 = _l1(OpenAIWrapper(_ref), _den, _Cond(), _lat,
+                 {"ctx": synth_tensor("sdxl.ctx", (2, 77, _cfg["context_dim"])),
+                  "vec": synth_tensor("sdxl.y", (2, _cfg["adm_in_channels"]))})
+finally:
+    torch.randn_like = _orig_rl
+_loss1.mean().backward()
+out["l1.sigmas"] = _sig1.numpy()
+out["l1.loss"] = _loss1.detach().double().numpy()
+out["l1.grad_l2"] = np.array([_ref.get_parameter(n).grad.norm().item() for n in sorted(_sd)], dtype=np.float64)
