@@ -120,7 +120,9 @@ class BucketedGradReducer:
         if self._cuda:
             from . import ops
             ops.join_side_streams()  # weight gradients computed on the side stream (marks their parameters ready)
-        if self.world == 1:
+        if self.world == 1 or not self.enabled:
+            # inside no_sync(): a gradient-accumulation micro-step only joins the side streams (mark_ready is a no-op
+            # while disabled), nothing is communicated and the buckets keep accumulating
             return
         for b in self.buckets:  # parameters that received no gradient this step still take part
             if b["pending"] > 0:
@@ -143,7 +145,12 @@ class BucketedGradReducer:
                 reducer.enabled = False
 
             def __exit__(self, *a):
+                if reducer._cuda:
+                    from . import ops
+                    ops.join_side_streams()  # retire side-stream jobs while mark_ready is still a no-op
                 reducer.enabled = True
+                for b in reducer.buckets:  # the boundary micro-step counts every parameter again
+                    b["pending"] = len(b["params"])
 
         return _Ctx()
 

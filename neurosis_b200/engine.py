@@ -103,7 +103,11 @@ class DiffusionEngine(nn.Module):
 
     def training_step(self, batch: dict, batch_idx: int = 0) -> Tensor:
         for hook in self.forward_hooks:
-            batch = hook.pre_hook(None, self, batch, batch_idx)
+            # the reference ignores pre_hook's return value (models/diffusion.py:209-210, hooks mutate the batch in
+            # place); a hook that returns a new dict is honoured, one that returns None keeps the batch
+            new_batch = hook.pre_hook(None, self, batch, batch_idx)
+            if new_batch is not None:
+                batch = new_batch
         x = self.get_input(batch)
         if self.first_stage_model is not None:
             x = self.encode_first_stage(x)

@@ -30,6 +30,11 @@ class GraphedTrainStep:
                  vector: Optional[Tensor], warmup: int = 3, optimizer=None, ema=None):
         self.engine, self.reducer = engine, reducer
         self.optimizer, self.ema = optimizer, ema
+        if getattr(engine.loss_fn, "noise_offset", 0.0):
+            # apply_noise_offset draws its chance on the host and its offset with CPU torch.randn (loss.py): captured,
+            # both would be frozen into the graph and every replay would reuse the same offset
+            raise NotImplementedError("GraphedTrainStep: loss_fn.noise_offset > 0 is a per-step host-side random draw "
+                                      "and cannot be captured; run the eager DiffusionEngine.training_step instead")
         self._opt_ready = self._ema_ready = False
         dev = image.device
         self.image = image.clone()

@@ -167,7 +167,7 @@ class Adafactor(Optimizer):
                                  gi, owner))
                     blk_start.append(nblk)
                     nblk += blocks_for(kind, n, Bt, R, C)
-                live.append((p, len(recs), mirror is not None))
+                live.append((p, len(recs), mirror))  # the mirror tensor is held: the table stores its raw pointer
         if not rows:
             self._plan = None
             return
@@ -187,9 +187,20 @@ class Adafactor(Optimizer):
             self.state[p]["RMS"] = self._plan["rms"][t]
             t += nrec
 
+    def _mirror_ptr(self, p) -> int:
+        m = ops.registered_mirror(p) if self.refresh_mirrors else None
+        return m.data_ptr() if m is not None else 0
+
     def _table_key(self):
-        return tuple((p.data_ptr(), p.grad.data_ptr() if p.grad is not None else 0)
+        """parameter, gradient AND bf16-mirror addresses: mirrors are re-created by `ops.invalidate_weight_cache()`
+        (engine.init_from_ckpt) and by `bf16_weight_group` re-homing a parameter in a stacked buffer — a table built
+        before that would write bf16 through a dangling pointer."""
+        return tuple((p.data_ptr(), p.grad.data_ptr() if p.grad is not None else 0, self._mirror_ptr(p))
                      for g in self.param_groups for p in g["params"])
+
+    def _fresh_items(self):
+        """[(parameter, mirror_is_fresh)]: a mirror counts as rewritten only if it is still the tensor the table wrote."""
+        return [(p, m is not None and ops.registered_mirror(p) is m) for p, _, m in self._plan["live"]]
 
     def prepare(self) -> None:
         """(re)build the device tables if parameters / gradient buffers moved (host work; never inside a capture)."""
@@ -235,7 +246,7 @@ class Adafactor(Optimizer):
             h[7] = 1.0 if group["scale_parameter"] else 0.0
         plan["hyper"].copy_(plan["hyper_host"], non_blocking=True)
         self._launch()
-        ops.parameters_updated_in_place([(p, fresh) for p, _, fresh in plan["live"]])
+        ops.parameters_updated_in_place(self._fresh_items())
         return loss
 
     # ---- CUDA-graph form: the step count lives on the device ------------------------------------------------------
@@ -277,7 +288,7 @@ class Adafactor(Optimizer):
             for p in group["params"]:
                 if p.grad is not None and len(self.state[p]) > 0:
                     self.state[p]["step"] = int(steps[gi])
-        ops.parameters_updated_in_place([(p, fresh) for p, _, fresh in self._plan["live"]])
+        ops.parameters_updated_in_place(self._fresh_items())
 
 
 class AdafactorScheduler(LambdaLR):
@@ -322,6 +333,9 @@ class LitEma(nn.Module):
         self._decay_host = float(self.decay)  # the fp32 value the reference compares against
         self._table = None
         self._key = None
+        # resume: `num_updates` / `decay` arrive through load_state_dict (engine.init_from_ckpt, Lightning checkpoints);
+        # the reference reads the buffers directly (ema.py:44-46), so the host mirrors follow every load
+        self.register_load_state_dict_post_hook(lambda module, _incompatible: module.sync_from_device())
 
     def reset_num_updates(self):
         del self.num_updates
@@ -402,7 +416,9 @@ class LitEma(nn.Module):
         self._launch()
 
     def sync_from_device(self) -> None:
+        """host mirrors of the `num_updates` / `decay` buffers (after a checkpoint load or graph replays)."""
         self._n_host = int(self.num_updates)
+        self._decay_host = float(self.decay)
 
     def copy_to(self, model: nn.Module):
         shadow = dict(self.named_buffers())

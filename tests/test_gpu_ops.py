@@ -300,7 +300,12 @@ def sdpa_ref(q, k, v, scale):
 
 @pytest.mark.parametrize("B,H,Nq,Nk,D", [(2, 4, 256, 256, 64), (1, 2, 1024, 1024, 64), (2, 3, 200, 77, 64), (1, 5, 1008, 1008, 64),
                                          (1, 1, 128, 300, 64), (2, 8, 256, 256, 40), (1, 2, 320, 77, 160), (1, 1, 512, 512, 512),
-                                         (2, 2, 300, 200, 128), (1, 3, 256, 256, 192), (1, 1, 1024, 1000, 512)])
+                                         (2, 2, 300, 200, 128), (1, 3, 256, 256, 192), (1, 1, 1024, 1000, 512),
+                                         # the shapes that dominate the benchmarked SDXL step and the aspect buckets of
+                                         # BASELINE.json configs[3]: 64x64 / 72x56 / 52x76 token grids with 10 heads,
+                                         # 26x38 with 20 heads, and the 77-token cross attention of the 4096-token level
+                                         (1, 10, 4096, 4096, 64), (1, 10, 4032, 4032, 64), (1, 10, 3952, 3952, 64),
+                                         (1, 20, 988, 988, 64), (1, 10, 4096, 77, 64), (2, 20, 1024, 1024, 64)])
 def test_attention_fwd_bwd(B, H, Nq, Nk, D):
     q = rnd(B, Nq, H, D).to(BF).requires_grad_(True)
     k = rnd(B, Nk, H, D, seed=1).to(BF).requires_grad_(True)

@@ -191,3 +191,51 @@ def test_lit_ema_host_path_against_reference_goldens(emulated):
         for n in EMA_SHAPES:
             np.testing.assert_allclose(sh[n.replace(".", "_")].numpy(), G[f"ema.{n}"], rtol=1e-6, atol=1e-7)
         assert int(ema.num_updates) == 12 and ema._n_host == 12
+
+
+def test_lit_ema_resume_rederives_the_decay_from_the_loaded_counter(emulated):
+    """after `load_state_dict` the warm-up decay must come from the LOADED `num_updates` (the
+    reference reads the buffer directly, modules/ema.py:44-46) — resumed at 50 000 updates the decay is 0.9999, not the
+    2/11 of a fresh counter — and an interrupted-and-resumed run equals an uninterrupted one."""
+    from neurosis_b200.optim import LitEma
+
+    def model():
+        m = torch.nn.Linear(40, 30)
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                p.copy_(synth_tensor(f"ema.p.a.{n}", tuple(p.shape)))
+        return m
+
+    def drift(m, it):
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                p.add_(synth_tensor(f"ema.d.a.{n}.{it}", tuple(p.shape), scale=0.1))
+
+    # (1) decay after loading a long-trained counter
+    m = model()
+    ema = LitEma(m, decay=0.9999)
+    sd = ema.state_dict()
+    sd["num_updates"] = torch.tensor(50000, dtype=torch.int)
+    ema2 = LitEma(model(), decay=0.5)
+    ema2.load_state_dict(sd)
+    assert ema2._n_host == 50000 and abs(ema2._decay_host - 0.9999) < 1e-7
+    ema2._n_host += 1
+    assert abs(ema2.current_decay() - min(0.9999, 50002 / 50011)) < 1e-7  # 0.99982, not the 2/11 of a fresh counter
+    # (2) 4 updates + save/load + 4 updates == 8 updates
+    ma, mb = model(), model()
+    ea, eb = LitEma(ma, decay=0.9999), LitEma(mb, decay=0.9999)
+    for it in range(8):
+        drift(ma, it)
+        ea(ma)
+    for it in range(4):
+        drift(mb, it)
+        eb(mb)
+    ec = LitEma(mb, decay=0.9999)
+    ec.load_state_dict(eb.state_dict())
+    for it in range(4, 8):
+        drift(mb, it)
+        ec(mb)
+    assert int(ec.num_updates) == 8 == ec._n_host
+    for (na, ba), (nc, bc) in zip(ea.named_buffers(), ec.named_buffers()):
+        assert na == nc
+        np.testing.assert_allclose(bc.numpy(), ba.numpy(), rtol=1e-6, atol=1e-7)

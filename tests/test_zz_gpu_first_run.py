@@ -1,12 +1,9 @@
-"""First-run GPU tests of the opt-in "optimizer + EMA inside the captured step" path.
+"""GPU tests of the opt-in "optimizer + EMA inside the captured step" path, the L1 / rectified-flow objectives and the
+full-size VAE training step.
 
-This file sorts LAST on purpose: the tests below were written after the round's GPU budget was spent, so a fault in them
-must not be able to disturb the validated suites that run before it in the same process.
-
-Status after the last GPU call of round 1 (profiles/r01_pytest_gpu_first_run.log): the device-side step-scalar test
-passed; the graphed step hit an illegal address because `LitEma`'s `num_updates` buffer was still on the CPU when the
-captured decay kernel dereferenced it (the test built the EMA without `.to(device)`).  `LitEma.graph_prepare` now
-moves the counter to the parameters' device; that fix has not run on a GPU yet, hence the markers stay."""
+History: written at the end of round 1 after that round's GPU budget was spent and marked non-strict xfail; all of them
+passed on the driver's round-end box (GPUTEST_r01.json: 4 xpassed), so the markers are gone and a regression now fails
+the suite.  The file still sorts last: the graphed optimizer test is the heaviest capture in the suite."""
 import numpy as np
 import pytest
 import torch
@@ -20,10 +17,6 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
 
 
 # ---------------------------------------------------------------- optimizer / EMA inside the captured step (opt-in)
-# Written after this round's GPU budget was spent: these run for the first time at round end.  They are marked
-# non-strict xfail so that an unvalidated opt-in path cannot mask the state of the validated suite; an XPASS is the
-# expected outcome.  (Drop the marker once they have been seen green.)
-_first_run = pytest.mark.xfail(strict=False, reason="opt-in graph path, first GPU run happens after the round's budget")
 
 
 def test_device_side_step_scalars_match_host_side():  # seen green on a B200 (profiles/r01_pytest_gpu_first_run.log)
@@ -70,7 +63,6 @@ def test_device_side_step_scalars_match_host_side():  # seen green on a B200 (pr
     assert rel(eb.a_weight, ea.a_weight) < 1e-6
 
 
-@_first_run
 def test_graphed_step_with_optimizer_and_ema():
     """one replay = refresh -> encode -> loss -> backward -> reduce -> Adafactor -> EMA; counters advance per replay."""
     from test_gpu_modules import build_unet  # noqa: F401  (shared tiny-model builder)
@@ -125,7 +117,6 @@ def test_graphed_step_with_optimizer_and_ema():
     assert torch.isfinite(s).all() and float((s - w.detach()).abs().max()) > 0
 
 
-@_first_run
 def test_weighted_l1_loss_fwd_bwd():
     """StandardDiffusionLoss(loss_type="l1") arithmetic: loss[b] = w[b] * mean|D - T| (BatchL1Loss) and its gradient."""
     from neurosis_b200 import ops
@@ -143,7 +134,6 @@ def test_weighted_l1_loss_fwd_bwd():
     assert rel(loss, lr_) < 1e-5 and rel(D.grad, Dr.grad) < 1e-6
 
 
-@_first_run
 def test_full_size_vae_training_step_vs_reference_golden():
     """AutoencoderKL at the FULL SDXL KL-f8 configuration (108 + 140 tensors; 512-channel mid attention, d = 512) on a
     64x64 image: moments, reconstruction and loss against the reference's Encoder / Decoder (goldens), gradient norms
@@ -179,7 +169,6 @@ def test_full_size_vae_training_step_vs_reference_golden():
     assert np.allclose(dec_l2[keep_d], G["fullvae.dec_grad_l2"][keep_d], rtol=8e-2, atol=1e-7)
 
 
-@_first_run
 def test_rectified_flow_objective_vs_reference_golden():
     """StandardDiffusionLoss(objective_type="rf") + continuous Denoiser(RectifiedFlowComfyPreconditioning) +
     RectifiedFlowComfyWeighting on the CUDA modules: bf16 step loss within 1e-2 of the reference's fp32 value, gradient
