@@ -92,6 +92,19 @@ int nk_linear_dgrad(const void* dy, int64_t lddy, const void* w, int64_t ldw, co
 int nk_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw,
                     int accumulate, int M, int N, int K, nk_stream_t stream);
 
+/* GEGLU feed-forward input projection, gate fused into the GEMM epilogue — replaces `GEGLU.forward`
+ * (/root/reference/src/neurosis/modules/attention.py:50-57: `x, gate = self.proj(x).chunk(2, dim=-1); x * F.gelu(gate)`).
+ *   h[M, 2D] = x[M,K] @ w[2D,K]^T + bias[2D]     (bf16; optional — null skips the store; saved for the backward)
+ *   out[M, D] = h[:, :D] * gelu_erf(h[:, D:])     (bf16)
+ * D % 16 == 0; ldh, ldo % 8 == 0. */
+int nk_linear_geglu_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* h, int64_t ldh,
+                        void* out, int64_t ldo, int M, int D, int K, nk_stream_t stream);
+/* Data gradient of the projection that FOLLOWS a GEGLU (`FeedForward.net[2]`, attention.py:60-74) with the GEGLU
+ * backward fused into its epilogue: d_out = dy[M,N] @ w[N,D] is never written,
+ *   dh[M, :D] = d_out * gelu_erf(h[:, D:])      dh[M, D:] = d_out * h[:, :D] * gelu_erf'(h[:, D:]). */
+int nk_linear_dgrad_geglu(const void* dy, int64_t lddy, const void* w, int64_t ldw, const void* h, int64_t ldh, void* dh,
+                          int64_t lddh, int M, int N, int D, nk_stream_t stream);
+
 /* 3x3 (pad 1) or 1x1 (pad 0) stride-1 convolution on NHWC bf16 activations as implicit GEMM.
  *   y[n,h,w,co] = sum_{tap,ci} x[n,h+dy,w+dx,ci] * wp[co, tap*Cin+ci] + bias[co] + bias_img[n,co]
  *                 + residual[n,h,w,co]

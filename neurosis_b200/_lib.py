@@ -110,6 +110,13 @@ def parse_header(path: Path = HEADER) -> dict[str, tuple]:
 
 def _load() -> ctypes.CDLL:
     path = Path(os.environ.get("NK_B200_LIB", LIB_PATH))
+    if "NK_B200_LIB" not in os.environ:
+        # a fresh clone has no binary (the .so is git-ignored) and an edited source tree has a stale one: (re)build in
+        # tree when nvcc is available — the same routine `__graft_entry__.build()` runs
+        from . import build as _build
+        stale = (not path.exists()) or _build._stale(path, _build._sources() + _build._headers())
+        if stale and Path(_build.NVCC).exists() and not os.environ.get("NK_B200_NO_AUTOBUILD"):
+            _build.build(verbose=True)
     if not path.exists():
         raise ImportError(
             f"neurosis_b200: kernel library {path} is missing - run `python -m neurosis_b200.build` "

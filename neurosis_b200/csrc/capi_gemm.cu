@@ -135,6 +135,45 @@ int nk_linear_dgrad(const void* dy, int64_t lddy, const void* w, int64_t ldw, co
     return launch_gemm(p, ::nk::enter(stream));
 }
 
+int nk_linear_geglu_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* h, int64_t ldh,
+                        void* out, int64_t ldo, int M, int D, int K, nk_stream_t stream) {
+    GemmProblem p = blank_problem();
+    p.A = matrix(x, 0, M, K, ldx);
+    p.B = matrix(w, 0, 2LL * D, K, ldw);
+    p.M = M;
+    p.N = D;
+    p.K = K;
+    p.C = h;
+    p.ldc = ldh > 0 ? ldh : 2LL * D;
+    p.C2 = out;
+    p.ldc2 = ldo;
+    p.geglu_d = D;
+    p.out = OUT_BF16;
+    p.epi = EPI_GEGLU_FWD;
+    p.bias = bias;
+    return launch_gemm(p, ::nk::enter(stream));
+}
+
+int nk_linear_dgrad_geglu(const void* dy, int64_t lddy, const void* w, int64_t ldw, const void* h, int64_t ldh, void* dh,
+                          int64_t lddh, int M, int N, int D, nk_stream_t stream) {
+    // d(out)[m,d] = sum_n dy[m,n] w[n,d] (w = the [N, D] weight of the projection after the GEGLU), turned into
+    // dh [M, 2D] by the epilogue
+    GemmProblem p = blank_problem();
+    p.A = matrix(dy, 0, M, N, lddy);
+    p.B = matrix(w, 1, N, D, ldw);
+    p.M = M;
+    p.N = D;
+    p.K = N;
+    p.C = dh;
+    p.ldc = lddh;
+    p.geglu_d = D;
+    p.aux = static_cast<const bf16*>(h);
+    p.ldr = ldh;
+    p.out = OUT_BF16;
+    p.epi = EPI_GEGLU_BWD;
+    return launch_gemm(p, ::nk::enter(stream));
+}
+
 int nk_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw,
                     int accumulate, int M, int N, int K, nk_stream_t stream) {
     // dw[n,k] = sum_m dy[m,n] x[m,k]: reduction over tokens m; both operands MN-major

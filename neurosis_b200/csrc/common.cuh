@@ -89,6 +89,34 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     return __bfloat1622float2(v);
 }
 
+// exact-erf GELU (F.gelu default, reference modules/attention.py:57) and its derivative.
+// Phi(x) = 0.5 (1 + erf(x / sqrt 2)) through the rational approximation of Abramowitz & Stegun 7.1.26
+// (|error| <= 1.5e-7 on erf, i.e. below fp32 rounding of the bf16-bound results): with z = |x| / sqrt 2,
+// t = 1 / (1 + p z):  1 - erf(z) = (a1 t + ... + a5 t^5) e^{-z^2}.  The exponential e^{-x^2/2} is the Gaussian density
+// the derivative needs, so gelu and gelu' share it: ~13 FMA-pipe instructions + 2 MUFU (rcp, ex2) per element, about
+// half of erff + __expf — these run inside GEMM epilogues (EPI_GEGLU_*) where the instruction count is the bottleneck.
+__device__ __forceinline__ float gauss_cdf_pdf(float x, float& pdf) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+    const float e = exp2f(x * x * -0.72134752044448170f);  // e^{-x^2/2}
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float q = 0.5f * p * t * e;  // upper tail probability of |x|
+    pdf = 0.39894228040143268f * e;
+    return x >= 0.f ? 1.f - q : q;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+    float pdf;
+    return x * gauss_cdf_pdf(x, pdf);
+}
+__device__ __forceinline__ float dgelu_erf(float x) {
+    float pdf;
+    const float cdf = gauss_cdf_pdf(x, pdf);
+    return fmaf(x, pdf, cdf);
+}
+
 // device-side watchdog: a pipeline bug must not hang the GPU box.  Waits give up after
 // ~2 s of wall clock and trap (the host sees cudaErrorLaunchFailure).
 __device__ __forceinline__ uint64_t globaltimer_ns() {

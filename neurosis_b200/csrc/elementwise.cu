@@ -35,12 +35,7 @@ __device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
     *reinterpret_cast<uint4*>(p) = q;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float dgelu_erf(float x) {
-    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-    const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
-}
+// gelu_erf / dgelu_erf live in common.cuh (shared with the GEGLU epilogues of the GEMM kernel)
 
 // ---- GEGLU ----------------------------------------------------------------------------------
 // h: [M, 2D] = (value | gate); out[m, d] = value * gelu(gate)

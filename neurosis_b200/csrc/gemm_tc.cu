@@ -47,6 +47,8 @@ struct alignas(64) GemmDev {
     int stages;
     int a_mn, b_mn;
     int mode;
+    int dbg_skip;                // NK_GEMM_DBG_SKIP bit 1: no A loads, bit 2: no B loads (timing experiments, wrong results)
+    int raster_gm;               // > 0: tiles are walked in groups of raster_gm row blocks x all N tiles (see launch_gemm)
     int a_b2, a_b1, b_b2, b_b1;  // 0/1: does the operand carry that batch dimension
     // conv geometry
     int cH, cW, bw, bh, tiles_w, tiles_h, cin_blocks, ksize, pad;  // cH, cW: OUTPUT image (= input unless strided)
@@ -63,6 +65,9 @@ struct alignas(64) GemmDev {
     long long ldr;
     const float* rowvec;
     const bf16* aux;
+    int geglu_d;       // EPI_GEGLU_*: D (the tile scheduler runs over N = D columns)
+    void* C2;          // EPI_GEGLU_FWD: gated output [M, D]
+    long long ldc2;
     uint32_t idesc;
     uint32_t a_bytes, b_bytes;  // bytes landed per stage for A and B
     long long* dbg;             // optional per-CTA cycle counters (NK_GEMM_DEBUG_TIMING), 8 per CTA
@@ -74,10 +79,23 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const GemmDev& g, int t) {
     TileCoord c;
-    c.mt = t % g.tiles_m;
-    t /= g.tiles_m;
-    c.nt = t % g.tiles_n;
-    t /= g.tiles_n;
+    if (g.raster_gm > 0) {
+        const int per_batch = g.tiles_m * g.tiles_n;
+        const int tb = t % per_batch;
+        t /= per_batch;
+        const int per_group = g.raster_gm * g.tiles_n;
+        const int grp = tb / per_group;
+        const int r = tb - grp * per_group;
+        const int m0 = grp * g.raster_gm;
+        const int gsize = min(g.raster_gm, g.tiles_m - m0);  // the last group may be short
+        c.nt = r / gsize;
+        c.mt = m0 + (r - c.nt * gsize);
+    } else {
+        c.mt = t % g.tiles_m;
+        t /= g.tiles_m;
+        c.nt = t % g.tiles_n;
+        t /= g.tiles_n;
+    }
     c.b2 = t % g.nb2;
     t /= g.nb2;
     c.b1 = t % g.nb1;
@@ -108,10 +126,12 @@ __device__ __forceinline__ void add_vec16(float (&v)[16], const float* p, bool f
     }
 }
 
-// TRANSPOSED = true is the MODE_CONV_FWD_T instance (its epilogue lives in a separate instantiation so that its register
-// pressure cannot spill into the main kernel)
-template <int CG, bool TRANSPOSED = false>
+// VAR selects an epilogue family that lives in its own instantiation (so that its register pressure cannot spill into the
+// main kernel): 0 = general, 1 = MODE_CONV_FWD_T (transposed convolution), 2 = EPI_GEGLU_FWD, 3 = EPI_GEGLU_BWD
+enum { VAR_MAIN = 0, VAR_TRANSPOSED = 1, VAR_GEGLU_FWD = 2, VAR_GEGLU_BWD = 3 };
+template <int CG, int VAR = VAR_MAIN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmDev g) {
+    constexpr bool TRANSPOSED = VAR == VAR_TRANSPOSED;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024B alignment is required by the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -221,16 +241,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         const long long tw0 = g.dbg ? clock64() : 0;
                         mbar_wait(&empty_bar[stage], phase ^ 1u, 100u + stage);
                         if (g.dbg) dbg_acc0 += clock64() - tw0;
-                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * (g.a_bytes + g.b_bytes));
+                        if (rank == 0)
+                            mbar_arrive_expect_tx(&full_bar[stage], CG * (((g.dbg_skip & 1) ? 0u : g.a_bytes) +
+                                                                          ((g.dbg_skip & 2) ? 0u : g.b_bytes)));
                     }
                     __syncwarp();
                     uint8_t* sa = smem_a + static_cast<size_t>(stage) * A_STAGE_BYTES;
                     uint8_t* sb = smem_b + static_cast<size_t>(stage) * b_stage_bytes;
-                    if (g.mode == MODE_PLAIN) {
+                    if (VAR == VAR_GEGLU_FWD) {
+                        // B = W [2D, K]: the tile's first BN/2 rows are value features [nt*BN/2, ...), the last BN/2
+                        // rows the gate rows of the same features (D rows further down).  A CTA pair gets that split for
+                        // free — rank 0 holds the value half of the UMMA's N range, rank 1 the gate half.
+                        const int k0 = gi * BK;
+                        const int hr = g.BN / 2;
+                        if (lane == 0) {
+                            tma_load(&g.tmA, &full_bar[stage], sa, k0, m0, 0, 0);
+                        } else if (CG == 2) {
+                            if (lane == 1)
+                                tma_load(&g.tmB, &full_bar[stage], sb, k0, static_cast<int>(rank) * g.geglu_d + tc.nt * hr, 0, 0);
+                        } else if (lane <= 2) {
+                            const int j = lane - 1;
+                            tma_load(&g.tmB, &full_bar[stage], sb + static_cast<size_t>(j) * hr * 128, k0,
+                                     j * g.geglu_d + tc.nt * hr, 0, 0);
+                        }
+                    } else if (g.mode == MODE_PLAIN) {
                         const int k0 = gi * BK;
                         const int na = g.a_mn ? 2 : 1;
                         const int nb = g.b_mn ? nb_atoms : 1;
-                        if (lane < na) {
+                        if (g.dbg_skip && ((lane < na && (g.dbg_skip & 1)) || (lane >= na && (g.dbg_skip & 2)))) {
+                            // timing experiment: this operand is not fetched (stale shared memory is multiplied)
+                        } else if (lane < na) {
                             if (!g.a_mn)
                                 tma_load(&g.tmA, &full_bar[stage], sa, k0, m0, tc.b2 * g.a_b2, tc.b1 * g.a_b1);
                             else
@@ -591,6 +631,117 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         }
                     }
                 }
+            } else if constexpr (VAR == VAR_GEGLU_FWD) {
+                // value chunk c (columns [16c, 16c+16) of the tile) pairs with gate chunk nx + c; the two warps of a lane
+                // quadrant split the value chunks.  h = acc + bias is rounded to bf16 FIRST (it is what the backward
+                // reads), the gate uses the rounded values.
+                const int D = g.geglu_d;
+                const int nx = nch / 2;
+                const int cb = half ? (nx + 1) / 2 : 0, ce = half ? nx : (nx + 1) / 2;
+                const int n0x = tc.nt * (g.BN / 2);
+                bf16* hrow = g.C ? reinterpret_cast<bf16*>(g.C) + row * g.ldc : nullptr;
+                bf16* orow = reinterpret_cast<bf16*>(g.C2) + row * g.ldc2;
+                auto ld2 = [&](int c, uint32_t (&rx)[16], uint32_t (&rg)[16]) {
+                    tc_ld16(taddr0 + static_cast<uint32_t>(c * 16), rx);
+                    tc_ld16(taddr0 + static_cast<uint32_t>((nx + c) * 16), rg);
+                };
+                auto proc = [&](int c, const uint32_t (&rx)[16], const uint32_t (&rg)[16]) {
+                    const int n = n0x + c * 16;
+                    if (!row_ok || n >= D) return;
+                    float v[16], t[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        v[j] = __uint_as_float(rx[j]);
+                        t[j] = __uint_as_float(rg[j]);
+                    }
+                    if (g.bias) {
+                        add_vec16(v, g.bias + n, true, 16);
+                        add_vec16(t, g.bias + D + n, true, 16);
+                    }
+                    uint32_t hv[8], hg[8], ov[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        hv[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                        hg[j] = pack_bf16x2(t[2 * j], t[2 * j + 1]);
+                        const float2 a = unpack_bf16x2(hv[j]), b = unpack_bf16x2(hg[j]);
+                        ov[j] = pack_bf16x2(a.x * gelu_erf(b.x), a.y * gelu_erf(b.y));
+                    }
+                    if (hrow) {
+                        reinterpret_cast<uint4*>(hrow + n)[0] = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+                        reinterpret_cast<uint4*>(hrow + n)[1] = make_uint4(hv[4], hv[5], hv[6], hv[7]);
+                        reinterpret_cast<uint4*>(hrow + D + n)[0] = make_uint4(hg[0], hg[1], hg[2], hg[3]);
+                        reinterpret_cast<uint4*>(hrow + D + n)[1] = make_uint4(hg[4], hg[5], hg[6], hg[7]);
+                    }
+                    reinterpret_cast<uint4*>(orow + n)[0] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                    reinterpret_cast<uint4*>(orow + n)[1] = make_uint4(ov[4], ov[5], ov[6], ov[7]);
+                };
+                if (cb < ce) {
+                    uint32_t ax[16], ag[16], bx[16], bg[16];
+                    ld2(cb, ax, ag);
+                    for (int c = cb; c < ce; c += 2) {
+                        tc_wait_ld16(ax);
+                        tc_wait_ld16(ag);
+                        if (c + 1 < ce) ld2(c + 1, bx, bg);
+                        proc(c, ax, ag);
+                        if (c + 1 < ce) {
+                            tc_wait_ld16(bx);
+                            tc_wait_ld16(bg);
+                            if (c + 2 < ce) ld2(c + 2, ax, ag);
+                            proc(c + 1, bx, bg);
+                        }
+                    }
+                }
+            } else if constexpr (VAR == VAR_GEGLU_BWD) {
+                // acc = d(out)[row, n..n+16); h = (value | gate) rows of the saved pre-activation (aux, row stride ldr):
+                //   dh[:, n] = acc * gelu(gate)      dh[:, D + n] = acc * value * gelu'(gate)
+                const int D = g.geglu_d;
+                const bf16* hrow = row_ok ? g.aux + row * g.ldr : nullptr;
+                bf16* drow = reinterpret_cast<bf16*>(g.C) + row * g.ldc;
+                auto issue_b = [&](int c, uint32_t (&raw)[16], uint4 (&hx)[2], uint4 (&hg)[2]) {
+                    tc_ld16(taddr0 + static_cast<uint32_t>(c * 16), raw);
+                    const int n = n0 + c * 16;
+                    if (hrow != nullptr && n < D) {
+                        const uint4* px = reinterpret_cast<const uint4*>(hrow + n);
+                        const uint4* pg = reinterpret_cast<const uint4*>(hrow + D + n);
+                        hx[0] = __ldg(px);
+                        hx[1] = __ldg(px + 1);
+                        hg[0] = __ldg(pg);
+                        hg[1] = __ldg(pg + 1);
+                    }
+                };
+                auto proc_b = [&](int c, const uint32_t (&raw)[16], const uint4 (&hx)[2], const uint4 (&hg)[2]) {
+                    const int n = n0 + c * 16;
+                    if (!row_ok || n >= D) return;
+                    const uint32_t wx[8] = {hx[0].x, hx[0].y, hx[0].z, hx[0].w, hx[1].x, hx[1].y, hx[1].z, hx[1].w};
+                    const uint32_t wg[8] = {hg[0].x, hg[0].y, hg[0].z, hg[0].w, hg[1].x, hg[1].y, hg[1].z, hg[1].w};
+                    uint32_t da[8], dg[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 a = unpack_bf16x2(wx[j]), b = unpack_bf16x2(wg[j]);
+                        const float d0 = __uint_as_float(raw[2 * j]) * g.alpha, d1 = __uint_as_float(raw[2 * j + 1]) * g.alpha;
+                        da[j] = pack_bf16x2(d0 * gelu_erf(b.x), d1 * gelu_erf(b.y));
+                        dg[j] = pack_bf16x2(d0 * a.x * dgelu_erf(b.x), d1 * a.y * dgelu_erf(b.y));
+                    }
+                    reinterpret_cast<uint4*>(drow + n)[0] = make_uint4(da[0], da[1], da[2], da[3]);
+                    reinterpret_cast<uint4*>(drow + n)[1] = make_uint4(da[4], da[5], da[6], da[7]);
+                    reinterpret_cast<uint4*>(drow + D + n)[0] = make_uint4(dg[0], dg[1], dg[2], dg[3]);
+                    reinterpret_cast<uint4*>(drow + D + n)[1] = make_uint4(dg[4], dg[5], dg[6], dg[7]);
+                };
+                if (c_begin < c_end) {
+                    uint32_t r0[16], r1[16];
+                    uint4 x0[2], g0[2], x1[2], g1[2];
+                    issue_b(c_begin, r0, x0, g0);
+                    for (int c = c_begin; c < c_end; c += 2) {
+                        tc_wait_ld16(r0);
+                        if (c + 1 < c_end) issue_b(c + 1, r1, x1, g1);
+                        proc_b(c, r0, x0, g0);
+                        if (c + 1 < c_end) {
+                            tc_wait_ld16(r1);
+                            if (c + 2 < c_end) issue_b(c + 2, r0, x0, g0);
+                            proc_b(c + 1, r1, x1, g1);
+                        }
+                    }
+                }
             } else if (c_begin < c_end) {
                 uint32_t r0[16], r1[16];
                 uint4 s0a = make_uint4(0, 0, 0, 0), s0b = s0a, s1a = s0a, s1b = s0a;
@@ -870,13 +1021,13 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
         }
         static bool attr_t_set = false;
         if (!attr_t_set) {
-            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_t));
+            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, VAR_TRANSPOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_t));
             attr_t_set = true;
         }
         g.dbg = dbg_buf;
         if (dbg_buf) NK_CUDA(cudaMemsetAsync(dbg_buf, 0, 8 * 1024 * sizeof(long long), stream));
         const int grid_t = static_cast<int>(std::min<long long>(g.tiles_n, nsm));
-        gemm_tc_kernel<1, true><<<grid_t, NUM_THREADS, smem_t, stream>>>(g);
+        gemm_tc_kernel<1, VAR_TRANSPOSED><<<grid_t, NUM_THREADS, smem_t, stream>>>(g);
         NK_CUDA(cudaGetLastError());
         if (dbg_buf) return debug_report(p, g, 1, g.tiles_n, nsm, dbg_buf, stream);
         return NK_OK;
@@ -895,9 +1046,23 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
 
     const long long tiles_mb = static_cast<long long>(g.tiles_m) * g.nb2 * g.nb1;
     g.BN = pick_bn(p, tiles_mb, nsm / cg, cg);
+    const bool geglu_fwd = p.epi == EPI_GEGLU_FWD, geglu_bwd = p.epi == EPI_GEGLU_BWD;
+    if (geglu_fwd || geglu_bwd) {
+        NK_REQUIRE(g.mode == MODE_PLAIN && !p.A.mn_major && p.nb1 <= 1 && p.nb2 <= 1 && p.out == OUT_BF16, NK_ERR_UNSUPPORTED,
+                   "GEGLU epilogues: plain bf16 GEMM only");
+        NK_REQUIRE(p.geglu_d == p.N && p.N % 16 == 0 && p.ldc % 8 == 0, NK_ERR_SHAPE, "GEGLU: D=%d must be a multiple of 16", p.N);
+        g.geglu_d = p.geglu_d;
+    }
+    if (geglu_fwd) {  // an N tile = BN/2 value columns + their BN/2 gate columns (see the producer)
+        NK_REQUIRE(!p.B.mn_major && p.C2 != nullptr && p.ldc2 % 8 == 0, NK_ERR_SHAPE, "GEGLU fwd: K-major W and an output");
+        g.BN = p.N >= 128 ? 256 : 2 * p.N;
+        g.C2 = p.C2;
+        g.ldc2 = p.ldc2;
+    }
+    if (geglu_bwd) NK_REQUIRE(p.aux != nullptr && p.ldr % 8 == 0, NK_ERR_SHAPE, "GEGLU bwd needs h (aux)");
     NK_REQUIRE(g.BN >= 16 * cg && g.BN <= 256 && g.BN % (16 * cg) == 0, NK_ERR_SHAPE, "bad BN %d (cta group %d)", g.BN, cg);
     NK_REQUIRE(!p.B.mn_major || g.BN % (64 * cg) == 0, NK_ERR_SHAPE, "MN-major B needs BN %% %d == 0", 64 * cg);
-    g.tiles_n = (p.N + g.BN - 1) / g.BN;
+    g.tiles_n = geglu_fwd ? (p.N + g.BN / 2 - 1) / (g.BN / 2) : (p.N + g.BN - 1) / g.BN;
     const int bnc = g.BN / cg;
     g.b_bytes = static_cast<uint32_t>(bnc) * 128u;
 
@@ -930,6 +1095,35 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     }
     g.k_iters = (g.k_iters_total + splits - 1) / splits;
     g.splits = (g.k_iters_total + g.k_iters - 1) / g.k_iters;
+    // Tile order.  The CTA groups that run at the same time should touch as few DISTINCT operand bytes as possible:
+    // identical requests from different SMs are merged at the L2 (measured: with the A loads of 16384 x 10240 x 1280
+    // removed — 40 distinct B tiles in flight — the kernel runs at 1229 TFLOP/s, with the B loads removed — 2 distinct A
+    // slabs — at 1430, with neither at 1442; profiles/r02_gemm_probe_skip.txt), and an activation operand larger than
+    // the 126 MB L2 must not be streamed from DRAM once per N tile (741 MB instead of 215 MB for 16384 x 1280 x 5120
+    // in the first-round order).  So tiles are walked in groups of `gm` row blocks x all N tiles, row block fastest,
+    // with gm ~ sqrt(#CTA groups): one wave covers ~gm row blocks x ~gm N tiles.  NK_GEMM_RASTER=0 restores the old
+    // order (all row blocks of one N tile first), =1 is one row block at a time (A/B switches).
+    {
+        static int env_raster = -1;
+        if (env_raster < 0) {
+            const char* e_ = getenv("NK_GEMM_RASTER");
+            env_raster = e_ ? atoi(e_) : 2;
+        }
+        const int conc = nsm / cg;
+        int side = 1;
+        while (side * side < conc) ++side;
+        const int ncols = std::max(1, std::min(g.tiles_n, side));
+        int gm = (conc + ncols - 1) / ncols;
+        if (env_raster == 0) gm = 0;
+        else if (env_raster == 1) gm = 1;
+        g.raster_gm = std::min(gm, g.tiles_m);
+        static int env_skip = -1;
+        if (env_skip < 0) {
+            const char* e_ = getenv("NK_GEMM_DBG_SKIP");
+            env_skip = e_ ? atoi(e_) : 0;
+        }
+        g.dbg_skip = (g.mode == MODE_PLAIN && !geglu_fwd) ? env_skip : 0;
+    }
 
     g.a_b2 = (!p.A.conv && p.A.nb2 > 1) ? 1 : 0;
     g.a_b1 = (!p.A.conv && p.A.nb1 > 1) ? 1 : 0;
@@ -938,7 +1132,7 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
 
     int e = make_operand_tmap(&g.tmA, p.A, a_box1, a_box2, g.mode == MODE_CONV_FWD ? g.cstride : 1);
     if (e) return e;
-    const int b_box1 = p.B.conv ? g.bw : (p.B.mn_major ? 64 : bnc);
+    const int b_box1 = p.B.conv ? g.bw : (p.B.mn_major ? 64 : (geglu_fwd ? g.BN / 2 : bnc));
     e = make_operand_tmap(&g.tmB, p.B, b_box1, b_box2);
     if (e) return e;
 
@@ -975,9 +1169,21 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     NK_REQUIRE(total < (1LL << 31), NK_ERR_SHAPE, "too many tiles");
     g.dbg = dbg_buf;
     if (dbg_buf) NK_CUDA(cudaMemsetAsync(dbg_buf, 0, 8 * 1024 * sizeof(long long), stream));
+    if (geglu_fwd || geglu_bwd) {
+        static bool attr_g_set = false;
+        if (!attr_g_set) {
+            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, VAR_GEGLU_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2, VAR_GEGLU_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, VAR_GEGLU_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2, VAR_GEGLU_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            attr_g_set = true;
+        }
+    }
     if (cg == 1) {
         const int grid = static_cast<int>(std::min<long long>(total, nsm));
-        gemm_tc_kernel<1><<<grid, NUM_THREADS, smem_bytes, stream>>>(g);
+        if (geglu_fwd) gemm_tc_kernel<1, VAR_GEGLU_FWD><<<grid, NUM_THREADS, smem_bytes, stream>>>(g);
+        else if (geglu_bwd) gemm_tc_kernel<1, VAR_GEGLU_BWD><<<grid, NUM_THREADS, smem_bytes, stream>>>(g);
+        else gemm_tc_kernel<1><<<grid, NUM_THREADS, smem_bytes, stream>>>(g);
     } else {
         const int grid = 2 * static_cast<int>(std::min<long long>(total, nsm / 2));
         cudaLaunchConfig_t cfg;
@@ -993,7 +1199,9 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        NK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, g));
+        if (geglu_fwd) NK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, VAR_GEGLU_FWD>, g));
+        else if (geglu_bwd) NK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, VAR_GEGLU_BWD>, g));
+        else NK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, g));
     }
     NK_CUDA(cudaGetLastError());
     if (dbg_buf) return debug_report(p, g, cg, total, nsm, dbg_buf, stream);

@@ -9,6 +9,13 @@ enum GemmEpilogue : int {
     EPI_LINEAR = 0,  // C = alpha*acc (+ bias[n]) (+ bias_img[img,n]) (+ residual[m,n])
     EPI_EXP2 = 1,    // C = exp2(alpha*acc - rowvec[m])                 (attention probabilities)
     EPI_DSOFTMAX = 2,  // C = aux[m,n] * (acc - rowvec[m]) * alpha       (attention dS)
+    // GEGLU fused into the feed-forward GEMMs (reference modules/attention.py:50-57: x, gate = proj(x).chunk(2); x * gelu(gate)).
+    // FWD: B = W [2D, K]; an N tile holds BN/2 value columns and the BN/2 gate columns of the same features, so one thread
+    //      sees both: C (optional) = h [M, 2D] = acc + bias (saved for the backward), C2 [M, D] = value * gelu(gate).
+    // BWD: the data-gradient GEMM of the projection that FOLLOWS the GEGLU: acc = d(out) [M, D]; with aux = h [M, 2D]
+    //      C [M, 2D] = (acc * gelu(gate) | acc * value * gelu'(gate)) — d(out) itself is never written.
+    EPI_GEGLU_FWD = 3,
+    EPI_GEGLU_BWD = 4,
 };
 
 enum GemmOut : int {
@@ -51,7 +58,10 @@ struct GemmProblem {
     const bf16* residual;     // [M, ldr] or null (batch strides = C's)
     long long ldr;
     const float* rowvec;      // [M] per batch entry (stride M), EPI_EXP2 / EPI_DSOFTMAX
-    const bf16* aux;          // [M, N] like C, EPI_DSOFTMAX
+    const bf16* aux;          // [M, N] like C, EPI_DSOFTMAX; h [M, 2D] with row stride ldr for EPI_GEGLU_BWD
+    int geglu_d;              // D of the GEGLU epilogues (N = D for both: the tile scheduler runs over D)
+    void* C2;                 // EPI_GEGLU_FWD: gated output [M, D]
+    long long ldc2;
     int force_bn;             // 0 = heuristic
     int force_splits;         // 0 = heuristic (only with OUT_F32_ATOMIC)
     int force_cta_group;      // 0 = heuristic, 1 = single CTA tiles, 2 = CTA pairs (cta_group::2)

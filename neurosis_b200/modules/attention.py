@@ -28,6 +28,9 @@ from .. import ops
 from .util import as_nhwc, from_nhwc, zero_module
 
 
+FUSED_GEGLU_MIN_DIM = 1 << 30 if os.environ.get("NK_NO_FUSED_GEGLU") else int(os.environ.get("NK_FUSED_GEGLU_MIN_DIM", "1024"))
+
+
 class GEGLU(nn.Module):
     def __init__(self, dim_in: int, dim_out: int):
         super().__init__()
@@ -59,8 +62,15 @@ class FeedForward(nn.Module):
         self.net = nn.Sequential(project_in, nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
 
     def forward(self, x: Tensor, residual: Optional[Tensor] = None) -> Tensor:
-        h = self.net[0](x)
         out = self.net[2]
+        proj = getattr(self.net[0], "proj", None)
+        if proj is not None and proj.out_features % 32 == 0 and proj.in_features >= FUSED_GEGLU_MIN_DIM:
+            # gate (forward) and its derivative (backward) live in the epilogues of the two GEMMs.  Only where the
+            # reduction is long enough to hide the heavier epilogue behind the main loop: at dim 640 (K = 640, 10
+            # k-iterations per tile) the fused kernels measured slower than GEMM + elementwise kernel
+            # (profiles/r02_breakdown_v26.txt: 8.9 vs 7.3 ms forward, 6.9 vs 4.6 ms backward at 65536 tokens).
+            return ops.feed_forward_geglu(x, proj.weight, proj.bias, out.weight, out.bias, residual)
+        h = self.net[0](x)
         return ops.linear(h, out.weight, out.bias, residual)
 
 

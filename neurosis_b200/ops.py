@@ -437,6 +437,40 @@ def linear_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     return dw
 
 
+def linear_geglu_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], keep_h: bool = True):
+    """(h [M, 2D] or None, out [M, D]): h = x @ w[2D, K]^T + bias, out = h[:, :D] * gelu(h[:, D:]) — the gate is applied
+    in the GEMM epilogue (one N tile holds the value and the gate columns of the same features)."""
+    _req_cuda(x, w)
+    K = x.shape[-1]
+    D = w.shape[0] // 2
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    h = torch.empty((M, 2 * D), dtype=BF16, device=x.device) if keep_h else None
+    out = torch.empty((M, D), dtype=BF16, device=x.device)
+    _tc(lib.nk_linear_geglu_fwd, "linear_geglu_fwd", 2.0 * M * 2 * D * K, x2.data_ptr(), x2.stride(0), w.data_ptr(),
+        w.stride(0), _p(bias), _p(h), 2 * D, out.data_ptr(), D, M, D, K, _stream())
+    _count()
+    return (h.view(*x.shape[:-1], 2 * D) if h is not None else None), out.view(*x.shape[:-1], D)
+
+
+def linear_dgrad_geglu(dy: Tensor, w: Tensor, h: Tensor) -> Tensor:
+    """dh [M, 2D] of a GEGLU whose output feeds y = out @ w[N, D]^T: d_out = dy @ w goes through the gate's derivative in
+    the epilogue of the data-gradient GEMM and is never written."""
+    N, D = w.shape
+    d2 = dy.reshape(-1, N)
+    if d2.stride(-1) != 1:
+        d2 = d2.contiguous()
+    h2 = h.reshape(-1, 2 * D)
+    M = d2.shape[0]
+    dh = torch.empty((M, 2 * D), dtype=BF16, device=dy.device)
+    _tc(lib.nk_linear_dgrad_geglu, "linear_dgrad_geglu", 2.0 * M * N * D, d2.data_ptr(), d2.stride(0), w.data_ptr(),
+        w.stride(0), h2.data_ptr(), h2.stride(0), dh.data_ptr(), 2 * D, M, N, D, _stream())
+    _count()
+    return dh.view(*dy.shape[:-1], 2 * D)
+
+
 def colsum(x: Tensor, groups: int = 1, out: Optional[Tensor] = None) -> Tensor:
     """fp32 [groups, C] column sums of a bf16 [groups*rows, C] matrix; with `out` given the sums are added to it."""
     C = x.shape[-1]
@@ -932,6 +966,76 @@ def noise_mix(x: Tensor, noise: Tensor, sigma: Tensor, rectified_flow: bool = Fa
 # --------------------------------------------------------------------------------------------
 # autograd Functions
 # --------------------------------------------------------------------------------------------
+def _linear_param_grads(dy: Tensor, x: Tensor, weight: Tensor, bias: Optional[Tensor], need_w: bool, need_b: bool):
+    """(dW, db) of y = x W^T + b.  With a gradient sink both go straight into the bucket storage — on the side stream
+    when WGRAD_OVERLAP is on: the weight-gradient GEMM AND the bias column sum (a bandwidth-bound pass over dy that
+    nothing downstream waits for; on the main stream it was 374 launches / 9.7 ms of the SDXL step)."""
+    dw = db = None
+    wbuf, wbase = _grad_sink(weight) if need_w else (None, None)
+    bbuf, bbase = _grad_sink(bias) if (need_b and bias is not None) else (None, None)
+    jobs, bases = [], []
+    if need_w:
+        if wbuf is not None:
+            jobs.append(lambda: linear_wgrad(dy, x, out=wbuf))
+            bases.append(wbase)
+        else:
+            dw = linear_wgrad(dy, x)
+    if need_b and bias is not None:
+        if bbuf is not None:
+            jobs.append(lambda: colsum(dy, out=bbuf.view(1, -1)))
+            bases.append(bbase)
+        else:
+            db = colsum(dy)[0]
+    if jobs:
+        if WGRAD_OVERLAP:
+            _fork_wgrad(lambda: [j() for j in jobs], (dy, x), tuple(bases))
+        else:
+            for j in jobs:
+                j()
+            for b in bases:
+                GRAD_SINK.mark_ready(b)
+    return dw, db
+
+
+class FeedForwardGegluFn(torch.autograd.Function):
+    """y = (GEGLU(x W1^T + b1)) W2^T + b2 (+ residual) — `FeedForward` with `glu=True` (reference
+    modules/attention.py:50-74) as two GEMMs with the gate and its derivative fused into their epilogues:
+      forward   h, a = nk_linear_geglu_fwd(x, W1, b1)      (gate in the epilogue; h kept for the backward)
+                y    = nk_linear_fwd(a, W2, b2, residual)
+      backward  dh   = nk_linear_dgrad_geglu(dy, W2, h)    (d_a is never written)
+                dx   = nk_linear_dgrad(dh, W1)
+                dW2 = dy^T a, db2, dW1 = dh^T x, db1        (side stream, into the gradient buckets)"""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual):
+        h, a = linear_geglu_fwd(x, bf16_weight(w1), f32_param(b1))
+        y = linear_fwd(a, bf16_weight(w2), f32_param(b2), residual)
+        ctx.save_for_backward(x, h, a, w1, w2)
+        ctx.biases = (b1, b2)
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, h, a, w1, w2 = ctx.saved_tensors
+        b1, b2 = ctx.biases
+        if dy.dtype != BF16:
+            dy = cast_bf16(dy)
+        dy = dy.contiguous()
+        need = ctx.needs_input_grad
+        dh = linear_dgrad_geglu(dy, bf16_weight(w2), h)
+        dx = linear_dgrad(dh, bf16_weight(w1)) if need[0] else None
+        dw2, db2 = _linear_param_grads(dy, a, w2, b2, need[3], b2 is not None and need[4])
+        dw1, db1 = _linear_param_grads(dh, x, w1, b1, need[1], b1 is not None and need[2])
+        dres = dy if (ctx.has_res and need[5]) else None
+        return dx, dw1, db1, dw2, db2, dres
+
+
+def feed_forward_geglu(x: Tensor, w1: Tensor, b1: Optional[Tensor], w2: Tensor, b2: Optional[Tensor],
+                       residual: Optional[Tensor] = None) -> Tensor:
+    return FeedForwardGegluFn.apply(x, w1, b1, w2, b2, residual)
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b (+ residual); W, b are the fp32 parameters (reference layout [out, in])."""
 
@@ -953,25 +1057,9 @@ class LinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         w = bf16_weight(weight)
         dx = linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
-        dw = None
-        if ctx.needs_input_grad[1]:
-            buf, base = _grad_sink(weight)
-            if buf is not None:  # accumulate straight into the (zeroed) gradient bucket, no autograd "+=" pass
-                if WGRAD_OVERLAP:
-                    _fork_wgrad(lambda: linear_wgrad(dy, x, out=buf), (dy, x), (base,))
-                else:
-                    linear_wgrad(dy, x, out=buf)
-                    GRAD_SINK.mark_ready(base)
-            else:
-                dw = linear_wgrad(dy, x)
-        db = None
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            buf, base = _grad_sink(ctx.bias)
-            if buf is not None:
-                colsum(dy, out=buf.view(1, -1))
-                GRAD_SINK.mark_ready(base)
-            else:
-                db = colsum(dy)[0]
+        dw = db = None
+        dw, db = _linear_param_grads(dy, x, weight, ctx.bias if ctx.has_bias else None, ctx.needs_input_grad[1],
+                                     ctx.has_bias and ctx.needs_input_grad[2])
         dres = dy.view(-1, dy.shape[-1]).view(dy.shape) if (ctx.has_res and ctx.needs_input_grad[3]) else None
         return dx, dw, db, dres, None
 
@@ -992,6 +1080,7 @@ class Conv2dFn(torch.autograd.Function):
         y = conv2d_fwd(x, wf, co, ks, f32_param(bias), bias_img, residual)
         ctx.save_for_backward(x, weight)
         ctx.flags = (bias is not None, bias_img is not None, residual is not None)
+        ctx.bias_param = bias
         return y
 
     @staticmethod
@@ -1006,10 +1095,17 @@ class Conv2dFn(torch.autograd.Function):
             dx = conv2d_fwd(dy, wd, x.shape[-1], ks)
             if dx.shape[-1] != x.shape[-1]:
                 dx = dx[..., : x.shape[-1]].contiguous()
+        # plain bias (no per-image bias): its column sum joins the weight-gradient job on the side stream
+        bias_p = ctx.bias_param if (has_bias and not has_bimg and ctx.needs_input_grad[2]) else None
+        bbuf, bbase = _grad_sink(bias_p) if (bias_p is not None and dy.shape[-1] == co) else (None, None)
         if ctx.needs_input_grad[1]:
             buf, base = _grad_sink(weight)
             if buf is not None and WGRAD_OVERLAP:
-                _fork_wgrad(lambda: conv_unpack_wgrad(conv2d_wgrad(dy, x, co, ks), co, ci, ks, out=buf), (dy, x), (base,))
+                def job():
+                    conv_unpack_wgrad(conv2d_wgrad(dy, x, co, ks), co, ci, ks, out=buf)
+                    if bbuf is not None:
+                        colsum(dy, out=bbuf.view(1, -1))
+                _fork_wgrad(job, (dy, x), (base,) if bbuf is None else (base, bbase))
             else:
                 dwp = conv2d_wgrad(dy, x, co, ks)
                 if buf is not None:
@@ -1017,13 +1113,19 @@ class Conv2dFn(torch.autograd.Function):
                     GRAD_SINK.mark_ready(base)
                 else:
                     dw = conv_unpack_wgrad(dwp, co, ci, ks)
+                if bbuf is not None:
+                    colsum(dy, out=bbuf.view(1, -1))
+                    GRAD_SINK.mark_ready(bbase)
+        elif bbuf is not None:
+            colsum(dy, out=bbuf.view(1, -1))
+            GRAD_SINK.mark_ready(bbase)
         if (has_bias and ctx.needs_input_grad[2]) or (has_bimg and ctx.needs_input_grad[3]):
             if has_bimg and ctx.needs_input_grad[3]:
                 s = colsum(dy, groups=dy.shape[0])[:, :co]  # per-image sums (timestep-embedding gradient)
                 dbi = s.contiguous()
                 if has_bias and ctx.needs_input_grad[2]:
                     db = s.sum(0)  # O(batch x C) glue
-            elif has_bias and ctx.needs_input_grad[2]:
+            elif has_bias and ctx.needs_input_grad[2] and bbuf is None:
                 db = colsum(dy)[0, :co].contiguous()
         if has_res and ctx.needs_input_grad[4]:
             dres = dy

@@ -257,6 +257,54 @@ def test_geglu_fwd_bwd():
     assert rel(y, yr) < 4e-3 and rel(h.grad, hr.grad) < 6e-3
 
 
+@pytest.mark.parametrize("M,C,D", [(512, 320, 1280), (300, 640, 2560), (100, 64, 256), (640, 128, 64), (2048, 1280, 5120)])
+@pytest.mark.parametrize("use_sink", [False, True])
+def test_feed_forward_geglu_fused_epilogues(M, C, D, use_sink):
+    """FeedForward(glu=True) with the gate in the epilogue of the input projection and its derivative in the epilogue of
+    the output projection's data-gradient GEMM (reference modules/attention.py:50-74) against torch fp32, including a
+    single-row-tile problem (M = 100: one CTA loads both halves of the B tile), ragged rows and D < 128 (narrow tile)."""
+    from neurosis_b200.ddp import BucketedGradReducer
+    x = rnd(M, C).to(BF).requires_grad_(True)
+    w1 = torch.nn.Parameter(rnd(2 * D, C, seed=1) * C ** -0.5)
+    b1 = torch.nn.Parameter(rnd(2 * D, seed=2) * 0.1)
+    w2 = torch.nn.Parameter(rnd(C, D, seed=3) * D ** -0.5)
+    b2 = torch.nn.Parameter(rnd(C, seed=4) * 0.1)
+    res = rnd(M, C, seed=5).to(BF).requires_grad_(True)
+    gy = rnd(M, C, seed=6).to(BF)
+    ps = [w1, b1, w2, b2]
+    red = BucketedGradReducer(ps, bucket_mb=64.0) if use_sink else None
+    if red is not None:
+        red.attach_as_grad_sink()
+        red.zero_grad()
+    try:
+        y = ops.feed_forward_geglu(x, w1, b1, w2, b2, res)
+        y.backward(gy)
+        if red is not None:
+            red.finish()
+        torch.cuda.synchronize()
+    finally:
+        if red is not None:
+            red.detach_grad_sink()
+    xr, rr = x.detach().float().requires_grad_(True), res.detach().float().requires_grad_(True)
+    pr = [p.detach().clone().requires_grad_(True) for p in ps]
+    h = F.linear(xr, pr[0].to(BF).float(), pr[1])
+    a, gate = h.chunk(2, dim=-1)
+    yr = F.linear(a * F.gelu(gate), pr[2].to(BF).float(), pr[3]) + rr
+    yr.backward(gy.float())
+    assert rel(y, yr) < 8e-3
+    assert rel(x.grad, xr.grad) < 1.5e-2 and rel(res.grad, rr.grad) < 1e-6
+    for p, q, name in zip(ps, pr, ("w1", "b1", "w2", "b2")):
+        assert rel(p.grad, q.grad) < 1.5e-2, name
+    # and the two raw entry points against the unfused kernels they replace (same bf16 rounding points: tight)
+    hb, ab = ops.linear_geglu_fwd(x.detach(), ops.cast_bf16(w1.detach()), b1.detach())
+    h_ref = ops.linear_fwd(x.detach(), ops.cast_bf16(w1.detach()), b1.detach())
+    assert torch.equal(hb, h_ref)
+    assert rel(ab, ops.geglu_fwd(h_ref)) < 1e-6
+    d_a = ops.linear_dgrad(gy, ops.cast_bf16(w2.detach()))
+    dh = ops.linear_dgrad_geglu(gy, ops.cast_bf16(w2.detach()), h_ref)
+    assert rel(dh, ops.geglu_bwd(h_ref, d_a)) < 6e-3  # (the unfused path rounds d_a to bf16 in between)
+
+
 def test_silu_add_cat_upsample():
     x = rnd(4, 1280).to(BF).requires_grad_(True)
     y = ops.silu(x)
