@@ -36,9 +36,23 @@ constexpr int ACC_STRIDE = 256;
 // and N = 256 (measured), so pixel-major tiles with N = Cout = 128 run the tensor pipe at half rate.
 enum { MODE_PLAIN = 0, MODE_CONV_FWD = 1, MODE_CONV_WGRAD = 2, MODE_CONV_FWD_T = 3 };
 
+// barrier of one epilogue warp-half (4 warps) with a compile-time barrier id: a register id makes ptxas reserve all 16
+// hardware barriers, and such a kernel fails to launch ("too many resources requested")
+__device__ __forceinline__ void half_bar_sync(int half) {
+    if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+
+constexpr int STG_BYTES = 128 * 128;  // one staging tile of the TMA-store epilogue: 128 rows x 128 bytes, 128B-swizzled
+
 struct alignas(64) GemmDev {
     CUtensorMap tmA;
     CUtensorMap tmB;
+    CUtensorMap tmC;   // output tile store (tma_out): bf16 boxes {64 cols, rows} / fp32 boxes {32 cols, rows}
+    CUtensorMap tmC2;  // EPI_GEGLU_FWD: the gated output [M, D]
+    int tma_out;       // 1: the epilogue stages 128-byte-wide column groups in shared memory and stores them with TMA
+    int stg_per_half;  // staging tiles per epilogue warp-half
+    int has_c;         // EPI_GEGLU_FWD: h is stored as well
     int M, N;
     int BN;
     int tiles_m, tiles_n, nb2, nb1, splits;  // tiles_m counts (CG*128)-row tiles
@@ -129,7 +143,8 @@ __device__ __forceinline__ void add_vec16(float (&v)[16], const float* p, bool f
 // VAR selects an epilogue family that lives in its own instantiation (so that its register pressure cannot spill into the
 // main kernel): 0 = general, 1 = MODE_CONV_FWD_T (transposed convolution), 2 = EPI_GEGLU_FWD, 3 = EPI_GEGLU_BWD
 enum { VAR_MAIN = 0, VAR_TRANSPOSED = 1, VAR_GEGLU_FWD = 2, VAR_GEGLU_BWD = 3 };
-template <int CG, int VAR = VAR_MAIN>
+// TMA_OUT: the epilogue leaves through shared-memory staging tiles and TMA stores (g.tma_out says the same at run time)
+template <int CG, int VAR = VAR_MAIN, bool TMA_OUT = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmDev g) {
     constexpr bool TRANSPOSED = VAR == VAR_TRANSPOSED;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -144,7 +159,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const int group = blockIdx.x / CG;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + static_cast<size_t>(stages) * A_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + static_cast<size_t>(stages) * b_stage_bytes);
+    uint8_t* smem_stg = smem_b + static_cast<size_t>(stages) * b_stage_bytes;  // 1024-aligned (stage sizes are multiples of 2 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + (TMA_OUT ? 2 * g.stg_per_half * STG_BYTES : 0));
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + stages;
     uint64_t* tmem_full = bars + 2 * stages;
@@ -390,12 +406,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int c_begin = half ? (nch + 1) / 2 : 0;
         const int c_end = half ? nch : (nch + 1) / 2;
         int local = 0;
+        int stg_it = 0;  // staging-buffer alternation of the TMA-store epilogue (runs across tiles)
+        const bool st_elected = (((warp - 2) & 3) == 0) && lane == 0;  // the thread of this warp-half that issues TMA stores
         long long dbg_wait = 0, dbg_proc = 0;
         for (int t = group; t < total_tiles; t += num_groups, ++local) {
             const TileCoord tc = decode_tile(g, t);
             const int n0 = tc.nt * g.BN;
             const int mt = tc.mt * CG + static_cast<int>(rank);
             const int acc = local & 1;
+            // coordinates of this CTA's output tile in the store tensor map (dims 1..3)
+            int sc1, sc2, sc3;
+            if (g.mode == MODE_CONV_FWD) {
+                sc1 = (mt % g.tiles_w) * g.bw;
+                sc2 = ((mt / g.tiles_w) % g.tiles_h) * g.bh;
+                sc3 = mt / (g.tiles_w * g.tiles_h);
+            } else {
+                sc1 = mt * BM;
+                sc2 = tc.b2;
+                sc3 = tc.b1;
+            }
+            const bool tile_ok = mt < g.tiles_m128;  // the odd last 128-row tile of a CTA pair stores nothing
             // output row of this thread
             long long row = 0;
             bool row_ok = false;
@@ -447,7 +477,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     sb = __ldg(sp + 1);
                 }
             };
-            auto process = [&](int c, const uint32_t (&raw)[16], const uint4& sa, const uint4& sb) {
+            // stg != nullptr: the 16 results go to row r of a 128B-swizzled staging tile (chunk `cig` of its column group)
+            // and leave through a TMA store; rows / columns outside the problem are clipped by the TMA unit
+            auto process = [&](int c, const uint32_t (&raw)[16], const uint4& sa, const uint4& sb, uint8_t* stg = nullptr,
+                               int cig = 0) {
                 const int n = n0 + c * 16;
                 if (!row_ok || n >= g.N) return;
                 float v[16];
@@ -488,6 +521,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     for (int j = 0; j < 16; ++j) v[j] = sv[j] * (v[j] - rv) * g.alpha;
                 }
                 // ---- store ----
+                if (TMA_OUT) {
+                    const uint32_t rowaddr = smem_u32(stg) + static_cast<uint32_t>(r * 128);
+                    const uint32_t sw = static_cast<uint32_t>(r & 7);
+                    if (g.out == OUT_BF16) {
+                        const uint32_t j0 = static_cast<uint32_t>(2 * cig);
+                        st_shared_v4(rowaddr + ((j0 ^ sw) << 4),
+                                     make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                                pack_bf16x2(v[6], v[7])));
+                        st_shared_v4(rowaddr + (((j0 + 1) ^ sw) << 4),
+                                     make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                                pack_bf16x2(v[14], v[15])));
+                    } else {
+                        const uint32_t j0 = static_cast<uint32_t>(4 * cig);
+#pragma unroll
+                        for (uint32_t j = 0; j < 4; ++j)
+                            st_shared_v4(rowaddr + (((j0 + j) ^ sw) << 4),
+                                         make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                    __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+                    }
+                    return;
+                }
                 if (g.out == OUT_BF16) {
                     bf16* cp = reinterpret_cast<bf16*>(g.C) + boff + row * g.ldc + n;
                     if (full && ((reinterpret_cast<uintptr_t>(cp) & 15u) == 0)) {
@@ -675,7 +729,80 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     reinterpret_cast<uint4*>(orow + n)[0] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
                     reinterpret_cast<uint4*>(orow + n)[1] = make_uint4(ov[4], ov[5], ov[6], ov[7]);
                 };
-                if (cb < ce) {
+                if constexpr (TMA_OUT) {
+                    // value column groups of 64: three staging tiles per group (h value part, h gate part, gated output)
+                    const int ng = nx / 4;
+                    const int gb = half ? (ng + 1) / 2 : 0, ge = half ? ng : (ng + 1) / 2;
+                    uint8_t* t_hv = smem_stg + static_cast<size_t>(half * 3) * STG_BYTES;
+                    uint8_t* t_hg = t_hv + STG_BYTES;
+                    uint8_t* t_o = t_hg + STG_BYTES;
+                    const uint32_t rowoff = static_cast<uint32_t>(r * 128), sw = static_cast<uint32_t>(r & 7);
+                    for (int gi = gb; gi < ge; ++gi) {
+                        uint32_t ax[16], ag[16], bx[16], bg[16];
+                        ld2(gi * 4, ax, ag);
+                        if (st_elected) tma_wait_group_read<0>();
+                        half_bar_sync(half);
+                        auto emit = [&](int cig, const uint32_t (&rx)[16], const uint32_t (&rg)[16]) {
+                            const int n = n0x + (gi * 4 + cig) * 16;
+                            if (!row_ok || n >= D) return;
+                            float v[16], tt[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                v[j] = __uint_as_float(rx[j]);
+                                tt[j] = __uint_as_float(rg[j]);
+                            }
+                            if (g.bias) {
+                                add_vec16(v, g.bias + n, true, 16);
+                                add_vec16(tt, g.bias + D + n, true, 16);
+                            }
+                            uint32_t hv[8], hg[8], ov[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                hv[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                                hg[j] = pack_bf16x2(tt[2 * j], tt[2 * j + 1]);
+                                const float2 a = unpack_bf16x2(hv[j]), b = unpack_bf16x2(hg[j]);
+                                ov[j] = pack_bf16x2(a.x * gelu_erf(b.x), a.y * gelu_erf(b.y));
+                            }
+                            const uint32_t o0 = rowoff + (((2u * cig) ^ sw) << 4), o1 = rowoff + (((2u * cig + 1u) ^ sw) << 4);
+                            if (g.has_c) {
+                                st_shared_v4(smem_u32(t_hv) + o0, make_uint4(hv[0], hv[1], hv[2], hv[3]));
+                                st_shared_v4(smem_u32(t_hv) + o1, make_uint4(hv[4], hv[5], hv[6], hv[7]));
+                                st_shared_v4(smem_u32(t_hg) + o0, make_uint4(hg[0], hg[1], hg[2], hg[3]));
+                                st_shared_v4(smem_u32(t_hg) + o1, make_uint4(hg[4], hg[5], hg[6], hg[7]));
+                            }
+                            st_shared_v4(smem_u32(t_o) + o0, make_uint4(ov[0], ov[1], ov[2], ov[3]));
+                            st_shared_v4(smem_u32(t_o) + o1, make_uint4(ov[4], ov[5], ov[6], ov[7]));
+                        };
+                        tc_wait_ld16(ax);
+                        tc_wait_ld16(ag);
+                        ld2(gi * 4 + 1, bx, bg);
+                        emit(0, ax, ag);
+                        tc_wait_ld16(bx);
+                        tc_wait_ld16(bg);
+                        ld2(gi * 4 + 2, ax, ag);
+                        emit(1, bx, bg);
+                        tc_wait_ld16(ax);
+                        tc_wait_ld16(ag);
+                        ld2(gi * 4 + 3, bx, bg);
+                        emit(2, ax, ag);
+                        tc_wait_ld16(bx);
+                        tc_wait_ld16(bg);
+                        emit(3, bx, bg);
+                        fence_proxy_async_smem();
+                        half_bar_sync(half);
+                        if (st_elected) {
+                            const int col = n0x + gi * 64;
+                            if (tile_ok && col < D) {
+                                if (g.has_c) {
+                                    tma_store_4d(&g.tmC, t_hv, col, sc1, sc2, sc3);
+                                    tma_store_4d(&g.tmC, t_hg, D + col, sc1, sc2, sc3);
+                                }
+                                tma_store_4d(&g.tmC2, t_o, col, sc1, sc2, sc3);
+                            }
+                            tma_commit_group();
+                        }
+                    }
+                } else if (cb < ce) {
                     uint32_t ax[16], ag[16], bx[16], bg[16];
                     ld2(cb, ax, ag);
                     for (int c = cb; c < ce; c += 2) {
@@ -709,7 +836,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         hg[1] = __ldg(pg + 1);
                     }
                 };
-                auto proc_b = [&](int c, const uint32_t (&raw)[16], const uint4 (&hx)[2], const uint4 (&hg)[2]) {
+                auto proc_b = [&](int c, const uint32_t (&raw)[16], const uint4 (&hx)[2], const uint4 (&hg)[2],
+                                  uint8_t* stg = nullptr, int cig = 0) {
                     const int n = n0 + c * 16;
                     if (!row_ok || n >= D) return;
                     const uint32_t wx[8] = {hx[0].x, hx[0].y, hx[0].z, hx[0].w, hx[1].x, hx[1].y, hx[1].z, hx[1].w};
@@ -722,12 +850,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         da[j] = pack_bf16x2(d0 * gelu_erf(b.x), d1 * gelu_erf(b.y));
                         dg[j] = pack_bf16x2(d0 * a.x * dgelu_erf(b.x), d1 * a.y * dgelu_erf(b.y));
                     }
+                    if (TMA_OUT) {  // tile 0: value-part gradient, tile 1: gate-part gradient
+                        const uint32_t rowoff = smem_u32(stg) + static_cast<uint32_t>(r * 128), sw = static_cast<uint32_t>(r & 7);
+                        const uint32_t o0 = rowoff + (((2u * cig) ^ sw) << 4), o1 = rowoff + (((2u * cig + 1u) ^ sw) << 4);
+                        st_shared_v4(o0, make_uint4(da[0], da[1], da[2], da[3]));
+                        st_shared_v4(o1, make_uint4(da[4], da[5], da[6], da[7]));
+                        st_shared_v4(o0 + STG_BYTES, make_uint4(dg[0], dg[1], dg[2], dg[3]));
+                        st_shared_v4(o1 + STG_BYTES, make_uint4(dg[4], dg[5], dg[6], dg[7]));
+                        return;
+                    }
                     reinterpret_cast<uint4*>(drow + n)[0] = make_uint4(da[0], da[1], da[2], da[3]);
                     reinterpret_cast<uint4*>(drow + n)[1] = make_uint4(da[4], da[5], da[6], da[7]);
                     reinterpret_cast<uint4*>(drow + D + n)[0] = make_uint4(dg[0], dg[1], dg[2], dg[3]);
                     reinterpret_cast<uint4*>(drow + D + n)[1] = make_uint4(dg[4], dg[5], dg[6], dg[7]);
                 };
-                if (c_begin < c_end) {
+                if constexpr (TMA_OUT) {
+                    const int ng = g.BN / 64;
+                    const int gb = half ? (ng + 1) / 2 : 0, ge = half ? ng : (ng + 1) / 2;
+                    uint8_t* buf = smem_stg + static_cast<size_t>(half * 2) * STG_BYTES;
+                    for (int gi = gb; gi < ge; ++gi) {
+                        uint32_t r0[16], r1[16];
+                        uint4 x0[2], g0[2], x1[2], g1[2];
+                        issue_b(gi * 4, r0, x0, g0);
+                        if (st_elected) tma_wait_group_read<0>();
+                        half_bar_sync(half);
+#pragma unroll
+                        for (int cc = 0; cc < 4; cc += 2) {
+                            tc_wait_ld16(r0);
+                            issue_b(gi * 4 + cc + 1, r1, x1, g1);
+                            proc_b(gi * 4 + cc, r0, x0, g0, buf, cc);
+                            tc_wait_ld16(r1);
+                            if (cc + 2 < 4) issue_b(gi * 4 + cc + 2, r0, x0, g0);
+                            proc_b(gi * 4 + cc + 1, r1, x1, g1, buf, cc + 1);
+                        }
+                        fence_proxy_async_smem();
+                        half_bar_sync(half);
+                        if (st_elected) {
+                            const int col = n0 + gi * 64;
+                            if (tile_ok && col < D) {
+                                tma_store_4d(&g.tmC, buf, col, sc1, sc2, sc3);
+                                tma_store_4d(&g.tmC, buf + STG_BYTES, D + col, sc1, sc2, sc3);
+                            }
+                            tma_commit_group();
+                        }
+                    }
+                } else if (c_begin < c_end) {
                     uint32_t r0[16], r1[16];
                     uint4 x0[2], g0[2], x1[2], g1[2];
                     issue_b(c_begin, r0, x0, g0);
@@ -740,6 +907,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                             if (c + 2 < c_end) issue_b(c + 2, r0, x0, g0);
                             proc_b(c + 1, r1, x1, g1);
                         }
+                    }
+                }
+            } else if constexpr (TMA_OUT) {
+                // 128-byte-wide column groups (64 bf16 / 32 fp32 columns): TMEM -> registers -> swizzled staging tile ->
+                // ONE TMA store (or reduce-add) per group, double buffered per warp-half.  Replaces per-thread 32-byte
+                // global stores whose 32 lanes hit 32 different rows (32 LSU wavefronts per instruction).
+                const int gw = (g.out == OUT_BF16) ? 64 : 32;
+                const int cpg = gw / 16;
+                const int ng = g.BN / gw;
+                const int gb = half ? (ng + 1) / 2 : 0, ge = half ? ng : (ng + 1) / 2;
+                for (int gi = gb; gi < ge; ++gi, ++stg_it) {
+                    uint8_t* buf = smem_stg + static_cast<size_t>(half * 2 + (stg_it & 1)) * STG_BYTES;
+                    const int c0 = gi * cpg;
+                    uint32_t r0[16], r1[16];
+                    uint4 s0a = make_uint4(0, 0, 0, 0), s0b = s0a, s1a = s0a, s1b = s0a;
+                    issue(c0, r0, s0a, s0b);
+                    if (st_elected) tma_wait_group_read<1>();  // the store issued two groups ago has released this buffer
+                    half_bar_sync(half);
+                    for (int c = c0; c < c0 + cpg; c += 2) {
+                        tc_wait_ld16(r0);
+                        issue(c + 1, r1, s1a, s1b);
+                        process(c, r0, s0a, s0b, buf, c - c0);
+                        tc_wait_ld16(r1);
+                        if (c + 2 < c0 + cpg) issue(c + 2, r0, s0a, s0b);
+                        process(c + 1, r1, s1a, s1b, buf, c + 1 - c0);
+                    }
+                    fence_proxy_async_smem();
+                    half_bar_sync(half);
+                    if (st_elected) {
+                        const int col = n0 + gi * gw;
+                        if (tile_ok && col < g.N) {
+                            if (g.out == OUT_F32_ATOMIC) tma_reduce_add_4d(&g.tmC, buf, col, sc1, sc2, sc3);
+                            else tma_store_4d(&g.tmC, buf, col, sc1, sc2, sc3);
+                        }
+                        tma_commit_group();
                     }
                 }
             } else if (c_begin < c_end) {
@@ -767,6 +969,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 dbg_proc += clock64() - te1;
             }
         }
+        if (TMA_OUT && st_elected) tma_wait_group<0>();  // shared memory must outlive the last store
         if (g.dbg && warp == 2 && lane == 0) {
             g.dbg[blockIdx.x * 8 + 4] = dbg_wait;
             g.dbg[blockIdx.x * 8 + 5] = dbg_proc;
@@ -827,7 +1030,7 @@ int make_operand_tmap(CUtensorMap* tm, const GemmOperand& o, int box_rows_or_bw,
 }
 
 // tile width (and CTA-group size) minimising waves x per-k16 cost.  `groups` = CTA groups that run concurrently.
-int pick_bn(const GemmProblem& p, long long tiles_m_batches, int groups, int cg) {
+int pick_bn(const GemmProblem& p, long long tiles_m_batches, int groups, int cg, int min_step = 1) {
     if (p.force_bn > 0) return p.force_bn;
     static int env_bn = -1;
     if (env_bn < 0) {
@@ -835,7 +1038,8 @@ int pick_bn(const GemmProblem& p, long long tiles_m_batches, int groups, int cg)
         env_bn = e_ ? atoi(e_) : 0;
     }
     if (env_bn > 0) return env_bn;
-    const int step = p.B.mn_major ? 64 * cg : 16 * cg;
+    int step = p.B.mn_major ? 64 * cg : 16 * cg;
+    while (step % min_step != 0) step += p.B.mn_major ? 64 * cg : 16 * cg;  // TMA-store epilogue: whole column groups
     long long best_cost = -1;
     int best = 256;
     for (int bn = 256; bn >= step; bn -= step) {
@@ -901,9 +1105,39 @@ static int debug_report(const GemmProblem& p, const GemmDev& g, int cg, long lon
     return NK_OK;
 }
 
+// tensor map of an output matrix for the TMA-store epilogue: boxes of one 128-byte column group x the tile's rows
+static int make_out_tmap(CUtensorMap* tm, const void* ptr, int is_f32, long long ncols, long long ld, const GemmDev& g,
+                         const GemmProblem& p) {
+    const uint64_t es = is_f32 ? 4 : 2;
+    uint64_t dims[4], strides[3];
+    uint32_t box[4];
+    dims[0] = static_cast<uint64_t>(ncols);
+    strides[0] = static_cast<uint64_t>(ld) * es;
+    box[0] = is_f32 ? 32 : 64;
+    if (g.mode == MODE_CONV_FWD) {
+        dims[1] = static_cast<uint64_t>(g.cW);
+        dims[2] = static_cast<uint64_t>(g.cH);
+        dims[3] = static_cast<uint64_t>(p.A.nimg);
+        strides[1] = strides[0] * dims[1];
+        strides[2] = strides[1] * dims[2];
+        box[1] = static_cast<uint32_t>(g.bw);
+        box[2] = static_cast<uint32_t>(g.bh);
+        box[3] = 1;
+    } else {
+        dims[1] = static_cast<uint64_t>(p.M);
+        dims[2] = static_cast<uint64_t>(g.nb2);
+        dims[3] = static_cast<uint64_t>(g.nb1);
+        strides[1] = (g.nb2 > 1 ? static_cast<uint64_t>(p.c_b2_stride) : static_cast<uint64_t>(ld) * dims[1]) * es;
+        strides[2] = (g.nb1 > 1 ? static_cast<uint64_t>(p.c_b1_stride) : static_cast<uint64_t>(ld) * dims[1] * dims[2]) * es;
+        box[1] = BM;
+        box[2] = 1;
+        box[3] = 1;
+    }
+    return encode_tmap(tm, ptr, 4, dims, strides, box, is_f32);
+}
+
 int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     static int nsm = 0;
-    static bool attr_set = false;
     if (nsm == 0) nsm = device_sm_count();
     NK_REQUIRE(nsm > 0, NK_ERR_CUDA, "no CUDA device");
     NK_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, NK_ERR_SHAPE, "gemm: empty problem %d %d %d", p.M, p.N, p.K);
@@ -1014,11 +1248,6 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
         const int max_smem_t = 227 * 1024;
         g.stages = std::max(2, std::min((max_smem_t - 1024 - 256) / stage_bytes_t, 8));
         const int smem_t = g.stages * stage_bytes_t + 1024 + (2 * g.stages + 5) * 8;
-        if (!attr_set) {
-            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_t));
-            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_t));
-            attr_set = true;
-        }
         static bool attr_t_set = false;
         if (!attr_t_set) {
             NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, VAR_TRANSPOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_t));
@@ -1045,8 +1274,26 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     g.tiles_m = (g.tiles_m128 + cg - 1) / cg;
 
     const long long tiles_mb = static_cast<long long>(g.tiles_m) * g.nb2 * g.nb1;
-    g.BN = pick_bn(p, tiles_mb, nsm / cg, cg);
     const bool geglu_fwd = p.epi == EPI_GEGLU_FWD, geglu_bwd = p.epi == EPI_GEGLU_BWD;
+    // TMA-store epilogue (NK_GEMM_TMA_OUT=0: A/B switch back to per-thread global stores): needs 16-byte aligned rows
+    static int env_tma_out = -1;
+    if (env_tma_out < 0) {
+        const char* e_ = getenv("NK_GEMM_TMA_OUT");
+        env_tma_out = e_ ? atoi(e_) : 1;
+    }
+    const int out_es = p.out == OUT_BF16 ? 2 : 4;
+    const int gw_out = p.out == OUT_BF16 ? 64 : 32;
+    auto aligned16 = [](const void* ptr, long long ld_bytes) {
+        return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 && (ld_bytes & 15) == 0;
+    };
+    bool tma_out = env_tma_out != 0 && (p.epi == EPI_LINEAR || geglu_fwd || geglu_bwd) &&
+                   (g.mode == MODE_PLAIN || g.mode == MODE_CONV_FWD || g.mode == MODE_CONV_WGRAD) &&
+                   (p.C == nullptr ? geglu_fwd : aligned16(p.C, p.ldc * out_es)) &&
+                   (g.nb2 <= 1 || (p.c_b2_stride * out_es) % 16 == 0) && (g.nb1 <= 1 || (p.c_b1_stride * out_es) % 16 == 0) &&
+                   (!geglu_fwd || (aligned16(p.C2, p.ldc2 * 2) && p.N % 64 == 0)) && (!geglu_bwd || p.N % 64 == 0) &&
+                   (p.force_bn <= 0 || p.force_bn % ((geglu_fwd ? 2 : 1) * gw_out) == 0);
+    g.BN = pick_bn(p, tiles_mb, nsm / cg, cg, tma_out ? gw_out : 1);
+    if (tma_out && g.BN % gw_out != 0) tma_out = false;  // NK_GEMM_FORCE_BN experiments
     if (geglu_fwd || geglu_bwd) {
         NK_REQUIRE(g.mode == MODE_PLAIN && !p.A.mn_major && p.nb1 <= 1 && p.nb2 <= 1 && p.out == OUT_BF16, NK_ERR_UNSUPPORTED,
                    "GEGLU epilogues: plain bf16 GEMM only");
@@ -1154,54 +1401,71 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     NK_REQUIRE(p.epi != EPI_DSOFTMAX || (p.aux && p.rowvec), NK_ERR_SHAPE, "dsoftmax needs aux+rowvec");
     NK_REQUIRE(p.epi != EPI_EXP2 || p.rowvec, NK_ERR_SHAPE, "exp2 epilogue needs rowvec");
 
+    g.tma_out = tma_out ? 1 : 0;
+    g.stg_per_half = geglu_fwd ? 3 : 2;
+    g.has_c = p.C != nullptr;
+    if (tma_out) {
+        if (p.C != nullptr) {
+            e = make_out_tmap(&g.tmC, p.C, p.out != OUT_BF16, (geglu_fwd || geglu_bwd) ? 2LL * p.N : p.N, p.ldc, g, p);
+            if (e) return e;
+        }
+        if (geglu_fwd) {
+            e = make_out_tmap(&g.tmC2, p.C2, 0, p.N, p.ldc2, g, p);
+            if (e) return e;
+        }
+    }
+    const int staging_bytes = tma_out ? 2 * g.stg_per_half * STG_BYTES : 0;
     const int stage_bytes = A_STAGE_BYTES + bnc * 128;
     const int max_smem = 227 * 1024;
-    int stages = (max_smem - 1024 - 256) / stage_bytes;
+    int stages = (max_smem - 1024 - 256 - staging_bytes) / stage_bytes;
     stages = std::max(2, std::min(stages, 8));
     g.stages = stages;
-    const int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 5) * 8;
-    if (!attr_set) {
-        NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_set = true;
-    }
+    const int smem_bytes = stages * stage_bytes + staging_bytes + 1024 /*align slack*/ + (2 * stages + 5) * 8;
     const long long total = tiles_mb * g.tiles_n * g.splits;
     NK_REQUIRE(total < (1LL << 31), NK_ERR_SHAPE, "too many tiles");
     g.dbg = dbg_buf;
     if (dbg_buf) NK_CUDA(cudaMemsetAsync(dbg_buf, 0, 8 * 1024 * sizeof(long long), stream));
-    if (geglu_fwd || geglu_bwd) {
-        static bool attr_g_set = false;
-        if (!attr_g_set) {
-            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, VAR_GEGLU_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2, VAR_GEGLU_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, VAR_GEGLU_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-            NK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2, VAR_GEGLU_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-            attr_g_set = true;
+    // kernel instantiation: CTA-group size x epilogue family x TMA-store epilogue
+    const void* fn = nullptr;
+    {
+        const int var = geglu_fwd ? VAR_GEGLU_FWD : (geglu_bwd ? VAR_GEGLU_BWD : VAR_MAIN);
+#define NK_PICK(CGV, VARV, TMAV) \
+    if (cg == CGV && var == VARV && tma_out == TMAV) fn = reinterpret_cast<const void*>(&gemm_tc_kernel<CGV, VARV, TMAV>);
+        NK_PICK(1, VAR_MAIN, false) NK_PICK(2, VAR_MAIN, false) NK_PICK(1, VAR_MAIN, true) NK_PICK(2, VAR_MAIN, true)
+        NK_PICK(1, VAR_GEGLU_FWD, false) NK_PICK(2, VAR_GEGLU_FWD, false) NK_PICK(1, VAR_GEGLU_FWD, true)
+        NK_PICK(2, VAR_GEGLU_FWD, true) NK_PICK(1, VAR_GEGLU_BWD, false) NK_PICK(2, VAR_GEGLU_BWD, false)
+        NK_PICK(1, VAR_GEGLU_BWD, true) NK_PICK(2, VAR_GEGLU_BWD, true)
+#undef NK_PICK
+    }
+    NK_REQUIRE(fn != nullptr, NK_ERR_UNSUPPORTED, "no kernel instantiation");
+    {
+        static const void* attr_done[16];
+        static int n_attr_done = 0;
+        bool seen = false;
+        for (int i = 0; i < n_attr_done; ++i) seen = seen || attr_done[i] == fn;
+        if (!seen) {
+            NK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            if (n_attr_done < 16) attr_done[n_attr_done++] = fn;
         }
     }
-    if (cg == 1) {
-        const int grid = static_cast<int>(std::min<long long>(total, nsm));
-        if (geglu_fwd) gemm_tc_kernel<1, VAR_GEGLU_FWD><<<grid, NUM_THREADS, smem_bytes, stream>>>(g);
-        else if (geglu_bwd) gemm_tc_kernel<1, VAR_GEGLU_BWD><<<grid, NUM_THREADS, smem_bytes, stream>>>(g);
-        else gemm_tc_kernel<1><<<grid, NUM_THREADS, smem_bytes, stream>>>(g);
-    } else {
-        const int grid = 2 * static_cast<int>(std::min<long long>(total, nsm / 2));
+    {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
+        const int grid = cg == 1 ? static_cast<int>(std::min<long long>(total, nsm))
+                                 : 2 * static_cast<int>(std::min<long long>(total, nsm / 2));
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(NUM_THREADS);
         cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.x = cg;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (geglu_fwd) NK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, VAR_GEGLU_FWD>, g));
-        else if (geglu_bwd) NK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, VAR_GEGLU_BWD>, g));
-        else NK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, g));
+        void* args[1] = {const_cast<GemmDev*>(&g)};
+        NK_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
     }
     NK_CUDA(cudaGetLastError());
     if (dbg_buf) return debug_report(p, g, cg, total, nsm, dbg_buf, stream);
