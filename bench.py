@@ -31,10 +31,33 @@ SDXL_UNET = dict(in_channels=4, model_channels=320, out_channels=4, num_res_bloc
                  spatial_transformer_attn_type="b200", use_checkpoint=False)  # configs/sdxl/sdxl.example.yaml:68-84
 SDXL_VAE = dict(ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], in_channels=3,
                 resolution=256, z_channels=4, double_z=True)                    # configs/sdxl/sdxl.example.yaml:102-113
+SD15_UNET = dict(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=[4, 2, 1],
+                 channel_mult=[1, 2, 4, 4], num_heads=8, transformer_depth=1, context_dim=768,
+                 use_linear_in_transformer=False, spatial_transformer_attn_type="b200",
+                 use_checkpoint=False)  # configs/sd15/sd15.example.yml:68-81
 GFLOP_UNET_STEP = 20283.7   # per image, fwd + bwd (3x fwd), SURVEY.md §8d
 GFLOP_VAE_ENC = 4879.0      # per image, 1024^2 encode
 GFLOP_STEP = GFLOP_UNET_STEP + GFLOP_VAE_ENC
 METRIC = "sdxl_unet_train_images_per_sec_1024px_bf16"
+# BASELINE.json configs[1..4]: workload name, metric, algorithmic GFLOP per image and step
+CONFIGS = {
+    "sdxl": dict(family="sdxl", px=1024, batch=16, gflop=GFLOP_STEP, metric=METRIC,
+                 workload="SDXL base UNet (configs/sdxl) 1024x1024 training step: VAE encode + diffusion loss + backward"),
+    "sd15": dict(family="sd15", px=512, batch=32, gflop=2409.8 + 1116.7, metric="sd15_unet_train_images_per_sec_512px_bf16",
+                 workload="SD1.5 UNet (configs/sd15) 512x512 training step: VAE encode + diffusion loss + backward"),
+    "buckets": dict(family="sdxl", px=1024, batch=8, gflop=(25162.7 + (3 * 6644.9 + 4794.3) + (3 * 6499.9 + 4688.8)) / 3,
+                    metric="sdxl_aspect_bucket_train_images_per_sec_bf16",
+                    workload="SDXL aspect-bucketed batches (896x1152 / 1216x832 / 1024x1024, one bucket per rank and step) "
+                             "with tag-frequency loss scaling: VAE encode + diffusion loss + backward"),
+    "vae": dict(family="vae", px=1024, batch=2, gflop=46048.0, metric="vae_train_images_per_sec_1024px_bf16",
+                workload="AutoencoderKL (configs/vae) 1024x1024 training step: encoder + decoder forward/backward, L2 "
+                         "reconstruction loss (encode-only rate in config.encode_images_per_s)"),
+}
+
+
+# the UNMODIFIED reference under torch.autocast(bf16) on the same B200 (tools/stock_torch_bench.py, committed under
+# profiles/r02_stock_torch_*): images/s with use_checkpoint true (the example YAML) / false
+STOCK_TORCH = {"sdxl": {"use_checkpoint": 13.04, "no_checkpoint": 15.31, "source": "profiles/r02_stock_torch_vs_ours_b16.txt"}}
 
 
 def peaks() -> dict:
@@ -188,12 +211,20 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_sample(max(1, args.steps), max(0, args.warmup), budget_s=200.0)
-    line = {"impl": "reference", "metric": METRIC, "value": r["img_per_s"], "unit": "images/s", "n_gpus": args.gpus,
+    cfg = CONFIGS[args.config]
+    if cfg["family"] == "vae":
+        print(json.dumps({"impl": "reference", "metric": cfg["metric"], "unavailable":
+                          "the reference's VAE training step needs its LPIPS/discriminator loss stack (not vendored); its "
+                          "Encoder/Decoder fwd+bwd on host cores is timed by tests/cpu_baseline_next_rows.py "
+                          "(profiles/r01_next_rows_cpu_reference.log)"}), flush=True)
+        return
+    r = cpu_reference_sample(max(1, args.steps), max(0, args.warmup), budget_s=200.0, family=cfg["family"])
+    line = {"impl": "reference", "metric": cfg["metric"], "value": r["img_per_s"], "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_sample_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SDXL base UNet (configs/sdxl) 1024x1024 training step: VAE encode + diffusion loss + backward",
-                       "batch_per_gpu": args.batch, "global_batch": args.batch, "latent": "128x128x4", "parallelism": "dp1",
+            "config": {"workload": cfg["workload"],
+                       "batch_per_gpu": args.batch, "global_batch": args.batch, "latent": f"{cfg['px'] // 8}x{cfg['px'] // 8}x4",
+                       "parallelism": "dp1",
                        "note": "the reference's own CPU implementation of the path timed on the host cores; each step "
                                "is a bounded sample of the workload (see cpu_baseline.sample)"},
             "cpu_baseline": {"value": r["img_per_s"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"],
@@ -205,7 +236,7 @@ def run_reference(args) -> None:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def build_engine(dev, seed: int = 42):
+def build_engine(dev, seed: int = 42, family: str = "sdxl"):
     import torch
     from neurosis_b200.engine import DiffusionEngine
     from neurosis_b200.modules import UNetModel
@@ -217,7 +248,7 @@ def build_engine(dev, seed: int = 42):
 
     torch.manual_seed(seed)  # identical weights on every rank
     with torch.device(dev):
-        unet = UNetModel(**SDXL_UNET)
+        unet = UNetModel(**(SDXL_UNET if family == "sdxl" else SD15_UNET))
         enc = Encoder(**SDXL_VAE, embed_dim=4, standalone=True)
     with torch.no_grad():  # re-draw the zero-initialised layers, otherwise most gradients are identically zero
         for name, p in unet.named_parameters():
@@ -231,11 +262,254 @@ def build_engine(dev, seed: int = 42):
         def __call__(self, n, t=None):
             return super().__call__(n, None).clamp_min(0.03)
 
+    embedders = [IdentityEncoder(input_key="crossattn_emb")]
+    if family == "sdxl":
+        embedders.append(IdentityEncoder(input_key="vector_emb"))
     return DiffusionEngine(
-        unet, DiscreteDenoiser(EpsPreconditioning(), 1000, LegacyDDPMDiscretization()), enc,
-        GeneralConditioner([IdentityEncoder(input_key="crossattn_emb"), IdentityEncoder(input_key="vector_emb")]),
+        unet, DiscreteDenoiser(EpsPreconditioning(), 1000, LegacyDDPMDiscretization()), enc, GeneralConditioner(embedders),
         StandardDiffusionLoss(RandIdxSigma(LegacyDDPMDiscretization(), 1000), EpsWeighting()),
-        scale_factor=0.13025, vae_batch_size=None).to(dev)
+        scale_factor=0.13025 if family == "sdxl" else 0.18215, vae_batch_size=None).to(dev)
+
+# ------------------------------------------------------------------------------------------------
+# shared timing helpers of the --config buckets / vae arms
+# ------------------------------------------------------------------------------------------------
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return world, rank, local, dev
+
+
+def _timed(world, dev, k: int, fn) -> float:
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        fn()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def _finish(world) -> None:
+    if world > 1:  # see the tear-down note at the end of main()
+        import gc
+
+        import torch
+        import torch.distributed as dist
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
+def _burst_peak() -> float:
+    p = ROOT / "MEASURED_PEAKS.json"
+    return json.loads(p.read_text()).get("bf16_tflops", 1673.6) if p.exists() else 1590.0
+
+
+def run_buckets(args) -> None:
+    """BASELINE.json configs[3]: SDXL over mixed aspect buckets with tag-frequency loss scaling.  One captured step per
+    bucket shape (the three graphs share one memory pool); every step each rank draws its own bucket (single-bucket
+    batches, reference dataset/imagefolder/aspect.py:160-191), builds the size / crop conditioning vector on the device and
+    feeds the `TagFrequencyHook` weights of its captions into the fused weighted-MSE reduction."""
+    import torch
+    from neurosis_b200 import ops
+    from neurosis_b200.ddp import BucketedGradReducer
+    from neurosis_b200.graph import GraphedTrainStep
+    from neurosis_b200.modules.conditioner import ConcatTimestepEmbedderND
+    from neurosis_b200.modules.loss import TagFreqScale, TagFrequencyHook
+    from neurosis_b200.synthetic import SDXL_BUCKETS, AspectBucketBatches
+    cfg = CONFIGS["buckets"]
+    world, rank, local, dev = _dist_setup()
+    W = max(int(os.environ.get("NK_BENCH_MIN_WARMUP", "3")), args.warmup)
+    B = args.batch
+    eng = build_engine(dev)
+    reducer = BucketedGradReducer([p for p in eng.model.parameters() if p.requires_grad], bucket_mb=256.0)
+    reducer.attach_as_grad_sink()
+    data = AspectBucketBatches(B, rank=rank)
+    hook = TagFrequencyHook(alpha=0.2, beta=0.99, strength=1.0,
+                            freq_scale=TagFreqScale([[-1, 1.1], [100, 1.0], [1000, 0.95], [40000, 0.8]]))
+    fourier = ConcatTimestepEmbedderND(256)
+
+    def vector(batch: dict):
+        parts = [batch["pooled_emb"].to(dev, non_blocking=True)]
+        for k in ("original_size_as_tuple", "crop_coords_top_left", "target_size_as_tuple"):
+            parts.append(fourier(torch.tensor(batch[k], dtype=torch.float32).to(dev, non_blocking=True)).float())
+        return torch.cat(parts, 1)  # (B, 2816)
+
+    graphs, pool = {}, None
+    order = sorted(range(len(SDXL_BUCKETS)), key=lambda b: -SDXL_BUCKETS[b][0] * SDXL_BUCKETS[b][1])  # largest first
+    for b in order:
+        first = data(bucket=b)
+        graphs[b] = GraphedTrainStep(eng, reducer, first["image"].to(dev), first["crossattn_emb"].to(dev), vector(first),
+                                     warmup=1, pool=pool)
+        pool = graphs[b].pool
+        torch.cuda.synchronize()
+    # a fixed schedule of host batches (pinned), drawn per rank: the timed region copies them in every step
+    sched = []
+    for _ in range(max(args.steps, 8)):
+        bt = data()
+        sched.append({"bucket": bt["bucket"], "image": bt["image"].pin_memory(), "ctx": bt["crossattn_emb"].pin_memory(),
+                      "batch": bt, "caption": bt["caption"]})
+    h2d = sum(s_["image"].numel() * 4 + s_["ctx"].numel() * 4 + B * 1280 * 4 + B * 4 for s_ in sched[: args.steps]) // max(1, args.steps)
+    it = {"i": 0}
+
+    def step(read_loss: bool) -> float:
+        s_ = sched[it["i"] % len(sched)]
+        it["i"] += 1
+        w = torch.tensor(hook.sample_weights(s_["caption"]), dtype=torch.float32)
+        loss = graphs[s_["bucket"]].step(s_["image"], s_["ctx"], vector(s_["batch"]), weights=w)
+        return loss.item() if read_loss else 0.0
+
+    for _ in range(W):
+        step(False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    it["i"] = 0
+    ms_dev = _timed(world, dev, args.steps, lambda: step(False))
+    it["i"] = 0
+    ms_e2e = _timed(world, dev, args.steps, lambda: step(True))
+    clocks = sampler.stop() if sampler else None
+    # the same schedule with every rank on the square bucket: what the straggler effect of mixed buckets costs
+    sq = SDXL_BUCKETS.index((1024, 1024))
+    sq_batch = next((s_ for s_ in sched if s_["bucket"] == sq), None)
+    ms_sq = None
+    if sq_batch is not None:
+        w1 = torch.ones(B)
+        ms_sq = _timed(world, dev, args.steps, lambda: graphs[sq].step(sq_batch["image"], sq_batch["ctx"], None, weights=w1))
+    if rank == 0:
+        ips = world * B * args.steps / (ms_dev * 1e-3)
+        launches = sum(graphs[sched[i % len(sched)]["bucket"]].launches_per_replay for i in range(args.steps))
+        tfl = ips / world * cfg["gflop"] / 1e3
+        line = {"metric": cfg["metric"], "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": cfg["workload"] + (" + bucketed NCCL gradient all-reduce" if world > 1 else ""),
+                           "batch_per_gpu": B, "global_batch": B * world, "cuda_graph": "one per bucket, shared memory pool",
+                           "buckets_wh": SDXL_BUCKETS, "buckets_drawn_rank0": [s_["bucket"] for s_ in sched[: args.steps]],
+                           "tag_frequency_hook": "alpha 0.2, beta 0.99, Zipf(1.1) captions of 8-40 tags from a 50k vocabulary; "
+                                                 "weights enter the weighted-MSE reduction as a (B,) device buffer",
+                           "square_only_ms_per_step": None if ms_sq is None else ms_sq / args.steps,
+                           "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2",
+                           "step_tflop_algorithmic": cfg["gflop"] * B / 1e3},
+                "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"kernel": "whole step (tcgen05 GEMM / implicit-GEMM conv dominate, see --config sdxl)",
+                             "bound": "tensor", "achieved": tfl, "peak": peaks()["tflops"], "unit": "TFLOP/s",
+                             "frac": tfl / peaks()["tflops"], "frac_of_burst_peak": tfl / _burst_peak(), "traffic": None}}
+        print(json.dumps(line), flush=True)
+    graphs.clear()
+    _finish(world)
+
+
+def run_vae(args) -> None:
+    """BASELINE.json configs[4]: AutoencoderKL encode + VAE training step (encoder + decoder forward / backward, plain L2
+    reconstruction loss — the reference's LPIPS / discriminator losses are outside the hot path) at 1024^2."""
+    import torch
+    from neurosis_b200 import ops
+    from neurosis_b200.ddp import BucketedGradReducer
+    from neurosis_b200.modules.vae import AutoencoderKL, DiagonalGaussianRegularizer
+    cfg = CONFIGS["vae"]
+    world, rank, local, dev = _dist_setup()
+    W = max(int(os.environ.get("NK_BENCH_MIN_WARMUP", "3")), args.warmup)
+    B, px = args.batch, cfg["px"]
+    torch.manual_seed(42)
+    ae = AutoencoderKL(4, SDXL_VAE, regularizer=DiagonalGaussianRegularizer(sample=True)).to(dev)
+    reducer = BucketedGradReducer([p for p in ae.parameters() if p.requires_grad], bucket_mb=256.0)
+    reducer.attach_as_grad_sink()
+    g = torch.Generator().manual_seed(42 + rank)
+    host = (torch.rand(B, 3, px, px, generator=g) * 2 - 1).pin_memory()
+    resident = host.to(dev)
+    static = resident.clone()
+
+    def train_step(img) -> "torch.Tensor":
+        ops.refresh_weight_copies(force=True)
+        reducer.zero_grad()
+        loss = ae.training_step({"image": img})
+        loss.backward()
+        reducer.finish()
+        return loss
+
+    # eager warm-up on a side stream (the CUDA-graph recipe): autograd's AccumulateGrad nodes remember the stream they
+    # were created on, and the legacy default stream cannot take part in a capture
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    l0 = ops.LAUNCHES
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            train_step(static)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    launches_per_step = (ops.LAUNCHES - l0) // 2
+    graph, loss_buf = None, torch.zeros((), device=dev)
+    if not args.no_graph:
+        torch.cuda.empty_cache()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss_buf.copy_(train_step(static).detach())
+
+    def step(src, read_loss: bool) -> float:
+        if src is not None:
+            static.copy_(src, non_blocking=True)
+        if graph is not None:
+            graph.replay()
+            return loss_buf.item() if read_loss else 0.0
+        loss = train_step(static)
+        return loss.item() if read_loss else 0.0
+
+    for _ in range(W):
+        step(None, False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev = _timed(world, dev, args.steps, lambda: step(None, False))
+    ms_e2e = _timed(world, dev, args.steps, lambda: step(host, True))
+    with torch.no_grad():
+        ms_enc = _timed(world, dev, args.steps, lambda: ae.encode(resident))
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        ips = world * B * args.steps / (ms_dev * 1e-3)
+        tfl = ips / world * cfg["gflop"] / 1e3
+        line = {"metric": cfg["metric"], "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": cfg["workload"] + (" + bucketed NCCL gradient all-reduce" if world > 1 else ""),
+                           "batch_per_gpu": B, "global_batch": B * world, "cuda_graph": graph is not None,
+                           "encode_images_per_s": world * B * args.steps / (ms_enc * 1e-3),
+                           "encode_tflops_per_gpu": B * args.steps * GFLOP_VAE_ENC / 1e3 / (ms_enc * 1e-3),
+                           "parallelism": f"dp{world}", "l2": "activations (GBs per layer at 1024^2) >> 126 MB L2",
+                           "step_tflop_algorithmic": cfg["gflop"] * B / 1e3,
+                           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30},
+                "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
+                        "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+                "roofline": {"kernel": "whole step (implicit-GEMM convolutions dominate)", "bound": "tensor", "achieved": tfl,
+                             "peak": peaks()["tflops"], "unit": "TFLOP/s", "frac": tfl / peaks()["tflops"],
+                             "frac_of_burst_peak": tfl / _burst_peak(), "traffic": None}}
+        print(json.dumps(line), flush=True)
+    graph = None
+    _finish(world)
 
 
 def main() -> None:
@@ -243,7 +517,11 @@ def main() -> None:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("NK_BENCH_BATCH", "16")), help="images per GPU")
+    ap.add_argument("--config", default="sdxl", choices=sorted(CONFIGS),
+                    help="BASELINE.json configuration: sdxl = configs[2] (the headline metric, default), sd15 = configs[1], "
+                         "buckets = configs[3], vae = configs[4]")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("NK_BENCH_BATCH", "0")),
+                    help="images per GPU (default: 16 sdxl, 32 sd15, 8 buckets, 2 vae)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -264,9 +542,16 @@ def main() -> None:
                     help="run under `ncu --profile-from-start off`: after the warm-up, ONE eager step with every N-th "
                          "tensor-core launch inside a profiler range, then exit (feeds roofline.traffic)")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.batch <= 0:
+        args.batch = cfg["batch"]
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.config == "buckets":
+        return run_buckets(args)
+    if args.config == "vae":
+        return run_vae(args)
 
     import torch
     import torch.distributed as dist
@@ -284,7 +569,8 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=dev)
     W = max(int(os.environ.get("NK_BENCH_MIN_WARMUP", "3")), args.warmup)  # >= 3 unless overridden for profiler runs
     B = args.batch
-    eng = build_engine(dev)
+    family, px = cfg["family"], cfg["px"]
+    eng = build_engine(dev, family=family)
     params = [p for p in eng.model.parameters() if p.requires_grad]
     if args.shard_optimizer and args.optimizer != "none":
         from neurosis_b200.ddp import ShardedOptimizerReducer
@@ -294,9 +580,10 @@ def main() -> None:
     reducer.attach_as_grad_sink()  # wgrad kernels accumulate straight into the gradient buckets
 
     g = torch.Generator().manual_seed(42 + rank)  # per-rank data
-    host = {"image": (torch.rand(B, 3, 1024, 1024, generator=g) * 2 - 1).pin_memory(),
-            "crossattn_emb": torch.randn(B, 77, 2048, generator=g).pin_memory(),
-            "vector_emb": torch.randn(B, 2816, generator=g).pin_memory()}
+    host = {"image": (torch.rand(B, 3, px, px, generator=g) * 2 - 1).pin_memory(),
+            "crossattn_emb": torch.randn(B, 77, 2048 if family == "sdxl" else 768, generator=g).pin_memory()}
+    if family == "sdxl":
+        host["vector_emb"] = torch.randn(B, 2816, generator=g).pin_memory()
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
@@ -403,13 +690,13 @@ def main() -> None:
     graphed = None
     if not args.no_graph:
         from neurosis_b200.graph import GraphedTrainStep
-        graphed = GraphedTrainStep(eng, reducer, resident["image"], resident["crossattn_emb"], resident["vector_emb"],
+        graphed = GraphedTrainStep(eng, reducer, resident["image"], resident["crossattn_emb"], resident.get("vector_emb"),
                                    warmup=1, optimizer=optimizer, ema=ema)
 
         def step(batch: dict, read_loss: bool) -> float:  # noqa: F811  (replays the captured step)
             same = batch is resident
             loss = graphed.step(None if same else batch["image"], None if same else batch["crossattn_emb"],
-                                None if same else batch["vector_emb"])
+                                None if same else batch.get("vector_emb"))
             return loss.item() if read_loss else 0.0
 
     def barrier():
@@ -463,13 +750,15 @@ def main() -> None:
     if rank == 0:
         ips = world * B * args.steps / (ms_dev * 1e-3)
         ips_e2e = world * B * args.steps / (ms_e2e * 1e-3)
-        line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+        gflop_img = cfg["gflop"]
+        burst = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("bf16_tflops", 1673.6) if (
+            ROOT / "MEASURED_PEAKS.json").exists() else 1590.0
+        line = {"metric": cfg["metric"], "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "SDXL base UNet (configs/sdxl) 1024x1024 training step: VAE encode + diffusion loss + backward"
-                                       + (" + bucketed NCCL gradient all-reduce" if world > 1 else ""),
+                "config": {"workload": cfg["workload"] + (" + bucketed NCCL gradient all-reduce" if world > 1 else ""),
                            "batch_per_gpu": B, "global_batch": B * world, "cuda_graph": graphed is not None,
-                           "wgrad_side_stream": bool(ops.WGRAD_OVERLAP), "latent": "128x128x4",
+                           "wgrad_side_stream": bool(ops.WGRAD_OVERLAP), "latent": f"{px // 8}x{px // 8}x4",
                            "optimizer_step": ("fused Adafactor (relative step, scale_parameter, warmup_init) inside the timed step"
                                               if optimizer is not None else
                                               "not in the timed step (north_star path = encode + loss + backward + "
@@ -477,12 +766,14 @@ def main() -> None:
                                               "measures 15.0 ms, LitEma 5.0 ms (profiles/r01_next_rows_bench.log)"),
                            "ema": ema is not None, "optimizer_sharded": hasattr(reducer, "owned_params"),
                            "parallelism": f"dp{world}", "l2": "working set (5 GB bf16 weights + activations) >> 126 MB L2",
-                           "step_tflop_algorithmic": GFLOP_STEP * B / 1e3,
-                           "mfu_vs_peak": ips / world * GFLOP_STEP * 1e9 / (pk["tflops"] * 1e12)},
+                           "step_tflop_algorithmic": gflop_img * B / 1e3,
+                           "stock_torch_img_s": STOCK_TORCH.get(args.config),
+                           "mfu_vs_sustained_peak": ips / world * gflop_img * 1e9 / (pk["tflops"] * 1e12),
+                           "mfu_vs_burst_peak": ips / world * gflop_img * 1e9 / (burst * 1e12)},
                 "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof}
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_sample(1, 0, budget_s=30.0)  # bounded: ~10-30 s of host work next to the GPU numbers
+            r = cpu_reference_sample(1, 0, budget_s=30.0, family=family)  # bounded: ~10-30 s of host work
             line["cpu_baseline"] = {"value": r["img_per_s"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"],
                                     "sample": r["sample"]}
         print(json.dumps(line), flush=True)

@@ -33,6 +33,7 @@ struct alignas(64) AttnDev {
     float* lse;
     long long o_row_stride, o_batch_stride;  // elements; head offset = h*HD
     int Nq, Nk, H, B;
+    int D;             // valid head dim (<= 64, multiple of 8): columns D..63 of the Q/K/V tiles are zero-filled by TMA
     float scale_log2;  // softmax scale * log2(e)
     float scale;
 };
@@ -299,9 +300,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
         if (q < g.Nq) {
             const float inv = 1.f / l_run;
             bf16* op = g.O + static_cast<long long>(b) * g.o_batch_stride + static_cast<long long>(q) * g.o_row_stride +
-                       static_cast<long long>(h) * HD;
+                       static_cast<long long>(h) * g.D;
 #pragma unroll
             for (int c = 0; c < HD / 8; ++c) {
+                if (8 * c >= g.D) break;  // head dims below 64 (SD1.5: 40): only the valid columns exist in memory
                 uint4 w;
                 w.x = pack_bf16x2(o[8 * c + 0] * inv, o[8 * c + 1] * inv);
                 w.y = pack_bf16x2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
@@ -565,6 +567,7 @@ struct alignas(64) AttnBwdDev {
     bf16* dV;            // [B, Nk, H, 64]
     long long dq_row_stride, dq_batch_stride, dkv_row_stride, dkv_batch_stride;
     int Nq, Nk, H, B;
+    int D;    // valid head dim (<= 64, multiple of 8); the tiles' columns D..63 are TMA zero fill
     float scale, scale_log2;
     int dbg;  // NK_ATTN_DBG A/B switch: 4 = per-thread red.global for dQ instead of the staged TMA reduce-add
 };
@@ -855,9 +858,10 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __gr
             tc_wait_ld();
             if (kvrow < g.Nk) {
                 bf16* op = (which ? g.dK : g.dV) + static_cast<long long>(b) * g.dkv_batch_stride +
-                           static_cast<long long>(kvrow) * g.dkv_row_stride + static_cast<long long>(h) * HD + half * 32;
+                           static_cast<long long>(kvrow) * g.dkv_row_stride + static_cast<long long>(h) * g.D + half * 32;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
+                    if (half * 32 + 8 * c >= g.D) break;
                     uint4 w;
                     w.x = pack_bf16x2(__uint_as_float(raw[8 * c + 0]), __uint_as_float(raw[8 * c + 1]));
                     w.y = pack_bf16x2(__uint_as_float(raw[8 * c + 2]), __uint_as_float(raw[8 * c + 3]));
@@ -879,8 +883,9 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 1) attn_bwd_kernel(const __gr
 }
 
 int make_qkv_tmap(CUtensorMap* tm, const void* p, int N, int H, int B, long long row_stride, long long head_stride,
-                  long long batch_stride) {
-    const uint64_t dims[4] = {static_cast<uint64_t>(HD), static_cast<uint64_t>(H), static_cast<uint64_t>(N),
+                  long long batch_stride, int d_valid = HD) {
+    // d_valid < 64: the 64-wide box reaches past the head; the TMA unit fills the missing columns with zeros
+    const uint64_t dims[4] = {static_cast<uint64_t>(d_valid), static_cast<uint64_t>(H), static_cast<uint64_t>(N),
                               static_cast<uint64_t>(B)};
     const uint64_t strides[3] = {static_cast<uint64_t>(head_stride) * 2, static_cast<uint64_t>(row_stride) * 2,
                                  static_cast<uint64_t>(batch_stride) * 2};
@@ -902,8 +907,9 @@ int nk_attention_fwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
                      int64_t o_row_stride, int64_t o_batch_stride, float* lse, int B, int H, int Nq, int Nk,
                      int head_dim, float scale, nk_stream_t stream) {
     ::nk::enter(stream);
-    NK_REQUIRE(head_dim % HD == 0 && head_dim >= HD && head_dim <= 8 * HD, NK_ERR_UNSUPPORTED,
-               "fused attention supports head_dim 64..512 in steps of 64 (got %d)", head_dim);
+    NK_REQUIRE((head_dim % HD == 0 && head_dim >= HD && head_dim <= 8 * HD) || (head_dim < HD && head_dim % 8 == 0 && head_dim >= 8),
+               NK_ERR_UNSUPPORTED, "fused attention supports head_dim 8..64 in steps of 8 and 64..512 in steps of 64 (got %d)",
+               head_dim);
     NK_REQUIRE(B > 0 && H > 0 && Nq > 0 && Nk > 0, NK_ERR_SHAPE, "attention: empty problem");
     NK_REQUIRE(o_row_stride % 8 == 0 && o_batch_stride % 8 == 0, NK_ERR_SHAPE, "attention: output strides");
     if (head_dim > HD) {  // wide heads: heads must be packed (head stride = head_dim) so that 64-wide chunks tile them
@@ -941,12 +947,13 @@ int nk_attention_fwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
     }
     AttnDev g;
     memset(&g, 0, sizeof(g));
-    int e = make_qkv_tmap(&g.tmQ, q, Nq, H, B, q_row_stride, HD, q_batch_stride);
+    int e = make_qkv_tmap(&g.tmQ, q, Nq, H, B, q_row_stride, head_dim, q_batch_stride, head_dim);
     if (e) return e;
-    e = make_qkv_tmap(&g.tmK, k, Nk, H, B, k_row_stride, HD, k_batch_stride);
+    e = make_qkv_tmap(&g.tmK, k, Nk, H, B, k_row_stride, head_dim, k_batch_stride, head_dim);
     if (e) return e;
-    e = make_qkv_tmap(&g.tmV, v, Nk, H, B, v_row_stride, HD, v_batch_stride);
+    e = make_qkv_tmap(&g.tmV, v, Nk, H, B, v_row_stride, head_dim, v_batch_stride, head_dim);
     if (e) return e;
+    g.D = head_dim;
     g.O = static_cast<bf16*>(o);
     g.lse = lse;
     g.o_row_stride = o_row_stride;
@@ -979,23 +986,26 @@ int nk_attention_bwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
                      int64_t dkv_batch_stride, int B, int H, int Nq, int Nk, int head_dim, float scale,
                      nk_stream_t stream) {
     ::nk::enter(stream);
-    NK_REQUIRE(head_dim == HD, NK_ERR_UNSUPPORTED, "fused attention backward supports head_dim 64 (got %d)", head_dim);
+    NK_REQUIRE(head_dim <= HD && head_dim >= 8 && head_dim % 8 == 0, NK_ERR_UNSUPPORTED,
+               "fused attention backward supports head_dim 8..64 in steps of 8 (got %d)", head_dim);
     NK_REQUIRE(B > 0 && H > 0 && Nq > 0 && Nk > 0, NK_ERR_SHAPE, "attention bwd: empty problem");
     AttnBwdDev g;
     memset(&g, 0, sizeof(g));
-    int e = make_qkv_tmap(&g.tmQ, q, Nq, H, B, q_row_stride, HD, q_batch_stride);
+    const int D = head_dim;
+    int e = make_qkv_tmap(&g.tmQ, q, Nq, H, B, q_row_stride, D, q_batch_stride, D);
     if (e) return e;
-    e = make_qkv_tmap(&g.tmK, k, Nk, H, B, k_row_stride, HD, k_batch_stride);
+    e = make_qkv_tmap(&g.tmK, k, Nk, H, B, k_row_stride, D, k_batch_stride, D);
     if (e) return e;
-    e = make_qkv_tmap(&g.tmV, v, Nk, H, B, v_row_stride, HD, v_batch_stride);
+    e = make_qkv_tmap(&g.tmV, v, Nk, H, B, v_row_stride, D, v_batch_stride, D);
     if (e) return e;
-    e = make_qkv_tmap(&g.tmdO, dO, Nq, H, B, do_row_stride, HD, do_batch_stride);
+    e = make_qkv_tmap(&g.tmdO, dO, Nq, H, B, do_row_stride, D, do_batch_stride, D);
     if (e) return e;
+    g.D = D;
     {
-        const uint64_t dims[4] = {static_cast<uint64_t>(HD), static_cast<uint64_t>(H), static_cast<uint64_t>(Nq),
+        const uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(H), static_cast<uint64_t>(Nq),
                                   static_cast<uint64_t>(B)};
-        const uint64_t strides[3] = {static_cast<uint64_t>(HD) * 4, static_cast<uint64_t>(H) * HD * 4,
-                                     static_cast<uint64_t>(Nq) * H * HD * 4};
+        const uint64_t strides[3] = {static_cast<uint64_t>(D) * 4, static_cast<uint64_t>(H) * D * 4,
+                                     static_cast<uint64_t>(Nq) * H * D * 4};
         const uint32_t box[4] = {32, 1, 128, 1};
         e = encode_tmap(&g.tmdQ, dq_acc, 4, dims, strides, box, 1);
         if (e) return e;
@@ -1005,10 +1015,10 @@ int nk_attention_bwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
     g.dQ = dq_acc;
     g.dK = static_cast<bf16*>(dk);
     g.dV = static_cast<bf16*>(dv);
-    g.dq_row_stride = static_cast<long long>(H) * HD;
-    g.dq_batch_stride = static_cast<long long>(Nq) * H * HD;
-    g.dkv_row_stride = dkv_row_stride > 0 ? dkv_row_stride : static_cast<long long>(H) * HD;
-    g.dkv_batch_stride = dkv_batch_stride > 0 ? dkv_batch_stride : static_cast<long long>(Nk) * H * HD;
+    g.dq_row_stride = static_cast<long long>(H) * D;
+    g.dq_batch_stride = static_cast<long long>(Nq) * H * D;
+    g.dkv_row_stride = dkv_row_stride > 0 ? dkv_row_stride : static_cast<long long>(H) * D;
+    g.dkv_batch_stride = dkv_batch_stride > 0 ? dkv_batch_stride : static_cast<long long>(Nk) * H * D;
     NK_REQUIRE(g.dkv_row_stride % 8 == 0 && g.dkv_batch_stride % 8 == 0 &&
                    (reinterpret_cast<uintptr_t>(dk) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dv) & 15u) == 0,
                NK_ERR_SHAPE, "attention bwd: dk/dv must be 16-byte aligned with strides that are multiples of 8");

@@ -27,7 +27,7 @@ from .engine import DiffusionEngine
 
 class GraphedTrainStep:
     def __init__(self, engine: DiffusionEngine, reducer: BucketedGradReducer, image: Tensor, crossattn: Tensor,
-                 vector: Optional[Tensor], warmup: int = 3, optimizer=None, ema=None):
+                 vector: Optional[Tensor], warmup: int = 3, optimizer=None, ema=None, pool=None):
         self.engine, self.reducer = engine, reducer
         self.optimizer, self.ema = optimizer, ema
         if getattr(engine.loss_fn, "noise_offset", 0.0):
@@ -64,9 +64,12 @@ class GraphedTrainStep:
             self.ema.graph_prepare(engine.model)
             self._ema_ready = True
         l0 = ops.LAUNCHES
+        # `pool`: graphs that never replay concurrently (one captured step per aspect bucket) share one memory pool, so
+        # only the largest bucket's activations are resident instead of the sum over buckets
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, pool=pool):
             self._core()
+        self.pool = self.graph.pool()
         self.launches_per_replay = ops.LAUNCHES - l0
 
     def _core(self) -> None:

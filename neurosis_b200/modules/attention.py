@@ -103,7 +103,7 @@ class CrossAttention(nn.Module):
         b, n, _ = x.shape
         h, d = self.heads, self.dim_head
         out = self.to_out[0]
-        if (context is None and d == 64 and self.fuse_qkv and x.dtype == torch.bfloat16
+        if (context is None and d <= 64 and d % 8 == 0 and self.fuse_qkv and x.dtype == torch.bfloat16
                 and self.to_k.weight.shape == self.to_q.weight.shape):
             # self-attention: q, k, v are one GEMM (forward, data gradient and weight gradient alike)
             o = ops.self_attention_qkv(x, self.to_q.weight, self.to_k.weight, self.to_v.weight, h, self.scale)

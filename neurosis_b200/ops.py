@@ -809,7 +809,7 @@ def attention_fwd(q: Tensor, k: Tensor, v: Tensor, scale: float):
     # flash kernel: D = 64, or D = 128 as two 64-column chunks.  The kernel accepts up to D = 512, but every V/O chunk
     # recomputes the full score tile, so (D/64 + 1)/2 x the useful tensor work: measured on the VAE mid block
     # (1 x 512, 16384 tokens) it is 52 ms against 19.5 ms for the materialised path below, which therefore stays.
-    if D in FLASH_HEAD_DIMS and packed:
+    if (D in FLASH_HEAD_DIMS or (D < 64 and D % 8 == 0)) and packed:
         check(lib.nk_attention_fwd(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
                                    v.data_ptr(), v.stride(1), v.stride(0), o.data_ptr(), o.stride(1), o.stride(0),
                                    lse.data_ptr(), B, H, Nq, Nk, D, float(scale), _stream()), "attention_fwd")
@@ -865,7 +865,8 @@ def attention_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: T
     delta = torch.empty((B, H, Nq), dtype=F32, device=dev)
     doc = do.contiguous()
     check(lib.nk_attn_delta(doc.data_ptr(), o.data_ptr(), delta.data_ptr(), B, Nq, H, D, _stream()), "attn_delta")
-    if D == 64 and q.stride(2) == 64 and k.stride(2) == 64 and v.stride(2) == 64 and not FORCE_MATERIALIZED_ATTN_BWD:
+    if (D <= 64 and D % 8 == 0 and q.stride(2) == D and k.stride(2) == D and v.stride(2) == D
+            and not FORCE_MATERIALIZED_ATTN_BWD):
         # fused flash-style backward: one kernel, nothing of size Nq x Nk touches HBM
         dq_acc = torch.zeros((B, Nq, H, D), dtype=F32, device=dev)
         if out is not None:
@@ -1405,7 +1406,7 @@ class SelfAttentionQKVFn(torch.autograd.Function):
 
 
 def self_attention_qkv(x: Tensor, wq: Tensor, wk: Tensor, wv: Tensor, heads: int, scale: float) -> Tensor:
-    """fused q/k/v projection + attention for self-attention with head_dim 64; returns (B, N, heads*64)."""
+    """fused q/k/v projection + attention for self-attention with head_dim <= 64 (multiple of 8); returns (B, N, inner)."""
     return SelfAttentionQKVFn.apply(x, wq, wk, wv, heads, float(scale))
 
 

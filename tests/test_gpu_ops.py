@@ -353,7 +353,10 @@ def sdpa_ref(q, k, v, scale):
                                          # BASELINE.json configs[3]: 64x64 / 72x56 / 52x76 token grids with 10 heads,
                                          # 26x38 with 20 heads, and the 77-token cross attention of the 4096-token level
                                          (1, 10, 4096, 4096, 64), (1, 10, 4032, 4032, 64), (1, 10, 3952, 3952, 64),
-                                         (1, 20, 988, 988, 64), (1, 10, 4096, 77, 64), (2, 20, 1024, 1024, 64)])
+                                         (1, 20, 988, 988, 64), (1, 10, 4096, 77, 64), (2, 20, 1024, 1024, 64),
+                                         # SD1.5's 40-wide heads (configs/sd15: 320 channels / 8 heads) through the fused
+                                         # kernels: the 64-wide TMA boxes reach past the head and are zero-filled
+                                         (1, 8, 4096, 4096, 40), (2, 8, 1000, 77, 40), (1, 4, 300, 300, 32), (1, 2, 256, 200, 48)])
 def test_attention_fwd_bwd(B, H, Nq, Nk, D):
     q = rnd(B, Nq, H, D).to(BF).requires_grad_(True)
     k = rnd(B, Nk, H, D, seed=1).to(BF).requires_grad_(True)
