@@ -46,7 +46,16 @@ class BucketedGradReducer:
                 self._index[p] = bi
         self.enabled = True
         self._works: list = []
-        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        # Two sources report a gradient as complete: autograd's post-accumulate hook (gradients that autograd itself
+        # accumulates) and `mark_ready` (kernels of neurosis_b200.ops that wrote straight into the bucket storage).
+        # torch fires the post-accumulate hook for EVERY parameter an autograd Function was asked a gradient for, even
+        # when the Function returned None because a kernel already wrote the bucket (found by the 2-rank NCCL equality
+        # test: every sunk parameter was counted twice, so buckets were all-reduced half-way through backward).  A
+        # parameter whose storage was handed out through `buffer_for` this step is therefore counted by `mark_ready`
+        # only — its hook may even fire BEFORE the side-stream weight-gradient job has been joined.
+        self._sunk: set = set()
+        self._counted: set = set()
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_hook) for p in self.params]
         dev = self.params[0].device
         self._cuda = dev.type == "cuda"
         self._stream = torch.cuda.Stream(device=dev) if self._cuda else None
@@ -62,6 +71,8 @@ class BucketedGradReducer:
 
     # -- per step ---------------------------------------------------------------------------------
     def zero_grad(self) -> None:
+        self._sunk.clear()
+        self._counted.clear()
         for b in self.buckets:
             b["flat"].zero_()
             b["pending"] = len(b["params"])
@@ -80,9 +91,17 @@ class BucketedGradReducer:
         if p not in self._index:
             return None
         g = p.grad
-        return g if (g is not None and g.dtype == torch.float32) else None
+        if g is None or g.dtype != torch.float32:
+            return None
+        self._sunk.add(id(p))
+        return g
 
     def mark_ready(self, p: nn.Parameter) -> None:
+        self._on_grad(p)
+
+    def _on_hook(self, p: nn.Parameter) -> None:
+        if id(p) in self._sunk:
+            return  # a kernel owns this gradient; `mark_ready` reports it once the write is ordered on the main stream
         self._on_grad(p)
 
     def attach_as_grad_sink(self) -> None:
@@ -99,6 +118,9 @@ class BucketedGradReducer:
     def _on_grad(self, p: nn.Parameter) -> None:
         if not self.enabled or self.world == 1:
             return
+        if id(p) in self._counted:  # once per parameter and step, whatever the source
+            return
+        self._counted.add(id(p))
         b = self.buckets[self._index[p]]
         b["pending"] -= 1
         if b["pending"] == 0:
@@ -149,6 +171,8 @@ class BucketedGradReducer:
                     from . import ops
                     ops.join_side_streams()  # retire side-stream jobs while mark_ready is still a no-op
                 reducer.enabled = True
+                reducer._sunk.clear()
+                reducer._counted.clear()
                 for b in reducer.buckets:  # the boundary micro-step counts every parameter again
                     b["pending"] = len(b["params"])
 

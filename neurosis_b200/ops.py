@@ -96,7 +96,9 @@ FLASH_HEAD_DIMS = (64, 128)  # head dims routed to the fused attention forward (
 # those SMs, and memory-bound kernels of the main chain overlap tensor-bound weight-gradient GEMMs.
 # Only used when the gradient goes to a sink (ddp.BucketedGradReducer): autograd never sees the tensor, and the
 # parameter is reported ready (mark_ready -> bucket all-reduce) only after the main stream has joined the side work.
-WGRAD_OVERLAP = True
+import os as _os
+
+WGRAD_OVERLAP = not _os.environ.get("NK_NO_WGRAD_OVERLAP")
 _side_streams: dict = {}
 _inflight: collections.deque = collections.deque()  # (event on the side stream, tensors kept alive, sink base params)
 
@@ -1380,8 +1382,11 @@ class SelfAttentionQKVFn(torch.autograd.Function):
         need = ctx.needs_input_grad[1:4]
         sinks = [_grad_sink(w) for w in (wv, wk, wq)]
         x2 = x.reshape(B * N, -1)
+        # adjacent slices of ONE bucket (adjacent addresses alone are not enough: two buckets' flat buffers can be
+        # neighbours in the allocator — found by the 2-rank NCCL test with 2 MB buckets)
         stacked = all(need) and all(b is not None for b, _ in sinks) and all(
-            sinks[i][0].data_ptr() + sinks[i][0].numel() * 4 == sinks[i + 1][0].data_ptr() for i in range(2))
+            sinks[i][0].data_ptr() + sinks[i][0].numel() * 4 == sinks[i + 1][0].data_ptr()
+            and sinks[i][0].untyped_storage().data_ptr() == sinks[i + 1][0].untyped_storage().data_ptr() for i in range(2))
         if stacked:  # [dWv; dWk; dWq] is one contiguous [3*inner, C] block of a gradient bucket
             bases = tuple(b for _, b in sinks)
             buf = torch.as_strided(sinks[0][0], (3 * inner, x2.shape[1]), (x2.shape[1], 1))

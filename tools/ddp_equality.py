@@ -88,16 +88,26 @@ def main() -> int:
     red.attach_as_grad_sink()
     red.zero_grad()
     loss_of(m, *batch(rank)).backward()
+    ops.join_side_streams()
+    pending_before_finish = [b["pending"] for b in red.buckets]
     red.finish()
     torch.cuda.synchronize()
     red.detach_grad_sink()
     grads = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    # every bucket must have been launched exactly when its last gradient arrived (0 left, none negative: a negative
+    # count means a parameter was reported twice and the bucket was all-reduced before it was complete)
+    out["pending_before_finish"] = pending_before_finish
+    ok = ok and all(v == 0 for v in pending_before_finish)
     # identical on every rank: compare a checksum vector
     chk = torch.stack([g.double().sum() for g in grads.values()])
     gathered = [torch.zeros_like(chk) for _ in range(world)]
     dist.all_gather(gathered, chk)
     same = all(torch.equal(gathered[0], g) for g in gathered)
     out["reduced_grads_identical_on_all_ranks"] = bool(same)
+    if not same:
+        bad = [n for i, n in enumerate(names) if any(float(g[i]) != float(gathered[0][i]) for g in gathered)]
+        out["params_that_differ_between_ranks"] = bad[:12]
+        out["n_params_that_differ"] = len(bad)
     ok = ok and same
     if rank == 0:
         ref = make_model()
@@ -110,6 +120,8 @@ def main() -> int:
         errs = np.array([rel(grads[n], p.grad) for n, p in ref.named_parameters()])
         out["grad_rel_l2_median"] = float(np.median(errs))
         out["grad_rel_l2_max"] = float(errs.max())
+        order = np.argsort(-errs)[:6]
+        out["worst"] = [(names[i], float(errs[i])) for i in order]
         out["buckets"] = len(red.buckets)
         ok = ok and np.median(errs) < 2e-2 and errs.max() < 1.5e-1
         ref_grads = {n: p.grad.detach().clone() for n, p in ref.named_parameters()}
