@@ -34,6 +34,7 @@ struct alignas(64) AttnDev {
     long long o_row_stride, o_batch_stride;  // elements; head offset = h*HD
     int Nq, Nk, H, B;
     int D;             // valid head dim (<= 64, multiple of 8): columns D..63 of the Q/K/V tiles are zero-filled by TMA
+    int p_tmem;        // 1: P stays in tensor memory (A operand of the PV MMA); 0: swizzled shared-memory tile (NK_ATTN_P_TMEM=0)
     float scale_log2;  // softmax scale * log2(e)
     float scale;
 };
@@ -80,9 +81,11 @@ __device__ __forceinline__ float tile_rowmax(uint32_t s_addr, int kv_valid) {
 }
 
 // p = exp2(s*scale_log2 - mb) -> bf16, written to the 128B-swizzled [row][kv] tile pair at pbuf; returns the row sum
+// p_tmem != 0: the bf16 probabilities go to tensor memory (columns p_tmem + 8c .. + 8: two per 32-bit column) as the
+// A operand of the PV MMA, instead of the swizzled shared-memory tile at pbuf
 template <bool MASK>
 __device__ __forceinline__ float tile_probs(uint32_t s_addr, int kv_valid, float scale_log2, float mb, uint8_t* pbuf,
-                                            int r) {
+                                            int r, uint32_t p_tmem = 0) {
     float l0 = 0.f, l1 = 0.f;
     auto emit = [&](int c, const uint32_t (&raw)[16]) {  // c = 16-column chunk 0..7
         uint32_t w[8];
@@ -97,6 +100,10 @@ __device__ __forceinline__ float tile_probs(uint32_t s_addr, int kv_valid, float
             l0 += v0;
             l1 += v1;
             w[i >> 1] = pack_bf16x2(v0, v1);
+        }
+        if (p_tmem != 0) {
+            tc_st8(p_tmem + static_cast<uint32_t>(c * 8), w);
+            return;
         }
         uint8_t* rowp = pbuf + (c >> 2) * TILE_BYTES + r * 128;
         const int ch = (c & 3) * 2;
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t TM_S = 0, TM_O = 128;
+    const uint32_t TM_S = 0, TM_O = 128, TM_P = 192;  // P: 128 x 128 bf16 = 64 columns
 
     if (warp == 0) {
         if (lane == 0) {
@@ -214,12 +221,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                     const uint32_t d = tmem_base + TM_O;
                     const uint32_t pbase = smem_u32(smem + SM_P);
                     const uint32_t vbase = smem_u32(smem + SM_V + stage * TILE_BYTES);
+                    if (g.p_tmem) {  // A = P from tensor memory: 8 columns (16 bf16) per k16 step
 #pragma unroll
-                    for (int kk = 0; kk < BKV / 16; ++kk) {
-                        const uint64_t p_desc =
-                            make_smem_desc(pbase + static_cast<uint32_t>((kk >> 2) * TILE_BYTES + (kk & 3) * 32), 16u, 1024u);
-                        const uint64_t v_desc = make_smem_desc(vbase + static_cast<uint32_t>(kk * 2048), 8192u, 1024u);
-                        tc_mma_ss(d, p_desc, v_desc, idesc_o, kk > 0 ? 1u : 0u);
+                        for (int kk = 0; kk < BKV / 16; ++kk) {
+                            const uint64_t v_desc = make_smem_desc(vbase + static_cast<uint32_t>(kk * 2048), 8192u, 1024u);
+                            tc_mma_ts(d, tmem_base + TM_P + static_cast<uint32_t>(kk * 8), v_desc, idesc_o, kk > 0 ? 1u : 0u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < BKV / 16; ++kk) {
+                            const uint64_t p_desc = make_smem_desc(
+                                pbase + static_cast<uint32_t>((kk >> 2) * TILE_BYTES + (kk & 3) * 32), 16u, 1024u);
+                            const uint64_t v_desc = make_smem_desc(vbase + static_cast<uint32_t>(kk * 2048), 8192u, 1024u);
+                            tc_mma_ss(d, p_desc, v_desc, idesc_o, kk > 0 ? 1u : 0u);
+                        }
                     }
                     tc_commit(o_full);
                     tc_commit(&kv_empty[stage]);
@@ -273,9 +288,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                 l_run = fmaf(l_run, alpha_prev, l_prev);
             }
             uint8_t* pbuf = smem + SM_P;
-            l_prev = tail ? tile_probs<true>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r)
-                          : tile_probs<false>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r);
-            fence_proxy_async_smem();
+            const uint32_t p_dst = g.p_tmem ? lane_addr + TM_P : 0u;
+            l_prev = tail ? tile_probs<true>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r, p_dst)
+                          : tile_probs<false>(s_addr, kv_valid, g.scale_log2, mb, pbuf, r, p_dst);
+            if (g.p_tmem) tc_wait_st(); else fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(p_full);
             alpha_prev = alpha;
@@ -954,6 +970,14 @@ int nk_attention_fwd(const void* q, int64_t q_row_stride, int64_t q_batch_stride
     e = make_qkv_tmap(&g.tmV, v, Nk, H, B, v_row_stride, head_dim, v_batch_stride, head_dim);
     if (e) return e;
     g.D = head_dim;
+    {
+        static int env_p = -1;
+        if (env_p < 0) {
+            const char* e_ = getenv("NK_ATTN_P_TMEM");
+            env_p = e_ ? atoi(e_) : 1;
+        }
+        g.p_tmem = env_p;
+    }
     g.O = static_cast<bf16*>(o);
     g.lse = lse;
     g.o_row_stride = o_row_stride;
