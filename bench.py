@@ -284,7 +284,8 @@ def _dist_setup():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     return world, rank, local, dev
 
 
@@ -392,13 +393,14 @@ def run_buckets(args) -> None:
     it["i"] = 0
     ms_e2e = _timed(world, dev, args.steps, lambda: step(True))
     clocks = sampler.stop() if sampler else None
-    # the same schedule with every rank on the square bucket: what the straggler effect of mixed buckets costs
+    # the same number of steps with EVERY rank on the square bucket: what the straggler effect of mixed buckets costs.
+    # (Every rank must take this branch — the step contains collectives.  A rank whose drawn schedule happened to hold
+    # no square batch used to skip it, which hung the 8-GPU run of round 2 until the box limit.)
     sq = SDXL_BUCKETS.index((1024, 1024))
-    sq_batch = next((s_ for s_ in sched if s_["bucket"] == sq), None)
-    ms_sq = None
-    if sq_batch is not None:
-        w1 = torch.ones(B)
-        ms_sq = _timed(world, dev, args.steps, lambda: graphs[sq].step(sq_batch["image"], sq_batch["ctx"], None, weights=w1))
+    sq_b = data(bucket=sq)
+    sq_img, sq_ctx, w1 = sq_b["image"].pin_memory(), sq_b["crossattn_emb"].pin_memory(), torch.ones(B)
+    graphs[sq].step(sq_img, sq_ctx, vector(sq_b), weights=w1)
+    ms_sq = _timed(world, dev, args.steps, lambda: graphs[sq].step(sq_img, sq_ctx, None, weights=w1))
     if rank == 0:
         ips = world * B * args.steps / (ms_dev * 1e-3)
         launches = sum(graphs[sched[i % len(sched)]["bucket"]].launches_per_replay for i in range(args.steps))
@@ -566,7 +568,8 @@ def main() -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     W = max(int(os.environ.get("NK_BENCH_MIN_WARMUP", "3")), args.warmup)  # >= 3 unless overridden for profiler runs
     B = args.batch
     family, px = cfg["family"], cfg["px"]
