@@ -80,8 +80,9 @@ class GraphedTrainStep:
         cond = {"crossattn": self.crossattn}
         if self.vector is not None:
             cond["vector"] = self.vector
-        loss = eng.loss_fn._forward(eng.model, eng.denoiser, cond, z, {}, sigmas=self.sigmas)
-        total = (loss * self.weights).mean()
+        # hook weights (tag-frequency scaling) enter the reduction kernel's weight vector, not a multiply afterwards
+        loss = eng.loss_fn._forward(eng.model, eng.denoiser, cond, z, {}, sigmas=self.sigmas, sample_weights=self.weights)
+        total = loss.mean()
         total.backward()
         self.reducer.finish()
         self.per_sample.copy_(loss.detach())

@@ -28,6 +28,13 @@ from .denoiser import Denoiser, DenoiserWeighting
 from .schedule import SigmaGenerator, append_dims
 
 
+# batch key under which a `LossHook.pre_hook` leaves per-sample loss multipliers for the loss to consume: they are folded
+# into the (B,) weight vector of the weighted-MSE / L1 reduction kernel instead of being a separate
+# multiply on the reduced loss; APPLIED_KEY tells the hook's post-loss call that this already happened
+SAMPLE_WEIGHT_KEY = "_nk_loss_sample_weights"
+APPLIED_KEY = "_nk_loss_sample_weights_applied"
+
+
 class DiffusionLoss(ABC, nn.Module):
     def __init__(self, noise_offset: float = 0.0, noise_offset_chance: float = 0.0, *args, **kwargs):
         super().__init__()
@@ -79,9 +86,13 @@ class StandardDiffusionLoss(DiffusionLoss):
         return self.sigma_generator(n, torch.rand((n,), dtype=torch.float64))
 
     def _forward(self, network, denoiser, cond, inputs, batch, return_dict=False, *,
-                 t: Optional[Tensor] = None, noise: Optional[Tensor] = None, sigmas: Optional[Tensor] = None):
+                 t: Optional[Tensor] = None, noise: Optional[Tensor] = None, sigmas: Optional[Tensor] = None,
+                 sample_weights: Optional[Tensor] = None):
         """`t` / `noise` overrides exist for parity tests (the reference draws both internally); `sigmas` (a device
-        tensor filled from `draw_sigmas`) lets the whole step be captured in a CUDA graph without a host copy."""
+        tensor filled from `draw_sigmas`) lets the whole step be captured in a CUDA graph without a host copy;
+        `sample_weights` (B,) — or `batch[SAMPLE_WEIGHT_KEY]`, left there by a loss hook's `pre_hook` — are per-sample
+        loss multipliers that enter the reduction kernel through its weight vector: loss[b] = sw[b] * w(sigma[b]) *
+        mean((D - T)^2)."""
         extra = {k: batch[k] for k in batch if k in self.input_keys}
         n = inputs.shape[0]
         if sigmas is None:
@@ -96,6 +107,11 @@ class StandardDiffusionLoss(DiffusionLoss):
         rf = self.objective_type == "rf"
         z_t = ops.noise_mix(inputs, noise, sigmas, rectified_flow=rf)
         weight = self.loss_weighting(sigmas)
+        if sample_weights is None and isinstance(batch, dict) and SAMPLE_WEIGHT_KEY in batch:
+            sample_weights = batch[SAMPLE_WEIGHT_KEY]
+            batch[APPLIED_KEY] = True
+        if sample_weights is not None:
+            weight = weight.reshape(-1) * sample_weights.to(device=weight.device, dtype=weight.dtype).reshape(-1)
         if rf:
             out = denoiser(network, z_t, sigmas, cond, "F", **extra)
             loss = self.get_loss(out, noise, weight)
@@ -210,8 +226,23 @@ class TagFrequencyHook(LossHook):
             weights.append(1.0 + self.strength * self.alpha * (mean - 1.0))
         return weights
 
+    def pre_hook(self, trainer, pl_module, batch, batch_idx):
+        """the multipliers depend only on the captions, so they are computed BEFORE the loss and handed to it through
+        the batch: the loss folds them into the weight vector of its reduction kernel (no extra pass over the loss)."""
+        if isinstance(batch, dict) and self.input_key in batch:
+            batch[SAMPLE_WEIGHT_KEY] = torch.tensor(self.sample_weights(list(batch[self.input_key])), dtype=torch.float32)
+            batch.pop(APPLIED_KEY, None)
+        return batch
+
     def batch_hook(self, pl_module, batch: dict, loss: Tensor, loss_dict: dict = {}, **kwargs):
-        w = torch.tensor(self.sample_weights(list(batch[self.input_key])), dtype=loss.dtype).to(loss.device)
         loss_dict = dict(loss_dict)
+        if batch.pop(APPLIED_KEY, False):  # the loss already carries the multipliers (pre_hook path)
+            w = batch.pop(SAMPLE_WEIGHT_KEY)
+            loss_dict[f"{self.name}/scale_mean"] = w.mean()
+            return loss, loss_dict
+        w = batch.pop(SAMPLE_WEIGHT_KEY, None)  # pre_hook ran but the loss did not consume them (foreign loss class)
+        if w is None:
+            w = torch.tensor(self.sample_weights(list(batch[self.input_key])), dtype=torch.float32)
+        w = w.to(device=loss.device, dtype=loss.dtype)
         loss_dict[f"{self.name}/scale_mean"] = w.mean()
         return loss * w, loss_dict

@@ -176,3 +176,44 @@ def test_sampling_posterior_host_code_vs_oracle(emulated):
     np.testing.assert_allclose(a.grad.numpy(), b.grad.numpy(), rtol=1e-5, atol=1e-6)
     zm, log0 = DiagonalGaussianRegularizer(sample=False)(m)
     assert torch.equal(zm, m[:, :4]) and log0 == {}
+
+
+def test_hook_sample_weights_enter_the_reduction_kernel(emulated):
+    """the tag-frequency multipliers are folded into the weight vector of the weighted-MSE kernel.
+    (1) `_forward(sample_weights=w)` == w * `_forward()` in value and in every gradient; (2) the hook protocol of
+    `DiffusionEngine.training_step` — pre_hook leaves the weights in the batch, the loss consumes them, the post-loss hook
+    call does not multiply a second time — gives the same numbers as the multiply-afterwards form."""
+    from neurosis_b200.modules.denoiser import DiscreteDenoiser, EpsPreconditioning, EpsWeighting
+    from neurosis_b200.modules.loss import (APPLIED_KEY, SAMPLE_WEIGHT_KEY, StandardDiffusionLoss, TagFreqScale,
+                                            TagFrequencyHook)
+    from neurosis_b200.modules.schedule import LegacyDDPMDiscretization
+    den = DiscreteDenoiser(EpsPreconditioning(), 1000, LegacyDDPMDiscretization())
+    sig = torch.from_numpy(G0["step.sigmas"])
+    w = torch.tensor([0.8, 1.3])
+    sd, lat, noise, cond, network = _setup()
+    loss_fn = StandardDiffusionLoss(_fixed(sig), EpsWeighting())
+    fused = loss_fn._forward(network, den, cond, lat, {}, noise=noise, sample_weights=w)
+    np.testing.assert_allclose(fused.detach().numpy(), G0["step.loss"] * w.numpy(), rtol=1e-4)
+    fused.mean().backward()
+    g_fused = {n: sd[n].grad.clone() for n in sd}
+    sd2, lat, noise, cond, network2 = _setup()
+    plain = loss_fn._forward(network2, den, cond, lat, {}, noise=noise)
+    (plain * w).mean().backward()
+    for n in sd2:
+        np.testing.assert_allclose(g_fused[n].numpy(), sd2[n].grad.numpy(), rtol=2e-4, atol=1e-8)
+    # hook protocol: same captions through two identical hooks, fused vs multiply-afterwards
+    caps = ["1girl solo smile", "landscape scenery sky cloud"]
+    mk = lambda: TagFrequencyHook(alpha=0.5, beta=0.9, freq_scale=TagFreqScale([[-1, 1.4], [0.5, 0.7]]))  # noqa: E731
+    h1, h2 = mk(), mk()
+    batch = {"caption": list(caps)}
+    batch = h1.pre_hook(None, None, batch, 0)
+    assert SAMPLE_WEIGHT_KEY in batch
+    sd3, lat, noise, cond, network3 = _setup()
+    l1 = loss_fn._forward(network3, den, cond, lat, batch, noise=noise)
+    assert batch.get(APPLIED_KEY)
+    l1b, log1 = h1(None, batch, l1, {})
+    assert l1b is l1 and SAMPLE_WEIGHT_KEY not in batch and APPLIED_KEY not in batch
+    l2, log2 = h2(None, {"caption": list(caps)}, plain.detach(), {})  # no pre_hook: the hook multiplies afterwards
+    np.testing.assert_allclose(l1.detach().numpy(), l2.numpy(), rtol=1e-4)
+    assert abs(float(log1["TagFrequencyHook/scale_mean"]) - float(log2["TagFrequencyHook/scale_mean"])) < 1e-6
+    assert h1.counts == h2.counts  # the running tag counts advanced exactly once per step in both forms
