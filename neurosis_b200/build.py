@@ -72,6 +72,28 @@ def build_ktest(force: bool = False) -> Path:
     return out
 
 
+def install_reference(src: Path = Path("/root/reference"), force: bool = False) -> Path | None:
+    """The reference arm of bench.py (`--impl reference`, `cpu_baseline`) and tools/stock_torch_bench.py run the UNMODIFIED
+    reference from baseline/_ref (git-ignored, shipped to the GPU box with the snapshot).  (Re)install it with the
+    contract's offline pip recipe when the source tree is present (the authoring container; the GPU box only uses the
+    prebuilt copy).  /root/reference is read-only and the build writes egg-info, so pip works on a copy under /tmp."""
+    import shutil
+    import tempfile
+    dst = ROOT / "baseline" / "_ref"
+    marker = dst / "neurosis" / "modules" / "diffusion" / "openaimodel.py"
+    if marker.exists() and not force:
+        return dst
+    if not (src / "src" / "neurosis").exists():
+        return None
+    with tempfile.TemporaryDirectory() as tmp:
+        copy = Path(tmp) / "refcopy"
+        shutil.copytree(src, copy, symlinks=True, ignore=shutil.ignore_patterns(".git"))
+        dst.parent.mkdir(exist_ok=True)
+        _run([sys.executable, "-m", "pip", "install", "--no-index", "--no-build-isolation", "--no-deps", "--find-links",
+              "/opt/wheelhouse", "--target", str(dst), "--upgrade", str(copy)])
+    return dst if marker.exists() else None
+
+
 if __name__ == "__main__":
     force = "--force" in sys.argv
     p = build(force=force, verbose=True)
