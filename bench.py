@@ -514,6 +514,85 @@ def run_vae(args) -> None:
     _finish(world)
 
 
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations, measured by the same default run (driver-visible)
+# ------------------------------------------------------------------------------------------------
+OTHER_CONFIGS = ("sd15", "buckets", "vae")  # BASELINE.json configs[1] / [3] / [4]
+
+
+def _child_cmd(name: str, args, world: int) -> list:
+    return [sys.executable, str(ROOT / "bench.py"), "--config", name, "--gpus", str(world), "--steps", str(args.steps),
+            "--warmup", str(args.warmup), "--no-cpu-baseline", "--no-profile"]
+
+
+def run_other_configs(args, world: int, rank: int, budget_s: float, per_config_s: float) -> dict:
+    """After the headline measurement (and after its graph, model and buckets are freed) every rank runs
+    `bench.py --config X` for the other BASELINE.json configurations as a CHILD process on its own GPU: the children of the
+    N ranks rendezvous among themselves on a fresh port (their own TCPStore: the launcher's agent store stays with the
+    parents), so a crash, hang or out-of-memory in a secondary configuration can never take the headline line with it —
+    a child that exceeds its limit is killed with its process group and recorded as {"error": ...}.  Returns, on rank
+    0, {config: summary of the child's JSON line}; other ranks return {}."""
+    import signal
+    out: dict = {}
+    t_start = time.monotonic()
+    base_port = int(os.environ.get("MASTER_PORT", "29500"))
+    for k, name in enumerate(OTHER_CONFIGS):
+        left = budget_s - (time.monotonic() - t_start)
+        if left < 30.0:
+            out[name] = {"error": f"skipped: {budget_s:.0f} s budget of the secondary configurations used up"}
+            continue
+        env = {key: v for key, v in os.environ.items() if not key.startswith("TORCHELASTIC_")}
+        env["MASTER_ADDR"] = "127.0.0.1"
+        env["MASTER_PORT"] = str(20000 + (base_port + 1013 * (k + 1)) % 20000)
+        env["NK_BENCH_EXTRAS"] = "0"
+        cmd = _child_cmd(name, args, world)
+        t0 = time.monotonic()
+        try:
+            proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                    start_new_session=True, cwd=str(ROOT))
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": f"spawn failed: {e}"}
+            continue
+        try:
+            so, se = proc.communicate(timeout=min(per_config_s, left))
+            rc = proc.returncode
+        except subprocess.TimeoutExpired:
+            try:
+                os.killpg(proc.pid, signal.SIGKILL)
+            except Exception:  # noqa: BLE001
+                proc.kill()
+            so, se = proc.communicate()
+            rc = "timeout"
+        wall = time.monotonic() - t0
+        if rank != 0:
+            continue
+        row = None
+        for ln in reversed((so or "").strip().splitlines()):
+            if ln.startswith("{"):
+                try:
+                    row = json.loads(ln)
+                except Exception:  # noqa: BLE001
+                    row = None
+                break
+        if row is None or "value" not in row:
+            tail = " | ".join((se or "").strip().splitlines()[-3:])[-400:]
+            out[name] = {"error": f"no result (exit {rc}) after {wall:.0f} s", "stderr_tail": tail}
+            continue
+        c = row.get("config", {})
+        summ = {"metric": row["metric"], "value": row["value"], "unit": row["unit"], "n_gpus": row["n_gpus"],
+                "steps": row["steps"], "warmup": row["warmup"], "ms_per_step": row["ms_per_step"],
+                "e2e": row.get("e2e"), "batch_per_gpu": c.get("batch_per_gpu"), "workload": c.get("workload"),
+                "gpu_launches": row.get("gpu_launches"), "clock_reasons": (row.get("clocks") or {}).get("reasons"),
+                "sm_mhz": (row.get("clocks") or {}).get("sm_mhz"),
+                "step_tflops_per_gpu": (row.get("roofline") or {}).get("achieved"), "wall_s": round(wall, 1)}
+        for extra in ("square_only_ms_per_step", "encode_images_per_s", "encode_tflops_per_gpu", "peak_mem_gb",
+                      "mfu_vs_burst_peak", "buckets_drawn_rank0"):
+            if extra in c:
+                summ[extra] = c[extra]
+        out[name] = summ
+    return out
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -528,6 +607,9 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--other-configs", default="auto", choices=["auto", "none"],
+                    help="auto (default run of --config sdxl only): after the headline measurement also run --config "
+                         "sd15 / buckets / vae as child processes and report them under `other_configs` of the same line")
     ap.add_argument("--optimizer", default="none", choices=["none", "adafactor"],
                     help="opt-in: put the fused Adafactor step (configs/sdxl/sdxl.example.yaml:158-164) inside the timed "
                          "step; the default measures the hot path BASELINE.json names (encode + loss + backward + all-reduce)")
@@ -750,12 +832,12 @@ def main() -> None:
                 "how": "CUDA events around every gemm_tc launch of one eagerly issued step with kernels running alone "
                        "(same kernels as the graph; in the timed step weight-gradient GEMMs overlap the main chain "
                        "on a side stream, so share_of_step is serial GEMM time over overlapped step time)"}
+    line = None
     if rank == 0:
         ips = world * B * args.steps / (ms_dev * 1e-3)
         ips_e2e = world * B * args.steps / (ms_e2e * 1e-3)
         gflop_img = cfg["gflop"]
-        burst = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("bf16_tflops", 1673.6) if (
-            ROOT / "MEASURED_PEAKS.json").exists() else 1590.0
+        burst = _burst_peak()
         line = {"metric": cfg["metric"], "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
@@ -779,19 +861,67 @@ def main() -> None:
             r = cpu_reference_sample(1, 0, budget_s=30.0, family=family)  # bounded: ~10-30 s of host work
             line["cpu_baseline"] = {"value": r["img_per_s"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"],
                                     "sample": r["sample"]}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        # Tear-down order matters: a captured graph holds NCCL kernels, and destroying the communicator while the
-        # graph is alive blocks forever (observed: the JSON line printed, then the ranks hung in
-        # destroy_process_group).  Drop the graph first, and leave through os._exit so no NCCL finaliser can stall
-        # the launcher after the result is out.
-        del step
-        graphed = None
+
+    printed = threading.Lock()
+
+    def emit() -> None:
+        """rank 0 prints the ONE JSON line, exactly once (the watchdog below and the normal path race for the lock)."""
+        if printed.acquire(blocking=False) and line is not None:
+            print(json.dumps(line), flush=True)
+
+    # ---- the other BASELINE.json configurations (configs[1] / [3] / [4]) on the same box, as child processes ----
+    extras = (args.config == "sdxl" and args.other_configs == "auto" and os.environ.get("NK_BENCH_EXTRAS", "1") != "0"
+              and graphed is not None and optimizer is None and not args.breakdown and not args.torch_profile)
+    # Tear-down order matters: a captured graph holds NCCL kernels, and destroying the communicator while the graph is
+    # alive blocks forever (observed: the JSON line printed, then the ranks hung in destroy_process_group).  Drop the
+    # graph first — and with it the model, gradient buckets and weight mirrors, so that the children below find the
+    # GPU (almost) empty.
+    del step, eager_step, graphed, eng, params, reducer, resident, optimizer, ema
+    try:
+        ops.GRAD_SINK = None
+        ops._inflight.clear()
+        ops.invalidate_weight_cache()
         import gc
         gc.collect()
         torch.cuda.synchronize()
-        dist.barrier()
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001  (nothing after the measurement may cost the line)
+        print(f"[bench] tear-down: {e!r}", file=sys.stderr)
+        extras = False
+    if extras:
+        budget = float(os.environ.get("NK_BENCH_EXTRAS_BUDGET_S", "330"))
+
+        def give_up() -> None:  # a child that cannot be reaped must not cost the headline line
+            if line is not None:
+                line["other_configs"] = {"error": "secondary configurations exceeded their wall-clock budget"}
+            emit()
+            sys.stdout.flush()
+            os._exit(0)
+
+        dog = threading.Timer(budget + 45.0, give_up)
+        dog.daemon = True
+        dog.start()
+        try:
+            other = run_other_configs(args, world, rank, budget_s=budget,
+                                      per_config_s=float(os.environ.get("NK_BENCH_EXTRAS_EACH_S", "150")))
+        except BaseException as e:  # noqa: BLE001
+            other = {"error": repr(e)}
+        dog.cancel()
+        if line is not None:
+            other["_note"] = ("each entry is the JSON line of `bench.py --config <name>` run by this same command after the "
+                              "headline measurement, one child process per rank on the same GPUs (N ranks over NCCL when "
+                              "N > 1); same steps / warm-up / CUDA-event timing rules as the headline")
+            other["_parent_reserved_gb_during_children"] = torch.cuda.memory_reserved() / 2 ** 30
+            line["other_configs"] = other
+    emit()
+    if world > 1:
+        # leave through os._exit so no NCCL finaliser can stall the launcher after the result is out
         torch.cuda.synchronize()
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+        except Exception:  # noqa: BLE001
+            pass
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)

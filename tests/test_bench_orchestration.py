@@ -1,0 +1,89 @@
+"""bench.py's default run also measures BASELINE.json configs[1] / [3] / [4] as child processes after the headline
+measurement (`run_other_configs`).  These CPU tests drive that orchestration with stand-in children: a child that
+answers, one that crashes, one that hangs (killed with its process group at the limit) — none may cost the parent
+its own line."""
+import json
+import sys
+import time
+import types
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import bench  # noqa: E402
+
+
+def _args(steps=2, warmup=1):
+    return types.SimpleNamespace(steps=steps, warmup=warmup)
+
+
+def test_children_answer_crash_and_hang(monkeypatch):
+    ok_line = {"metric": "m", "value": 12.5, "unit": "images/s", "n_gpus": 1, "steps": 2, "warmup": 3, "ms_per_step": 80.0,
+               "e2e": {"value": 12.0, "unit": "images/s", "h2d_bytes_per_step": 10, "d2h_bytes_per_step": 4},
+               "config": {"batch_per_gpu": 32, "workload": "w", "encode_images_per_s": 99.0}, "gpu_launches": 7,
+               "clocks": {"sm_mhz": 1900.0, "reasons": ["sw_power_cap"]}, "roofline": {"achieved": 500.0}}
+
+    def cmd(name, args, world):
+        if name == "sd15":  # noise on stdout before the line, as a warning would be
+            return [sys.executable, "-c", f"print('warming up'); print({json.dumps(ok_line)!r})"]
+        if name == "buckets":
+            return [sys.executable, "-c", "import sys; sys.stderr.write('boom: device-side assert\\n'); sys.exit(3)"]
+        return [sys.executable, "-c", "import time; time.sleep(60)"]
+
+    monkeypatch.setattr(bench, "_child_cmd", cmd)
+    t0 = time.monotonic()
+    out = bench.run_other_configs(_args(), world=1, rank=0, budget_s=100.0, per_config_s=2.0)
+    assert time.monotonic() - t0 < 20.0
+    assert out["sd15"]["value"] == 12.5 and out["sd15"]["batch_per_gpu"] == 32 and out["sd15"]["encode_images_per_s"] == 99.0
+    assert out["sd15"]["clock_reasons"] == ["sw_power_cap"] and out["sd15"]["e2e"]["value"] == 12.0
+    assert "exit 3" in out["buckets"]["error"] and "boom" in out["buckets"]["stderr_tail"]
+    assert "timeout" in out["vae"]["error"]
+
+
+def test_budget_exhaustion_skips_remaining_and_other_ranks_stay_silent(monkeypatch):
+    monkeypatch.setattr(bench, "_child_cmd", lambda name, args, world: [sys.executable, "-c", "print('{\"value\": 1}')"])
+    out = bench.run_other_configs(_args(), world=2, rank=1, budget_s=100.0, per_config_s=5.0)
+    assert out == {}  # only rank 0 collects
+    out = bench.run_other_configs(_args(), world=1, rank=0, budget_s=10.0, per_config_s=5.0)
+    assert all("skipped" in v["error"] for v in out.values())
+
+
+def test_children_get_their_own_rendezvous(monkeypatch):
+    """the children of the N ranks must not talk to the launcher's agent store: TORCHELASTIC_* is stripped and every
+    configuration gets its own port, identical on all ranks."""
+    seen = []
+
+    def cmd(name, args, world):
+        return [sys.executable, "-c", "import os, json; print(json.dumps({'value': 1, 'metric': 'm', 'unit': 'u', 'n_gpus': 2, "
+                "'steps': 1, 'warmup': 1, 'ms_per_step': 1.0, 'config': {'workload': os.environ['MASTER_PORT'] + ':' + "
+                "os.environ['MASTER_ADDR'] + ':' + str('TORCHELASTIC_USE_AGENT_STORE' in os.environ) + ':' + "
+                "os.environ['NK_BENCH_EXTRAS']}}))"]
+
+    monkeypatch.setattr(bench, "_child_cmd", cmd)
+    monkeypatch.setenv("MASTER_PORT", "29613")
+    monkeypatch.setenv("MASTER_ADDR", "127.0.0.1")
+    monkeypatch.setenv("TORCHELASTIC_USE_AGENT_STORE", "True")
+    out = bench.run_other_configs(_args(), world=2, rank=0, budget_s=100.0, per_config_s=10.0)
+    ports = set()
+    for name in bench.OTHER_CONFIGS:
+        port, addr, agent, extras = out[name]["workload"].split(":")
+        assert addr == "127.0.0.1" and agent == "False" and extras == "0"
+        assert 20000 <= int(port) < 40000 and int(port) != 29613
+        ports.add(port)
+    assert len(ports) == len(bench.OTHER_CONFIGS)
+
+
+def test_two_ranks_children_rendezvous_under_torchrun():
+    """the real launch shape: torchrun starts 2 parents (own process group, agent store), each spawns one child per
+    configuration; the children find each other on the fresh port and the parents' group is left alone."""
+    import subprocess
+    helpers = Path(__file__).resolve().parent / "helpers"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29641", str(helpers / "orch_parent.py")],
+                       capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")]
+    assert len(lines) == 1
+    out = json.loads(lines[0][len("RESULT "):])
+    for name in bench.OTHER_CONFIGS:
+        assert out[name]["value"] == 3.0 and out[name]["n_gpus"] == 2, out[name]
+    assert len({out[name]["workload"] for name in bench.OTHER_CONFIGS}) == 3  # one port per configuration
