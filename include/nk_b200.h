@@ -73,10 +73,21 @@ typedef struct nk_gemm_desc {
     const float* rowvec;
     const void* aux; /* bf16 */
     int32_t force_bn, force_splits;
-    int32_t force_cta_group, _reserved; /* 0 = heuristic, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2) */
+    int32_t force_cta_group; /* 0 = heuristic, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2) */
+    int32_t force_dual;      /* row-tile pairing: 0 = library mode (nk_gemm_set_dual), -1 = off, 1 = cost model, 2 = wherever legal */
 } nk_gemm_desc;
 
 int nk_gemm_ex(const nk_gemm_desc* d, nk_stream_t stream);
+
+/* Row-tile pairing of the tensor-core GEMM / implicit-GEMM convolution kernels (gemm_tc.cu, the DUAL instantiations: a CTA
+ * owns two 128-row tiles that share one B tile, 25 % fewer operand bytes per FLOP through the L2 -> SM fabric that bounds
+ * the kernel).  mode 0 = off (the library default, or NK_GEMM_DUAL), 1 = where the launch cost model expects a gain,
+ * 2 = wherever legal; anything else only queries.  Returns the previous mode.  A scheduling choice only: results are
+ * bit-identical to the unpaired kernels (same k order per output element) except for the fp32 accumulation order of
+ * split-K weight gradients.  neurosis_b200.tune enables it after checking exactly that on the device it runs on.
+ * No reference counterpart (the reference delegates every contraction to cuBLAS / cuDNN: modules/attention.py:283-290,
+ * modules/diffusion/openaimodel.py:247-301). */
+int nk_gemm_set_dual(int mode);
 
 /* y[M,N] = x[M,K] @ w[N,K]^T (+ bias[N]) (+ residual[M,N]);  y bf16 (out_f32 = 0) or fp32.
  * Replaces nn.Linear forward: modules/attention.py:283-290 (to_q/k/v/to_out), :53,:67-71 (GEGLU /

@@ -67,7 +67,7 @@ class nk_gemm_desc(ctypes.Structure):
         ("force_bn", ctypes.c_int32),
         ("force_splits", ctypes.c_int32),
         ("force_cta_group", ctypes.c_int32),
-        ("_reserved", ctypes.c_int32),
+        ("force_dual", ctypes.c_int32),
     ]
 
 

@@ -64,6 +64,7 @@ extern "C" {
 int nk_version(void) { return 100; }
 const char* nk_last_error(void) { return nk::last_error(); }
 int nk_sm_count(void) { return nk::device_sm_count(); }
+int nk_gemm_set_dual(int mode) { return nk::gemm_set_dual(mode); }
 
 int nk_gemm_ex(const nk_gemm_desc* d, nk_stream_t stream) {
     NK_REQUIRE(d != nullptr, NK_ERR_SHAPE, "null descriptor");
@@ -95,6 +96,7 @@ int nk_gemm_ex(const nk_gemm_desc* d, nk_stream_t stream) {
     p.force_bn = d->force_bn;
     p.force_splits = d->force_splits;
     p.force_cta_group = d->force_cta_group;
+    p.force_dual = d->force_dual;
     return launch_gemm(p, ::nk::enter(stream));
 }
 

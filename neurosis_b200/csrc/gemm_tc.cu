@@ -144,9 +144,18 @@ __device__ __forceinline__ void add_vec16(float (&v)[16], const float* p, bool f
 // main kernel): 0 = general, 1 = MODE_CONV_FWD_T (transposed convolution), 2 = EPI_GEGLU_FWD, 3 = EPI_GEGLU_BWD
 enum { VAR_MAIN = 0, VAR_TRANSPOSED = 1, VAR_GEGLU_FWD = 2, VAR_GEGLU_BWD = 3 };
 // TMA_OUT: the epilogue leaves through shared-memory staging tiles and TMA stores (g.tma_out says the same at run time)
-template <int CG, int VAR = VAR_MAIN, bool TMA_OUT = false>
+// DUAL (CTA pairs, VAR_MAIN): one scheduler tile is TWO row tiles that share the B tile — 256 rows per CTA, 512 per pair.
+//   The kernel is bound by the L2 -> SM operand feed (profiles/r02_gemm_vs_cublas.txt: cuBLAS and this kernel both move
+//   operands at ~9.1 TB/s, cuBLAS needs 25 % fewer bytes because its CTA owns 256 x 256 outputs); a stage then holds
+//   A0 | A1 | B-half = 48 KB for twice the MMA work of the 32 KB single-tile stage.  The two row tiles accumulate in the
+//   two 256-column TMEM buffers at the same time (no accumulator double buffering across tiles); the epilogue warps see
+//   them as two ordinary 128-row tiles (accumulator = sub-tile), so every epilogue family is unchanged.  While the
+//   epilogue drains, the producer keeps filling the ring, which is what matters in the feed-bound regime.
+template <int CG, int VAR = VAR_MAIN, bool TMA_OUT = false, bool DUAL = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmDev g) {
     constexpr bool TRANSPOSED = VAR == VAR_TRANSPOSED;
+    static_assert(!DUAL || (CG == 2 && VAR == VAR_MAIN), "DUAL: CTA pairs, general epilogue family only");
+    constexpr int A_STG = DUAL ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;  // bytes of one ring slot's A part
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024B alignment is required by the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const int num_groups = gridDim.x / CG;
     const int group = blockIdx.x / CG;
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + static_cast<size_t>(stages) * A_STAGE_BYTES;
+    uint8_t* smem_b = smem + static_cast<size_t>(stages) * A_STG;
     uint8_t* smem_stg = smem_b + static_cast<size_t>(stages) * b_stage_bytes;  // 1024-aligned (stage sizes are multiples of 2 KB)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + (TMA_OUT ? 2 * g.stg_per_half * STG_BYTES : 0));
     uint64_t* full_bar = bars;
@@ -216,10 +225,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             for (int t = group; t < total_tiles; t += num_groups) {
                 const TileCoord tc = decode_tile(g, t);
                 const int n0 = tc.nt * g.BN + static_cast<int>(rank) * BNc;  // this CTA's slice of the B tile
-                const int mt = tc.mt * CG + static_cast<int>(rank);          // this CTA's 128-row tile
+                // this CTA's 128-row tile (DUAL: the first of its two; the second lies CG tiles = one pair tile further)
+                const int mt = (DUAL ? 2 * tc.mt : tc.mt) * CG + static_cast<int>(rank);
                 const int m0 = mt * BM;
                 const int iters = iters_of_split(g, tc.split);
                 int img = 0, th = 0, tw = 0;
+                int img1 = 0, th1 = 0, tw1 = 0;  // DUAL, conv forward: pixel tile of the second row tile
                 // Every integer division in this k-loop is ~40 clk of latency that delays all operand traffic of the CTA
                 // (the conv weight gradient spent 1 500 clk per k-iteration here, 3x the tensor time).  Everything that
                 // depends only on the tile is computed once; the k-dependent indices (filter tap / channel block, or the
@@ -233,6 +244,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     tw = ptile % g.tiles_w;
                     th = (ptile / g.tiles_w) % g.tiles_h;
                     img = ptile / (g.tiles_w * g.tiles_h);  // may be >= nimg for the odd last tile: TMA zero-fills
+                    if (DUAL) {
+                        const int ptile1 = mt + CG;
+                        tw1 = ptile1 % g.tiles_w;
+                        th1 = (ptile1 / g.tiles_w) % g.tiles_h;
+                        img1 = ptile1 / (g.tiles_w * g.tiles_h);
+                    }
                     const int tap = gi0 / g.cin_blocks;
                     cb = gi0 - tap * g.cin_blocks;
                     dy = tap / g.ksize;
@@ -251,6 +268,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     my_dx = t_ % g.ksize - g.pad;
                 }
                 const int x0 = g.cstride * (tw * g.bw) - g.pad_l, y0 = g.cstride * (th * g.bh) - g.pad_t;
+                const int x1 = g.cstride * (tw1 * g.bw) - g.pad_l, y1 = g.cstride * (th1 * g.bh) - g.pad_t;
                 for (int it = 0; it < iters; ++it) {
                     const int gi = gi0 + it;
                     if (lane == 0) {
@@ -258,11 +276,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         mbar_wait(&empty_bar[stage], phase ^ 1u, 100u + stage);
                         if (g.dbg) dbg_acc0 += clock64() - tw0;
                         if (rank == 0)
-                            mbar_arrive_expect_tx(&full_bar[stage], CG * (((g.dbg_skip & 1) ? 0u : g.a_bytes) +
+                            mbar_arrive_expect_tx(&full_bar[stage], CG * (((g.dbg_skip & 1) ? 0u : (DUAL ? 2u : 1u) * g.a_bytes) +
                                                                           ((g.dbg_skip & 2) ? 0u : g.b_bytes)));
                     }
                     __syncwarp();
-                    uint8_t* sa = smem_a + static_cast<size_t>(stage) * A_STAGE_BYTES;
+                    uint8_t* sa = smem_a + static_cast<size_t>(stage) * A_STG;
                     uint8_t* sb = smem_b + static_cast<size_t>(stage) * b_stage_bytes;
                     if (VAR == VAR_GEGLU_FWD) {
                         // B = W [2D, K]: the tile's first BN/2 rows are value features [nt*BN/2, ...), the last BN/2
@@ -282,16 +300,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         }
                     } else if (g.mode == MODE_PLAIN) {
                         const int k0 = gi * BK;
-                        const int na = g.a_mn ? 2 : 1;
+                        const int na = (g.a_mn ? 2 : 1) * (DUAL ? 2 : 1);
                         const int nb = g.b_mn ? nb_atoms : 1;
                         if (g.dbg_skip && ((lane < na && (g.dbg_skip & 1)) || (lane >= na && (g.dbg_skip & 2)))) {
                             // timing experiment: this operand is not fetched (stale shared memory is multiplied)
                         } else if (lane < na) {
+                            // DUAL: lanes [0, na/2) fetch the first row tile, [na/2, na) the second (A1 follows A0 in the slot)
+                            const int sub = DUAL ? (g.a_mn ? (lane >> 1) : lane) : 0;
+                            const int at = g.a_mn ? (lane & 1) : 0;  // 64-row atom of an MN-major A tile
+                            const int ms = m0 + sub * (CG * BM);
+                            uint8_t* dst = sa + sub * A_STAGE_BYTES + at * ATOM_BYTES;
                             if (!g.a_mn)
-                                tma_load(&g.tmA, &full_bar[stage], sa, k0, m0, tc.b2 * g.a_b2, tc.b1 * g.a_b1);
+                                tma_load(&g.tmA, &full_bar[stage], dst, k0, ms, tc.b2 * g.a_b2, tc.b1 * g.a_b1);
                             else
-                                tma_load(&g.tmA, &full_bar[stage], sa + lane * ATOM_BYTES, m0 + 64 * lane, k0,
-                                         tc.b2 * g.a_b2, tc.b1 * g.a_b1);
+                                tma_load(&g.tmA, &full_bar[stage], dst, ms + 64 * at, k0, tc.b2 * g.a_b2, tc.b1 * g.a_b1);
                         } else if (lane < na + nb) {
                             const int j = lane - na;
                             if (!g.b_mn)
@@ -304,6 +326,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         if (g.mode == MODE_CONV_FWD) {
                             if (lane == 0) tma_load(&g.tmA, &full_bar[stage], sa, cb * 64, x0 + dx, y0 + dy, img);
                             else if (lane == 1) tma_load(&g.tmB, &full_bar[stage], sb, gi * BK, n0, 0, 0);
+                            else if (DUAL && lane == 2)
+                                tma_load(&g.tmA, &full_bar[stage], sa + A_STAGE_BYTES, cb * 64, x1 + dx, y1 + dy, img1);
                         } else {  // transposed: A = packed weights [Cout, taps*Cin], B = 256-pixel box
                             if (lane == 0) tma_load(&g.tmA, &full_bar[stage], sa, gi * BK, m0, 0, 0);
                             else if (lane == 1) tma_load(&g.tmB, &full_bar[stage], sb, cb * 64, x0 + dx, y0 + dy, img);
@@ -353,6 +377,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             const uint32_t b_lbo = g.b_mn ? static_cast<uint32_t>(ATOM_BYTES) : 16u;
             const uint64_t a_desc0 = make_smem_desc(smem_u32(smem_a), a_lbo, 1024u);
             const uint64_t b_desc0 = make_smem_desc(smem_u32(smem_b), b_lbo, 1024u);
+            if constexpr (DUAL) {
+                // both accumulators belong to the current scheduler tile: buffer s = row tile s, same B stage for both
+                for (int t = group; t < total_tiles; t += num_groups, ++local) {
+                    const TileCoord tc = decode_tile(g, t);
+                    const int iters = iters_of_split(g, tc.split);
+                    const uint32_t par = (static_cast<uint32_t>(local) & 1u) ^ 1u;  // n-th use of each buffer, n = local
+                    for (int it = 0; it < iters; ++it) {
+                        long long tw = g.dbg ? clock64() : 0;
+                        mbar_wait(&full_bar[stage], phase, 300u + stage);
+                        if (g.dbg) dbg_full += clock64() - tw;
+                        tc_fence_after();
+                        const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * A_STG) >> 4);
+                        const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * b_stage_bytes) >> 4);
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            if (it == 0) {  // the epilogue of the previous scheduler tile has drained this buffer
+                                tw = g.dbg ? clock64() : 0;
+                                mbar_wait(&tmem_empty[s], par, 200u + s);
+                                if (g.dbg) dbg_tempty += clock64() - tw;
+                                tc_fence_after();
+                            }
+                            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(s * ACC_STRIDE);
+                            const uint64_t a_s = a_desc + static_cast<uint64_t>((s * A_STAGE_BYTES) >> 4);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                tc_mma_ss_2cta(d_tmem, a_s + static_cast<uint64_t>(k * a_adv),
+                                               b_desc + static_cast<uint64_t>(k * b_adv), g.idesc, (it > 0 || k > 0) ? 1u : 0u);
+                            if (it == iters - 1) tc_commit_2cta(&tmem_full[s]);  // row tile s complete -> epilogue
+                        }
+                        tc_commit_2cta(&empty_bar[stage]);  // frees the smem slot once both row tiles have read it
+                        if (++stage == stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            } else
             for (int t = group; t < total_tiles; t += num_groups, ++local) {
                 const TileCoord tc = decode_tile(g, t);
                 const int iters = iters_of_split(g, tc.split);
@@ -409,8 +470,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         int stg_it = 0;  // staging-buffer alternation of the TMA-store epilogue (runs across tiles)
         const bool st_elected = (((warp - 2) & 3) == 0) && lane == 0;  // the thread of this warp-half that issues TMA stores
         long long dbg_wait = 0, dbg_proc = 0;
-        for (int t = group; t < total_tiles; t += num_groups, ++local) {
-            const TileCoord tc = decode_tile(g, t);
+        for (;; ++local) {
+            // DUAL: scheduler tile local >> 1, row tile (= accumulator) local & 1 — from here on an ordinary 128-row tile
+            const int t = group + (DUAL ? (local >> 1) : local) * num_groups;
+            if (t >= total_tiles) break;
+            TileCoord tc = decode_tile(g, t);
+            if (DUAL) tc.mt = 2 * tc.mt + (local & 1);
             const int n0 = tc.nt * g.BN;
             const int mt = tc.mt * CG + static_cast<int>(rank);
             const int acc = local & 1;
@@ -1136,6 +1201,23 @@ static int make_out_tmap(CUtensorMap* tm, const void* ptr, int is_f32, long long
     return encode_tmap(tm, ptr, 4, dims, strides, box, is_f32);
 }
 
+// Row-tile pairing (the DUAL instantiations): 0 = off, 1 = where the cost model below expects a gain, 2 = wherever legal.
+// Starts from NK_GEMM_DUAL (default 0); neurosis_b200.tune switches it on at run time after the variant has reproduced
+// the single-tile kernel's results bit for bit on the device it runs on (nk_gemm_set_dual).
+static int g_dual_mode = -1;
+static int dual_mode() {
+    if (g_dual_mode < 0) {
+        const char* e_ = getenv("NK_GEMM_DUAL");
+        g_dual_mode = e_ ? atoi(e_) : 0;
+    }
+    return g_dual_mode;
+}
+int gemm_set_dual(int mode) {
+    const int prev = dual_mode();
+    if (mode >= 0 && mode <= 2) g_dual_mode = mode;
+    return prev;
+}
+
 int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     static int nsm = 0;
     if (nsm == 0) nsm = device_sm_count();
@@ -1313,11 +1395,37 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     const int bnc = g.BN / cg;
     g.b_bytes = static_cast<uint32_t>(bnc) * 128u;
 
+    // ---- row-tile pairing (DUAL) ----
+    bool dual = false;
+    long long tiles_mb_sched = tiles_mb;  // M tiles the scheduler walks (x batches)
+    {
+        const int dm = p.force_dual > 0 ? p.force_dual : (p.force_dual < 0 ? 0 : dual_mode());
+        // (the batched attention GEMMs with their softmax epilogues stay unpaired: neurosis_b200.tune does not cover them)
+        const bool legal = cg == 2 && p.epi == EPI_LINEAR && (g.mode == MODE_PLAIN || g.mode == MODE_CONV_FWD) &&
+                           g.nb1 * g.nb2 == 1 && g.tiles_m >= 2;
+        if (dm != 0 && legal) {
+            const long long tm2 = (g.tiles_m + 1) / 2;
+            const long long single = tiles_mb * g.tiles_n, paired = tm2 * g.nb2 * g.nb1 * g.tiles_n;
+            const long long groups = nsm / cg;
+            if (dm == 2) {
+                dual = true;
+            } else if (p.out == OUT_F32_ATOMIC) {
+                // split-K spreads the work over the machine either way: pairing pays unless the odd last tile wastes much
+                dual = paired * 2 * 100 <= single * 115;
+            } else {
+                // feed-bound: a paired tile moves 48 KB per k-iteration where two single tiles move 64 KB (x 0.75)
+                const long long ws = (single + groups - 1) / groups, wd = (paired + groups - 1) / groups;
+                dual = wd * 2 * 75 < ws * 97;
+            }
+            if (dual) tiles_mb_sched = tm2 * g.nb2 * g.nb1;
+        }
+    }
+
     // split-K only when accumulating atomically: pick the split count that minimises
     // waves x (k-iterations per split + fixed per-tile cost), i.e. fills the last wave
     int splits = 1;
     if (p.out == OUT_F32_ATOMIC) {
-        const long long tiles = tiles_mb * g.tiles_n;
+        const long long tiles = tiles_mb_sched * g.tiles_n;
         const int groups = nsm / cg;
         static int env_splits = -1;
         if (env_splits < 0) {
@@ -1356,6 +1464,7 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
             const char* e_ = getenv("NK_GEMM_RASTER");
             env_raster = e_ ? atoi(e_) : 2;
         }
+        if (dual) g.tiles_m = (g.tiles_m + 1) / 2;  // from here on: scheduler tiles (the kernel derives the row tiles)
         const int conc = nsm / cg;
         int side = 1;
         while (side * side < conc) ++side;
@@ -1415,13 +1524,13 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
         }
     }
     const int staging_bytes = tma_out ? 2 * g.stg_per_half * STG_BYTES : 0;
-    const int stage_bytes = A_STAGE_BYTES + bnc * 128;
+    const int stage_bytes = (dual ? 2 : 1) * A_STAGE_BYTES + bnc * 128;
     const int max_smem = 227 * 1024;
     int stages = (max_smem - 1024 - 256 - staging_bytes) / stage_bytes;
     stages = std::max(2, std::min(stages, 8));
     g.stages = stages;
     const int smem_bytes = stages * stage_bytes + staging_bytes + 1024 /*align slack*/ + (2 * stages + 5) * 8;
-    const long long total = tiles_mb * g.tiles_n * g.splits;
+    const long long total = tiles_mb_sched * g.tiles_n * g.splits;
     NK_REQUIRE(total < (1LL << 31), NK_ERR_SHAPE, "too many tiles");
     g.dbg = dbg_buf;
     if (dbg_buf) NK_CUDA(cudaMemsetAsync(dbg_buf, 0, 8 * 1024 * sizeof(long long), stream));
@@ -1430,7 +1539,9 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     {
         const int var = geglu_fwd ? VAR_GEGLU_FWD : (geglu_bwd ? VAR_GEGLU_BWD : VAR_MAIN);
 #define NK_PICK(CGV, VARV, TMAV) \
-    if (cg == CGV && var == VARV && tma_out == TMAV) fn = reinterpret_cast<const void*>(&gemm_tc_kernel<CGV, VARV, TMAV>);
+    if (cg == CGV && var == VARV && tma_out == TMAV && !dual) fn = reinterpret_cast<const void*>(&gemm_tc_kernel<CGV, VARV, TMAV>);
+        if (dual && !tma_out) fn = reinterpret_cast<const void*>(&gemm_tc_kernel<2, VAR_MAIN, false, true>);
+        if (dual && tma_out) fn = reinterpret_cast<const void*>(&gemm_tc_kernel<2, VAR_MAIN, true, true>);
         NK_PICK(1, VAR_MAIN, false) NK_PICK(2, VAR_MAIN, false) NK_PICK(1, VAR_MAIN, true) NK_PICK(2, VAR_MAIN, true)
         NK_PICK(1, VAR_GEGLU_FWD, false) NK_PICK(2, VAR_GEGLU_FWD, false) NK_PICK(1, VAR_GEGLU_FWD, true)
         NK_PICK(2, VAR_GEGLU_FWD, true) NK_PICK(1, VAR_GEGLU_BWD, false) NK_PICK(2, VAR_GEGLU_BWD, false)

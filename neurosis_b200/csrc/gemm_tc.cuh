@@ -65,8 +65,11 @@ struct GemmProblem {
     int force_bn;             // 0 = heuristic
     int force_splits;         // 0 = heuristic (only with OUT_F32_ATOMIC)
     int force_cta_group;      // 0 = heuristic, 1 = single CTA tiles, 2 = CTA pairs (cta_group::2)
+    int force_dual;           // 0 = global mode (gemm_set_dual / NK_GEMM_DUAL), -1 = single row tiles, 1 = cost model, 2 = pair wherever legal
 };
 
 int launch_gemm(const GemmProblem& p, cudaStream_t stream);
+// row-tile pairing mode of launch_gemm (see gemm_tc.cu): 0 off, 1 cost model, 2 wherever legal; returns the previous mode
+int gemm_set_dual(int mode);
 
 }  // namespace nk

@@ -1,0 +1,245 @@
+"""Run-time selection of kernel scheduling variants, gated by an on-device equality check.
+
+One variant so far: ROW-TILE PAIRING of the tensor-core GEMM / implicit-GEMM convolution kernel (`gemm_tc_kernel<.., DUAL>`,
+csrc/gemm_tc.cu): a CTA owns two 128-row tiles that share one B tile, which cuts the operand bytes per FLOP that cross
+the L2 -> SM fabric by 25 % — the measured bound of the kernel.  It changes WHICH CTA computes an output
+tile and in which order tiles are visited, never the arithmetic of an output element, so against the unpaired kernel it
+must be bit-identical (split-K weight gradients: identical up to the fp32 accumulation order).
+
+`autotune()` checks exactly that, in a CHILD process on the same GPU (a variant that traps or dead-locks — every
+mbarrier wait of the kernels traps after 2 s — takes the child down, not the caller), times both forms on the GEMM
+shapes of the SDXL / SD1.5 steps, and switches the library to the paired form (`nk_gemm_set_dual(1)`: wherever the launch
+cost model expects a gain) only if every comparison passed and the weighted time went down.  The verdict is returned
+(bench.py prints it in its JSON line).  Environment: NK_GEMM_DUAL=0/1/2 pins the mode and skips the probe;
+NK_B200_TUNE=0 skips the probe and leaves the library default (off).
+
+No reference counterpart: the reference delegates its contractions to cuBLAS / cuDNN heuristics
+(/root/reference/src/neurosis/modules/attention.py:283-290, modules/diffusion/openaimodel.py:247-301).
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+from typing import Optional
+
+ROOT = Path(__file__).resolve().parent.parent
+
+# (kind, dims, launches per SDXL B=16 step) — the call sites of profiles/r02_gemm_callsite_breakdown_v28_b16.txt that the
+# pairing can apply to; the weights make the verdict a step-level one
+TIMED_SHAPES = [
+    ("linear_fwd", (16384, 1280, 1280), 192), ("linear_dgrad", (16384, 1280, 1280), 192),
+    ("linear_fwd", (16384, 3840, 1280), 60), ("linear_dgrad", (16384, 3840, 1280), 60),
+    ("linear_fwd", (16384, 1280, 5120), 60), ("linear_dgrad", (16384, 10240, 1280), 60),
+    ("linear_wgrad", (16384, 10240, 1280), 60), ("linear_wgrad", (16384, 1280, 5120), 60),
+    ("linear_wgrad", (16384, 3840, 1280), 55), ("linear_wgrad", (16384, 1280, 1280), 207),
+    ("linear_fwd", (65536, 640, 640), 40), ("linear_dgrad", (65536, 640, 640), 40),
+    ("linear_fwd", (65536, 5120, 640), 10), ("linear_dgrad", (65536, 5120, 640), 10),
+    ("conv", (16, 32, 32, 1280, 1280, 3), 20), ("conv", (16, 64, 64, 640, 640, 3), 12),
+    ("conv", (16, 128, 128, 320, 320, 3), 14), ("conv", (2, 512, 512, 256, 256, 3), 3),
+    ("conv", (2, 1024, 1024, 128, 128, 3), 4), ("conv", (16, 128, 128, 320, 320, 1), 2),
+]
+# equality only: ragged sizes, odd tile counts (the half-empty last pair), tiny problems, bias / residual epilogues,
+# fp32 outputs, convolutions whose image is smaller than a pixel tile
+CHECK_SHAPES = [
+    ("linear_fwd", (1232, 1280, 2048)), ("linear_fwd", (384, 320, 64)), ("linear_fwd", (640, 96, 320)),
+    ("linear_fwd", (4096 + 128, 1000, 200)), ("linear_fwd_f32", (1152, 256, 512)), ("linear_dgrad", (1232, 2048, 1280)),
+    ("linear_dgrad", (900, 320, 1280)), ("linear_wgrad", (4096, 640, 640)), ("linear_wgrad", (1232, 1280, 2048)),
+    ("linear_wgrad", (5000, 5120, 640)), ("linear_wgrad_acc", (2048, 1280, 320)),
+    ("conv", (2, 24, 16, 128, 192, 3)), ("conv", (3, 12, 20, 64, 320, 3)), ("conv", (1, 144, 112, 320, 320, 3)),
+    ("conv", (2, 8, 8, 1280, 1280, 3)), ("conv", (5, 32, 32, 640, 1280, 1)), ("conv_s2", (2, 64, 64, 320, 320, 3)),
+]
+
+
+def _make_case(kind: str, dims: tuple, dev, gen):
+    """returns fn() -> output tensor, running one launch of the call site on fixed inputs."""
+    import torch
+
+    from . import ops
+    bf = torch.bfloat16
+
+    def rnd(*shape, scale=1.0):
+        return (torch.randn(*shape, generator=gen, device=dev) * scale).to(bf)
+
+    if kind in ("linear_fwd", "linear_fwd_f32"):
+        M, N, K = dims
+        x, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+        bias = torch.randn(N, generator=gen, device=dev)
+        res = rnd(M, N)
+        f32 = kind.endswith("f32")
+        return lambda: ops.linear_fwd(x, w, bias, None if f32 else res, out_f32=f32)
+    if kind == "linear_dgrad":
+        M, N, K = dims  # dy [M, N] @ w [N, K]
+        dy, w = rnd(M, N), rnd(N, K, scale=N ** -0.5)
+        res = rnd(M, K)
+        return lambda: ops.linear_dgrad(dy, w, res)
+    if kind in ("linear_wgrad", "linear_wgrad_acc"):
+        M, N, K = dims  # dw [N, K] = dy [M, N]^T @ x [M, K]
+        dy, x = rnd(M, N, scale=M ** -0.5), rnd(M, K)
+        if kind.endswith("acc"):
+            base = torch.randn(N, K, generator=gen, device=dev)
+            return lambda: ops.linear_wgrad(dy, x, out=base.clone())
+        return lambda: ops.linear_wgrad(dy, x)
+    if kind in ("conv", "conv_s2"):
+        n, h, w_, cin, cout, ks = dims
+        x = rnd(n, h, w_, cin)
+        wt = torch.randn(cout, cin, ks, ks, generator=gen, device=dev) * (cin * ks * ks) ** -0.5
+        wp, _ = ops.packed_conv_weight(wt)
+        bias = torch.randn(cout, generator=gen, device=dev)
+        if kind == "conv_s2":
+            ho, wo = h // 2, w_ // 2
+            return lambda: ops.conv2d_stride2_fwd(x, wp, cout, ks, bias, 0, 0, ho, wo)
+        res = rnd(n, h, w_, max(cout, 64))
+        bimg = torch.randn(n, cout, generator=gen, device=dev)
+        return lambda: ops.conv2d_fwd(x, wp, cout, ks, bias, bimg, res)
+    raise ValueError(kind)
+
+
+def _time(fn, iters: int) -> float:
+    import torch
+    fn()
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def probe(device: int = 0, timed: bool = True) -> dict:
+    """IN-PROCESS comparison of the paired and the unpaired kernels (run it through `autotune()` or
+    `python -m neurosis_b200.tune --probe` unless a crash of the calling process is acceptable)."""
+    import torch
+
+    from ._lib import lib
+    torch.cuda.set_device(device)
+    dev = torch.device("cuda", device)
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    report = {"variant": "gemm_row_tile_pairing", "checks": [], "timings": [], "ok": True}
+    prev = lib.nk_gemm_set_dual(-1)
+    try:
+        for kind, dims in CHECK_SHAPES + [(k, d) for k, d, _ in TIMED_SHAPES]:
+            fn = _make_case(kind, dims, dev, gen)
+            lib.nk_gemm_set_dual(0)
+            ref = fn().float()
+            lib.nk_gemm_set_dual(2)  # wherever legal: also the shapes the cost model would leave unpaired
+            got = fn().float()
+            torch.cuda.synchronize()
+            if "wgrad" in kind:  # split-K: fp32 atomics in a different order
+                err = float((got - ref).norm() / ref.norm().clamp_min(1e-20))
+                ok = bool(torch.isfinite(got).all()) and err < 2e-6
+            else:
+                err = float((got - ref).abs().max())
+                ok = bool(torch.equal(got, ref))
+            report["checks"].append({"kind": kind, "dims": list(dims), "ok": ok, "err": err})
+            report["ok"] = report["ok"] and ok
+            del fn, ref, got
+        if timed and report["ok"]:
+            t_off = t_on = 0.0
+            for kind, dims, weight in TIMED_SHAPES:
+                fn = _make_case(kind, dims, dev, gen)
+                lib.nk_gemm_set_dual(0)
+                a = _time(fn, 8)
+                lib.nk_gemm_set_dual(1)
+                b = _time(fn, 8)
+                report["timings"].append({"kind": kind, "dims": list(dims), "launches_per_step": weight,
+                                          "ms_unpaired": a, "ms_paired_mode1": b})
+                t_off += a * weight
+                t_on += b * weight
+                del fn
+            report["step_ms_unpaired"] = t_off
+            report["step_ms_paired"] = t_on
+            report["speedup"] = t_off / t_on if t_on > 0 else 0.0
+    finally:
+        lib.nk_gemm_set_dual(prev)
+    return report
+
+
+def _summary(rep: dict, max_timings: int = 6) -> dict:
+    """what bench.py prints: verdict, weighted times, the failed checks and the largest movers."""
+    out = {k: rep[k] for k in ("variant", "ok", "step_ms_unpaired", "step_ms_paired", "speedup", "error", "enabled", "mode",
+                               "probe_wall_s", "source") if k in rep}
+    out["checks_run"] = len(rep.get("checks", []))
+    bad = [c for c in rep.get("checks", []) if not c["ok"]]
+    if bad:
+        out["failed_checks"] = bad[:8]
+    tm = sorted(rep.get("timings", []), key=lambda r: -(r["ms_unpaired"] - r["ms_paired_mode1"]) * r["launches_per_step"])
+    if tm:
+        out["largest_gains"] = [{"kind": r["kind"], "dims": r["dims"], "ms": [round(r["ms_unpaired"], 4), round(r["ms_paired_mode1"], 4)]}
+                                for r in tm[:max_timings]]
+        out["largest_losses"] = [{"kind": r["kind"], "dims": r["dims"], "ms": [round(r["ms_unpaired"], 4), round(r["ms_paired_mode1"], 4)]}
+                                 for r in tm[::-1][:3] if r["ms_paired_mode1"] > r["ms_unpaired"]]
+    return out
+
+
+def autotune(device: int = 0, timeout_s: float = 120.0, min_speedup: float = 1.01) -> dict:
+    """probe in a child process, then set the library mode of THIS process.  Never raises: any failure leaves the
+    library at its default (unpaired) and is reported in the returned dict."""
+    from ._lib import lib
+    env_mode = os.environ.get("NK_GEMM_DUAL")
+    if env_mode is not None:
+        return {"variant": "gemm_row_tile_pairing", "enabled": env_mode not in ("", "0"), "mode": int(env_mode or 0),
+                "source": "NK_GEMM_DUAL (pinned, no probe)"}
+    if os.environ.get("NK_B200_TUNE", "1") == "0":
+        return {"variant": "gemm_row_tile_pairing", "enabled": False, "mode": 0, "source": "NK_B200_TUNE=0 (no probe)"}
+    t0 = time.monotonic()
+    rep: dict = {"variant": "gemm_row_tile_pairing", "ok": False}
+    try:
+        import signal
+        proc = subprocess.Popen([sys.executable, "-m", "neurosis_b200.tune", "--probe", "--device", str(device)],
+                                stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=str(ROOT),
+                                start_new_session=True, env={**os.environ, "NK_B200_TUNE": "0"})
+        try:
+            so, se = proc.communicate(timeout=timeout_s)
+        except subprocess.TimeoutExpired:
+            try:
+                os.killpg(proc.pid, signal.SIGKILL)
+            except Exception:  # noqa: BLE001
+                proc.kill()
+            so, se = proc.communicate()
+            rep["error"] = f"probe exceeded {timeout_s:.0f} s"
+        for ln in reversed((so or "").strip().splitlines()):
+            if ln.startswith("{"):
+                rep = json.loads(ln)
+                break
+        else:
+            rep.setdefault("error", f"probe exit {proc.returncode}: " + " | ".join((se or "").strip().splitlines()[-3:])[-300:])
+    except Exception as e:  # noqa: BLE001
+        rep["error"] = repr(e)
+    rep["probe_wall_s"] = round(time.monotonic() - t0, 1)
+    enable = bool(rep.get("ok")) and float(rep.get("speedup", 0.0)) >= min_speedup
+    rep["enabled"], rep["mode"] = enable, 1 if enable else 0
+    rep["source"] = "on-device probe (child process)"
+    lib.nk_gemm_set_dual(1 if enable else 0)
+    return rep
+
+
+def apply(mode: int) -> int:
+    """set the pairing mode of this process (0 off, 1 cost model, 2 wherever legal); returns the previous mode."""
+    from ._lib import lib
+    return lib.nk_gemm_set_dual(int(mode))
+
+
+def main(argv: Optional[list] = None) -> int:
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--probe", action="store_true")
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--no-timing", action="store_true")
+    a = ap.parse_args(argv)
+    if a.probe:
+        rep = probe(a.device, timed=not a.no_timing)
+        print(json.dumps(rep), flush=True)
+        return 0 if rep["ok"] else 1
+    print(json.dumps(_summary(autotune(a.device))), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
