@@ -50,7 +50,8 @@ CHECK_SHAPES = [
     ("linear_dgrad", (900, 320, 1280)), ("linear_wgrad", (4096, 640, 640)), ("linear_wgrad", (1232, 1280, 2048)),
     ("linear_wgrad", (5000, 5120, 640)), ("linear_wgrad_acc", (2048, 1280, 320)),
     ("conv", (2, 24, 16, 128, 192, 3)), ("conv", (3, 12, 20, 64, 320, 3)), ("conv", (1, 144, 112, 320, 320, 3)),
-    ("conv", (2, 8, 8, 1280, 1280, 3)), ("conv", (5, 32, 32, 640, 1280, 1)), ("conv_s2", (2, 64, 64, 320, 320, 3)),
+    ("conv", (2, 8, 8, 1280, 1280, 3)), ("conv", (5, 8, 8, 640, 640, 3)), ("conv", (5, 32, 32, 640, 1280, 1)),
+    ("conv_s2", (2, 64, 64, 320, 320, 3)), ("conv_s2", (3, 32, 32, 640, 640, 3)),
 ]
 
 
