@@ -305,6 +305,7 @@ def _autotune(world: int, local: int, dev) -> dict:
             rep["note"] = "another rank rejected the variant"
             tune.apply(0)
     os.environ["NK_GEMM_DUAL"] = str(rep.get("mode", 0))
+    os.environ["NK_GEMM_DUAL_MIN_K"] = str(int(rep.get("min_k_iters") or 0) if rep.get("enabled") else 0)
     return tune._summary(rep)
 
 

@@ -88,6 +88,11 @@ int nk_gemm_ex(const nk_gemm_desc* d, nk_stream_t stream);
  * No reference counterpart (the reference delegates every contraction to cuBLAS / cuDNN: modules/attention.py:283-290,
  * modules/diffusion/openaimodel.py:247-301). */
 int nk_gemm_set_dual(int mode);
+/* Mode 1 pairs only launches whose reduction has at least k_iters 64-deep k-iterations (K / 64; convolutions: taps * Cin / 64):
+ * with a short reduction the two epilogues that pairing exposes per scheduler tile outweigh the saved operand traffic.
+ * neurosis_b200.tune measures the break-even on the device; NK_GEMM_DUAL_MIN_K pins it.  k_iters < 0 only queries.
+ * Returns the previous value (default 0 = no limit). */
+int nk_gemm_set_dual_min_k(int k_iters);
 
 /* y[M,N] = x[M,K] @ w[N,K]^T (+ bias[N]) (+ residual[M,N]);  y bf16 (out_f32 = 0) or fp32.
  * Replaces nn.Linear forward: modules/attention.py:283-290 (to_q/k/v/to_out), :53,:67-71 (GEGLU /

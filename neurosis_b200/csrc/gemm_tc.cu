@@ -1217,6 +1217,22 @@ int gemm_set_dual(int mode) {
     if (mode >= 0 && mode <= 2) g_dual_mode = mode;
     return prev;
 }
+// mode 1 pairs only launches with at least this many 64-deep k-iterations: with a short reduction the two epilogues that
+// pairing exposes per scheduler tile outweigh the saved operand traffic.  Where the break-even lies is measured by
+// neurosis_b200.tune on the device (NK_GEMM_DUAL_MIN_K pins it; default 0 = no limit).
+static int g_dual_min_k = -1;
+static int dual_min_k() {
+    if (g_dual_min_k < 0) {
+        const char* e_ = getenv("NK_GEMM_DUAL_MIN_K");
+        g_dual_min_k = e_ ? std::max(0, atoi(e_)) : 0;
+    }
+    return g_dual_min_k;
+}
+int gemm_set_dual_min_k(int k_iters) {
+    const int prev = dual_min_k();
+    if (k_iters >= 0) g_dual_min_k = k_iters;
+    return prev;
+}
 
 int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     static int nsm = 0;
@@ -1409,6 +1425,8 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
             const long long groups = nsm / cg;
             if (dm == 2) {
                 dual = true;
+            } else if (g.k_iters_total < dual_min_k()) {
+                dual = false;  // reduction too short for pairing to pay (threshold measured by neurosis_b200.tune)
             } else if (p.out == OUT_F32_ATOMIC) {
                 // split-K spreads the work over the machine either way: pairing pays unless the odd last tile wastes much
                 dual = paired * 2 * 100 <= single * 115;

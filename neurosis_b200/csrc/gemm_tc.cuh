@@ -71,5 +71,7 @@ struct GemmProblem {
 int launch_gemm(const GemmProblem& p, cudaStream_t stream);
 // row-tile pairing mode of launch_gemm (see gemm_tc.cu): 0 off, 1 cost model, 2 wherever legal; returns the previous mode
 int gemm_set_dual(int mode);
+// mode 1 only: smallest number of 64-deep k-iterations a launch must have to be paired (< 0 queries); returns the previous value
+int gemm_set_dual_min_k(int k_iters);
 
 }  // namespace nk

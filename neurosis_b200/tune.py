@@ -9,8 +9,9 @@ must be bit-identical (split-K weight gradients: identical up to the fp32 accumu
 `autotune()` checks exactly that, in a CHILD process on the same GPU (a variant that traps or dead-locks — every
 mbarrier wait of the kernels traps after 2 s — takes the child down, not the caller), times both forms on the GEMM
 shapes of the SDXL / SD1.5 steps, and switches the library to the paired form (`nk_gemm_set_dual(1)`: wherever the launch
-cost model expects a gain) only if every comparison passed and the weighted time went down.  The verdict is returned
-(bench.py prints it in its JSON line).  Environment: NK_GEMM_DUAL=0/1/2 pins the mode and skips the probe;
+cost model expects a gain, and only for reductions at least as deep as the measured break-even, `nk_gemm_set_dual_min_k`)
+only if every comparison passed and the weighted time went down.  The verdict is returned
+(bench.py prints it in its JSON line).  Environment: NK_GEMM_DUAL=0/1/2 (with NK_GEMM_DUAL_MIN_K) pins the mode and skips the probe;
 NK_B200_TUNE=0 skips the probe and leaves the library default (off).
 
 No reference counterpart: the reference delegates its contractions to cuBLAS / cuDNN heuristics
@@ -99,6 +100,29 @@ def _make_case(kind: str, dims: tuple, dev, gen):
     raise ValueError(kind)
 
 
+def _k_iters(kind: str, dims: tuple) -> int:
+    """64-deep k-iterations of the launch (what `nk_gemm_set_dual_min_k` thresholds)."""
+    if kind.startswith("linear_fwd"):
+        return (dims[2] + 63) // 64
+    if kind == "linear_dgrad":
+        return (dims[1] + 63) // 64
+    if kind.startswith("linear_wgrad"):
+        return (dims[0] + 63) // 64
+    n, h, w_, cin, cout, ks = dims
+    return ks * ks * cin // 64
+
+
+def pick_min_k(rows: list, tol: float = 1.02) -> Optional[int]:
+    """smallest reduction depth T such that mode 1 is no slower (within timing noise `tol`) than the unpaired kernel on
+    EVERY measured shape with k_iters >= T; None if there is no such depth (pairing never pays).  Launches the cost model
+    leaves unpaired run the same kernel in both columns and pass trivially."""
+    depths = sorted({r["k_iters"] for r in rows})
+    for T in depths:
+        if all(r["ms_mode1_no_limit"] <= tol * r["ms_unpaired"] for r in rows if r["k_iters"] >= T):
+            return T
+    return None
+
+
 def _time(fn, iters: int) -> float:
     import torch
     fn()
@@ -124,6 +148,8 @@ def probe(device: int = 0, timed: bool = True) -> dict:
     gen = torch.Generator(device=dev).manual_seed(1234)
     report = {"variant": "gemm_row_tile_pairing", "checks": [], "timings": [], "ok": True}
     prev = lib.nk_gemm_set_dual(-1)
+    prev_k = lib.nk_gemm_set_dual_min_k(-1)
+    lib.nk_gemm_set_dual_min_k(0)
     try:
         for kind, dims in CHECK_SHAPES + [(k, d) for k, d, _ in TIMED_SHAPES]:
             fn = _make_case(kind, dims, dev, gen)
@@ -142,35 +168,53 @@ def probe(device: int = 0, timed: bool = True) -> dict:
             report["ok"] = report["ok"] and ok
             del fn, ref, got
         if timed and report["ok"]:
-            t_off = t_on = 0.0
+            # pass 1: every step shape unpaired and in mode 1 without a depth limit (the cost model alone decides which
+            # launches pair) -> where, in reduction depth, pairing starts to pay
+            rows = []
             for kind, dims, weight in TIMED_SHAPES:
                 fn = _make_case(kind, dims, dev, gen)
                 lib.nk_gemm_set_dual(0)
                 a = _time(fn, 8)
                 lib.nk_gemm_set_dual(1)
                 b = _time(fn, 8)
-                report["timings"].append({"kind": kind, "dims": list(dims), "launches_per_step": weight,
-                                          "ms_unpaired": a, "ms_paired_mode1": b})
-                t_off += a * weight
-                t_on += b * weight
+                rows.append({"kind": kind, "dims": list(dims), "launches_per_step": weight, "k_iters": _k_iters(kind, dims),
+                             "ms_unpaired": a, "ms_mode1_no_limit": b})
                 del fn
+            min_k = pick_min_k(rows)
+            report["min_k_iters"] = min_k
+            # pass 2: the mode that would be used (cost model + threshold) against unpaired, weighted by launches per step
+            t_off = t_on = 0.0
+            if min_k is not None:
+                lib.nk_gemm_set_dual_min_k(min_k)
+                for r, (kind, dims, weight) in zip(rows, TIMED_SHAPES):
+                    fn = _make_case(kind, dims, dev, gen)
+                    lib.nk_gemm_set_dual(1)
+                    r["ms_paired_mode1"] = _time(fn, 8)
+                    lib.nk_gemm_set_dual(0)
+                    r["ms_unpaired"] = min(r["ms_unpaired"], _time(fn, 8))  # second sample of the baseline, same thermal state
+                    t_off += r["ms_unpaired"] * weight
+                    t_on += r["ms_paired_mode1"] * weight
+                    del fn
+            report["timings"] = rows
             report["step_ms_unpaired"] = t_off
             report["step_ms_paired"] = t_on
             report["speedup"] = t_off / t_on if t_on > 0 else 0.0
     finally:
         lib.nk_gemm_set_dual(prev)
+        lib.nk_gemm_set_dual_min_k(prev_k)
     return report
 
 
 def _summary(rep: dict, max_timings: int = 6) -> dict:
     """what bench.py prints: verdict, weighted times, the failed checks and the largest movers."""
     out = {k: rep[k] for k in ("variant", "ok", "step_ms_unpaired", "step_ms_paired", "speedup", "error", "enabled", "mode",
-                               "probe_wall_s", "source") if k in rep}
+                               "probe_wall_s", "source", "min_k_iters", "note") if k in rep}
     out["checks_run"] = len(rep.get("checks", []))
     bad = [c for c in rep.get("checks", []) if not c["ok"]]
     if bad:
         out["failed_checks"] = bad[:8]
-    tm = sorted(rep.get("timings", []), key=lambda r: -(r["ms_unpaired"] - r["ms_paired_mode1"]) * r["launches_per_step"])
+    tm = sorted((r for r in rep.get("timings", []) if "ms_paired_mode1" in r),
+                key=lambda r: -(r["ms_unpaired"] - r["ms_paired_mode1"]) * r["launches_per_step"])
     if tm:
         out["largest_gains"] = [{"kind": r["kind"], "dims": r["dims"], "ms": [round(r["ms_unpaired"], 4), round(r["ms_paired_mode1"], 4)]}
                                 for r in tm[:max_timings]]
@@ -214,9 +258,10 @@ def autotune(device: int = 0, timeout_s: float = 120.0, min_speedup: float = 1.0
     except Exception as e:  # noqa: BLE001
         rep["error"] = repr(e)
     rep["probe_wall_s"] = round(time.monotonic() - t0, 1)
-    enable = bool(rep.get("ok")) and float(rep.get("speedup", 0.0)) >= min_speedup
+    enable = bool(rep.get("ok")) and rep.get("min_k_iters") is not None and float(rep.get("speedup", 0.0)) >= min_speedup
     rep["enabled"], rep["mode"] = enable, 1 if enable else 0
     rep["source"] = "on-device probe (child process)"
+    lib.nk_gemm_set_dual_min_k(int(rep["min_k_iters"]) if enable else 0)
     lib.nk_gemm_set_dual(1 if enable else 0)
     return rep
 

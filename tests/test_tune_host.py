@@ -34,6 +34,9 @@ def test_pinned_and_disabled_environments_skip_the_probe(monkeypatch):
 
 def test_failed_probe_leaves_the_default_kernels(monkeypatch):
     """no CUDA device here: the child exits with an error -> not enabled, mode 0, the reason is reported."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine WITHOUT a CUDA device (the probe must fail)")
     monkeypatch.delenv("NK_GEMM_DUAL", raising=False)
     monkeypatch.delenv("NK_B200_TUNE", raising=False)
     lib.nk_gemm_set_dual(2)
@@ -56,14 +59,18 @@ def test_verdict_rules(monkeypatch):
 
     monkeypatch.delenv("NK_GEMM_DUAL", raising=False)
     monkeypatch.delenv("NK_B200_TUNE", raising=False)
-    cases = [({"ok": True, "speedup": 1.08, "checks": [], "timings": []}, True),
-             ({"ok": True, "speedup": 1.001, "checks": [], "timings": []}, False),
-             ({"ok": False, "speedup": 1.5, "checks": [{"kind": "conv", "dims": [1], "ok": False, "err": 3.0}], "timings": []}, False)]
+    cases = [({"ok": True, "speedup": 1.08, "min_k_iters": 20, "checks": [], "timings": []}, True),
+             ({"ok": True, "speedup": 1.001, "min_k_iters": 10, "checks": [], "timings": []}, False),
+             ({"ok": True, "speedup": 0.0, "min_k_iters": None, "checks": [], "timings": []}, False),
+             ({"ok": False, "speedup": 1.5, "min_k_iters": 10,
+               "checks": [{"kind": "conv", "dims": [1], "ok": False, "err": 3.0}], "timings": []}, False)]
     for rep, want in cases:
         monkeypatch.setattr(subprocess, "Popen", lambda *a, _r=rep, **k: FakeProc(_r))
         got = tune.autotune()
         assert got["enabled"] is want and lib.nk_gemm_set_dual(-1) == (1 if want else 0)
+        assert lib.nk_gemm_set_dual_min_k(-1) == (rep["min_k_iters"] if want else 0)
     lib.nk_gemm_set_dual(0)
+    lib.nk_gemm_set_dual_min_k(0)
 
 
 def test_probe_shapes_cover_every_paired_mode():
@@ -72,3 +79,17 @@ def test_probe_shapes_cover_every_paired_mode():
     # odd pair-tile counts (the half-empty last pair) are present for a matrix and for an image operand
     assert any(k == "linear_fwd" and ((d[0] + 127) // 128 + 1) // 2 % 2 == 1 for k, d in tune.CHECK_SHAPES)
     assert any(k == "conv" and d[0] * d[1] * d[2] < 128 * 2 for k, d in tune.CHECK_SHAPES)
+
+
+def test_depth_threshold_selection():
+    """pick_min_k: the smallest reduction depth from which mode 1 never loses (2 % timing noise allowed)."""
+    def row(k, off, on):
+        return {"k_iters": k, "ms_unpaired": off, "ms_mode1_no_limit": on}
+    assert tune.pick_min_k([row(10, 1.0, 1.2), row(20, 1.0, 0.9), row(80, 1.0, 0.8), row(256, 1.0, 1.01)]) == 20
+    assert tune.pick_min_k([row(10, 1.0, 0.9), row(20, 1.0, 0.9)]) == 10
+    assert tune.pick_min_k([row(10, 1.0, 0.9), row(256, 1.0, 1.3)]) is None  # loses at the deepest reductions: never pays
+    assert tune._k_iters("linear_fwd", (16384, 1280, 5120)) == 80 and tune._k_iters("linear_dgrad", (16384, 10240, 1280)) == 160
+    assert tune._k_iters("linear_wgrad", (16384, 1280, 1280)) == 256 and tune._k_iters("conv", (16, 32, 32, 1280, 1280, 3)) == 180
+    assert lib.nk_gemm_set_dual_min_k(-1) >= 0
+    prev = lib.nk_gemm_set_dual_min_k(20)
+    assert lib.nk_gemm_set_dual_min_k(prev) == 20
