@@ -306,6 +306,7 @@ def _autotune(world: int, local: int, dev) -> dict:
             tune.apply(0)
     os.environ["NK_GEMM_DUAL"] = str(rep.get("mode", 0))
     os.environ["NK_GEMM_DUAL_MIN_K"] = str(int(rep.get("min_k_iters") or 0) if rep.get("enabled") else 0)
+    os.environ["NK_GEMM_DUAL_SKEW"] = str(int(rep.get("skew") or 0) if rep.get("enabled") else 0)
     return tune._summary(rep)
 
 

@@ -93,6 +93,11 @@ int nk_gemm_set_dual(int mode);
  * neurosis_b200.tune measures the break-even on the device; NK_GEMM_DUAL_MIN_K pins it.  k_iters < 0 only queries.
  * Returns the previous value (default 0 = no limit). */
 int nk_gemm_set_dual_min_k(int k_iters);
+/* Paired launches: the MMA issuer lets the second row tile trail the first by k_iters k-iterations (0 = interleaved; the
+ * kernel clamps to ring depth - 1), so that the first tile starts while the epilogue still drains the other TMEM buffer
+ * and reaches its own epilogue earlier.  Does not change results.  0..7 sets, anything else queries; returns the previous
+ * value (default 0, or NK_GEMM_DUAL_SKEW). */
+int nk_gemm_set_dual_skew(int k_iters);
 
 /* y[M,N] = x[M,K] @ w[N,K]^T (+ bias[N]) (+ residual[M,N]);  y bf16 (out_f32 = 0) or fp32.
  * Replaces nn.Linear forward: modules/attention.py:283-290 (to_q/k/v/to_out), :53,:67-71 (GEGLU /

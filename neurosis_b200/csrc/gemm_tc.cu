@@ -63,6 +63,7 @@ struct alignas(64) GemmDev {
     int mode;
     int dbg_skip;                // NK_GEMM_DBG_SKIP bit 1: no A loads, bit 2: no B loads (timing experiments, wrong results)
     int raster_gm;               // > 0: tiles are walked in groups of raster_gm row blocks x all N tiles (see launch_gemm)
+    int dual_skew;               // DUAL: k-iterations by which row tile 1 trails row tile 0 (clamped to stages - 1 in the kernel)
     int a_b2, a_b1, b_b2, b_b1;  // 0/1: does the operand carry that batch dimension
     // conv geometry
     int cH, cW, bw, bh, tiles_w, tiles_h, cin_blocks, ksize, pad;  // cH, cW: OUTPUT image (= input unless strided)
@@ -378,38 +379,59 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             const uint64_t a_desc0 = make_smem_desc(smem_u32(smem_a), a_lbo, 1024u);
             const uint64_t b_desc0 = make_smem_desc(smem_u32(smem_b), b_lbo, 1024u);
             if constexpr (DUAL) {
-                // both accumulators belong to the current scheduler tile: buffer s = row tile s, same B stage for both
+                // Both accumulators belong to the current scheduler tile: buffer s = row tile s, same B slot for both.
+                // Row tile 1 trails row tile 0 by `sk` k-iterations (g.dual_skew, at most stages - 1: the slot of
+                // k-iteration j is reused by j + stages, and it is row tile 1 that frees it).  The lead lets row tile 0
+                // start while the epilogue still drains buffer 1 of the previous scheduler tile, and hands buffer 0 to
+                // the epilogue `sk` k-iterations before buffer 1 is complete; sk = 0 is the plain interleaved order.
                 for (int t = group; t < total_tiles; t += num_groups, ++local) {
                     const TileCoord tc = decode_tile(g, t);
                     const int iters = iters_of_split(g, tc.split);
+                    const int sk = min(min(g.dual_skew, stages - 1), iters);
                     const uint32_t par = (static_cast<uint32_t>(local) & 1u) ^ 1u;  // n-th use of each buffer, n = local
-                    for (int it = 0; it < iters; ++it) {
-                        long long tw = g.dbg ? clock64() : 0;
-                        mbar_wait(&full_bar[stage], phase, 300u + stage);
-                        if (g.dbg) dbg_full += clock64() - tw;
-                        tc_fence_after();
-                        const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * A_STG) >> 4);
-                        const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * b_stage_bytes) >> 4);
-#pragma unroll
-                        for (int s = 0; s < 2; ++s) {
-                            if (it == 0) {  // the epilogue of the previous scheduler tile has drained this buffer
+                    int st1 = stage;  // ring position of row tile 1 (row tile 0 walks `stage` / `phase`)
+                    for (int j = 0; j < iters + sk; ++j) {
+                        if (j < iters) {  // ---- row tile 0, k-iteration j
+                            long long tw = g.dbg ? clock64() : 0;
+                            mbar_wait(&full_bar[stage], phase, 300u + stage);
+                            if (g.dbg) dbg_full += clock64() - tw;
+                            tc_fence_after();
+                            if (j == 0) {  // the epilogue of the previous scheduler tile has drained buffer 0
                                 tw = g.dbg ? clock64() : 0;
-                                mbar_wait(&tmem_empty[s], par, 200u + s);
+                                mbar_wait(&tmem_empty[0], par, 200u);
                                 if (g.dbg) dbg_tempty += clock64() - tw;
                                 tc_fence_after();
                             }
-                            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(s * ACC_STRIDE);
-                            const uint64_t a_s = a_desc + static_cast<uint64_t>((s * A_STAGE_BYTES) >> 4);
+                            const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * A_STG) >> 4);
+                            const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * b_stage_bytes) >> 4);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
-                                tc_mma_ss_2cta(d_tmem, a_s + static_cast<uint64_t>(k * a_adv),
-                                               b_desc + static_cast<uint64_t>(k * b_adv), g.idesc, (it > 0 || k > 0) ? 1u : 0u);
-                            if (it == iters - 1) tc_commit_2cta(&tmem_full[s]);  // row tile s complete -> epilogue
+                                tc_mma_ss_2cta(tmem_base, a_desc + static_cast<uint64_t>(k * a_adv),
+                                               b_desc + static_cast<uint64_t>(k * b_adv), g.idesc, (j > 0 || k > 0) ? 1u : 0u);
+                            if (j == iters - 1) tc_commit_2cta(&tmem_full[0]);  // row tile 0 complete -> epilogue
+                            if (++stage == stages) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
                         }
-                        tc_commit_2cta(&empty_bar[stage]);  // frees the smem slot once both row tiles have read it
-                        if (++stage == stages) {
-                            stage = 0;
-                            phase ^= 1u;
+                        if (j >= sk) {  // ---- row tile 1, k-iteration j - sk (its slot was waited for by row tile 0)
+                            const int j1 = j - sk;
+                            if (j1 == 0) {
+                                const long long tw = g.dbg ? clock64() : 0;
+                                mbar_wait(&tmem_empty[1], par, 201u);
+                                if (g.dbg) dbg_tempty += clock64() - tw;
+                                tc_fence_after();
+                            }
+                            const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((st1 * A_STG + A_STAGE_BYTES) >> 4);
+                            const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((st1 * b_stage_bytes) >> 4);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                tc_mma_ss_2cta(tmem_base + static_cast<uint32_t>(ACC_STRIDE),
+                                               a_desc + static_cast<uint64_t>(k * a_adv),
+                                               b_desc + static_cast<uint64_t>(k * b_adv), g.idesc, (j1 > 0 || k > 0) ? 1u : 0u);
+                            if (j1 == iters - 1) tc_commit_2cta(&tmem_full[1]);  // row tile 1 complete -> epilogue
+                            tc_commit_2cta(&empty_bar[st1]);  // frees the smem slot: both row tiles have read it
+                            if (++st1 == stages) st1 = 0;
                         }
                     }
                 }
@@ -1228,6 +1250,21 @@ static int dual_min_k() {
     }
     return g_dual_min_k;
 }
+// DUAL: k-iterations by which the second row tile trails the first (see the MMA issuer); 0 = interleaved.  Clamped to
+// stages - 1 by the kernel.  NK_GEMM_DUAL_SKEW pins it; default 0 until neurosis_b200.tune has measured it.
+static int g_dual_skew = -1;
+static int dual_skew() {
+    if (g_dual_skew < 0) {
+        const char* e_ = getenv("NK_GEMM_DUAL_SKEW");
+        g_dual_skew = e_ ? std::max(0, std::min(7, atoi(e_))) : 0;
+    }
+    return g_dual_skew;
+}
+int gemm_set_dual_skew(int k_iters) {
+    const int prev = dual_skew();
+    if (k_iters >= 0 && k_iters <= 7) g_dual_skew = k_iters;
+    return prev;
+}
 int gemm_set_dual_min_k(int k_iters) {
     const int prev = dual_min_k();
     if (k_iters >= 0) g_dual_min_k = k_iters;
@@ -1436,6 +1473,7 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
                 dual = wd * 2 * 75 < ws * 97;
             }
             if (dual) tiles_mb_sched = tm2 * g.nb2 * g.nb1;
+            g.dual_skew = dual ? dual_skew() : 0;
         }
     }
 

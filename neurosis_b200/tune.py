@@ -137,7 +137,10 @@ def _time(fn, iters: int) -> float:
     return e0.elapsed_time(e1) / iters
 
 
-def probe(device: int = 0, timed: bool = True) -> dict:
+SKEWS = (0, 3)  # candidates of `nk_gemm_set_dual_skew`, plain order first (the kernel clamps to ring depth - 1)
+
+
+def probe(device: int = 0, timed: bool = True, skew: int = 0) -> dict:
     """IN-PROCESS comparison of the paired and the unpaired kernels (run it through `autotune()` or
     `python -m neurosis_b200.tune --probe` unless a crash of the calling process is acceptable)."""
     import torch
@@ -146,10 +149,12 @@ def probe(device: int = 0, timed: bool = True) -> dict:
     torch.cuda.set_device(device)
     dev = torch.device("cuda", device)
     gen = torch.Generator(device=dev).manual_seed(1234)
-    report = {"variant": "gemm_row_tile_pairing", "checks": [], "timings": [], "ok": True}
+    report = {"variant": "gemm_row_tile_pairing", "skew": skew, "checks": [], "timings": [], "ok": True}
     prev = lib.nk_gemm_set_dual(-1)
     prev_k = lib.nk_gemm_set_dual_min_k(-1)
+    prev_s = lib.nk_gemm_set_dual_skew(-1)
     lib.nk_gemm_set_dual_min_k(0)
+    lib.nk_gemm_set_dual_skew(skew)
     try:
         for kind, dims in CHECK_SHAPES + [(k, d) for k, d, _ in TIMED_SHAPES]:
             fn = _make_case(kind, dims, dev, gen)
@@ -202,13 +207,14 @@ def probe(device: int = 0, timed: bool = True) -> dict:
     finally:
         lib.nk_gemm_set_dual(prev)
         lib.nk_gemm_set_dual_min_k(prev_k)
+        lib.nk_gemm_set_dual_skew(prev_s)
     return report
 
 
 def _summary(rep: dict, max_timings: int = 6) -> dict:
     """what bench.py prints: verdict, weighted times, the failed checks and the largest movers."""
     out = {k: rep[k] for k in ("variant", "ok", "step_ms_unpaired", "step_ms_paired", "speedup", "error", "enabled", "mode",
-                               "probe_wall_s", "source", "min_k_iters", "note") if k in rep}
+                               "probe_wall_s", "source", "min_k_iters", "skew", "candidates", "note") if k in rep}
     out["checks_run"] = len(rep.get("checks", []))
     bad = [c for c in rep.get("checks", []) if not c["ok"]]
     if bad:
@@ -223,14 +229,15 @@ def _summary(rep: dict, max_timings: int = 6) -> dict:
     return out
 
 
-def autotune(device: int = 0, timeout_s: float = 120.0, min_speedup: float = 1.01) -> dict:
+def autotune(device: int = 0, timeout_s: float = 150.0, min_speedup: float = 1.01) -> dict:
     """probe in a child process, then set the library mode of THIS process.  Never raises: any failure leaves the
     library at its default (unpaired) and is reported in the returned dict."""
     from ._lib import lib
     env_mode = os.environ.get("NK_GEMM_DUAL")
     if env_mode is not None:
         return {"variant": "gemm_row_tile_pairing", "enabled": env_mode not in ("", "0"), "mode": int(env_mode or 0),
-                "source": "NK_GEMM_DUAL (pinned, no probe)"}
+                "min_k_iters": int(os.environ.get("NK_GEMM_DUAL_MIN_K", "0") or 0),
+                "skew": int(os.environ.get("NK_GEMM_DUAL_SKEW", "0") or 0), "source": "NK_GEMM_DUAL (pinned, no probe)"}
     if os.environ.get("NK_B200_TUNE", "1") == "0":
         return {"variant": "gemm_row_tile_pairing", "enabled": False, "mode": 0, "source": "NK_B200_TUNE=0 (no probe)"}
     t0 = time.monotonic()
@@ -249,11 +256,25 @@ def autotune(device: int = 0, timeout_s: float = 120.0, min_speedup: float = 1.0
                 proc.kill()
             so, se = proc.communicate()
             rep["error"] = f"probe exceeded {timeout_s:.0f} s"
-        for ln in reversed((so or "").strip().splitlines()):
+        cands = []
+        for ln in (so or "").strip().splitlines():
             if ln.startswith("{"):
-                rep = json.loads(ln)
-                break
-        else:
+                try:
+                    cands.append(json.loads(ln))
+                except Exception:  # noqa: BLE001
+                    pass
+        good = [c for c in cands if c.get("ok") and c.get("min_k_iters") is not None]
+        if good:  # the fastest candidate that reproduced the unpaired kernels
+            rep = max(good, key=lambda c: float(c.get("speedup", 0.0)))
+        elif cands:
+            rep = cands[0]
+        if cands:
+            rep["candidates"] = [{"skew": c.get("skew"), "ok": c.get("ok"), "speedup": c.get("speedup"),
+                                  "min_k_iters": c.get("min_k_iters")} for c in cands]
+        if len(cands) < len(SKEWS) or proc.returncode not in (0, 1):
+            rep.setdefault("note", f"probe child ended early (exit {proc.returncode}) after {len(cands)} of {len(SKEWS)} candidates: "
+                           + " | ".join((se or "").strip().splitlines()[-2:])[-300:])
+        if not cands:
             rep.setdefault("error", f"probe exit {proc.returncode}: " + " | ".join((se or "").strip().splitlines()[-3:])[-300:])
     except Exception as e:  # noqa: BLE001
         rep["error"] = repr(e)
@@ -262,6 +283,7 @@ def autotune(device: int = 0, timeout_s: float = 120.0, min_speedup: float = 1.0
     rep["enabled"], rep["mode"] = enable, 1 if enable else 0
     rep["source"] = "on-device probe (child process)"
     lib.nk_gemm_set_dual_min_k(int(rep["min_k_iters"]) if enable else 0)
+    lib.nk_gemm_set_dual_skew(int(rep.get("skew", 0)) if enable else 0)
     lib.nk_gemm_set_dual(1 if enable else 0)
     return rep
 
@@ -280,9 +302,12 @@ def main(argv: Optional[list] = None) -> int:
     ap.add_argument("--no-timing", action="store_true")
     a = ap.parse_args(argv)
     if a.probe:
-        rep = probe(a.device, timed=not a.no_timing)
-        print(json.dumps(rep), flush=True)
-        return 0 if rep["ok"] else 1
+        ok = True
+        for skew in SKEWS:  # one JSON line per candidate, flushed: a later candidate that traps cannot take an earlier verdict with it
+            rep = probe(a.device, timed=not a.no_timing, skew=skew)
+            print(json.dumps(rep), flush=True)
+            ok = ok and rep["ok"]
+        return 0 if ok else 1
     print(json.dumps(_summary(autotune(a.device))), flush=True)
     return 0
 

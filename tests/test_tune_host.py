@@ -69,8 +69,21 @@ def test_verdict_rules(monkeypatch):
         got = tune.autotune()
         assert got["enabled"] is want and lib.nk_gemm_set_dual(-1) == (1 if want else 0)
         assert lib.nk_gemm_set_dual_min_k(-1) == (rep["min_k_iters"] if want else 0)
+    # several candidates: the fastest one that passed wins, and its skew is applied
+    class Multi(FakeProc):
+        def communicate(self, timeout=None):
+            return "\n".join(json.dumps(r) for r in self.rep) + "\n", ""
+    reps = [{"ok": True, "skew": 0, "speedup": 1.05, "min_k_iters": 20, "checks": [], "timings": []},
+            {"ok": True, "skew": 3, "speedup": 1.09, "min_k_iters": 10, "checks": [], "timings": []}]
+    monkeypatch.setattr(subprocess, "Popen", lambda *a, **k: Multi(reps))
+    got = tune.autotune()
+    assert got["enabled"] and got["skew"] == 3 and lib.nk_gemm_set_dual_skew(-1) == 3 and lib.nk_gemm_set_dual_min_k(-1) == 10
+    reps[1]["ok"] = False  # the skewed order failed its equality checks: the plain order is used
+    got = tune.autotune()
+    assert got["enabled"] and got["skew"] == 0 and lib.nk_gemm_set_dual_skew(-1) == 0 and len(got["candidates"]) == 2
     lib.nk_gemm_set_dual(0)
     lib.nk_gemm_set_dual_min_k(0)
+    lib.nk_gemm_set_dual_skew(0)
 
 
 def test_probe_shapes_cover_every_paired_mode():
