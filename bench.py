@@ -290,24 +290,36 @@ def _dist_setup():
 
 
 def _autotune(world: int, local: int, dev) -> dict:
-    """kernel scheduling variants that are validated on the device before use (neurosis_b200.tune): every rank probes its
-    own GPU in a child process; a variant is used only if ALL ranks accepted it.  The mode is exported to the child
-    processes of `run_other_configs` through NK_GEMM_DUAL (pinned there, no second probe)."""
+    """kernel variants that are validated on the device before use (neurosis_b200.tune): every rank probes its own GPU in
+    a child process; a variant is used only if ALL ranks accepted it.  The verdicts are exported to the child processes
+    of `run_other_configs` through NK_GEMM_DUAL* / NK_NORM_VARIANT (pinned there, no second probe)."""
     import torch
     import torch.distributed as dist
     from neurosis_b200 import tune
+    from neurosis_b200._lib import lib
     rep = tune.autotune(local)
+    ln = rep.setdefault("layernorm_column_owner", {"enabled": False})
     if world > 1:
-        flag = torch.tensor([1 if rep.get("enabled") else 0], device=dev)
+        flag = torch.tensor([1 if rep.get("enabled") else 0, 1 if ln.get("enabled") else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if bool(rep.get("enabled")) != bool(flag.item()):
+        if bool(rep.get("enabled")) != bool(flag[0].item()):
             rep["enabled"], rep["mode"] = False, 0
             rep["note"] = "another rank rejected the variant"
             tune.apply(0)
-    os.environ["NK_GEMM_DUAL"] = str(rep.get("mode", 0))
-    os.environ["NK_GEMM_DUAL_MIN_K"] = str(int(rep.get("min_k_iters") or 0) if rep.get("enabled") else 0)
-    os.environ["NK_GEMM_DUAL_SKEW"] = str(int(rep.get("skew") or 0) if rep.get("enabled") else 0)
+        if bool(ln.get("enabled")) != bool(flag[1].item()):
+            ln["enabled"] = False
+            ln["error"] = "another rank rejected the variant"
+            lib.nk_norm_set_variant(0)
+    _export_tuned(rep)
     return tune._summary(rep)
+
+
+def _export_tuned(rep: dict) -> None:
+    on = bool(rep.get("enabled"))
+    os.environ["NK_GEMM_DUAL"] = str(rep.get("mode", 0) if on else 0)
+    os.environ["NK_GEMM_DUAL_MIN_K"] = str(int(rep.get("min_k_iters") or 0) if on else 0)
+    os.environ["NK_GEMM_DUAL_SKEW"] = str(int(rep.get("skew") or 0) if on else 0)
+    os.environ["NK_NORM_VARIANT"] = "1" if (rep.get("layernorm_column_owner") or {}).get("enabled") else "0"
 
 
 def _timed(world, dev, k: int, fn) -> float:
@@ -437,7 +449,7 @@ def run_buckets(args) -> None:
                                                  "weights enter the weighted-MSE reduction as a (B,) device buffer",
                            "square_only_ms_per_step": None if ms_sq is None else ms_sq / args.steps,
                            "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2",
-                           "step_tflop_algorithmic": cfg["gflop"] * B / 1e3, "gemm_row_tile_pairing": tuned},
+                           "step_tflop_algorithmic": cfg["gflop"] * B / 1e3, "tuned_variants": tuned},
                 "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clocks,
@@ -524,7 +536,7 @@ def run_vae(args) -> None:
                            "encode_images_per_s": world * B * args.steps / (ms_enc * 1e-3),
                            "encode_tflops_per_gpu": B * args.steps * GFLOP_VAE_ENC / 1e3 / (ms_enc * 1e-3),
                            "parallelism": f"dp{world}", "l2": "activations (GBs per layer at 1024^2) >> 126 MB L2",
-                           "step_tflop_algorithmic": cfg["gflop"] * B / 1e3, "gemm_row_tile_pairing": tuned,
+                           "step_tflop_algorithmic": cfg["gflop"] * B / 1e3, "tuned_variants": tuned,
                            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30},
                 "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                         "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": 4},
@@ -725,36 +737,57 @@ def main() -> None:
     for _ in range(2):
         eager_step(resident, False)
     torch.cuda.synchronize()
-    if tuned.get("enabled"):
-        # step-level guard of the tuned variant, on the real model: the same step (same sigma / noise draws) with the
-        # unpaired and with the paired kernels.  The forward GEMMs are bit-identical, so the losses agree to the
-        # run-to-run noise of the atomic loss reduction; the gradients differ by the fp32 accumulation order of split-K
-        # weight gradients only.
+    ln_tuned = tuned.get("layernorm_column_owner") or {}
+    if tuned.get("enabled") or ln_tuned.get("enabled"):
+        # step-level guard of the tuned variants, on the real model: the same step (same sigma / noise draws) with the
+        # measured kernels and with the variants.  Stage 1, GEMM row-tile pairing: the forward GEMMs are bit-identical, so
+        # the losses agree to the run-to-run noise of the atomic loss reduction (1e-5) and the gradients differ by the fp32
+        # accumulation order of split-K weight gradients only (abs-sum within 2e-3).  Stage 2, LayerNorm second form on top:
+        # same formulas in another reduction order, outputs agree to bf16 rounding (loss within 2e-3, abs-sum within 1e-2).
         from neurosis_b200 import tune as _tune
+        from neurosis_b200._lib import lib as _lib_
 
-        def guarded(mode: int):
+        def guarded(mode: int, norm_mask: int):
             _tune.apply(mode)
+            _lib_.nk_norm_set_variant(norm_mask)
             torch.manual_seed(1234)
             torch.cuda.manual_seed(1234)
             loss = eager_step(resident, True)
             gsum = sum(float(b["flat"].double().abs().sum()) for b in getattr(reducer, "buckets", []))
             return loss, gsum
 
-        l_off, g_off = guarded(0)
-        l_on, g_on = guarded(tuned.get("mode", 1))
-        # (tolerances cover run-to-run atomics of the loss reduction / weight gradients; a wrong tile is orders above)
-        same = (l_on == l_on and abs(l_on - l_off) <= 1e-5 * max(abs(l_off), 1e-30)
-                and abs(g_on - g_off) <= 2e-3 * max(abs(g_off), 1e-30))
-        flag = torch.tensor([1 if same else 0], device=dev)
-        if world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        tuned["step_guard"] = {"loss_unpaired": l_off, "loss_paired": l_on, "grad_abs_sum_unpaired": g_off,
-                               "grad_abs_sum_paired": g_on, "equal": bool(flag.item())}
-        if not bool(flag.item()):
-            tuned["enabled"], tuned["mode"] = False, 0
-            tuned["note"] = "rejected by the step-level guard (losses / gradients differ)"
-            _tune.apply(0)
-            os.environ["NK_GEMM_DUAL"] = "0"
+        def agree(a, b, tol_loss, tol_grad) -> bool:
+            same = (b[0] == b[0] and abs(b[0] - a[0]) <= tol_loss * max(abs(a[0]), 1e-30)
+                    and abs(b[1] - a[1]) <= tol_grad * max(abs(a[1]), 1e-30))
+            flag = torch.tensor([1 if same else 0], device=dev)
+            if world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            return bool(flag.item())
+
+        base = guarded(0, 0)
+        ref = base  # the step with every accepted variant so far
+        gmode = tuned.get("mode", 1) if tuned.get("enabled") else 0
+        if tuned.get("enabled"):
+            got = guarded(gmode, 0)
+            ok = agree(base, got, 1e-5, 2e-3)
+            tuned["step_guard"] = {"loss_unpaired": base[0], "loss_paired": got[0], "grad_abs_sum_unpaired": base[1],
+                                   "grad_abs_sum_paired": got[1], "equal": ok}
+            if ok:
+                ref = got
+            else:
+                tuned["enabled"], tuned["mode"], gmode = False, 0, 0
+                tuned["note"] = "rejected by the step-level guard (losses / gradients differ)"
+        if ln_tuned.get("enabled"):
+            got2 = guarded(gmode, 1)
+            ok2 = agree(ref, got2, 2e-3, 1e-2)
+            ln_tuned["step_guard"] = {"loss_old": ref[0], "loss_new": got2[0], "grad_abs_sum_old": ref[1],
+                                      "grad_abs_sum_new": got2[1], "agree": ok2}
+            if not ok2:
+                ln_tuned["enabled"] = False
+                ln_tuned["error"] = "rejected by the step-level guard"
+        _tune.apply(gmode)
+        _lib_.nk_norm_set_variant(1 if ln_tuned.get("enabled") else 0)
+        _export_tuned({**tuned, "layernorm_column_owner": ln_tuned})
     if args.ncu_step:  # under `ncu --profile-from-start off`: exactly one eager step inside the profiler range
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -908,7 +941,7 @@ def main() -> None:
                            "ema": ema is not None, "optimizer_sharded": hasattr(reducer, "owned_params"),
                            "parallelism": f"dp{world}", "l2": "working set (5 GB bf16 weights + activations) >> 126 MB L2",
                            "step_tflop_algorithmic": gflop_img * B / 1e3,
-                           "stock_torch_img_s": STOCK_TORCH.get(args.config), "gemm_row_tile_pairing": tuned,
+                           "stock_torch_img_s": STOCK_TORCH.get(args.config), "tuned_variants": tuned,
                            "mfu_vs_sustained_peak": ips / world * gflop_img * 1e9 / (pk["tflops"] * 1e12),
                            "mfu_vs_burst_peak": ips / world * gflop_img * 1e9 / (burst * 1e12)},
                 "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},

@@ -540,12 +540,247 @@ __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const bf16* __restric
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm, second form ("column owners"; nk_norm_set_variant bit 0; written without a GPU at hand, selected only
+// after neurosis_b200.tune has compared it with the kernels above on the device)
+// ------------------------------------------------------------------------------------------
+// One block = W warps spanning ONE row: thread t owns columns [8t, 8t + 8) (t < V = C / 8; lanes past V idle) for every
+// row of the block's row range, RB rows in flight per thread.  What this buys over the warp-per-row kernels above:
+//   * gamma / beta live in registers for the whole row range (above, every lane re-reads 64 bytes of gamma / beta per
+//     16-byte vector of x and row: 4x the row's own bytes through L1);
+//   * backward: dgamma / dbeta accumulate in the owner's registers, so the second streaming pass over x and dy
+//     (ln_bwd_param_kernel) and its shared-memory transpose disappear — one global red per column and block at the end.
+// Row statistics need a block reduction: warp shuffles, one shared-memory exchange and ONE __syncthreads per RB rows
+// (the exchange buffer is double buffered: a thread can only reach the barrier of batch k + 1 after it has read batch k).
+// Forward variance: single pass over values shifted by the row's first element (sum d, sum d^2 with d = x - x[row][0]),
+// which is free of the cancellation of E[x^2] - E[x]^2 and needs one reduction instead of two.
+constexpr int LN2_MAXW = 8;  // warps per row: C <= 2048
+
+template <int RB>
+__global__ void __launch_bounds__(LN2_MAXW * 32, 3) ln_fwd_v2_kernel(const bf16* __restrict__ x, long long ldx,
+                                                                 bf16* __restrict__ y, long long ldy,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float* __restrict__ mean,
+                                                                 float* __restrict__ rstd, int rows, int C, float eps,
+                                                                 int rows_per_block) {
+    __shared__ float red[2][RB][2][LN2_MAXW];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, W = blockDim.x >> 5;
+    const bool active = t < C / 8;
+    float g[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = b[j] = 0.f;
+    if (active) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + t * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + t * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + t * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + t * 8 + 4));
+        g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+    }
+    const long long r_begin = static_cast<long long>(blockIdx.x) * rows_per_block;
+    const long long r_end = min(static_cast<long long>(rows), r_begin + rows_per_block);
+    const float inv_c = 1.f / static_cast<float>(C);
+    int buf = 0;
+    for (long long r0 = r_begin; r0 < r_end; r0 += RB, buf ^= 1) {
+        uint4 q[RB];
+        float sh[RB], s[RB], ss[RB];
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            const long long row = r0 + i;
+            const bool valid = row < r_end;
+            q[i] = (active && valid) ? __ldg(reinterpret_cast<const uint4*>(x + row * ldx + t * 8)) : make_uint4(0, 0, 0, 0);
+            sh[i] = valid ? __bfloat162float(x[row * ldx]) : 0.f;  // same address for the whole block: one broadcast load
+        }
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            const uint32_t w[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+            float a = 0.f, c = 0.f;
+            if (active) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = unpack_bf16x2(w[e]);
+                    const float d0 = f.x - sh[i], d1 = f.y - sh[i];
+                    a += d0 + d1;
+                    c = fmaf(d0, d0, fmaf(d1, d1, c));
+                }
+            }
+            s[i] = warp_sum(a);
+            ss[i] = warp_sum(c);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                red[buf][i][0][warp] = s[i];
+                red[buf][i][1][warp] = ss[i];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            const long long row = r0 + i;
+            if (row >= r_end) break;
+            float S = 0.f, SS = 0.f;
+            for (int k = 0; k < W; ++k) {
+                S += red[buf][i][0][k];
+                SS += red[buf][i][1][k];
+            }
+            const float mu = S * inv_c;                       // mean of the shifted values
+            const float var = fmaxf(SS * inv_c - mu * mu, 0.f);
+            const float m = sh[i] + mu;
+            const float r = rsqrtf(var + eps);
+            if (t == 0) {
+                mean[row] = m;
+                rstd[row] = r;
+            }
+            if (active) {
+                const uint32_t w[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = unpack_bf16x2(w[e]);
+                    o[2 * e] = (f.x - m) * r * g[2 * e] + b[2 * e];
+                    o[2 * e + 1] = (f.y - m) * r * g[2 * e + 1] + b[2 * e + 1];
+                }
+                store8(y + row * ldy + t * 8, o);
+            }
+        }
+    }
+}
+
+template <int RB>
+__global__ void __launch_bounds__(LN2_MAXW * 32) ln_bwd_v2_kernel(const bf16* __restrict__ dy, long long lddy,
+                                                                 const bf16* __restrict__ x, long long ldx,
+                                                                 bf16* __restrict__ dx, long long lddx,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ mean,
+                                                                 const float* __restrict__ rstd,
+                                                                 const bf16* __restrict__ dres, long long lddres,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                 int rows, int C, int rows_per_block) {
+    __shared__ float red[2][RB][2][LN2_MAXW];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, W = blockDim.x >> 5;
+    const bool active = t < C / 8;
+    float g[8], ag[8], ab[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = ag[j] = ab[j] = 0.f;
+    if (active) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + t * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + t * 8 + 4));
+        g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+    }
+    const long long r_begin = static_cast<long long>(blockIdx.x) * rows_per_block;
+    const long long r_end = min(static_cast<long long>(rows), r_begin + rows_per_block);
+    const float inv_c = 1.f / static_cast<float>(C);
+    int buf = 0;
+    for (long long r0 = r_begin; r0 < r_end; r0 += RB, buf ^= 1) {
+        uint4 qx[RB], qd[RB];
+        float m[RB], r[RB], s1[RB], s2[RB];
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            const long long row = r0 + i;
+            const bool valid = row < r_end;
+            const bool ld = active && valid;
+            qx[i] = ld ? __ldg(reinterpret_cast<const uint4*>(x + row * ldx + t * 8)) : make_uint4(0, 0, 0, 0);
+            qd[i] = ld ? __ldg(reinterpret_cast<const uint4*>(dy + row * lddy + t * 8)) : make_uint4(0, 0, 0, 0);
+            m[i] = valid ? __ldg(mean + row) : 0.f;
+            r[i] = valid ? __ldg(rstd + row) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            const uint32_t wx[4] = {qx[i].x, qx[i].y, qx[i].z, qx[i].w};
+            const uint32_t wd[4] = {qd[i].x, qd[i].y, qd[i].z, qd[i].w};
+            float a = 0.f, c = 0.f;
+            // (idle lanes and rows past the range carry dy = 0, so every product below vanishes for them)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 fx = unpack_bf16x2(wx[e]);
+                const float2 fd = unpack_bf16x2(wd[e]);
+                const float xh0 = (fx.x - m[i]) * r[i], xh1 = (fx.y - m[i]) * r[i];
+                const float gd0 = fd.x * g[2 * e], gd1 = fd.y * g[2 * e + 1];
+                a += gd0 + gd1;
+                c = fmaf(gd0, xh0, fmaf(gd1, xh1, c));
+                ag[2 * e] = fmaf(fd.x, xh0, ag[2 * e]);
+                ag[2 * e + 1] = fmaf(fd.y, xh1, ag[2 * e + 1]);
+                ab[2 * e] += fd.x;
+                ab[2 * e + 1] += fd.y;
+            }
+            s1[i] = warp_sum(a);
+            s2[i] = warp_sum(c);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                red[buf][i][0][warp] = s1[i];
+                red[buf][i][1][warp] = s2[i];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            const long long row = r0 + i;
+            if (row >= r_end) break;
+            if (!active) continue;
+            float S1 = 0.f, S2 = 0.f;
+            for (int k = 0; k < W; ++k) {
+                S1 += red[buf][i][0][k];
+                S2 += red[buf][i][1][k];
+            }
+            S1 *= inv_c;
+            S2 *= inv_c;
+            const uint32_t wx[4] = {qx[i].x, qx[i].y, qx[i].z, qx[i].w};
+            const uint32_t wd[4] = {qd[i].x, qd[i].y, qd[i].z, qd[i].w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 fx = unpack_bf16x2(wx[e]);
+                const float2 fd = unpack_bf16x2(wd[e]);
+                const float xh0 = (fx.x - m[i]) * r[i], xh1 = (fx.y - m[i]) * r[i];
+                o[e] = pack_bf16x2(r[i] * (fd.x * g[2 * e] - S1 - xh0 * S2), r[i] * (fd.y * g[2 * e + 1] - S1 - xh1 * S2));
+            }
+            if (dres) {  // gradient arriving through the residual branch that bypasses this norm: dx += dres
+                const uint4 qr = __ldg(reinterpret_cast<const uint4*>(dres + row * lddres + t * 8));
+                const uint32_t wr[4] = {qr.x, qr.y, qr.z, qr.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 p0 = unpack_bf16x2(o[e]);
+                    const float2 p1 = unpack_bf16x2(wr[e]);
+                    o[e] = pack_bf16x2(p0.x + p1.x, p0.y + p1.y);
+                }
+            }
+            *reinterpret_cast<uint4*>(dx + row * lddx + t * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    if (active && dgamma != nullptr && dbeta != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(dgamma + t * 8 + j, ag[j]);
+            atomicAdd(dbeta + t * 8 + j, ab[j]);
+        }
+    }
+}
+
 }  // namespace
 }  // namespace nk
 
 using namespace nk;
 
+// Kernel forms of this file that were written after the last GPU run: bit 0 = LayerNorm forward / backward as column-owner
+// blocks (ln_*_v2_kernel).  0 (the default, or NK_NORM_VARIANT) = the forms measured in DESIGN.md section 2.3;
+// neurosis_b200.tune sets bits only after comparing both forms on the device.
+static int g_norm_variant = -1;
+static int norm_variant() {
+    if (g_norm_variant < 0) {
+        const char* e_ = getenv("NK_NORM_VARIANT");
+        g_norm_variant = e_ ? (atoi(e_) & 0xff) : 0;
+    }
+    return g_norm_variant;
+}
+
 extern "C" {
+
+int nk_norm_set_variant(int mask) {
+    const int prev = norm_variant();
+    if (mask >= 0 && mask <= 0xff) g_norm_variant = mask;
+    return prev;
+}
 
 int64_t nk_groupnorm_workspace_bytes(int nimg, int HW, int C, int G) {
     if (C <= 0 || C % 8 != 0 || G <= 0) return -1;
@@ -605,6 +840,17 @@ int nk_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float
                      float* mean, float* rstd, int rows, int C, float eps, nk_stream_t stream) {
     NK_REQUIRE(C % 8 == 0 && C <= 2560, NK_ERR_SHAPE, "layernorm: C=%d", C);
     cudaStream_t st = ::nk::enter(stream);
+    if ((norm_variant() & 1) && C <= LN2_MAXW * 256 && ldx % 8 == 0 && ldy % 8 == 0) {
+        constexpr int RB = 8;
+        const int warps = (C / 8 + 31) / 32;
+        const long long want = (static_cast<long long>(rows) + 148 * 8 - 1) / (148 * 8);
+        const int rpb = static_cast<int>(std::max<long long>(RB, (want + RB - 1) / RB * RB));
+        const int blocks = (rows + rpb - 1) / rpb;
+        ln_fwd_v2_kernel<RB><<<blocks, warps * 32, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, gamma,
+                                                          beta, mean, rstd, rows, C, eps, rpb);
+        NK_CUDA(cudaGetLastError());
+        return NK_OK;
+    }
     const int wpb = 8;
     const int grid = static_cast<int>(std::min<long long>((rows + wpb - 1) / wpb, 148LL * 8));
     const int V = C / 8;
@@ -634,6 +880,17 @@ int nk_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, c
     const bf16* rp = static_cast<const bf16*>(dres);
     NK_REQUIRE(!dres || (lddres % 8 == 0 && (reinterpret_cast<uintptr_t>(dres) & 15u) == 0), NK_ERR_SHAPE,
                "layernorm bwd: dres alignment");
+    if ((norm_variant() & 1) && lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0) {
+        constexpr int RB = 4;
+        const int warps = (C / 8 + 31) / 32;
+        const long long want = (static_cast<long long>(rows) + 148 * 4 - 1) / (148 * 4);
+        const int rpb = static_cast<int>(std::max<long long>(RB, (want + RB - 1) / RB * RB));
+        const int blocks = (rows + rpb - 1) / rpb;
+        ln_bwd_v2_kernel<RB><<<blocks, warps * 32, 0, st>>>(dyp, lddy, xp, ldx, static_cast<bf16*>(dx), lddx, gamma, mean, rstd,
+                                                          rp, lddres, dgamma, dbeta, rows, C, rpb);
+        NK_CUDA(cudaGetLastError());
+        return NK_OK;
+    }
     if (V <= 64)
         ln_bwd_dx_kernel<2><<<grid, wpb * 32, 0, st>>>(dyp, lddy, xp, ldx, static_cast<bf16*>(dx), lddx, gamma, mean,
                                                        rstd, rp, lddres, rows, C);

@@ -1,6 +1,6 @@
-"""Run-time selection of kernel scheduling variants, gated by an on-device equality check.
+"""Run-time selection of kernel variants, gated by an on-device comparison with the measured kernels.
 
-One variant so far: ROW-TILE PAIRING of the tensor-core GEMM / implicit-GEMM convolution kernel (`gemm_tc_kernel<.., DUAL>`,
+Two variants: the second form of the LayerNorm kernels (`probe_layernorm`, norm.cu, `nk_norm_set_variant`) and ROW-TILE PAIRING of the tensor-core GEMM / implicit-GEMM convolution kernel (`gemm_tc_kernel<.., DUAL>`,
 csrc/gemm_tc.cu): a CTA owns two 128-row tiles that share one B tile, which cuts the operand bytes per FLOP that cross
 the L2 -> SM fabric by 25 % — the measured bound of the kernel.  It changes WHICH CTA computes an output
 tile and in which order tiles are visited, never the arithmetic of an output element, so against the unpaired kernel it
@@ -211,10 +211,108 @@ def probe(device: int = 0, timed: bool = True, skew: int = 0) -> dict:
     return report
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# LayerNorm as column-owner blocks (norm.cu ln_*_v2_kernel, nk_norm_set_variant bit 0)
+# ---------------------------------------------------------------------------------------------------------------------
+LN_TIMED = [((16384, 1280), 180), ((65536, 640), 30)]  # (rows, C), LayerNorm calls per SDXL B=16 step (forward and backward each)
+LN_CHECKS = [(16384, 1280, 0, True), (4096, 640, 0, False), (1000, 320, 0, True), (77, 768, 0, False), (5, 2048, 0, True),
+             (3, 64, 0, False), (2050, 1280, 64, True), (8192, 640, 128, True)]  # (rows, C, extra row stride, residual gradient)
+
+
+def probe_layernorm(device: int = 0, timed: bool = True) -> dict:
+    """second form of the LayerNorm kernels against the first AND against an fp32 torch evaluation of the same bf16 inputs:
+    same formulas in a different reduction order, so outputs agree to bf16 rounding (relative L2 < 4e-3 between the
+    forms), the new form may not be further from the fp32 result than the old one (x 1.2 + 1e-4), statistics and
+    parameter gradients agree to 1e-5 / 2e-4."""
+    import torch
+
+    from . import ops
+    from ._lib import lib
+    torch.cuda.set_device(device)
+    dev = torch.device("cuda", device)
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    rep = {"variant": "layernorm_column_owner", "checks": [], "timings": [], "ok": True}
+    prev = lib.nk_norm_set_variant(-1)
+
+    def rel(a, b):
+        return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20))
+
+    def case(rows, c, pad, with_res):
+        buf = torch.randn(rows, c + pad, generator=gen, device=dev) * 1.7 + 0.3
+        x = buf.to(torch.bfloat16)[:, :c]
+        dy = (torch.randn(rows, c + pad, generator=gen, device=dev) * 0.05).to(torch.bfloat16)[:, :c]
+        gamma = 1.0 + 0.2 * torch.randn(c, generator=gen, device=dev)
+        beta = 0.1 * torch.randn(c, generator=gen, device=dev)
+        dres = (torch.randn(rows, c, generator=gen, device=dev) * 0.05).to(torch.bfloat16) if with_res else None
+        return x, dy, gamma, beta, dres
+
+    def run(x, dy, gamma, beta, dres):
+        y, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-5)
+        dx, dg, db = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dres=dres)
+        return y, mean, rstd, dx, dg, db
+
+    try:
+        for rows, c, pad, with_res in LN_CHECKS:
+            x, dy, gamma, beta, dres = case(rows, c, pad, with_res)
+            lib.nk_norm_set_variant(0)
+            a = run(x, dy, gamma, beta, dres)
+            lib.nk_norm_set_variant(1)
+            b = run(x, dy, gamma, beta, dres)
+            # fp32 evaluation of the same bf16 inputs
+            xf = x.float().requires_grad_(True)
+            gf, bf_ = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+            yf = torch.nn.functional.layer_norm(xf, (c,), gf, bf_, 1e-5)
+            yf.backward(dy.float())
+            dxf = xf.grad + (dres.float() if dres is not None else 0)
+            torch.cuda.synchronize()
+            e = {"y_forms": rel(b[0], a[0]), "dx_forms": rel(b[3], a[3]), "mean": rel(b[1], a[1]), "rstd": rel(b[2], a[2]),
+                 "dgamma": rel(b[4], a[4]), "dbeta": rel(b[5], a[5]), "y_new_vs_fp32": rel(b[0], yf), "y_old_vs_fp32": rel(a[0], yf),
+                 "dx_new_vs_fp32": rel(b[3], dxf), "dx_old_vs_fp32": rel(a[3], dxf), "dgamma_vs_fp32": rel(b[4], gf.grad),
+                 "dbeta_vs_fp32": rel(b[5], bf_.grad)}
+            finite = all(bool(torch.isfinite(t.float()).all()) for t in b)
+            ok = (finite and e["y_forms"] < 4e-3 and e["dx_forms"] < 4e-3 and e["mean"] < 1e-5 and e["rstd"] < 1e-5
+                  and e["dgamma"] < 2e-4 and e["dbeta"] < 2e-4
+                  and e["y_new_vs_fp32"] <= 1.2 * e["y_old_vs_fp32"] + 1e-4 and e["dx_new_vs_fp32"] <= 1.2 * e["dx_old_vs_fp32"] + 1e-4
+                  and e["dgamma_vs_fp32"] < 1e-3 and e["dbeta_vs_fp32"] < 1e-3)
+            rep["checks"].append({"rows": rows, "C": c, "row_pad": pad, "residual": with_res, "ok": ok,
+                                  **{k: float(f"{v:.3e}") for k, v in e.items()}})
+            rep["ok"] = rep["ok"] and ok
+        if timed and rep["ok"]:
+            t_old = t_new = 0.0
+            for (rows, c), weight in LN_TIMED:
+                x, dy, gamma, beta, dres = case(rows, c, 0, True)
+                dg, db = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+                lib.nk_norm_set_variant(0)
+                _, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-5)
+                row = {"rows": rows, "C": c, "calls_per_step": weight}
+                for name, mask in (("old", 0), ("new", 1)):
+                    lib.nk_norm_set_variant(mask)
+                    row[f"fwd_ms_{name}"] = _time(lambda: ops.layernorm_fwd(x, gamma, beta, 1e-5), 10)
+                    row[f"bwd_ms_{name}"] = _time(lambda: ops.layernorm_bwd(dy, x, gamma, mean, rstd, out=(dg, db), dres=dres), 10)
+                t_old += weight * (row["fwd_ms_old"] + row["bwd_ms_old"])
+                t_new += weight * (row["fwd_ms_new"] + row["bwd_ms_new"])
+                rep["timings"].append(row)
+            rep["step_ms_old"], rep["step_ms_new"] = t_old, t_new
+            rep["speedup"] = t_old / t_new if t_new > 0 else 0.0
+    finally:
+        lib.nk_norm_set_variant(prev)
+    return rep
+
+
 def _summary(rep: dict, max_timings: int = 6) -> dict:
     """what bench.py prints: verdict, weighted times, the failed checks and the largest movers."""
     out = {k: rep[k] for k in ("variant", "ok", "step_ms_unpaired", "step_ms_paired", "speedup", "error", "enabled", "mode",
                                "probe_wall_s", "source", "min_k_iters", "skew", "candidates", "note") if k in rep}
+    ln = rep.get("layernorm_column_owner")
+    if ln is not None:
+        out["layernorm_column_owner"] = {k: ln[k] for k in ("ok", "enabled", "speedup", "step_ms_old", "step_ms_new", "error", "source")
+                                         if k in ln}
+        out["layernorm_column_owner"]["checks_run"] = len(ln.get("checks", []))
+        badl = [c for c in ln.get("checks", []) if not c["ok"]]
+        if badl:
+            out["layernorm_column_owner"]["failed_checks"] = badl[:4]
+        if ln.get("timings"):
+            out["layernorm_column_owner"]["timings"] = ln["timings"]
     out["checks_run"] = len(rep.get("checks", []))
     bad = [c for c in rep.get("checks", []) if not c["ok"]]
     if bad:
@@ -235,9 +333,11 @@ def autotune(device: int = 0, timeout_s: float = 150.0, min_speedup: float = 1.0
     from ._lib import lib
     env_mode = os.environ.get("NK_GEMM_DUAL")
     if env_mode is not None:
+        nv = int(os.environ.get("NK_NORM_VARIANT", "0") or 0)
         return {"variant": "gemm_row_tile_pairing", "enabled": env_mode not in ("", "0"), "mode": int(env_mode or 0),
                 "min_k_iters": int(os.environ.get("NK_GEMM_DUAL_MIN_K", "0") or 0),
-                "skew": int(os.environ.get("NK_GEMM_DUAL_SKEW", "0") or 0), "source": "NK_GEMM_DUAL (pinned, no probe)"}
+                "skew": int(os.environ.get("NK_GEMM_DUAL_SKEW", "0") or 0), "source": "NK_GEMM_DUAL (pinned, no probe)",
+                "layernorm_column_owner": {"enabled": bool(nv & 1), "source": "NK_NORM_VARIANT (pinned with NK_GEMM_DUAL, no probe)"}}
     if os.environ.get("NK_B200_TUNE", "1") == "0":
         return {"variant": "gemm_row_tile_pairing", "enabled": False, "mode": 0, "source": "NK_B200_TUNE=0 (no probe)"}
     t0 = time.monotonic()
@@ -263,6 +363,8 @@ def autotune(device: int = 0, timeout_s: float = 150.0, min_speedup: float = 1.0
                     cands.append(json.loads(ln))
                 except Exception:  # noqa: BLE001
                     pass
+        ln_reps = [c for c in cands if c.get("variant") == "layernorm_column_owner"]
+        cands = [c for c in cands if c.get("variant") == "gemm_row_tile_pairing"]
         good = [c for c in cands if c.get("ok") and c.get("min_k_iters") is not None]
         if good:  # the fastest candidate that reproduced the unpaired kernels
             rep = max(good, key=lambda c: float(c.get("speedup", 0.0)))
@@ -271,6 +373,8 @@ def autotune(device: int = 0, timeout_s: float = 150.0, min_speedup: float = 1.0
         if cands:
             rep["candidates"] = [{"skew": c.get("skew"), "ok": c.get("ok"), "speedup": c.get("speedup"),
                                   "min_k_iters": c.get("min_k_iters")} for c in cands]
+        if ln_reps:
+            rep["layernorm_column_owner"] = ln_reps[-1]
         if len(cands) < len(SKEWS) or proc.returncode not in (0, 1):
             rep.setdefault("note", f"probe child ended early (exit {proc.returncode}) after {len(cands)} of {len(SKEWS)} candidates: "
                            + " | ".join((se or "").strip().splitlines()[-2:])[-300:])
@@ -285,6 +389,12 @@ def autotune(device: int = 0, timeout_s: float = 150.0, min_speedup: float = 1.0
     lib.nk_gemm_set_dual_min_k(int(rep["min_k_iters"]) if enable else 0)
     lib.nk_gemm_set_dual_skew(int(rep.get("skew", 0)) if enable else 0)
     lib.nk_gemm_set_dual(1 if enable else 0)
+    ln = rep.get("layernorm_column_owner")
+    if ln is None:
+        ln = rep["layernorm_column_owner"] = {"ok": False, "error": "no verdict from the probe child"}
+    ln["enabled"] = bool(ln.get("ok")) and float(ln.get("speedup", 0.0)) >= 1.02
+    ln["source"] = "on-device probe (child process)"
+    lib.nk_norm_set_variant(1 if ln["enabled"] else 0)
     return rep
 
 
@@ -303,10 +413,16 @@ def main(argv: Optional[list] = None) -> int:
     a = ap.parse_args(argv)
     if a.probe:
         ok = True
-        for skew in SKEWS:  # one JSON line per candidate, flushed: a later candidate that traps cannot take an earlier verdict with it
+        # one JSON line per candidate, flushed, least adventurous first: a later candidate that traps cannot take an earlier
+        # verdict with it (order: pairing in plain order, LayerNorm second form, pairing with skew)
+        for i, skew in enumerate(SKEWS):
             rep = probe(a.device, timed=not a.no_timing, skew=skew)
             print(json.dumps(rep), flush=True)
             ok = ok and rep["ok"]
+            if i == 0:
+                ln = probe_layernorm(a.device, timed=not a.no_timing)
+                print(json.dumps(ln), flush=True)
+                ok = ok and ln["ok"]
         return 0 if ok else 1
     print(json.dumps(_summary(autotune(a.device))), flush=True)
     return 0

@@ -59,10 +59,11 @@ def test_verdict_rules(monkeypatch):
 
     monkeypatch.delenv("NK_GEMM_DUAL", raising=False)
     monkeypatch.delenv("NK_B200_TUNE", raising=False)
-    cases = [({"ok": True, "speedup": 1.08, "min_k_iters": 20, "checks": [], "timings": []}, True),
-             ({"ok": True, "speedup": 1.001, "min_k_iters": 10, "checks": [], "timings": []}, False),
-             ({"ok": True, "speedup": 0.0, "min_k_iters": None, "checks": [], "timings": []}, False),
-             ({"ok": False, "speedup": 1.5, "min_k_iters": 10,
+    V = {"variant": "gemm_row_tile_pairing"}
+    cases = [({**V, "ok": True, "speedup": 1.08, "min_k_iters": 20, "checks": [], "timings": []}, True),
+             ({**V, "ok": True, "speedup": 1.001, "min_k_iters": 10, "checks": [], "timings": []}, False),
+             ({**V, "ok": True, "speedup": 0.0, "min_k_iters": None, "checks": [], "timings": []}, False),
+             ({**V, "ok": False, "speedup": 1.5, "min_k_iters": 10,
                "checks": [{"kind": "conv", "dims": [1], "ok": False, "err": 3.0}], "timings": []}, False)]
     for rep, want in cases:
         monkeypatch.setattr(subprocess, "Popen", lambda *a, _r=rep, **k: FakeProc(_r))
@@ -73,17 +74,28 @@ def test_verdict_rules(monkeypatch):
     class Multi(FakeProc):
         def communicate(self, timeout=None):
             return "\n".join(json.dumps(r) for r in self.rep) + "\n", ""
-    reps = [{"ok": True, "skew": 0, "speedup": 1.05, "min_k_iters": 20, "checks": [], "timings": []},
-            {"ok": True, "skew": 3, "speedup": 1.09, "min_k_iters": 10, "checks": [], "timings": []}]
+    L = {"variant": "layernorm_column_owner", "checks": [], "timings": []}
+    reps = [{**V, "ok": True, "skew": 0, "speedup": 1.05, "min_k_iters": 20, "checks": [], "timings": []},
+            {**L, "ok": True, "speedup": 1.4},
+            {**V, "ok": True, "skew": 3, "speedup": 1.09, "min_k_iters": 10, "checks": [], "timings": []}]
     monkeypatch.setattr(subprocess, "Popen", lambda *a, **k: Multi(reps))
     got = tune.autotune()
     assert got["enabled"] and got["skew"] == 3 and lib.nk_gemm_set_dual_skew(-1) == 3 and lib.nk_gemm_set_dual_min_k(-1) == 10
-    reps[1]["ok"] = False  # the skewed order failed its equality checks: the plain order is used
+    # the LayerNorm verdict is independent of the GEMM one
+    assert got["layernorm_column_owner"]["enabled"] and lib.nk_norm_set_variant(-1) == 1
+    json.dumps(tune._summary(got))
+    reps[1] = {**L, "ok": True, "speedup": 0.97}   # correct but slower: stays off
+    assert not tune.autotune()["layernorm_column_owner"]["enabled"] and lib.nk_norm_set_variant(-1) == 0
+    reps[1] = {**L, "ok": False, "speedup": 1.6}   # faster but wrong: stays off
+    assert not tune.autotune()["layernorm_column_owner"]["enabled"] and lib.nk_norm_set_variant(-1) == 0
+    reps[1] = {**L, "ok": True, "speedup": 1.4}
+    reps[2]["ok"] = False  # the skewed order failed its equality checks: the plain order is used
     got = tune.autotune()
     assert got["enabled"] and got["skew"] == 0 and lib.nk_gemm_set_dual_skew(-1) == 0 and len(got["candidates"]) == 2
     lib.nk_gemm_set_dual(0)
     lib.nk_gemm_set_dual_min_k(0)
     lib.nk_gemm_set_dual_skew(0)
+    lib.nk_norm_set_variant(0)
 
 
 def test_probe_shapes_cover_every_paired_mode():

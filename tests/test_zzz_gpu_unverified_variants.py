@@ -16,12 +16,18 @@ from common import ROOT
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(400)]
 
 
+_CACHE = {}
+
+
 def _probe(*extra):
+    if extra in _CACHE:
+        return _CACHE[extra]
     r = subprocess.run([sys.executable, "-m", "neurosis_b200.tune", "--probe", *extra], cwd=str(ROOT), capture_output=True,
                        text=True, timeout=360)
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert lines, f"probe produced no report (exit {r.returncode}): {r.stderr[-1500:]}"
-    return [json.loads(ln) for ln in lines]  # one report per skew candidate
+    _CACHE[extra] = [json.loads(ln) for ln in lines]  # one report per candidate (pairing plain, LayerNorm, pairing skewed)
+    return _CACHE[extra]
 
 
 @pytest.mark.xfail(strict=False, reason="row-tile pairing of gemm_tc_kernel: first run on hardware")
@@ -30,12 +36,24 @@ def test_gemm_row_tile_pairing_is_bit_identical_to_the_unpaired_kernel():
     the unpaired kernels: bit-identical for bf16 / fp32 stores, 2e-6 relative for split-K atomics; includes odd tile
     counts (half-empty last pair), ragged M / N / K and images smaller than a pixel tile."""
     from neurosis_b200 import tune
-    reps = _probe("--no-timing")
+    reps = [r for r in _probe("--no-timing") if r["variant"] == "gemm_row_tile_pairing"]
     assert [r["skew"] for r in reps] == list(tune.SKEWS)
     for rep in reps:
         bad = [c for c in rep["checks"] if not c["ok"]]
         assert rep["ok"] and not bad, (rep["skew"], bad[:10])
         assert len(rep["checks"]) >= 30
+
+
+@pytest.mark.xfail(strict=False, reason="second form of the LayerNorm kernels: first run on hardware")
+def test_layernorm_column_owner_form_agrees_with_the_measured_kernels_and_fp32():
+    """ln_fwd_v2 / ln_bwd_v2 (gamma / beta / dgamma / dbeta in the column owner's registers, one pass over x and dy in
+    the backward) against the warp-per-row kernels and against torch's fp32 layer_norm on the same bf16 inputs: ragged row
+    counts, C from 64 to 2048, padded row strides, with and without the residual gradient."""
+    reps = [r for r in _probe("--no-timing") if r["variant"] == "layernorm_column_owner"]
+    assert len(reps) == 1
+    bad = [c for c in reps[0]["checks"] if not c["ok"]]
+    assert reps[0]["ok"] and not bad, bad[:4]
+    assert len(reps[0]["checks"]) >= 8
 
 
 @pytest.mark.xfail(strict=False, reason="row-tile pairing of gemm_tc_kernel: first run on hardware")
@@ -51,6 +69,13 @@ def test_autotune_verdict_is_consistent_and_leaves_a_working_library():
         assert lib.nk_gemm_set_dual(-1) == (1 if rep["enabled"] else 0)
         assert rep["enabled"] == (bool(rep.get("ok")) and rep.get("min_k_iters") is not None and rep.get("speedup", 0) >= 1.01)
         assert lib.nk_gemm_set_dual_skew(-1) == (rep.get("skew", 0) if rep["enabled"] else 0)
+        ln = rep["layernorm_column_owner"]
+        assert lib.nk_norm_set_variant(-1) == (1 if ln["enabled"] else 0)
+        assert ln["enabled"] == (bool(ln.get("ok")) and ln.get("speedup", 0) >= 1.02)
+        gam, bet = torch.ones(1280, device="cuda"), torch.zeros(1280, device="cuda")
+        yn, _, _ = ops.layernorm_fwd(x, gam, bet, 1e-5)
+        refn = torch.nn.functional.layer_norm(x.float(), (1280,))
+        assert float((yn.float() - refn).norm() / refn.norm()) < 4e-3
         g = torch.Generator(device="cuda").manual_seed(0)
         x = torch.randn(4096, 1280, device="cuda", generator=g).bfloat16()
         w = (torch.randn(1280, 1280, device="cuda", generator=g) * 1280 ** -0.5).bfloat16()
@@ -61,6 +86,7 @@ def test_autotune_verdict_is_consistent_and_leaves_a_working_library():
         lib.nk_gemm_set_dual(0)
         lib.nk_gemm_set_dual_min_k(0)
         lib.nk_gemm_set_dual_skew(0)
+        lib.nk_norm_set_variant(0)
 
 
 # ---------------------------------------------------------------- error budget next to the reference's own bf16 path
