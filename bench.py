@@ -289,7 +289,7 @@ def _dist_setup():
     return world, rank, local, dev
 
 
-def _autotune(world: int, local: int, dev) -> dict:
+def _autotune_unsafe(world: int, local: int, dev) -> dict:
     """kernel variants that are validated on the device before use (neurosis_b200.tune): every rank probes its own GPU in
     a child process; a variant is used only if ALL ranks accepted it.  The verdicts are exported to the child processes
     of `run_other_configs` through NK_GEMM_DUAL* / NK_NORM_VARIANT (pinned there, no second probe)."""
@@ -314,12 +314,173 @@ def _autotune(world: int, local: int, dev) -> dict:
     return tune._summary(rep)
 
 
+def _autotune(world: int, local: int, dev) -> dict:
+    """`_autotune_unsafe`, but nothing in it may cost the measurement: on any exception the measured kernels are used."""
+    try:
+        return _autotune_unsafe(world, local, dev)
+    except Exception as e:  # noqa: BLE001
+        tuned = {"enabled": False, "mode": 0, "error": f"autotune failed: {e!r}", "layernorm_column_owner": {"enabled": False}}
+        try:
+            _apply_tuned(tuned)
+        except Exception:  # noqa: BLE001
+            pass
+        return tuned
+
+
 def _export_tuned(rep: dict) -> None:
     on = bool(rep.get("enabled"))
     os.environ["NK_GEMM_DUAL"] = str(rep.get("mode", 0) if on else 0)
     os.environ["NK_GEMM_DUAL_MIN_K"] = str(int(rep.get("min_k_iters") or 0) if on else 0)
     os.environ["NK_GEMM_DUAL_SKEW"] = str(int(rep.get("skew") or 0) if on else 0)
     os.environ["NK_NORM_VARIANT"] = "1" if (rep.get("layernorm_column_owner") or {}).get("enabled") else "0"
+
+
+def _apply_tuned(tuned: dict) -> None:
+    """library state of this process = the verdicts in `tuned` (summary form), exported to later child processes."""
+    from neurosis_b200 import tune
+    from neurosis_b200._lib import lib
+    on = bool(tuned.get("enabled"))
+    lib.nk_gemm_set_dual_min_k(int(tuned.get("min_k_iters") or 0) if on else 0)
+    lib.nk_gemm_set_dual_skew(int(tuned.get("skew") or 0) if on else 0)
+    tune.apply(int(tuned.get("mode", 1)) if on else 0)
+    lib.nk_norm_set_variant(1 if (tuned.get("layernorm_column_owner") or {}).get("enabled") else 0)
+    _export_tuned(tuned)
+
+
+def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
+    """Step-level guard of the variants the op-level probe accepted, on the real model and batch of this configuration,
+    in a CHILD process (`bench.py --guard-child`, single GPU, no process group): the same training step (same sigma /
+    noise draws) with the measured kernels and with the variants.  A variant that traps on a shape the probe did not
+    cover takes the child down, never the process that measures; a variant whose step disagrees is dropped.
+      stage 1, GEMM row-tile pairing: the forward GEMMs are bit-identical, so the losses agree to the run-to-run noise of
+        the atomic loss reduction (1e-5); the gradients differ by the fp32 accumulation order of split-K weight gradients
+        only (abs-sum within 2e-3);
+      stage 2, LayerNorm second form on top: same formulas in another reduction order, outputs agree to bf16 rounding (loss
+        within 2e-3, gradient abs-sum within 1e-2).
+    Under N > 1 a variant survives only if every rank's guard accepted it."""
+    import signal
+
+    import torch
+    import torch.distributed as dist
+    ln = tuned.setdefault("layernorm_column_owner", {"enabled": False})
+    try:
+        if tuned.get("enabled") or ln.get("enabled"):
+            env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")
+                   and k not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "MASTER_PORT", "MASTER_ADDR")}
+            env.update({"LOCAL_RANK": str(local), "NK_BENCH_EXTRAS": "0", "NK_B200_TUNE": "0"})
+            cmd = [sys.executable, str(ROOT / "bench.py"), "--guard-child", "--config", args.config, "--batch", str(args.batch)]
+            res, err = None, None
+            t0 = time.monotonic()
+            try:
+                proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                        start_new_session=True, cwd=str(ROOT))
+                try:
+                    so, se = proc.communicate(timeout=float(os.environ.get("NK_BENCH_GUARD_S", "240")))
+                except subprocess.TimeoutExpired:
+                    try:
+                        os.killpg(proc.pid, signal.SIGKILL)
+                    except Exception:  # noqa: BLE001
+                        proc.kill()
+                    so, se = proc.communicate()
+                    err = "guard child exceeded its time limit"
+                for ln_ in reversed((so or "").strip().splitlines()):
+                    if ln_.startswith("{"):
+                        res = json.loads(ln_)
+                        break
+                if res is None and err is None:
+                    err = f"guard child exit {proc.returncode}: " + " | ".join((se or "").strip().splitlines()[-3:])[-300:]
+            except Exception as e:  # noqa: BLE001
+                err = repr(e)
+            wall = round(time.monotonic() - t0, 1)
+            g_ok = bool(res and (res.get("gemm") or {}).get("equal")) if tuned.get("enabled") else False
+            l_ok = bool(res and (res.get("layernorm") or {}).get("agree")) if ln.get("enabled") else False
+            if tuned.get("enabled"):
+                tuned["step_guard"] = dict((res or {}).get("gemm") or {"error": err}, wall_s=wall)
+                if not g_ok:
+                    tuned["enabled"], tuned["mode"] = False, 0
+                    tuned["note"] = "rejected by the step-level guard"
+            if ln.get("enabled"):
+                ln["step_guard"] = dict((res or {}).get("layernorm") or {"error": err}, wall_s=wall)
+                if not l_ok:
+                    ln["enabled"] = False
+                    ln["error"] = "rejected by the step-level guard"
+        if world > 1:
+            flag = torch.tensor([1 if tuned.get("enabled") else 0, 1 if ln.get("enabled") else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if tuned.get("enabled") and not bool(flag[0].item()):
+                tuned["enabled"], tuned["mode"], tuned["note"] = False, 0, "another rank's step guard rejected the variant"
+            if ln.get("enabled") and not bool(flag[1].item()):
+                ln["enabled"], ln["error"] = False, "another rank's step guard rejected the variant"
+    except Exception as e:  # noqa: BLE001  (nothing here may cost the measurement: fall back to the measured kernels)
+        tuned["enabled"], tuned["mode"], ln["enabled"] = False, 0, False
+        tuned["note"] = f"step guard failed: {e!r}"
+    _apply_tuned(tuned)
+    return tuned
+
+
+def run_guard_child(args) -> None:
+    """child side of `_step_guard`: prints {"gemm": {...}, "layernorm": {...}} for the variants pinned in the environment
+    (NK_GEMM_DUAL / _MIN_K / _SKEW, NK_NORM_VARIANT — exported by the parent's `_autotune`)."""
+    import torch
+    from neurosis_b200 import ops, tune
+    from neurosis_b200._lib import lib
+    from neurosis_b200.ddp import BucketedGradReducer
+    gmode = int(os.environ.get("NK_GEMM_DUAL", "0") or 0)
+    nmask = int(os.environ.get("NK_NORM_VARIANT", "0") or 0) & 1
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = CONFIGS[args.config]
+    family, px, B = cfg["family"], cfg["px"], args.batch
+    tune.apply(0)
+    lib.nk_norm_set_variant(0)
+    eng = build_engine(dev, family=family)
+    reducer = BucketedGradReducer([p for p in eng.model.parameters() if p.requires_grad], bucket_mb=256.0)
+    reducer.attach_as_grad_sink()
+    g = torch.Generator().manual_seed(42)
+    batch = {"image": (torch.rand(B, 3, px, px, generator=g) * 2 - 1).to(dev),
+             "crossattn_emb": torch.randn(B, 77, 2048 if family == "sdxl" else 768, generator=g).to(dev)}
+    if family == "sdxl":
+        batch["vector_emb"] = torch.randn(B, 2816, generator=g).to(dev)
+
+    def step(mode: int, norm_mask: int):
+        tune.apply(mode)
+        lib.nk_norm_set_variant(norm_mask)
+        torch.manual_seed(1234)
+        torch.cuda.manual_seed(1234)
+        ops.refresh_weight_copies(force=True)
+        reducer.zero_grad()
+        loss = eng.training_step(dict(batch))
+        loss.backward()
+        reducer.finish()
+        torch.cuda.synchronize()
+        return float(loss.item()), sum(float(b["flat"].double().abs().sum()) for b in reducer.buckets)
+
+    def agree(a, b, tol_loss, tol_grad) -> bool:
+        return bool(b[0] == b[0] and abs(b[0] - a[0]) <= tol_loss * max(abs(a[0]), 1e-30)
+                    and abs(b[1] - a[1]) <= tol_grad * max(abs(a[1]), 1e-30))
+
+    out: dict = {}
+    step(0, 0)  # warm-up (allocator, weight packing)
+    base = step(0, 0)
+    again = step(0, 0)  # run-to-run noise of the measured kernels themselves, reported next to the comparisons
+    out["baseline_repeat"] = {"loss": [base[0], again[0]], "grad_abs_sum": [base[1], again[1]]}
+    ref = base
+    if gmode:
+        got = step(gmode, 0)
+        ok = agree(base, got, 1e-5, 2e-3)
+        out["gemm"] = {"loss_unpaired": base[0], "loss_paired": got[0], "grad_abs_sum_unpaired": base[1],
+                       "grad_abs_sum_paired": got[1], "equal": ok}
+        print(json.dumps(out), flush=True)  # (a later stage that traps must not take this verdict with it)
+        if ok:
+            ref = got
+        else:
+            gmode = 0
+    if nmask:
+        got2 = step(gmode, 1)
+        out["layernorm"] = {"loss_old": ref[0], "loss_new": got2[0], "grad_abs_sum_old": ref[1], "grad_abs_sum_new": got2[1],
+                            "agree": agree(ref, got2, 2e-3, 1e-2)}
+    print(json.dumps(out), flush=True)
 
 
 def _timed(world, dev, k: int, fn) -> float:
@@ -571,15 +732,21 @@ def run_other_configs(args, world: int, rank: int, budget_s: float, per_config_s
     out: dict = {}
     t_start = time.monotonic()
     base_port = int(os.environ.get("MASTER_PORT", "29500"))
-    for k, name in enumerate(OTHER_CONFIGS):
+    variants_on = os.environ.get("NK_GEMM_DUAL", "0") not in ("", "0") or os.environ.get("NK_NORM_VARIANT", "0") not in ("", "0")
+    attempts = [(name, False) for name in OTHER_CONFIGS]
+    while attempts:
+        name, plain = attempts.pop(0)
         left = budget_s - (time.monotonic() - t_start)
         if left < 30.0:
-            out[name] = {"error": f"skipped: {budget_s:.0f} s budget of the secondary configurations used up"}
+            out.setdefault(name, {"error": f"skipped: {budget_s:.0f} s budget of the secondary configurations used up"})
             continue
         env = {key: v for key, v in os.environ.items() if not key.startswith("TORCHELASTIC_")}
         env["MASTER_ADDR"] = "127.0.0.1"
-        env["MASTER_PORT"] = str(20000 + (base_port + 1013 * (k + 1)) % 20000)
+        # the port depends on (configuration, attempt) only, never on what happened to earlier children of THIS rank
+        env["MASTER_PORT"] = str(20000 + (base_port + 1013 * (OTHER_CONFIGS.index(name) + 1) + (517 if plain else 0)) % 20000)
         env["NK_BENCH_EXTRAS"] = "0"
+        if plain:  # second attempt of a configuration that failed with the tuned kernel variants: the measured kernels only
+            env.update({"NK_GEMM_DUAL": "0", "NK_GEMM_DUAL_MIN_K": "0", "NK_GEMM_DUAL_SKEW": "0", "NK_NORM_VARIANT": "0"})
         cmd = _child_cmd(name, args, world)
         t0 = time.monotonic()
         try:
@@ -599,6 +766,12 @@ def run_other_configs(args, world: int, rank: int, budget_s: float, per_config_s
             so, se = proc.communicate()
             rc = "timeout"
         wall = time.monotonic() - t0
+        failed = rc != 0
+        # every rank must take the same decision about a second attempt (the children rendezvous with each other): the
+        # exit status of the own child is what each rank sees, and a multi-rank child set fails or succeeds together
+        # (a rank whose peers died ends in the NCCL timeout or is killed at the limit)
+        if failed and variants_on and not plain:
+            attempts.insert(0, (name, True))
         if rank != 0:
             continue
         row = None
@@ -611,7 +784,11 @@ def run_other_configs(args, world: int, rank: int, budget_s: float, per_config_s
                 break
         if row is None or "value" not in row:
             tail = " | ".join((se or "").strip().splitlines()[-3:])[-400:]
-            out[name] = {"error": f"no result (exit {rc}) after {wall:.0f} s", "stderr_tail": tail}
+            err = {"error": f"no result (exit {rc}) after {wall:.0f} s", "stderr_tail": tail}
+            if failed and variants_on and not plain:
+                out[name + "_with_tuned_variants"] = err  # kept next to the second attempt's result
+            else:
+                out[name] = err
             continue
         c = row.get("config", {})
         summ = {"metric": row["metric"], "value": row["value"], "unit": row["unit"], "n_gpus": row["n_gpus"],
@@ -619,7 +796,8 @@ def run_other_configs(args, world: int, rank: int, budget_s: float, per_config_s
                 "e2e": row.get("e2e"), "batch_per_gpu": c.get("batch_per_gpu"), "workload": c.get("workload"),
                 "gpu_launches": row.get("gpu_launches"), "clock_reasons": (row.get("clocks") or {}).get("reasons"),
                 "sm_mhz": (row.get("clocks") or {}).get("sm_mhz"),
-                "step_tflops_per_gpu": (row.get("roofline") or {}).get("achieved"), "wall_s": round(wall, 1)}
+                "step_tflops_per_gpu": (row.get("roofline") or {}).get("achieved"), "wall_s": round(wall, 1),
+                "tuned_variants_on": bool(variants_on and not plain)}
         for extra in ("square_only_ms_per_step", "encode_images_per_s", "encode_tflops_per_gpu", "peak_mem_gb",
                       "mfu_vs_burst_peak", "buckets_drawn_rank0"):
             if extra in c:
@@ -642,6 +820,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--guard-child", action="store_true", help=argparse.SUPPRESS)  # internal: child side of _step_guard
     ap.add_argument("--other-configs", default="auto", choices=["auto", "none"],
                     help="auto (default run of --config sdxl only): after the headline measurement also run --config "
                          "sd15 / buckets / vae as child processes and report them under `other_configs` of the same line")
@@ -669,6 +848,8 @@ def main() -> None:
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.guard_child:
+        return run_guard_child(args)
     if args.config == "buckets":
         return run_buckets(args)
     if args.config == "vae":
@@ -692,7 +873,10 @@ def main() -> None:
     W = max(int(os.environ.get("NK_BENCH_MIN_WARMUP", "3")), args.warmup)  # >= 3 unless overridden for profiler runs
     B = args.batch
     family, px = cfg["family"], cfg["px"]
-    tuned = _autotune(world, local, dev)  # before the model exists: the probe child needs GPU memory of its own
+    # before the model exists (the probe and guard children need GPU memory of their own): op-level probe of the kernel
+    # variants, then the whole training step of THIS configuration with and without the accepted ones, in a child process
+    tuned = _autotune(world, local, dev)
+    tuned = _step_guard(args, tuned, world, local, dev)
     eng = build_engine(dev, family=family)
     params = [p for p in eng.model.parameters() if p.requires_grad]
     if args.shard_optimizer and args.optimizer != "none":
@@ -737,57 +921,6 @@ def main() -> None:
     for _ in range(2):
         eager_step(resident, False)
     torch.cuda.synchronize()
-    ln_tuned = tuned.get("layernorm_column_owner") or {}
-    if tuned.get("enabled") or ln_tuned.get("enabled"):
-        # step-level guard of the tuned variants, on the real model: the same step (same sigma / noise draws) with the
-        # measured kernels and with the variants.  Stage 1, GEMM row-tile pairing: the forward GEMMs are bit-identical, so
-        # the losses agree to the run-to-run noise of the atomic loss reduction (1e-5) and the gradients differ by the fp32
-        # accumulation order of split-K weight gradients only (abs-sum within 2e-3).  Stage 2, LayerNorm second form on top:
-        # same formulas in another reduction order, outputs agree to bf16 rounding (loss within 2e-3, abs-sum within 1e-2).
-        from neurosis_b200 import tune as _tune
-        from neurosis_b200._lib import lib as _lib_
-
-        def guarded(mode: int, norm_mask: int):
-            _tune.apply(mode)
-            _lib_.nk_norm_set_variant(norm_mask)
-            torch.manual_seed(1234)
-            torch.cuda.manual_seed(1234)
-            loss = eager_step(resident, True)
-            gsum = sum(float(b["flat"].double().abs().sum()) for b in getattr(reducer, "buckets", []))
-            return loss, gsum
-
-        def agree(a, b, tol_loss, tol_grad) -> bool:
-            same = (b[0] == b[0] and abs(b[0] - a[0]) <= tol_loss * max(abs(a[0]), 1e-30)
-                    and abs(b[1] - a[1]) <= tol_grad * max(abs(a[1]), 1e-30))
-            flag = torch.tensor([1 if same else 0], device=dev)
-            if world > 1:
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            return bool(flag.item())
-
-        base = guarded(0, 0)
-        ref = base  # the step with every accepted variant so far
-        gmode = tuned.get("mode", 1) if tuned.get("enabled") else 0
-        if tuned.get("enabled"):
-            got = guarded(gmode, 0)
-            ok = agree(base, got, 1e-5, 2e-3)
-            tuned["step_guard"] = {"loss_unpaired": base[0], "loss_paired": got[0], "grad_abs_sum_unpaired": base[1],
-                                   "grad_abs_sum_paired": got[1], "equal": ok}
-            if ok:
-                ref = got
-            else:
-                tuned["enabled"], tuned["mode"], gmode = False, 0, 0
-                tuned["note"] = "rejected by the step-level guard (losses / gradients differ)"
-        if ln_tuned.get("enabled"):
-            got2 = guarded(gmode, 1)
-            ok2 = agree(ref, got2, 2e-3, 1e-2)
-            ln_tuned["step_guard"] = {"loss_old": ref[0], "loss_new": got2[0], "grad_abs_sum_old": ref[1],
-                                      "grad_abs_sum_new": got2[1], "agree": ok2}
-            if not ok2:
-                ln_tuned["enabled"] = False
-                ln_tuned["error"] = "rejected by the step-level guard"
-        _tune.apply(gmode)
-        _lib_.nk_norm_set_variant(1 if ln_tuned.get("enabled") else 0)
-        _export_tuned({**tuned, "layernorm_column_owner": ln_tuned})
     if args.ncu_step:  # under `ncu --profile-from-start off`: exactly one eager step inside the profiler range
         torch.cuda.synchronize()
         torch.cuda.profiler.start()

@@ -87,3 +87,75 @@ def test_two_ranks_children_rendezvous_under_torchrun():
     for name in bench.OTHER_CONFIGS:
         assert out[name]["value"] == 3.0 and out[name]["n_gpus"] == 2, out[name]
     assert len({out[name]["workload"] for name in bench.OTHER_CONFIGS}) == 3  # one port per configuration
+
+
+def test_configuration_that_fails_with_tuned_variants_is_retried_on_the_measured_kernels(monkeypatch):
+    """the kernel variants are validated on the SDXL step only; a secondary configuration whose child dies with them
+    pinned on is run again with every variant off, and both outcomes are reported."""
+    code = ("import os, sys, json\n"
+            "if os.environ.get('NK_GEMM_DUAL', '0') != '0': sys.stderr.write('trap\\n'); sys.exit(134)\n"
+            "print(json.dumps({'metric': 'm', 'value': 7.0, 'unit': 'u', 'n_gpus': 1, 'steps': 1, 'warmup': 1, 'ms_per_step': 1.0,"
+            " 'config': {'workload': os.environ['MASTER_PORT']}}))")
+    monkeypatch.setattr(bench, "_child_cmd", lambda name, args, world: [sys.executable, "-c", code])
+    monkeypatch.setenv("NK_GEMM_DUAL", "1")
+    monkeypatch.setenv("MASTER_PORT", "29500")
+    out = bench.run_other_configs(_args(), world=1, rank=0, budget_s=200.0, per_config_s=20.0)
+    for name in bench.OTHER_CONFIGS:
+        assert out[name]["value"] == 7.0 and out[name]["tuned_variants_on"] is False
+        assert "exit 134" in out[name + "_with_tuned_variants"]["error"]
+    # retry ports differ from first-attempt ports and from each other
+    assert len({out[n]["workload"] for n in bench.OTHER_CONFIGS}) == 3
+    monkeypatch.setenv("NK_GEMM_DUAL", "0")  # nothing tuned: a failure is final, no second attempt
+    monkeypatch.setattr(bench, "_child_cmd", lambda name, args, world: [sys.executable, "-c", "import sys; sys.exit(3)"])
+    out = bench.run_other_configs(_args(), world=1, rank=0, budget_s=200.0, per_config_s=20.0)
+    assert all("error" in out[n] for n in bench.OTHER_CONFIGS) and not any(k.endswith("_with_tuned_variants") for k in out)
+
+
+def test_step_guard_keeps_or_drops_variants_and_sets_the_library(monkeypatch):
+    """parent side of the child-process step guard: verdicts of the child -> `tuned`, library modes and the exported
+    environment; a child that dies (no verdict) drops every variant."""
+    from neurosis_b200._lib import lib
+
+    class Fake:
+        def __init__(self, out, rc=0):
+            self.out, self.returncode, self.pid = out, rc, 0
+
+        def communicate(self, timeout=None):
+            return self.out, "boom"
+
+    def tuned():
+        return {"enabled": True, "mode": 1, "min_k_iters": 20, "skew": 3,
+                "layernorm_column_owner": {"enabled": True, "speedup": 1.3}}
+
+    args = types.SimpleNamespace(config="sdxl", batch=16)
+    both = json.dumps({"gemm": {"equal": True, "loss_unpaired": 1.0, "loss_paired": 1.0},
+                       "layernorm": {"agree": True, "loss_old": 1.0, "loss_new": 1.0005}})
+    monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: Fake("warm\n" + both + "\n"))
+    t = bench._step_guard(args, tuned(), 1, 0, None)
+    assert t["enabled"] and t["layernorm_column_owner"]["enabled"] and t["step_guard"]["equal"]
+    assert (lib.nk_gemm_set_dual(-1), lib.nk_gemm_set_dual_min_k(-1), lib.nk_gemm_set_dual_skew(-1), lib.nk_norm_set_variant(-1)) == (1, 20, 3, 1)
+    assert (bench.os.environ["NK_GEMM_DUAL"], bench.os.environ["NK_GEMM_DUAL_MIN_K"], bench.os.environ["NK_NORM_VARIANT"]) == ("1", "20", "1")
+    # the GEMM stage passed and was flushed, then the LayerNorm stage took the child down
+    first = json.dumps({"gemm": {"equal": True}})
+    monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: Fake(first + "\n", rc=-6))
+    t = bench._step_guard(args, tuned(), 1, 0, None)
+    assert t["enabled"] and not t["layernorm_column_owner"]["enabled"]
+    assert (lib.nk_gemm_set_dual(-1), lib.nk_norm_set_variant(-1), bench.os.environ["NK_NORM_VARIANT"]) == (1, 0, "0")
+    # the step disagrees with pairing on
+    bad = json.dumps({"gemm": {"equal": False, "loss_unpaired": 1.0, "loss_paired": 1.7}, "layernorm": {"agree": True}})
+    monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: Fake(bad + "\n"))
+    t = bench._step_guard(args, tuned(), 1, 0, None)
+    assert not t["enabled"] and t["layernorm_column_owner"]["enabled"] and lib.nk_gemm_set_dual(-1) == 0
+    # no verdict at all
+    monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: Fake("", rc=-9))
+    t = bench._step_guard(args, tuned(), 1, 0, None)
+    assert not t["enabled"] and not t["layernorm_column_owner"]["enabled"] and "error" in t["step_guard"]
+    assert (lib.nk_gemm_set_dual(-1), lib.nk_norm_set_variant(-1), bench.os.environ["NK_GEMM_DUAL"]) == (0, 0, "0")
+    # nothing accepted by the probe: no child is started
+    monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: (_ for _ in ()).throw(AssertionError("no child expected")))
+    t = bench._step_guard(args, {"enabled": False, "layernorm_column_owner": {"enabled": False}}, 1, 0, None)
+    assert not t["enabled"]
+    for k in ("NK_GEMM_DUAL", "NK_GEMM_DUAL_MIN_K", "NK_GEMM_DUAL_SKEW", "NK_NORM_VARIANT"):
+        bench.os.environ.pop(k, None)
+    lib.nk_gemm_set_dual_min_k(0)
+    lib.nk_gemm_set_dual_skew(0)
