@@ -299,9 +299,14 @@ def _autotune_unsafe(world: int, local: int, dev) -> dict:
     from neurosis_b200._lib import lib
     rep = tune.autotune(local)
     ln = rep.setdefault("layernorm_column_owner", {"enabled": False})
+    pf = rep.setdefault("epilogue_l2_prefetch", {"enabled": False})
     if world > 1:
-        flag = torch.tensor([1 if rep.get("enabled") else 0, 1 if ln.get("enabled") else 0], device=dev)
+        flag = torch.tensor([1 if rep.get("enabled") else 0, 1 if ln.get("enabled") else 0, 1 if pf.get("enabled") else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if bool(pf.get("enabled")) != bool(flag[2].item()):
+            pf["enabled"] = False
+            pf["error"] = "another rank rejected the variant"
+            lib.nk_gemm_set_epi_prefetch(0)
         if bool(rep.get("enabled")) != bool(flag[0].item()):
             rep["enabled"], rep["mode"] = False, 0
             rep["note"] = "another rank rejected the variant"
@@ -333,6 +338,7 @@ def _export_tuned(rep: dict) -> None:
     os.environ["NK_GEMM_DUAL_MIN_K"] = str(int(rep.get("min_k_iters") or 0) if on else 0)
     os.environ["NK_GEMM_DUAL_SKEW"] = str(int(rep.get("skew") or 0) if on else 0)
     os.environ["NK_NORM_VARIANT"] = "1" if (rep.get("layernorm_column_owner") or {}).get("enabled") else "0"
+    os.environ["NK_GEMM_EPI_PREFETCH"] = "1" if (rep.get("epilogue_l2_prefetch") or {}).get("enabled") else "0"
 
 
 def _apply_tuned(tuned: dict) -> None:
@@ -344,6 +350,7 @@ def _apply_tuned(tuned: dict) -> None:
     lib.nk_gemm_set_dual_skew(int(tuned.get("skew") or 0) if on else 0)
     tune.apply(int(tuned.get("mode", 1)) if on else 0)
     lib.nk_norm_set_variant(1 if (tuned.get("layernorm_column_owner") or {}).get("enabled") else 0)
+    lib.nk_gemm_set_epi_prefetch(1 if (tuned.get("epilogue_l2_prefetch") or {}).get("enabled") else 0)
     _export_tuned(tuned)
 
 
@@ -352,6 +359,7 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
     in a CHILD process (`bench.py --guard-child`, single GPU, no process group): the same training step (same sigma /
     noise draws) with the measured kernels and with the variants.  A variant that traps on a shape the probe did not
     cover takes the child down, never the process that measures; a variant whose step disagrees is dropped.
+      stage 0, epilogue L2 prefetch: a hint, the step must be unchanged (same tolerances as stage 1);
       stage 1, GEMM row-tile pairing: the forward GEMMs are bit-identical, so the losses agree to the run-to-run noise of
         the atomic loss reduction (1e-5); the gradients differ by the fp32 accumulation order of split-K weight gradients
         only (abs-sum within 2e-3);
@@ -363,8 +371,9 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
     import torch
     import torch.distributed as dist
     ln = tuned.setdefault("layernorm_column_owner", {"enabled": False})
+    pf = tuned.setdefault("epilogue_l2_prefetch", {"enabled": False})
     try:
-        if tuned.get("enabled") or ln.get("enabled"):
+        if tuned.get("enabled") or ln.get("enabled") or pf.get("enabled"):
             env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")
                    and k not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "MASTER_PORT", "MASTER_ADDR")}
             env.update({"LOCAL_RANK": str(local), "NK_BENCH_EXTRAS": "0", "NK_B200_TUNE": "0"})
@@ -404,15 +413,23 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
                 if not l_ok:
                     ln["enabled"] = False
                     ln["error"] = "rejected by the step-level guard"
+            if pf.get("enabled"):
+                pf["step_guard"] = dict((res or {}).get("prefetch") or {"error": err}, wall_s=wall)
+                if not bool(res and (res.get("prefetch") or {}).get("equal")):
+                    pf["enabled"] = False
+                    pf["error"] = "rejected by the step-level guard"
         if world > 1:
-            flag = torch.tensor([1 if tuned.get("enabled") else 0, 1 if ln.get("enabled") else 0], device=dev)
+            flag = torch.tensor([1 if tuned.get("enabled") else 0, 1 if ln.get("enabled") else 0, 1 if pf.get("enabled") else 0],
+                                device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if pf.get("enabled") and not bool(flag[2].item()):
+                pf["enabled"], pf["error"] = False, "another rank's step guard rejected the variant"
             if tuned.get("enabled") and not bool(flag[0].item()):
                 tuned["enabled"], tuned["mode"], tuned["note"] = False, 0, "another rank's step guard rejected the variant"
             if ln.get("enabled") and not bool(flag[1].item()):
                 ln["enabled"], ln["error"] = False, "another rank's step guard rejected the variant"
     except Exception as e:  # noqa: BLE001  (nothing here may cost the measurement: fall back to the measured kernels)
-        tuned["enabled"], tuned["mode"], ln["enabled"] = False, 0, False
+        tuned["enabled"], tuned["mode"], ln["enabled"], pf["enabled"] = False, 0, False, False
         tuned["note"] = f"step guard failed: {e!r}"
     _apply_tuned(tuned)
     return tuned
@@ -427,6 +444,7 @@ def run_guard_child(args) -> None:
     from neurosis_b200.ddp import BucketedGradReducer
     gmode = int(os.environ.get("NK_GEMM_DUAL", "0") or 0)
     nmask = int(os.environ.get("NK_NORM_VARIANT", "0") or 0) & 1
+    pfon = 1 if os.environ.get("NK_GEMM_EPI_PREFETCH", "0") not in ("", "0") else 0
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -434,6 +452,7 @@ def run_guard_child(args) -> None:
     family, px, B = cfg["family"], cfg["px"], args.batch
     tune.apply(0)
     lib.nk_norm_set_variant(0)
+    lib.nk_gemm_set_epi_prefetch(0)
     eng = build_engine(dev, family=family)
     reducer = BucketedGradReducer([p for p in eng.model.parameters() if p.requires_grad], bucket_mb=256.0)
     reducer.attach_as_grad_sink()
@@ -466,10 +485,21 @@ def run_guard_child(args) -> None:
     again = step(0, 0)  # run-to-run noise of the measured kernels themselves, reported next to the comparisons
     out["baseline_repeat"] = {"loss": [base[0], again[0]], "grad_abs_sum": [base[1], again[1]]}
     ref = base
+    if pfon:
+        lib.nk_gemm_set_epi_prefetch(1)
+        gotp = step(0, 0)
+        okp = agree(base, gotp, 1e-5, 2e-3)
+        out["prefetch"] = {"loss_off": base[0], "loss_on": gotp[0], "grad_abs_sum_off": base[1], "grad_abs_sum_on": gotp[1],
+                           "equal": okp}
+        print(json.dumps(out), flush=True)
+        if okp:
+            ref = gotp
+        else:
+            lib.nk_gemm_set_epi_prefetch(0)
     if gmode:
         got = step(gmode, 0)
-        ok = agree(base, got, 1e-5, 2e-3)
-        out["gemm"] = {"loss_unpaired": base[0], "loss_paired": got[0], "grad_abs_sum_unpaired": base[1],
+        ok = agree(ref, got, 1e-5, 2e-3)
+        out["gemm"] = {"loss_unpaired": ref[0], "loss_paired": got[0], "grad_abs_sum_unpaired": ref[1],
                        "grad_abs_sum_paired": got[1], "equal": ok}
         print(json.dumps(out), flush=True)  # (a later stage that traps must not take this verdict with it)
         if ok:

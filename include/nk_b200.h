@@ -98,6 +98,14 @@ int nk_gemm_set_dual_min_k(int k_iters);
  * and reaches its own epilogue earlier.  Does not change results.  0..7 sets, anything else queries; returns the previous
  * value (default 0, or NK_GEMM_DUAL_SKEW). */
 int nk_gemm_set_dual_skew(int k_iters);
+/* Epilogue side-input prefetch: at the start of every output tile one thread per epilogue warp-half issues
+ * `cp.async.bulk.prefetch.tensor.L2` for the boxes of the residual (EPI_LINEAR) or of the saved GEGLU pre-activation h
+ * (nk_linear_dgrad_geglu) that the epilogue will read — while the tile's main loop still runs.  The epilogue reads that
+ * input with one 32-byte load per thread (= row) and 16-column chunk, which is latency-bound when the rows come from DRAM.
+ * A hint to the memory system: results are unchanged by construction.  0 off (default, or NK_GEMM_EPI_PREFETCH), 1 on,
+ * anything else queries; returns the previous value.  Reference sites of the fused adds: modules/attention.py:497-511
+ * (x + attn(...), x + ff(...)), modules/diffusion/openaimodel.py:337-342 (skip_connection(x) + h). */
+int nk_gemm_set_epi_prefetch(int on);
 
 /* y[M,N] = x[M,K] @ w[N,K]^T (+ bias[N]) (+ residual[M,N]);  y bf16 (out_f32 = 0) or fp32.
  * Replaces nn.Linear forward: modules/attention.py:283-290 (to_q/k/v/to_out), :53,:67-71 (GEGLU /

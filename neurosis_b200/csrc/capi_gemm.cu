@@ -67,6 +67,7 @@ int nk_sm_count(void) { return nk::device_sm_count(); }
 int nk_gemm_set_dual(int mode) { return nk::gemm_set_dual(mode); }
 int nk_gemm_set_dual_min_k(int k_iters) { return nk::gemm_set_dual_min_k(k_iters); }
 int nk_gemm_set_dual_skew(int k_iters) { return nk::gemm_set_dual_skew(k_iters); }
+int nk_gemm_set_epi_prefetch(int on) { return nk::gemm_set_epi_prefetch(on); }
 
 int nk_gemm_ex(const nk_gemm_desc* d, nk_stream_t stream) {
     NK_REQUIRE(d != nullptr, NK_ERR_SHAPE, "null descriptor");

@@ -219,6 +219,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* 
         : "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// hint: fetch one box of a tensor map into L2 (no shared memory, no completion tracking); out-of-range parts are ignored
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the newest N bulk groups of this thread have finished READING their smem source
 template <int N>

@@ -49,7 +49,7 @@ struct alignas(64) GemmDev {
     CUtensorMap tmA;
     CUtensorMap tmB;
     CUtensorMap tmC;   // output tile store (tma_out): bf16 boxes {64 cols, rows} / fp32 boxes {32 cols, rows}
-    CUtensorMap tmC2;  // EPI_GEGLU_FWD: the gated output [M, D]
+    CUtensorMap tmC2;  // EPI_GEGLU_FWD: the gated output [M, D]; with epi_prefetch: the epilogue's side input (residual / GEGLU h)
     int tma_out;       // 1: the epilogue stages 128-byte-wide column groups in shared memory and stores them with TMA
     int stg_per_half;  // staging tiles per epilogue warp-half
     int has_c;         // EPI_GEGLU_FWD: h is stored as well
@@ -64,6 +64,7 @@ struct alignas(64) GemmDev {
     int dbg_skip;                // NK_GEMM_DBG_SKIP bit 1: no A loads, bit 2: no B loads (timing experiments, wrong results)
     int raster_gm;               // > 0: tiles are walked in groups of raster_gm row blocks x all N tiles (see launch_gemm)
     int dual_skew;               // DUAL: k-iterations by which row tile 1 trails row tile 0 (clamped to stages - 1 in the kernel)
+    int epi_prefetch;            // 1: tmC2 maps the epilogue's side input (residual, or h of EPI_GEGLU_BWD); its boxes are prefetched into L2
     int a_b2, a_b1, b_b2, b_b1;  // 0/1: does the operand carry that batch dimension
     // conv geometry
     int cH, cW, bw, bh, tiles_w, tiles_h, cin_blocks, ksize, pad;  // cH, cW: OUTPUT image (= input unless strided)
@@ -544,6 +545,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
             const float* bias_img_row = g.bias_img ? g.bias_img + static_cast<long long>(img) * g.N : nullptr;
 
+            if (TMA_OUT && g.epi_prefetch && st_elected && tile_ok) {
+                // The side input of this warp-half's column groups goes to L2 NOW, while the main loop of this tile still
+                // runs: the epilogue reads it with one 32-byte load per thread = row and chunk (32 rows per warp
+                // instruction), which is latency-bound when the rows come from DRAM (the GEGLU data gradient reads
+                // 335 MB of h per call this way and runs at half the rate of the other GEMMs).  A hint only.
+                if constexpr (VAR == VAR_GEGLU_BWD) {
+                    const int ngp = g.BN / 64;
+                    const int pb = half ? (ngp + 1) / 2 : 0, pe = half ? ngp : (ngp + 1) / 2;
+                    for (int gi = pb; gi < pe; ++gi) {
+                        const int col = n0 + gi * 64;
+                        if (col < g.geglu_d) {
+                            tma_prefetch_l2_4d(&g.tmC2, col, sc1, sc2, sc3);
+                            tma_prefetch_l2_4d(&g.tmC2, g.geglu_d + col, sc1, sc2, sc3);
+                        }
+                    }
+                } else if constexpr (VAR == VAR_MAIN) {
+                    const int ngp = (g.BN + 63) / 64;
+                    const int pb = half ? (ngp + 1) / 2 : 0, pe = half ? ngp : (ngp + 1) / 2;
+                    for (int gi = pb; gi < pe; ++gi) {
+                        const int col = n0 + gi * 64;
+                        if (col < g.N) tma_prefetch_l2_4d(&g.tmC2, col, sc1, sc2, sc3);
+                    }
+                }
+            }
             const long long te0 = g.dbg ? clock64() : 0;
             mbar_wait(&tmem_full[acc], (local >> 1) & 1u, 400u + acc);
             const long long te1 = g.dbg ? clock64() : 0;
@@ -1265,6 +1290,21 @@ int gemm_set_dual_skew(int k_iters) {
     if (k_iters >= 0 && k_iters <= 7) g_dual_skew = k_iters;
     return prev;
 }
+// L2 prefetch of the epilogue's side input (residual of EPI_LINEAR, h of EPI_GEGLU_BWD) at the start of every tile: 0 off
+// (default, or NK_GEMM_EPI_PREFETCH), 1 on.  A hint to the memory system, results are unchanged by construction.
+static int g_epi_prefetch = -1;
+static int epi_prefetch_mode() {
+    if (g_epi_prefetch < 0) {
+        const char* e_ = getenv("NK_GEMM_EPI_PREFETCH");
+        g_epi_prefetch = e_ ? (atoi(e_) != 0 ? 1 : 0) : 0;
+    }
+    return g_epi_prefetch;
+}
+int gemm_set_epi_prefetch(int on) {
+    const int prev = epi_prefetch_mode();
+    if (on == 0 || on == 1) g_epi_prefetch = on;
+    return prev;
+}
 int gemm_set_dual_min_k(int k_iters) {
     const int prev = dual_min_k();
     if (k_iters >= 0) g_dual_min_k = k_iters;
@@ -1577,6 +1617,17 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
         if (geglu_fwd) {
             e = make_out_tmap(&g.tmC2, p.C2, 0, p.N, p.ldc2, g, p);
             if (e) return e;
+        } else if (epi_prefetch_mode()) {
+            // side-input map (same logical shape and batch strides as the output, its own row stride)
+            if (geglu_bwd && aligned16(p.aux, p.ldr * 2)) {
+                e = make_out_tmap(&g.tmC2, p.aux, 0, 2LL * p.N, p.ldr, g, p);
+                if (e) return e;
+                g.epi_prefetch = 1;
+            } else if (!geglu_bwd && p.epi == EPI_LINEAR && p.residual != nullptr && aligned16(p.residual, p.ldr * 2)) {
+                e = make_out_tmap(&g.tmC2, p.residual, 0, p.N, p.ldr, g, p);
+                if (e) return e;
+                g.epi_prefetch = 1;
+            }
         }
     }
     const int staging_bytes = tma_out ? 2 * g.stg_per_half * STG_BYTES : 0;

@@ -73,6 +73,8 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream);
 int gemm_set_dual(int mode);
 // mode 1 only: smallest number of 64-deep k-iterations a launch must have to be paired (< 0 queries); returns the previous value
 int gemm_set_dual_min_k(int k_iters);
+// L2 prefetch of the epilogue's side input (residual / GEGLU h) at tile start: 0 off, 1 on, anything else queries; returns the previous value
+int gemm_set_epi_prefetch(int on);
 // paired launches: k-iterations by which the second row tile trails the first (0..7, clamped to stages - 1; < 0 queries)
 int gemm_set_dual_skew(int k_iters);
 

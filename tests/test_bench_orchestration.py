@@ -125,21 +125,23 @@ def test_step_guard_keeps_or_drops_variants_and_sets_the_library(monkeypatch):
 
     def tuned():
         return {"enabled": True, "mode": 1, "min_k_iters": 20, "skew": 3,
-                "layernorm_column_owner": {"enabled": True, "speedup": 1.3}}
+                "layernorm_column_owner": {"enabled": True, "speedup": 1.3}, "epilogue_l2_prefetch": {"enabled": True, "speedup": 1.1}}
 
     args = types.SimpleNamespace(config="sdxl", batch=16)
-    both = json.dumps({"gemm": {"equal": True, "loss_unpaired": 1.0, "loss_paired": 1.0},
+    both = json.dumps({"prefetch": {"equal": True}, "gemm": {"equal": True, "loss_unpaired": 1.0, "loss_paired": 1.0},
                        "layernorm": {"agree": True, "loss_old": 1.0, "loss_new": 1.0005}})
     monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: Fake("warm\n" + both + "\n"))
     t = bench._step_guard(args, tuned(), 1, 0, None)
     assert t["enabled"] and t["layernorm_column_owner"]["enabled"] and t["step_guard"]["equal"]
+    assert t["epilogue_l2_prefetch"]["enabled"] and lib.nk_gemm_set_epi_prefetch(-1) == 1 and bench.os.environ["NK_GEMM_EPI_PREFETCH"] == "1"
     assert (lib.nk_gemm_set_dual(-1), lib.nk_gemm_set_dual_min_k(-1), lib.nk_gemm_set_dual_skew(-1), lib.nk_norm_set_variant(-1)) == (1, 20, 3, 1)
     assert (bench.os.environ["NK_GEMM_DUAL"], bench.os.environ["NK_GEMM_DUAL_MIN_K"], bench.os.environ["NK_NORM_VARIANT"]) == ("1", "20", "1")
     # the GEMM stage passed and was flushed, then the LayerNorm stage took the child down
-    first = json.dumps({"gemm": {"equal": True}})
+    first = json.dumps({"prefetch": {"equal": False}, "gemm": {"equal": True}})
     monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: Fake(first + "\n", rc=-6))
     t = bench._step_guard(args, tuned(), 1, 0, None)
-    assert t["enabled"] and not t["layernorm_column_owner"]["enabled"]
+    assert t["enabled"] and not t["layernorm_column_owner"]["enabled"] and not t["epilogue_l2_prefetch"]["enabled"]
+    assert lib.nk_gemm_set_epi_prefetch(-1) == 0 and bench.os.environ["NK_GEMM_EPI_PREFETCH"] == "0"
     assert (lib.nk_gemm_set_dual(-1), lib.nk_norm_set_variant(-1), bench.os.environ["NK_NORM_VARIANT"]) == (1, 0, "0")
     # the step disagrees with pairing on
     bad = json.dumps({"gemm": {"equal": False, "loss_unpaired": 1.0, "loss_paired": 1.7}, "layernorm": {"agree": True}})
@@ -155,7 +157,7 @@ def test_step_guard_keeps_or_drops_variants_and_sets_the_library(monkeypatch):
     monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: (_ for _ in ()).throw(AssertionError("no child expected")))
     t = bench._step_guard(args, {"enabled": False, "layernorm_column_owner": {"enabled": False}}, 1, 0, None)
     assert not t["enabled"]
-    for k in ("NK_GEMM_DUAL", "NK_GEMM_DUAL_MIN_K", "NK_GEMM_DUAL_SKEW", "NK_NORM_VARIANT"):
+    for k in ("NK_GEMM_DUAL", "NK_GEMM_DUAL_MIN_K", "NK_GEMM_DUAL_SKEW", "NK_NORM_VARIANT", "NK_GEMM_EPI_PREFETCH"):
         bench.os.environ.pop(k, None)
     lib.nk_gemm_set_dual_min_k(0)
     lib.nk_gemm_set_dual_skew(0)

@@ -89,13 +89,22 @@ def test_verdict_rules(monkeypatch):
     reps[1] = {**L, "ok": False, "speedup": 1.6}   # faster but wrong: stays off
     assert not tune.autotune()["layernorm_column_owner"]["enabled"] and lib.nk_norm_set_variant(-1) == 0
     reps[1] = {**L, "ok": True, "speedup": 1.4}
-    reps[2]["ok"] = False  # the skewed order failed its equality checks: the plain order is used
+    # third variant: the epilogue prefetch hint
+    assert not got["epilogue_l2_prefetch"]["enabled"] and "no verdict" in got["epilogue_l2_prefetch"]["error"]
+    reps.insert(2, {"variant": "epilogue_l2_prefetch", "ok": True, "speedup": 1.06, "checks": [], "timings": []})
+    got = tune.autotune()
+    assert got["epilogue_l2_prefetch"]["enabled"] and lib.nk_gemm_set_epi_prefetch(-1) == 1
+    json.dumps(tune._summary(got))
+    reps[2]["speedup"] = 1.0
+    assert not tune.autotune()["epilogue_l2_prefetch"]["enabled"] and lib.nk_gemm_set_epi_prefetch(-1) == 0
+    reps[3]["ok"] = False  # the skewed order failed its equality checks: the plain order is used
     got = tune.autotune()
     assert got["enabled"] and got["skew"] == 0 and lib.nk_gemm_set_dual_skew(-1) == 0 and len(got["candidates"]) == 2
     lib.nk_gemm_set_dual(0)
     lib.nk_gemm_set_dual_min_k(0)
     lib.nk_gemm_set_dual_skew(0)
     lib.nk_norm_set_variant(0)
+    lib.nk_gemm_set_epi_prefetch(0)
 
 
 def test_probe_shapes_cover_every_paired_mode():
