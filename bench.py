@@ -300,9 +300,14 @@ def _autotune_unsafe(world: int, local: int, dev) -> dict:
     rep = tune.autotune(local)
     ln = rep.setdefault("layernorm_column_owner", {"enabled": False})
     pf = rep.setdefault("epilogue_l2_prefetch", {"enabled": False})
+    gn = rep.setdefault("groupnorm_reverse_apply", {"enabled": False})
     if world > 1:
-        flag = torch.tensor([1 if rep.get("enabled") else 0, 1 if ln.get("enabled") else 0, 1 if pf.get("enabled") else 0], device=dev)
+        flag = torch.tensor([1 if rep.get("enabled") else 0, 1 if ln.get("enabled") else 0, 1 if pf.get("enabled") else 0,
+                             1 if gn.get("enabled") else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if bool(gn.get("enabled")) != bool(flag[3].item()):
+            gn["enabled"] = False
+            gn["error"] = "another rank rejected the variant"
         if bool(pf.get("enabled")) != bool(flag[2].item()):
             pf["enabled"] = False
             pf["error"] = "another rank rejected the variant"
@@ -314,7 +319,7 @@ def _autotune_unsafe(world: int, local: int, dev) -> dict:
         if bool(ln.get("enabled")) != bool(flag[1].item()):
             ln["enabled"] = False
             ln["error"] = "another rank rejected the variant"
-            lib.nk_norm_set_variant(0)
+        lib.nk_norm_set_variant(_norm_mask(rep))
     _export_tuned(rep)
     return tune._summary(rep)
 
@@ -332,12 +337,17 @@ def _autotune(world: int, local: int, dev) -> dict:
         return tuned
 
 
+def _norm_mask(tuned: dict) -> int:
+    return ((1 if (tuned.get("layernorm_column_owner") or {}).get("enabled") else 0)
+            | (2 if (tuned.get("groupnorm_reverse_apply") or {}).get("enabled") else 0))
+
+
 def _export_tuned(rep: dict) -> None:
     on = bool(rep.get("enabled"))
     os.environ["NK_GEMM_DUAL"] = str(rep.get("mode", 0) if on else 0)
     os.environ["NK_GEMM_DUAL_MIN_K"] = str(int(rep.get("min_k_iters") or 0) if on else 0)
     os.environ["NK_GEMM_DUAL_SKEW"] = str(int(rep.get("skew") or 0) if on else 0)
-    os.environ["NK_NORM_VARIANT"] = "1" if (rep.get("layernorm_column_owner") or {}).get("enabled") else "0"
+    os.environ["NK_NORM_VARIANT"] = str(_norm_mask(rep))
     os.environ["NK_GEMM_EPI_PREFETCH"] = "1" if (rep.get("epilogue_l2_prefetch") or {}).get("enabled") else "0"
 
 
@@ -349,7 +359,7 @@ def _apply_tuned(tuned: dict) -> None:
     lib.nk_gemm_set_dual_min_k(int(tuned.get("min_k_iters") or 0) if on else 0)
     lib.nk_gemm_set_dual_skew(int(tuned.get("skew") or 0) if on else 0)
     tune.apply(int(tuned.get("mode", 1)) if on else 0)
-    lib.nk_norm_set_variant(1 if (tuned.get("layernorm_column_owner") or {}).get("enabled") else 0)
+    lib.nk_norm_set_variant(_norm_mask(tuned))
     lib.nk_gemm_set_epi_prefetch(1 if (tuned.get("epilogue_l2_prefetch") or {}).get("enabled") else 0)
     _export_tuned(tuned)
 
@@ -363,6 +373,7 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
       stage 1, GEMM row-tile pairing: the forward GEMMs are bit-identical, so the losses agree to the run-to-run noise of
         the atomic loss reduction (1e-5); the gradients differ by the fp32 accumulation order of split-K weight gradients
         only (abs-sum within 2e-3);
+      stage 1b, GroupNorm second passes backwards: only the block dispatch order changes, same tolerances as stage 1;
       stage 2, LayerNorm second form on top: same formulas in another reduction order, outputs agree to bf16 rounding (loss
         within 2e-3, gradient abs-sum within 1e-2).
     Under N > 1 a variant survives only if every rank's guard accepted it."""
@@ -372,8 +383,9 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
     import torch.distributed as dist
     ln = tuned.setdefault("layernorm_column_owner", {"enabled": False})
     pf = tuned.setdefault("epilogue_l2_prefetch", {"enabled": False})
+    gn = tuned.setdefault("groupnorm_reverse_apply", {"enabled": False})
     try:
-        if tuned.get("enabled") or ln.get("enabled") or pf.get("enabled"):
+        if tuned.get("enabled") or ln.get("enabled") or pf.get("enabled") or gn.get("enabled"):
             env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")
                    and k not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "MASTER_PORT", "MASTER_ADDR")}
             env.update({"LOCAL_RANK": str(local), "NK_BENCH_EXTRAS": "0", "NK_B200_TUNE": "0"})
@@ -413,15 +425,22 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
                 if not l_ok:
                     ln["enabled"] = False
                     ln["error"] = "rejected by the step-level guard"
+            if gn.get("enabled"):
+                gn["step_guard"] = dict((res or {}).get("groupnorm") or {"error": err}, wall_s=wall)
+                if not bool(res and (res.get("groupnorm") or {}).get("equal")):
+                    gn["enabled"] = False
+                    gn["error"] = "rejected by the step-level guard"
             if pf.get("enabled"):
                 pf["step_guard"] = dict((res or {}).get("prefetch") or {"error": err}, wall_s=wall)
                 if not bool(res and (res.get("prefetch") or {}).get("equal")):
                     pf["enabled"] = False
                     pf["error"] = "rejected by the step-level guard"
         if world > 1:
-            flag = torch.tensor([1 if tuned.get("enabled") else 0, 1 if ln.get("enabled") else 0, 1 if pf.get("enabled") else 0],
-                                device=dev)
+            flag = torch.tensor([1 if tuned.get("enabled") else 0, 1 if ln.get("enabled") else 0, 1 if pf.get("enabled") else 0,
+                                 1 if gn.get("enabled") else 0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if gn.get("enabled") and not bool(flag[3].item()):
+                gn["enabled"], gn["error"] = False, "another rank's step guard rejected the variant"
             if pf.get("enabled") and not bool(flag[2].item()):
                 pf["enabled"], pf["error"] = False, "another rank's step guard rejected the variant"
             if tuned.get("enabled") and not bool(flag[0].item()):
@@ -429,7 +448,7 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
             if ln.get("enabled") and not bool(flag[1].item()):
                 ln["enabled"], ln["error"] = False, "another rank's step guard rejected the variant"
     except Exception as e:  # noqa: BLE001  (nothing here may cost the measurement: fall back to the measured kernels)
-        tuned["enabled"], tuned["mode"], ln["enabled"], pf["enabled"] = False, 0, False, False
+        tuned["enabled"], tuned["mode"], ln["enabled"], pf["enabled"], gn["enabled"] = False, 0, False, False, False
         tuned["note"] = f"step guard failed: {e!r}"
     _apply_tuned(tuned)
     return tuned
@@ -443,7 +462,7 @@ def run_guard_child(args) -> None:
     from neurosis_b200._lib import lib
     from neurosis_b200.ddp import BucketedGradReducer
     gmode = int(os.environ.get("NK_GEMM_DUAL", "0") or 0)
-    nmask = int(os.environ.get("NK_NORM_VARIANT", "0") or 0) & 1
+    nmask = int(os.environ.get("NK_NORM_VARIANT", "0") or 0) & 3
     pfon = 1 if os.environ.get("NK_GEMM_EPI_PREFETCH", "0") not in ("", "0") else 0
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -506,8 +525,17 @@ def run_guard_child(args) -> None:
             ref = got
         else:
             gmode = 0
-    if nmask:
-        got2 = step(gmode, 1)
+    keep = 0
+    if nmask & 2:  # GroupNorm second passes backwards: same blocks, other dispatch order — the step must be unchanged
+        got3 = step(gmode, 2)
+        ok3 = agree(ref, got3, 1e-5, 2e-3)
+        out["groupnorm"] = {"loss_old": ref[0], "loss_new": got3[0], "grad_abs_sum_old": ref[1], "grad_abs_sum_new": got3[1],
+                            "equal": ok3}
+        print(json.dumps(out), flush=True)
+        if ok3:
+            ref, keep = got3, 2
+    if nmask & 1:
+        got2 = step(gmode, keep | 1)
         out["layernorm"] = {"loss_old": ref[0], "loss_new": got2[0], "grad_abs_sum_old": ref[1], "grad_abs_sum_new": got2[1],
                             "agree": agree(ref, got2, 2e-3, 1e-2)}
     print(json.dumps(out), flush=True)

@@ -114,11 +114,14 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long x_stride, 
                                 long long y_stride, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, int HW, int C, int G, int V, int ppb,
-                                int pix_per_chunk, int silu) {
+                                int pix_per_chunk, int silu, int reverse) {
     extern __shared__ float sm[];  // a[C], b[C]
     float* s_a = sm;
     float* s_b = sm + C;
-    const int img = blockIdx.y, chunk = blockIdx.x;
+    // reverse (nk_norm_set_variant bit 1): blocks are dispatched in increasing linear index, the statistics pass read x in
+    // that order, so walking the (image, chunk) grid backwards lets this pass start on the part of x that is still in L2
+    const int img = reverse ? static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y) : static_cast<int>(blockIdx.y);
+    const int chunk = reverse ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
     const int cpg = C / G;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
@@ -274,8 +277,9 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_st
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float2* __restrict__ coef, int HW, int C, int G, int V, int ppb,
-                                    int pix_per_chunk, int silu, float inv_m) {
-    const int img = blockIdx.y, chunk = blockIdx.x;
+                                    int pix_per_chunk, int silu, float inv_m, int reverse) {
+    const int img = reverse ? static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y) : static_cast<int>(blockIdx.y);
+    const int chunk = reverse ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
     const int cpg = C / G;
     const int v = threadIdx.x % V, pl = threadIdx.x / V;
     if (pl >= ppb) return;
@@ -763,7 +767,8 @@ __global__ void __launch_bounds__(LN2_MAXW * 32) ln_bwd_v2_kernel(const bf16* __
 using namespace nk;
 
 // Kernel forms of this file that were written after the last GPU run: bit 0 = LayerNorm forward / backward as column-owner
-// blocks (ln_*_v2_kernel).  0 (the default, or NK_NORM_VARIANT) = the forms measured in DESIGN.md section 2.3;
+// blocks (ln_*_v2_kernel); bit 1 = the GroupNorm apply passes walk the (image, chunk) grid backwards (L2 reuse of what the
+// statistics pass read last; bit-identical results).  0 (the default, or NK_NORM_VARIANT) = the forms measured in DESIGN.md section 2.3;
 // neurosis_b200.tune sets bits only after comparing both forms on the device.
 static int g_norm_variant = -1;
 static int norm_variant() {
@@ -807,7 +812,7 @@ int nk_groupnorm_fwd(const void* x, int64_t x_pix_stride, const float* gamma, co
                                                              1.f / (static_cast<float>(HW) * (C / G)), eps);
     gn_apply_kernel<<<dim3(p.chunks, nimg), p.threads, 2 * C * sizeof(float), st>>>(
         static_cast<const bf16*>(x), x_pix_stride, static_cast<bf16*>(y), y_pix_stride, gamma, beta, mean, rstd, HW,
-        C, G, p.V, p.ppb, p.pix_per_chunk, silu);
+        C, G, p.V, p.ppb, p.pix_per_chunk, silu, (norm_variant() >> 1) & 1);
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }
@@ -831,7 +836,7 @@ int nk_groupnorm_bwd(const void* dy, int64_t dy_pix_stride, const void* x, int64
     gn_bwd_apply_kernel<<<dim3(p.chunks, nimg), p.threads, 0, st>>>(
         static_cast<const bf16*>(dy), dy_pix_stride, static_cast<const bf16*>(x), x_pix_stride,
         static_cast<bf16*>(dx), dx_pix_stride, gamma, beta, mean, rstd, coef, HW, C, G, p.V, p.ppb, p.pix_per_chunk,
-        silu, 1.f / (static_cast<float>(HW) * (C / G)));
+        silu, 1.f / (static_cast<float>(HW) * (C / G)), (norm_variant() >> 1) & 1);
     NK_CUDA(cudaGetLastError());
     return NK_OK;
 }

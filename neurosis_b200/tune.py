@@ -1,6 +1,7 @@
 """Run-time selection of kernel variants, gated by an on-device comparison with the measured kernels.
 
-Three variants: the second form of the LayerNorm kernels (`probe_layernorm`, norm.cu, `nk_norm_set_variant`), an L2 prefetch of
+Four variants: the second form of the LayerNorm kernels (`probe_layernorm`, norm.cu, `nk_norm_set_variant` bit 0), GroupNorm's
+second passes walking their grid backwards for L2 reuse (`probe_groupnorm_reverse`, bit 1), an L2 prefetch of
 the GEMM epilogue's side input (`probe_epilogue_prefetch`, `nk_gemm_set_epi_prefetch`) and ROW-TILE PAIRING of the tensor-core GEMM / implicit-GEMM convolution kernel (`gemm_tc_kernel<.., DUAL>`,
 csrc/gemm_tc.cu): a CTA owns two 128-row tiles that share one B tile, which cuts the operand bytes per FLOP that cross
 the L2 -> SM fabric by 25 % — the measured bound of the kernel.  It changes WHICH CTA computes an output
@@ -362,6 +363,70 @@ def probe_epilogue_prefetch(device: int = 0, timed: bool = True) -> dict:
     return rep
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# GroupNorm: second passes walk their grid backwards (norm.cu, nk_norm_set_variant bit 1)
+# ---------------------------------------------------------------------------------------------------------------------
+GN_TIMED = [((16, 128, 128, 320), 14), ((16, 128, 128, 640), 4), ((16, 128, 128, 960), 2), ((16, 64, 64, 640), 12),
+            ((16, 64, 64, 1280), 6), ((16, 32, 32, 1280), 20)]   # NHWC shapes of the SDXL B=16 step, GroupNorm+SiLU calls per step
+GN_CHECKS = [(2, 24, 16, 64), (3, 12, 20, 320), (1, 144, 112, 320), (5, 8, 8, 1280), (2, 33, 7, 960)]
+
+
+def probe_groupnorm_reverse(device: int = 0, timed: bool = True) -> dict:
+    """every block does the same work on the same data, only the order in which blocks are dispatched changes: outputs
+    must be bit-identical (the parameter-gradient sums are formed by the unchanged first passes)."""
+    import torch
+
+    from . import ops
+    from ._lib import lib
+    torch.cuda.set_device(device)
+    dev = torch.device("cuda", device)
+    gen = torch.Generator(device=dev).manual_seed(99)
+    rep = {"variant": "groupnorm_reverse_apply", "checks": [], "timings": [], "ok": True}
+    prev = lib.nk_norm_set_variant(-1)
+
+    def case(n, h, w_, c):
+        x = (torch.randn(n, h, w_, c, generator=gen, device=dev) * 1.3 + 0.2).to(torch.bfloat16)
+        dy = (torch.randn(n, h, w_, c, generator=gen, device=dev) * 0.1).to(torch.bfloat16)
+        return x, dy, 1.0 + 0.2 * torch.randn(c, generator=gen, device=dev), 0.1 * torch.randn(c, generator=gen, device=dev)
+
+    def run(x, dy, gamma, beta, silu):
+        y, mean, rstd = ops.groupnorm_fwd(x, gamma, beta, 32, 1e-5, silu)
+        dx, dg, db = ops.groupnorm_bwd(dy, x, gamma, beta, mean, rstd, 32, silu)
+        return y, dx, dg, db
+
+    try:
+        for shape in GN_CHECKS + [s_ for s_, _ in GN_TIMED[:2]]:
+            for silu in (True, False):
+                x, dy, gamma, beta = case(*shape)
+                lib.nk_norm_set_variant(prev & ~2 & 0xff)
+                a = run(x, dy, gamma, beta, silu)
+                lib.nk_norm_set_variant((prev | 2) & 0xff)
+                b = run(x, dy, gamma, beta, silu)
+                torch.cuda.synchronize()
+                ok = bool(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]))
+                rep["checks"].append({"shape": list(shape), "silu": silu, "ok": ok})
+                rep["ok"] = rep["ok"] and ok
+        if timed and rep["ok"]:
+            t_old = t_new = 0.0
+            for shape, weight in GN_TIMED:
+                x, dy, gamma, beta = case(*shape)
+                _, mean, rstd = ops.groupnorm_fwd(x, gamma, beta, 32, 1e-5, True)
+                dg, db = torch.zeros(shape[3], device=dev), torch.zeros(shape[3], device=dev)
+                row = {"shape": list(shape), "calls_per_step": weight}
+                for name, mask in (("old", prev & ~2 & 0xff), ("new", (prev | 2) & 0xff)):
+                    lib.nk_norm_set_variant(mask)
+                    row[f"fwd_ms_{name}"] = _time(lambda: ops.groupnorm_fwd(x, gamma, beta, 32, 1e-5, True), 10)
+                    row[f"bwd_ms_{name}"] = _time(lambda: ops.groupnorm_bwd(dy, x, gamma, beta, mean, rstd, 32, True, out=(dg, db)), 10)
+                t_old += weight * (row["fwd_ms_old"] + row["bwd_ms_old"])
+                t_new += weight * (row["fwd_ms_new"] + row["bwd_ms_new"])
+                rep["timings"].append(row)
+            rep["step_ms_old"], rep["step_ms_new"] = t_old, t_new
+            rep["speedup"] = t_old / t_new if t_new > 0 else 0.0
+    finally:
+        lib.nk_norm_set_variant(prev)
+    return rep
+
+
 def _summary(rep: dict, max_timings: int = 6) -> dict:
     """what bench.py prints: verdict, weighted times, the failed checks and the largest movers."""
     out = {k: rep[k] for k in ("variant", "ok", "step_ms_unpaired", "step_ms_paired", "speedup", "error", "enabled", "mode",
@@ -376,6 +441,13 @@ def _summary(rep: dict, max_timings: int = 6) -> dict:
             out["layernorm_column_owner"]["failed_checks"] = badl[:4]
         if ln.get("timings"):
             out["layernorm_column_owner"]["timings"] = ln["timings"]
+    gn = rep.get("groupnorm_reverse_apply")
+    if gn is not None:
+        out["groupnorm_reverse_apply"] = {k: gn[k] for k in ("ok", "enabled", "speedup", "step_ms_old", "step_ms_new", "error", "source",
+                                                             "step_guard") if k in gn}
+        out["groupnorm_reverse_apply"]["checks_run"] = len(gn.get("checks", []))
+        if gn.get("timings"):
+            out["groupnorm_reverse_apply"]["timings"] = gn["timings"]
     pf = rep.get("epilogue_l2_prefetch")
     if pf is not None:
         out["epilogue_l2_prefetch"] = {k: pf[k] for k in ("ok", "enabled", "speedup", "step_ms_off", "step_ms_on", "error", "source",
@@ -409,6 +481,7 @@ def autotune(device: int = 0, timeout_s: float = 150.0, min_speedup: float = 1.0
                 "min_k_iters": int(os.environ.get("NK_GEMM_DUAL_MIN_K", "0") or 0),
                 "skew": int(os.environ.get("NK_GEMM_DUAL_SKEW", "0") or 0), "source": "NK_GEMM_DUAL (pinned, no probe)",
                 "layernorm_column_owner": {"enabled": bool(nv & 1), "source": "NK_NORM_VARIANT (pinned with NK_GEMM_DUAL, no probe)"},
+                "groupnorm_reverse_apply": {"enabled": bool(nv & 2), "source": "NK_NORM_VARIANT (pinned with NK_GEMM_DUAL, no probe)"},
                 "epilogue_l2_prefetch": {"enabled": os.environ.get("NK_GEMM_EPI_PREFETCH", "0") not in ("", "0"),
                                          "source": "NK_GEMM_EPI_PREFETCH (pinned with NK_GEMM_DUAL, no probe)"}}
     if os.environ.get("NK_B200_TUNE", "1") == "0":
@@ -438,6 +511,7 @@ def autotune(device: int = 0, timeout_s: float = 150.0, min_speedup: float = 1.0
                     pass
         ln_reps = [c for c in cands if c.get("variant") == "layernorm_column_owner"]
         pf_reps = [c for c in cands if c.get("variant") == "epilogue_l2_prefetch"]
+        gn_reps = [c for c in cands if c.get("variant") == "groupnorm_reverse_apply"]
         cands = [c for c in cands if c.get("variant") == "gemm_row_tile_pairing"]
         good = [c for c in cands if c.get("ok") and c.get("min_k_iters") is not None]
         if good:  # the fastest candidate that reproduced the unpaired kernels
@@ -451,6 +525,8 @@ def autotune(device: int = 0, timeout_s: float = 150.0, min_speedup: float = 1.0
             rep["layernorm_column_owner"] = ln_reps[-1]
         if pf_reps:
             rep["epilogue_l2_prefetch"] = pf_reps[-1]
+        if gn_reps:
+            rep["groupnorm_reverse_apply"] = gn_reps[-1]
         if len(cands) < len(SKEWS) or proc.returncode not in (0, 1):
             rep.setdefault("note", f"probe child ended early (exit {proc.returncode}) after {len(cands)} of {len(SKEWS)} candidates: "
                            + " | ".join((se or "").strip().splitlines()[-2:])[-300:])
@@ -470,7 +546,12 @@ def autotune(device: int = 0, timeout_s: float = 150.0, min_speedup: float = 1.0
         ln = rep["layernorm_column_owner"] = {"ok": False, "error": "no verdict from the probe child"}
     ln["enabled"] = bool(ln.get("ok")) and float(ln.get("speedup", 0.0)) >= 1.02
     ln["source"] = "on-device probe (child process)"
-    lib.nk_norm_set_variant(1 if ln["enabled"] else 0)
+    gn = rep.get("groupnorm_reverse_apply")
+    if gn is None:
+        gn = rep["groupnorm_reverse_apply"] = {"ok": False, "error": "no verdict from the probe child"}
+    gn["enabled"] = bool(gn.get("ok")) and float(gn.get("speedup", 0.0)) >= 1.01
+    gn["source"] = "on-device probe (child process)"
+    lib.nk_norm_set_variant((1 if ln["enabled"] else 0) | (2 if gn["enabled"] else 0))
     pf = rep.get("epilogue_l2_prefetch")
     if pf is None:
         pf = rep["epilogue_l2_prefetch"] = {"ok": False, "error": "no verdict from the probe child"}
@@ -506,7 +587,9 @@ def main(argv: Optional[list] = None) -> int:
                 print(json.dumps(ln), flush=True)
                 pf = probe_epilogue_prefetch(a.device, timed=not a.no_timing)
                 print(json.dumps(pf), flush=True)
-                ok = ok and ln["ok"] and pf["ok"]
+                gn = probe_groupnorm_reverse(a.device, timed=not a.no_timing)
+                print(json.dumps(gn), flush=True)
+                ok = ok and ln["ok"] and pf["ok"] and gn["ok"]
         return 0 if ok else 1
     print(json.dumps(_summary(autotune(a.device))), flush=True)
     return 0

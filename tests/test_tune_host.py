@@ -89,6 +89,13 @@ def test_verdict_rules(monkeypatch):
     reps[1] = {**L, "ok": False, "speedup": 1.6}   # faster but wrong: stays off
     assert not tune.autotune()["layernorm_column_owner"]["enabled"] and lib.nk_norm_set_variant(-1) == 0
     reps[1] = {**L, "ok": True, "speedup": 1.4}
+    # GroupNorm reverse order: its bit is OR-ed into the norm mask
+    reps.append({"variant": "groupnorm_reverse_apply", "ok": True, "speedup": 1.04, "checks": [], "timings": []})
+    got = tune.autotune()
+    assert got["groupnorm_reverse_apply"]["enabled"] and lib.nk_norm_set_variant(-1) == 3
+    reps.pop()
+    got = tune.autotune()
+    assert not got["groupnorm_reverse_apply"]["enabled"] and lib.nk_norm_set_variant(-1) == 1
     # third variant: the epilogue prefetch hint
     assert not got["epilogue_l2_prefetch"]["enabled"] and "no verdict" in got["epilogue_l2_prefetch"]["error"]
     reps.insert(2, {"variant": "epilogue_l2_prefetch", "ok": True, "speedup": 1.06, "checks": [], "timings": []})

@@ -56,6 +56,17 @@ def test_layernorm_column_owner_form_agrees_with_the_measured_kernels_and_fp32()
     assert len(reps[0]["checks"]) >= 8
 
 
+@pytest.mark.xfail(strict=False, reason="GroupNorm second passes in reverse block order: first run on hardware")
+def test_groupnorm_reverse_apply_order_is_bit_identical():
+    """nk_norm_set_variant bit 1: gn_apply_kernel / gn_bwd_apply_kernel walk the (image, chunk) grid backwards; y and dx must be
+    bit-identical, with and without SiLU, on ragged / tiny / bucket-shaped images."""
+    reps = [r for r in _probe("--no-timing") if r["variant"] == "groupnorm_reverse_apply"]
+    assert len(reps) == 1
+    bad = [c for c in reps[0]["checks"] if not c["ok"]]
+    assert reps[0]["ok"] and not bad, bad[:4]
+    assert len(reps[0]["checks"]) >= 14
+
+
 @pytest.mark.xfail(strict=False, reason="L2 prefetch of the GEMM epilogue's side input: first run on hardware")
 def test_epilogue_side_input_prefetch_does_not_change_results():
     """`cp.async.bulk.prefetch.tensor.L2` of the residual / GEGLU-h boxes at tile start (nk_gemm_set_epi_prefetch): the GEGLU
@@ -81,7 +92,7 @@ def test_autotune_verdict_is_consistent_and_leaves_a_working_library():
         assert rep["enabled"] == (bool(rep.get("ok")) and rep.get("min_k_iters") is not None and rep.get("speedup", 0) >= 1.01)
         assert lib.nk_gemm_set_dual_skew(-1) == (rep.get("skew", 0) if rep["enabled"] else 0)
         ln = rep["layernorm_column_owner"]
-        assert lib.nk_norm_set_variant(-1) == (1 if ln["enabled"] else 0)
+        assert lib.nk_norm_set_variant(-1) == (1 if ln["enabled"] else 0) | (2 if rep["groupnorm_reverse_apply"]["enabled"] else 0)
         assert ln["enabled"] == (bool(ln.get("ok")) and ln.get("speedup", 0) >= 1.02)
         gam, bet = torch.ones(1280, device="cuda"), torch.zeros(1280, device="cuda")
         yn, _, _ = ops.layernorm_fwd(x, gam, bet, 1e-5)
