@@ -470,7 +470,7 @@ def _summary(rep: dict, max_timings: int = 6) -> dict:
     return out
 
 
-def autotune(device: int = 0, timeout_s: float = 150.0, min_speedup: float = 1.01) -> dict:
+def autotune(device: int = 0, timeout_s: float = 240.0, min_speedup: float = 1.01) -> dict:
     """probe in a child process, then set the library mode of THIS process.  Never raises: any failure leaves the
     library at its default (unpaired) and is reported in the returned dict."""
     from ._lib import lib
