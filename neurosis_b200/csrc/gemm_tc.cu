@@ -553,6 +553,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 if constexpr (VAR == VAR_GEGLU_BWD) {
                     const int ngp = g.BN / 64;
                     const int pb = half ? (ngp + 1) / 2 : 0, pe = half ? ngp : (ngp + 1) / 2;
+#pragma unroll 1
                     for (int gi = pb; gi < pe; ++gi) {
                         const int col = n0 + gi * 64;
                         if (col < g.geglu_d) {
@@ -563,6 +564,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 } else if constexpr (VAR == VAR_MAIN) {
                     const int ngp = (g.BN + 63) / 64;
                     const int pb = half ? (ngp + 1) / 2 : 0, pe = half ? ngp : (ngp + 1) / 2;
+#pragma unroll 1
                     for (int gi = pb; gi < pe; ++gi) {
                         const int col = n0 + gi * 64;
                         if (col < g.N) tma_prefetch_l2_4d(&g.tmC2, col, sc1, sc2, sc3);
