@@ -22,6 +22,11 @@ _CACHE = {}
 def _probe(*extra):
     if extra in _CACHE:
         return _CACHE[extra]
+    import gc
+
+    import torch
+    gc.collect()
+    torch.cuda.empty_cache()  # the child allocates on the same GPU: give back what earlier tests left in the caching allocator
     r = subprocess.run([sys.executable, "-m", "neurosis_b200.tune", "--probe", *extra], cwd=str(ROOT), capture_output=True,
                        text=True, timeout=360)
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
@@ -86,6 +91,7 @@ def test_autotune_verdict_is_consistent_and_leaves_a_working_library():
 
     from neurosis_b200 import ops, tune
     from neurosis_b200._lib import lib
+    torch.cuda.empty_cache()
     rep = tune.autotune(0, timeout_s=300)
     try:
         assert lib.nk_gemm_set_dual(-1) == (1 if rep["enabled"] else 0)
