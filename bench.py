@@ -24,6 +24,15 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+T_START = time.monotonic()
+# wall-clock target of one default invocation ("finishes within minutes"): the optional parts (step guard of the tuned kernel
+# variants, secondary configurations) only get what the mandatory parts leave of it
+WALL_TARGET_S = float(os.environ.get("NK_BENCH_WALL_S", "285"))
+
+
+def wall_left() -> float:
+    return WALL_TARGET_S - (time.monotonic() - T_START)
+
 
 SDXL_UNET = dict(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=[4, 2],
                  channel_mult=[1, 2, 4], num_head_channels=64, transformer_depth=[1, 2, 10], context_dim=2048,
@@ -297,7 +306,7 @@ def _autotune_unsafe(world: int, local: int, dev) -> dict:
     import torch.distributed as dist
     from neurosis_b200 import tune
     from neurosis_b200._lib import lib
-    rep = tune.autotune(local)
+    rep = tune.autotune(local, timeout_s=min(240.0, max(60.0, wall_left() - 150.0)))
     ln = rep.setdefault("layernorm_column_owner", {"enabled": False})
     pf = rep.setdefault("epilogue_l2_prefetch", {"enabled": False})
     gn = rep.setdefault("groupnorm_reverse_apply", {"enabled": False})
@@ -385,7 +394,11 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
     pf = tuned.setdefault("epilogue_l2_prefetch", {"enabled": False})
     gn = tuned.setdefault("groupnorm_reverse_apply", {"enabled": False})
     try:
-        if tuned.get("enabled") or ln.get("enabled") or pf.get("enabled") or gn.get("enabled"):
+        if os.environ.get("NK_BENCH_NO_STEP_GUARD"):
+            # child of `run_other_configs`: the variants were guarded on the headline configuration by the parent, and a
+            # child that fails with them is retried on the measured kernels — no nested guard process here
+            tuned["note"] = "variants inherited from the parent run (guarded there); failure => retried without them"
+        elif tuned.get("enabled") or ln.get("enabled") or pf.get("enabled") or gn.get("enabled"):
             env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")
                    and k not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "MASTER_PORT", "MASTER_ADDR")}
             env.update({"LOCAL_RANK": str(local), "NK_BENCH_EXTRAS": "0", "NK_B200_TUNE": "0"})
@@ -396,7 +409,8 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
                 proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                                         start_new_session=True, cwd=str(ROOT))
                 try:
-                    so, se = proc.communicate(timeout=float(os.environ.get("NK_BENCH_GUARD_S", "240")))
+                    so, se = proc.communicate(timeout=min(float(os.environ.get("NK_BENCH_GUARD_S", "240")),
+                                                          max(45.0, wall_left() - 110.0)))
                 except subprocess.TimeoutExpired:
                     try:
                         os.killpg(proc.pid, signal.SIGKILL)
@@ -803,6 +817,7 @@ def run_other_configs(args, world: int, rank: int, budget_s: float, per_config_s
         # the port depends on (configuration, attempt) only, never on what happened to earlier children of THIS rank
         env["MASTER_PORT"] = str(20000 + (base_port + 1013 * (OTHER_CONFIGS.index(name) + 1) + (517 if plain else 0)) % 20000)
         env["NK_BENCH_EXTRAS"] = "0"
+        env["NK_BENCH_NO_STEP_GUARD"] = "1"
         if plain:  # second attempt of a configuration that failed with the tuned kernel variants: the measured kernels only
             env.update({"NK_GEMM_DUAL": "0", "NK_GEMM_DUAL_MIN_K": "0", "NK_GEMM_DUAL_SKEW": "0", "NK_NORM_VARIANT": "0"})
         cmd = _child_cmd(name, args, world)
@@ -1169,7 +1184,7 @@ def main() -> None:
         print(f"[bench] tear-down: {e!r}", file=sys.stderr)
         extras = False
     if extras:
-        budget = float(os.environ.get("NK_BENCH_EXTRAS_BUDGET_S", "330"))
+        budget = min(float(os.environ.get("NK_BENCH_EXTRAS_BUDGET_S", "330")), wall_left() - 10.0)
 
         def give_up() -> None:  # a child that cannot be reaped must not cost the headline line
             if line is not None:
@@ -1178,7 +1193,7 @@ def main() -> None:
             sys.stdout.flush()
             os._exit(0)
 
-        dog = threading.Timer(budget + 45.0, give_up)
+        dog = threading.Timer(max(budget, 0.0) + 45.0, give_up)
         dog.daemon = True
         dog.start()
         try:
