@@ -380,8 +380,9 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
     cover takes the child down, never the process that measures; a variant whose step disagrees is dropped.
       stage 0, epilogue L2 prefetch: a hint, the step must be unchanged (same tolerances as stage 1);
       stage 1, GEMM row-tile pairing: the forward GEMMs are bit-identical, so the losses agree to the run-to-run noise of
-        the atomic loss reduction (1e-5); the gradients differ by the fp32 accumulation order of split-K weight gradients
-        only (abs-sum within 2e-3);
+        the measured kernels themselves (atomics in the GroupNorm statistics and the loss reduction: 5e-4, or 10 x the
+        difference of two baseline steps); the gradients differ by the fp32 accumulation order of split-K weight
+        gradients only (abs-sum within 5e-3);
       stage 1b, GroupNorm second passes backwards: only the block dispatch order changes, same tolerances as stage 1;
       stage 2, LayerNorm second form on top: same formulas in another reduction order, outputs agree to bf16 rounding (loss
         within 2e-3, gradient abs-sum within 1e-2).
@@ -517,11 +518,17 @@ def run_guard_child(args) -> None:
     base = step(0, 0)
     again = step(0, 0)  # run-to-run noise of the measured kernels themselves, reported next to the comparisons
     out["baseline_repeat"] = {"loss": [base[0], again[0]], "grad_abs_sum": [base[1], again[1]]}
+    # "unchanged" = within the run-to-run noise of the measured kernels themselves: GroupNorm statistics and the loss
+    # reduction accumulate with shared-memory / global atomics, whose order moves the last fp32 bit and with it a few bf16
+    # roundings downstream.  Tolerance: 5e-4 (loss) / 5e-3 (gradient abs-sum), or 10 x the observed repeat difference.
+    tl = max(5e-4, 10.0 * abs(again[0] - base[0]) / max(abs(base[0]), 1e-30))
+    tg = max(5e-3, 10.0 * abs(again[1] - base[1]) / max(abs(base[1]), 1e-30))
+    out["tolerance"] = {"loss": tl, "grad_abs_sum": tg}
     ref = base
     if pfon:
         lib.nk_gemm_set_epi_prefetch(1)
         gotp = step(0, 0)
-        okp = agree(base, gotp, 1e-5, 2e-3)
+        okp = agree(base, gotp, tl, tg)
         out["prefetch"] = {"loss_off": base[0], "loss_on": gotp[0], "grad_abs_sum_off": base[1], "grad_abs_sum_on": gotp[1],
                            "equal": okp}
         print(json.dumps(out), flush=True)
@@ -531,7 +538,7 @@ def run_guard_child(args) -> None:
             lib.nk_gemm_set_epi_prefetch(0)
     if gmode:
         got = step(gmode, 0)
-        ok = agree(ref, got, 1e-5, 2e-3)
+        ok = agree(ref, got, tl, tg)
         out["gemm"] = {"loss_unpaired": ref[0], "loss_paired": got[0], "grad_abs_sum_unpaired": ref[1],
                        "grad_abs_sum_paired": got[1], "equal": ok}
         print(json.dumps(out), flush=True)  # (a later stage that traps must not take this verdict with it)
@@ -542,7 +549,7 @@ def run_guard_child(args) -> None:
     keep = 0
     if nmask & 2:  # GroupNorm second passes backwards: same blocks, other dispatch order — the step must be unchanged
         got3 = step(gmode, 2)
-        ok3 = agree(ref, got3, 1e-5, 2e-3)
+        ok3 = agree(ref, got3, tl, tg)
         out["groupnorm"] = {"loss_old": ref[0], "loss_new": got3[0], "grad_abs_sum_old": ref[1], "grad_abs_sum_new": got3[1],
                             "equal": ok3}
         print(json.dumps(out), flush=True)
@@ -551,7 +558,7 @@ def run_guard_child(args) -> None:
     if nmask & 1:
         got2 = step(gmode, keep | 1)
         out["layernorm"] = {"loss_old": ref[0], "loss_new": got2[0], "grad_abs_sum_old": ref[1], "grad_abs_sum_new": got2[1],
-                            "agree": agree(ref, got2, 2e-3, 1e-2)}
+                            "agree": agree(ref, got2, max(tl, 2e-3), max(tg, 1e-2))}
     print(json.dumps(out), flush=True)
 
 
