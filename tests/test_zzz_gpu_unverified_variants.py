@@ -62,9 +62,9 @@ def test_layernorm_column_owner_form_agrees_with_the_measured_kernels_and_fp32()
 
 
 @pytest.mark.xfail(strict=False, reason="GroupNorm second passes in reverse block order: first run on hardware")
-def test_groupnorm_reverse_apply_order_is_bit_identical():
+def test_groupnorm_reverse_apply_order_changes_nothing_beyond_atomic_noise():
     """nk_norm_set_variant bit 1: gn_apply_kernel / gn_bwd_apply_kernel walk the (image, chunk) grid backwards; y and dx must be
-    bit-identical, with and without SiLU, on ragged / tiny / bucket-shaped images."""
+    equal up to the run-to-run noise of the statistics atomics, with and without SiLU, on ragged / tiny / bucket-shaped images."""
     reps = [r for r in _probe("--no-timing") if r["variant"] == "groupnorm_reverse_apply"]
     assert len(reps) == 1
     bad = [c for c in reps[0]["checks"] if not c["ok"]]
