@@ -373,6 +373,30 @@ def _apply_tuned(tuned: dict) -> None:
     _export_tuned(tuned)
 
 
+def _run_guard_child(cmd: list, env: dict):
+    """(last JSON line of the child or None, error text or None); the child is killed with its process group at its limit."""
+    import signal
+    res, err = None, None
+    proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True,
+                            cwd=str(ROOT))
+    try:
+        so, se = proc.communicate(timeout=min(float(os.environ.get("NK_BENCH_GUARD_S", "240")), max(45.0, wall_left() - 110.0)))
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(proc.pid, signal.SIGKILL)
+        except Exception:  # noqa: BLE001
+            proc.kill()
+        so, se = proc.communicate()
+        err = "guard child exceeded its time limit"
+    for ln_ in reversed((so or "").strip().splitlines()):
+        if ln_.startswith("{"):
+            res = json.loads(ln_)
+            break
+    if err is None and (res is None or proc.returncode != 0):
+        err = f"guard child exit {proc.returncode}: " + " | ".join((se or "").strip().splitlines()[-3:])[-300:]
+    return res, err
+
+
 def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
     """Step-level guard of the variants the op-level probe accepted, on the real model and batch of this configuration,
     in a CHILD process (`bench.py --guard-child`, single GPU, no process group): the same training step (same sigma /
@@ -406,25 +430,20 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
             cmd = [sys.executable, str(ROOT / "bench.py"), "--guard-child", "--config", args.config, "--batch", str(args.batch)]
             res, err = None, None
             t0 = time.monotonic()
+            from neurosis_b200 import tune as _tune
+            # a verdict for exactly these variants, configuration and batch on this machine and library build is reused
+            # (the driver starts the benchmark several times per box: 1 / 2 / 4 / 8 GPUs)
+            gtag = "guard:" + ":".join([args.config, str(args.batch)] + [os.environ.get(k, "0") for k in (
+                "NK_GEMM_DUAL", "NK_GEMM_DUAL_MIN_K", "NK_GEMM_DUAL_SKEW", "NK_NORM_VARIANT", "NK_GEMM_EPI_PREFETCH")])
+            cached = _tune.cache_load(gtag, local)
+            if cached is not None:
+                res = cached
+                res["source"] = f"cached ({cached.pop('_cache', '')})"
             try:
-                proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
-                                        start_new_session=True, cwd=str(ROOT))
-                try:
-                    so, se = proc.communicate(timeout=min(float(os.environ.get("NK_BENCH_GUARD_S", "240")),
-                                                          max(45.0, wall_left() - 110.0)))
-                except subprocess.TimeoutExpired:
-                    try:
-                        os.killpg(proc.pid, signal.SIGKILL)
-                    except Exception:  # noqa: BLE001
-                        proc.kill()
-                    so, se = proc.communicate()
-                    err = "guard child exceeded its time limit"
-                for ln_ in reversed((so or "").strip().splitlines()):
-                    if ln_.startswith("{"):
-                        res = json.loads(ln_)
-                        break
-                if res is None and err is None:
-                    err = f"guard child exit {proc.returncode}: " + " | ".join((se or "").strip().splitlines()[-3:])[-300:]
+                if res is None:
+                    res, err = _run_guard_child(cmd, env)
+                    if res is not None and err is None:
+                        _tune.cache_store(gtag, res, local)
             except Exception as e:  # noqa: BLE001
                 err = repr(e)
             wall = round(time.monotonic() - t0, 1)

@@ -112,6 +112,7 @@ def test_configuration_that_fails_with_tuned_variants_is_retried_on_the_measured
 
 
 def test_step_guard_keeps_or_drops_variants_and_sets_the_library(monkeypatch):
+    monkeypatch.setenv("NK_B200_TUNE_CACHE", "0")
     """parent side of the child-process step guard: verdicts of the child -> `tuned`, library modes and the exported
     environment; a child that dies (no verdict) drops every variant."""
     from neurosis_b200._lib import lib

@@ -9,6 +9,12 @@ from neurosis_b200 import tune
 from neurosis_b200._lib import lib
 
 
+@pytest.fixture(autouse=True)
+def _no_verdict_cache(monkeypatch):
+    """the verdict cache (tune.cache_*) is exercised by its own test; everywhere else every call must probe."""
+    monkeypatch.setenv("NK_B200_TUNE_CACHE", "0")
+
+
 def test_mode_switch_roundtrip_through_the_c_abi():
     start = lib.nk_gemm_set_dual(-1)  # out of range: query only
     try:
@@ -134,3 +140,47 @@ def test_depth_threshold_selection():
     assert lib.nk_gemm_set_dual_min_k(-1) >= 0
     prev = lib.nk_gemm_set_dual_min_k(20)
     assert lib.nk_gemm_set_dual_min_k(prev) == 20
+
+
+def test_verdict_cache_is_keyed_and_reused(monkeypatch, tmp_path):
+    """a complete probe verdict is remembered per (library build, GPU model): the next autotune() on the same machine
+    applies it without starting a child; an incomplete probe (a candidate took the child down) is not remembered."""
+    import subprocess
+    import tempfile
+    monkeypatch.setenv("NK_B200_TUNE_CACHE", "1")
+    monkeypatch.setattr(tempfile, "gettempdir", lambda: str(tmp_path))
+    monkeypatch.delenv("NK_GEMM_DUAL", raising=False)
+    monkeypatch.delenv("NK_B200_TUNE", raising=False)
+    V = {"variant": "gemm_row_tile_pairing", "checks": [], "timings": []}
+    reps = [{**V, "ok": True, "skew": 0, "speedup": 1.07, "min_k_iters": 20}, {**V, "ok": True, "skew": 3, "speedup": 1.03, "min_k_iters": 20},
+            {"variant": "layernorm_column_owner", "ok": True, "speedup": 1.5, "checks": [], "timings": []}]
+
+    class Proc:
+        def __init__(self, rows, rc=0):
+            self.rows, self.returncode, self.pid = rows, rc, 0
+
+        def communicate(self, timeout=None):
+            return "\n".join(json.dumps(r) for r in self.rows) + "\n", ""
+
+    calls = []
+    monkeypatch.setattr(subprocess, "Popen", lambda *a, **k: (calls.append(1), Proc(reps))[1])
+    first = tune.autotune()
+    assert first["enabled"] and first["skew"] == 0 and len(calls) == 1 and "child process" in first["source"]
+    assert len(list(tmp_path.glob("nk_b200_tune_*.json"))) == 1
+    lib.nk_gemm_set_dual(0)
+    lib.nk_norm_set_variant(0)
+    second = tune.autotune()
+    assert len(calls) == 1 and "cached" in second["source"] and second["enabled"] and second["min_k_iters"] == 20
+    assert lib.nk_gemm_set_dual(-1) == 1 and lib.nk_norm_set_variant(-1) == 1 and second["layernorm_column_owner"]["enabled"]
+    assert tune.cache_path("probe") != tune.cache_path("guard:sdxl:16")
+    # an incomplete probe is not stored
+    for f in tmp_path.glob("nk_b200_tune_*.json"):
+        f.unlink()
+    monkeypatch.setattr(subprocess, "Popen", lambda *a, **k: (calls.append(1), Proc(reps[:1], rc=-6))[1])
+    tune.autotune()
+    assert not list(tmp_path.glob("nk_b200_tune_*.json"))
+    lib.nk_gemm_set_dual(0)
+    lib.nk_gemm_set_dual_min_k(0)
+    lib.nk_gemm_set_dual_skew(0)
+    lib.nk_norm_set_variant(0)
+    lib.nk_gemm_set_epi_prefetch(0)
