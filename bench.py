@@ -1020,6 +1020,19 @@ def main() -> None:
     for _ in range(2):
         eager_step(resident, False)
     torch.cuda.synchronize()
+    timeline = None
+    if world > 1 and hasattr(reducer, "start_timeline") and not (args.ncu_step or args.ncu_sample):
+        # one more eager step with CUDA events around every bucket all-reduce: where communication sits relative to
+        # backward on this rank, and how much of it the compute stream has to wait for (diagnostics; never fatal)
+        try:
+            reducer.start_timeline()
+            eager_step(resident, False)
+            timeline = reducer.end_timeline()
+            if timeline and len(timeline["buckets"]) > 12:  # keep the line readable: first / last buckets only
+                timeline["buckets"] = timeline["buckets"][:6] + [{"...": len(timeline["buckets"]) - 12}] + timeline["buckets"][-6:]
+        except Exception as e:  # noqa: BLE001
+            timeline = {"error": repr(e)}
+            reducer._timeline = None
     if args.ncu_step:  # under `ncu --profile-from-start off`: exactly one eager step inside the profiler range
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -1174,6 +1187,7 @@ def main() -> None:
                            "parallelism": f"dp{world}", "l2": "working set (5 GB bf16 weights + activations) >> 126 MB L2",
                            "step_tflop_algorithmic": gflop_img * B / 1e3,
                            "stock_torch_img_s": STOCK_TORCH.get(args.config), "tuned_variants": tuned,
+                           "allreduce_timeline_rank0_eager_step": timeline,
                            "mfu_vs_sustained_peak": ips / world * gflop_img * 1e9 / (pk["tflops"] * 1e12),
                            "mfu_vs_burst_peak": ips / world * gflop_img * 1e9 / (burst * 1e12)},
                 "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},

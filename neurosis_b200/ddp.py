@@ -46,6 +46,7 @@ class BucketedGradReducer:
                 self._index[p] = bi
         self.enabled = True
         self._works: list = []
+        self._timeline = None  # start_timeline(): CUDA events per bucket all-reduce of ONE step (diagnostics, off by default)
         # Two sources report a gradient as complete: autograd's post-accumulate hook (gradients that autograd itself
         # accumulates) and `mark_ready` (kernels of neurosis_b200.ops that wrote straight into the bucket storage).
         # torch fires the post-accumulate hook for EVERY parameter an autograd Function was asked a gradient for, even
@@ -126,12 +127,43 @@ class BucketedGradReducer:
         if b["pending"] == 0:
             self._launch(b)
 
+    # -- diagnostics: where do the bucket all-reduces sit relative to backward? ------------------------------------
+    def start_timeline(self) -> None:
+        """record CUDA events around every bucket all-reduce of the NEXT step (call before zero_grad / backward)."""
+        if self._cuda:
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            self._timeline = {"t0": t0, "buckets": [], "backward_done": None}
+
+    def end_timeline(self) -> Optional[dict]:
+        """after finish(): milliseconds relative to start_timeline().  `exposed_ms` = time the compute stream had to wait for
+        communication after its own last kernel (end of the last all-reduce minus end of backward, floored at 0)."""
+        tl, self._timeline = self._timeline, None
+        if not tl or tl["backward_done"] is None:
+            return None
+        torch.cuda.synchronize()
+        t0 = tl["t0"]
+        rows = [{"bucket": i, "mbytes": round(n * 4 / 2 ** 20, 1), "start_ms": round(t0.elapsed_time(a), 3),
+                 "end_ms": round(t0.elapsed_time(b), 3)} for i, n, a, b in tl["buckets"]]
+        bwd = t0.elapsed_time(tl["backward_done"])
+        last = max((r["end_ms"] for r in rows), default=bwd)
+        busy = sum(r["end_ms"] - r["start_ms"] for r in rows)
+        return {"backward_done_ms": round(bwd, 3), "last_allreduce_end_ms": round(last, 3),
+                "exposed_ms": round(max(0.0, last - bwd), 3), "allreduce_busy_ms": round(busy, 3), "buckets": rows}
+
     def _launch(self, b: dict) -> None:
         flat = b["flat"]
         if self._cuda:
             ev = torch.cuda.current_stream().record_event()
             with torch.cuda.stream(self._stream):
                 self._stream.wait_event(ev)
+                if self._timeline is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(self._stream)
+                    dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+                    e1.record(self._stream)
+                    self._timeline["buckets"].append((self.buckets.index(b), flat.numel(), e0, e1))
+                    return
                 dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
         else:
             w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -151,6 +183,10 @@ class BucketedGradReducer:
                 self._launch(b)
                 b["pending"] = 0
         if self._cuda:
+            if self._timeline is not None:  # end of this rank's own backward work, before it waits for communication
+                done = torch.cuda.Event(enable_timing=True)
+                done.record()
+                self._timeline["backward_done"] = done
             torch.cuda.current_stream().wait_stream(self._stream)
         else:
             for w, flat in self._works:
