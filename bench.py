@@ -1153,8 +1153,8 @@ def main() -> None:
         t_ms, fl, nrec = prof_raw
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
         traffic, traffic_src = None, None
-        tfiles = sorted((ROOT / "profiles").glob("*gemm_traffic*.json"))
-        if tfiles:  # committed summary of the ncu DRAM-byte sample of this kernel (tools/ncu_gemm_traffic.py)
+        tfiles = sorted((ROOT / "profiles").glob("*gemm_traffic*.json")) if (args.config == "sdxl" and B == 16) else []
+        if tfiles:  # committed summary of the ncu DRAM-byte sample of this kernel at THIS workload (tools/ncu_gemm_traffic.py)
             td = json.loads(tfiles[-1].read_text())
             traffic, traffic_src = td.get("dram_bytes_per_launch"), f"profiles/{tfiles[-1].name}: {td.get('source')}"
         roof = {"kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "bound": "tensor", "achieved": ach,
