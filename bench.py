@@ -469,6 +469,10 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
                 if not bool(res and (res.get("prefetch") or {}).get("equal")):
                     pf["enabled"] = False
                     pf["error"] = "rejected by the step-level guard"
+    except Exception as e:  # noqa: BLE001  (a local failure must not make this rank skip the collective below)
+        tuned["enabled"], tuned["mode"], ln["enabled"], pf["enabled"], gn["enabled"] = False, 0, False, False, False
+        tuned["note"] = f"step guard failed: {e!r}"
+    try:
         if world > 1:
             flag = torch.tensor([1 if tuned.get("enabled") else 0, 1 if ln.get("enabled") else 0, 1 if pf.get("enabled") else 0,
                                  1 if gn.get("enabled") else 0], device=dev)
