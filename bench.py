@@ -1030,7 +1030,10 @@ def main() -> None:
         # backward on this rank, and how much of it the compute stream has to wait for (diagnostics; never fatal)
         try:
             reducer.start_timeline()
-            eager_step(resident, False)
+        except Exception:  # noqa: BLE001
+            reducer._timeline = None
+        eager_step(resident, False)  # (outside the try: every rank must run the same collectives)
+        try:
             timeline = reducer.end_timeline()
             if timeline and len(timeline["buckets"]) > 12:  # keep the line readable: first / last buckets only
                 timeline["buckets"] = timeline["buckets"][:6] + [{"...": len(timeline["buckets"]) - 12}] + timeline["buckets"][-6:]
