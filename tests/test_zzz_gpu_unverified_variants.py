@@ -173,3 +173,86 @@ def test_error_vs_fp32_oracle_is_at_the_level_of_the_reference_under_autocast(ta
     print(f"[error budget {tag}] (output, median grad, worst grad) rel L2 vs fp32 oracle: ours {ours}  reference under autocast {theirs}")
     for o, t, floor in zip(ours, theirs, (5e-3, 1e-2, 3e-2)):
         assert o <= 4.0 * t + floor, (ours, theirs)
+
+
+# ---------------------------------------------------------------- tag-frequency weights through the fused reduction
+@pytest.mark.xfail(strict=False, reason="numeric check of the hook path written after the GPU budget ended: first run on hardware")
+def test_tag_frequency_weights_enter_the_loss_reduction_numerically():
+    """VERDICT r1 'weak' item 4: the engine test with a TagFrequencyHook only checked finiteness.  Here the hooked
+    training_step (pre_hook -> batch -> weight vector of nk_weighted_mse_fwd) must equal mean(per-sample loss without
+    the hook x the hook's multipliers) on the same sigma / noise / posterior draws, with multipliers that differ per
+    sample, and the gradients must scale accordingly (checked through the gradient of the mean)."""
+    import random
+
+    import torch
+
+    from common import TINY_SDXL, TINY_VAE
+    from neurosis_b200.engine import DiffusionEngine
+    from neurosis_b200.modules import UNetModel
+    from neurosis_b200.modules.conditioner import GeneralConditioner, IdentityEncoder
+    from neurosis_b200.modules.denoiser import DiscreteDenoiser, EpsPreconditioning, EpsWeighting
+    from neurosis_b200.modules.loss import StandardDiffusionLoss, TagFreqScale, TagFrequencyHook, TagRewards
+    from neurosis_b200.modules.schedule import DiscreteSigmaGenerator, LegacyDDPMDiscretization
+    from neurosis_b200.modules.vae import Encoder
+    from oracle.unet import unet_param_shapes
+    from oracle.vae import vae_param_shapes
+    from oracle.weights import synth_state_dict, synth_tensor
+
+    cfg = TINY_SDXL
+    unet = UNetModel(**cfg)
+    unet.load_state_dict(synth_state_dict(unet_param_shapes(cfg), seed=1))
+    enc = Encoder(**TINY_VAE, embed_dim=4, standalone=True)
+    enc.load_state_dict(synth_state_dict(vae_param_shapes(TINY_VAE, embed_dim=4, standalone=True), seed=2))
+
+    class RandIdx(DiscreteSigmaGenerator):
+        def __call__(self, n, t=None):
+            return super().__call__(n, None).clamp_min(0.03)
+
+    def hook():
+        return TagFrequencyHook(alpha=0.5, beta=0.99, strength=1.0, freq_scale=TagFreqScale([[-1, 1.4], [1.5, 0.6]]),
+                                tag_rewards=TagRewards(solo=2.0, sky=0.5))
+
+    def engine(hooks):
+        return DiffusionEngine(unet, DiscreteDenoiser(EpsPreconditioning(), 1000, LegacyDDPMDiscretization()), enc,
+                               GeneralConditioner([IdentityEncoder(input_key="ctx"), IdentityEncoder(input_key="vec")]),
+                               StandardDiffusionLoss(RandIdx(LegacyDDPMDiscretization(), 1000), EpsWeighting()),
+                               scale_factor=0.13025, forward_hooks=hooks).to("cuda")
+
+    captions = ["1girl solo solo", "landscape scenery sky", "solo sky"]
+    batch = {"image": synth_tensor("vae.img3", (3, 3, 128, 128), uniform=True).cuda(),
+             "ctx": synth_tensor("sdxl.ctx3", (3, 77, cfg["context_dim"])).cuda(),
+             "vec": synth_tensor("sdxl.y3", (3, cfg["adm_in_channels"])).cuda(), "caption": captions}
+    w = torch.tensor(hook().sample_weights(list(captions)), dtype=torch.float32)
+    assert float(w.max() - w.min()) > 0.1, w  # the multipliers really differ per sample
+
+    def seeded():
+        random.seed(7)
+        torch.manual_seed(7)
+        torch.cuda.manual_seed(7)
+
+    plain = engine([])
+    seeded()
+    with torch.no_grad():
+        x = plain.encode_first_stage(batch["image"])
+    per_sample, _ = plain(x, dict(batch))
+    expected = (per_sample.detach().float().cpu() * w).mean()
+
+    hooked = engine([hook()])
+    for p in unet.parameters():
+        p.grad = None
+    seeded()
+    loss = hooked.training_step(dict(batch))
+    assert abs(float(loss) - float(expected)) <= 2e-5 * abs(float(expected)), (float(loss), float(expected))
+    assert abs(float(hooked.last_loss_dict["TagFrequencyHook/scale_mean"]) - float(w.mean())) < 1e-6
+    loss.backward()
+    g_hooked = torch.cat([p.grad.flatten().float() for p in unet.parameters()]).cpu()
+    # reference gradient: the same weighted mean formed with autograd from the un-hooked per-sample losses
+    for p in unet.parameters():
+        p.grad = None
+    seeded()
+    with torch.no_grad():
+        x = plain.encode_first_stage(batch["image"])
+    per_sample, _ = plain(x, dict(batch))
+    (per_sample * w.to(per_sample)).mean().backward()
+    g_ref = torch.cat([p.grad.flatten().float() for p in unet.parameters()]).cpu()
+    assert float((g_hooked - g_ref).norm() / g_ref.norm()) < 2e-2  # two runs of the bf16 backward (atomic accumulation order)
