@@ -1058,7 +1058,7 @@ def main() -> None:
         return
     # per-kernel roofline of the dominant kernel (gemm_tc_kernel): CUDA events around every launch of one extra step
     pk = peaks()
-    prof_raw = None
+    prof_raw = prof_raw_off = None
     overlap = ops.WGRAD_OVERLAP
     ops.WGRAD_OVERLAP = False  # per-kernel timings below need kernels that run alone (no side-stream weight gradients)
     if not args.no_profile:
@@ -1101,6 +1101,18 @@ def main() -> None:
                     fh.write(f"{ms:9.3f} ms  {n:5d}x  {f / ms / 1e9 if ms > 0 else 0:8.1f} TFLOP/s  {what} {dims}\n")
         prof_raw = (t_ms, fl, len(recs))
         del recs
+        if (tuned.get("enabled") or any((tuned.get(k) or {}).get("enabled") for k in (
+                "layernorm_column_owner", "groupnorm_reverse_apply", "epilogue_l2_prefetch"))) and not args.breakdown:
+            # the same per-launch timing with every tuned variant off: the roofline reported below is the one of the
+            # kernels the headline is finally measured with (see the step-level A/B further down)
+            _apply_tuned({"enabled": False, "mode": 0})
+            ops.PROFILE_GEMM = []
+            eager_step(resident, False)
+            torch.cuda.synchronize()
+            recs, ops.PROFILE_GEMM = ops.PROFILE_GEMM, None
+            prof_raw_off = (sum(r[0].elapsed_time(r[1]) for r in recs), sum(r[2] for r in recs), len(recs))
+            del recs
+            _apply_tuned(tuned)
     if args.torch_profile and rank == 0:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
@@ -1111,19 +1123,6 @@ def main() -> None:
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     ops.WGRAD_OVERLAP = overlap and not os.environ.get("NK_NO_WGRAD_OVERLAP")
-
-    step = eager_step
-    graphed = None
-    if not args.no_graph:
-        from neurosis_b200.graph import GraphedTrainStep
-        graphed = GraphedTrainStep(eng, reducer, resident["image"], resident["crossattn_emb"], resident.get("vector_emb"),
-                                   warmup=1, optimizer=optimizer, ema=ema)
-
-        def step(batch: dict, read_loss: bool) -> float:  # noqa: F811  (replays the captured step)
-            same = batch is resident
-            loss = graphed.step(None if same else batch["image"], None if same else batch["crossattn_emb"],
-                                None if same else batch.get("vector_emb"))
-            return loss.item() if read_loss else 0.0
 
     def barrier():
         if world > 1:
@@ -1143,16 +1142,63 @@ def main() -> None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(W):
-        step(resident, False)  # (graph capture already ran its own eager warm-up steps)
+    def measure():
+        """capture the step with the library's CURRENT kernel selection (or issue it eagerly), W warm-up steps, then the
+        two timed regions: inputs resident / pinned host batches + loss read-back.  -> (graphed, step, ms_dev, ms_e2e, launches)"""
+        step_, graphed_ = eager_step, None
+        if not args.no_graph:
+            from neurosis_b200.graph import GraphedTrainStep
+            graphed_ = GraphedTrainStep(eng, reducer, resident["image"], resident["crossattn_emb"], resident.get("vector_emb"),
+                                        warmup=1, optimizer=optimizer, ema=ema)
+
+            def step_(batch: dict, read_loss: bool) -> float:  # noqa: F811  (replays the captured step)
+                same = batch is resident
+                loss = graphed_.step(None if same else batch["image"], None if same else batch["crossattn_emb"],
+                                     None if same else batch.get("vector_emb"))
+                return loss.item() if read_loss else 0.0
+
+        for _ in range(W):
+            step_(resident, False)  # (graph capture already ran its own eager warm-up steps)
+        l0 = ops.LAUNCHES
+        ms_dev_ = timed(args.steps, lambda: step_(resident, False))
+        launches_ = ops.LAUNCHES - l0 if graphed_ is None else graphed_.launches_per_replay * args.steps
+        if graphed_ is not None:
+            ms_e2e_ = timed(args.steps, lambda: step_(host, True))  # pinned host -> static device buffers -> replay -> loss
+        else:
+            ms_e2e_ = timed(args.steps, lambda: step_({k: v.to(dev, non_blocking=True) for k, v in host.items()}, True))
+        return graphed_, step_, ms_dev_, ms_e2e_, launches_
+
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = ops.LAUNCHES
-    ms_dev = timed(args.steps, lambda: step(resident, False))
-    launches = ops.LAUNCHES - l0 if graphed is None else graphed.launches_per_replay * args.steps
-    if graphed is not None:
-        ms_e2e = timed(args.steps, lambda: step(host, True))  # pinned host -> static device buffers -> replay -> loss
-    else:
-        ms_e2e = timed(args.steps, lambda: step({k: v.to(dev, non_blocking=True) for k, v in host.items()}, True))
+    graphed, step, ms_dev, ms_e2e, launches = measure()
+    any_variant = bool(tuned.get("enabled") or any((tuned.get(k) or {}).get("enabled") for k in (
+        "layernorm_column_owner", "groupnorm_reverse_apply", "epilogue_l2_prefetch")))
+    if any_variant and graphed is not None:
+        # A/B at step level, same process, same data: the step is captured and timed a second time with every variant off
+        # (the kernels of DESIGN.md section 9).  The headline is the faster of the two; both are reported.  (`tuned` agrees
+        # across ranks and `timed` returns the max over ranks on every rank, so all ranks take the same branch.)
+        on = (ms_dev, ms_e2e, launches)
+        prof_raw_on = prof_raw
+        del step
+        graphed = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        _apply_tuned({"enabled": False, "mode": 0})
+        graphed, step, ms_dev, ms_e2e, launches = measure()
+        ab = {"ms_per_step_variants_on": on[0] / args.steps, "ms_per_step_variants_off": ms_dev / args.steps,
+              "e2e_ms_per_step_variants_on": on[1] / args.steps, "e2e_ms_per_step_variants_off": ms_e2e / args.steps}
+        if on[0] < ms_dev:
+            ms_dev, ms_e2e, launches = on
+            ab["headline_uses_variants"] = True
+            _apply_tuned(tuned)  # (library + environment for the child configurations; this process is done measuring)
+        else:
+            ab["headline_uses_variants"] = False
+            if prof_raw_off is not None:
+                prof_raw = prof_raw_off
+        if prof_raw_on is not None and prof_raw_off is not None:  # serial gemm_tc time of one eager step, on / off
+            ab["gemm_tc_ms_eager_step_variants_on_off"] = [round(prof_raw_on[0], 2), round(prof_raw_off[0], 2)]
+        tuned["step_ab"] = ab
     clocks = sampler.stop() if sampler else None
 
     roof = None
