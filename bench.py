@@ -356,6 +356,7 @@ def _export_tuned(rep: dict) -> None:
     os.environ["NK_GEMM_DUAL"] = str(rep.get("mode", 0) if on else 0)
     os.environ["NK_GEMM_DUAL_MIN_K"] = str(int(rep.get("min_k_iters") or 0) if on else 0)
     os.environ["NK_GEMM_DUAL_SKEW"] = str(int(rep.get("skew") or 0) if on else 0)
+    os.environ["NK_GEMM_DUAL_CLASSES"] = str(int(rep.get("classes", 7)) if on else 7)
     os.environ["NK_NORM_VARIANT"] = str(_norm_mask(rep))
     os.environ["NK_GEMM_EPI_PREFETCH"] = "1" if (rep.get("epilogue_l2_prefetch") or {}).get("enabled") else "0"
 
@@ -367,6 +368,7 @@ def _apply_tuned(tuned: dict) -> None:
     on = bool(tuned.get("enabled"))
     lib.nk_gemm_set_dual_min_k(int(tuned.get("min_k_iters") or 0) if on else 0)
     lib.nk_gemm_set_dual_skew(int(tuned.get("skew") or 0) if on else 0)
+    lib.nk_gemm_set_dual_classes(int(tuned.get("classes", 7)) if on else 7)
     tune.apply(int(tuned.get("mode", 1)) if on else 0)
     lib.nk_norm_set_variant(_norm_mask(tuned))
     lib.nk_gemm_set_epi_prefetch(1 if (tuned.get("epilogue_l2_prefetch") or {}).get("enabled") else 0)
@@ -434,7 +436,8 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
             # a verdict for exactly these variants, configuration and batch on this machine and library build is reused
             # (the driver starts the benchmark several times per box: 1 / 2 / 4 / 8 GPUs)
             gtag = "guard:" + ":".join([args.config, str(args.batch)] + [os.environ.get(k, "0") for k in (
-                "NK_GEMM_DUAL", "NK_GEMM_DUAL_MIN_K", "NK_GEMM_DUAL_SKEW", "NK_NORM_VARIANT", "NK_GEMM_EPI_PREFETCH")])
+                "NK_GEMM_DUAL", "NK_GEMM_DUAL_MIN_K", "NK_GEMM_DUAL_SKEW", "NK_GEMM_DUAL_CLASSES", "NK_NORM_VARIANT",
+                "NK_GEMM_EPI_PREFETCH")])
             cached = _tune.cache_load(gtag, local)
             if cached is not None:
                 res = cached
@@ -849,7 +852,8 @@ def run_other_configs(args, world: int, rank: int, budget_s: float, per_config_s
         env["NK_BENCH_EXTRAS"] = "0"
         env["NK_BENCH_NO_STEP_GUARD"] = "1"
         if plain:  # second attempt of a configuration that failed with the tuned kernel variants: the measured kernels only
-            env.update({"NK_GEMM_DUAL": "0", "NK_GEMM_DUAL_MIN_K": "0", "NK_GEMM_DUAL_SKEW": "0", "NK_NORM_VARIANT": "0"})
+            env.update({"NK_GEMM_DUAL": "0", "NK_GEMM_DUAL_MIN_K": "0", "NK_GEMM_DUAL_SKEW": "0", "NK_GEMM_DUAL_CLASSES": "7",
+                        "NK_NORM_VARIANT": "0", "NK_GEMM_EPI_PREFETCH": "0"})
         cmd = _child_cmd(name, args, world)
         t0 = time.monotonic()
         try:

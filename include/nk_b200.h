@@ -93,6 +93,11 @@ int nk_gemm_set_dual(int mode);
  * neurosis_b200.tune measures the break-even on the device; NK_GEMM_DUAL_MIN_K pins it.  k_iters < 0 only queries.
  * Returns the previous value (default 0 = no limit). */
 int nk_gemm_set_dual_min_k(int k_iters);
+/* Mode 1 only: which classes of launches may pair — bit 0 matrix GEMM with K-major A (nk_linear_fwd / nk_linear_dgrad),
+ * bit 1 matrix GEMM with MN-major A (nk_linear_wgrad), bit 2 implicit-GEMM convolution (nk_conv2d_fwd, also used for the data
+ * gradient, nk_conv2d_stride2_fwd).  Default 7 (or NK_GEMM_DUAL_CLASSES); neurosis_b200.tune clears the classes that lose on the
+ * device.  0..7 sets, anything else queries; returns the previous mask. */
+int nk_gemm_set_dual_classes(int mask);
 /* Paired launches: the MMA issuer lets the second row tile trail the first by k_iters k-iterations (0 = interleaved; the
  * kernel clamps to ring depth - 1), so that the first tile starts while the epilogue still drains the other TMEM buffer
  * and reaches its own epilogue earlier.  Does not change results.  0..7 sets, anything else queries; returns the previous

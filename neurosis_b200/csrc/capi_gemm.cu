@@ -66,6 +66,7 @@ const char* nk_last_error(void) { return nk::last_error(); }
 int nk_sm_count(void) { return nk::device_sm_count(); }
 int nk_gemm_set_dual(int mode) { return nk::gemm_set_dual(mode); }
 int nk_gemm_set_dual_min_k(int k_iters) { return nk::gemm_set_dual_min_k(k_iters); }
+int nk_gemm_set_dual_classes(int mask) { return nk::gemm_set_dual_classes(mask); }
 int nk_gemm_set_dual_skew(int k_iters) { return nk::gemm_set_dual_skew(k_iters); }
 int nk_gemm_set_epi_prefetch(int on) { return nk::gemm_set_epi_prefetch(on); }
 

@@ -1307,6 +1307,22 @@ int gemm_set_epi_prefetch(int on) {
     if (on == 0 || on == 1) g_epi_prefetch = on;
     return prev;
 }
+// Which launch classes may pair: bit 0 = matrix GEMM with K-major A (linear forward / data gradient), bit 1 = matrix GEMM
+// with MN-major A (linear weight gradient), bit 2 = implicit-GEMM convolution forward / data gradient.  Default 7
+// (NK_GEMM_DUAL_CLASSES); neurosis_b200.tune clears the bits of classes that lose on the device.
+static int g_dual_classes = -1;
+static int dual_classes() {
+    if (g_dual_classes < 0) {
+        const char* e_ = getenv("NK_GEMM_DUAL_CLASSES");
+        g_dual_classes = e_ ? (atoi(e_) & 7) : 7;
+    }
+    return g_dual_classes;
+}
+int gemm_set_dual_classes(int mask) {
+    const int prev = dual_classes();
+    if (mask >= 0 && mask <= 7) g_dual_classes = mask;
+    return prev;
+}
 int gemm_set_dual_min_k(int k_iters) {
     const int prev = dual_min_k();
     if (k_iters >= 0) g_dual_min_k = k_iters;
@@ -1502,8 +1518,11 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
             const long long tm2 = (g.tiles_m + 1) / 2;
             const long long single = tiles_mb * g.tiles_n, paired = tm2 * g.nb2 * g.nb1 * g.tiles_n;
             const long long groups = nsm / cg;
+            const int cls = g.mode == MODE_CONV_FWD ? 4 : (g.a_mn ? 2 : 1);
             if (dm == 2) {
                 dual = true;
+            } else if ((dual_classes() & cls) == 0) {
+                dual = false;  // this class of launches lost on the device (neurosis_b200.tune)
             } else if (g.k_iters_total < dual_min_k()) {
                 dual = false;  // reduction too short for pairing to pay (threshold measured by neurosis_b200.tune)
             } else if (p.out == OUT_F32_ATOMIC) {

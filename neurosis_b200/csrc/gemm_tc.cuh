@@ -73,6 +73,8 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream);
 int gemm_set_dual(int mode);
 // mode 1 only: smallest number of 64-deep k-iterations a launch must have to be paired (< 0 queries); returns the previous value
 int gemm_set_dual_min_k(int k_iters);
+// mode 1 only: launch classes that may pair (bit 0 K-major-A matrix GEMM, bit 1 MN-major-A matrix GEMM, bit 2 convolution); 0..7 sets, else queries
+int gemm_set_dual_classes(int mask);
 // L2 prefetch of the epilogue's side input (residual / GEGLU h) at tile start: 0 off, 1 on, anything else queries; returns the previous value
 int gemm_set_epi_prefetch(int on);
 // paired launches: k-iterations by which the second row tile trails the first (0..7, clamped to stages - 1; < 0 queries)

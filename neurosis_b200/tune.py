@@ -118,6 +118,33 @@ def _k_iters(kind: str, dims: tuple) -> int:
     return ks * ks * cin // 64
 
 
+def _class_bit(kind: str) -> int:
+    """launch class of `nk_gemm_set_dual_classes`: 1 K-major-A matrix GEMM, 2 MN-major-A (weight gradient), 4 convolution."""
+    return 4 if kind.startswith("conv") else (2 if "wgrad" in kind else 1)
+
+
+def pick_classes_and_min_k(rows: list, tol: float = 1.02):
+    """(class mask, depth limit): a class of launches is kept if there is a reduction depth from which mode 1 never loses on
+    its measured shapes.  The common depth limit is the largest limit of the kept forward-type classes (conservative);
+    weight gradients reduce over the tokens (hundreds of k-iterations, far above any such limit), so their class is simply
+    kept or dropped."""
+    mask, limit = 0, 0
+    for bit in (1, 2, 4):
+        sub = [r for r in rows if _class_bit(r["kind"]) == bit]
+        if not sub:
+            continue
+        t = pick_min_k(sub, tol)
+        if t is None:
+            continue
+        if bit == 2:
+            if t == min(r["k_iters"] for r in sub):  # never loses
+                mask |= bit
+        else:
+            mask |= bit
+            limit = max(limit, t)
+    return mask, (limit if mask else None)
+
+
 def pick_min_k(rows: list, tol: float = 1.02) -> Optional[int]:
     """smallest reduction depth T such that mode 1 is no slower (within timing noise `tol`) than the unpaired kernel on
     EVERY measured shape with k_iters >= T; None if there is no such depth (pairing never pays).  Launches the cost model
@@ -163,6 +190,8 @@ def probe(device: int = 0, timed: bool = True, skew: int = 0) -> dict:
     prev = lib.nk_gemm_set_dual(-1)
     prev_k = lib.nk_gemm_set_dual_min_k(-1)
     prev_s = lib.nk_gemm_set_dual_skew(-1)
+    prev_c = lib.nk_gemm_set_dual_classes(-1)
+    lib.nk_gemm_set_dual_classes(7)
     lib.nk_gemm_set_dual_min_k(0)
     lib.nk_gemm_set_dual_skew(skew)
     try:
@@ -195,12 +224,14 @@ def probe(device: int = 0, timed: bool = True, skew: int = 0) -> dict:
                 rows.append({"kind": kind, "dims": list(dims), "launches_per_step": weight, "k_iters": _k_iters(kind, dims),
                              "ms_unpaired": a, "ms_mode1_no_limit": b})
                 del fn
-            min_k = pick_min_k(rows)
-            report["min_k_iters"] = min_k
+            classes, min_k = pick_classes_and_min_k(rows)
+            # (a class limit below the common one only matters for shapes between the two; those pay the conservative choice)
+            report["classes"], report["min_k_iters"] = classes, min_k
             # pass 2: the mode that would be used (cost model + threshold) against unpaired, weighted by launches per step
             t_off = t_on = 0.0
             if min_k is not None:
                 lib.nk_gemm_set_dual_min_k(min_k)
+                lib.nk_gemm_set_dual_classes(classes)
                 for r, (kind, dims, weight) in zip(rows, TIMED_SHAPES):
                     fn = _make_case(kind, dims, dev, gen)
                     lib.nk_gemm_set_dual(1)
@@ -218,6 +249,7 @@ def probe(device: int = 0, timed: bool = True, skew: int = 0) -> dict:
         lib.nk_gemm_set_dual(prev)
         lib.nk_gemm_set_dual_min_k(prev_k)
         lib.nk_gemm_set_dual_skew(prev_s)
+        lib.nk_gemm_set_dual_classes(prev_c)
     return report
 
 
@@ -439,7 +471,7 @@ def probe_groupnorm_reverse(device: int = 0, timed: bool = True) -> dict:
 def _summary(rep: dict, max_timings: int = 6) -> dict:
     """what bench.py prints: verdict, weighted times, the failed checks and the largest movers."""
     out = {k: rep[k] for k in ("variant", "ok", "step_ms_unpaired", "step_ms_paired", "speedup", "error", "enabled", "mode",
-                               "probe_wall_s", "source", "min_k_iters", "skew", "candidates", "note", "step_guard") if k in rep}
+                               "probe_wall_s", "source", "min_k_iters", "classes", "skew", "candidates", "note", "step_guard", "step_ab") if k in rep}
     ln = rep.get("layernorm_column_owner")
     if ln is not None:
         out["layernorm_column_owner"] = {k: ln[k] for k in ("ok", "enabled", "speedup", "step_ms_old", "step_ms_new", "error", "source",
@@ -530,6 +562,7 @@ def _apply_report(rep: dict, min_speedup: float) -> dict:
     rep["enabled"], rep["mode"] = enable, 1 if enable else 0
     lib.nk_gemm_set_dual_min_k(int(rep["min_k_iters"]) if enable else 0)
     lib.nk_gemm_set_dual_skew(int(rep.get("skew", 0)) if enable else 0)
+    lib.nk_gemm_set_dual_classes(int(rep.get("classes", 7)) if enable else 7)
     lib.nk_gemm_set_dual(1 if enable else 0)
     ln = rep.get("layernorm_column_owner")
     if ln is None:
@@ -557,7 +590,8 @@ def autotune(device: int = 0, timeout_s: float = 240.0, min_speedup: float = 1.0
         nv = int(os.environ.get("NK_NORM_VARIANT", "0") or 0)
         return {"variant": "gemm_row_tile_pairing", "enabled": env_mode not in ("", "0"), "mode": int(env_mode or 0),
                 "min_k_iters": int(os.environ.get("NK_GEMM_DUAL_MIN_K", "0") or 0),
-                "skew": int(os.environ.get("NK_GEMM_DUAL_SKEW", "0") or 0), "source": "NK_GEMM_DUAL (pinned, no probe)",
+                "skew": int(os.environ.get("NK_GEMM_DUAL_SKEW", "0") or 0),
+                "classes": int(os.environ.get("NK_GEMM_DUAL_CLASSES", "7") or 7), "source": "NK_GEMM_DUAL (pinned, no probe)",
                 "layernorm_column_owner": {"enabled": bool(nv & 1), "source": "NK_NORM_VARIANT (pinned with NK_GEMM_DUAL, no probe)"},
                 "groupnorm_reverse_apply": {"enabled": bool(nv & 2), "source": "NK_NORM_VARIANT (pinned with NK_GEMM_DUAL, no probe)"},
                 "epilogue_l2_prefetch": {"enabled": os.environ.get("NK_GEMM_EPI_PREFETCH", "0") not in ("", "0"),
@@ -606,7 +640,7 @@ def autotune(device: int = 0, timeout_s: float = 240.0, min_speedup: float = 1.0
             rep = cands[0]
         if cands:
             rep["candidates"] = [{"skew": c.get("skew"), "ok": c.get("ok"), "speedup": c.get("speedup"),
-                                  "min_k_iters": c.get("min_k_iters")} for c in cands]
+                                  "min_k_iters": c.get("min_k_iters"), "classes": c.get("classes")} for c in cands]
         if ln_reps:
             rep["layernorm_column_owner"] = ln_reps[-1]
         if pf_reps:

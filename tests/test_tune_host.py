@@ -128,6 +128,23 @@ def test_probe_shapes_cover_every_paired_mode():
     assert any(k == "conv" and d[0] * d[1] * d[2] < 128 * 2 for k, d in tune.CHECK_SHAPES)
 
 
+def test_class_mask_selection():
+    """a class of launches that loses at every depth is dropped without taking the others with it."""
+    def row(kind, k, off, on):
+        return {"kind": kind, "k_iters": k, "ms_unpaired": off, "ms_mode1_no_limit": on}
+    rows = [row("linear_fwd", 10, 1.0, 1.1), row("linear_fwd", 20, 1.0, 0.9), row("linear_dgrad", 160, 1.0, 0.85),
+            row("linear_wgrad", 256, 1.0, 1.2), row("conv", 45, 1.0, 0.95), row("conv", 180, 1.0, 0.8)]
+    assert tune.pick_classes_and_min_k(rows) == (1 | 4, 45)
+    rows[3]["ms_mode1_no_limit"] = 0.9
+    assert tune.pick_classes_and_min_k(rows) == (7, 45)   # the weight-gradient class does not raise the depth limit
+    rows.append(row("linear_wgrad", 1024, 1.0, 0.8))
+    rows[3]["ms_mode1_no_limit"] = 1.3                    # loses at one of its depths: the class goes, the others stay
+    assert tune.pick_classes_and_min_k(rows) == (1 | 4, 45)
+    assert tune.pick_classes_and_min_k([row("linear_fwd", 20, 1.0, 1.3), row("conv", 45, 1.0, 1.2)]) == (0, None)
+    prev = lib.nk_gemm_set_dual_classes(5)
+    assert lib.nk_gemm_set_dual_classes(-1) == 5 and lib.nk_gemm_set_dual_classes(prev) == 5
+
+
 def test_depth_threshold_selection():
     """pick_min_k: the smallest reduction depth from which mode 1 never loses (2 % timing noise allowed)."""
     def row(k, off, on):
