@@ -351,6 +351,11 @@ def _norm_mask(tuned: dict) -> int:
             | (2 if (tuned.get("groupnorm_reverse_apply") or {}).get("enabled") else 0))
 
 
+def _prefetch_mask(tuned: dict) -> int:
+    pf = tuned.get("epilogue_l2_prefetch") or {}
+    return int(pf.get("mask", 3) or 0) if pf.get("enabled") else 0
+
+
 def _export_tuned(rep: dict) -> None:
     on = bool(rep.get("enabled"))
     os.environ["NK_GEMM_DUAL"] = str(rep.get("mode", 0) if on else 0)
@@ -358,7 +363,7 @@ def _export_tuned(rep: dict) -> None:
     os.environ["NK_GEMM_DUAL_SKEW"] = str(int(rep.get("skew") or 0) if on else 0)
     os.environ["NK_GEMM_DUAL_CLASSES"] = str(int(rep.get("classes", 7)) if on else 7)
     os.environ["NK_NORM_VARIANT"] = str(_norm_mask(rep))
-    os.environ["NK_GEMM_EPI_PREFETCH"] = "1" if (rep.get("epilogue_l2_prefetch") or {}).get("enabled") else "0"
+    os.environ["NK_GEMM_EPI_PREFETCH"] = str(_prefetch_mask(rep))
 
 
 def _apply_tuned(tuned: dict) -> None:
@@ -371,7 +376,7 @@ def _apply_tuned(tuned: dict) -> None:
     lib.nk_gemm_set_dual_classes(int(tuned.get("classes", 7)) if on else 7)
     tune.apply(int(tuned.get("mode", 1)) if on else 0)
     lib.nk_norm_set_variant(_norm_mask(tuned))
-    lib.nk_gemm_set_epi_prefetch(1 if (tuned.get("epilogue_l2_prefetch") or {}).get("enabled") else 0)
+    lib.nk_gemm_set_epi_prefetch(_prefetch_mask(tuned))
     _export_tuned(tuned)
 
 
@@ -504,7 +509,7 @@ def run_guard_child(args) -> None:
     from neurosis_b200.ddp import BucketedGradReducer
     gmode = int(os.environ.get("NK_GEMM_DUAL", "0") or 0)
     nmask = int(os.environ.get("NK_NORM_VARIANT", "0") or 0) & 3
-    pfon = 1 if os.environ.get("NK_GEMM_EPI_PREFETCH", "0") not in ("", "0") else 0
+    pfon = int(os.environ.get("NK_GEMM_EPI_PREFETCH", "0") or 0) & 3
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -552,7 +557,7 @@ def run_guard_child(args) -> None:
     out["tolerance"] = {"loss": tl, "grad_abs_sum": tg}
     ref = base
     if pfon:
-        lib.nk_gemm_set_epi_prefetch(1)
+        lib.nk_gemm_set_epi_prefetch(pfon)
         gotp = step(0, 0)
         okp = agree(base, gotp, tl, tg)
         out["prefetch"] = {"loss_off": base[0], "loss_on": gotp[0], "grad_abs_sum_off": base[1], "grad_abs_sum_on": gotp[1],

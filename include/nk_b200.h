@@ -107,8 +107,8 @@ int nk_gemm_set_dual_skew(int k_iters);
  * `cp.async.bulk.prefetch.tensor.L2` for the boxes of the residual (EPI_LINEAR) or of the saved GEGLU pre-activation h
  * (nk_linear_dgrad_geglu) that the epilogue will read — while the tile's main loop still runs.  The epilogue reads that
  * input with one 32-byte load per thread (= row) and 16-column chunk, which is latency-bound when the rows come from DRAM.
- * A hint to the memory system: results are unchanged by construction.  0 off (default, or NK_GEMM_EPI_PREFETCH), 1 on,
- * anything else queries; returns the previous value.  Reference sites of the fused adds: modules/attention.py:497-511
+ * A hint to the memory system: results are unchanged by construction.  `on` is a mask: bit 0 = h of the GEGLU data gradient,
+ * bit 1 = residuals; 0 off (default, or NK_GEMM_EPI_PREFETCH); 0..3 sets, anything else queries; returns the previous mask.  Reference sites of the fused adds: modules/attention.py:497-511
  * (x + attn(...), x + ff(...)), modules/diffusion/openaimodel.py:337-342 (skip_connection(x) + h). */
 int nk_gemm_set_epi_prefetch(int on);
 

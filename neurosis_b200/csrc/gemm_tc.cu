@@ -1292,19 +1292,20 @@ int gemm_set_dual_skew(int k_iters) {
     if (k_iters >= 0 && k_iters <= 7) g_dual_skew = k_iters;
     return prev;
 }
-// L2 prefetch of the epilogue's side input (residual of EPI_LINEAR, h of EPI_GEGLU_BWD) at the start of every tile: 0 off
-// (default, or NK_GEMM_EPI_PREFETCH), 1 on.  A hint to the memory system, results are unchanged by construction.
+// L2 prefetch of the epilogue's side input at the start of every tile, a bit mask: bit 0 = h of EPI_GEGLU_BWD, bit 1 = the
+// residual of EPI_LINEAR.  0 off (default, or NK_GEMM_EPI_PREFETCH).  A hint to the memory system, results are unchanged
+// by construction.
 static int g_epi_prefetch = -1;
 static int epi_prefetch_mode() {
     if (g_epi_prefetch < 0) {
         const char* e_ = getenv("NK_GEMM_EPI_PREFETCH");
-        g_epi_prefetch = e_ ? (atoi(e_) != 0 ? 1 : 0) : 0;
+        g_epi_prefetch = e_ ? (atoi(e_) & 3) : 0;
     }
     return g_epi_prefetch;
 }
 int gemm_set_epi_prefetch(int on) {
     const int prev = epi_prefetch_mode();
-    if (on == 0 || on == 1) g_epi_prefetch = on;
+    if (on >= 0 && on <= 3) g_epi_prefetch = on;
     return prev;
 }
 // Which launch classes may pair: bit 0 = matrix GEMM with K-major A (linear forward / data gradient), bit 1 = matrix GEMM
@@ -1640,11 +1641,12 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
             if (e) return e;
         } else if (epi_prefetch_mode()) {
             // side-input map (same logical shape and batch strides as the output, its own row stride)
-            if (geglu_bwd && aligned16(p.aux, p.ldr * 2)) {
+            if (geglu_bwd && (epi_prefetch_mode() & 1) && aligned16(p.aux, p.ldr * 2)) {
                 e = make_out_tmap(&g.tmC2, p.aux, 0, 2LL * p.N, p.ldr, g, p);
                 if (e) return e;
                 g.epi_prefetch = 1;
-            } else if (!geglu_bwd && p.epi == EPI_LINEAR && p.residual != nullptr && aligned16(p.residual, p.ldr * 2)) {
+            } else if (!geglu_bwd && (epi_prefetch_mode() & 2) && p.epi == EPI_LINEAR && p.residual != nullptr &&
+                       aligned16(p.residual, p.ldr * 2)) {
                 e = make_out_tmap(&g.tmC2, p.residual, 0, p.N, p.ldr, g, p);
                 if (e) return e;
                 g.epi_prefetch = 1;

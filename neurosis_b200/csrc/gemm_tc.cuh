@@ -75,7 +75,7 @@ int gemm_set_dual(int mode);
 int gemm_set_dual_min_k(int k_iters);
 // mode 1 only: launch classes that may pair (bit 0 K-major-A matrix GEMM, bit 1 MN-major-A matrix GEMM, bit 2 convolution); 0..7 sets, else queries
 int gemm_set_dual_classes(int mask);
-// L2 prefetch of the epilogue's side input (residual / GEGLU h) at tile start: 0 off, 1 on, anything else queries; returns the previous value
+// L2 prefetch of the epilogue's side input at tile start: mask (bit 0 GEGLU h, bit 1 residual), 0..3 sets, anything else queries; returns the previous mask
 int gemm_set_epi_prefetch(int on);
 // paired launches: k-iterations by which the second row tile trails the first (0..7, clamped to stages - 1; < 0 queries)
 int gemm_set_dual_skew(int k_iters);

@@ -368,7 +368,7 @@ def probe_epilogue_prefetch(device: int = 0, timed: bool = True) -> dict:
             fn = _make_case(kind, dims, dev, gen)
             lib.nk_gemm_set_epi_prefetch(0)
             ref = fn().float()
-            lib.nk_gemm_set_epi_prefetch(1)
+            lib.nk_gemm_set_epi_prefetch(3)
             got = fn().float()
             torch.cuda.synchronize()
             ok = bool(torch.equal(got, ref))
@@ -385,12 +385,24 @@ def probe_epilogue_prefetch(device: int = 0, timed: bool = True) -> dict:
                 for _ in range(2):
                     lib.nk_gemm_set_epi_prefetch(0)
                     a = min(a, _time(fn, 8))
-                    lib.nk_gemm_set_epi_prefetch(1)
+                    lib.nk_gemm_set_epi_prefetch(3)
                     b = min(b, _time(fn, 8))
                 rep["timings"].append({"kind": kind, "dims": list(dims), "launches_per_step": weight, "ms_off": a, "ms_on": b})
-                t_off += a * weight
-                t_on += b * weight
                 del fn
+            # the two side inputs are judged separately (bit 0: GEGLU h, bit 1: residuals): a bit is kept if its call sites
+            # together gain at least 1 %
+            mask = 0
+            for bit, sel in ((1, lambda r: r["kind"] == "geglu_bwd"), (2, lambda r: r["kind"] != "geglu_bwd")):
+                rows = [r for r in rep["timings"] if sel(r)]
+                off = sum(r["ms_off"] * r["launches_per_step"] for r in rows)
+                on = sum(r["ms_on"] * r["launches_per_step"] for r in rows)
+                if rows and on > 0 and off / on >= 1.01:
+                    mask |= bit
+            rep["mask"] = mask
+            for r in rep["timings"]:
+                use = bool(mask & (1 if r["kind"] == "geglu_bwd" else 2))
+                t_off += r["ms_off"] * r["launches_per_step"]
+                t_on += (r["ms_on"] if use else r["ms_off"]) * r["launches_per_step"]
             rep["step_ms_off"], rep["step_ms_on"] = t_off, t_on
             rep["speedup"] = t_off / t_on if t_on > 0 else 0.0
     finally:
@@ -491,7 +503,7 @@ def _summary(rep: dict, max_timings: int = 6) -> dict:
             out["groupnorm_reverse_apply"]["timings"] = gn["timings"]
     pf = rep.get("epilogue_l2_prefetch")
     if pf is not None:
-        out["epilogue_l2_prefetch"] = {k: pf[k] for k in ("ok", "enabled", "speedup", "step_ms_off", "step_ms_on", "error", "source",
+        out["epilogue_l2_prefetch"] = {k: pf[k] for k in ("ok", "enabled", "mask", "speedup", "step_ms_off", "step_ms_on", "error", "source",
                                                           "step_guard") if k in pf}
         out["epilogue_l2_prefetch"]["checks_run"] = len(pf.get("checks", []))
         if pf.get("timings"):
@@ -576,8 +588,8 @@ def _apply_report(rep: dict, min_speedup: float) -> dict:
     pf = rep.get("epilogue_l2_prefetch")
     if pf is None:
         pf = rep["epilogue_l2_prefetch"] = {"ok": False, "error": "no verdict from the probe child"}
-    pf["enabled"] = bool(pf.get("ok")) and float(pf.get("speedup", 0.0)) >= 1.01
-    lib.nk_gemm_set_epi_prefetch(1 if pf["enabled"] else 0)
+    pf["enabled"] = bool(pf.get("ok")) and int(pf.get("mask", 0) or 0) != 0 and float(pf.get("speedup", 0.0)) >= 1.005
+    lib.nk_gemm_set_epi_prefetch(int(pf.get("mask", 0) or 0) if pf["enabled"] else 0)
     return rep
 
 
@@ -595,6 +607,7 @@ def autotune(device: int = 0, timeout_s: float = 240.0, min_speedup: float = 1.0
                 "layernorm_column_owner": {"enabled": bool(nv & 1), "source": "NK_NORM_VARIANT (pinned with NK_GEMM_DUAL, no probe)"},
                 "groupnorm_reverse_apply": {"enabled": bool(nv & 2), "source": "NK_NORM_VARIANT (pinned with NK_GEMM_DUAL, no probe)"},
                 "epilogue_l2_prefetch": {"enabled": os.environ.get("NK_GEMM_EPI_PREFETCH", "0") not in ("", "0"),
+                                         "mask": int(os.environ.get("NK_GEMM_EPI_PREFETCH", "0") or 0),
                                          "source": "NK_GEMM_EPI_PREFETCH (pinned with NK_GEMM_DUAL, no probe)"}}
     if os.environ.get("NK_B200_TUNE", "1") == "0":
         return {"variant": "gemm_row_tile_pairing", "enabled": False, "mode": 0, "source": "NK_B200_TUNE=0 (no probe)"}

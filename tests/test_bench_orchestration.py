@@ -126,7 +126,7 @@ def test_step_guard_keeps_or_drops_variants_and_sets_the_library(monkeypatch):
 
     def tuned():
         return {"enabled": True, "mode": 1, "min_k_iters": 20, "skew": 3,
-                "layernorm_column_owner": {"enabled": True, "speedup": 1.3}, "epilogue_l2_prefetch": {"enabled": True, "speedup": 1.1},
+                "layernorm_column_owner": {"enabled": True, "speedup": 1.3}, "epilogue_l2_prefetch": {"enabled": True, "speedup": 1.1, "mask": 1},
                 "groupnorm_reverse_apply": {"enabled": True, "speedup": 1.05}}
 
     args = types.SimpleNamespace(config="sdxl", batch=16)

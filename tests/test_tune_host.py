@@ -104,9 +104,14 @@ def test_verdict_rules(monkeypatch):
     assert not got["groupnorm_reverse_apply"]["enabled"] and lib.nk_norm_set_variant(-1) == 1
     # third variant: the epilogue prefetch hint
     assert not got["epilogue_l2_prefetch"]["enabled"] and "no verdict" in got["epilogue_l2_prefetch"]["error"]
-    reps.insert(2, {"variant": "epilogue_l2_prefetch", "ok": True, "speedup": 1.06, "checks": [], "timings": []})
+    reps.insert(2, {"variant": "epilogue_l2_prefetch", "ok": True, "speedup": 1.06, "mask": 1, "checks": [], "timings": []})
     got = tune.autotune()
     assert got["epilogue_l2_prefetch"]["enabled"] and lib.nk_gemm_set_epi_prefetch(-1) == 1
+    reps[2]["mask"] = 3
+    assert tune.autotune()["epilogue_l2_prefetch"]["enabled"] and lib.nk_gemm_set_epi_prefetch(-1) == 3
+    reps[2]["mask"] = 0   # neither side input gained: nothing to enable
+    assert not tune.autotune()["epilogue_l2_prefetch"]["enabled"] and lib.nk_gemm_set_epi_prefetch(-1) == 0
+    reps[2]["mask"] = 1
     json.dumps(tune._summary(got))
     reps[2]["speedup"] = 1.0
     assert not tune.autotune()["epilogue_l2_prefetch"]["enabled"] and lib.nk_gemm_set_epi_prefetch(-1) == 0
