@@ -347,7 +347,8 @@ def _autotune(world: int, local: int, dev) -> dict:
 
 
 def _norm_mask(tuned: dict) -> int:
-    return ((1 if (tuned.get("layernorm_column_owner") or {}).get("enabled") else 0)
+    ln = tuned.get("layernorm_column_owner") or {}
+    return ((int(ln.get("mask", 5) or 0) & 5 if ln.get("enabled") else 0)
             | (2 if (tuned.get("groupnorm_reverse_apply") or {}).get("enabled") else 0))
 
 
@@ -508,7 +509,7 @@ def run_guard_child(args) -> None:
     from neurosis_b200._lib import lib
     from neurosis_b200.ddp import BucketedGradReducer
     gmode = int(os.environ.get("NK_GEMM_DUAL", "0") or 0)
-    nmask = int(os.environ.get("NK_NORM_VARIANT", "0") or 0) & 3
+    nmask = int(os.environ.get("NK_NORM_VARIANT", "0") or 0) & 7
     pfon = int(os.environ.get("NK_GEMM_EPI_PREFETCH", "0") or 0) & 3
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -586,8 +587,8 @@ def run_guard_child(args) -> None:
         print(json.dumps(out), flush=True)
         if ok3:
             ref, keep = got3, 2
-    if nmask & 1:
-        got2 = step(gmode, keep | 1)
+    if nmask & 5:
+        got2 = step(gmode, keep | (nmask & 5))
         out["layernorm"] = {"loss_old": ref[0], "loss_new": got2[0], "grad_abs_sum_old": ref[1], "grad_abs_sum_new": got2[1],
                             "agree": agree(ref, got2, max(tl, 2e-3), max(tg, 1e-2))}
     print(json.dumps(out), flush=True)

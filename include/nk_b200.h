@@ -208,13 +208,15 @@ int nk_groupnorm_bwd(const void* dy, int64_t dy_pix_stride, const void* x, int64
                      const float* gamma, const float* beta, const float* mean, const float* rstd, void* dx,
                      int64_t dx_pix_stride, float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
                      int nimg, int HW, int C, int G, int silu, nk_stream_t stream);
-/* Kernel forms written after the last GPU run: bit 0 = LayerNorm forward / backward as column-owner
- * blocks (gamma / beta and the dgamma / dbeta sums in registers, one pass over x and dy in the backward); bit 1 = the second
- * pass of GroupNorm forward / backward walks its (image, chunk) grid backwards, starting on the part of x (and dy) the
- * statistics pass read last and that is still in L2 (bit-identical results, openaimodel.py:247-249).  0 = the measured
- * forms (library default, or NK_NORM_VARIANT).  Same formulas, different reduction order: outputs agree to bf16 rounding,
- * statistics to fp32 rounding.  mask outside 0..255 only queries; returns the previous mask.  neurosis_b200.tune sets bits
- * after an on-device comparison.  Reference counterpart of the kernels: nn.LayerNorm, modules/attention.py:468-470. */
+/* Kernel forms written after the last GPU run, a bit mask:
+ *   bit 0  LayerNorm forward as column-owner blocks (gamma / beta in registers, shifted single-pass variance);
+ *   bit 2  LayerNorm backward as column-owner blocks (dgamma / dbeta sums in registers, ONE pass over x and dy);
+ *   bit 1  the second pass of GroupNorm forward / backward walks its (image, chunk) grid backwards, starting on the part of
+ *          x (and dy) the statistics pass read last and that is still in L2 (openaimodel.py:247-249).
+ * 0 = the measured forms (library default, or NK_NORM_VARIANT).  Same formulas, different reduction / dispatch order: outputs
+ * agree to bf16 rounding, statistics to fp32 rounding.  mask outside 0..255 only queries; returns the previous mask.
+ * neurosis_b200.tune sets bits after an on-device comparison.  Reference counterpart of the kernels: nn.LayerNorm,
+ * modules/attention.py:468-470. */
 int nk_norm_set_variant(int mask);
 
 /* LayerNorm over the last dim of [rows, C] bf16.  Replaces nn.LayerNorm: modules/attention.py:468-470. */

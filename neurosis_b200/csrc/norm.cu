@@ -766,9 +766,9 @@ __global__ void __launch_bounds__(LN2_MAXW * 32) ln_bwd_v2_kernel(const bf16* __
 
 using namespace nk;
 
-// Kernel forms of this file that were written after the last GPU run: bit 0 = LayerNorm forward / backward as column-owner
-// blocks (ln_*_v2_kernel); bit 1 = the GroupNorm apply passes walk the (image, chunk) grid backwards (L2 reuse of what the
-// statistics pass read last; bit-identical results).  0 (the default, or NK_NORM_VARIANT) = the forms measured in DESIGN.md section 2.3;
+// Kernel forms of this file that were written after the last GPU run: bit 0 = LayerNorm forward as column-owner blocks
+// (ln_fwd_v2_kernel), bit 2 = LayerNorm backward likewise (ln_bwd_v2_kernel: one pass over x and dy); bit 1 = the GroupNorm
+// apply passes walk the (image, chunk) grid backwards (L2 reuse of what the statistics pass read last).  0 (the default, or NK_NORM_VARIANT) = the forms measured in DESIGN.md section 2.3;
 // neurosis_b200.tune sets bits only after comparing both forms on the device.
 static int g_norm_variant = -1;
 static int norm_variant() {
@@ -885,7 +885,7 @@ int nk_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, c
     const bf16* rp = static_cast<const bf16*>(dres);
     NK_REQUIRE(!dres || (lddres % 8 == 0 && (reinterpret_cast<uintptr_t>(dres) & 15u) == 0), NK_ERR_SHAPE,
                "layernorm bwd: dres alignment");
-    if ((norm_variant() & 1) && lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0) {
+    if ((norm_variant() & 4) && lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0) {
         constexpr int RB = 4;
         const int warps = (C / 8 + 31) / 32;
         const long long want = (static_cast<long long>(rows) + 148 * 4 - 1) / (148 * 4);

@@ -298,7 +298,7 @@ def probe_layernorm(device: int = 0, timed: bool = True) -> dict:
             x, dy, gamma, beta, dres = case(rows, c, pad, with_res)
             lib.nk_norm_set_variant(0)
             a = run(x, dy, gamma, beta, dres)
-            lib.nk_norm_set_variant(1)
+            lib.nk_norm_set_variant(5)  # forward (bit 0) and backward (bit 2) second forms
             b = run(x, dy, gamma, beta, dres)
             # fp32 evaluation of the same bf16 inputs
             xf = x.float().requires_grad_(True)
@@ -327,13 +327,21 @@ def probe_layernorm(device: int = 0, timed: bool = True) -> dict:
                 lib.nk_norm_set_variant(0)
                 _, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-5)
                 row = {"rows": rows, "C": c, "calls_per_step": weight}
-                for name, mask in (("old", 0), ("new", 1)):
+                for name, mask in (("old", 0), ("new", 5)):
                     lib.nk_norm_set_variant(mask)
                     row[f"fwd_ms_{name}"] = _time(lambda: ops.layernorm_fwd(x, gamma, beta, 1e-5), 10)
                     row[f"bwd_ms_{name}"] = _time(lambda: ops.layernorm_bwd(dy, x, gamma, mean, rstd, out=(dg, db), dres=dres), 10)
-                t_old += weight * (row["fwd_ms_old"] + row["bwd_ms_old"])
-                t_new += weight * (row["fwd_ms_new"] + row["bwd_ms_new"])
                 rep["timings"].append(row)
+            # forward and backward are separate kernels with separate switches: each is kept if it gains >= 2 % on its own
+            f_old = sum(r["calls_per_step"] * r["fwd_ms_old"] for r in rep["timings"])
+            f_new = sum(r["calls_per_step"] * r["fwd_ms_new"] for r in rep["timings"])
+            b_old = sum(r["calls_per_step"] * r["bwd_ms_old"] for r in rep["timings"])
+            b_new = sum(r["calls_per_step"] * r["bwd_ms_new"] for r in rep["timings"])
+            mask = (1 if f_new > 0 and f_old / f_new >= 1.02 else 0) | (4 if b_new > 0 and b_old / b_new >= 1.02 else 0)
+            rep["mask"] = mask
+            t_old = f_old + b_old
+            t_new = (f_new if mask & 1 else f_old) + (b_new if mask & 4 else b_old)
+            rep["fwd_ms_old_new"], rep["bwd_ms_old_new"] = [f_old, f_new], [b_old, b_new]
             rep["step_ms_old"], rep["step_ms_new"] = t_old, t_new
             rep["speedup"] = t_old / t_new if t_new > 0 else 0.0
     finally:
@@ -486,7 +494,8 @@ def _summary(rep: dict, max_timings: int = 6) -> dict:
                                "probe_wall_s", "source", "min_k_iters", "classes", "skew", "candidates", "note", "step_guard", "step_ab") if k in rep}
     ln = rep.get("layernorm_column_owner")
     if ln is not None:
-        out["layernorm_column_owner"] = {k: ln[k] for k in ("ok", "enabled", "speedup", "step_ms_old", "step_ms_new", "error", "source",
+        out["layernorm_column_owner"] = {k: ln[k] for k in ("ok", "enabled", "mask", "speedup", "fwd_ms_old_new", "bwd_ms_old_new",
+                                                            "step_ms_old", "step_ms_new", "error", "source",
                                                             "step_guard") if k in ln}
         out["layernorm_column_owner"]["checks_run"] = len(ln.get("checks", []))
         badl = [c for c in ln.get("checks", []) if not c["ok"]]
@@ -579,12 +588,12 @@ def _apply_report(rep: dict, min_speedup: float) -> dict:
     ln = rep.get("layernorm_column_owner")
     if ln is None:
         ln = rep["layernorm_column_owner"] = {"ok": False, "error": "no verdict from the probe child"}
-    ln["enabled"] = bool(ln.get("ok")) and float(ln.get("speedup", 0.0)) >= 1.02
+    ln["enabled"] = bool(ln.get("ok")) and int(ln.get("mask", 0) or 0) != 0 and float(ln.get("speedup", 0.0)) >= 1.01
     gn = rep.get("groupnorm_reverse_apply")
     if gn is None:
         gn = rep["groupnorm_reverse_apply"] = {"ok": False, "error": "no verdict from the probe child"}
     gn["enabled"] = bool(gn.get("ok")) and float(gn.get("speedup", 0.0)) >= 1.01
-    lib.nk_norm_set_variant((1 if ln["enabled"] else 0) | (2 if gn["enabled"] else 0))
+    lib.nk_norm_set_variant((int(ln.get("mask", 0) or 0) & 5 if ln["enabled"] else 0) | (2 if gn["enabled"] else 0))
     pf = rep.get("epilogue_l2_prefetch")
     if pf is None:
         pf = rep["epilogue_l2_prefetch"] = {"ok": False, "error": "no verdict from the probe child"}
@@ -604,7 +613,8 @@ def autotune(device: int = 0, timeout_s: float = 240.0, min_speedup: float = 1.0
                 "min_k_iters": int(os.environ.get("NK_GEMM_DUAL_MIN_K", "0") or 0),
                 "skew": int(os.environ.get("NK_GEMM_DUAL_SKEW", "0") or 0),
                 "classes": int(os.environ.get("NK_GEMM_DUAL_CLASSES", "7") or 7), "source": "NK_GEMM_DUAL (pinned, no probe)",
-                "layernorm_column_owner": {"enabled": bool(nv & 1), "source": "NK_NORM_VARIANT (pinned with NK_GEMM_DUAL, no probe)"},
+                "layernorm_column_owner": {"enabled": bool(nv & 5), "mask": nv & 5,
+                                           "source": "NK_NORM_VARIANT (pinned with NK_GEMM_DUAL, no probe)"},
                 "groupnorm_reverse_apply": {"enabled": bool(nv & 2), "source": "NK_NORM_VARIANT (pinned with NK_GEMM_DUAL, no probe)"},
                 "epilogue_l2_prefetch": {"enabled": os.environ.get("NK_GEMM_EPI_PREFETCH", "0") not in ("", "0"),
                                          "mask": int(os.environ.get("NK_GEMM_EPI_PREFETCH", "0") or 0),

@@ -126,7 +126,7 @@ def test_step_guard_keeps_or_drops_variants_and_sets_the_library(monkeypatch):
 
     def tuned():
         return {"enabled": True, "mode": 1, "min_k_iters": 20, "skew": 3,
-                "layernorm_column_owner": {"enabled": True, "speedup": 1.3}, "epilogue_l2_prefetch": {"enabled": True, "speedup": 1.1, "mask": 1},
+                "layernorm_column_owner": {"enabled": True, "speedup": 1.3, "mask": 5}, "epilogue_l2_prefetch": {"enabled": True, "speedup": 1.1, "mask": 1},
                 "groupnorm_reverse_apply": {"enabled": True, "speedup": 1.05}}
 
     args = types.SimpleNamespace(config="sdxl", batch=16)
@@ -136,8 +136,8 @@ def test_step_guard_keeps_or_drops_variants_and_sets_the_library(monkeypatch):
     t = bench._step_guard(args, tuned(), 1, 0, None)
     assert t["enabled"] and t["layernorm_column_owner"]["enabled"] and t["step_guard"]["equal"]
     assert t["epilogue_l2_prefetch"]["enabled"] and lib.nk_gemm_set_epi_prefetch(-1) == 1 and bench.os.environ["NK_GEMM_EPI_PREFETCH"] == "1"
-    assert (lib.nk_gemm_set_dual(-1), lib.nk_gemm_set_dual_min_k(-1), lib.nk_gemm_set_dual_skew(-1), lib.nk_norm_set_variant(-1)) == (1, 20, 3, 3)
-    assert (bench.os.environ["NK_GEMM_DUAL"], bench.os.environ["NK_GEMM_DUAL_MIN_K"], bench.os.environ["NK_NORM_VARIANT"]) == ("1", "20", "3")
+    assert (lib.nk_gemm_set_dual(-1), lib.nk_gemm_set_dual_min_k(-1), lib.nk_gemm_set_dual_skew(-1), lib.nk_norm_set_variant(-1)) == (1, 20, 3, 7)
+    assert (bench.os.environ["NK_GEMM_DUAL"], bench.os.environ["NK_GEMM_DUAL_MIN_K"], bench.os.environ["NK_NORM_VARIANT"]) == ("1", "20", "7")
     # the GEMM stage passed and was flushed, then the LayerNorm stage took the child down
     first = json.dumps({"prefetch": {"equal": False}, "gemm": {"equal": True}})
     monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: Fake(first + "\n", rc=-6))
@@ -150,7 +150,7 @@ def test_step_guard_keeps_or_drops_variants_and_sets_the_library(monkeypatch):
     monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: Fake(bad + "\n"))
     t = bench._step_guard(args, tuned(), 1, 0, None)
     assert not t["enabled"] and t["layernorm_column_owner"]["enabled"] and lib.nk_gemm_set_dual(-1) == 0
-    assert not t["groupnorm_reverse_apply"]["enabled"] and lib.nk_norm_set_variant(-1) == 1  # no groupnorm verdict -> dropped
+    assert not t["groupnorm_reverse_apply"]["enabled"] and lib.nk_norm_set_variant(-1) == 5  # no groupnorm verdict -> dropped
     # no verdict at all
     monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: Fake("", rc=-9))
     t = bench._step_guard(args, tuned(), 1, 0, None)

@@ -82,26 +82,28 @@ def test_verdict_rules(monkeypatch):
             return "\n".join(json.dumps(r) for r in self.rep) + "\n", ""
     L = {"variant": "layernorm_column_owner", "checks": [], "timings": []}
     reps = [{**V, "ok": True, "skew": 0, "speedup": 1.05, "min_k_iters": 20, "checks": [], "timings": []},
-            {**L, "ok": True, "speedup": 1.4},
+            {**L, "ok": True, "speedup": 1.4, "mask": 5},
             {**V, "ok": True, "skew": 3, "speedup": 1.09, "min_k_iters": 10, "checks": [], "timings": []}]
     monkeypatch.setattr(subprocess, "Popen", lambda *a, **k: Multi(reps))
     got = tune.autotune()
     assert got["enabled"] and got["skew"] == 3 and lib.nk_gemm_set_dual_skew(-1) == 3 and lib.nk_gemm_set_dual_min_k(-1) == 10
     # the LayerNorm verdict is independent of the GEMM one
-    assert got["layernorm_column_owner"]["enabled"] and lib.nk_norm_set_variant(-1) == 1
+    assert got["layernorm_column_owner"]["enabled"] and lib.nk_norm_set_variant(-1) == 5
     json.dumps(tune._summary(got))
-    reps[1] = {**L, "ok": True, "speedup": 0.97}   # correct but slower: stays off
+    reps[1] = {**L, "ok": True, "speedup": 1.2, "mask": 4}   # only the backward form gained: only its bit is set
+    assert tune.autotune()["layernorm_column_owner"]["enabled"] and lib.nk_norm_set_variant(-1) == 4
+    reps[1] = {**L, "ok": True, "speedup": 1.0, "mask": 0}   # correct but neither kernel gained: stays off
     assert not tune.autotune()["layernorm_column_owner"]["enabled"] and lib.nk_norm_set_variant(-1) == 0
-    reps[1] = {**L, "ok": False, "speedup": 1.6}   # faster but wrong: stays off
+    reps[1] = {**L, "ok": False, "speedup": 1.6, "mask": 5}   # faster but wrong: stays off
     assert not tune.autotune()["layernorm_column_owner"]["enabled"] and lib.nk_norm_set_variant(-1) == 0
-    reps[1] = {**L, "ok": True, "speedup": 1.4}
+    reps[1] = {**L, "ok": True, "speedup": 1.4, "mask": 5}
     # GroupNorm reverse order: its bit is OR-ed into the norm mask
     reps.append({"variant": "groupnorm_reverse_apply", "ok": True, "speedup": 1.04, "checks": [], "timings": []})
     got = tune.autotune()
-    assert got["groupnorm_reverse_apply"]["enabled"] and lib.nk_norm_set_variant(-1) == 3
+    assert got["groupnorm_reverse_apply"]["enabled"] and lib.nk_norm_set_variant(-1) == 7
     reps.pop()
     got = tune.autotune()
-    assert not got["groupnorm_reverse_apply"]["enabled"] and lib.nk_norm_set_variant(-1) == 1
+    assert not got["groupnorm_reverse_apply"]["enabled"] and lib.nk_norm_set_variant(-1) == 5
     # third variant: the epilogue prefetch hint
     assert not got["epilogue_l2_prefetch"]["enabled"] and "no verdict" in got["epilogue_l2_prefetch"]["error"]
     reps.insert(2, {"variant": "epilogue_l2_prefetch", "ok": True, "speedup": 1.06, "mask": 1, "checks": [], "timings": []})
@@ -175,7 +177,7 @@ def test_verdict_cache_is_keyed_and_reused(monkeypatch, tmp_path):
     monkeypatch.delenv("NK_B200_TUNE", raising=False)
     V = {"variant": "gemm_row_tile_pairing", "checks": [], "timings": []}
     reps = [{**V, "ok": True, "skew": 0, "speedup": 1.07, "min_k_iters": 20}, {**V, "ok": True, "skew": 3, "speedup": 1.03, "min_k_iters": 20},
-            {"variant": "layernorm_column_owner", "ok": True, "speedup": 1.5, "checks": [], "timings": []}]
+            {"variant": "layernorm_column_owner", "ok": True, "speedup": 1.5, "mask": 5, "checks": [], "timings": []}]
 
     class Proc:
         def __init__(self, rows, rc=0):
@@ -193,7 +195,7 @@ def test_verdict_cache_is_keyed_and_reused(monkeypatch, tmp_path):
     lib.nk_norm_set_variant(0)
     second = tune.autotune()
     assert len(calls) == 1 and "cached" in second["source"] and second["enabled"] and second["min_k_iters"] == 20
-    assert lib.nk_gemm_set_dual(-1) == 1 and lib.nk_norm_set_variant(-1) == 1 and second["layernorm_column_owner"]["enabled"]
+    assert lib.nk_gemm_set_dual(-1) == 1 and lib.nk_norm_set_variant(-1) == 5 and second["layernorm_column_owner"]["enabled"]
     assert tune.cache_path("probe") != tune.cache_path("guard:sdxl:16")
     # an incomplete probe is not stored
     for f in tmp_path.glob("nk_b200_tune_*.json"):

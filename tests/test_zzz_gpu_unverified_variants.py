@@ -98,8 +98,8 @@ def test_autotune_verdict_is_consistent_and_leaves_a_working_library():
         assert rep["enabled"] == (bool(rep.get("ok")) and rep.get("min_k_iters") is not None and rep.get("speedup", 0) >= 1.01)
         assert lib.nk_gemm_set_dual_skew(-1) == (rep.get("skew", 0) if rep["enabled"] else 0)
         ln = rep["layernorm_column_owner"]
-        assert lib.nk_norm_set_variant(-1) == (1 if ln["enabled"] else 0) | (2 if rep["groupnorm_reverse_apply"]["enabled"] else 0)
-        assert ln["enabled"] == (bool(ln.get("ok")) and ln.get("speedup", 0) >= 1.02)
+        assert lib.nk_norm_set_variant(-1) == (ln.get("mask", 0) & 5 if ln["enabled"] else 0) | (2 if rep["groupnorm_reverse_apply"]["enabled"] else 0)
+        assert ln["enabled"] == (bool(ln.get("ok")) and ln.get("mask", 0) != 0 and ln.get("speedup", 0) >= 1.01)
         gam, bet = torch.ones(1280, device="cuda"), torch.zeros(1280, device="cuda")
         yn, _, _ = ops.layernorm_fwd(x, gam, bet, 1e-5)
         refn = torch.nn.functional.layer_norm(x.float(), (1280,))
