@@ -848,7 +848,9 @@ int nk_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float
     if ((norm_variant() & 1) && C <= LN2_MAXW * 256 && ldx % 8 == 0 && ldy % 8 == 0) {
         constexpr int RB = 8;
         const int warps = (C / 8 + 31) / 32;
-        const long long want = (static_cast<long long>(rows) + 148 * 8 - 1) / (148 * 8);
+        // one resident wave: 80 registers x 160 threads (C = 1280) -> 5 blocks per SM; fewer, longer blocks also amortise the
+        // per-block gamma / beta load over more rows
+        const long long want = (static_cast<long long>(rows) + 148 * 5 - 1) / (148 * 5);
         const int rpb = static_cast<int>(std::max<long long>(RB, (want + RB - 1) / RB * RB));
         const int blocks = (rows + rpb - 1) / rpb;
         ln_fwd_v2_kernel<RB><<<blocks, warps * 32, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, gamma,
@@ -888,7 +890,8 @@ int nk_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, c
     if ((norm_variant() & 4) && lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0) {
         constexpr int RB = 4;
         const int warps = (C / 8 + 31) / 32;
-        const long long want = (static_cast<long long>(rows) + 148 * 4 - 1) / (148 * 4);
+        // one resident wave: 127 registers x 160 threads -> 3 blocks per SM (and fewer blocks = fewer global reds at the end)
+        const long long want = (static_cast<long long>(rows) + 148 * 3 - 1) / (148 * 3);
         const int rpb = static_cast<int>(std::max<long long>(RB, (want + RB - 1) / RB * RB));
         const int blocks = (rows + rpb - 1) / rpb;
         ln_bwd_v2_kernel<RB><<<blocks, warps * 32, 0, st>>>(dyp, lddy, xp, ldx, static_cast<bf16*>(dx), lddx, gamma, mean, rstd,
