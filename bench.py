@@ -298,39 +298,55 @@ def _dist_setup():
     return world, rank, local, dev
 
 
+SUB_VARIANTS = ("layernorm_column_owner", "groupnorm_reverse_apply", "epilogue_l2_prefetch", "fused_cross_kv")
+# result key of the guard child -> (variant key or None for the GEMM pairing, flag inside the child's verdict)
+GUARD_STAGES = (("prefetch", "epilogue_l2_prefetch", "equal"), ("gemm", None, "equal"), ("groupnorm", "groupnorm_reverse_apply", "equal"),
+                ("cross_kv", "fused_cross_kv", "equal"), ("layernorm", "layernorm_column_owner", "agree"))
+
+
+def _variant_dicts(tuned: dict) -> list:
+    """[the GEMM pairing verdict (the top-level dict itself), then one dict per SUB_VARIANTS] — each carries `enabled`."""
+    return [tuned] + [tuned.setdefault(k, {"enabled": False}) for k in SUB_VARIANTS]
+
+
+def _any_variant(tuned: dict) -> bool:
+    return any(bool(d.get("enabled")) for d in _variant_dicts(tuned))
+
+
+def _drop(d: dict, why: str) -> None:
+    d["enabled"] = False
+    if "mode" in d:
+        d["mode"] = 0
+    d["note" if "mode" in d else "error"] = why
+
+
+def _agree_across_ranks(tuned: dict, world: int, dev, why: str) -> None:
+    """a variant is used only if every rank still has it enabled (MIN all-reduce of the flags; every rank calls this)."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    ds = _variant_dicts(tuned)
+    flag = torch.tensor([1 if d.get("enabled") else 0 for d in ds], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    for d, f in zip(ds, flag.tolist()):
+        if d.get("enabled") and not f:
+            _drop(d, why)
+
+
 def _autotune_unsafe(world: int, local: int, dev) -> dict:
     """kernel variants that are validated on the device before use (neurosis_b200.tune): every rank probes its own GPU in
     a child process; a variant is used only if ALL ranks accepted it.  The verdicts are exported to the child processes
-    of `run_other_configs` through NK_GEMM_DUAL* / NK_NORM_VARIANT (pinned there, no second probe)."""
-    import torch
-    import torch.distributed as dist
+    of `run_other_configs` through NK_GEMM_DUAL* / NK_NORM_VARIANT / ... (pinned there, no second probe)."""
     from neurosis_b200 import tune
-    from neurosis_b200._lib import lib
     rep = tune.autotune(local, timeout_s=min(240.0, max(60.0, wall_left() - 150.0)))
-    ln = rep.setdefault("layernorm_column_owner", {"enabled": False})
-    pf = rep.setdefault("epilogue_l2_prefetch", {"enabled": False})
-    gn = rep.setdefault("groupnorm_reverse_apply", {"enabled": False})
-    if world > 1:
-        flag = torch.tensor([1 if rep.get("enabled") else 0, 1 if ln.get("enabled") else 0, 1 if pf.get("enabled") else 0,
-                             1 if gn.get("enabled") else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if bool(gn.get("enabled")) != bool(flag[3].item()):
-            gn["enabled"] = False
-            gn["error"] = "another rank rejected the variant"
-        if bool(pf.get("enabled")) != bool(flag[2].item()):
-            pf["enabled"] = False
-            pf["error"] = "another rank rejected the variant"
-            lib.nk_gemm_set_epi_prefetch(0)
-        if bool(rep.get("enabled")) != bool(flag[0].item()):
-            rep["enabled"], rep["mode"] = False, 0
-            rep["note"] = "another rank rejected the variant"
-            tune.apply(0)
-        if bool(ln.get("enabled")) != bool(flag[1].item()):
-            ln["enabled"] = False
-            ln["error"] = "another rank rejected the variant"
-        lib.nk_norm_set_variant(_norm_mask(rep))
-    _export_tuned(rep)
-    return tune._summary(rep)
+    _agree_across_ranks(rep, world, dev, "another rank rejected the variant")
+    summ = tune._summary(rep)
+    for k in ("mode", "min_k_iters", "skew", "classes"):
+        if k in rep:
+            summ[k] = rep[k]
+    _apply_tuned(summ)
+    return summ
 
 
 def _autotune(world: int, local: int, dev) -> dict:
@@ -338,7 +354,7 @@ def _autotune(world: int, local: int, dev) -> dict:
     try:
         return _autotune_unsafe(world, local, dev)
     except Exception as e:  # noqa: BLE001
-        tuned = {"enabled": False, "mode": 0, "error": f"autotune failed: {e!r}", "layernorm_column_owner": {"enabled": False}}
+        tuned = {"enabled": False, "mode": 0, "error": f"autotune failed: {e!r}"}
         try:
             _apply_tuned(tuned)
         except Exception:  # noqa: BLE001
@@ -365,6 +381,7 @@ def _export_tuned(rep: dict) -> None:
     os.environ["NK_GEMM_DUAL_CLASSES"] = str(int(rep.get("classes", 7)) if on else 7)
     os.environ["NK_NORM_VARIANT"] = str(_norm_mask(rep))
     os.environ["NK_GEMM_EPI_PREFETCH"] = str(_prefetch_mask(rep))
+    os.environ["NK_FUSED_CROSS_KV"] = "1" if (rep.get("fused_cross_kv") or {}).get("enabled") else "0"
 
 
 def _apply_tuned(tuned: dict) -> None:
@@ -378,6 +395,8 @@ def _apply_tuned(tuned: dict) -> None:
     tune.apply(int(tuned.get("mode", 1)) if on else 0)
     lib.nk_norm_set_variant(_norm_mask(tuned))
     lib.nk_gemm_set_epi_prefetch(_prefetch_mask(tuned))
+    from neurosis_b200 import ops as _ops
+    _ops.FUSE_CROSS_KV = bool((tuned.get("fused_cross_kv") or {}).get("enabled"))
     _export_tuned(tuned)
 
 
@@ -419,19 +438,13 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
       stage 2, LayerNorm second form on top: same formulas in another reduction order, outputs agree to bf16 rounding (loss
         within 2e-3, gradient abs-sum within 1e-2).
     Under N > 1 a variant survives only if every rank's guard accepted it."""
-    import signal
-
-    import torch
-    import torch.distributed as dist
-    ln = tuned.setdefault("layernorm_column_owner", {"enabled": False})
-    pf = tuned.setdefault("epilogue_l2_prefetch", {"enabled": False})
-    gn = tuned.setdefault("groupnorm_reverse_apply", {"enabled": False})
+    _variant_dicts(tuned)  # (creates the missing verdict dicts)
     try:
         if os.environ.get("NK_BENCH_NO_STEP_GUARD"):
             # child of `run_other_configs`: the variants were guarded on the headline configuration by the parent, and a
             # child that fails with them is retried on the measured kernels — no nested guard process here
             tuned["note"] = "variants inherited from the parent run (guarded there); failure => retried without them"
-        elif tuned.get("enabled") or ln.get("enabled") or pf.get("enabled") or gn.get("enabled"):
+        elif _any_variant(tuned):
             env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")
                    and k not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "MASTER_PORT", "MASTER_ADDR")}
             env.update({"LOCAL_RANK": str(local), "NK_BENCH_EXTRAS": "0", "NK_B200_TUNE": "0"})
@@ -443,7 +456,7 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
             # (the driver starts the benchmark several times per box: 1 / 2 / 4 / 8 GPUs)
             gtag = "guard:" + ":".join([args.config, str(args.batch)] + [os.environ.get(k, "0") for k in (
                 "NK_GEMM_DUAL", "NK_GEMM_DUAL_MIN_K", "NK_GEMM_DUAL_SKEW", "NK_GEMM_DUAL_CLASSES", "NK_NORM_VARIANT",
-                "NK_GEMM_EPI_PREFETCH")])
+                "NK_GEMM_EPI_PREFETCH", "NK_FUSED_CROSS_KV")])
             cached = _tune.cache_load(gtag, local)
             if cached is not None:
                 res = cached
@@ -456,47 +469,22 @@ def _step_guard(args, tuned: dict, world: int, local: int, dev) -> dict:
             except Exception as e:  # noqa: BLE001
                 err = repr(e)
             wall = round(time.monotonic() - t0, 1)
-            g_ok = bool(res and (res.get("gemm") or {}).get("equal")) if tuned.get("enabled") else False
-            l_ok = bool(res and (res.get("layernorm") or {}).get("agree")) if ln.get("enabled") else False
-            if tuned.get("enabled"):
-                tuned["step_guard"] = dict((res or {}).get("gemm") or {"error": err}, wall_s=wall)
-                if not g_ok:
-                    tuned["enabled"], tuned["mode"] = False, 0
-                    tuned["note"] = "rejected by the step-level guard"
-            if ln.get("enabled"):
-                ln["step_guard"] = dict((res or {}).get("layernorm") or {"error": err}, wall_s=wall)
-                if not l_ok:
-                    ln["enabled"] = False
-                    ln["error"] = "rejected by the step-level guard"
-            if gn.get("enabled"):
-                gn["step_guard"] = dict((res or {}).get("groupnorm") or {"error": err}, wall_s=wall)
-                if not bool(res and (res.get("groupnorm") or {}).get("equal")):
-                    gn["enabled"] = False
-                    gn["error"] = "rejected by the step-level guard"
-            if pf.get("enabled"):
-                pf["step_guard"] = dict((res or {}).get("prefetch") or {"error": err}, wall_s=wall)
-                if not bool(res and (res.get("prefetch") or {}).get("equal")):
-                    pf["enabled"] = False
-                    pf["error"] = "rejected by the step-level guard"
+            for stage, key, flag in GUARD_STAGES:
+                d = tuned if key is None else tuned[key]
+                if not d.get("enabled"):
+                    continue
+                verdict = (res or {}).get(stage)
+                d["step_guard"] = dict(verdict or {"error": err or "the guard child ended before this stage"}, wall_s=wall)
+                if not (verdict and verdict.get(flag)):
+                    _drop(d, "rejected by the step-level guard")
     except Exception as e:  # noqa: BLE001  (a local failure must not make this rank skip the collective below)
-        tuned["enabled"], tuned["mode"], ln["enabled"], pf["enabled"], gn["enabled"] = False, 0, False, False, False
-        tuned["note"] = f"step guard failed: {e!r}"
+        for d in _variant_dicts(tuned):
+            _drop(d, f"step guard failed: {e!r}")
     try:
-        if world > 1:
-            flag = torch.tensor([1 if tuned.get("enabled") else 0, 1 if ln.get("enabled") else 0, 1 if pf.get("enabled") else 0,
-                                 1 if gn.get("enabled") else 0], device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if gn.get("enabled") and not bool(flag[3].item()):
-                gn["enabled"], gn["error"] = False, "another rank's step guard rejected the variant"
-            if pf.get("enabled") and not bool(flag[2].item()):
-                pf["enabled"], pf["error"] = False, "another rank's step guard rejected the variant"
-            if tuned.get("enabled") and not bool(flag[0].item()):
-                tuned["enabled"], tuned["mode"], tuned["note"] = False, 0, "another rank's step guard rejected the variant"
-            if ln.get("enabled") and not bool(flag[1].item()):
-                ln["enabled"], ln["error"] = False, "another rank's step guard rejected the variant"
+        _agree_across_ranks(tuned, world, dev, "another rank's step guard rejected the variant")
     except Exception as e:  # noqa: BLE001  (nothing here may cost the measurement: fall back to the measured kernels)
-        tuned["enabled"], tuned["mode"], ln["enabled"], pf["enabled"], gn["enabled"] = False, 0, False, False, False
-        tuned["note"] = f"step guard failed: {e!r}"
+        for d in _variant_dicts(tuned):
+            _drop(d, f"step guard failed: {e!r}")
     _apply_tuned(tuned)
     return tuned
 
@@ -519,6 +507,7 @@ def run_guard_child(args) -> None:
     tune.apply(0)
     lib.nk_norm_set_variant(0)
     lib.nk_gemm_set_epi_prefetch(0)
+    ops.FUSE_CROSS_KV = False
     eng = build_engine(dev, family=family)
     reducer = BucketedGradReducer([p for p in eng.model.parameters() if p.requires_grad], bucket_mb=256.0)
     reducer.attach_as_grad_sink()
@@ -578,6 +567,17 @@ def run_guard_child(args) -> None:
             ref = got
         else:
             gmode = 0
+    if os.environ.get("NK_FUSED_CROSS_KV", "0") not in ("", "0"):
+        # context k | v projections as one GEMM: the forward is bit-identical, the two weight gradients come from one split-K launch
+        ops.FUSE_CROSS_KV = True
+        gotx = step(gmode, 0)
+        okx = agree(ref, gotx, tl, tg)
+        out["cross_kv"] = {"loss_off": ref[0], "loss_on": gotx[0], "grad_abs_sum_off": ref[1], "grad_abs_sum_on": gotx[1], "equal": okx}
+        print(json.dumps(out), flush=True)
+        if okx:
+            ref = gotx
+        else:
+            ops.FUSE_CROSS_KV = False
     keep = 0
     if nmask & 2:  # GroupNorm second passes backwards: same blocks, other dispatch order — the step must be unchanged
         got3 = step(gmode, 2)
@@ -843,7 +843,8 @@ def run_other_configs(args, world: int, rank: int, budget_s: float, per_config_s
     out: dict = {}
     t_start = time.monotonic()
     base_port = int(os.environ.get("MASTER_PORT", "29500"))
-    variants_on = os.environ.get("NK_GEMM_DUAL", "0") not in ("", "0") or os.environ.get("NK_NORM_VARIANT", "0") not in ("", "0")
+    variants_on = any(os.environ.get(k, "0") not in ("", "0") for k in ("NK_GEMM_DUAL", "NK_NORM_VARIANT", "NK_GEMM_EPI_PREFETCH",
+                                                                       "NK_FUSED_CROSS_KV"))
     attempts = [(name, False) for name in OTHER_CONFIGS]
     while attempts:
         name, plain = attempts.pop(0)
@@ -859,7 +860,7 @@ def run_other_configs(args, world: int, rank: int, budget_s: float, per_config_s
         env["NK_BENCH_NO_STEP_GUARD"] = "1"
         if plain:  # second attempt of a configuration that failed with the tuned kernel variants: the measured kernels only
             env.update({"NK_GEMM_DUAL": "0", "NK_GEMM_DUAL_MIN_K": "0", "NK_GEMM_DUAL_SKEW": "0", "NK_GEMM_DUAL_CLASSES": "7",
-                        "NK_NORM_VARIANT": "0", "NK_GEMM_EPI_PREFETCH": "0"})
+                        "NK_NORM_VARIANT": "0", "NK_GEMM_EPI_PREFETCH": "0", "NK_FUSED_CROSS_KV": "0"})
         cmd = _child_cmd(name, args, world)
         t0 = time.monotonic()
         try:
@@ -1111,8 +1112,7 @@ def main() -> None:
                     fh.write(f"{ms:9.3f} ms  {n:5d}x  {f / ms / 1e9 if ms > 0 else 0:8.1f} TFLOP/s  {what} {dims}\n")
         prof_raw = (t_ms, fl, len(recs))
         del recs
-        if (tuned.get("enabled") or any((tuned.get(k) or {}).get("enabled") for k in (
-                "layernorm_column_owner", "groupnorm_reverse_apply", "epilogue_l2_prefetch"))) and not args.breakdown:
+        if _any_variant(tuned) and not args.breakdown:
             # the same per-launch timing with every tuned variant off: the roofline reported below is the one of the
             # kernels the headline is finally measured with (see the step-level A/B further down)
             _apply_tuned({"enabled": False, "mode": 0})
@@ -1180,8 +1180,7 @@ def main() -> None:
 
     sampler = ClockSampler(local) if rank == 0 else None
     graphed, step, ms_dev, ms_e2e, launches = measure()
-    any_variant = bool(tuned.get("enabled") or any((tuned.get(k) or {}).get("enabled") for k in (
-        "layernorm_column_owner", "groupnorm_reverse_apply", "epilogue_l2_prefetch")))
+    any_variant = _any_variant(tuned)
     if any_variant and graphed is not None:
         # A/B at step level, same process, same data: the step is captured and timed a second time with every variant off
         # (the kernels of DESIGN.md section 9).  The headline is the faster of the two; both are reported.  (`tuned` agrees

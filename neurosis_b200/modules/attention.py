@@ -110,6 +110,11 @@ class CrossAttention(nn.Module):
             return ops.linear(o, out.weight, out.bias, residual)
         context = x if context is None else ops.cast_bf16(context) if context.dtype != torch.bfloat16 else context
         q = ops.linear(x, self.to_q.weight).view(b, n, h, d)
+        if (ops.FUSE_CROSS_KV and context is not x and context.dim() == 3 and context.is_contiguous()
+                and self.to_k.weight.shape == self.to_v.weight.shape and d % 8 == 0):
+            # the two context projections as one GEMM (ops.CrossAttentionKVFn); off by default, see ops.FUSE_CROSS_KV
+            o = ops.cross_attention_kv(q, context, self.to_k.weight, self.to_v.weight, h, self.scale).view(b, n, h * d)
+            return ops.linear(o, out.weight, out.bias, residual)
         k = ops.linear(context, self.to_k.weight).view(b, context.shape[1], h, d)
         v = ops.linear(context, self.to_v.weight).view(b, context.shape[1], h, d)
         o = ops.attention(q, k, v, self.scale).view(b, n, h * d)

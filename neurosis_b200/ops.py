@@ -1410,6 +1410,84 @@ class SelfAttentionQKVFn(torch.autograd.Function):
         return dx, grads[0], grads[1], grads[2], None, None
 
 
+# Cross-attention with the k and v projections of the context as ONE GEMM (module switch; off until neurosis_b200.tune's step
+# guard has compared the training step with and without it on the device — written after the last GPU run)
+FUSE_CROSS_KV = _os.environ.get("NK_FUSED_CROSS_KV", "0") not in ("", "0")
+
+
+class CrossAttentionKVFn(torch.autograd.Function):
+    """o = attention(q, ctx Wk^T, ctx Wv^T) with the two context projections as ONE GEMM (N = 2*inner) in each direction:
+    forward ctx[M,C] @ [Wv;Wk]^T, weight gradient d[v|k]^T @ ctx (one launch into adjacent bucket slices, like the fused
+    q|k|v of self-attention), data gradient d[v|k] @ [Wv;Wk] only if the context needs one (it is an input of the step).
+    The 77-token context gives M = 77*B rows: 25 output tiles per separate projection on 74 CTA pairs — half as many,
+    twice as wide launches (reference modules/attention.py:283-290, 346-352: to_k / to_v of CrossAttention)."""
+
+    @staticmethod
+    def forward(ctx, q, context, wk, wv, heads, scale):
+        B, Nk, _ = context.shape
+        inner = wk.shape[0]
+        D = inner // heads
+        wf = bf16_weight_group((wv, wk))
+        vk = linear_fwd(context, wf).view(B, Nk, 2, heads, D)
+        v, k = vk[:, :, 0], vk[:, :, 1]
+        o, lse = attention_fwd(q, k, v, scale)
+        ctx.save_for_backward(q, context, vk, o, lse, wk, wv)
+        ctx.scale = scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, context, vk, o, lse, wk, wv = ctx.saved_tensors
+        B, Nk, _, H, D = vk.shape
+        inner = H * D
+        v, k = vk[:, :, 0], vk[:, :, 1]
+        if do.dtype != BF16:
+            do = cast_bf16(do)
+        dvk = torch.empty_like(vk)
+        dq = torch.empty(q.shape, dtype=BF16, device=q.device)
+        outs = (dq, dvk[:, :, 1], dvk[:, :, 0])
+        res = attention_bwd(do.reshape(q.shape), q, k, v, o, lse, ctx.scale, out=outs)
+        for r_, o_ in zip(res, outs):  # the materialised fallback returns fresh tensors
+            if r_.data_ptr() != o_.data_ptr():
+                o_.copy_(r_)
+        d2 = dvk.view(B * Nk, 2 * inner)
+        wf = bf16_weight_group((wv, wk))
+        dctx = linear_dgrad(d2, wf).view(context.shape) if ctx.needs_input_grad[1] else None
+        grads = [None, None]  # for wk, wv
+        need = ctx.needs_input_grad[2:4]
+        sinks = [_grad_sink(w) for w in (wv, wk)]
+        c2 = context.reshape(B * Nk, -1)
+        stacked = all(need) and all(b is not None for b, _ in sinks) and (
+            sinks[0][0].data_ptr() + sinks[0][0].numel() * 4 == sinks[1][0].data_ptr()
+            and sinks[0][0].untyped_storage().data_ptr() == sinks[1][0].untyped_storage().data_ptr())
+        if stacked:  # [dWv; dWk] is one contiguous [2*inner, C] block of a gradient bucket
+            bases = tuple(b for _, b in sinks)
+            buf = torch.as_strided(sinks[0][0], (2 * inner, c2.shape[1]), (c2.shape[1], 1))
+            if WGRAD_OVERLAP:
+                _fork_wgrad(lambda: linear_wgrad(d2, c2, out=buf), (d2, c2), bases)
+            else:
+                linear_wgrad(d2, c2, out=buf)
+                for b in bases:
+                    GRAD_SINK.mark_ready(b)
+        else:
+            for slot, (w, col) in enumerate(((wk, 1), (wv, 0))):
+                if not need[slot]:
+                    continue
+                dy = d2[:, col * inner: (col + 1) * inner]
+                buf, base = _grad_sink(w)
+                if buf is not None:
+                    linear_wgrad(dy, c2, out=buf)
+                    GRAD_SINK.mark_ready(base)
+                else:
+                    grads[slot] = linear_wgrad(dy, c2)
+        return dq, dctx, grads[0], grads[1], None, None
+
+
+def cross_attention_kv(q: Tensor, context: Tensor, wk: Tensor, wv: Tensor, heads: int, scale: float) -> Tensor:
+    """q (B, Nq, H, D) bf16, context (B, Nk, C) bf16 -> o (B, Nq, H, D): fused k|v projection of the context + attention."""
+    return CrossAttentionKVFn.apply(q, context, wk, wv, heads, float(scale))
+
+
 def self_attention_qkv(x: Tensor, wq: Tensor, wk: Tensor, wv: Tensor, heads: int, scale: float) -> Tensor:
     """fused q/k/v projection + attention for self-attention with head_dim <= 64 (multiple of 8); returns (B, N, inner)."""
     return SelfAttentionQKVFn.apply(x, wq, wk, wv, heads, float(scale))

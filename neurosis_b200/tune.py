@@ -1,6 +1,6 @@
 """Run-time selection of kernel variants, gated by an on-device comparison with the measured kernels.
 
-Four variants: the second form of the LayerNorm kernels (`probe_layernorm`, norm.cu, `nk_norm_set_variant` bit 0), GroupNorm's
+Five variants: the context projections of cross-attention as one GEMM (`probe_cross_kv`, `ops.FUSE_CROSS_KV`), the second form of the LayerNorm kernels (`probe_layernorm`, norm.cu, `nk_norm_set_variant` bit 0), GroupNorm's
 second passes walking their grid backwards for L2 reuse (`probe_groupnorm_reverse`, bit 1), an L2 prefetch of
 the GEMM epilogue's side input (`probe_epilogue_prefetch`, `nk_gemm_set_epi_prefetch`) and ROW-TILE PAIRING of the tensor-core GEMM / implicit-GEMM convolution kernel (`gemm_tc_kernel<.., DUAL>`,
 csrc/gemm_tc.cu): a CTA owns two 128-row tiles that share one B tile, which cuts the operand bytes per FLOP that cross
@@ -488,6 +488,68 @@ def probe_groupnorm_reverse(device: int = 0, timed: bool = True) -> dict:
     return rep
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# cross-attention: k and v projections of the context as one GEMM (ops.CrossAttentionKVFn, ops.FUSE_CROSS_KV)
+# ---------------------------------------------------------------------------------------------------------------------
+XKV_CASES = [(16, 1024, 1280, 2048, 20, 60), (16, 4096, 640, 2048, 10, 10)]   # (B, Nq, dim, context dim, heads, blocks per SDXL step)
+
+
+def probe_cross_kv(device: int = 0, timed: bool = True) -> dict:
+    """`CrossAttention` forward + backward with the context projections separate and fused: outputs and dx bit-identical
+    (the stacked GEMM accumulates every k / v element over the same K order), weight gradients to split-K rounding."""
+    import torch
+
+    from . import ops
+    from .modules.attention import CrossAttention
+    torch.cuda.set_device(device)
+    dev = torch.device("cuda", device)
+    gen = torch.Generator(device=dev).manual_seed(31)
+    rep = {"variant": "fused_cross_kv", "checks": [], "timings": [], "ok": True}
+    prev = ops.FUSE_CROSS_KV
+    try:
+        t_off = t_on = 0.0
+        for B, Nq, dim, cdim, heads, weight in [(2, 200, 320, 96, 5, 0), (3, 64, 640, 768, 8, 0)] + XKV_CASES:
+            mod = CrossAttention(query_dim=dim, context_dim=cdim, heads=heads, dim_head=dim // heads).to(dev)
+            x = (torch.randn(B, Nq, dim, generator=gen, device=dev)).to(torch.bfloat16).requires_grad_(True)
+            c = torch.randn(B, 77, cdim, generator=gen, device=dev).to(torch.bfloat16)
+            go = (torch.randn(B, Nq, dim, generator=gen, device=dev) * 0.1).to(torch.bfloat16)
+
+            def run():
+                for p_ in mod.parameters():
+                    p_.grad = None
+                x.grad = None
+                y = mod(x, c)
+                y.backward(go)
+                return y.detach(), x.grad, mod.to_k.weight.grad, mod.to_v.weight.grad
+
+            ops.FUSE_CROSS_KV = False
+            a = [t.clone() for t in run()]
+            ops.FUSE_CROSS_KV = True
+            b = [t.clone() for t in run()]
+            torch.cuda.synchronize()
+            e = {"y": _rel(b[0], a[0]), "dx": _rel(b[1], a[1]), "dWk": _rel(b[2], a[2]), "dWv": _rel(b[3], a[3])}
+            # (dx passes through the attention backward, whose dq accumulation uses atomics: run-to-run noise, not equality)
+            ok = bool(torch.equal(b[0], a[0]) and e["dx"] < 2e-2 and e["dWk"] < 2e-2 and e["dWv"] < 2e-2
+                      and all(bool(torch.isfinite(t.float()).all()) for t in b))
+            rep["checks"].append({"case": [B, Nq, dim, cdim, heads], "ok": ok, **{k_: float(f"{v_:.3e}") for k_, v_ in e.items()}})
+            rep["ok"] = rep["ok"] and ok
+            if timed and weight and rep["ok"]:
+                row = {"case": [B, Nq, dim, cdim, heads], "blocks_per_step": weight}
+                for name, flag in (("off", False), ("on", True)):
+                    ops.FUSE_CROSS_KV = flag
+                    row[f"ms_{name}"] = min(_time(run, 6), _time(run, 6))
+                rep["timings"].append(row)
+                t_off += weight * row["ms_off"]
+                t_on += weight * row["ms_on"]
+            del mod, x, c, go
+        if timed and rep["ok"]:
+            rep["step_ms_off"], rep["step_ms_on"] = t_off, t_on
+            rep["speedup"] = t_off / t_on if t_on > 0 else 0.0
+    finally:
+        ops.FUSE_CROSS_KV = prev
+    return rep
+
+
 def _summary(rep: dict, max_timings: int = 6) -> dict:
     """what bench.py prints: verdict, weighted times, the failed checks and the largest movers."""
     out = {k: rep[k] for k in ("variant", "ok", "step_ms_unpaired", "step_ms_paired", "speedup", "error", "enabled", "mode",
@@ -510,6 +572,14 @@ def _summary(rep: dict, max_timings: int = 6) -> dict:
         out["groupnorm_reverse_apply"]["checks_run"] = len(gn.get("checks", []))
         if gn.get("timings"):
             out["groupnorm_reverse_apply"]["timings"] = gn["timings"]
+    xk = rep.get("fused_cross_kv")
+    if xk is not None:
+        out["fused_cross_kv"] = {k: xk[k] for k in ("ok", "enabled", "speedup", "step_ms_off", "step_ms_on", "error", "source",
+                                                    "step_guard", "timings") if k in xk}
+        out["fused_cross_kv"]["checks_run"] = len(xk.get("checks", []))
+        badx = [c for c in xk.get("checks", []) if not c["ok"]]
+        if badx:
+            out["fused_cross_kv"]["failed_checks"] = badx[:4]
     pf = rep.get("epilogue_l2_prefetch")
     if pf is not None:
         out["epilogue_l2_prefetch"] = {k: pf[k] for k in ("ok", "enabled", "mask", "speedup", "step_ms_off", "step_ms_on", "error", "source",
@@ -597,6 +667,12 @@ def _apply_report(rep: dict, min_speedup: float) -> dict:
     pf = rep.get("epilogue_l2_prefetch")
     if pf is None:
         pf = rep["epilogue_l2_prefetch"] = {"ok": False, "error": "no verdict from the probe child"}
+    xk = rep.get("fused_cross_kv")
+    if xk is None:
+        xk = rep["fused_cross_kv"] = {"ok": False, "error": "no verdict from the probe child"}
+    xk["enabled"] = bool(xk.get("ok")) and float(xk.get("speedup", 0.0)) >= 1.01
+    from . import ops as _ops
+    _ops.FUSE_CROSS_KV = bool(xk["enabled"])
     pf["enabled"] = bool(pf.get("ok")) and int(pf.get("mask", 0) or 0) != 0 and float(pf.get("speedup", 0.0)) >= 1.005
     lib.nk_gemm_set_epi_prefetch(int(pf.get("mask", 0) or 0) if pf["enabled"] else 0)
     return rep
@@ -616,6 +692,8 @@ def autotune(device: int = 0, timeout_s: float = 240.0, min_speedup: float = 1.0
                 "layernorm_column_owner": {"enabled": bool(nv & 5), "mask": nv & 5,
                                            "source": "NK_NORM_VARIANT (pinned with NK_GEMM_DUAL, no probe)"},
                 "groupnorm_reverse_apply": {"enabled": bool(nv & 2), "source": "NK_NORM_VARIANT (pinned with NK_GEMM_DUAL, no probe)"},
+                "fused_cross_kv": {"enabled": os.environ.get("NK_FUSED_CROSS_KV", "0") not in ("", "0"),
+                                   "source": "NK_FUSED_CROSS_KV (pinned with NK_GEMM_DUAL, no probe)"},
                 "epilogue_l2_prefetch": {"enabled": os.environ.get("NK_GEMM_EPI_PREFETCH", "0") not in ("", "0"),
                                          "mask": int(os.environ.get("NK_GEMM_EPI_PREFETCH", "0") or 0),
                                          "source": "NK_GEMM_EPI_PREFETCH (pinned with NK_GEMM_DUAL, no probe)"}}
@@ -625,7 +703,7 @@ def autotune(device: int = 0, timeout_s: float = 240.0, min_speedup: float = 1.0
     if cached is not None and cached.get("variant") == "gemm_row_tile_pairing":
         cached = _apply_report(cached, min_speedup)
         src = f"cached verdict of an on-device probe on this machine with this library build ({cached.pop('_cache', '')})"
-        for k in (None, "layernorm_column_owner", "groupnorm_reverse_apply", "epilogue_l2_prefetch"):
+        for k in (None, "layernorm_column_owner", "groupnorm_reverse_apply", "epilogue_l2_prefetch", "fused_cross_kv"):
             (cached if k is None else cached[k])["source"] = src
         cached["probe_wall_s"] = 0.0
         return cached
@@ -655,6 +733,7 @@ def autotune(device: int = 0, timeout_s: float = 240.0, min_speedup: float = 1.0
         ln_reps = [c for c in cands if c.get("variant") == "layernorm_column_owner"]
         pf_reps = [c for c in cands if c.get("variant") == "epilogue_l2_prefetch"]
         gn_reps = [c for c in cands if c.get("variant") == "groupnorm_reverse_apply"]
+        xk_reps = [c for c in cands if c.get("variant") == "fused_cross_kv"]
         cands = [c for c in cands if c.get("variant") == "gemm_row_tile_pairing"]
         good = [c for c in cands if c.get("ok") and c.get("min_k_iters") is not None]
         if good:  # the fastest candidate that reproduced the unpaired kernels
@@ -670,6 +749,8 @@ def autotune(device: int = 0, timeout_s: float = 240.0, min_speedup: float = 1.0
             rep["epilogue_l2_prefetch"] = pf_reps[-1]
         if gn_reps:
             rep["groupnorm_reverse_apply"] = gn_reps[-1]
+        if xk_reps:
+            rep["fused_cross_kv"] = xk_reps[-1]
         if len(cands) < len(SKEWS) or proc.returncode not in (0, 1):
             rep.setdefault("note", f"probe child ended early (exit {proc.returncode}) after {len(cands)} of {len(SKEWS)} candidates: "
                            + " | ".join((se or "").strip().splitlines()[-2:])[-300:])
@@ -680,7 +761,7 @@ def autotune(device: int = 0, timeout_s: float = 240.0, min_speedup: float = 1.0
     rep["probe_wall_s"] = round(time.monotonic() - t0, 1)
     complete = "error" not in rep and len(rep.get("candidates", [])) == len(SKEWS)
     rep = _apply_report(rep, min_speedup)
-    for k in (None, "layernorm_column_owner", "groupnorm_reverse_apply", "epilogue_l2_prefetch"):
+    for k in (None, "layernorm_column_owner", "groupnorm_reverse_apply", "epilogue_l2_prefetch", "fused_cross_kv"):
         (rep if k is None else rep[k])["source"] = "on-device probe (child process)"
     if complete:  # only a probe that ran to its end is worth remembering
         cache_store("probe", rep, device)
@@ -715,7 +796,9 @@ def main(argv: Optional[list] = None) -> int:
                 print(json.dumps(pf), flush=True)
                 gn = probe_groupnorm_reverse(a.device, timed=not a.no_timing)
                 print(json.dumps(gn), flush=True)
-                ok = ok and ln["ok"] and pf["ok"] and gn["ok"]
+                xk = probe_cross_kv(a.device, timed=not a.no_timing)
+                print(json.dumps(xk), flush=True)
+                ok = ok and ln["ok"] and pf["ok"] and gn["ok"] and xk["ok"]
         return 0 if ok else 1
     print(json.dumps(_summary(autotune(a.device))), flush=True)
     return 0

@@ -127,15 +127,17 @@ def test_step_guard_keeps_or_drops_variants_and_sets_the_library(monkeypatch):
     def tuned():
         return {"enabled": True, "mode": 1, "min_k_iters": 20, "skew": 3,
                 "layernorm_column_owner": {"enabled": True, "speedup": 1.3, "mask": 5}, "epilogue_l2_prefetch": {"enabled": True, "speedup": 1.1, "mask": 1},
-                "groupnorm_reverse_apply": {"enabled": True, "speedup": 1.05}}
+                "groupnorm_reverse_apply": {"enabled": True, "speedup": 1.05}, "fused_cross_kv": {"enabled": True, "speedup": 1.2}}
 
     args = types.SimpleNamespace(config="sdxl", batch=16)
-    both = json.dumps({"prefetch": {"equal": True}, "groupnorm": {"equal": True}, "gemm": {"equal": True, "loss_unpaired": 1.0, "loss_paired": 1.0},
+    both = json.dumps({"prefetch": {"equal": True}, "groupnorm": {"equal": True}, "cross_kv": {"equal": True}, "gemm": {"equal": True, "loss_unpaired": 1.0, "loss_paired": 1.0},
                        "layernorm": {"agree": True, "loss_old": 1.0, "loss_new": 1.0005}})
     monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: Fake("warm\n" + both + "\n"))
     t = bench._step_guard(args, tuned(), 1, 0, None)
     assert t["enabled"] and t["layernorm_column_owner"]["enabled"] and t["step_guard"]["equal"]
     assert t["epilogue_l2_prefetch"]["enabled"] and lib.nk_gemm_set_epi_prefetch(-1) == 1 and bench.os.environ["NK_GEMM_EPI_PREFETCH"] == "1"
+    from neurosis_b200 import ops
+    assert t["fused_cross_kv"]["enabled"] and ops.FUSE_CROSS_KV is True and bench.os.environ["NK_FUSED_CROSS_KV"] == "1"
     assert (lib.nk_gemm_set_dual(-1), lib.nk_gemm_set_dual_min_k(-1), lib.nk_gemm_set_dual_skew(-1), lib.nk_norm_set_variant(-1)) == (1, 20, 3, 7)
     assert (bench.os.environ["NK_GEMM_DUAL"], bench.os.environ["NK_GEMM_DUAL_MIN_K"], bench.os.environ["NK_NORM_VARIANT"]) == ("1", "20", "7")
     # the GEMM stage passed and was flushed, then the LayerNorm stage took the child down
@@ -144,6 +146,7 @@ def test_step_guard_keeps_or_drops_variants_and_sets_the_library(monkeypatch):
     t = bench._step_guard(args, tuned(), 1, 0, None)
     assert t["enabled"] and not t["layernorm_column_owner"]["enabled"] and not t["epilogue_l2_prefetch"]["enabled"]
     assert lib.nk_gemm_set_epi_prefetch(-1) == 0 and bench.os.environ["NK_GEMM_EPI_PREFETCH"] == "0"
+    assert not t["fused_cross_kv"]["enabled"] and ops.FUSE_CROSS_KV is False and "exit -6" in t["fused_cross_kv"]["step_guard"]["error"]
     assert (lib.nk_gemm_set_dual(-1), lib.nk_norm_set_variant(-1), bench.os.environ["NK_NORM_VARIANT"]) == (1, 0, "0")
     # the step disagrees with pairing on
     bad = json.dumps({"gemm": {"equal": False, "loss_unpaired": 1.0, "loss_paired": 1.7}, "layernorm": {"agree": True}})
@@ -160,7 +163,9 @@ def test_step_guard_keeps_or_drops_variants_and_sets_the_library(monkeypatch):
     monkeypatch.setattr(bench.subprocess, "Popen", lambda *a, **k: (_ for _ in ()).throw(AssertionError("no child expected")))
     t = bench._step_guard(args, {"enabled": False, "layernorm_column_owner": {"enabled": False}}, 1, 0, None)
     assert not t["enabled"]
-    for k in ("NK_GEMM_DUAL", "NK_GEMM_DUAL_MIN_K", "NK_GEMM_DUAL_SKEW", "NK_NORM_VARIANT", "NK_GEMM_EPI_PREFETCH"):
+    ops.FUSE_CROSS_KV = False
+    for k in ("NK_GEMM_DUAL", "NK_GEMM_DUAL_MIN_K", "NK_GEMM_DUAL_SKEW", "NK_GEMM_DUAL_CLASSES", "NK_NORM_VARIANT", "NK_GEMM_EPI_PREFETCH",
+              "NK_FUSED_CROSS_KV"):
         bench.os.environ.pop(k, None)
     lib.nk_gemm_set_dual_min_k(0)
     lib.nk_gemm_set_dual_skew(0)

@@ -72,6 +72,18 @@ def test_groupnorm_reverse_apply_order_changes_nothing_beyond_atomic_noise():
     assert len(reps[0]["checks"]) >= 14
 
 
+@pytest.mark.xfail(strict=False, reason="fused k|v projection of the cross-attention context: first run on hardware")
+def test_cross_attention_with_fused_context_projections_matches_the_separate_ones():
+    """ops.CrossAttentionKVFn (one [Wv;Wk] GEMM forward, one stacked weight-gradient GEMM backward) against the two separate
+    projections through the `CrossAttention` module: output bit-identical, dx / dWk / dWv to the attention backward's own
+    atomic noise; head dims 64 (flash path) and 80 (materialised path)."""
+    reps = [r for r in _probe("--no-timing") if r["variant"] == "fused_cross_kv"]
+    assert len(reps) == 1
+    bad = [c for c in reps[0]["checks"] if not c["ok"]]
+    assert reps[0]["ok"] and not bad, bad[:4]
+    assert len(reps[0]["checks"]) >= 4
+
+
 @pytest.mark.xfail(strict=False, reason="L2 prefetch of the GEMM epilogue's side input: first run on hardware")
 def test_epilogue_side_input_prefetch_does_not_change_results():
     """`cp.async.bulk.prefetch.tensor.L2` of the residual / GEGLU-h boxes at tile start (nk_gemm_set_epi_prefetch): the GEGLU
@@ -116,6 +128,7 @@ def test_autotune_verdict_is_consistent_and_leaves_a_working_library():
         lib.nk_gemm_set_dual_skew(0)
         lib.nk_norm_set_variant(0)
         lib.nk_gemm_set_epi_prefetch(0)
+        ops.FUSE_CROSS_KV = False
 
 
 # ---------------------------------------------------------------- error budget next to the reference's own bf16 path
