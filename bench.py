@@ -828,7 +828,8 @@ OTHER_CONFIGS = ("sd15", "buckets", "vae")  # BASELINE.json configs[1] / [3] / [
 
 
 def _child_cmd(name: str, args, world: int) -> list:
-    return [sys.executable, str(ROOT / "bench.py"), "--config", name, "--gpus", str(world), "--steps", str(args.steps),
+    # (secondary measurements: at most 10 timed steps each, so that a long headline run leaves them room in the wall-clock target)
+    return [sys.executable, str(ROOT / "bench.py"), "--config", name, "--gpus", str(world), "--steps", str(min(int(args.steps), 10)),
             "--warmup", str(args.warmup), "--no-cpu-baseline", "--no-profile"]
 
 
