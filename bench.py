@@ -27,7 +27,7 @@ sys.path.insert(0, str(ROOT))
 T_START = time.monotonic()
 # wall-clock target of one default invocation ("finishes within minutes"): the optional parts (step guard of the tuned kernel
 # variants, secondary configurations) only get what the mandatory parts leave of it
-WALL_TARGET_S = float(os.environ.get("NK_BENCH_WALL_S", "285"))
+WALL_TARGET_S = float(os.environ.get("NK_BENCH_WALL_S", "300"))
 
 
 def wall_left() -> float:
