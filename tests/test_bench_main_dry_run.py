@@ -181,3 +181,21 @@ def test_variants_that_win_the_step_are_kept_for_the_headline_and_the_children(d
 def test_secondary_configurations_can_be_switched_off(dry, monkeypatch, capsys):
     line = _run(monkeypatch, capsys, ["--steps", "1", "--warmup", "1", "--other-configs", "none", "--no-cpu-baseline"])
     assert "other_configs" not in line and "cpu_baseline" not in line
+
+
+def test_guard_child_reports_every_stage(dry, monkeypatch, capsys):
+    """`bench.py --guard-child` (the sacrificial process of the step guard) with every variant pinned on: one verdict per stage,
+    flushed progressively, the last line carrying all of them plus the baseline repeat and the tolerances in use."""
+    from neurosis_b200 import ops
+    for k, v in (("NK_GEMM_DUAL", "1"), ("NK_GEMM_DUAL_MIN_K", "20"), ("NK_NORM_VARIANT", "7"), ("NK_GEMM_EPI_PREFETCH", "3"),
+                 ("NK_FUSED_CROSS_KV", "1")):
+        monkeypatch.setenv(k, v)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--guard-child", "--config", "sdxl", "--batch", "2"])
+    bench.main()
+    lines = [json.loads(ln) for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    last = lines[-1]
+    assert {"baseline_repeat", "tolerance", "prefetch", "gemm", "cross_kv", "groupnorm", "layernorm"} <= set(last)
+    assert last["prefetch"]["equal"] and last["gemm"]["equal"] and last["cross_kv"]["equal"] and last["groupnorm"]["equal"]
+    assert last["layernorm"]["agree"] and last["tolerance"]["loss"] >= 5e-4
+    assert len(lines) >= 5 and "gemm" not in lines[0]          # progressive: the first flushed line only has the first stage
+    assert ops.FUSE_CROSS_KV is True                            # (state of the child process after its last stage)
