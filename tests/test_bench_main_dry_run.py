@@ -47,6 +47,7 @@ class _Graphed:
     def __init__(self, eng, reducer, image, ctx, vec, warmup=1, optimizer=None, ema=None, pool=None):
         _Graphed.made += 1
         self.loss = torch.tensor(0.25)
+        self.pool = pool or (0, _Graphed.made)
 
     def step(self, image=None, crossattn=None, vector=None, weights=None):
         from neurosis_b200._lib import lib
@@ -199,3 +200,65 @@ def test_guard_child_reports_every_stage(dry, monkeypatch, capsys):
     assert last["layernorm"]["agree"] and last["tolerance"]["loss"] >= 5e-4
     assert len(lines) >= 5 and "gemm" not in lines[0]          # progressive: the first flushed line only has the first stage
     assert ops.FUSE_CROSS_KV is True                            # (state of the child process after its last stage)
+
+
+class _Stream:
+    def __init__(self, device=None):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+
+class _CUDAGraph:
+    def replay(self):
+        pass
+
+    def pool(self):
+        return (0, 0)
+
+
+@pytest.fixture
+def dry_streams(dry, monkeypatch):
+    import contextlib
+    monkeypatch.setattr(torch.cuda, "Stream", _Stream)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", _CUDAGraph)
+    monkeypatch.setattr(torch.cuda, "graph", lambda g, pool=None: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "max_memory_allocated", lambda *a, **k: 0)
+    yield
+
+
+def test_bucket_configuration_dry_run(dry_streams, monkeypatch, capsys):
+    """--config buckets (BASELINE.json configs[3]): one captured step per aspect bucket, per-step tag-frequency weights,
+    the square-only comparison that EVERY rank must run — control flow and the shape of its line."""
+    line = _run(monkeypatch, capsys, ["--config", "buckets", "--steps", "2", "--warmup", "1", "--batch", "1"])
+    assert line["metric"] == bench.CONFIGS["buckets"]["metric"] and line["n_gpus"] == 1 and line["steps"] == 2
+    assert _Graphed.made == len(line["config"]["buckets_wh"]) == 3
+    assert line["config"]["square_only_ms_per_step"] is not None and "tuned_variants" in line["config"]
+    assert len(line["config"]["buckets_drawn_rank0"]) == 2 and line["e2e"]["d2h_bytes_per_step"] == 4
+
+
+def test_vae_configuration_dry_run(dry_streams, monkeypatch, capsys):
+    """--config vae (BASELINE.json configs[4]) with a toy autoencoder: eager warm-up on a side stream, capture, the three
+    timed regions (resident, host batches, encode only)."""
+    from neurosis_b200.modules import vae
+
+    class ToyAE(torch.nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(3))
+
+        def training_step(self, batch):
+            return (batch["image"].mean(dim=(2, 3)) * self.w).pow(2).mean()
+
+        def encode(self, x):
+            return x[:, :, ::8, ::8]
+
+    monkeypatch.setattr(vae, "AutoencoderKL", ToyAE)
+    monkeypatch.setitem(bench.CONFIGS["vae"], "px", 64)
+    line = _run(monkeypatch, capsys, ["--config", "vae", "--steps", "2", "--warmup", "1", "--batch", "2"])
+    assert line["metric"] == bench.CONFIGS["vae"]["metric"] and line["config"]["cuda_graph"] is True
+    assert line["config"]["encode_images_per_s"] > 0 and "tuned_variants" in line["config"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 2 * 3 * 64 * 64 * 4
