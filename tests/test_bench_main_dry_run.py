@@ -262,3 +262,30 @@ def test_vae_configuration_dry_run(dry_streams, monkeypatch, capsys):
     assert line["metric"] == bench.CONFIGS["vae"]["metric"] and line["config"]["cuda_graph"] is True
     assert line["config"]["encode_images_per_s"] > 0 and "tuned_variants" in line["config"]
     assert line["e2e"]["h2d_bytes_per_step"] == 2 * 3 * 64 * 64 * 4
+
+
+@pytest.mark.parametrize("mode", ["plain", "variants"])
+def test_two_rank_dry_run_under_torchrun(mode):
+    """the default invocation as the driver launches it for N = 2 (torch.distributed.run, one process per rank), on the CPU
+    with gloo: the agreement collectives, the A/B decision (identical on both ranks), the children, the final barrier and
+    the exit — exactly one JSON line, printed by rank 0.  'variants': rank 1 rejected one variant, so both ranks drop it."""
+    import subprocess
+    helper = Path(__file__).resolve().parent / "helpers" / "bench_dry_rank.py"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29677" if mode == "plain" else "29679", str(helper), mode],
+                       capture_output=True, text=True, timeout=400)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{"metric"')]
+    assert len(lines) == 1, r.stdout[-2000:]
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["config"]["global_batch"] == 2 * line["config"]["batch_per_gpu"]
+    assert "cpu_baseline" not in line  # N = 1 only
+    assert {k for k in line["other_configs"] if not k.startswith("_")} == set(bench.OTHER_CONFIGS)
+    assert all(line["other_configs"][k]["n_gpus"] == 2 for k in bench.OTHER_CONFIGS)
+    tv = line["config"]["tuned_variants"]
+    if mode == "plain":
+        assert tv["enabled"] is False
+    else:
+        assert tv["enabled"] is True and tv["layernorm_column_owner"]["enabled"] is False
+        assert tv["step_ab"]["headline_uses_variants"] is True
+        assert all(line["other_configs"][k]["workload"] == "1" for k in bench.OTHER_CONFIGS)  # children inherit NK_GEMM_DUAL=1
