@@ -157,7 +157,8 @@ def pick_min_k(rows: list, tol: float = 1.02) -> Optional[int]:
 
 
 def _rel(a, b) -> float:
-    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20))
+    a, b = a.detach().float(), b.detach().float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
 
 
 def _time(fn, iters: int) -> float:
@@ -276,8 +277,7 @@ def probe_layernorm(device: int = 0, timed: bool = True) -> dict:
     rep = {"variant": "layernorm_column_owner", "checks": [], "timings": [], "ok": True}
     prev = lib.nk_norm_set_variant(-1)
 
-    def rel(a, b):
-        return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20))
+    rel = _rel
 
     def case(rows, c, pad, with_res):
         buf = torch.randn(rows, c + pad, generator=gen, device=dev) * 1.7 + 0.3
